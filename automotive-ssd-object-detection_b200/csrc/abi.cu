@@ -1,0 +1,24 @@
+// abi.cu -- library-level entry points of libssdhot.so (include/ssdhot.h).
+#include "common.cuh"
+
+namespace ssdhot {
+unsigned long long g_launches = 0ull;
+}
+
+extern "C" int ssdhot_abi_version(void) { return SSDHOT_ABI_VERSION; }
+
+extern "C" unsigned long long ssdhot_launch_count(void) { return ssdhot::g_launches; }
+
+extern "C" const char* ssdhot_status_string(int status) {
+    switch (status) {
+        case SSDHOT_OK: return "ok";
+        case SSDHOT_ERR_NULL: return "a required pointer is NULL";
+        case SSDHOT_ERR_SHAPE: return "a size is outside the supported range";
+        case SSDHOT_ERR_VALUE: return "a scalar argument is invalid";
+        case SSDHOT_ERR_DEVICE: return "not an sm_100 device";
+        case SSDHOT_ERR_ALIGN: return "a pointer is not aligned as documented";
+        default: break;
+    }
+    if (status > 0) return cudaGetErrorString((cudaError_t)status);
+    return "unknown ssdhot status";
+}

@@ -1,0 +1,74 @@
+// common.cuh -- shared device helpers for libssdhot (sm_100a only).
+//
+// Arithmetic rule of the whole library: every +,-,*,/ of the reference is a separately rounded
+// fp32 ATen op, so the kernels spell each one with the __f*_rn intrinsics, which nvcc never
+// contracts into FMA.  Transcendentals (atanf, expf, logf) are the CUDA libdevice ones, i.e.
+// the same functions eager torch-CUDA kernels call.
+#pragma once
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdint.h>
+
+#include "../../include/ssdhot.h"
+
+namespace cg = cooperative_groups;
+
+namespace ssdhot {
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libssdhot is written for sm_100a (B200) only"
+#endif
+
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// Order-preserving map fp32 -> u32 (larger float <=> larger integer); every NaN maps to the top.
+__device__ __forceinline__ unsigned ord_encode(float v) {
+    unsigned u = __float_as_uint(v);
+    u ^= (u & 0x80000000u) ? 0xffffffffu : 0x80000000u;
+    return (v != v) ? 0xffffffffu : u;
+}
+__device__ __forceinline__ float ord_decode(unsigned u) {
+    u ^= (u & 0x80000000u) ? 0x80000000u : 0xffffffffu;
+    return __uint_as_float(u);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(FULL, v); }
+
+// Block-wide sums in a fixed (deterministic) order.  `scratch` holds >= 32 elements; the result
+// is returned to every thread.  Contains two __syncthreads().
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    T total = T(0);
+    for (int w = 0; w < nwarp; ++w) total += scratch[w];
+    return total;
+}
+
+// 128-bit read-only loads.
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+
+extern unsigned long long g_launches;   // host-side counter (abi.cu)
+
+}  // namespace ssdhot
+
+#define SSDHOT_CHECK_LAUNCH()                              \
+    do {                                                   \
+        ++ssdhot::g_launches;                              \
+        cudaError_t e__ = cudaGetLastError();              \
+        if (e__ != cudaSuccess) return (int)e__;           \
+    } while (0)

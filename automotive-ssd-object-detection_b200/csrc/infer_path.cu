@@ -1,0 +1,514 @@
+// infer_path.cu -- decode, score threshold, ranking and greedy DIoU/CIoU NMS
+// (SURVEY.md section 8a rows a6-a8).
+//
+// Unit of work = one (image, foreground class) pair (or one image when class-agnostic): one CTA.
+// The unit's scores live in shared memory as a dense array of order-preserving keys indexed by
+// candidate id (0 = not a candidate), so thresholding needs no compaction and ties are ordered
+// by candidate id for free.  Candidates are consumed best-first in chunks: a 4-pass radix select
+// pulls the next CHUNK highest keys, a bitonic network sorts them, their boxes are decoded, and
+// greedy NMS walks the chunk in tiles of 64 -- every (kept box | earlier tile member) x (tile
+// member) predicate is evaluated in parallel into 64-bit suppression masks (ballot), then one
+// thread resolves the tile serially with bit operations.  The walk stops as soon as max_keep
+// boxes survive, which is lossless for the reference's post-NMS `keep[:max_per_img]`
+// (SSD_from_scratch.py:465) because survivors are produced in score order.
+#include "boxmath.cuh"
+
+namespace ssdhot {
+
+constexpr int UT = 512;        // threads per unit CTA
+constexpr int UW = UT / 32;    // warps
+constexpr int CHUNK = 512;     // candidates ranked per round
+constexpr int TILE = 64;
+
+struct UnitShared {
+    unsigned hist[256];
+    unsigned long long rowmask[TILE];   // bit j of rowmask[i]: tile member i suppresses tile member j (j > i)
+    unsigned long long supp;            // tile members suppressed by an earlier kept box
+    unsigned long long keepbits;
+    unsigned sel_prefix, sel_need, sel_eq;
+    int counter;                        // gather cursor
+    int iscratch[32];
+};
+
+// ---- ranking helpers ---------------------------------------------------------------------------
+
+// Radix select over the non-zero entries of dense[0..n): the K-th largest key.  Returns the key,
+// how many entries equal to it are needed (`need`) and how many exist (`eq`).
+__device__ __forceinline__ void select_kth(const unsigned* dense, int n, unsigned K, UnitShared& us,
+                                           unsigned& thr, unsigned& need, unsigned& eq) {
+    const int tid = threadIdx.x;
+    unsigned prefix = 0u, remaining = K, count_eq = 0u;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (int i = tid; i < 256; i += UT) us.hist[i] = 0u;
+        __syncthreads();
+        for (int i = tid; i < n; i += UT) {
+            const unsigned k = dense[i];
+            if (k != 0u && (k & himask) == prefix) atomicAdd(&us.hist[(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            unsigned mine = 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mine += us.hist[255 - (tid * 8 + j)];
+            unsigned incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(FULL, incl, o);
+                if (tid >= o) incl += y;
+            }
+            const unsigned excl = incl - mine;
+            if (excl < remaining && remaining <= incl) {
+                unsigned run = excl;
+                for (int j = 0; j < 8; ++j) {
+                    const int bin = 255 - (tid * 8 + j);
+                    const unsigned c = us.hist[bin];
+                    if (run + c >= remaining) { us.sel_prefix = (unsigned)bin; us.sel_need = remaining - run; us.sel_eq = c; break; }
+                    run += c;
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= us.sel_prefix << shift;
+        remaining = us.sel_need;
+        count_eq = us.sel_eq;
+        __syncthreads();
+    }
+    thr = prefix; need = remaining; eq = count_eq;
+}
+
+// In-place bitonic sort (descending) of n_pad (power of two <= CHUNK) 64-bit keys in shared memory.
+__device__ __forceinline__ void bitonic_desc(unsigned long long* keys, int n_pad) {
+    const int tid = threadIdx.x;
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            if (tid < n_pad) {
+                const int partner = tid ^ j;
+                if (partner > tid) {
+                    const unsigned long long a = keys[tid], b = keys[partner];
+                    const bool desc = (tid & k) == 0;
+                    if (desc ? (a < b) : (a > b)) { keys[tid] = b; keys[partner] = a; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---- the unit ------------------------------------------------------------------------------------
+// dense:   [n] keys (0 = absent), consumed (zeroed) as candidates are ranked
+// Fetch:   BoxC operator()(unsigned idx)      -- pixel box + constants of candidate idx
+// Emit:    void operator()(int pos, unsigned long long key, unsigned idx, const BoxC&)
+// kept:    storage for the surviving boxes (shared or global memory), capacity max_keep
+// returns the number of survivors (valid in every thread)
+template <int METRIC, typename Fetch, typename Emit>
+__device__ int nms_unit(unsigned* dense, int n, int n_cand, unsigned long long* ckey, BoxC* cbox, BoxC* kept,
+                        int max_keep, float thr, UnitShared& us, Fetch fetch, Emit emit) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int kept_n = 0;
+    int remaining = n_cand;
+    while (remaining > 0 && kept_n < max_keep) {
+        const int K = remaining < CHUNK ? remaining : CHUNK;
+        // ---- pull the K best remaining candidates ------------------------------------------
+        unsigned tkey = 1u, need = 0u, eq = 0u;
+        const bool all = remaining <= CHUNK;
+        if (!all) select_kth(dense, n, (unsigned)K, us, tkey, need, eq);
+        if (tid == 0) us.counter = 0;
+        __syncthreads();
+        if (all || need == eq) {
+            for (int i = tid; i < n; i += UT) {
+                const unsigned k = dense[i];
+                if (k != 0u && k >= tkey) {
+                    const int pos = atomicAdd(&us.counter, 1);
+                    ckey[pos] = ((unsigned long long)k << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+                    dense[i] = 0u;
+                }
+            }
+        } else {
+            // more entries equal to the threshold key than needed: take the lowest ids first
+            int taken_eq = 0;
+            for (int base = 0; base < n; base += UT) {
+                const int i = base + tid;
+                const unsigned k = i < n ? dense[i] : 0u;
+                const bool is_eq = k != 0u && k == tkey;
+                const unsigned bal = __ballot_sync(FULL, is_eq);
+                __syncthreads();
+                if (lane == 0) us.iscratch[warp] = __popc(bal);
+                __syncthreads();
+                int before = taken_eq, tot = 0;
+                for (int w = 0; w < UW; ++w) { if (w < warp) before += us.iscratch[w]; tot += us.iscratch[w]; }
+                const int my_rank = before + __popc(bal & ((1u << lane) - 1u));
+                if (k != 0u && (k > tkey || (is_eq && (unsigned)my_rank < need))) {
+                    const int pos = atomicAdd(&us.counter, 1);
+                    ckey[pos] = ((unsigned long long)k << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+                    dense[i] = 0u;
+                }
+                taken_eq += tot;
+            }
+        }
+        int n_pad = 64;
+        while (n_pad < K) n_pad <<= 1;
+        __syncthreads();
+        for (int i = K + tid; i < n_pad; i += UT) ckey[i] = 0ull;
+        bitonic_desc(ckey, n_pad);
+        for (int i = tid; i < K; i += UT) cbox[i] = fetch(0xffffffffu - (unsigned)(ckey[i] & 0xffffffffull));
+        __syncthreads();
+
+        // ---- greedy NMS over the sorted chunk, tile by tile ----------------------------------
+        for (int t0 = 0; t0 < K && kept_n < max_keep; t0 += TILE) {
+            const int m = (K - t0) < TILE ? (K - t0) : TILE;
+            if (tid < TILE) us.rowmask[tid] = 0ull;
+            if (tid == 0) us.supp = 0ull;
+            __syncthreads();
+            const BoxC c_lo = cbox[t0 + (lane < m ? lane : 0)];
+            const BoxC c_hi = cbox[t0 + (lane + 32 < m ? lane + 32 : 0)];
+            const int n_sup = kept_n + m;
+            for (int s = warp; s < n_sup; s += UW) {
+                const bool from_kept = s < kept_n;
+                const int si = s - kept_n;                     // tile index of the suppressor (if not kept)
+                const BoxC S = from_kept ? kept[s] : cbox[t0 + si];
+                const bool v_lo = lane < m && (from_kept || si < lane);
+                const bool v_hi = lane + 32 < m && (from_kept || si < lane + 32);
+                // a box survives a suppressor iff metric <= thr; NaN therefore suppresses (SFS:690)
+                const bool s_lo = v_lo && !(pair_metric<METRIC>(S, c_lo) <= thr);
+                const bool s_hi = v_hi && !(pair_metric<METRIC>(S, c_hi) <= thr);
+                const unsigned b_lo = __ballot_sync(FULL, s_lo), b_hi = __ballot_sync(FULL, s_hi);
+                if (lane == 0) {
+                    const unsigned long long bits = ((unsigned long long)b_hi << 32) | b_lo;
+                    if (from_kept) { if (bits) atomicOr(&us.supp, bits); }
+                    else us.rowmask[si] = bits;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
+                unsigned long long alive = ~us.supp & valid, keepb = 0ull;
+                int cnt = kept_n;
+                while (alive) {
+                    const int i = __ffsll((long long)alive) - 1;
+                    keepb |= 1ull << i;
+                    alive &= ~us.rowmask[i];
+                    alive &= ~(1ull << i);
+                    if (++cnt >= max_keep) break;
+                }
+                us.keepbits = keepb;
+            }
+            __syncthreads();
+            const unsigned long long keepb = us.keepbits;
+            if (tid < m && ((keepb >> tid) & 1ull)) {
+                const int pos = kept_n + __popcll(keepb & ((1ull << tid) - 1ull));
+                const BoxC bx = cbox[t0 + tid];
+                kept[pos] = bx;
+                const unsigned long long key = ckey[t0 + tid];
+                emit(pos, key, 0xffffffffu - (unsigned)(key & 0xffffffffull), bx);
+            }
+            kept_n += __popcll(keepb);
+            __syncthreads();
+        }
+        remaining -= K;
+    }
+    return kept_n;
+}
+
+// ---- predict -------------------------------------------------------------------------------------
+struct PredictParams {
+    const float* pri; int P; const float* loc_all; const float* conf_all; int B, C;
+    float score_thresh, nms_thresh; int max_keep; float vc, vs, img_w, img_h;
+    unsigned long long* list_key;   // [B*units][max_keep]
+    float4* list_box;               // [B*units][max_keep]
+    int* list_count;                // [B*units]
+};
+
+// foreground softmax scores of one row in eager torch-CUDA order (see boxmath.cuh / train_path.cu)
+template <int CT>
+__device__ __forceinline__ void row_softmax_stats(const float* __restrict__ row, int C, float& mx, float& sum) {
+    if (CT == 6) {
+        const float2 a = ldg2(row), b = ldg2(row + 2), c = ldg2(row + 4);
+        mx = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y)), fmaxf(c.x, c.y));
+        const float e0 = expf(fsub(a.x, mx)), e1 = expf(fsub(a.y, mx)), e2 = expf(fsub(b.x, mx));
+        const float e3 = expf(fsub(b.y, mx)), e4 = expf(fsub(c.x, mx)), e5 = expf(fsub(c.y, mx));
+        sum = fadd(fadd(fadd(e0, e4), e2), fadd(fadd(e1, e5), e3));
+    } else {
+        int lanes = 1;
+        while (lanes < C && lanes < 32) lanes <<= 1;
+        mx = __ldg(row);
+        for (int i = 1; i < C; ++i) mx = fmaxf(mx, __ldg(row + i));
+        float part[32];
+        for (int l = 0; l < 32; ++l) part[l] = 0.0f;
+        for (int i = 0; i < C; ++i) {
+            const int l = i & (lanes - 1);
+            part[l] = fadd(part[l], expf(fsub(__ldg(row + i), mx)));
+        }
+        for (int off = lanes >> 1; off > 0; off >>= 1)
+            for (int l = 0; l < off; ++l) part[l] = fadd(part[l], part[l + off]);
+        sum = part[0];
+    }
+}
+
+template <int METRIC, bool AGN, int CT>
+__global__ void __launch_bounds__(UT) predict_unit_kernel(const PredictParams prm) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ UnitShared us;
+    const int tid = threadIdx.x;
+    const int n_fg = prm.C - 1;
+    const int units = AGN ? 1 : n_fg;
+    const int b = blockIdx.x / units, c = blockIdx.x % units;
+    const int P = prm.P;
+    const int n = AGN ? P * n_fg : P;
+
+    BoxC* kept = reinterpret_cast<BoxC*>(dyn);
+    BoxC* cbox = kept + prm.max_keep;
+    unsigned long long* ckey = reinterpret_cast<unsigned long long*>(cbox + CHUNK);
+    unsigned* dense = reinterpret_cast<unsigned*>(ckey + CHUNK);
+
+    // ---- scores -> dense keys ----------------------------------------------------------------
+    int mine = 0;
+    const float* conf_b = prm.conf_all + (long long)b * P * prm.C;
+    for (int p = tid; p < P; p += UT) {
+        const float* row = conf_b + (long long)p * prm.C;
+        float mx, sum;
+        row_softmax_stats<CT>(row, prm.C, mx, sum);
+        if (AGN) {
+            for (int k = 0; k < n_fg; ++k) {
+                const float s = fdiv(expf(fsub(__ldg(row + k + 1), mx)), sum);
+                const bool on = s > prm.score_thresh;
+                dense[p * n_fg + k] = on ? ord_encode(s) : 0u;
+                mine += on ? 1 : 0;
+            }
+        } else {
+            const float s = fdiv(expf(fsub(__ldg(row + c + 1), mx)), sum);
+            const bool on = s > prm.score_thresh;
+            dense[p] = on ? ord_encode(s) : 0u;
+            mine += on ? 1 : 0;
+        }
+    }
+    const int n_cand = block_sum<int>(mine, us.iscratch);
+    __syncthreads();
+
+    const float* loc_b = prm.loc_all + 4ll * b * P;
+    const bool want_atan = METRIC == SSDHOT_METRIC_CIOU;
+    auto fetch = [&](unsigned idx) -> BoxC {
+        const unsigned p = AGN ? idx / (unsigned)n_fg : idx;
+        const float4 box = decode_box(ldg4(loc_b + 4ll * p), ldg4(prm.pri + 4ll * p), prm.vc, prm.vs);
+        const float4 px = to_pixel_xyxy(box, prm.img_w, prm.img_h);
+        return box_consts(px.x, px.y, px.z, px.w, want_atan);
+    };
+    unsigned long long* out_key = prm.list_key + (long long)blockIdx.x * prm.max_keep;
+    float4* out_box = prm.list_box + (long long)blockIdx.x * prm.max_keep;
+    auto emit = [&](int pos, unsigned long long key, unsigned idx, const BoxC& bx) {
+        // re-key by the flat candidate id prior*(C-1)+class so that lists of different classes merge
+        const unsigned flat = AGN ? idx : idx * (unsigned)n_fg + (unsigned)c;
+        out_key[pos] = (key & 0xffffffff00000000ull) | (unsigned long long)(0xffffffffu - flat);
+        out_box[pos] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
+    };
+    const int kept_n = nms_unit<METRIC>(dense, n, n_cand, ckey, cbox, kept, prm.max_keep, prm.nms_thresh, us, fetch, emit);
+    if (tid == 0) prm.list_count[blockIdx.x] = kept_n;
+}
+
+// Merge the per-class survivor lists of one image (each already score-descending) and keep the
+// max_keep best (SSD_from_scratch.py:461-474).  Rank of an element = its position in its own list
+// + the number of strictly larger keys in every other list (keys are unique).
+__global__ void __launch_bounds__(256) merge_lists_kernel(const unsigned long long* __restrict__ list_key,
+                                                          const float4* __restrict__ list_box,
+                                                          const int* __restrict__ list_count, int units, int max_keep, int n_fg,
+                                                          int64_t* __restrict__ out_labels, float* __restrict__ out_scores,
+                                                          float* __restrict__ out_boxes, int32_t* __restrict__ out_cand,
+                                                          int32_t* __restrict__ out_count) {
+    const int b = blockIdx.x;
+    const unsigned long long* keys = list_key + (long long)b * units * max_keep;
+    const float4* boxes = list_box + (long long)b * units * max_keep;
+    const int* counts = list_count + (long long)b * units;
+    int total = 0;
+    for (int u = 0; u < units; ++u) total += counts[u];
+    for (int e = threadIdx.x; e < units * max_keep; e += blockDim.x) {
+        const int u = e / max_keep, i = e % max_keep;
+        if (i >= counts[u]) continue;
+        const unsigned long long key = keys[(long long)u * max_keep + i];
+        int rank = i;
+        for (int v = 0; v < units; ++v) {
+            if (v == u) continue;
+            int lo = 0, hi = counts[v];          // first position whose key is < key
+            const unsigned long long* kv = keys + (long long)v * max_keep;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (kv[mid] > key) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < max_keep) {
+            const long long o = (long long)b * max_keep + rank;
+            const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffull);
+            out_labels[o] = (int64_t)(flat % (unsigned)n_fg);
+            out_scores[o] = ord_decode((unsigned)(key >> 32));
+            reinterpret_cast<float4*>(out_boxes)[o] = boxes[(long long)u * max_keep + i];
+            if (out_cand) out_cand[o] = (int32_t)flat;
+        }
+    }
+    if (threadIdx.x == 0) out_count[b] = total < max_keep ? total : max_keep;
+}
+
+// ---- stand-alone NMS -------------------------------------------------------------------------------
+template <int METRIC>
+__global__ void __launch_bounds__(UT) nms_sets_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                                                      const int32_t* __restrict__ set_offsets, float thr, int max_keep,
+                                                      int64_t* __restrict__ keep, int32_t* __restrict__ keep_count,
+                                                      BoxC* __restrict__ kept_all) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ UnitShared us;
+    const int tid = threadIdx.x;
+    const int begin = set_offsets[blockIdx.x];
+    const int n = set_offsets[blockIdx.x + 1] - begin;
+    BoxC* cbox = reinterpret_cast<BoxC*>(dyn);
+    unsigned long long* ckey = reinterpret_cast<unsigned long long*>(cbox + CHUNK);
+    unsigned* dense = reinterpret_cast<unsigned*>(ckey + CHUNK);
+    for (int i = tid; i < n; i += UT) {
+        const unsigned k = ord_encode(__ldg(scores + begin + i));
+        dense[i] = k == 0u ? 1u : k;
+    }
+    __syncthreads();
+    const bool want_atan = METRIC == SSDHOT_METRIC_CIOU;
+    auto fetch = [&](unsigned idx) -> BoxC {
+        const float4 bx = ldg4(boxes + 4ll * (begin + (long long)idx));
+        return box_consts(bx.x, bx.y, bx.z, bx.w, want_atan);
+    };
+    int64_t* out = keep + begin;
+    auto emit = [&](int pos, unsigned long long, unsigned idx, const BoxC&) { out[pos] = (int64_t)idx; };
+    const int cap = (max_keep > 0 && max_keep < n) ? max_keep : n;
+    const int kept_n = nms_unit<METRIC>(dense, n, n, ckey, cbox, kept_all + begin, cap, thr, us, fetch, emit);
+    if (tid == 0) keep_count[blockIdx.x] = kept_n;
+}
+
+__global__ void decode_kernel(const float* __restrict__ loc, const float* __restrict__ pri, int M, float vc, float vs,
+                              float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    reinterpret_cast<float4*>(out)[i] = decode_box(ldg4(loc + 4ll * i), ldg4(pri + 4ll * i), vc, vs);
+}
+
+constexpr size_t kMaxDynSmem = 227 * 1024 - sizeof(UnitShared) - 1024;
+
+template <typename K>
+static int set_smem(K kern, size_t bytes) {
+    if (bytes > kMaxDynSmem) return SSDHOT_ERR_SHAPE;
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return SSDHOT_OK;
+}
+
+template <int METRIC, bool AGN>
+static int launch_predict(const PredictParams& prm, size_t dyn, int grid, cudaStream_t stream) {
+    int rc;
+    if (prm.C == 6) {
+        rc = set_smem(predict_unit_kernel<METRIC, AGN, 6>, dyn);
+        if (rc) return rc;
+        predict_unit_kernel<METRIC, AGN, 6><<<grid, UT, dyn, stream>>>(prm);
+    } else {
+        rc = set_smem(predict_unit_kernel<METRIC, AGN, 0>, dyn);
+        if (rc) return rc;
+        predict_unit_kernel<METRIC, AGN, 0><<<grid, UT, dyn, stream>>>(prm);
+    }
+    SSDHOT_CHECK_LAUNCH();
+    return SSDHOT_OK;
+}
+
+}  // namespace ssdhot
+
+using namespace ssdhot;
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" int ssdhot_decode(const float* loc, const float* priors_cxcywh, int M, float var_center, float var_size,
+                             float* out, ssdhot_stream_t stream) {
+    if (!loc || !priors_cxcywh || !out) return SSDHOT_ERR_NULL;
+    if (M < 0) return SSDHOT_ERR_SHAPE;
+    if (!al16(loc) || !al16(priors_cxcywh) || !al16(out)) return SSDHOT_ERR_ALIGN;
+    if (M == 0) return SSDHOT_OK;
+    decode_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(loc, priors_cxcywh, M, var_center, var_size, out);
+    SSDHOT_CHECK_LAUNCH();
+    return SSDHOT_OK;
+}
+
+extern "C" unsigned long long ssdhot_nms_workspace_bytes(long long total_boxes) {
+    return total_boxes <= 0 ? 64ull : (unsigned long long)total_boxes * sizeof(BoxC) + 64ull;
+}
+
+extern "C" int ssdhot_nms(const float* boxes, const float* scores, const int32_t* set_offsets, int n_sets,
+                          long long total_boxes, int max_set_size, float thresh, int metric, int max_keep,
+                          int64_t* keep, int32_t* keep_count, void* work, ssdhot_stream_t stream) {
+    if (!set_offsets || !keep_count) return SSDHOT_ERR_NULL;
+    if (n_sets <= 0 || total_boxes < 0 || max_set_size < 0) return SSDHOT_ERR_SHAPE;
+    if (total_boxes > 0 && (!boxes || !scores || !keep || !work)) return SSDHOT_ERR_NULL;
+    if (!al16(boxes) || !al16(work)) return SSDHOT_ERR_ALIGN;
+    const size_t dyn = (size_t)CHUNK * (sizeof(BoxC) + 8) + (size_t)(max_set_size > 0 ? max_set_size : 1) * 4;
+    BoxC* kept_all = reinterpret_cast<BoxC*>(work);
+    int rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (metric) {
+        case SSDHOT_METRIC_DIOU:
+            if ((rc = set_smem(nms_sets_kernel<SSDHOT_METRIC_DIOU>, dyn))) return rc;
+            nms_sets_kernel<SSDHOT_METRIC_DIOU><<<n_sets, UT, dyn, s>>>(boxes, scores, set_offsets, thresh, max_keep, keep, keep_count, kept_all);
+            break;
+        case SSDHOT_METRIC_CIOU:
+            if ((rc = set_smem(nms_sets_kernel<SSDHOT_METRIC_CIOU>, dyn))) return rc;
+            nms_sets_kernel<SSDHOT_METRIC_CIOU><<<n_sets, UT, dyn, s>>>(boxes, scores, set_offsets, thresh, max_keep, keep, keep_count, kept_all);
+            break;
+        case SSDHOT_METRIC_IOU:
+            if ((rc = set_smem(nms_sets_kernel<SSDHOT_METRIC_IOU>, dyn))) return rc;
+            nms_sets_kernel<SSDHOT_METRIC_IOU><<<n_sets, UT, dyn, s>>>(boxes, scores, set_offsets, thresh, max_keep, keep, keep_count, kept_all);
+            break;
+        default: return SSDHOT_ERR_VALUE;
+    }
+    SSDHOT_CHECK_LAUNCH();
+    return SSDHOT_OK;
+}
+
+extern "C" unsigned long long ssdhot_predict_workspace_bytes(int B, int C, int max_per_img) {
+    if (B <= 0 || C < 2 || max_per_img <= 0) return 64ull;
+    const unsigned long long lists = (unsigned long long)B * (C - 1);
+    return lists * max_per_img * (8ull + 16ull) + lists * 4ull + 256ull;
+}
+
+extern "C" int ssdhot_predict(const float* priors_cxcywh, int P, const float* loc_all, const float* conf_all,
+                              int B, int C, float score_thresh, float nms_thresh, int max_per_img,
+                              int class_agnostic, int metric, float var_center, float var_size,
+                              float img_w, float img_h,
+                              int64_t* out_labels, float* out_scores, float* out_boxes, int32_t* out_cand,
+                              int32_t* out_count, void* work, ssdhot_stream_t stream) {
+    if (!priors_cxcywh || !loc_all || !conf_all || !out_labels || !out_scores || !out_boxes || !out_count || !work)
+        return SSDHOT_ERR_NULL;
+    if (P <= 0 || B <= 0 || C < 2 || C > SSDHOT_MAX_CLASSES || max_per_img <= 0) return SSDHOT_ERR_SHAPE;
+    // same validation as SSD_from_scratch.py:369-373
+    if (!(score_thresh >= 0.0f && score_thresh < 1.0f) || !(nms_thresh > 0.0f && nms_thresh < 1.0f)) return SSDHOT_ERR_VALUE;
+    if (metric != SSDHOT_METRIC_DIOU && metric != SSDHOT_METRIC_CIOU && metric != SSDHOT_METRIC_IOU) return SSDHOT_ERR_VALUE;
+    if (!al16(priors_cxcywh) || !al16(loc_all) || !al16(out_boxes) || !al16(work) ||
+        (reinterpret_cast<uintptr_t>(conf_all) & 7u)) return SSDHOT_ERR_ALIGN;
+    const int units = class_agnostic ? 1 : C - 1;
+    const long long lists = (long long)B * units;
+    PredictParams prm = {};
+    prm.pri = priors_cxcywh; prm.P = P; prm.loc_all = loc_all; prm.conf_all = conf_all; prm.B = B; prm.C = C;
+    prm.score_thresh = score_thresh; prm.nms_thresh = nms_thresh; prm.max_keep = max_per_img;
+    prm.vc = var_center; prm.vs = var_size; prm.img_w = img_w; prm.img_h = img_h;
+    unsigned char* w = reinterpret_cast<unsigned char*>(work);
+    prm.list_box = reinterpret_cast<float4*>(w); w += (size_t)lists * max_per_img * 16;
+    prm.list_key = reinterpret_cast<unsigned long long*>(w); w += (size_t)lists * max_per_img * 8;
+    prm.list_count = reinterpret_cast<int*>(w);
+    const long long n = class_agnostic ? (long long)P * (C - 1) : P;
+    const size_t dyn = (size_t)max_per_img * sizeof(BoxC) + (size_t)CHUNK * (sizeof(BoxC) + 8) + (size_t)n * 4;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+#define SSDHOT_DISPATCH(M)                                                                   \
+    rc = class_agnostic ? launch_predict<M, true>(prm, dyn, (int)lists, s) : launch_predict<M, false>(prm, dyn, (int)lists, s)
+    if (metric == SSDHOT_METRIC_DIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_DIOU); }
+    else if (metric == SSDHOT_METRIC_CIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_CIOU); }
+    else { SSDHOT_DISPATCH(SSDHOT_METRIC_IOU); }
+#undef SSDHOT_DISPATCH
+    if (rc) return rc;
+    merge_lists_kernel<<<B, 256, 0, s>>>(prm.list_key, prm.list_box, prm.list_count, units, max_per_img, C - 1,
+                                         out_labels, out_scores, out_boxes, out_cand, out_count);
+    SSDHOT_CHECK_LAUNCH();
+    return SSDHOT_OK;
+}

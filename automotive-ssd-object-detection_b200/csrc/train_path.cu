@@ -1,0 +1,737 @@
+// train_path.cu -- match + encode + mined multibox loss.
+//
+// Decomposition: one thread-block CLUSTER per image (up to 8 CTAs of 256 threads), each CTA owns
+// a contiguous slice of the priors and each thread keeps KP of them in registers.  The image's
+// ground truth lives in shared memory with its per-box constants.  Column arg-max (best prior per
+// ground truth), the positive count and the hard-negative radix select are combined across the
+// cluster through distributed shared memory; nothing of shape [B,P] touches HBM unless the
+// caller asks for it.
+#include "boxmath.cuh"
+
+namespace ssdhot {
+
+constexpr int TT = 256;          // threads per CTA
+constexpr int KP = 5;            // priors per thread
+constexpr int SLOTS = TT * KP;   // prior slots per CTA
+constexpr int MAX_CS = 8;        // portable cluster size
+
+enum { MODE_MATCH = 0, MODE_LOSS = 1, MODE_FUSED = 2 };
+
+struct TrainParams {
+    // priors
+    const float* pri; const float* pri_xyxy; const float* pri_aux; int P;
+    // ground truth
+    const float* gt_boxes; const int64_t* gt_labels; const int32_t* gt_offsets;
+    int B, max_gt; float norm_w, norm_h;
+    float thresh, inv_vc, inv_vs;
+    // head outputs
+    const float* loc_all; const float* conf_all; int C;
+    double ratio;
+    // given targets (MODE_LOSS)
+    const int64_t* in_cls; const uint8_t* in_pos;
+    // match outputs
+    float* loc_t; int loc_pos_only; int64_t* cls_t; uint8_t* pos_mask; int32_t* matched32;
+    float* matched_box; int32_t* n_pos;
+    // loss outputs
+    double* cta_part;      // [B*CS][2]  (smooth-L1, CE) partial sums per CTA
+    int8_t* sel_cls; int16_t* matched16;
+    int32_t* flags;
+};
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory carve-up (dynamic): ground-truth records, column keys, champions, forced table
+// ---------------------------------------------------------------------------------------------
+struct Smem {
+    float4* gt_a;              // [G] x1 y1 x2 y2 (normalised)
+    float4* gt_b;              // [G] area xc yc atan
+    int* gt_label;             // [G]
+    unsigned long long* col;   // [G] packed (ord(ciou) << 32 | ~prior) of this CTA's best prior per GT
+    unsigned* champ;           // [G] cluster-wide best prior per GT
+    int* forced;               // [SLOTS] lowest GT index that forces this prior, or INT_MAX
+};
+
+__host__ __device__ inline size_t smem_bytes(int g_cap) {
+    return (size_t)g_cap * (16 + 16 + 4 + 8 + 4) + (size_t)SLOTS * 4 + 64;
+}
+
+__device__ __forceinline__ Smem carve(unsigned char* base, int g_cap) {
+    Smem s;
+    s.gt_a = reinterpret_cast<float4*>(base); base += (size_t)g_cap * 16;
+    s.gt_b = reinterpret_cast<float4*>(base); base += (size_t)g_cap * 16;
+    s.col = reinterpret_cast<unsigned long long*>(base); base += (size_t)g_cap * 8;
+    s.gt_label = reinterpret_cast<int*>(base); base += (size_t)g_cap * 4;
+    s.champ = reinterpret_cast<unsigned*>(base); base += (size_t)g_cap * 4;
+    s.forced = reinterpret_cast<int*>(base);
+    return s;
+}
+
+struct Static {                 // static shared state used by the cluster exchanges
+    unsigned hist[2][256];
+    unsigned total[256];
+    double dscratch[32];
+    int iscratch[32];
+    int npos_cta;               // positives in this CTA (read remotely)
+    int ties_cta;               // elements equal to the threshold in this CTA (read remotely)
+    int first_nan;              // lowest GT index whose CIoU column is NaN, or INT_MAX
+    unsigned sel_digit, sel_need;
+};
+
+// ---------------------------------------------------------------------------------------------
+// per-row softmax statistics in eager torch-CUDA order: returns (max, log(sum exp(x - max)))
+// ---------------------------------------------------------------------------------------------
+template <int CT>
+__device__ __forceinline__ void row_lse(const float* __restrict__ row, int C, float& mx, float& lg) {
+    if (CT == 6) {
+        const float2 a = ldg2(row), b = ldg2(row + 2), c = ldg2(row + 4);
+        mx = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y)), fmaxf(c.x, c.y));
+        const float e0 = expf(fsub(a.x, mx)), e1 = expf(fsub(a.y, mx)), e2 = expf(fsub(b.x, mx));
+        const float e3 = expf(fsub(b.y, mx)), e4 = expf(fsub(c.x, mx)), e5 = expf(fsub(c.y, mx));
+        const float s = fadd(fadd(fadd(e0, e4), e2), fadd(fadd(e1, e5), e3));   // 8-lane butterfly
+        lg = logf(s);
+    } else {
+        // generic C: lane l of a 32-wide (or next_pow2(C)-wide) warp sums elements l, l+W, ...
+        int lanes = 1;
+        while (lanes < C && lanes < 32) lanes <<= 1;
+        mx = __ldg(row);
+        for (int i = 1; i < C; ++i) mx = fmaxf(mx, __ldg(row + i));
+        float part[32];
+        for (int l = 0; l < 32; ++l) part[l] = 0.0f;
+        for (int i = 0; i < C; ++i) {
+            const int l = i & (lanes - 1);
+            part[l] = fadd(part[l], expf(fsub(__ldg(row + i), mx)));
+        }
+        for (int off = lanes >> 1; off > 0; off >>= 1)
+            for (int l = 0; l < off; ++l) part[l] = fadd(part[l], part[l + off]);
+        lg = logf(part[0]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int MODE, int CT>
+__global__ void __launch_bounds__(TT) train_kernel(const TrainParams prm) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ Static st;
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cs = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.x / cs;
+    const int tid = threadIdx.x;
+    const int P = prm.P;
+    const int chunk = (P + cs - 1) / cs;
+    const int p0 = rank * chunk;
+    const int p1 = min(P, p0 + chunk);
+
+    int g_begin = 0, G = 0;
+    if (MODE != MODE_LOSS) {
+        g_begin = prm.gt_offsets[b];
+        G = prm.gt_offsets[b + 1] - g_begin;
+        if (G > prm.max_gt) {
+            if (tid == 0 && rank == 0 && prm.flags) atomicOr(prm.flags, 1);
+            G = prm.max_gt;
+        }
+    }
+    Smem sm = carve(dyn, prm.max_gt > 0 ? prm.max_gt : 1);
+
+    // ---- per-thread prior state -------------------------------------------------------------
+    int best_g[KP];
+    float best_v[KP];
+    bool pos[KP];
+    int cls[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) { best_g[k] = 0; best_v[k] = -INFINITY; pos[k] = false; cls[k] = 0; }
+
+    if (MODE != MODE_LOSS) {
+        // ---- stage ground truth ------------------------------------------------------------
+        if (tid == 0) st.first_nan = INT_MAX;
+        for (int i = tid; i < SLOTS; i += TT) sm.forced[i] = INT_MAX;
+        __syncthreads();
+        for (int g = tid; g < G; g += TT) {
+            const float4 px = ldg4(prm.gt_boxes + 4ll * (g_begin + g));
+            const BoxC c = box_consts(fdiv(px.x, prm.norm_w), fdiv(px.y, prm.norm_h),
+                                      fdiv(px.z, prm.norm_w), fdiv(px.w, prm.norm_h), true);
+            sm.gt_a[g] = make_float4(c.x1, c.y1, c.x2, c.y2);
+            sm.gt_b[g] = make_float4(c.area, c.xc, c.yc, c.at);
+            sm.gt_label[g] = (int)prm.gt_labels[g_begin + g];
+            sm.col[g] = 0ull;
+            if (c.at != c.at) atomicMin(&st.first_nan, g);
+        }
+        __syncthreads();
+
+        // ---- CIoU sweep: row arg-max in registers, column arg-max per warp -> shared ---------
+        BoxC pr[KP];
+        bool valid[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const int p = p0 + k * TT + tid;
+            valid[k] = p < p1;
+            const int q = valid[k] ? p : p0;
+            const float4 a = ldg4(prm.pri_xyxy + 4ll * q), x = ldg4(prm.pri_aux + 4ll * q);
+            pr[k].x1 = a.x; pr[k].y1 = a.y; pr[k].x2 = a.z; pr[k].y2 = a.w;
+            pr[k].area = x.x; pr[k].xc = x.y; pr[k].yc = x.z; pr[k].at = x.w;
+        }
+        const int lane = tid & 31;
+        for (int g = 0; g < G; ++g) {
+            const float4 ga = sm.gt_a[g], gb = sm.gt_b[g];
+            if (gb.w != gb.w) continue;            // NaN column (degenerate box): handled below
+            BoxC gc;
+            gc.x1 = ga.x; gc.y1 = ga.y; gc.x2 = ga.z; gc.y2 = ga.w;
+            gc.area = gb.x; gc.xc = gb.y; gc.yc = gb.z; gc.at = gb.w;
+            float cbest = -INFINITY;
+            unsigned cidx = 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const float v = pair_ciou(pr[k], gc);
+                if (v > best_v[k]) { best_v[k] = v; best_g[k] = g; }
+                if (valid[k] && v > cbest) { cbest = v; cidx = (unsigned)(p0 + k * TT + tid); }
+            }
+            const unsigned enc = (cidx == 0xffffffffu) ? 0u : ord_encode(cbest);
+            const unsigned wmax = __reduce_max_sync(FULL, enc);
+            const unsigned wmin = __reduce_min_sync(FULL, enc == wmax ? cidx : 0xffffffffu);
+            if (lane == 0 && wmin != 0xffffffffu) {
+                const unsigned long long key = ((unsigned long long)wmax << 32) | (unsigned long long)(0xffffffffu - wmin);
+                if (key > sm.col[g]) atomicMax(&sm.col[g], key);
+            }
+        }
+        // ---- cluster-wide champions --------------------------------------------------------
+        cluster.sync();
+        for (int g = tid; g < G; g += TT) {
+            unsigned long long key = 0ull;
+            for (int r = 0; r < cs; ++r) {
+                const unsigned long long* remote = cluster.map_shared_rank(sm.col, r);
+                const unsigned long long kr = remote[g];
+                key = kr > key ? kr : key;
+            }
+            const float4 gb = sm.gt_b[g];
+            const unsigned champ = (gb.w != gb.w) ? 0u : (0xffffffffu - (unsigned)(key & 0xffffffffull));
+            sm.champ[g] = champ;
+            if ((int)champ >= p0 && (int)champ < p1) atomicMin(&sm.forced[(int)champ - p0], g);
+        }
+        __syncthreads();
+        const int first_nan = st.first_nan;
+
+        // ---- resolve rows, write targets ----------------------------------------------------
+        int my_pos = 0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const int p = p0 + k * TT + tid;
+            if (!valid[k]) continue;
+            if (G > 0) {
+                const int f = sm.forced[p - p0];
+                if (first_nan != INT_MAX && p != 0) { best_g[k] = first_nan; best_v[k] = __int_as_float(0x7fc00000); }
+                else if (f != INT_MAX) { best_g[k] = f; best_v[k] = 2.0f; }
+                pos[k] = best_v[k] >= prm.thresh;
+                cls[k] = pos[k] ? sm.gt_label[best_g[k]] + 1 : 0;
+            }
+            my_pos += pos[k] ? 1 : 0;
+            const long long row = (long long)b * P + p;
+            if (MODE == MODE_MATCH) {
+                if (prm.pos_mask) prm.pos_mask[row] = pos[k] ? 1 : 0;
+                if (prm.cls_t) prm.cls_t[row] = (int64_t)cls[k];
+                if (prm.matched32) prm.matched32[row] = best_g[k];
+                const bool want_loc = prm.loc_t && (!prm.loc_pos_only || pos[k]);
+                if (want_loc || prm.matched_box) {
+                    float4 gbox = make_float4(0.f, 0.f, 0.f, 0.f), t = gbox;
+                    if (G > 0) {
+                        const float4 ga = sm.gt_a[best_g[k]], gb = sm.gt_b[best_g[k]];
+                        gbox = make_float4(gb.y, gb.z, fsub(ga.z, ga.x), fsub(ga.w, ga.y));
+                        t = encode_offsets(gbox, ldg4(prm.pri + 4ll * p), prm.inv_vc, prm.inv_vs);
+                    }
+                    if (want_loc) reinterpret_cast<float4*>(prm.loc_t)[row] = t;
+                    if (prm.matched_box) reinterpret_cast<float4*>(prm.matched_box)[row] = gbox;
+                }
+            }
+        }
+        const int cta_pos = block_sum<int>(my_pos, st.iscratch);
+        if (tid == 0) st.npos_cta = cta_pos;
+    } else {
+        // ---- MODE_LOSS: targets are given --------------------------------------------------
+        int my_pos = 0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const int p = p0 + k * TT + tid;
+            if (p < p1) {
+                const long long row = (long long)b * P + p;
+                pos[k] = prm.in_pos[row] != 0;
+                cls[k] = (int)prm.in_cls[row];
+                my_pos += pos[k] ? 1 : 0;
+            }
+        }
+        const int cta_pos = block_sum<int>(my_pos, st.iscratch);
+        if (tid == 0) st.npos_cta = cta_pos;
+    }
+
+    // ---- positives of the whole image ------------------------------------------------------
+    cluster.sync();
+    int n_pos_img = 0;
+    for (int r = 0; r < cs; ++r) n_pos_img += cluster.map_shared_rank(&st, r)->npos_cta;
+    if (rank == 0 && tid == 0 && prm.n_pos) prm.n_pos[b] = n_pos_img;
+    if (MODE == MODE_MATCH) {
+        cluster.sync();      // keep this CTA's shared memory alive until every peer has read it
+        return;
+    }
+
+    // ---- per-prior losses -------------------------------------------------------------------
+    float ce[KP];
+    unsigned key[KP];        // CE bits of negatives (CE >= 0, so the bit pattern orders them); 0 otherwise
+    bool neg[KP];
+    double acc_loc = 0.0, acc_ce = 0.0;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const int p = p0 + k * TT + tid;
+        ce[k] = 0.0f; key[k] = 0u; neg[k] = false;
+        if (p >= p1) continue;
+        const long long row = (long long)b * P + p;
+        float mx, lg;
+        row_lse<CT>(prm.conf_all + row * prm.C, prm.C, mx, lg);
+        const float xc = __ldg(prm.conf_all + row * prm.C + cls[k]);
+        // -log_softmax[c] = -((x_c - max) - log(sum))  (ATen PersistentSoftmax.cuh, nll_loss)
+        ce[k] = -fsub(fsub(xc, mx), lg);
+        if (pos[k]) {
+            acc_ce += (double)ce[k];
+            if (MODE == MODE_FUSED) {
+                const float4 ga = sm.gt_a[best_g[k]], gb = sm.gt_b[best_g[k]];
+                const float4 gbox = make_float4(gb.y, gb.z, fsub(ga.z, ga.x), fsub(ga.w, ga.y));
+                const float4 t = encode_offsets(gbox, ldg4(prm.pri + 4ll * p), prm.inv_vc, prm.inv_vs);
+                const float4 l = ldg4(prm.loc_all + 4ll * row);
+                const float d[4] = {fsub(l.x, t.x), fsub(l.y, t.y), fsub(l.z, t.z), fsub(l.w, t.w)};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float z = fabsf(d[j]);
+                    acc_loc += (double)(z < 1.0f ? fmul(fmul(0.5f, z), z) : fsub(z, 0.5f));
+                }
+            }
+        } else {
+            neg[k] = true;
+            key[k] = __float_as_uint(ce[k]);
+        }
+    }
+
+    // ---- hard-negative budget (SSD_trainer.py:585-596) --------------------------------------
+    const long long n_neg = (long long)P - n_pos_img;
+    long long want = (n_pos_img == 0) ? (long long)prm.ratio : (long long)(prm.ratio * (double)n_pos_img);
+    if (want < 0) want = 0;
+    const long long kk = want < n_neg ? want : n_neg;
+    unsigned thr_key = 0u;        // selected negatives: key > thr_key, plus `need` of those == thr_key
+    unsigned need = 0u;
+    bool take_all = (kk >= n_neg);
+    if (kk > 0 && !take_all) {
+        // 4-pass MSD radix select of the kk-th largest key over the cluster
+        unsigned prefix = 0u, remaining = (unsigned)kk;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            unsigned* h = st.hist[pass & 1];
+            for (int i = tid; i < 256; i += TT) h[i] = 0u;
+            __syncthreads();
+            const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                if (neg[k] && ((key[k] & himask) == prefix)) atomicAdd(&h[(key[k] >> shift) & 255u], 1u);
+            cluster.sync();
+            for (int i = tid; i < 256; i += TT) {
+                unsigned t = 0u;
+                for (int r = 0; r < cs; ++r) t += cluster.map_shared_rank(&st, r)->hist[pass & 1][i];
+                st.total[i] = t;
+            }
+            __syncthreads();
+            if (tid < 32) {
+                // bins 255..0: lane l owns bins [255-8l-7 .. 255-8l]; find where the suffix count reaches `remaining`
+                unsigned mine = 0u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mine += st.total[255 - (tid * 8 + j)];
+                unsigned incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned y = __shfl_up_sync(FULL, incl, o);
+                    if (tid >= o) incl += y;
+                }
+                const unsigned excl = incl - mine;
+                if (excl < remaining && remaining <= incl) {
+                    unsigned run = excl;
+                    for (int j = 0; j < 8; ++j) {
+                        const int bin = 255 - (tid * 8 + j);
+                        const unsigned c = st.total[bin];
+                        if (run + c >= remaining) { st.sel_digit = (unsigned)bin; st.sel_need = remaining - run; break; }
+                        run += c;
+                    }
+                }
+            }
+            __syncthreads();
+            prefix |= st.sel_digit << shift;
+            remaining = st.sel_need;
+        }
+        thr_key = prefix;
+        need = remaining;
+    }
+
+    // ---- sums (and the backward selection) --------------------------------------------------
+    int my_ties = 0;
+    if (kk > 0) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            if (!neg[k]) continue;
+            if (take_all || key[k] > thr_key) acc_ce += (double)ce[k];
+            else if (key[k] == thr_key) my_ties += 1;
+        }
+    }
+    if (prm.sel_cls) {
+        // which of the elements equal to the threshold are taken: the first `need` in prior order
+        int before = 0;          // ties owned by lower-ranked CTAs
+        bool all_ties = true;
+        if (kk > 0 && !take_all) {
+            const int cta_ties = block_sum<int>(my_ties, st.iscratch);
+            if (tid == 0) st.ties_cta = cta_ties;
+            cluster.sync();
+            int tot = 0;
+            for (int r = 0; r < cs; ++r) {
+                const int t = cluster.map_shared_rank(&st, r)->ties_cta;
+                if (r < rank) before += t;
+                tot += t;
+            }
+            all_ties = (unsigned)tot == need;
+        }
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const int p = p0 + k * TT + tid;
+            // ordered rank of this tie inside the CTA: slots are visited k-major, then by thread
+            int rank_in_cta = 0;
+            const bool tie = kk > 0 && !take_all && neg[k] && key[k] == thr_key;
+            if (!all_ties) {
+                const unsigned bal = __ballot_sync(FULL, tie);
+                const int lane = tid & 31, warp = tid >> 5;
+                __syncthreads();
+                if (lane == 0) st.iscratch[warp] = __popc(bal);
+                __syncthreads();
+                for (int w = 0; w < warp; ++w) rank_in_cta += st.iscratch[w];
+                rank_in_cta += __popc(bal & ((1u << lane) - 1u));
+                int slot_total = 0;
+                for (int w = 0; w < (TT >> 5); ++w) slot_total += st.iscratch[w];
+                rank_in_cta += before;
+                before += slot_total;
+            }
+            if (p >= p1) continue;
+            const long long row = (long long)b * P + p;
+            int8_t s = -1;
+            if (pos[k]) s = (int8_t)cls[k];
+            else if (kk > 0 && (take_all || key[k] > thr_key || (tie && (all_ties || (unsigned)rank_in_cta < need)))) s = 0;
+            prm.sel_cls[row] = s;
+            if (prm.matched16) prm.matched16[row] = pos[k] ? (int16_t)best_g[k] : (int16_t)-1;
+        }
+    }
+    // the `need` threshold-valued elements are counted once, by rank 0
+    if (rank == 0 && tid == 0 && kk > 0 && !take_all) acc_ce += (double)need * (double)__uint_as_float(thr_key);
+
+    const double s_loc = block_sum<double>(acc_loc, st.dscratch);
+    const double s_ce = block_sum<double>(acc_ce, st.dscratch);
+    if (tid == 0) {
+        prm.cta_part[2ll * blockIdx.x + 0] = s_loc;
+        prm.cta_part[2ll * blockIdx.x + 1] = s_ce;
+    }
+    cluster.sync();          // peers may still be reading this CTA's histograms / counters
+}
+
+// Fixed-order final reduction: sums[0..1] = sum of the per-CTA partials, sums[2] = sum n_pos.
+__global__ void __launch_bounds__(256) finalize_sums_kernel(const double* __restrict__ cta_part, int n_part,
+                                                            const int32_t* __restrict__ n_pos, int B,
+                                                            double* __restrict__ sums) {
+    __shared__ double scratch[32];
+    double a = 0.0, c = 0.0, n = 0.0;
+    for (int i = threadIdx.x; i < n_part; i += blockDim.x) { a += cta_part[2ll * i]; c += cta_part[2ll * i + 1]; }
+    for (int i = threadIdx.x; i < B; i += blockDim.x) n += (double)n_pos[i];
+    a = block_sum<double>(a, scratch);
+    c = block_sum<double>(c, scratch);
+    n = block_sum<double>(n, scratch);
+    if (threadIdx.x == 0) { sums[0] = a; sums[1] = c; sums[2] = n; }
+}
+
+// per-prior constants of the clamped xyxy priors
+__global__ void prior_tables_kernel(const float* __restrict__ pri, int P, float* __restrict__ xyxy, float* __restrict__ aux) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const float4 c = ldg4(pri + 4ll * p);
+    const float hw = fmul(0.5f, c.z), hh = fmul(0.5f, c.w);
+    const float x1 = fminf(fmaxf(fsub(c.x, hw), 0.f), 1.f), y1 = fminf(fmaxf(fsub(c.y, hh), 0.f), 1.f);
+    const float x2 = fminf(fmaxf(fadd(c.x, hw), 0.f), 1.f), y2 = fminf(fmaxf(fadd(c.y, hh), 0.f), 1.f);
+    const BoxC k = box_consts(x1, y1, x2, y2, true);
+    if (xyxy) reinterpret_cast<float4*>(xyxy)[p] = make_float4(x1, y1, x2, y2);
+    if (aux) reinterpret_cast<float4*>(aux)[p] = make_float4(k.area, k.xc, k.yc, k.at);
+}
+
+// only aux, from caller-provided xyxy
+__global__ void prior_aux_kernel(const float* __restrict__ xyxy, int P, float* __restrict__ aux) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const float4 a = ldg4(xyxy + 4ll * p);
+    const BoxC k = box_consts(a.x, a.y, a.z, a.w, true);
+    reinterpret_cast<float4*>(aux)[p] = make_float4(k.area, k.xc, k.yc, k.at);
+}
+
+// loc_t[pos_mask]: one CTA per image, ordered compaction of the rows whose mask byte is set
+__global__ void __launch_bounds__(256) compact_rows_kernel(const float* __restrict__ loc_t, const uint8_t* __restrict__ mask,
+                                                           const int32_t* __restrict__ n_pos, int P, float* __restrict__ out) {
+    __shared__ int warp_cnt[8];
+    __shared__ long long base_s;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        long long base = 0;
+        for (int i = 0; i < b; ++i) base += n_pos[i];
+        base_s = base;
+    }
+    __syncthreads();
+    long long run = base_s;
+    for (int p_base = 0; p_base < P; p_base += 256) {
+        const int p = p_base + tid;
+        const bool on = p < P && mask[(long long)b * P + p] != 0;
+        const unsigned bal = __ballot_sync(FULL, on);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < 8; ++w) { if (w < warp) before += warp_cnt[w]; total += warp_cnt[w]; }
+        if (on) {
+            const long long dst = run + before + __popc(bal & ((1u << lane) - 1u));
+            reinterpret_cast<float4*>(out)[dst] = reinterpret_cast<const float4*>(loc_t)[(long long)b * P + p];
+        }
+        run += total;
+        __syncthreads();
+    }
+}
+
+// gradients of both losses w.r.t. the head outputs
+template <int CT>
+__global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__ pri, int P,
+                                                       const float* __restrict__ gt_boxes, const int32_t* __restrict__ gt_offsets,
+                                                       long long rows, float norm_w, float norm_h,
+                                                       const float* __restrict__ loc_all, const float* __restrict__ conf_all, int C,
+                                                       float inv_vc, float inv_vs,
+                                                       const int8_t* __restrict__ sel, const int16_t* __restrict__ matched,
+                                                       const double* __restrict__ scales,
+                                                       float* __restrict__ g_loc, float* __restrict__ g_conf) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const int s = sel[row];
+    const float k_loc = (float)scales[0], k_conf = (float)scales[1];
+    if (g_conf) {
+        float* out = g_conf + row * C;
+        if (s < 0) {
+            for (int i = 0; i < C; ++i) out[i] = 0.0f;
+        } else {
+            const float* in = conf_all + row * C;
+            float mx = __ldg(in);
+            for (int i = 1; i < C; ++i) mx = fmaxf(mx, __ldg(in + i));
+            float sum = 0.0f;
+            for (int i = 0; i < C; ++i) sum += expf(__ldg(in + i) - mx);
+            const float inv = 1.0f / sum;
+            for (int i = 0; i < C; ++i) {
+                const float pr = expf(__ldg(in + i) - mx) * inv;
+                out[i] = k_conf * (pr - (i == s ? 1.0f : 0.0f));
+            }
+        }
+    }
+    if (g_loc) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int m = matched[row];
+        if (m >= 0) {
+            const int b = (int)(row / P), p = (int)(row % P);
+            const float4 px = ldg4(gt_boxes + 4ll * (gt_offsets[b] + m));
+            const float x1 = fdiv(px.x, norm_w), y1 = fdiv(px.y, norm_h), x2 = fdiv(px.z, norm_w), y2 = fdiv(px.w, norm_h);
+            const float4 gbox = make_float4(fmul(fadd(x1, x2), 0.5f), fmul(fadd(y1, y2), 0.5f), fsub(x2, x1), fsub(y2, y1));
+            const float4 t = encode_offsets(gbox, ldg4(pri + 4ll * p), inv_vc, inv_vs);
+            const float4 l = ldg4(loc_all + 4ll * row);
+            g.x = k_loc * fminf(fmaxf(l.x - t.x, -1.f), 1.f);
+            g.y = k_loc * fminf(fmaxf(l.y - t.y, -1.f), 1.f);
+            g.z = k_loc * fminf(fmaxf(l.z - t.z, -1.f), 1.f);
+            g.w = k_loc * fminf(fmaxf(l.w - t.w, -1.f), 1.f);
+        }
+        reinterpret_cast<float4*>(g_loc)[row] = g;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+
+template <int MODE, int CT>
+static int launch_train(const TrainParams& prm, cudaStream_t stream) {
+    // a fixed cluster of 8 balances best at SSD300 sizes (1092 priors per CTA); smaller P shrink it
+    int cs = MAX_CS;
+    while (cs > 1 && (cs / 2) * SLOTS >= prm.P && prm.P <= 2048) cs >>= 1;
+    if (cs * SLOTS < prm.P) return SSDHOT_ERR_SHAPE;
+    const size_t dyn = smem_bytes(prm.max_gt > 0 ? prm.max_gt : 1);
+    auto kern = train_kernel<MODE, CT>;
+    if (dyn > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return (int)e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(prm.B * cs));
+    cfg.blockDim = dim3(TT);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, prm);
+    ++g_launches;
+    if (e != cudaSuccess) return (int)e;
+    return SSDHOT_OK;
+}
+
+int train_cluster_size(int P) {
+    int cs = MAX_CS;
+    while (cs > 1 && (cs / 2) * SLOTS >= P && P <= 2048) cs >>= 1;
+    return cs;
+}
+
+}  // namespace ssdhot
+
+using namespace ssdhot;
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" int ssdhot_prior_tables(const float* priors_cxcywh, int P, float* priors_xyxy, float* prior_aux,
+                                   ssdhot_stream_t stream) {
+    if (!priors_cxcywh || (!priors_xyxy && !prior_aux)) return SSDHOT_ERR_NULL;
+    if (P <= 0 || P > SSDHOT_MAX_PRIORS) return SSDHOT_ERR_SHAPE;
+    if (!aligned16(priors_cxcywh) || !aligned16(priors_xyxy) || !aligned16(prior_aux)) return SSDHOT_ERR_ALIGN;
+    prior_tables_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(priors_cxcywh, P, priors_xyxy, prior_aux);
+    SSDHOT_CHECK_LAUNCH();
+    return SSDHOT_OK;
+}
+
+extern "C" int ssdhot_prior_aux(const float* priors_xyxy, int P, float* prior_aux, ssdhot_stream_t stream) {
+    if (!priors_xyxy || !prior_aux) return SSDHOT_ERR_NULL;
+    if (P <= 0 || P > SSDHOT_MAX_PRIORS) return SSDHOT_ERR_SHAPE;
+    if (!aligned16(priors_xyxy) || !aligned16(prior_aux)) return SSDHOT_ERR_ALIGN;
+    prior_aux_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(priors_xyxy, P, prior_aux);
+    SSDHOT_CHECK_LAUNCH();
+    return SSDHOT_OK;
+}
+
+static int check_gt_args(const float* pri, const float* pri_xyxy, const float* aux, int P, const float* gt_boxes,
+                         const int64_t* gt_labels, const int32_t* gt_offsets, int B, int max_gt,
+                         float norm_w, float norm_h, float var_center, float var_size) {
+    if (!pri || !pri_xyxy || !aux || !gt_offsets) return SSDHOT_ERR_NULL;
+    if (max_gt > 0 && (!gt_boxes || !gt_labels)) return SSDHOT_ERR_NULL;
+    if (P <= 0 || P > SSDHOT_MAX_PRIORS || B <= 0 || max_gt < 0 || max_gt > SSDHOT_MAX_GT) return SSDHOT_ERR_SHAPE;
+    if (!(norm_w > 0.f) || !(norm_h > 0.f) || !(var_center > 0.f) || !(var_size > 0.f)) return SSDHOT_ERR_VALUE;
+    if (!aligned16(pri) || !aligned16(pri_xyxy) || !aligned16(aux) || !aligned16(gt_boxes)) return SSDHOT_ERR_ALIGN;
+    return SSDHOT_OK;
+}
+
+extern "C" int ssdhot_match_encode(const float* priors_cxcywh, const float* priors_xyxy, const float* prior_aux, int P,
+                                   const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
+                                   int B, int max_gt, float norm_w, float norm_h,
+                                   float iou_thresh, float var_center, float var_size,
+                                   float* loc_t, int loc_positives_only, int64_t* cls_t, uint8_t* pos_mask,
+                                   int32_t* matched_gt, float* matched_cxcywh, int32_t* n_pos,
+                                   int32_t* dev_flags, ssdhot_stream_t stream) {
+    int rc = check_gt_args(priors_cxcywh, priors_xyxy, prior_aux, P, gt_boxes, gt_labels, gt_offsets, B, max_gt,
+                           norm_w, norm_h, var_center, var_size);
+    if (rc) return rc;
+    if (!aligned16(loc_t) || !aligned16(matched_cxcywh)) return SSDHOT_ERR_ALIGN;
+    TrainParams prm = {};
+    prm.pri = priors_cxcywh; prm.pri_xyxy = priors_xyxy; prm.pri_aux = prior_aux; prm.P = P;
+    prm.gt_boxes = gt_boxes; prm.gt_labels = gt_labels; prm.gt_offsets = gt_offsets;
+    prm.B = B; prm.max_gt = max_gt; prm.norm_w = norm_w; prm.norm_h = norm_h;
+    prm.thresh = iou_thresh; prm.inv_vc = 1.0f / var_center; prm.inv_vs = 1.0f / var_size;
+    prm.loc_t = loc_t; prm.loc_pos_only = loc_positives_only; prm.cls_t = cls_t; prm.pos_mask = pos_mask;
+    prm.matched32 = matched_gt; prm.matched_box = matched_cxcywh; prm.n_pos = n_pos; prm.flags = dev_flags;
+    return launch_train<MODE_MATCH, 0>(prm, (cudaStream_t)stream);
+}
+
+extern "C" int ssdhot_compact_rows(const float* loc_t, const uint8_t* pos_mask, const int32_t* n_pos, int B, int P,
+                                   float* out, ssdhot_stream_t stream) {
+    if (!loc_t || !pos_mask || !n_pos || !out) return SSDHOT_ERR_NULL;
+    if (B <= 0 || P <= 0) return SSDHOT_ERR_SHAPE;
+    if (!aligned16(loc_t) || !aligned16(out)) return SSDHOT_ERR_ALIGN;
+    compact_rows_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(loc_t, pos_mask, n_pos, P, out);
+    SSDHOT_CHECK_LAUNCH();
+    return SSDHOT_OK;
+}
+
+extern "C" unsigned long long ssdhot_loss_workspace_bytes(int B) {
+    if (B <= 0) return 0;
+    // per-CTA partial sums [B*8][2] doubles + n_pos [B] int32 (used when the caller passes none)
+    return (unsigned long long)B * MAX_CS * 2 * sizeof(double) + (unsigned long long)B * sizeof(int32_t) + 64;
+}
+
+static int finalize(const TrainParams& prm, int n_part, const int32_t* n_pos, double* sums, cudaStream_t stream) {
+    finalize_sums_kernel<<<1, 256, 0, stream>>>(prm.cta_part, n_part, n_pos, prm.B, sums);
+    SSDHOT_CHECK_LAUNCH();
+    return SSDHOT_OK;
+}
+
+extern "C" int ssdhot_multibox_loss_fwd(const float* priors_cxcywh, const float* priors_xyxy, const float* prior_aux, int P,
+                                        const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
+                                        int B, int max_gt, float norm_w, float norm_h,
+                                        const float* loc_all, const float* conf_all, int C,
+                                        float iou_thresh, float var_center, float var_size, double neg_pos_ratio,
+                                        double* sums, void* work, int8_t* sel_cls, int16_t* matched_gt, int32_t* n_pos,
+                                        int32_t* dev_flags, ssdhot_stream_t stream) {
+    int rc = check_gt_args(priors_cxcywh, priors_xyxy, prior_aux, P, gt_boxes, gt_labels, gt_offsets, B, max_gt,
+                           norm_w, norm_h, var_center, var_size);
+    if (rc) return rc;
+    if (!loc_all || !conf_all || !sums || !work) return SSDHOT_ERR_NULL;
+    if (C < 2 || C > SSDHOT_MAX_CLASSES) return SSDHOT_ERR_SHAPE;
+    if (!(neg_pos_ratio >= 0.0)) return SSDHOT_ERR_VALUE;
+    if (!aligned16(loc_all) || (reinterpret_cast<uintptr_t>(conf_all) & 7u) || (reinterpret_cast<uintptr_t>(work) & 7u))
+        return SSDHOT_ERR_ALIGN;
+    TrainParams prm = {};
+    prm.pri = priors_cxcywh; prm.pri_xyxy = priors_xyxy; prm.pri_aux = prior_aux; prm.P = P;
+    prm.gt_boxes = gt_boxes; prm.gt_labels = gt_labels; prm.gt_offsets = gt_offsets;
+    prm.B = B; prm.max_gt = max_gt; prm.norm_w = norm_w; prm.norm_h = norm_h;
+    prm.thresh = iou_thresh; prm.inv_vc = 1.0f / var_center; prm.inv_vs = 1.0f / var_size;
+    prm.loc_all = loc_all; prm.conf_all = conf_all; prm.C = C; prm.ratio = neg_pos_ratio;
+    prm.cta_part = reinterpret_cast<double*>(work);
+    int32_t* np = n_pos ? n_pos : reinterpret_cast<int32_t*>(prm.cta_part + (size_t)B * MAX_CS * 2);
+    prm.n_pos = np; prm.sel_cls = sel_cls; prm.matched16 = matched_gt; prm.flags = dev_flags;
+    rc = (C == 6) ? launch_train<MODE_FUSED, 6>(prm, (cudaStream_t)stream)
+                  : launch_train<MODE_FUSED, 0>(prm, (cudaStream_t)stream);
+    if (rc) return rc;
+    return finalize(prm, B * train_cluster_size(P), np, sums, (cudaStream_t)stream);
+}
+
+extern "C" int ssdhot_mined_ce_fwd(const float* conf_all, const int64_t* cls_t, const uint8_t* pos_mask,
+                                   int B, int P, int C, double neg_pos_ratio,
+                                   double* sums, void* work, int8_t* sel_cls, ssdhot_stream_t stream) {
+    if (!conf_all || !cls_t || !pos_mask || !sums || !work) return SSDHOT_ERR_NULL;
+    if (P <= 0 || P > SSDHOT_MAX_PRIORS || B <= 0 || C < 2 || C > SSDHOT_MAX_CLASSES) return SSDHOT_ERR_SHAPE;
+    if (!(neg_pos_ratio >= 0.0)) return SSDHOT_ERR_VALUE;
+    if ((reinterpret_cast<uintptr_t>(conf_all) & 7u) || (reinterpret_cast<uintptr_t>(work) & 7u)) return SSDHOT_ERR_ALIGN;
+    TrainParams prm = {};
+    prm.P = P; prm.B = B; prm.max_gt = 0; prm.conf_all = conf_all; prm.C = C; prm.ratio = neg_pos_ratio;
+    prm.in_cls = cls_t; prm.in_pos = pos_mask;
+    prm.cta_part = reinterpret_cast<double*>(work);
+    prm.n_pos = reinterpret_cast<int32_t*>(prm.cta_part + (size_t)B * MAX_CS * 2);
+    prm.sel_cls = sel_cls;
+    int rc = (C == 6) ? launch_train<MODE_LOSS, 6>(prm, (cudaStream_t)stream)
+                      : launch_train<MODE_LOSS, 0>(prm, (cudaStream_t)stream);
+    if (rc) return rc;
+    return finalize(prm, B * train_cluster_size(P), prm.n_pos, sums, (cudaStream_t)stream);
+}
+
+extern "C" int ssdhot_multibox_loss_bwd(const float* priors_cxcywh, int P,
+                                        const float* gt_boxes, const int32_t* gt_offsets, int B,
+                                        float norm_w, float norm_h,
+                                        const float* loc_all, const float* conf_all, int C,
+                                        float var_center, float var_size,
+                                        const int8_t* sel_cls, const int16_t* matched_gt, const double* scales,
+                                        float* grad_loc, float* grad_conf, ssdhot_stream_t stream) {
+    if (!sel_cls || !scales || (!grad_loc && !grad_conf)) return SSDHOT_ERR_NULL;
+    if (grad_conf && !conf_all) return SSDHOT_ERR_NULL;
+    if (grad_loc && (!loc_all || !matched_gt || !priors_cxcywh || !gt_offsets)) return SSDHOT_ERR_NULL;
+    if (P <= 0 || B <= 0 || C < 2 || C > SSDHOT_MAX_CLASSES) return SSDHOT_ERR_SHAPE;
+    if (!aligned16(loc_all) || !aligned16(grad_loc) || !aligned16(priors_cxcywh) || !aligned16(gt_boxes)) return SSDHOT_ERR_ALIGN;
+    const long long rows = (long long)B * P;
+    loss_bwd_kernel<0><<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        priors_cxcywh, P, gt_boxes, gt_offsets, rows, norm_w, norm_h, loc_all, conf_all, C,
+        1.0f / var_center, 1.0f / var_size, sel_cls, matched_gt, scales, grad_loc, grad_conf);
+    SSDHOT_CHECK_LAUNCH();
+    return SSDHOT_OK;
+}

@@ -1,0 +1,392 @@
+"""Drop-in Python surface of the hot path: the same call signatures as the reference's
+`build_targets` / `CELoss_w_neg_mining` (SSD_trainer.py:491, :551) and `mySSD.encode_ssd` /
+`decode_ssd` / `iou_nms` / `predict` (SSD_from_scratch.py:697, :776, :664, :338), each a thin shim
+(argument validation identical to the reference, ground-truth packing, output allocation, ONE
+C-ABI call per stage).  Tensors must live on a CUDA device; there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .priors import PriorSet
+
+METRICS = {"diou": 0, "ciou": 1, "iou": 2}
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.SsdhotError("ssdhot runs on CUDA tensors only (no CPU fallback)")
+        dev = t.device if dev is None else dev
+        if t.device != dev:
+            raise _lib.SsdhotError("all tensors must be on the same CUDA device")
+    return dev
+
+
+class PackedTargets:
+    """Ragged ground truth of a batch as three device tensors (hard part 9):
+    boxes [sumG,4] f32 pixel xyxy, labels [sumG] i64, offsets [B+1] i32; max_gt known on the host."""
+
+    def __init__(self, boxes: torch.Tensor, labels: torch.Tensor, offsets: torch.Tensor, max_gt: int, n_img: int):
+        self.boxes, self.labels, self.offsets, self.max_gt, self.n_img = boxes, labels, offsets, int(max_gt), int(n_img)
+
+
+def pack_targets(targets: Sequence[Dict[str, torch.Tensor]], device) -> PackedTargets:
+    """List[Dict] (collate_detection, SSD_trainer.py:806-813) -> PackedTargets on `device`.
+    Works for CPU or CUDA member tensors; one concatenation + (for CPU input) one H2D copy each."""
+    if isinstance(targets, PackedTargets):
+        return targets
+    device = torch.device(device)
+    counts = [int(t["boxes"].shape[0]) if t["boxes"].numel() else 0 for t in targets]
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + c)
+    offsets = torch.tensor(offs, dtype=torch.int32).to(device, non_blocking=True)
+    live = [i for i, c in enumerate(counts) if c > 0]
+    if not live:
+        boxes = torch.zeros((1, 4), dtype=torch.float32, device=device)   # never read (max_gt = 0)
+        labels = torch.zeros((1,), dtype=torch.int64, device=device)
+    else:
+        boxes = torch.cat([targets[i]["boxes"].as_subclass(torch.Tensor).reshape(-1, 4) for i in live], 0)
+        labels = torch.cat([targets[i]["labels"].reshape(-1) for i in live], 0)
+        boxes = boxes.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        labels = labels.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
+    return PackedTargets(boxes, labels, offsets, max(counts) if counts else 0, len(counts))
+
+
+# ------------------------------------------------------------------------------------------------
+# match + encode
+# ------------------------------------------------------------------------------------------------
+def match_encode_batch(priors: PriorSet, packed: PackedTargets, iou_thresh: float, norm_wh: Tuple[float, float],
+                       want_loc: str = "none", want_cls: bool = True, want_pos: bool = True,
+                       want_matched_idx: bool = False, want_matched_box: bool = False):
+    """One ssdhot_match_encode launch.  want_loc: 'none' | 'positives' | 'all'.  Returns a dict."""
+    dev = priors.device
+    B, P = packed.n_img, priors.P
+    out = {}
+    out["n_pos"] = torch.empty((B,), dtype=torch.int32, device=dev)
+    loc = None
+    if want_loc != "none":
+        loc = torch.empty((B, P, 4), dtype=torch.float32, device=dev)
+    out["loc_t"] = loc
+    out["cls_t"] = torch.empty((B, P), dtype=torch.int64, device=dev) if want_cls else None
+    out["pos_mask"] = torch.empty((B, P), dtype=torch.bool, device=dev) if want_pos else None
+    out["matched_gt"] = torch.empty((B, P), dtype=torch.int32, device=dev) if want_matched_idx else None
+    out["matched_cxcywh"] = torch.empty((B, P, 4), dtype=torch.float32, device=dev) if want_matched_box else None
+    with torch.cuda.device(dev):
+        rc = _lib.lib().ssdhot_match_encode(
+            priors.priors.data_ptr(), priors.priors_xyxy.data_ptr(), priors.aux.data_ptr(), P,
+            packed.boxes.data_ptr(), packed.labels.data_ptr(), packed.offsets.data_ptr(), B, packed.max_gt,
+            float(norm_wh[0]), float(norm_wh[1]), float(iou_thresh), priors.variances[0], priors.variances[1],
+            _ptr(loc), 1 if want_loc == "positives" else 0, _ptr(out["cls_t"]), _ptr(out["pos_mask"]),
+            _ptr(out["matched_gt"]), _ptr(out["matched_cxcywh"]), out["n_pos"].data_ptr(), None, _stream(dev))
+    _lib.check(rc, "ssdhot_match_encode")
+    return out
+
+
+def build_targets(model, targets: List[Dict], H: int = 300, W: int = 300, iou_thresh: float = 0.50,
+                  device="cuda") -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Drop-in for SSD_trainer.build_targets (SSD_trainer.py:491-547):
+    -> (pos_mask [B,P] bool, loc_t[pos_mask] [N_pos,4] f32, cls_t [B,P] i64)."""
+    if not (0.0 < iou_thresh < 1.0):
+        raise ValueError(f"Score threshold should be greater than 0 and less than 1, recieved {iou_thresh}.")
+    priors = PriorSet.of(model)
+    if torch.device(device).type != "cuda":
+        raise _lib.SsdhotError("ssdhot.build_targets needs device='cuda' (no CPU fallback)")
+    packed = pack_targets(targets, priors.device)
+    r = match_encode_batch(priors, packed, iou_thresh, (W, H), want_loc="positives")
+    total = int(r["n_pos"].sum().item())            # the reference's return shape needs N_pos on the host
+    loc_pm = torch.empty((total, 4), dtype=torch.float32, device=priors.device)
+    if total > 0:
+        with torch.cuda.device(priors.device):
+            rc = _lib.lib().ssdhot_compact_rows(r["loc_t"].data_ptr(), r["pos_mask"].data_ptr(), r["n_pos"].data_ptr(),
+                                                packed.n_img, priors.P, loc_pm.data_ptr(), _stream(priors.device))
+        _lib.check(rc, "ssdhot_compact_rows")
+    return r["pos_mask"], loc_pm, r["cls_t"]
+
+
+def encode_ssd(model, gt_boxes_xyxy: torch.Tensor, gt_labels: torch.Tensor, iou_thresh: float = 0.5,
+               background_class: int = 0):
+    """Drop-in for mySSD.encode_ssd (SSD_from_scratch.py:697-773), one image, normalised boxes:
+    -> (loc_target [P,4], cls_target [P], pos_mask [P] bool, matched_gt_cxcywh [P,4])."""
+    if background_class != 0:
+        raise ValueError(f"Background should be 0, recieved {background_class}.")
+    priors = PriorSet.of(model)
+    _need_cuda(gt_boxes_xyxy, gt_labels)
+    packed = pack_targets([{"boxes": gt_boxes_xyxy, "labels": gt_labels}], priors.device)
+    r = match_encode_batch(priors, packed, iou_thresh, (1.0, 1.0), want_loc="all", want_matched_box=True)
+    cls = r["cls_t"][0]
+    if gt_labels.dtype != torch.int64:
+        cls = cls.to(gt_labels.dtype)
+    return r["loc_t"][0], cls, r["pos_mask"][0], r["matched_cxcywh"][0]
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------
+_work_cache: Dict[Tuple, torch.Tensor] = {}
+
+
+def _workspace(tag: str, dev: torch.device, nbytes: int) -> torch.Tensor:
+    key = (tag, dev)
+    buf = _work_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=dev)
+        _work_cache[key] = buf
+    return buf
+
+
+class _MinedCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, conf_all, cls_t, pos_mask, total_pos, ratio):
+        dev = _need_cuda(conf_all, cls_t, pos_mask)
+        B, P, C = conf_all.shape
+        conf = conf_all.detach().to(torch.float32).contiguous()
+        cls = cls_t.to(torch.int64).contiguous()
+        pos = pos_mask.to(torch.bool).contiguous()
+        sums = torch.empty((3,), dtype=torch.float64, device=dev)
+        sel = torch.empty((B, P), dtype=torch.int8, device=dev) if conf_all.requires_grad else None
+        work = _workspace("loss", dev, _lib.lib().ssdhot_loss_workspace_bytes(B))
+        with torch.cuda.device(dev):
+            rc = _lib.lib().ssdhot_mined_ce_fwd(conf.data_ptr(), cls.data_ptr(), pos.data_ptr(), B, P, C, float(ratio),
+                                                sums.data_ptr(), work.data_ptr(), _ptr(sel), _stream(dev))
+        _lib.check(rc, "ssdhot_mined_ce_fwd")
+        total = torch.as_tensor(total_pos, device=dev).to(torch.float64)
+        ctx.save_for_backward(conf, sel, total)
+        return (sums[1] / total).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        conf, sel, total = ctx.saved_tensors
+        dev = conf.device
+        B, P, C = conf.shape
+        scales = torch.stack((torch.zeros((), dtype=torch.float64, device=dev), g.to(torch.float64) / total))
+        grad = torch.empty_like(conf)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().ssdhot_multibox_loss_bwd(None, P, None, None, B, 1.0, 1.0, None, conf.data_ptr(), C, 0.1, 0.2,
+                                                     sel.data_ptr(), None, scales.data_ptr(), None, grad.data_ptr(),
+                                                     _stream(dev))
+        _lib.check(rc, "ssdhot_multibox_loss_bwd")
+        return grad, None, None, None, None
+
+
+def CELoss_w_neg_mining(conf_all: torch.Tensor, cls_t: torch.Tensor, pos_mask: torch.Tensor,
+                        num_pos_per_img: torch.Tensor, total_pos, neg_pos_ratio: float = 3.0) -> torch.Tensor:
+    """Drop-in for SSD_trainer.CELoss_w_neg_mining (SSD_trainer.py:551-600); differentiable w.r.t.
+    conf_all.  `num_pos_per_img` is accepted for signature parity; the kernel recounts positives
+    from pos_mask on the device instead of syncing once per image as the reference does (:585)."""
+    return _MinedCE.apply(conf_all, cls_t, pos_mask, total_pos, float(neg_pos_ratio))
+
+
+class _FusedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, loc_all, conf_all, priors: PriorSet, packed: PackedTargets, iou_thresh, ratio, norm_wh, group):
+        dev = _need_cuda(loc_all, conf_all)
+        B, P, C = conf_all.shape
+        loc = loc_all.detach().to(torch.float32).contiguous()
+        conf = conf_all.detach().to(torch.float32).contiguous()
+        need_grad = loc_all.requires_grad or conf_all.requires_grad
+        sums = torch.empty((3,), dtype=torch.float64, device=dev)
+        sel = torch.empty((B, P), dtype=torch.int8, device=dev) if need_grad else None
+        matched = torch.empty((B, P), dtype=torch.int16, device=dev) if need_grad else None
+        work = _workspace("loss", dev, _lib.lib().ssdhot_loss_workspace_bytes(B))
+        with torch.cuda.device(dev):
+            rc = _lib.lib().ssdhot_multibox_loss_fwd(
+                priors.priors.data_ptr(), priors.priors_xyxy.data_ptr(), priors.aux.data_ptr(), P,
+                packed.boxes.data_ptr(), packed.labels.data_ptr(), packed.offsets.data_ptr(), B, packed.max_gt,
+                float(norm_wh[0]), float(norm_wh[1]), loc.data_ptr(), conf.data_ptr(), C,
+                float(iou_thresh), priors.variances[0], priors.variances[1], float(ratio),
+                sums.data_ptr(), work.data_ptr(), _ptr(sel), _ptr(matched), None, None, _stream(dev))
+        _lib.check(rc, "ssdhot_multibox_loss_fwd")
+        if group is not None:
+            # the only exchange of the sharded path: [sum smooth-L1, sum CE, sum positives]
+            torch.distributed.all_reduce(sums, op=torch.distributed.ReduceOp.SUM, group=group)
+        total = sums[2].clamp_min(1.0)
+        if need_grad:
+            ctx.save_for_backward(loc, conf, sel, matched, total, packed.boxes, packed.offsets)
+            ctx.meta = (priors, norm_wh)
+        losses = (sums[:2] / total).to(torch.float32)
+        ctx.mark_non_differentiable(sums)
+        return losses[0], losses[1], sums
+
+    @staticmethod
+    def backward(ctx, g_loc, g_conf, _g_sums):
+        loc, conf, sel, matched, total, gt_boxes, gt_offsets = ctx.saved_tensors
+        priors, norm_wh = ctx.meta
+        dev = conf.device
+        B, P, C = conf.shape
+        scales = torch.stack((g_loc.to(torch.float64) / total, g_conf.to(torch.float64) / total))
+        d_loc = torch.empty_like(loc) if ctx.needs_input_grad[0] else None
+        d_conf = torch.empty_like(conf) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(dev):
+            rc = _lib.lib().ssdhot_multibox_loss_bwd(
+                priors.priors.data_ptr(), P, gt_boxes.data_ptr(), gt_offsets.data_ptr(), B,
+                float(norm_wh[0]), float(norm_wh[1]), loc.data_ptr(), conf.data_ptr(), C,
+                priors.variances[0], priors.variances[1], sel.data_ptr(), matched.data_ptr(), scales.data_ptr(),
+                _ptr(d_loc), _ptr(d_conf), _stream(dev))
+        _lib.check(rc, "ssdhot_multibox_loss_bwd")
+        return d_loc, d_conf, None, None, None, None, None, None
+
+
+def multibox_loss(model, loc_all: torch.Tensor, conf_all: torch.Tensor, targets, iou_thresh: float = 0.5,
+                  neg_pos_ratio: float = 3.0, H: int = 300, W: int = 300, group=None, return_sums: bool = False):
+    """The whole post-backbone training step of SSD_train_step (SSD_trainer.py:92-117) in one
+    launch: -> (batch_loc_loss, batch_conf_loss), 0-d fp32, differentiable w.r.t. loc_all/conf_all.
+    With `group` (a torch.distributed process group) the batch is this rank's shard: the three
+    partial sums are all-reduced so every rank returns the global-batch losses."""
+    if not (0.0 < iou_thresh < 1.0):
+        raise ValueError(f"Score threshold should be greater than 0 and less than 1, recieved {iou_thresh}.")
+    priors = PriorSet.of(model)
+    packed = pack_targets(targets, priors.device)
+    l_loc, l_conf, sums = _FusedLoss.apply(loc_all, conf_all, priors, packed, float(iou_thresh), float(neg_pos_ratio),
+                                           (W, H), group)
+    if return_sums:
+        return l_loc, l_conf, sums
+    return l_loc, l_conf
+
+
+def smooth_l1_positive_loss(loc_all: torch.Tensor, pos_mask: torch.Tensor, loc_t_pm: torch.Tensor, total_pos) -> torch.Tensor:
+    """SSD_trainer.py:108 as the reference writes it (kept in torch: it is one gather + one library
+    loss on N_pos rows; the fused path above never materialises it)."""
+    return torch.nn.functional.smooth_l1_loss(loc_all[pos_mask], loc_t_pm, reduction="sum") / total_pos
+
+
+# ------------------------------------------------------------------------------------------------
+# decode / NMS / predict
+# ------------------------------------------------------------------------------------------------
+def decode_ssd(loc: torch.Tensor, priors: torch.Tensor, variances: Tuple[float, float]) -> torch.Tensor:
+    """Drop-in for mySSD.decode_ssd (SSD_from_scratch.py:776-800)."""
+    dev = _need_cuda(loc, priors)
+    loc_c = loc.to(torch.float32).contiguous()
+    pri_c = priors.to(torch.float32).contiguous()
+    out = torch.empty_like(loc_c)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().ssdhot_decode(loc_c.data_ptr(), pri_c.data_ptr(), int(loc_c.shape[0]), float(variances[0]),
+                                      float(variances[1]), out.data_ptr(), _stream(dev))
+    _lib.check(rc, "ssdhot_decode")
+    return out
+
+
+def nms_sets(boxes: torch.Tensor, scores: torch.Tensor, set_sizes: Sequence[int], thresh: float, metric: str = "diou",
+             max_keep: int = 0):
+    """Greedy NMS of several independent box sets stored back to back -> (keep [total] i64 with set
+    s's survivors at offset sum(set_sizes[:s]), keep_count [n_sets] i32)."""
+    dev = _need_cuda(boxes, scores)
+    offs = [0]
+    for n in set_sizes:
+        offs.append(offs[-1] + int(n))
+    total = offs[-1]
+    set_offsets = torch.tensor(offs, dtype=torch.int32).to(dev)
+    bx = boxes.to(torch.float32).contiguous()
+    sc = scores.to(torch.float32).contiguous()
+    keep = torch.empty((max(total, 1),), dtype=torch.int64, device=dev)
+    count = torch.empty((len(set_sizes),), dtype=torch.int32, device=dev)
+    work = _workspace("nms", dev, _lib.lib().ssdhot_nms_workspace_bytes(total))
+    with torch.cuda.device(dev):
+        rc = _lib.lib().ssdhot_nms(bx.data_ptr(), sc.data_ptr(), set_offsets.data_ptr(), len(set_sizes), total,
+                                   max(set_sizes) if len(set_sizes) else 0, float(thresh), METRICS[metric], int(max_keep),
+                                   keep.data_ptr(), count.data_ptr(), work.data_ptr(), _stream(dev))
+    _lib.check(rc, "ssdhot_nms")
+    return keep[:total], count
+
+
+def iou_nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float, metric: str = "diou") -> torch.Tensor:
+    """Drop-in for mySSD.iou_nms (SSD_from_scratch.py:664-692): LongTensor of kept indices,
+    score-descending (equal scores: ascending index)."""
+    if boxes.numel() == 0:
+        return boxes.new_zeros((0,), dtype=torch.long)
+    keep, count = nms_sets(boxes, scores, [int(boxes.shape[0])], iou_threshold, metric)
+    return keep[: int(count.item())]
+
+
+def predict_padded(model, loc_all: torch.Tensor, conf_all: torch.Tensor, score_thresh: float = 0.2,
+                   nms_thresh: float = 0.5, max_per_img: int = 100, class_agnostic: bool = False,
+                   metric: str = "diou", want_cand: bool = False):
+    """Device-resident form of predict: padded outputs, no host synchronisation.
+    -> (labels [B,max] i64, scores [B,max] f32, boxes [B,max,4] f32 px xyxy, count [B] i32[, cand])."""
+    if not (0.0 <= score_thresh < 1.0):
+        raise ValueError(f"Score threshold should be greater than 0 and less than 1, recieved {score_thresh}.")
+    if not (0.0 < nms_thresh < 1.0):
+        raise ValueError(f"NMS threshold should be greater than 0 and less than 1, recieved {nms_thresh}.")
+    priors = PriorSet.of(model)
+    dev = _need_cuda(loc_all, conf_all)
+    B, P, C = conf_all.shape
+    assert P == priors.P
+    assert C >= 2
+    loc = loc_all.detach().to(torch.float32).contiguous()
+    conf = conf_all.detach().to(torch.float32).contiguous()
+    labels = torch.empty((B, max_per_img), dtype=torch.int64, device=dev)
+    scores = torch.empty((B, max_per_img), dtype=torch.float32, device=dev)
+    boxes = torch.empty((B, max_per_img, 4), dtype=torch.float32, device=dev)
+    cand = torch.empty((B, max_per_img), dtype=torch.int32, device=dev) if want_cand else None
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    work = _workspace("predict", dev, _lib.lib().ssdhot_predict_workspace_bytes(B, C, max_per_img))
+    with torch.cuda.device(dev):
+        rc = _lib.lib().ssdhot_predict(priors.priors.data_ptr(), P, loc.data_ptr(), conf.data_ptr(), B, C,
+                                       float(score_thresh), float(nms_thresh), int(max_per_img), 1 if class_agnostic else 0,
+                                       METRICS[metric], priors.variances[0], priors.variances[1],
+                                       float(priors.img_w), float(priors.img_h),
+                                       labels.data_ptr(), scores.data_ptr(), boxes.data_ptr(), _ptr(cand),
+                                       count.data_ptr(), work.data_ptr(), _stream(dev))
+    _lib.check(rc, "ssdhot_predict")
+    if want_cand:
+        return labels, scores, boxes, count, cand
+    return labels, scores, boxes, count
+
+
+@torch.no_grad()
+def predict(model, images: Optional[torch.Tensor], score_thresh: float = 0.2, nms_thresh: float = 0.5,
+            max_per_img: int = 100, class_agnostic: bool = False, pre_loc_all: Optional[torch.Tensor] = None,
+            pre_conf_all: Optional[torch.Tensor] = None, metric: str = "diou") -> List[Dict[str, torch.Tensor]]:
+    """Drop-in for mySSD.predict (SSD_from_scratch.py:338-476): List[Dict] with 'labels' i64[K],
+    'scores' f32[K], 'boxes' f32[K,4] pixel xyxy, K <= max_per_img, score-descending."""
+    if not (0.0 <= score_thresh < 1.0):
+        raise ValueError(f"Score threshold should be greater than 0 and less than 1, recieved {score_thresh}.")
+    if not (0.0 < nms_thresh < 1.0):
+        raise ValueError(f"NMS threshold should be greater than 0 and less than 1, recieved {nms_thresh}.")
+    if hasattr(model, "eval"):
+        model.eval()                                   # side effect of the reference (:375)
+    if (pre_loc_all is not None) and (pre_conf_all is not None):
+        loc_all, conf_all = pre_loc_all, pre_conf_all
+    else:
+        loc_all, conf_all = model(images)
+    if hasattr(model, "num_classes"):
+        assert conf_all.shape[-1] == model.num_classes and conf_all.shape[-1] >= 2
+    labels, scores, boxes, count = predict_padded(model, loc_all, conf_all, score_thresh, nms_thresh, max_per_img,
+                                                  class_agnostic, metric)
+    ks = count.tolist()                                # the one D2H of the call
+    return [{"labels": l[:k], "scores": s[:k], "boxes": b[:k]}
+            for l, s, b, k in zip(labels.unbind(0), scores.unbind(0), boxes.unbind(0), ks)]
+
+
+# ------------------------------------------------------------------------------------------------
+# patching the reference in place
+# ------------------------------------------------------------------------------------------------
+def patch(model=None, trainer_module=None):
+    """Route a reference `mySSD` instance and/or the imported `SSD_trainer` module through ssdhot:
+    model.encode_ssd / decode_ssd / iou_nms / predict and trainer.build_targets /
+    trainer.CELoss_w_neg_mining keep their signatures."""
+    import types
+    if model is not None:
+        model.encode_ssd = types.MethodType(lambda self, *a, **k: encode_ssd(self, *a, **k), model)
+        model.predict = types.MethodType(lambda self, *a, **k: predict(self, *a, **k), model)
+        model.decode_ssd = decode_ssd
+        model.iou_nms = iou_nms
+    if trainer_module is not None:
+        trainer_module.build_targets = build_targets
+        trainer_module.CELoss_w_neg_mining = CELoss_w_neg_mining
+    return model

@@ -1,0 +1,180 @@
+/*
+ * ssdhot.h -- C ABI of libssdhot.so, the B200 (sm_100a) implementation of the SSD300 multibox
+ * post-backbone hot path of ElliotBlackstone/automotive-ssd-object-detection.
+ *
+ * The reference has no FFI of its own: the boundary it offers is a set of Python callables
+ * (SURVEY.md section 8b).  Each entry point below replaces the device work behind one of them;
+ * the citation says which (SFS = SSD_from_scratch.py, TR = SSD_trainer.py, tv = torchvision/ops).
+ * INTEGRATION.md shows the ctypes stubs a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns all
+ *     buffers, nothing is allocated, freed or cached inside the library;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host
+ *     synchronisation and is safe to capture in a CUDA graph;
+ *   - return value: 0 = SSDHOT_OK, negative = ssdhot_status (bad argument), positive =
+ *     cudaError_t of the failed launch;
+ *   - thread-compatible: concurrent calls must use different streams and different output buffers;
+ *   - floating point is fp32 with IEEE round-to-nearest +,-,*,/ in the operation order of the
+ *     reference (no FMA contraction, no fast-math); labels are int64, masks are one byte per
+ *     element (torch.bool layout);
+ *   - P (number of priors) must be <= SSDHOT_MAX_PRIORS; the reference uses 8732.
+ */
+#ifndef SSDHOT_H_
+#define SSDHOT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SSDHOT_API __attribute__((visibility("default")))
+#else
+#define SSDHOT_API
+#endif
+
+#define SSDHOT_ABI_VERSION 1
+#define SSDHOT_MAX_PRIORS 10240   /* 8 CTAs x 256 threads x 5 priors per image cluster */
+#define SSDHOT_MAX_GT 2048        /* ground-truth boxes per image held in shared memory */
+#define SSDHOT_MAX_CLASSES 256
+
+typedef enum {
+    SSDHOT_OK = 0,
+    SSDHOT_ERR_NULL = -1,        /* a required pointer is NULL */
+    SSDHOT_ERR_SHAPE = -2,       /* a size is out of the supported range */
+    SSDHOT_ERR_VALUE = -3,       /* a scalar violates the reference's own validation */
+    SSDHOT_ERR_DEVICE = -4,      /* not an sm_100 device */
+    SSDHOT_ERR_ALIGN = -5        /* a pointer is not aligned as documented (16 B for [.,4] fp32) */
+} ssdhot_status;
+
+typedef void* ssdhot_stream_t;   /* cudaStream_t */
+
+/* metric used by the NMS predicates: the reference CODE uses DIoU (SFS:688); CIoU is offered
+ * because README.md:17 / BASELINE.json name it. */
+#define SSDHOT_METRIC_DIOU 0
+#define SSDHOT_METRIC_CIOU 1
+#define SSDHOT_METRIC_IOU 2
+
+SSDHOT_API int ssdhot_abi_version(void);
+SSDHOT_API const char* ssdhot_status_string(int status);
+/* number of kernels this library has launched so far in this process (bench.py gpu_launches) */
+SSDHOT_API unsigned long long ssdhot_launch_count(void);
+
+/* ---- a1: per-prior constants -------------------------------------------------------------
+ * priors_xyxy [P,4] = clamp(cxcywh -> xyxy, 0, 1) as registered at SFS:34-35
+ * (tv _box_convert.py:5-24); prior_aux [P,4] = (area, x centre, y centre, atan(w/h)) of the
+ * clamped box, the per-row constants of complete_box_iou (tv boxes.py:296, :470-471, :430). */
+SSDHOT_API int ssdhot_prior_tables(const float* priors_cxcywh, int P, float* priors_xyxy, float* prior_aux,
+                        ssdhot_stream_t stream);
+/* prior_aux only, from caller-owned (already clamped) xyxy priors such as mySSD.priors_xyxy. */
+SSDHOT_API int ssdhot_prior_aux(const float* priors_xyxy, int P, float* prior_aux, ssdhot_stream_t stream);
+
+/* ---- a2/a3: match + encode ----------------------------------------------------------------
+ * Replaces the per-image loop of build_targets (TR:525-545) around mySSD.encode_ssd
+ * (SFS:697-773): CIoU of every prior against the image's ground truth, forced best-prior
+ * match, best ground truth per prior, positives, centre-size offsets, class targets.
+ *   gt_boxes   [sumG,4] xyxy, divided in-kernel by (norm_w,norm_h,norm_w,norm_h) (TR:519,532);
+ *              pass 1,1 for already-normalised boxes (the encode_ssd signature)
+ *   gt_labels  [sumG] int64 foreground ids 0..C-2
+ *   gt_offsets [B+1] int32, image b owns rows gt_offsets[b] .. gt_offsets[b+1]
+ *   max_gt     host-known upper bound of boxes per image (<= SSDHOT_MAX_GT)
+ * Outputs (each may be NULL to skip it):
+ *   loc_t [B,P,4] (every prior, like encode_ssd; or only positives' rows when
+ *   loc_positives_only != 0, the other rows are left untouched), cls_t [B,P] int64,
+ *   pos_mask [B,P] bytes, matched_gt [B,P] int32 (index inside the image),
+ *   matched_cxcywh [B,P,4], n_pos [B] int32.
+ * An image whose box count exceeds max_gt sets bit 0 of *dev_flags (optional). */
+SSDHOT_API int ssdhot_match_encode(const float* priors_cxcywh, const float* priors_xyxy, const float* prior_aux, int P,
+                        const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
+                        int B, int max_gt, float norm_w, float norm_h,
+                        float iou_thresh, float var_center, float var_size,
+                        float* loc_t, int loc_positives_only, int64_t* cls_t, uint8_t* pos_mask,
+                        int32_t* matched_gt, float* matched_cxcywh, int32_t* n_pos,
+                        int32_t* dev_flags, ssdhot_stream_t stream);
+
+/* Ordered compaction loc_t[pos_mask] (TR:547): rows of loc_t [B,P,4] whose mask byte is set, in
+ * (image, prior) order, written to out[sum(n_pos),4].  n_pos [B] as written by
+ * ssdhot_match_encode. */
+SSDHOT_API int ssdhot_compact_rows(const float* loc_t, const uint8_t* pos_mask, const int32_t* n_pos, int B, int P,
+                        float* out, ssdhot_stream_t stream);
+
+/* ---- a4/a5: losses ------------------------------------------------------------------------
+ * Fused forward of the post-backbone training step (TR:92-117): matching as above, smooth-L1
+ * over positives (TR:108), softmax cross-entropy over positives plus the hardest
+ * k = min(int(ratio*n_pos) [int(ratio) if n_pos == 0], #negatives) negatives of each image
+ * (TR:577-598).  Nothing of shape [B,P] is materialised unless asked for.
+ *   sums [3] double, OVERWRITTEN: { sum smooth-L1, sum CE (positives + mined), sum n_pos } --
+ *   un-normalised, ready for one all-reduce; loss = sums[0..1] / max(sums[2], 1) (TR:105,600).
+ *   work: scratch of ssdhot_loss_workspace_bytes(B) bytes.
+ *   Optional, for the backward pass: sel_cls [B,P] int8 (-1 = prior not in the loss, else its
+ *   target class), matched_gt [B,P] int16 (positives only, -1 elsewhere), n_pos [B]. */
+SSDHOT_API unsigned long long ssdhot_loss_workspace_bytes(int B);
+SSDHOT_API int ssdhot_multibox_loss_fwd(const float* priors_cxcywh, const float* priors_xyxy, const float* prior_aux, int P,
+                             const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
+                             int B, int max_gt, float norm_w, float norm_h,
+                             const float* loc_all, const float* conf_all, int C,
+                             float iou_thresh, float var_center, float var_size, double neg_pos_ratio,
+                             double* sums, void* work, int8_t* sel_cls, int16_t* matched_gt, int32_t* n_pos,
+                             int32_t* dev_flags, ssdhot_stream_t stream);
+
+/* CELoss_w_neg_mining (TR:551-600) with the targets given: sums[1] and sums[2] are written
+ * (sums[0] = 0).  cls_t [B,P] int64, pos_mask [B,P] bytes. */
+SSDHOT_API int ssdhot_mined_ce_fwd(const float* conf_all, const int64_t* cls_t, const uint8_t* pos_mask,
+                        int B, int P, int C, double neg_pos_ratio,
+                        double* sums, void* work, int8_t* sel_cls, ssdhot_stream_t stream);
+
+/* Backward of the two losses w.r.t. the head outputs (autograd of TR:108 and TR:577-600):
+ *   grad_conf [B,P,C] = scale_conf * (softmax(conf) - onehot(sel_cls)) where sel_cls >= 0, else 0
+ *   grad_loc  [B,P,4] = scale_loc * clamp(loc - loc_t, -1, 1) on positives, else 0
+ * scale_* = upstream gradient / max(total positives, 1), read from scales [2] (device, double).
+ * Positives' loc targets are re-encoded from matched_gt (int16) and the ground truth.
+ * Either gradient may be NULL. */
+SSDHOT_API int ssdhot_multibox_loss_bwd(const float* priors_cxcywh, int P,
+                             const float* gt_boxes, const int32_t* gt_offsets, int B,
+                             float norm_w, float norm_h,
+                             const float* loc_all, const float* conf_all, int C,
+                             float var_center, float var_size,
+                             const int8_t* sel_cls, const int16_t* matched_gt, const double* scales,
+                             float* grad_loc, float* grad_conf, ssdhot_stream_t stream);
+
+/* ---- a6: decode ---------------------------------------------------------------------------
+ * mySSD.decode_ssd (SFS:776-800): out [M,4] cxcywh from loc [M,4] and priors [M,4]. */
+SSDHOT_API int ssdhot_decode(const float* loc, const float* priors_cxcywh, int M, float var_center, float var_size,
+                  float* out, ssdhot_stream_t stream);
+
+/* ---- a8: greedy NMS -----------------------------------------------------------------------
+ * mySSD.iou_nms (SFS:664-692) for `n_sets` independent box sets stored back to back:
+ * set s owns boxes[set_offsets[s] .. set_offsets[s+1]) (xyxy) and the matching scores.
+ * A box is dropped iff NOT(metric(kept, box) <= thresh) for an earlier kept box, boxes visited by
+ * descending score, equal scores by ascending index.  keep [total] int64 receives, per set and
+ * starting at set_offsets[s], the surviving indices (relative to the set) in that order;
+ * keep_count [n_sets] int32 their number.  max_keep > 0 stops each set after that many survivors.
+ * work: ssdhot_nms_workspace_bytes(total) bytes. */
+SSDHOT_API unsigned long long ssdhot_nms_workspace_bytes(long long total_boxes);
+SSDHOT_API int ssdhot_nms(const float* boxes, const float* scores, const int32_t* set_offsets, int n_sets,
+               long long total_boxes, int max_set_size, float thresh, int metric, int max_keep,
+               int64_t* keep, int32_t* keep_count, void* work, ssdhot_stream_t stream);
+
+/* ---- a7: post-process ---------------------------------------------------------------------
+ * mySSD.predict after the forward pass (SFS:388-476): softmax, strict score threshold on every
+ * (prior, foreground class) pair, decode + clamp + scale to pixels of the survivors, greedy
+ * NMS per class (or over all classes when class_agnostic != 0), global score sort and
+ * truncation to max_per_img.  Outputs are padded to max_per_img per image:
+ *   out_labels [B,max_per_img] int64 (0-based foreground id), out_scores [B,max_per_img],
+ *   out_boxes [B,max_per_img,4] pixel xyxy, out_cand [B,max_per_img] int32 (optional: flat
+ *   candidate id prior*(C-1)+class), out_count [B] int32 valid entries per image.
+ * work: ssdhot_predict_workspace_bytes(B, C, max_per_img) bytes. */
+SSDHOT_API unsigned long long ssdhot_predict_workspace_bytes(int B, int C, int max_per_img);
+SSDHOT_API int ssdhot_predict(const float* priors_cxcywh, int P, const float* loc_all, const float* conf_all,
+                   int B, int C, float score_thresh, float nms_thresh, int max_per_img,
+                   int class_agnostic, int metric, float var_center, float var_size,
+                   float img_w, float img_h,
+                   int64_t* out_labels, float* out_scores, float* out_boxes, int32_t* out_cand,
+                   int32_t* out_count, void* work, ssdhot_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSDHOT_H_ */
