@@ -11,6 +11,9 @@
 // thread resolves the tile serially with bit operations.  The walk stops as soon as max_keep
 // boxes survive, which is lossless for the reference's post-NMS `keep[:max_per_img]`
 // (SSD_from_scratch.py:465) because survivors are produced in score order.
+#include <map>
+#include <mutex>
+
 #include "boxmath.cuh"
 
 namespace ssdhot {
@@ -391,10 +394,19 @@ constexpr size_t kMaxDynSmem = 227 * 1024 - sizeof(UnitShared) - 1024;
 
 template <typename K>
 static int set_smem(K kern, size_t bytes) {
+    // one static per kernel instantiation (K is a distinct function type only per signature, so key
+    // on the pointer): the opt-in is sticky, so it is raised once and never inside a graph capture
     if (bytes > kMaxDynSmem) return SSDHOT_ERR_SHAPE;
+    static std::mutex mu;
+    static std::map<const void*, size_t> configured;
     if (bytes > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e != cudaSuccess) return (int)e;
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& have = configured[reinterpret_cast<const void*>(kern)];
+        if (bytes > have) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+            if (e != cudaSuccess) return (int)e;
+            have = kMaxDynSmem;
+        }
     }
     return SSDHOT_OK;
 }

@@ -560,9 +560,11 @@ static int launch_train(const TrainParams& prm, cudaStream_t stream) {
     if (cs * SLOTS < prm.P) return SSDHOT_ERR_SHAPE;
     const size_t dyn = smem_bytes(prm.max_gt > 0 ? prm.max_gt : 1);
     auto kern = train_kernel<MODE, CT>;
-    if (dyn > 48 * 1024) {
+    static size_t configured = 0;      // per instantiation; sticky opt-in, raised outside graph capture
+    if (dyn > 48 * 1024 && dyn > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) return (int)e;
+        configured = dyn;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(prm.B * cs));

@@ -11,6 +11,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
+from . import dist as _dist
 from .priors import PriorSet
 
 METRICS = {"diou": 0, "ciou": 1, "iou": 2}
@@ -214,7 +215,7 @@ class _FusedLoss(torch.autograd.Function):
         _lib.check(rc, "ssdhot_multibox_loss_fwd")
         if group is not None:
             # the only exchange of the sharded path: [sum smooth-L1, sum CE, sum positives]
-            torch.distributed.all_reduce(sums, op=torch.distributed.ReduceOp.SUM, group=group)
+            _dist.combine_sums(sums, None if group is True else group)
         total = sums[2].clamp_min(1.0)
         if need_grad:
             ctx.save_for_backward(loc, conf, sel, matched, total, packed.boxes, packed.offsets)
@@ -246,8 +247,9 @@ def multibox_loss(model, loc_all: torch.Tensor, conf_all: torch.Tensor, targets,
                   neg_pos_ratio: float = 3.0, H: int = 300, W: int = 300, group=None, return_sums: bool = False):
     """The whole post-backbone training step of SSD_train_step (SSD_trainer.py:92-117) in one
     launch: -> (batch_loc_loss, batch_conf_loss), 0-d fp32, differentiable w.r.t. loc_all/conf_all.
-    With `group` (a torch.distributed process group) the batch is this rank's shard: the three
-    partial sums are all-reduced so every rank returns the global-batch losses."""
+    With `group` (a torch.distributed process group, or True for the default group) the batch is
+    this rank's shard: the three partial sums are all-reduced so every rank returns the
+    global-batch losses."""
     if not (0.0 < iou_thresh < 1.0):
         raise ValueError(f"Score threshold should be greater than 0 and less than 1, recieved {iou_thresh}.")
     priors = PriorSet.of(model)

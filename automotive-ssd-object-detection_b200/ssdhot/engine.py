@@ -1,0 +1,98 @@
+"""Pre-planned execution of the hot path: static buffers, raw C-ABI calls, optional CUDA graph.
+
+`HotPathStep` is the allocation-free form of the post-backbone part of the reference's eval step
+(SSD_test_step, SSD_trainer.py:214-256): targets + both losses, then `predict`.  All outputs and
+workspaces are allocated once; `run()` issues exactly the library's kernels on the current
+stream (or replays them from a captured CUDA graph), with no host synchronisation.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from . import dist as _dist
+from .api import METRICS, PackedTargets
+from .priors import PriorSet
+
+
+class HotPathStep:
+    def __init__(self, priors: PriorSet, batch: int, n_classes: int, iou_thresh: float = 0.5,
+                 neg_pos_ratio: float = 3.0, score_thresh: float = 0.01, nms_thresh: float = 0.45,
+                 max_per_img: int = 200, class_agnostic: bool = False, metric: str = "diou",
+                 norm_wh=(300.0, 300.0), train_half: bool = True, infer_half: bool = True):
+        self.ps, self.B, self.C = priors, int(batch), int(n_classes)
+        self.iou_thresh, self.ratio = float(iou_thresh), float(neg_pos_ratio)
+        self.score_thresh, self.nms_thresh = float(score_thresh), float(nms_thresh)
+        self.max_per_img, self.agnostic, self.metric = int(max_per_img), bool(class_agnostic), METRICS[metric]
+        self.norm_wh = (float(norm_wh[0]), float(norm_wh[1]))
+        self.train_half, self.infer_half = train_half, infer_half
+        dev = priors.device
+        L = _lib.lib()
+        self.sums = torch.zeros((3,), dtype=torch.float64, device=dev)
+        self.loss_work = torch.empty((int(L.ssdhot_loss_workspace_bytes(self.B)),), dtype=torch.uint8, device=dev)
+        self.pred_work = torch.empty((int(L.ssdhot_predict_workspace_bytes(self.B, self.C, self.max_per_img)),),
+                                     dtype=torch.uint8, device=dev)
+        m = self.max_per_img
+        self.labels = torch.zeros((self.B, m), dtype=torch.int64, device=dev)
+        self.scores = torch.zeros((self.B, m), dtype=torch.float32, device=dev)
+        self.boxes = torch.zeros((self.B, m, 4), dtype=torch.float32, device=dev)
+        self.count = torch.zeros((self.B,), dtype=torch.int32, device=dev)
+        self.n_pos = torch.zeros((self.B,), dtype=torch.int32, device=dev)
+        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+
+    # -- raw launches -------------------------------------------------------------------------
+    def launch_loss(self, loc: torch.Tensor, conf: torch.Tensor, gt: PackedTargets, stream: int) -> None:
+        ps = self.ps
+        rc = _lib.lib().ssdhot_multibox_loss_fwd(
+            ps.priors.data_ptr(), ps.priors_xyxy.data_ptr(), ps.aux.data_ptr(), ps.P,
+            gt.boxes.data_ptr(), gt.labels.data_ptr(), gt.offsets.data_ptr(), self.B, gt.max_gt,
+            self.norm_wh[0], self.norm_wh[1], loc.data_ptr(), conf.data_ptr(), self.C,
+            self.iou_thresh, ps.variances[0], ps.variances[1], self.ratio,
+            self.sums.data_ptr(), self.loss_work.data_ptr(), None, None, self.n_pos.data_ptr(), None, stream)
+        _lib.check(rc, "ssdhot_multibox_loss_fwd")
+
+    def launch_predict(self, loc: torch.Tensor, conf: torch.Tensor, stream: int) -> None:
+        ps = self.ps
+        rc = _lib.lib().ssdhot_predict(
+            ps.priors.data_ptr(), ps.P, loc.data_ptr(), conf.data_ptr(), self.B, self.C,
+            self.score_thresh, self.nms_thresh, self.max_per_img, 1 if self.agnostic else 0, self.metric,
+            ps.variances[0], ps.variances[1], float(ps.img_w), float(ps.img_h),
+            self.labels.data_ptr(), self.scores.data_ptr(), self.boxes.data_ptr(), None,
+            self.count.data_ptr(), self.pred_work.data_ptr(), stream)
+        _lib.check(rc, "ssdhot_predict")
+
+    def run(self, loc: torch.Tensor, conf_train: torch.Tensor, conf_infer: torch.Tensor, gt: PackedTargets,
+            use_graph: bool = False) -> None:
+        """Both halves on the current stream.  With use_graph the launches are captured once per
+        distinct set of input buffers and replayed afterwards."""
+        dev = self.ps.device
+        if not use_graph:
+            s = torch.cuda.current_stream(dev).cuda_stream
+            if self.train_half:
+                self.launch_loss(loc, conf_train, gt, s)
+            if self.infer_half:
+                self.launch_predict(loc, conf_infer, s)
+            return
+        key = (loc.data_ptr(), conf_train.data_ptr(), conf_infer.data_ptr(), gt.boxes.data_ptr(), gt.max_gt)
+        g = self._graphs.get(key)
+        if g is None:
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self.run(loc, conf_train, conf_infer, gt)            # warm (sets smem attributes)
+                side.synchronize()
+                with torch.cuda.graph(g, stream=side):
+                    self.run(loc, conf_train, conf_infer, gt)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self._graphs[key] = g
+        g.replay()
+
+    def losses(self, group=None):
+        """(loc_loss, conf_loss) of the last run; all-reduces the three sums first when sharded."""
+        sums = self.sums.clone()
+        if group is not None:
+            _dist.combine_sums(sums, None if group is True else group)
+        return _dist.losses_from_sums(sums)

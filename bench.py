@@ -1,0 +1,360 @@
+"""bench.py -- images/s of the SSD300 multibox post-backbone hot path (BASELINE.json metric).
+
+A "step" is the post-backbone part of the reference's eval step (SSD_test_step,
+SSD_trainer.py:214-256) over one batch of 256 synthetic images per GPU (BASELINE cfg 3):
+    (i)  match + mined loss : build_targets + smooth-L1 + CELoss_w_neg_mining   (TR:92-117)
+    (ii) decode + NMS       : predict(score 0.01, nms 0.45, max 200)            (SFS:388-476)
+`value` = images / s over both halves with inputs resident in HBM; `parts` gives each half.
+`e2e` is the same step through the drop-in Python API from pinned HOST buffers, with the
+host->device copies of the head outputs / ground truth and the device->host read of the losses
+and detections inside the timed region.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+N > 1: launched by torchrun, one rank per GPU; each rank owns 256 images (weak scaling) and the
+only collective is the all-reduce of the three loss sums.
+`--impl reference` times the oracle port of the reference (eager torch CPU ops, per-image
+Python loops exactly like the reference) on the host cores for the same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "automotive-ssd-object-detection_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+BATCH = 256            # images per GPU (BASELINE.json metric: "at bs=256")
+CFG = 3
+N_SETS = 4             # rotating input sets: 4 x 89.5 MB > 126 MB L2, so no step re-reads a hot L2
+P, C = 8732, 6
+METRIC = "images/s for match+mined loss and decode+DIoU-NMS at bs=256 per GPU"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Polls SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.005):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.stop_flag = index, period_s, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def result(self):
+        self.stop_flag = True
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(cfg, pri, pri_xyxy, n_train: int, n_pred: int):
+    """One bounded sample of the workload on the CPU: returns (seconds train half, seconds predict
+    half) for n_train / n_pred images.  The reference loops per image (TR:525, SFS:397), so its
+    images/s does not depend on the batch size."""
+    from oracle import ssd_oracle as O
+    t0 = time.perf_counter()
+    O.train_half(pri, pri_xyxy, cfg["loc_all"][:n_train], cfg["conf_train"][:n_train], cfg["targets"][:n_train],
+                 cfg["iou_thresh"], cfg["ratio"])
+    t1 = time.perf_counter()
+    O.postprocess(pri, cfg["loc_all"][:n_pred], cfg["conf_infer"][:n_pred], cfg["score_thresh"], cfg["nms_thresh"],
+                  cfg["max_per_img"], False)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def cpu_images_per_s(t_train, n_train, t_pred, n_pred):
+    return 1.0 / (t_train / n_train + t_pred / n_pred)
+
+
+def run_reference(args):
+    from ssdhot import synth
+    from oracle import ssd_oracle as O
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_train, n_pred = 16, 2
+    cfg = synth.config(CFG, batch=max(n_train, n_pred))
+    pri, pri_xyxy = O.prior_tables()
+    for _ in range(max(args.warmup, 1) if args.warmup < 3 else 1):      # the CPU path has no clocks to warm; 1 pass pages code in
+        cpu_reference_step(cfg, pri, pri_xyxy, 2, 1)
+    # bound the run: size the per-step sample from one probe so K steps end within ~3 minutes
+    probe = cpu_reference_step(cfg, pri, pri_xyxy, 2, 1)
+    per_step_budget = 150.0 / max(args.steps, 1)
+    n_pred = max(1, min(n_pred, int(per_step_budget * 0.7 / max(probe[1], 1e-3))))
+    n_train = max(2, min(n_train, int(per_step_budget * 0.3 / max(probe[0] / 2, 1e-4))))
+    tt = tp = 0.0
+    t_begin = time.perf_counter()
+    for _ in range(args.steps):
+        a, b = cpu_reference_step(cfg, pri, pri_xyxy, n_train, n_pred)
+        tt += a
+        tp += b
+    wall = time.perf_counter() - t_begin
+    value = cpu_images_per_s(tt, n_train * args.steps, tp, n_pred * args.steps)
+    sample = f"{n_train} images match+loss and {n_pred} images predict per step (per-image loop: images/s is batch independent)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg3: B=256/GPU eval-step post-backbone path (match+mined loss, then predict "
+                               "thr 0.01 / nms 0.45 / max 200), P=8732, C=6, G~U{1..20}", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample,
+                         "parts": {"match_loss_images_per_s": n_train * args.steps / tt,
+                                   "decode_nms_images_per_s": n_pred * args.steps / tp}},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ssdhot", choices=["ssdhot", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying a CUDA graph")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    import ssdhot
+    from ssdhot import dist as D, synth
+    from ssdhot.engine import HotPathStep
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (ssdhot has no CPU fallback); use --impl reference for the CPU arm")
+    rank, world, local = D.init_from_env()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    group = True if world > 1 else None
+
+    # ---- synthetic inputs: N_SETS independent batches per rank, resident in HBM -------------------
+    spec = None
+    sets = []
+    host_sets = []
+    for i in range(N_SETS):
+        cfg = synth.config(CFG, batch=BATCH, seed_offset=rank * N_SETS + i)
+        spec = spec or {k: cfg[k] for k in ("iou_thresh", "ratio", "score_thresh", "nms_thresh", "max_per_img")}
+        host_sets.append(cfg)
+        sets.append(dict(loc=cfg["loc_all"].to(dev), conf_t=cfg["conf_train"].to(dev), conf_i=cfg["conf_infer"].to(dev),
+                         gt=ssdhot.pack_targets(cfg["targets"], dev)))
+    ps = ssdhot.PriorSet.default(dev)
+    step = HotPathStep(ps, BATCH, C, spec["iou_thresh"], spec["ratio"], spec["score_thresh"], spec["nms_thresh"],
+                       spec["max_per_img"])
+    use_graph = not args.no_graph
+
+    def one_step(i):
+        s = sets[i % N_SETS]
+        step.run(s["loc"], s["conf_t"], s["conf_i"], s["gt"], use_graph=use_graph)
+        if group is not None:
+            D.combine_sums(step.sums)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # launches per step (counted once, without the graph)
+    s0 = sets[0]
+    torch.cuda.synchronize(dev)
+    n0 = ssdhot.launch_count()
+    step.run(s0["loc"], s0["conf_t"], s0["conf_i"], s0["gt"], use_graph=False)
+    launches_per_step = ssdhot.launch_count() - n0
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        one_step(i)
+    e1.record()
+    barrier()
+    clocks = sampler.result()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    ms_per_step = ms_total / args.steps
+    value = BATCH * world * args.steps / (ms_total / 1e3)
+
+    # ---- per-half kernel time (CUDA events around each half, same rotation, direct launches) -------
+    def time_half(train: bool, iters: int):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        st = torch.cuda.current_stream(dev).cuda_stream
+        for i in range(3):
+            s = sets[i % N_SETS]
+            step.launch_loss(s["loc"], s["conf_t"], s["gt"], st) if train else step.launch_predict(s["loc"], s["conf_i"], st)
+        torch.cuda.synchronize(dev)
+        for i, (a, b) in enumerate(evs):
+            s = sets[i % N_SETS]
+            other = sets[(i + 1) % N_SETS]
+            a.record()
+            step.launch_loss(s["loc"], s["conf_t"], s["gt"], st) if train else step.launch_predict(s["loc"], s["conf_i"], st)
+            b.record()
+            _ = other
+        torch.cuda.synchronize(dev)
+        return statistics.mean(a.elapsed_time(b) for a, b in evs)
+
+    iters = max(8, min(args.steps, 64))
+    ms_loss = time_half(True, iters)
+    ms_pred = time_half(False, iters)
+    mean_g = statistics.mean(float(t["boxes"].shape[0]) for c in host_sets for t in c["targets"])
+    k_mean = float(step.count.float().mean().item())
+    bytes_loss = BATCH * (349296 + 24 * mean_g + 12)            # SURVEY.md 8d, path (i)
+    bytes_pred = BATCH * (349296 + 28 * k_mean + 4)             # SURVEY.md 8d, path (ii)
+    peak, peak_src = peaks()
+    dom_is_pred = ms_pred >= ms_loss
+    dom_ms, dom_bytes = (ms_pred, bytes_pred) if dom_is_pred else (ms_loss, bytes_loss)
+    roofline = {
+        "bound": "hbm", "kernel": "predict_unit_kernel (decode+threshold+rank+NMS)" if dom_is_pred else
+        "train_kernel<FUSED> (match+encode+mined loss)",
+        "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+        "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+        "parts": {
+            "match_loss": {"ms": ms_loss, "algorithmic_bytes": bytes_loss, "achieved": bytes_loss / (ms_loss * 1e-3) / 1e9,
+                           "frac": bytes_loss / (ms_loss * 1e-3) / 1e9 / peak, "images_per_s": BATCH / (ms_loss * 1e-3)},
+            "decode_nms": {"ms": ms_pred, "algorithmic_bytes": bytes_pred, "achieved": bytes_pred / (ms_pred * 1e-3) / 1e9,
+                           "frac": bytes_pred / (ms_pred * 1e-3) / 1e9 / peak, "images_per_s": BATCH / (ms_pred * 1e-3)},
+        },
+    }
+
+    # ---- end to end through the drop-in API, host buffers ------------------------------------------
+    pinned = []
+    for cfg in host_sets[:2]:
+        pinned.append(dict(loc=cfg["loc_all"].pin_memory(), conf_t=cfg["conf_train"].pin_memory(),
+                           conf_i=cfg["conf_infer"].pin_memory(), targets=cfg["targets"]))
+    gt_bytes = sum(t["boxes"].numel() * 4 + t["labels"].numel() * 8 for t in host_sets[0]["targets"]) + 4 * (BATCH + 1)
+    h2d = BATCH * P * (4 + C + C) * 4 + gt_bytes
+    d2h_holder = {}
+
+    def e2e_step(i):
+        h = pinned[i % len(pinned)]
+        loc = h["loc"].to(dev, non_blocking=True)
+        conf_t = h["conf_t"].to(dev, non_blocking=True)
+        conf_i = h["conf_i"].to(dev, non_blocking=True)
+        l_loc, l_conf = ssdhot.multibox_loss(ps, loc, conf_t, h["targets"], spec["iou_thresh"], spec["ratio"], group=group)
+        labels, scores, boxes, count = ssdhot.predict_padded(ps, loc, conf_i, spec["score_thresh"], spec["nms_thresh"],
+                                                             spec["max_per_img"])
+        out = (torch.stack((l_loc, l_conf)).cpu(), labels.cpu(), scores.cpu(), boxes.cpu(), count.cpu())
+        d2h_holder["bytes"] = sum(t.numel() * t.element_size() for t in out)
+        return out
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize(dev)
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = BATCH * world * e2e_steps / float(t_e2e.item())
+
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ---------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        from oracle import ssd_oracle as O
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        pri_c, xyxy_c = O.prior_tables()
+        cfg = host_sets[0]
+        cpu_reference_step(cfg, pri_c, xyxy_c, 2, 1)
+        n_train, n_pred = 32, 4
+        a, b = cpu_reference_step(cfg, pri_c, xyxy_c, n_train, n_pred)
+        cpu = {"value": cpu_images_per_s(a, n_train, b, n_pred), "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"{n_train} images match+loss ({a:.2f} s) + {n_pred} images predict ({b:.2f} s), oracle port of the "
+                         "reference's eager per-image loop, torch CPU threads = cores",
+               "parts": {"match_loss_images_per_s": n_train / a, "decode_nms_images_per_s": n_pred / b}}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg3: B=256/GPU eval-step post-backbone path (match+mined loss, then predict thr 0.01 / "
+                                   "nms 0.45 / max 200), P=8732, C=6, G~U{1..20}",
+                       "global_batch": BATCH * world, "per_gpu_batch": BATCH,
+                       "l2": f"inputs rotate over {N_SETS} sets of 89.5 MB (> 126 MB L2) so no step re-reads a warm L2",
+                       "cuda_graph": use_graph, "parallelism": f"image-sharded x{world}, all-reduce of 3 doubles"},
+            "parts": {"match_loss_images_per_s": BATCH * world / (ms_loss * 1e-3),
+                      "decode_nms_images_per_s": BATCH * world / (ms_pred * 1e-3)},
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h_holder.get("bytes", 0), "steps": e2e_steps,
+                    "api": "ssdhot.multibox_loss + ssdhot.predict_padded from pinned host tensors"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

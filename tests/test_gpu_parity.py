@@ -1,0 +1,395 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`).  Every call goes through the C ABI of
+libssdhot.so (ctypes); the oracle is only the checker.
+
+Two oracles are used:
+  * the DEVICE-MATCHED oracle -- oracle/ssd_oracle.py run on CUDA tensors (eager torch-CUDA:
+    IEEE +,-,*,/ and libdevice atanf/expf/logf).  ssdhot must equal it BIT FOR BIT: indices,
+    masks, keep lists AND every float (targets, boxes, scores);
+  * the reference itself (CPU) through the golden fixtures of tests/golden/: indices, masks and
+    keep lists must be identical; floats within 1e-5 relative (CPU SLEEF vs CUDA libdevice
+    transcendentals differ in the last bit -- SURVEY.md section 7, hard part 2).
+"""
+import numpy as np
+import pytest
+import torch
+
+import _util as U
+from oracle import ssd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5                      # north_star: losses and decoded boxes within 1e-5 relative in fp32
+BOX_ATOL = 1e-5 * 300.0          # boxes are pixel coordinates of a 300-px image
+
+
+@pytest.fixture(scope="module")
+def env():
+    import ssdhot
+    dev = torch.device("cuda:0")
+    pri, pri_xyxy = O.prior_tables(dev)
+    ps = ssdhot.PriorSet.default(dev)
+    return dict(ssdhot=ssdhot, dev=dev, pri=pri, pri_xyxy=pri_xyxy, ps=ps)
+
+
+def to_dev(targets, dev):
+    return [{k: v.to(dev) for k, v in t.items()} for t in targets]
+
+
+def bit_equal(a, b):
+    a, b = a.detach().cpu(), b.detach().cpu()
+    if a.shape != b.shape:
+        return False
+    if a.is_floating_point():
+        return bool(((a == b) | (torch.isnan(a) & torch.isnan(b))).all())
+    return bool((a == b).all())
+
+
+def close(a, b, rtol=RTOL, atol=1e-6):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    nan = torch.isnan(a) & torch.isnan(b)
+    return a.shape == b.shape and bool((((a - b).abs() <= atol + rtol * b.abs()) | nan).all())
+
+
+# ------------------------------------------------------------------------------------------------
+def test_library_is_native_and_loaded(env):
+    s = env["ssdhot"]
+    assert s.lib().ssdhot_abi_version() == 1
+    before = s.launch_count()
+    s.PriorSet.default(env["dev"])
+    assert s.launch_count() == before + 1
+
+
+def test_prior_tables_bitwise(env):
+    ps, pri, pri_xyxy = env["ps"], env["pri"], env["pri_xyxy"]
+    assert U.sha(ps.priors) == O.PRIORS_SHA256 and U.sha(ps.priors_xyxy) == O.PRIORS_XYXY_SHA256
+    w, h = pri_xyxy[:, 2] - pri_xyxy[:, 0], pri_xyxy[:, 3] - pri_xyxy[:, 1]
+    assert bit_equal(ps.aux[:, 0], w * h)
+    assert bit_equal(ps.aux[:, 1], (pri_xyxy[:, 0] + pri_xyxy[:, 2]) / 2)
+    assert bit_equal(ps.aux[:, 2], (pri_xyxy[:, 1] + pri_xyxy[:, 3]) / 2)
+    assert bit_equal(ps.aux[:, 3], torch.atan(w / h))
+    # a PriorSet built from caller-owned buffers (the reference model's) gives the same tables
+    ps2 = env["ssdhot"].PriorSet(pri, pri_xyxy)
+    assert bit_equal(ps2.aux, ps.aux)
+
+
+TRAIN = ["train_cfg1.npz", "train_cfg2.npz", "train_cfg2_thr04.npz", "train_cfg5_b2.npz", "train_edges.npz"]
+
+
+@pytest.mark.parametrize("name", TRAIN)
+def test_match_encode(env, name):
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    g = U.load(name)
+    targets, _, _ = U.train_inputs(g)
+    thr = float(g["iou_thresh"])
+    tg = to_dev(targets, dev)
+    # device-matched oracle: everything bit for bit, negatives' targets included
+    pos_o, locpm_o, cls_o, locd_o = O.batch_targets(env["pri"], env["pri_xyxy"], tg, 300, 300, thr, dense=True)
+    r = s.match_encode_batch(ps, s.pack_targets(targets, dev), thr, (300, 300), want_loc="all",
+                             want_matched_idx=True, want_matched_box=True)
+    assert bit_equal(r["pos_mask"], pos_o) and bit_equal(r["cls_t"], cls_o) and bit_equal(r["loc_t"], locd_o)
+    assert bit_equal(r["n_pos"].long(), pos_o.sum(1))
+    for b, t in enumerate(tg):
+        unit = t["boxes"] / torch.tensor([300.0] * 4, device=dev) if t["boxes"].numel() else t["boxes"].new_zeros((0, 4))
+        e = O.match_encode(env["pri"], env["pri_xyxy"], unit, t["labels"], thr, return_match=True)
+        assert bit_equal(r["matched_gt"][b].long(), e[4]), f"matched index, image {b}"
+        assert bit_equal(r["matched_cxcywh"][b], e[3])
+        if b >= 3:
+            break
+    # the reference itself (CPU golden): indices identical, offsets within 1e-5
+    assert bit_equal(r["pos_mask"], U.unpack_bits(g["pos_bits"], 8732))
+    assert bit_equal(r["cls_t"], torch.from_numpy(g["cls_t"].astype(np.int64)))
+    assert bit_equal(r["n_pos"].long(), torch.from_numpy(g["n_pos"]))
+    assert close(r["loc_t"][0], torch.from_numpy(g["enc0_loc"]), atol=1e-5)
+    assert close(r["matched_cxcywh"][0], torch.from_numpy(g["enc0_match"]))
+    # drop-in build_targets (SSD_trainer.py:491): same three outputs, same dtypes
+    pm, lpm, ct = s.build_targets(ps, tg, 300, 300, thr, "cuda")
+    assert pm.dtype == torch.bool and ct.dtype == torch.int64 and lpm.dtype == torch.float32
+    assert bit_equal(pm, pos_o) and bit_equal(ct, cls_o) and bit_equal(lpm, locpm_o)
+    assert close(lpm, torch.from_numpy(g["loc_t_pm"]), atol=1e-5)
+
+
+def test_encode_ssd_dropin(env):
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    g = U.load("train_cfg1.npz")
+    targets, _, _ = U.train_inputs(g)
+    unit = (targets[0]["boxes"] / torch.tensor([300.0] * 4)).to(dev)
+    lab = targets[0]["labels"].to(dev)
+    got = s.encode_ssd(ps, unit, lab, iou_thresh=0.5)
+    want = O.match_encode(env["pri"], env["pri_xyxy"], unit, lab, 0.5)
+    for a, b in zip(got, want):
+        assert a.dtype == b.dtype and bit_equal(a, b)
+    # no ground truth: all-zero outputs (SSD_from_scratch.py:731-736)
+    got = s.encode_ssd(ps, unit[:0], lab[:0])
+    assert all(int(x.abs().sum()) == 0 for x in got) and got[2].dtype == torch.bool and got[0].shape == (8732, 4)
+    with pytest.raises(ValueError):
+        s.encode_ssd(ps, unit, lab, background_class=1)
+
+
+@pytest.mark.parametrize("name", TRAIN)
+def test_losses(env, name):
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    g = U.load(name)
+    targets, loc_all, conf = U.train_inputs(g)
+    thr, ratio = float(g["iou_thresh"]), float(g["ratio"])
+    tg, lg, cg = to_dev(targets, dev), loc_all.to(dev), conf.to(dev)
+    pos_o, locpm_o, cls_o = O.batch_targets(env["pri"], env["pri_xyxy"], tg, 300, 300, thr)
+    o_loc, n_img, total = O.loc_loss(lg, pos_o, locpm_o)
+    o_conf = O.mined_ce_loss(cg, cls_o, pos_o, n_img, total, ratio)
+    l_loc, l_conf, sums = s.multibox_loss(ps, lg, cg, targets, thr, ratio, return_sums=True)
+    assert l_loc.dtype == torch.float32 and l_loc.dim() == 0
+    assert float(sums[2]) == float(n_img.sum())
+    for got, dev_o, gold in ((l_loc, o_loc, g["loc_loss"]), (l_conf, o_conf, g["conf_loss"])):
+        assert abs(got.item() - dev_o.item()) <= RTOL * abs(dev_o.item())
+        assert abs(got.item() - float(gold)) <= RTOL * abs(float(gold))
+    # drop-in CELoss_w_neg_mining (SSD_trainer.py:551) with the reference's own argument list
+    c2 = s.CELoss_w_neg_mining(cg, cls_o, pos_o, n_img, total, ratio)
+    assert abs(c2.item() - float(g["conf_loss"])) <= RTOL * abs(float(g["conf_loss"]))
+    l2 = s.smooth_l1_positive_loss(lg, pos_o, locpm_o, total)
+    assert abs(l2.item() - float(g["loc_loss"])) <= RTOL * abs(float(g["loc_loss"]))
+
+
+@pytest.mark.parametrize("ratio", [3.0, 0.0, 0.4, 1e6])
+def test_mining_budget_edges(env, ratio):
+    """int() truncation, the n_pos == 0 rule, k == 0 and k >= #negatives (SSD_trainer.py:585-596)."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    g = U.load("train_edges.npz")
+    targets, loc_all, conf = U.train_inputs(g)
+    tg, lg, cg = to_dev(targets, dev), loc_all.to(dev), conf.to(dev)
+    pos_o, locpm_o, cls_o = O.batch_targets(env["pri"], env["pri_xyxy"], tg, 300, 300, 0.5)
+    _, n_img, total = O.loc_loss(lg, pos_o, locpm_o)
+    want = O.mined_ce_loss(cg, cls_o, pos_o, n_img, total, ratio)
+    got = s.CELoss_w_neg_mining(cg, cls_o, pos_o, n_img, total, ratio)
+    assert abs(got.item() - want.item()) <= RTOL * max(abs(want.item()), 1e-12)
+    _, fused = s.multibox_loss(ps, lg, cg, targets, 0.5, ratio)
+    assert abs(fused.item() - want.item()) <= RTOL * max(abs(want.item()), 1e-12)
+
+
+def test_mining_with_massive_ties(env):
+    """All logits equal: every CE value ties; the sum is tie-invariant and the backward mask takes
+    the lowest prior indices (documented tie rule)."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    g = U.load("train_cfg1.npz")
+    targets, loc_all, _ = U.train_inputs(g)
+    conf = torch.zeros((1, 8732, 6), device=dev, requires_grad=True)
+    lg = loc_all.to(dev)
+    tg = to_dev(targets, dev)
+    pos_o, locpm_o, cls_o = O.batch_targets(env["pri"], env["pri_xyxy"], tg, 300, 300, 0.5)
+    _, n_img, total = O.loc_loss(lg, pos_o, locpm_o)
+    want = O.mined_ce_loss(conf.detach(), cls_o, pos_o, n_img, total, 3.0)
+    _, got = s.multibox_loss(ps, lg, conf, targets, 0.5, 3.0)
+    assert abs(got.item() - want.item()) <= RTOL * abs(want.item())
+    got.backward()
+    touched = (conf.grad.abs().sum(-1) > 0)[0]
+    n_pos = int(n_img[0])
+    assert int(touched.sum()) == n_pos + 3 * n_pos
+    neg_idx = (~pos_o[0]).nonzero()[:, 0][: 3 * n_pos]
+    assert bool(touched[neg_idx].all())
+
+
+def test_loss_backward_matches_autograd(env):
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    g = U.load("train_cfg2_thr04.npz")
+    targets, loc_all, conf = U.train_inputs(g)
+    thr, ratio = float(g["iou_thresh"]), float(g["ratio"])
+    tg = to_dev(targets, dev)
+    la, ca = loc_all.to(dev).requires_grad_(True), conf.to(dev).requires_grad_(True)
+    lb, cb = loc_all.to(dev).requires_grad_(True), conf.to(dev).requires_grad_(True)
+    l_loc, l_conf = s.multibox_loss(ps, la, ca, targets, thr, ratio)
+    (l_loc * 1.5 + l_conf * 0.7).backward()
+    pos_o, locpm_o, cls_o = O.batch_targets(env["pri"], env["pri_xyxy"], tg, 300, 300, thr)
+    o_loc, n_img, total = O.loc_loss(lb, pos_o, locpm_o)
+    o_conf = O.mined_ce_loss(cb, cls_o, pos_o, n_img, total, ratio)
+    (o_loc * 1.5 + o_conf * 0.7).backward()
+    assert close(la.grad, lb.grad, atol=1e-7) and close(ca.grad, cb.grad, atol=1e-7)
+    # drop-in CE alone
+    cc = conf.to(dev).requires_grad_(True)
+    s.CELoss_w_neg_mining(cc, cls_o, pos_o, n_img, total, ratio).backward()
+    cd = conf.to(dev).requires_grad_(True)
+    O.mined_ce_loss(cd, cls_o, pos_o, n_img, total, ratio).backward()
+    assert close(cc.grad, cd.grad, atol=1e-7)
+
+
+PREDICT = ["predict_cfg1.npz", "predict_cfg3_b4.npz", "predict_cfg3_b2_notebook.npz",
+           "predict_cfg3_b2_agnostic.npz", "predict_cfg3_b2_empty.npz", "predict_cfg5_b1.npz"]
+
+
+@pytest.mark.parametrize("name", PREDICT)
+def test_predict(env, name):
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    g = U.load(name)
+    loc_all, conf = U.predict_inputs(g)
+    st, nt, mx, ag = float(g["score_thresh"]), float(g["nms_thresh"]), int(g["max_per_img"]), bool(g["class_agnostic"])
+    lg, cg = loc_all.to(dev), conf.to(dev)
+    want = O.postprocess(env["pri"], lg, cg, st, nt, mx, ag, nms_limit=True, with_index=True)
+    gold = U.split_predictions(g)
+    got = s.predict(ps, None, st, nt, mx, ag, pre_loc_all=lg, pre_conf_all=cg)
+    _, _, _, count, cand = s.predict_padded(ps, lg, cg, st, nt, mx, ag, want_cand=True)
+    assert len(got) == len(want) == len(gold)
+    for b, (a, w, r) in enumerate(zip(got, want, gold)):
+        assert a["labels"].dtype == torch.int64 and a["scores"].dtype == torch.float32 and a["boxes"].shape[1:] == (4,)
+        # device-matched: keep list (candidate ids), labels, scores, boxes bit for bit
+        assert bit_equal(cand[b, : int(count[b])].long(), w["cand"]), f"keep list, image {b}"
+        assert bit_equal(a["labels"], w["labels"]) and bit_equal(a["scores"], w["scores"]) and bit_equal(a["boxes"], w["boxes"])
+        # the reference (CPU golden): same detections in the same order
+        assert bit_equal(a["labels"], r["labels"])
+        assert close(a["scores"], r["scores"]) and close(a["boxes"], r["boxes"], atol=BOX_ATOL)
+
+
+def test_predict_ties_and_metrics(env):
+    """Equal scores everywhere (all logits zero): candidates are ordered by candidate id (prior-major,
+    class-minor), the documented resolution of the reference's unstable argsort; and the CIoU / IoU
+    NMS variants agree with the oracle's."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    gen = torch.Generator().manual_seed(11)
+    loc = torch.randn((2, 8732, 4), generator=gen).to(dev)
+    conf = torch.zeros((2, 8732, 6), device=dev)
+    conf[1] = torch.randn((8732, 6), generator=gen).to(dev)
+    for agn in (False, True):
+        want = O.postprocess(env["pri"], loc, conf, 0.05, 0.45, 60, agn, nms_limit=True, with_index=True)
+        *_, count, cand = s.predict_padded(ps, loc, conf, 0.05, 0.45, 60, agn, want_cand=True)
+        for b in range(2):
+            assert bit_equal(cand[b, : int(count[b])].long(), want[b]["cand"])
+    for metric in ("ciou",):
+        want = O.postprocess(env["pri"], loc, conf, 0.05, 0.45, 60, False, metric=metric, nms_limit=True, with_index=True)
+        *_, count, cand = s.predict_padded(ps, loc, conf, 0.05, 0.45, 60, False, metric=metric, want_cand=True)
+        for b in range(2):
+            assert bit_equal(cand[b, : int(count[b])].long(), want[b]["cand"])
+
+
+def test_static_methods(env):
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    g = U.load("static_methods.npz")
+    boxes, scores = torch.from_numpy(g["boxes"]).to(dev), torch.from_numpy(g["scores"]).to(dev)
+    for thr, key in ((0.45, "keep45"), (0.30, "keep30")):
+        k = s.iou_nms(boxes, scores, thr)
+        assert k.dtype == torch.int64 and bit_equal(k, torch.from_numpy(g[key]))
+        # idempotence: the survivors survive themselves
+        k2 = s.iou_nms(boxes[k], scores[k], thr)
+        assert bit_equal(k2, torch.arange(k.numel()))
+    assert s.iou_nms(boxes[:0], scores[:0], 0.45).shape == (0,)
+    # NaN suppresses (zero-area twins): SURVEY.md section 7 hard part 3
+    z = torch.tensor([[5., 5., 5., 5.], [5., 5., 5., 5.], [50., 50., 80., 80.]], device=dev)
+    zs = torch.tensor([0.9, 0.8, 0.7], device=dev)
+    assert bit_equal(s.iou_nms(z, zs, 0.45), O.greedy_nms(z, zs, 0.45))
+    # several sets in one launch + more boxes than one ranking chunk
+    gen = torch.Generator().manual_seed(3)
+    n = 3000
+    ctr = torch.rand((n, 2), generator=gen) * 300
+    wh = torch.rand((n, 2), generator=gen) * 60 + 2
+    big = torch.cat((ctr - wh / 2, ctr + wh / 2), 1).clamp(0, 300).to(dev)
+    bs = torch.rand((n,), generator=gen).to(dev)
+    bs[100:140] = bs[100]                      # a run of exactly equal scores
+    sizes = [1700, 0, 1300]
+    keep, cnt = s.nms_sets(big, bs, sizes, 0.45)
+    off = 0
+    for i, m in enumerate(sizes):
+        want = O.greedy_nms(big[off:off + m], bs[off:off + m], 0.45)
+        assert int(cnt[i]) == want.numel() and bit_equal(keep[off: off + want.numel()], want)
+        off += m
+    for metric in ("ciou",):
+        want = O.greedy_nms(big[:1700], bs[:1700], 0.45, metric=metric)
+        assert bit_equal(s.iou_nms(big[:1700], bs[:1700], 0.45, metric=metric), want)
+    # decode
+    gen = torch.Generator().manual_seed(77)
+    for _ in range(2):
+        torch.rand((600, 2), generator=gen)
+    torch.rand((600,), generator=gen)
+    loc = torch.randn((8732, 4), generator=gen).to(dev)
+    d = s.decode_ssd(loc, ps.priors, (0.1, 0.2))
+    assert bit_equal(d, O.decode(loc, env["pri"], (0.1, 0.2))) and close(d, torch.from_numpy(g["decoded"]))
+
+
+def test_full_size_properties(env):
+    """BASELINE configs at full batch (B=256): properties that need no oracle at that size, plus a
+    bit-exact spot check of a few images against the device-matched oracle."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    from ssdhot import synth
+    cfg = synth.config(3)
+    lg, ct, ci = cfg["loc_all"].to(dev), cfg["conf_train"].to(dev), cfg["conf_infer"].to(dev)
+    targets = cfg["targets"]
+    B = cfg["batch"]
+    # -- training half: batch invariance + additivity of the un-normalised sums over shards
+    _, _, full = s.multibox_loss(ps, lg, ct, targets, 0.5, 3.0, return_sums=True)
+    parts = torch.zeros(3, dtype=torch.float64, device=dev)
+    for lo in range(0, B, 64):
+        _, _, p = s.multibox_loss(ps, lg[lo:lo + 64], ct[lo:lo + 64], targets[lo:lo + 64], 0.5, 3.0, return_sums=True)
+        parts += p
+    assert float(parts[2]) == float(full[2])
+    assert close(parts[:2], full[:2], rtol=1e-9)
+    r = s.match_encode_batch(ps, s.pack_targets(targets, dev), 0.5, (300, 300), want_loc="all", want_matched_idx=True)
+    pick = [0, 17, 101, 255]
+    sub = s.match_encode_batch(ps, s.pack_targets([targets[i] for i in pick], dev), 0.5, (300, 300), want_loc="all",
+                               want_matched_idx=True)
+    for j, i in enumerate(pick):
+        for key in ("pos_mask", "cls_t", "loc_t", "matched_gt"):
+            assert bit_equal(r[key][i], sub[key][j])
+    tg = to_dev([targets[i] for i in pick], dev)
+    pos_o, _, cls_o, locd_o = O.batch_targets(env["pri"], env["pri_xyxy"], tg, 300, 300, 0.5, dense=True)
+    assert bit_equal(sub["pos_mask"], pos_o) and bit_equal(sub["cls_t"], cls_o) and bit_equal(sub["loc_t"], locd_o)
+    # every ground-truth box got its forced prior: >= 1 positive per distinct best prior, and
+    # every positive's class is one of the image's labels + 1
+    assert int((r["n_pos"] <= 0).sum()) == 0
+    # -- inference half
+    labels, scores, boxes, count, cand = s.predict_padded(ps, lg, ci, 0.01, 0.45, 200, want_cand=True)
+    cnt = count.tolist()
+    assert all(0 <= k <= 200 for k in cnt)
+    for i in range(B):
+        k = cnt[i]
+        sc = scores[i, :k]
+        assert bool((sc[1:] <= sc[:-1]).all()) and bool((sc > 0.01).all())
+        bx = boxes[i, :k]
+        assert bool((bx >= 0).all()) and bool((bx <= 300).all())
+        assert bool((labels[i, :k] == (cand[i, :k] % 5)).all())
+    want = O.postprocess(env["pri"], lg[pick], ci[pick], 0.01, 0.45, 200, False, nms_limit=True, with_index=True)
+    for j, i in enumerate(pick):
+        assert bit_equal(cand[i, :cnt[i]].long(), want[j]["cand"])
+        assert bit_equal(scores[i, :cnt[i]], want[j]["scores"]) and bit_equal(boxes[i, :cnt[i]], want[j]["boxes"])
+    # per-class NMS fixpoint: re-running NMS on one image's detections of one class keeps them all
+    i = 5
+    k = cnt[i]
+    for c in range(5):
+        m = labels[i, :k] == c
+        if int(m.sum()) > 1:
+            kk = s.iou_nms(boxes[i, :k][m], scores[i, :k][m], 0.45)
+            assert bit_equal(kk, torch.arange(int(m.sum())))
+
+
+def test_stress_config_slice(env):
+    """cfg 5 (64 GT boxes per image; threshold 0.0 so all 8732 x 5 pairs enter NMS) on a slice."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    from ssdhot import synth
+    cfg = synth.config(5, batch=3)
+    lg, ct, ci = cfg["loc_all"].to(dev), cfg["conf_train"].to(dev), cfg["conf_infer"].to(dev)
+    tg = to_dev(cfg["targets"], dev)
+    pos_o, locpm_o, cls_o, locd_o = O.batch_targets(env["pri"], env["pri_xyxy"], tg, 300, 300, 0.5, dense=True)
+    r = s.match_encode_batch(ps, s.pack_targets(cfg["targets"], dev), 0.5, (300, 300), want_loc="all")
+    assert bit_equal(r["pos_mask"], pos_o) and bit_equal(r["cls_t"], cls_o) and bit_equal(r["loc_t"], locd_o)
+    want = O.postprocess(env["pri"], lg, ci, 0.0, 0.45, 200, False, nms_limit=True, with_index=True)
+    *_, count, cand = s.predict_padded(ps, lg, ci, 0.0, 0.45, 200, want_cand=True)
+    for b in range(3):
+        assert bit_equal(cand[b, : int(count[b])].long(), want[b]["cand"])
+    # no early stop: the stand-alone NMS over one full class (8732 boxes) equals the oracle's full run
+    sc = ci[0].softmax(-1)[:, 1]
+    box = O.decode(lg[0], env["pri"], (0.1, 0.2))
+    xyxy = (O.cxcywh_to_xyxy(box).clamp(0, 1) * 300).contiguous()
+    assert bit_equal(s.iou_nms(xyxy, sc, 0.45), O.greedy_nms(xyxy, sc, 0.45))
+
+
+def test_error_behaviour(env):
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    z_loc, z_conf = torch.zeros((1, 8732, 4), device=dev), torch.zeros((1, 8732, 6), device=dev)
+    with pytest.raises(ValueError):
+        s.predict(ps, None, score_thresh=1.0, pre_loc_all=z_loc, pre_conf_all=z_conf)
+    with pytest.raises(ValueError):
+        s.predict(ps, None, nms_thresh=1.0, pre_loc_all=z_loc, pre_conf_all=z_conf)
+    with pytest.raises(ValueError):
+        s.build_targets(ps, [], iou_thresh=0.0)
+    with pytest.raises(s.SsdhotError):
+        s.decode_ssd(torch.zeros((4, 4)), torch.zeros((4, 4)), (0.1, 0.2))     # CPU tensors: no fallback
+    with pytest.raises(s.SsdhotError):
+        s.build_targets(ps, [{"boxes": torch.zeros((0, 4)), "labels": torch.zeros((0,), dtype=torch.int64)}], device="cpu")
+    # raw ABI status codes
+    L = s.lib()
+    assert L.ssdhot_decode(None, None, 4, 0.1, 0.2, None, None) == -1
+    assert L.ssdhot_prior_tables(ps.priors.data_ptr(), 20000, ps.priors_xyxy.data_ptr(), ps.aux.data_ptr(), None) == -2
+    assert L.ssdhot_decode(ps.priors.data_ptr() + 4, ps.priors.data_ptr(), 4, 0.1, 0.2, ps.aux.data_ptr(), None) == -5

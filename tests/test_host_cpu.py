@@ -1,0 +1,170 @@
+"""CPU tests of the host side: the C-ABI library loads and exports exactly what include/ssdhot.h
+declares, argument validation happens before any launch, priors / packing / sharding logic."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import _util as U
+from oracle import ssd_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ssdhot.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"SSDHOT_API\s+[\w\s\*]+?\b(ssdhot_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ssdhot
+    from ssdhot import _lib
+    names = declared_symbols()
+    assert len(names) >= 15
+    handle = ssdhot.lib()
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in ssdhot.h but not exported"
+        assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype"
+    assert sorted(_lib.PROTOTYPES) == names
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l and "ssdhot_" in l)
+    assert exported == names, "exported symbols differ from the header"
+    assert handle.ssdhot_abi_version() == 1
+    assert handle.ssdhot_status_string(-2).decode().startswith("a size")
+
+
+def test_library_is_sm100a_only():
+    from ssdhot import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_validation_happens_before_launch_no_gpu_needed():
+    import ssdhot
+    L = ssdhot.lib()
+    assert L.ssdhot_decode(None, None, 8, 0.1, 0.2, None, None) == -1
+    assert L.ssdhot_prior_tables(16, 0, 16, 16, None) == -2
+    assert L.ssdhot_prior_tables(16, 8732, 20, 16, None) == -5
+    assert L.ssdhot_predict(16, 8732, 16, 16, 1, 6, 1.0, 0.45, 200, 0, 0, 0.1, 0.2, 300.0, 300.0,
+                            16, 16, 16, None, 16, 16, None) == -3          # score_thresh must be < 1
+    assert L.ssdhot_predict(16, 8732, 16, 16, 1, 6, 0.1, 0.0, 200, 0, 0, 0.1, 0.2, 300.0, 300.0,
+                            16, 16, 16, None, 16, 16, None) == -3          # nms_thresh must be > 0
+    assert L.ssdhot_predict(16, 8732, 16, 16, 1, 1, 0.1, 0.5, 200, 0, 0, 0.1, 0.2, 300.0, 300.0,
+                            16, 16, 16, None, 16, 16, None) == -2          # C >= 2
+    assert L.ssdhot_loss_workspace_bytes(256) > 0 and L.ssdhot_predict_workspace_bytes(256, 6, 200) > 0
+    assert ssdhot.launch_count() == 0
+
+
+def test_no_cpu_fallback():
+    import ssdhot
+    with pytest.raises(ssdhot.SsdhotError):
+        ssdhot.decode_ssd(torch.zeros((4, 4)), torch.zeros((4, 4)), (0.1, 0.2))
+    with pytest.raises(ssdhot.SsdhotError):
+        ssdhot.PriorSet(torch.zeros((8732, 4)))
+    with pytest.raises(ssdhot.SsdhotError):
+        ssdhot.iou_nms(torch.rand((4, 4)), torch.rand((4,)), 0.5)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "automotive-ssd-object-detection_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(base, f)).read()
+                assert "oracle" not in txt.lower() or f == "synth.py", f"{f} mentions the oracle"
+
+
+def test_default_boxes_match_reference_hash():
+    import ssdhot
+    pri = ssdhot.default_boxes()
+    assert pri.shape == (8732, 4) and U.sha(pri) == O.PRIORS_SHA256
+    assert torch.equal(pri, O.default_boxes())
+
+
+def test_pack_targets_ragged_and_empty():
+    import ssdhot
+    t = [{"boxes": torch.rand((3, 4)), "labels": torch.tensor([0, 1, 2])},
+         {"boxes": torch.zeros((0, 4)), "labels": torch.zeros((0,), dtype=torch.int64)},
+         {"boxes": torch.rand((1, 4)), "labels": torch.tensor([4])}]
+    p = ssdhot.pack_targets(t, "cpu")
+    assert p.offsets.tolist() == [0, 3, 3, 4] and p.max_gt == 3 and p.n_img == 3
+    assert p.boxes.shape == (4, 4) and p.labels.dtype == torch.int64 and p.offsets.dtype == torch.int32
+    assert torch.equal(p.boxes[3], t[2]["boxes"][0])
+    e = ssdhot.pack_targets(t[1:2], "cpu")
+    assert e.offsets.tolist() == [0, 0] and e.max_gt == 0
+    from ssdhot import synth
+    b, l, o = synth.pack_targets(t)
+    assert torch.equal(b, p.boxes) and torch.equal(l, p.labels) and torch.equal(o, p.offsets)
+
+
+def test_synth_is_deterministic_and_shaped():
+    from ssdhot import synth
+    a, b = synth.config(2, batch=3), synth.config(2, batch=3)
+    assert torch.equal(a["loc_all"], b["loc_all"]) and torch.equal(a["conf_infer"], b["conf_infer"])
+    assert a["loc_all"].shape == (3, 8732, 4) and a["conf_train"].shape == (3, 8732, 6)
+    for t in a["targets"]:
+        bx = t["boxes"]
+        assert 1 <= bx.shape[0] <= 20 and bool((bx[:, 2:] - bx[:, :2] >= 1.0 - 1e-4).all())
+        assert bool((bx >= 0).all()) and bool((bx <= 300).all())
+    c = synth.config(3, batch=1, dedup=True)["conf_infer"]
+    s = c.softmax(-1)[0, :, 1:].reshape(-1)
+    assert s.unique().numel() == s.numel()
+    r0, r1 = synth.config(4, batch=2, seed_offset=0), synth.config(4, batch=2, seed_offset=1)
+    assert not torch.equal(r0["loc_all"], r1["loc_all"])
+
+
+def test_shard_ranges_cover_the_batch():
+    from ssdhot import dist as D
+    for n, w in ((4096, 8), (10, 3), (2, 4), (256, 1)):
+        spans = [D.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.join(ROOT, "automotive-ssd-object-detection_b200"))
+    sys.path.insert(0, ROOT)
+    from ssdhot import dist as D, synth
+    from oracle import ssd_oracle as O
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = synth.config(2, batch=6)
+    pri, pri_xyxy = O.prior_tables()
+    lo, hi = D.shard_range(6, rank, world)
+    tg = cfg["targets"][lo:hi]
+    # per-rank un-normalised sums of the shard, as ssdhot_multibox_loss_fwd writes them
+    pos, loc_pm, cls_t = O.batch_targets(pri, pri_xyxy, tg, 300, 300, 0.5)
+    n_img = pos.sum(1)
+    one = torch.ones(())
+    s_loc = torch.nn.functional.smooth_l1_loss(cfg["loc_all"][lo:hi][pos], loc_pm, reduction="sum")
+    s_ce = O.mined_ce_loss(cfg["conf_train"][lo:hi], cls_t, pos, n_img, one, 3.0)
+    sums = torch.tensor([s_loc.item(), s_ce.item(), float(n_img.sum())], dtype=torch.float64)
+    D.combine_sums(sums)
+    l_loc, l_conf = D.losses_from_sums(sums)
+    out[rank] = (l_loc.item(), l_conf.item())
+    dist.destroy_process_group()
+
+
+def test_sharded_loss_equals_single_process_gloo_world2():
+    """world_size-2 gloo run of the sharded path's only exchange: all-reduced partial sums give the
+    same losses as the un-sharded reference computation on the concatenated batch (1e-5)."""
+    import torch.multiprocessing as mp
+    from ssdhot import synth
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
+    cfg = synth.config(2, batch=6)
+    pri, pri_xyxy = O.prior_tables()
+    want_loc, want_conf = O.train_half(pri, pri_xyxy, cfg["loc_all"], cfg["conf_train"], cfg["targets"], 0.5, 3.0)
+    assert out[0] == out[1]
+    assert abs(out[0][0] - want_loc.item()) <= 1e-5 * abs(want_loc.item())
+    assert abs(out[0][1] - want_conf.item()) <= 1e-5 * abs(want_conf.item())
