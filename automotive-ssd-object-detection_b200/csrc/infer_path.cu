@@ -1,16 +1,23 @@
 // infer_path.cu -- decode, score threshold, ranking and greedy DIoU/CIoU NMS
 // (SURVEY.md section 8a rows a6-a8).
 //
-// Unit of work = one (image, foreground class) pair (or one image when class-agnostic): one CTA.
-// The unit's scores live in shared memory as a dense array of order-preserving keys indexed by
-// candidate id (0 = not a candidate), so thresholding needs no compaction and ties are ordered
-// by candidate id for free.  Candidates are consumed best-first in chunks: a 4-pass radix select
-// pulls the next CHUNK highest keys, a bitonic network sorts them, their boxes are decoded, and
-// greedy NMS walks the chunk in tiles of 64 -- every (kept box | earlier tile member) x (tile
-// member) predicate is evaluated in parallel into 64-bit suppression masks (ballot), then one
-// thread resolves the tile serially with bit operations.  The walk stops as soon as max_keep
-// boxes survive, which is lossless for the reference's post-NMS `keep[:max_per_img]`
-// (SSD_from_scratch.py:465) because survivors are produced in score order.
+// Unit of work = one IMAGE: one CTA of 1024 threads walks the image's candidates of ALL classes in
+// one global score order and applies class-aware greedy NMS, so the walk can stop as soon as
+// max_per_img boxes survive.  That is exactly the reference's result -- per-class greedy NMS, then
+// a global score sort and `keep[:max_per_img]` (SSD_from_scratch.py:439-465): a candidate's fate
+// depends only on higher-scored candidates of its own class, all of which precede it in the
+// global order, and survivors are produced in global score order -- but it never ranks or tests
+// the thousands of low-score candidates that cannot reach the output.
+//
+// The image's scores live in shared memory as a dense array of order-preserving keys indexed by
+// candidate id prior*(C-1)+class (0 = not a candidate), so thresholding needs no compaction and
+// equal scores are ordered by candidate id for free.  Candidates are consumed best-first in
+// chunks: a 4-pass radix select pulls the next CHUNK highest keys, a bitonic network sorts them,
+// their boxes are decoded, and greedy NMS walks the chunk in tiles of 64 -- every (kept box |
+// earlier tile member) x (tile member) predicate is evaluated in parallel into 64-bit suppression
+// masks (ballot), then one thread resolves the tile serially with bit operations.
+// When the dense array does not fit in shared memory (many classes) the same unit runs per
+// (image, class) and a merge kernel combines the per-class survivor lists.
 #include <map>
 #include <mutex>
 
@@ -18,10 +25,9 @@
 
 namespace ssdhot {
 
-constexpr int UT = 512;        // threads per unit CTA
-constexpr int UW = UT / 32;    // warps
 constexpr int CHUNK = 512;     // candidates ranked per round
 constexpr int TILE = 64;
+constexpr float kFilterSlack = 0.999f;   // see suppresses()
 
 struct UnitShared {
     unsigned hist[256];
@@ -33,10 +39,39 @@ struct UnitShared {
     int iscratch[32];
 };
 
+// ---- the pair predicate --------------------------------------------------------------------------
+// "S suppresses c" iff NOT(metric(S, c) <= thr)  (SSD_from_scratch.py:690; NaN suppresses).
+// Every metric here is <= IoU (DIoU and CIoU subtract non-negative penalties), so a pair whose
+// intersection is below thr_lo * union, thr_lo = 0.999 * thr, has IoU < thr by a margin of 1e-3
+// -- four orders of magnitude above fp32 rounding -- and survives without the two IEEE divisions.
+// Pairs that pass (or whose union is not positive, where the exact test may yield NaN) take the
+// exact path, so the decision is bit-identical to evaluating the metric everywhere.
+template <int METRIC>
+__device__ __forceinline__ bool suppresses(const BoxC& S, const BoxC& c, float thr, float thr_lo) {
+    const float w = fmaxf(fsub(fminf(S.x2, c.x2), fmaxf(S.x1, c.x1)), 0.0f);
+    const float h = fmaxf(fsub(fminf(S.y2, c.y2), fmaxf(S.y1, c.y1)), 0.0f);
+    const float inter = fmul(w, h);
+    const float uni = fsub(fadd(S.area, c.area), inter);
+    if (inter < fmul(thr_lo, uni)) return false;
+    const float iou = fdiv(inter, uni);
+    float m = iou;
+    if (METRIC != SSDHOT_METRIC_IOU) {
+        m = pair_diou_from_iou(S, c, iou);
+        if (METRIC == SSDHOT_METRIC_CIOU) {
+            const float da = fsub(S.at, c.at);
+            const float v = fmul(kFourOverPiSq, fmul(da, da));
+            const float alpha = fdiv(v, fadd(fadd(fsub(1.0f, iou), v), kEps));
+            m = fsub(m, fmul(alpha, v));
+        }
+    }
+    return !(m <= thr);
+}
+
 // ---- ranking helpers ---------------------------------------------------------------------------
 
 // Radix select over the non-zero entries of dense[0..n): the K-th largest key.  Returns the key,
 // how many entries equal to it are needed (`need`) and how many exist (`eq`).
+template <int NT>
 __device__ __forceinline__ void select_kth(const unsigned* dense, int n, unsigned K, UnitShared& us,
                                            unsigned& thr, unsigned& need, unsigned& eq) {
     const int tid = threadIdx.x;
@@ -44,9 +79,9 @@ __device__ __forceinline__ void select_kth(const unsigned* dense, int n, unsigne
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
         const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-        for (int i = tid; i < 256; i += UT) us.hist[i] = 0u;
+        for (int i = tid; i < 256; i += NT) us.hist[i] = 0u;
         __syncthreads();
-        for (int i = tid; i < n; i += UT) {
+        for (int i = tid; i < n; i += NT) {
             const unsigned k = dense[i];
             if (k != 0u && (k & himask) == prefix) atomicAdd(&us.hist[(k >> shift) & 255u], 1u);
         }
@@ -103,13 +138,26 @@ __device__ __forceinline__ void bitonic_desc(unsigned long long* keys, int n_pad
 // ---- the unit ------------------------------------------------------------------------------------
 // dense:   [n] keys (0 = absent), consumed (zeroed) as candidates are ranked
 // Fetch:   BoxC operator()(unsigned idx)      -- pixel box + constants of candidate idx
+// Group:   int operator()(unsigned idx)       -- suppression group (class) of candidate idx; only
+//                                                members of the same group suppress each other
 // Emit:    void operator()(int pos, unsigned long long key, unsigned idx, const BoxC&)
-// kept:    storage for the surviving boxes (shared or global memory), capacity max_keep
+// kept / kgroup: storage for the surviving boxes and their groups, capacity max_keep
 // returns the number of survivors (valid in every thread)
-template <int METRIC, typename Fetch, typename Emit>
-__device__ int nms_unit(unsigned* dense, int n, int n_cand, unsigned long long* ckey, BoxC* cbox, BoxC* kept,
-                        int max_keep, float thr, UnitShared& us, Fetch fetch, Emit emit) {
+struct UnitBuffers {
+    unsigned* dense; unsigned long long* ckey; BoxC* cbox; unsigned char* cgroup;
+    BoxC* kept; unsigned char* kgroup;
+};
+
+template <int METRIC, int NT, bool GROUPS, typename Fetch, typename Group, typename Emit>
+__device__ int nms_unit(const UnitBuffers buf, int n, int n_cand, int max_keep, float thr, UnitShared& us,
+                        Fetch fetch, Group group_of, Emit emit) {
+    constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned* dense = buf.dense;
+    unsigned long long* ckey = buf.ckey;
+    BoxC* cbox = buf.cbox;
+    BoxC* kept = buf.kept;
+    const float thr_lo = fmul(thr, kFilterSlack);
     int kept_n = 0;
     int remaining = n_cand;
     while (remaining > 0 && kept_n < max_keep) {
@@ -117,11 +165,11 @@ __device__ int nms_unit(unsigned* dense, int n, int n_cand, unsigned long long* 
         // ---- pull the K best remaining candidates ------------------------------------------
         unsigned tkey = 1u, need = 0u, eq = 0u;
         const bool all = remaining <= CHUNK;
-        if (!all) select_kth(dense, n, (unsigned)K, us, tkey, need, eq);
+        if (!all) select_kth<NT>(dense, n, (unsigned)K, us, tkey, need, eq);
         if (tid == 0) us.counter = 0;
         __syncthreads();
         if (all || need == eq) {
-            for (int i = tid; i < n; i += UT) {
+            for (int i = tid; i < n; i += NT) {
                 const unsigned k = dense[i];
                 if (k != 0u && k >= tkey) {
                     const int pos = atomicAdd(&us.counter, 1);
@@ -132,7 +180,7 @@ __device__ int nms_unit(unsigned* dense, int n, int n_cand, unsigned long long* 
         } else {
             // more entries equal to the threshold key than needed: take the lowest ids first
             int taken_eq = 0;
-            for (int base = 0; base < n; base += UT) {
+            for (int base = 0; base < n; base += NT) {
                 const int i = base + tid;
                 const unsigned k = i < n ? dense[i] : 0u;
                 const bool is_eq = k != 0u && k == tkey;
@@ -141,7 +189,7 @@ __device__ int nms_unit(unsigned* dense, int n, int n_cand, unsigned long long* 
                 if (lane == 0) us.iscratch[warp] = __popc(bal);
                 __syncthreads();
                 int before = taken_eq, tot = 0;
-                for (int w = 0; w < UW; ++w) { if (w < warp) before += us.iscratch[w]; tot += us.iscratch[w]; }
+                for (int w = 0; w < NW; ++w) { if (w < warp) before += us.iscratch[w]; tot += us.iscratch[w]; }
                 const int my_rank = before + __popc(bal & ((1u << lane) - 1u));
                 if (k != 0u && (k > tkey || (is_eq && (unsigned)my_rank < need))) {
                     const int pos = atomicAdd(&us.counter, 1);
@@ -154,9 +202,13 @@ __device__ int nms_unit(unsigned* dense, int n, int n_cand, unsigned long long* 
         int n_pad = 64;
         while (n_pad < K) n_pad <<= 1;
         __syncthreads();
-        for (int i = K + tid; i < n_pad; i += UT) ckey[i] = 0ull;
+        for (int i = K + tid; i < n_pad; i += NT) ckey[i] = 0ull;
         bitonic_desc(ckey, n_pad);
-        for (int i = tid; i < K; i += UT) cbox[i] = fetch(0xffffffffu - (unsigned)(ckey[i] & 0xffffffffull));
+        for (int i = tid; i < K; i += NT) {
+            const unsigned idx = 0xffffffffu - (unsigned)(ckey[i] & 0xffffffffull);
+            cbox[i] = fetch(idx);
+            if (GROUPS) buf.cgroup[i] = (unsigned char)group_of(idx);
+        }
         __syncthreads();
 
         // ---- greedy NMS over the sorted chunk, tile by tile ----------------------------------
@@ -165,18 +217,20 @@ __device__ int nms_unit(unsigned* dense, int n, int n_cand, unsigned long long* 
             if (tid < TILE) us.rowmask[tid] = 0ull;
             if (tid == 0) us.supp = 0ull;
             __syncthreads();
-            const BoxC c_lo = cbox[t0 + (lane < m ? lane : 0)];
-            const BoxC c_hi = cbox[t0 + (lane + 32 < m ? lane + 32 : 0)];
+            const int i_lo = t0 + (lane < m ? lane : 0), i_hi = t0 + (lane + 32 < m ? lane + 32 : 0);
+            const BoxC c_lo = cbox[i_lo];
+            const BoxC c_hi = cbox[i_hi];
+            const int g_lo = GROUPS ? (int)buf.cgroup[i_lo] : 0, g_hi = GROUPS ? (int)buf.cgroup[i_hi] : 0;
             const int n_sup = kept_n + m;
-            for (int s = warp; s < n_sup; s += UW) {
+            for (int s = warp; s < n_sup; s += NW) {
                 const bool from_kept = s < kept_n;
                 const int si = s - kept_n;                     // tile index of the suppressor (if not kept)
                 const BoxC S = from_kept ? kept[s] : cbox[t0 + si];
-                const bool v_lo = lane < m && (from_kept || si < lane);
-                const bool v_hi = lane + 32 < m && (from_kept || si < lane + 32);
-                // a box survives a suppressor iff metric <= thr; NaN therefore suppresses (SFS:690)
-                const bool s_lo = v_lo && !(pair_metric<METRIC>(S, c_lo) <= thr);
-                const bool s_hi = v_hi && !(pair_metric<METRIC>(S, c_hi) <= thr);
+                const int sg = GROUPS ? (int)(from_kept ? buf.kgroup[s] : buf.cgroup[t0 + si]) : 0;
+                const bool v_lo = lane < m && (from_kept || si < lane) && sg == g_lo;
+                const bool v_hi = lane + 32 < m && (from_kept || si < lane + 32) && sg == g_hi;
+                const bool s_lo = v_lo && suppresses<METRIC>(S, c_lo, thr, thr_lo);
+                const bool s_hi = v_hi && suppresses<METRIC>(S, c_hi, thr, thr_lo);
                 const unsigned b_lo = __ballot_sync(FULL, s_lo), b_hi = __ballot_sync(FULL, s_hi);
                 if (lane == 0) {
                     const unsigned long long bits = ((unsigned long long)b_hi << 32) | b_lo;
@@ -204,6 +258,7 @@ __device__ int nms_unit(unsigned* dense, int n, int n_cand, unsigned long long* 
                 const int pos = kept_n + __popcll(keepb & ((1ull << tid) - 1ull));
                 const BoxC bx = cbox[t0 + tid];
                 kept[pos] = bx;
+                if (GROUPS) buf.kgroup[pos] = buf.cgroup[t0 + tid];
                 const unsigned long long key = ckey[t0 + tid];
                 emit(pos, key, 0xffffffffu - (unsigned)(key & 0xffffffffull), bx);
             }
@@ -215,75 +270,84 @@ __device__ int nms_unit(unsigned* dense, int n, int n_cand, unsigned long long* 
     return kept_n;
 }
 
+// shared-memory carve-up of one unit: kept | cbox | ckey | dense | cgroup | kgroup
+__host__ __device__ inline size_t unit_smem_bytes(long long n, int max_keep) {
+    return (size_t)max_keep * sizeof(BoxC) + (size_t)CHUNK * (sizeof(BoxC) + 8) + (size_t)n * 4 + (size_t)CHUNK +
+           (size_t)max_keep + 16;
+}
+__device__ __forceinline__ UnitBuffers carve_unit(unsigned char* dyn, long long n, int max_keep) {
+    UnitBuffers b;
+    b.kept = reinterpret_cast<BoxC*>(dyn);
+    b.cbox = b.kept + max_keep;
+    b.ckey = reinterpret_cast<unsigned long long*>(b.cbox + CHUNK);
+    b.dense = reinterpret_cast<unsigned*>(b.ckey + CHUNK);
+    b.cgroup = reinterpret_cast<unsigned char*>(b.dense + n);
+    b.kgroup = b.cgroup + CHUNK;
+    return b;
+}
+
 // ---- predict -------------------------------------------------------------------------------------
 struct PredictParams {
     const float* pri; int P; const float* loc_all; const float* conf_all; int B, C;
     float score_thresh, nms_thresh; int max_keep; float vc, vs, img_w, img_h;
+    // final outputs (per-image kernel)
+    int64_t* out_labels; float* out_scores; float* out_boxes; int32_t* out_cand; int32_t* out_count;
+    // per-class lists (fallback path)
     unsigned long long* list_key;   // [B*units][max_keep]
     float4* list_box;               // [B*units][max_keep]
     int* list_count;                // [B*units]
 };
 
-// foreground softmax scores of one row in eager torch-CUDA order (see boxmath.cuh / train_path.cu)
+// exp(x_i - max) of one row and their sum in eager torch-CUDA order (persistent warp softmax: one
+// element per lane, lanes = next_pow2(C), butterfly adds over xor offsets lanes/2 .. 1).  CT == 6 is
+// the reference's class count; CT == 0 handles any C <= 32 through `e` in local memory.
 template <int CT>
-__device__ __forceinline__ void row_softmax_stats(const float* __restrict__ row, int C, float& mx, float& sum) {
+__device__ __forceinline__ float row_exps(const float* __restrict__ row, int C, float* e) {
     if (CT == 6) {
         const float2 a = ldg2(row), b = ldg2(row + 2), c = ldg2(row + 4);
-        mx = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y)), fmaxf(c.x, c.y));
-        const float e0 = expf(fsub(a.x, mx)), e1 = expf(fsub(a.y, mx)), e2 = expf(fsub(b.x, mx));
-        const float e3 = expf(fsub(b.y, mx)), e4 = expf(fsub(c.x, mx)), e5 = expf(fsub(c.y, mx));
-        sum = fadd(fadd(fadd(e0, e4), e2), fadd(fadd(e1, e5), e3));
+        const float mx = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y)), fmaxf(c.x, c.y));
+        e[0] = expf(fsub(a.x, mx)); e[1] = expf(fsub(a.y, mx)); e[2] = expf(fsub(b.x, mx));
+        e[3] = expf(fsub(b.y, mx)); e[4] = expf(fsub(c.x, mx)); e[5] = expf(fsub(c.y, mx));
+        return fadd(fadd(fadd(e[0], e[4]), e[2]), fadd(fadd(e[1], e[5]), e[3]));
     } else {
         int lanes = 1;
-        while (lanes < C && lanes < 32) lanes <<= 1;
-        mx = __ldg(row);
+        while (lanes < C) lanes <<= 1;
+        float mx = __ldg(row);
         for (int i = 1; i < C; ++i) mx = fmaxf(mx, __ldg(row + i));
         float part[32];
         for (int l = 0; l < 32; ++l) part[l] = 0.0f;
-        for (int i = 0; i < C; ++i) {
-            const int l = i & (lanes - 1);
-            part[l] = fadd(part[l], expf(fsub(__ldg(row + i), mx)));
-        }
+        for (int i = 0; i < C; ++i) { e[i] = expf(fsub(__ldg(row + i), mx)); part[i] = e[i]; }
         for (int off = lanes >> 1; off > 0; off >>= 1)
             for (int l = 0; l < off; ++l) part[l] = fadd(part[l], part[l + off]);
-        sum = part[0];
+        return part[0];
     }
 }
 
+constexpr int PT = 1024;   // threads of the per-image kernel
+constexpr int UT = 512;    // threads of the per-(image, class) fallback and of stand-alone NMS
+
+// One CTA per image, all classes in one score-ordered stream (class-aware unless AGN).
 template <int METRIC, bool AGN, int CT>
-__global__ void __launch_bounds__(UT) predict_unit_kernel(const PredictParams prm) {
+__global__ void __launch_bounds__(PT) predict_image_kernel(const PredictParams prm) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ UnitShared us;
     const int tid = threadIdx.x;
-    const int n_fg = prm.C - 1;
-    const int units = AGN ? 1 : n_fg;
-    const int b = blockIdx.x / units, c = blockIdx.x % units;
-    const int P = prm.P;
-    const int n = AGN ? P * n_fg : P;
+    const int b = blockIdx.x;
+    const int n_fg = prm.C - 1, P = prm.P;
+    const int n = P * n_fg;
+    const UnitBuffers buf = carve_unit(dyn, n, prm.max_keep);
 
-    BoxC* kept = reinterpret_cast<BoxC*>(dyn);
-    BoxC* cbox = kept + prm.max_keep;
-    unsigned long long* ckey = reinterpret_cast<unsigned long long*>(cbox + CHUNK);
-    unsigned* dense = reinterpret_cast<unsigned*>(ckey + CHUNK);
-
-    // ---- scores -> dense keys ----------------------------------------------------------------
     int mine = 0;
     const float* conf_b = prm.conf_all + (long long)b * P * prm.C;
-    for (int p = tid; p < P; p += UT) {
-        const float* row = conf_b + (long long)p * prm.C;
-        float mx, sum;
-        row_softmax_stats<CT>(row, prm.C, mx, sum);
-        if (AGN) {
-            for (int k = 0; k < n_fg; ++k) {
-                const float s = fdiv(expf(fsub(__ldg(row + k + 1), mx)), sum);
-                const bool on = s > prm.score_thresh;
-                dense[p * n_fg + k] = on ? ord_encode(s) : 0u;
-                mine += on ? 1 : 0;
-            }
-        } else {
-            const float s = fdiv(expf(fsub(__ldg(row + c + 1), mx)), sum);
-            const bool on = s > prm.score_thresh;
-            dense[p] = on ? ord_encode(s) : 0u;
+    for (int p = tid; p < P; p += PT) {
+        float e[CT > 0 ? CT : 32];
+        const float sum = row_exps<CT>(conf_b + (long long)p * prm.C, prm.C, e);
+        const int nf = CT > 0 ? CT - 1 : n_fg;
+#pragma unroll
+        for (int k = 0; k < nf; ++k) {
+            const float s = fdiv(e[k + 1], sum);           // softmax(conf)[..., 1:]  (SFS:388)
+            const bool on = s > prm.score_thresh;          // strict (SFS:402)
+            buf.dense[p * n_fg + k] = on ? ord_encode(s) : 0u;
             mine += on ? 1 : 0;
         }
     }
@@ -293,20 +357,82 @@ __global__ void __launch_bounds__(UT) predict_unit_kernel(const PredictParams pr
     const float* loc_b = prm.loc_all + 4ll * b * P;
     const bool want_atan = METRIC == SSDHOT_METRIC_CIOU;
     auto fetch = [&](unsigned idx) -> BoxC {
-        const unsigned p = AGN ? idx / (unsigned)n_fg : idx;
+        const unsigned p = idx / (unsigned)n_fg;
         const float4 box = decode_box(ldg4(loc_b + 4ll * p), ldg4(prm.pri + 4ll * p), prm.vc, prm.vs);
         const float4 px = to_pixel_xyxy(box, prm.img_w, prm.img_h);
         return box_consts(px.x, px.y, px.z, px.w, want_atan);
     };
+    auto group_of = [&](unsigned idx) -> int { return (int)(idx % (unsigned)n_fg); };
+    const long long o = (long long)b * prm.max_keep;
+    auto emit = [&](int pos, unsigned long long key, unsigned idx, const BoxC& bx) {
+        prm.out_labels[o + pos] = (int64_t)(idx % (unsigned)n_fg);
+        prm.out_scores[o + pos] = ord_decode((unsigned)(key >> 32));
+        reinterpret_cast<float4*>(prm.out_boxes)[o + pos] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
+        if (prm.out_cand) prm.out_cand[o + pos] = (int32_t)idx;
+    };
+    const int kept_n = nms_unit<METRIC, PT, !AGN>(buf, n, n_cand, prm.max_keep, prm.nms_thresh, us, fetch, group_of, emit);
+    if (tid == 0) prm.out_count[b] = kept_n;
+}
+
+// Fallback for class counts whose dense score array does not fit in shared memory: one CTA per
+// (image, class) (or per image when class-agnostic and it fits), lists merged afterwards.
+template <int METRIC>
+__global__ void __launch_bounds__(UT) predict_class_kernel(const PredictParams prm) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ UnitShared us;
+    const int tid = threadIdx.x;
+    const int n_fg = prm.C - 1;
+    const int b = blockIdx.x / n_fg, c = blockIdx.x % n_fg;
+    const int P = prm.P;
+    const UnitBuffers buf = carve_unit(dyn, P, prm.max_keep);
+
+    int mine = 0;
+    const float* conf_b = prm.conf_all + (long long)b * P * prm.C;
+    for (int p = tid; p < P; p += UT) {
+        const float* row = conf_b + (long long)p * prm.C;
+        float sum;
+        float ec;
+        if (prm.C <= 32) {
+            float e[32];
+            sum = row_exps<0>(row, prm.C, e);
+            ec = e[c + 1];
+        } else {
+            // C > 32: eager torch-CUDA keeps ceil(C/32) elements per lane, summed in order, then the butterfly
+            float mx = __ldg(row);
+            for (int i = 1; i < prm.C; ++i) mx = fmaxf(mx, __ldg(row + i));
+            float part[32];
+            for (int l = 0; l < 32; ++l) part[l] = 0.0f;
+            for (int i = 0; i < prm.C; ++i) part[i & 31] = fadd(part[i & 31], expf(fsub(__ldg(row + i), mx)));
+            for (int off = 16; off > 0; off >>= 1)
+                for (int l = 0; l < off; ++l) part[l] = fadd(part[l], part[l + off]);
+            sum = part[0];
+            ec = expf(fsub(__ldg(row + c + 1), mx));
+        }
+        const float s = fdiv(ec, sum);
+        const bool on = s > prm.score_thresh;
+        buf.dense[p] = on ? ord_encode(s) : 0u;
+        mine += on ? 1 : 0;
+    }
+    const int n_cand = block_sum<int>(mine, us.iscratch);
+    __syncthreads();
+
+    const float* loc_b = prm.loc_all + 4ll * b * P;
+    const bool want_atan = METRIC == SSDHOT_METRIC_CIOU;
+    auto fetch = [&](unsigned idx) -> BoxC {
+        const float4 box = decode_box(ldg4(loc_b + 4ll * idx), ldg4(prm.pri + 4ll * idx), prm.vc, prm.vs);
+        const float4 px = to_pixel_xyxy(box, prm.img_w, prm.img_h);
+        return box_consts(px.x, px.y, px.z, px.w, want_atan);
+    };
+    auto group_of = [&](unsigned) -> int { return 0; };
     unsigned long long* out_key = prm.list_key + (long long)blockIdx.x * prm.max_keep;
     float4* out_box = prm.list_box + (long long)blockIdx.x * prm.max_keep;
     auto emit = [&](int pos, unsigned long long key, unsigned idx, const BoxC& bx) {
         // re-key by the flat candidate id prior*(C-1)+class so that lists of different classes merge
-        const unsigned flat = AGN ? idx : idx * (unsigned)n_fg + (unsigned)c;
+        const unsigned flat = idx * (unsigned)n_fg + (unsigned)c;
         out_key[pos] = (key & 0xffffffff00000000ull) | (unsigned long long)(0xffffffffu - flat);
         out_box[pos] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
     };
-    const int kept_n = nms_unit<METRIC>(dense, n, n_cand, ckey, cbox, kept, prm.max_keep, prm.nms_thresh, us, fetch, emit);
+    const int kept_n = nms_unit<METRIC, UT, false>(buf, P, n_cand, prm.max_keep, prm.nms_thresh, us, fetch, group_of, emit);
     if (tid == 0) prm.list_count[blockIdx.x] = kept_n;
 }
 
@@ -363,12 +489,15 @@ __global__ void __launch_bounds__(UT) nms_sets_kernel(const float* __restrict__ 
     const int tid = threadIdx.x;
     const int begin = set_offsets[blockIdx.x];
     const int n = set_offsets[blockIdx.x + 1] - begin;
-    BoxC* cbox = reinterpret_cast<BoxC*>(dyn);
-    unsigned long long* ckey = reinterpret_cast<unsigned long long*>(cbox + CHUNK);
-    unsigned* dense = reinterpret_cast<unsigned*>(ckey + CHUNK);
+    UnitBuffers buf;
+    buf.cbox = reinterpret_cast<BoxC*>(dyn);
+    buf.ckey = reinterpret_cast<unsigned long long*>(buf.cbox + CHUNK);
+    buf.dense = reinterpret_cast<unsigned*>(buf.ckey + CHUNK);
+    buf.kept = kept_all + begin;            // survivors of a stand-alone call are unbounded: global memory
+    buf.cgroup = nullptr; buf.kgroup = nullptr;
     for (int i = tid; i < n; i += UT) {
         const unsigned k = ord_encode(__ldg(scores + begin + i));
-        dense[i] = k == 0u ? 1u : k;
+        buf.dense[i] = k == 0u ? 1u : k;
     }
     __syncthreads();
     const bool want_atan = METRIC == SSDHOT_METRIC_CIOU;
@@ -376,10 +505,11 @@ __global__ void __launch_bounds__(UT) nms_sets_kernel(const float* __restrict__ 
         const float4 bx = ldg4(boxes + 4ll * (begin + (long long)idx));
         return box_consts(bx.x, bx.y, bx.z, bx.w, want_atan);
     };
+    auto group_of = [&](unsigned) -> int { return 0; };
     int64_t* out = keep + begin;
     auto emit = [&](int pos, unsigned long long, unsigned idx, const BoxC&) { out[pos] = (int64_t)idx; };
     const int cap = (max_keep > 0 && max_keep < n) ? max_keep : n;
-    const int kept_n = nms_unit<METRIC>(dense, n, n, ckey, cbox, kept_all + begin, cap, thr, us, fetch, emit);
+    const int kept_n = nms_unit<METRIC, UT, false>(buf, n, n, cap, thr, us, fetch, group_of, emit);
     if (tid == 0) keep_count[blockIdx.x] = kept_n;
 }
 
@@ -394,8 +524,7 @@ constexpr size_t kMaxDynSmem = 227 * 1024 - sizeof(UnitShared) - 1024;
 
 template <typename K>
 static int set_smem(K kern, size_t bytes) {
-    // one static per kernel instantiation (K is a distinct function type only per signature, so key
-    // on the pointer): the opt-in is sticky, so it is raised once and never inside a graph capture
+    // the opt-in is sticky per kernel, so it is raised once and never inside a graph capture
     if (bytes > kMaxDynSmem) return SSDHOT_ERR_SHAPE;
     static std::mutex mu;
     static std::map<const void*, size_t> configured;
@@ -412,17 +541,24 @@ static int set_smem(K kern, size_t bytes) {
 }
 
 template <int METRIC, bool AGN>
-static int launch_predict(const PredictParams& prm, size_t dyn, int grid, cudaStream_t stream) {
+static int launch_predict_image(const PredictParams& prm, size_t dyn, cudaStream_t stream) {
     int rc;
     if (prm.C == 6) {
-        rc = set_smem(predict_unit_kernel<METRIC, AGN, 6>, dyn);
-        if (rc) return rc;
-        predict_unit_kernel<METRIC, AGN, 6><<<grid, UT, dyn, stream>>>(prm);
+        if ((rc = set_smem(predict_image_kernel<METRIC, AGN, 6>, dyn))) return rc;
+        predict_image_kernel<METRIC, AGN, 6><<<prm.B, PT, dyn, stream>>>(prm);
     } else {
-        rc = set_smem(predict_unit_kernel<METRIC, AGN, 0>, dyn);
-        if (rc) return rc;
-        predict_unit_kernel<METRIC, AGN, 0><<<grid, UT, dyn, stream>>>(prm);
+        if ((rc = set_smem(predict_image_kernel<METRIC, AGN, 0>, dyn))) return rc;
+        predict_image_kernel<METRIC, AGN, 0><<<prm.B, PT, dyn, stream>>>(prm);
     }
+    SSDHOT_CHECK_LAUNCH();
+    return SSDHOT_OK;
+}
+
+template <int METRIC>
+static int launch_predict_class(const PredictParams& prm, size_t dyn, cudaStream_t stream) {
+    int rc;
+    if ((rc = set_smem(predict_class_kernel<METRIC>, dyn))) return rc;
+    predict_class_kernel<METRIC><<<prm.B * (prm.C - 1), UT, dyn, stream>>>(prm);
     SSDHOT_CHECK_LAUNCH();
     return SSDHOT_OK;
 }
@@ -498,26 +634,37 @@ extern "C" int ssdhot_predict(const float* priors_cxcywh, int P, const float* lo
     if (metric != SSDHOT_METRIC_DIOU && metric != SSDHOT_METRIC_CIOU && metric != SSDHOT_METRIC_IOU) return SSDHOT_ERR_VALUE;
     if (!al16(priors_cxcywh) || !al16(loc_all) || !al16(out_boxes) || !al16(work) ||
         (reinterpret_cast<uintptr_t>(conf_all) & 7u)) return SSDHOT_ERR_ALIGN;
-    const int units = class_agnostic ? 1 : C - 1;
-    const long long lists = (long long)B * units;
     PredictParams prm = {};
     prm.pri = priors_cxcywh; prm.P = P; prm.loc_all = loc_all; prm.conf_all = conf_all; prm.B = B; prm.C = C;
     prm.score_thresh = score_thresh; prm.nms_thresh = nms_thresh; prm.max_keep = max_per_img;
     prm.vc = var_center; prm.vs = var_size; prm.img_w = img_w; prm.img_h = img_h;
+    prm.out_labels = out_labels; prm.out_scores = out_scores; prm.out_boxes = out_boxes; prm.out_cand = out_cand;
+    prm.out_count = out_count;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    // preferred: one CTA per image, all classes in one score-ordered stream
+    const size_t dyn_image = unit_smem_bytes((long long)P * (C - 1), max_per_img);
+    if (dyn_image <= kMaxDynSmem && C <= 32) {
+#define SSDHOT_DISPATCH(M) rc = class_agnostic ? launch_predict_image<M, true>(prm, dyn_image, s) : launch_predict_image<M, false>(prm, dyn_image, s)
+        if (metric == SSDHOT_METRIC_DIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_DIOU); }
+        else if (metric == SSDHOT_METRIC_CIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_CIOU); }
+        else { SSDHOT_DISPATCH(SSDHOT_METRIC_IOU); }
+#undef SSDHOT_DISPATCH
+        return rc;
+    }
+    // fallback (many classes): one CTA per (image, class), then a merge; class-agnostic NMS over a
+    // candidate set that does not fit in shared memory is not supported
+    if (class_agnostic) return SSDHOT_ERR_SHAPE;
+    const int units = C - 1;
+    const long long lists = (long long)B * units;
     unsigned char* w = reinterpret_cast<unsigned char*>(work);
     prm.list_box = reinterpret_cast<float4*>(w); w += (size_t)lists * max_per_img * 16;
     prm.list_key = reinterpret_cast<unsigned long long*>(w); w += (size_t)lists * max_per_img * 8;
     prm.list_count = reinterpret_cast<int*>(w);
-    const long long n = class_agnostic ? (long long)P * (C - 1) : P;
-    const size_t dyn = (size_t)max_per_img * sizeof(BoxC) + (size_t)CHUNK * (sizeof(BoxC) + 8) + (size_t)n * 4;
-    cudaStream_t s = (cudaStream_t)stream;
-    int rc;
-#define SSDHOT_DISPATCH(M)                                                                   \
-    rc = class_agnostic ? launch_predict<M, true>(prm, dyn, (int)lists, s) : launch_predict<M, false>(prm, dyn, (int)lists, s)
-    if (metric == SSDHOT_METRIC_DIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_DIOU); }
-    else if (metric == SSDHOT_METRIC_CIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_CIOU); }
-    else { SSDHOT_DISPATCH(SSDHOT_METRIC_IOU); }
-#undef SSDHOT_DISPATCH
+    const size_t dyn = unit_smem_bytes(P, max_per_img);
+    if (metric == SSDHOT_METRIC_DIOU) rc = launch_predict_class<SSDHOT_METRIC_DIOU>(prm, dyn, s);
+    else if (metric == SSDHOT_METRIC_CIOU) rc = launch_predict_class<SSDHOT_METRIC_CIOU>(prm, dyn, s);
+    else rc = launch_predict_class<SSDHOT_METRIC_IOU>(prm, dyn, s);
     if (rc) return rc;
     merge_lists_kernel<<<B, 256, 0, s>>>(prm.list_key, prm.list_box, prm.list_count, units, max_per_img, C - 1,
                                          out_labels, out_scores, out_boxes, out_cand, out_count);

@@ -1,11 +1,22 @@
 // train_path.cu -- match + encode + mined multibox loss.
 //
-// Decomposition: one thread-block CLUSTER per image (up to 8 CTAs of 256 threads), each CTA owns
-// a contiguous slice of the priors and each thread keeps KP of them in registers.  The image's
+// Decomposition: one thread-block CLUSTER per image (8 CTAs of 256 threads), each CTA owns a
+// contiguous slice of the priors and each thread keeps KP of them in registers.  The image's
 // ground truth lives in shared memory with its per-box constants.  Column arg-max (best prior per
 // ground truth), the positive count and the hard-negative radix select are combined across the
 // cluster through distributed shared memory; nothing of shape [B,P] touches HBM unless the
 // caller asks for it.
+//
+// The CIoU sweep runs in one of two forms:
+//  * exact-everywhere (PRUNE = false): every (prior, box) pair is evaluated; needed only when the
+//    caller wants the matched box / offsets of NEGATIVE priors too (the encode_ssd signature);
+//  * pruned (PRUNE = true, the hot path): a pair is evaluated only if its IoU can matter.  Per box g
+//    a lower bound cb0[g] of the column maximum is taken from ~30 "seed" priors (the ones whose
+//    cell contains the box centre on each pyramid level); CIoU <= IoU always, so a pair with
+//    intersection < lim[g] * union, lim[g] = 0.999 * min(cb0[g], iou_thresh), can neither be the
+//    column champion (its CIoU < cb0[g] <= max) nor make its prior positive (CIoU < iou_thresh).
+//    Positives, their matched boxes and the forced champions are therefore bit-identical to the
+//    exact sweep while ~98 % of the pairs cost 13 instructions instead of ~75.
 #include "boxmath.cuh"
 
 namespace ssdhot {
@@ -14,6 +25,7 @@ constexpr int TT = 256;          // threads per CTA
 constexpr int KP = 5;            // priors per thread
 constexpr int SLOTS = TT * KP;   // prior slots per CTA
 constexpr int MAX_CS = 8;        // portable cluster size
+constexpr float kPruneSlack = 0.999f;
 
 enum { MODE_MATCH = 0, MODE_LOSS = 1, MODE_FUSED = 2 };
 
@@ -38,20 +50,28 @@ struct TrainParams {
     int32_t* flags;
 };
 
+// SSD300 pyramid (SSD_from_scratch.py:289-290): used only to pick seed priors, never for results
+__constant__ int kLevelSide[6] = {38, 19, 10, 5, 3, 1};
+__constant__ int kLevelShapes[6] = {4, 6, 6, 6, 4, 4};
+__constant__ int kLevelOffset[6] = {0, 5776, 7942, 8542, 8692, 8728};
+__constant__ int kSeedLevel[32] = {0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0, 1};
+__constant__ int kSeedShape[32] = {0, 1, 2, 3, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 0, 1, 2, 3, 0, 0};
+
 // ---------------------------------------------------------------------------------------------
 // shared-memory carve-up (dynamic): ground-truth records, column keys, champions, forced table
 // ---------------------------------------------------------------------------------------------
 struct Smem {
     float4* gt_a;              // [G] x1 y1 x2 y2 (normalised)
     float4* gt_b;              // [G] area xc yc atan
-    int* gt_label;             // [G]
     unsigned long long* col;   // [G] packed (ord(ciou) << 32 | ~prior) of this CTA's best prior per GT
+    int* gt_label;             // [G]
     unsigned* champ;           // [G] cluster-wide best prior per GT
+    float* lim;                // [G] prune bound (PRUNE) -- see header
     int* forced;               // [SLOTS] lowest GT index that forces this prior, or INT_MAX
 };
 
 __host__ __device__ inline size_t smem_bytes(int g_cap) {
-    return (size_t)g_cap * (16 + 16 + 4 + 8 + 4) + (size_t)SLOTS * 4 + 64;
+    return (size_t)g_cap * (16 + 16 + 8 + 4 + 4 + 4) + (size_t)SLOTS * 4 + 64;
 }
 
 __device__ __forceinline__ Smem carve(unsigned char* base, int g_cap) {
@@ -61,6 +81,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int g_cap) {
     s.col = reinterpret_cast<unsigned long long*>(base); base += (size_t)g_cap * 8;
     s.gt_label = reinterpret_cast<int*>(base); base += (size_t)g_cap * 4;
     s.champ = reinterpret_cast<unsigned*>(base); base += (size_t)g_cap * 4;
+    s.lim = reinterpret_cast<float*>(base); base += (size_t)g_cap * 4;
     s.forced = reinterpret_cast<int*>(base);
     return s;
 }
@@ -73,6 +94,7 @@ struct Static {                 // static shared state used by the cluster excha
     int npos_cta;               // positives in this CTA (read remotely)
     int ties_cta;               // elements equal to the threshold in this CTA (read remotely)
     int first_nan;              // lowest GT index whose CIoU column is NaN, or INT_MAX
+    int refill;                 // some column needs the exact sweep after all (PRUNE fallback)
     unsigned sel_digit, sel_need;
 };
 
@@ -106,10 +128,36 @@ __device__ __forceinline__ void row_lse(const float* __restrict__ row, int C, fl
     }
 }
 
+__device__ __forceinline__ BoxC load_prior(const float* __restrict__ xyxy, const float* __restrict__ aux, int p) {
+    const float4 a = ldg4(xyxy + 4ll * p), x = ldg4(aux + 4ll * p);
+    BoxC r;
+    r.x1 = a.x; r.y1 = a.y; r.x2 = a.z; r.y2 = a.w; r.area = x.x; r.xc = x.y; r.yc = x.z; r.at = x.w;
+    return r;
+}
+
+__device__ __forceinline__ BoxC gt_box(const float4 ga, const float4 gb) {
+    BoxC g;
+    g.x1 = ga.x; g.y1 = ga.y; g.x2 = ga.z; g.y2 = ga.w; g.area = gb.x; g.xc = gb.y; g.yc = gb.z; g.at = gb.w;
+    return g;
+}
+
+// one column of the exact sweep for this thread's priors (used by PRUNE = false and by the fallback)
+struct ColBest { float v; unsigned p; };
+
+__device__ __forceinline__ void publish_column(const ColBest cb, unsigned long long* slot) {
+    const unsigned enc = (cb.p == 0xffffffffu) ? 0u : ord_encode(cb.v);
+    const unsigned wmax = __reduce_max_sync(FULL, enc);
+    const unsigned wmin = __reduce_min_sync(FULL, enc == wmax ? cb.p : 0xffffffffu);
+    if ((threadIdx.x & 31) == 0 && wmin != 0xffffffffu) {
+        const unsigned long long key = ((unsigned long long)wmax << 32) | (unsigned long long)(0xffffffffu - wmin);
+        if (key > *slot) atomicMax(slot, key);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int MODE, int CT>
+template <int MODE, int CT, bool PRUNE>
 __global__ void __launch_bounds__(TT) train_kernel(const TrainParams prm) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ Static st;
@@ -118,7 +166,7 @@ __global__ void __launch_bounds__(TT) train_kernel(const TrainParams prm) {
     const int cs = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     const int b = blockIdx.x / cs;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = prm.P;
     const int chunk = (P + cs - 1) / cs;
     const int p0 = rank * chunk;
@@ -145,7 +193,7 @@ __global__ void __launch_bounds__(TT) train_kernel(const TrainParams prm) {
 
     if (MODE != MODE_LOSS) {
         // ---- stage ground truth ------------------------------------------------------------
-        if (tid == 0) st.first_nan = INT_MAX;
+        if (tid == 0) { st.first_nan = INT_MAX; st.refill = 0; }
         for (int i = tid; i < SLOTS; i += TT) sm.forced[i] = INT_MAX;
         __syncthreads();
         for (int g = tid; g < G; g += TT) {
@@ -156,58 +204,121 @@ __global__ void __launch_bounds__(TT) train_kernel(const TrainParams prm) {
             sm.gt_b[g] = make_float4(c.area, c.xc, c.yc, c.at);
             sm.gt_label[g] = (int)prm.gt_labels[g_begin + g];
             sm.col[g] = 0ull;
+            sm.lim[g] = 1e-30f;      // overlap-only pruning until a seed raises it
             if (c.at != c.at) atomicMin(&st.first_nan, g);
         }
         __syncthreads();
 
+        if (PRUNE && P == 8732) {
+            // ---- seeds: a lower bound of every column maximum from ~30 well-placed priors ----
+            for (int g = warp; g < G; g += TT / 32) {
+                const float4 ga = sm.gt_a[g], gb = sm.gt_b[g];
+                const int lv = kSeedLevel[lane], side = kLevelSide[lv];
+                int ix = (int)floorf(gb.y * (float)side), iy = (int)floorf(gb.z * (float)side);
+                ix = min(max(ix, 0), side - 1);
+                iy = min(max(iy, 0), side - 1);
+                const int ps = kLevelOffset[lv] + (iy * side + ix) * kLevelShapes[lv] + kSeedShape[lane];
+                const float v = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, ps), gt_box(ga, gb));
+                const float cb0 = ord_decode(__reduce_max_sync(FULL, ord_encode(v)));   // NaN sorts to the top
+                if (lane == 0 && cb0 > 0.0f) sm.lim[g] = fmaxf(fmul(kPruneSlack, fminf(cb0, prm.thresh)), 1e-30f);
+            }
+            __syncthreads();
+        }
+
         // ---- CIoU sweep: row arg-max in registers, column arg-max per warp -> shared ---------
-        BoxC pr[KP];
+        float4 pb[KP];      // x1 y1 x2 y2 of this thread's priors
+        float pa[KP];       // their areas
         bool valid[KP];
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
             const int p = p0 + k * TT + tid;
             valid[k] = p < p1;
             const int q = valid[k] ? p : p0;
-            const float4 a = ldg4(prm.pri_xyxy + 4ll * q), x = ldg4(prm.pri_aux + 4ll * q);
-            pr[k].x1 = a.x; pr[k].y1 = a.y; pr[k].x2 = a.z; pr[k].y2 = a.w;
-            pr[k].area = x.x; pr[k].xc = x.y; pr[k].yc = x.z; pr[k].at = x.w;
+            pb[k] = ldg4(prm.pri_xyxy + 4ll * q);
+            pa[k] = __ldg(prm.pri_aux + 4ll * q);
         }
-        const int lane = tid & 31;
         for (int g = 0; g < G; ++g) {
             const float4 ga = sm.gt_a[g], gb = sm.gt_b[g];
             if (gb.w != gb.w) continue;            // NaN column (degenerate box): handled below
-            BoxC gc;
-            gc.x1 = ga.x; gc.y1 = ga.y; gc.x2 = ga.z; gc.y2 = ga.w;
-            gc.area = gb.x; gc.xc = gb.y; gc.yc = gb.z; gc.at = gb.w;
-            float cbest = -INFINITY;
-            unsigned cidx = 0xffffffffu;
+            const BoxC gc = gt_box(ga, gb);
+            const float lim = PRUNE ? sm.lim[g] : 0.0f;
+            ColBest cb = {-INFINITY, 0xffffffffu};
 #pragma unroll
             for (int k = 0; k < KP; ++k) {
-                const float v = pair_ciou(pr[k], gc);
-                if (v > best_v[k]) { best_v[k] = v; best_g[k] = g; }
-                if (valid[k] && v > cbest) { cbest = v; cidx = (unsigned)(p0 + k * TT + tid); }
+                bool go = true;
+                if (PRUNE) {
+                    const float w = fmaxf(fsub(fminf(pb[k].z, gc.x2), fmaxf(pb[k].x, gc.x1)), 0.0f);
+                    const float h = fmaxf(fsub(fminf(pb[k].w, gc.y2), fmaxf(pb[k].y, gc.y1)), 0.0f);
+                    const float inter = fmul(w, h);
+                    const float uni = fsub(fadd(pa[k], gc.area), inter);
+                    go = !(inter < fmul(lim, uni));          // NaN-safe: anything odd takes the exact path
+                }
+                if (!PRUNE || __any_sync(FULL, go)) {
+                    if (go) {
+                        const int q = valid[k] ? p0 + k * TT + tid : p0;
+                        const float4 x = ldg4(prm.pri_aux + 4ll * q);
+                        BoxC pr;
+                        pr.x1 = pb[k].x; pr.y1 = pb[k].y; pr.x2 = pb[k].z; pr.y2 = pb[k].w;
+                        pr.area = x.x; pr.xc = x.y; pr.yc = x.z; pr.at = x.w;
+                        const float v = pair_ciou(pr, gc);
+                        if (v > best_v[k]) { best_v[k] = v; best_g[k] = g; }
+                        if (valid[k] && v > cb.v) { cb.v = v; cb.p = (unsigned)(p0 + k * TT + tid); }
+                    }
+                }
             }
-            const unsigned enc = (cidx == 0xffffffffu) ? 0u : ord_encode(cbest);
-            const unsigned wmax = __reduce_max_sync(FULL, enc);
-            const unsigned wmin = __reduce_min_sync(FULL, enc == wmax ? cidx : 0xffffffffu);
-            if (lane == 0 && wmin != 0xffffffffu) {
-                const unsigned long long key = ((unsigned long long)wmax << 32) | (unsigned long long)(0xffffffffu - wmin);
-                if (key > sm.col[g]) atomicMax(&sm.col[g], key);
-            }
+            if (!PRUNE || __any_sync(FULL, cb.p != 0xffffffffu)) publish_column(cb, &sm.col[g]);
         }
         // ---- cluster-wide champions --------------------------------------------------------
         cluster.sync();
         for (int g = tid; g < G; g += TT) {
             unsigned long long key = 0ull;
             for (int r = 0; r < cs; ++r) {
-                const unsigned long long* remote = cluster.map_shared_rank(sm.col, r);
-                const unsigned long long kr = remote[g];
+                const unsigned long long kr = cluster.map_shared_rank(sm.col, r)[g];
                 key = kr > key ? kr : key;
             }
             const float4 gb = sm.gt_b[g];
-            const unsigned champ = (gb.w != gb.w) ? 0u : (0xffffffffu - (unsigned)(key & 0xffffffffull));
+            const bool nan_col = gb.w != gb.w;
+            // PRUNE fallback: a column whose pruned maximum is not positive (box outside every prior,
+            // or seeds that bound nothing) is redone exactly
+            if (PRUNE && !nan_col && !((unsigned)(key >> 32) > ord_encode(0.0f))) st.refill = 1;
+            const unsigned champ = nan_col ? 0u : (0xffffffffu - (unsigned)(key & 0xffffffffull));
             sm.champ[g] = champ;
-            if ((int)champ >= p0 && (int)champ < p1) atomicMin(&sm.forced[(int)champ - p0], g);
+        }
+        __syncthreads();
+        if (PRUNE) {
+            // every CTA of the cluster reads the same keys, so `refill` is cluster-uniform
+            if (st.refill) {
+                cluster.sync();                       // all peers are done reading sm.col
+                for (int g = 0; g < G; ++g) {
+                    const float4 ga = sm.gt_a[g], gb = sm.gt_b[g];
+                    if (gb.w != gb.w) continue;
+                    const BoxC gc = gt_box(ga, gb);
+                    ColBest cb = {-INFINITY, 0xffffffffu};
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) {
+                        const int q = valid[k] ? p0 + k * TT + tid : p0;
+                        const float v = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, q), gc);
+                        if (v > best_v[k] || (v == best_v[k] && g < best_g[k])) { best_v[k] = v; best_g[k] = g; }
+                        if (valid[k] && v > cb.v) { cb.v = v; cb.p = (unsigned)q; }
+                    }
+                    publish_column(cb, &sm.col[g]);
+                }
+                cluster.sync();
+                for (int g = tid; g < G; g += TT) {
+                    unsigned long long key = 0ull;
+                    for (int r = 0; r < cs; ++r) {
+                        const unsigned long long kr = cluster.map_shared_rank(sm.col, r)[g];
+                        key = kr > key ? kr : key;
+                    }
+                    const float4 gb = sm.gt_b[g];
+                    sm.champ[g] = (gb.w != gb.w) ? 0u : (0xffffffffu - (unsigned)(key & 0xffffffffull));
+                }
+                __syncthreads();
+            }
+        }
+        for (int g = tid; g < G; g += TT) {
+            const int champ = (int)sm.champ[g];
+            if (champ >= p0 && champ < p1) atomicMin(&sm.forced[champ - p0], g);
         }
         __syncthreads();
         const int first_nan = st.first_nan;
@@ -263,7 +374,48 @@ __global__ void __launch_bounds__(TT) train_kernel(const TrainParams prm) {
         if (tid == 0) st.npos_cta = cta_pos;
     }
 
-    // ---- positives of the whole image ------------------------------------------------------
+    // ---- per-prior losses (MODE_MATCH skips) -------------------------------------------------
+    float ce[KP];
+    unsigned key[KP];        // CE bits of negatives (CE >= 0, so the bit pattern orders them); 0 otherwise
+    bool neg[KP];
+    double acc_loc = 0.0, acc_ce = 0.0;
+    if (MODE != MODE_MATCH) {
+        for (int i = tid; i < 256; i += TT) st.hist[0][i] = 0u;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const int p = p0 + k * TT + tid;
+            ce[k] = 0.0f; key[k] = 0u; neg[k] = false;
+            if (p >= p1) continue;
+            const long long row = (long long)b * P + p;
+            float mx, lg;
+            row_lse<CT>(prm.conf_all + row * prm.C, prm.C, mx, lg);
+            const float xc = __ldg(prm.conf_all + row * prm.C + cls[k]);
+            // -log_softmax[c] = -((x_c - max) - log(sum))  (ATen PersistentSoftmax.cuh, nll_loss)
+            ce[k] = -fsub(fsub(xc, mx), lg);
+            if (pos[k]) {
+                acc_ce += (double)ce[k];
+                if (MODE == MODE_FUSED) {
+                    const float4 ga = sm.gt_a[best_g[k]], gb = sm.gt_b[best_g[k]];
+                    const float4 gbox = make_float4(gb.y, gb.z, fsub(ga.z, ga.x), fsub(ga.w, ga.y));
+                    const float4 t = encode_offsets(gbox, ldg4(prm.pri + 4ll * p), prm.inv_vc, prm.inv_vs);
+                    const float4 l = ldg4(prm.loc_all + 4ll * row);
+                    const float d[4] = {fsub(l.x, t.x), fsub(l.y, t.y), fsub(l.z, t.z), fsub(l.w, t.w)};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float z = fabsf(d[j]);
+                        acc_loc += (double)(z < 1.0f ? fmul(fmul(0.5f, z), z) : fsub(z, 0.5f));
+                    }
+                }
+            } else {
+                neg[k] = true;
+                key[k] = __float_as_uint(ce[k]);
+                atomicAdd(&st.hist[0][key[k] >> 24], 1u);      // first radix pass rides along
+            }
+        }
+    }
+
+    // ---- positives of the whole image (+ first histogram) -----------------------------------
     cluster.sync();
     int n_pos_img = 0;
     for (int r = 0; r < cs; ++r) n_pos_img += cluster.map_shared_rank(&st, r)->npos_cta;
@@ -273,42 +425,6 @@ __global__ void __launch_bounds__(TT) train_kernel(const TrainParams prm) {
         return;
     }
 
-    // ---- per-prior losses -------------------------------------------------------------------
-    float ce[KP];
-    unsigned key[KP];        // CE bits of negatives (CE >= 0, so the bit pattern orders them); 0 otherwise
-    bool neg[KP];
-    double acc_loc = 0.0, acc_ce = 0.0;
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-        const int p = p0 + k * TT + tid;
-        ce[k] = 0.0f; key[k] = 0u; neg[k] = false;
-        if (p >= p1) continue;
-        const long long row = (long long)b * P + p;
-        float mx, lg;
-        row_lse<CT>(prm.conf_all + row * prm.C, prm.C, mx, lg);
-        const float xc = __ldg(prm.conf_all + row * prm.C + cls[k]);
-        // -log_softmax[c] = -((x_c - max) - log(sum))  (ATen PersistentSoftmax.cuh, nll_loss)
-        ce[k] = -fsub(fsub(xc, mx), lg);
-        if (pos[k]) {
-            acc_ce += (double)ce[k];
-            if (MODE == MODE_FUSED) {
-                const float4 ga = sm.gt_a[best_g[k]], gb = sm.gt_b[best_g[k]];
-                const float4 gbox = make_float4(gb.y, gb.z, fsub(ga.z, ga.x), fsub(ga.w, ga.y));
-                const float4 t = encode_offsets(gbox, ldg4(prm.pri + 4ll * p), prm.inv_vc, prm.inv_vs);
-                const float4 l = ldg4(prm.loc_all + 4ll * row);
-                const float d[4] = {fsub(l.x, t.x), fsub(l.y, t.y), fsub(l.z, t.z), fsub(l.w, t.w)};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float z = fabsf(d[j]);
-                    acc_loc += (double)(z < 1.0f ? fmul(fmul(0.5f, z), z) : fsub(z, 0.5f));
-                }
-            }
-        } else {
-            neg[k] = true;
-            key[k] = __float_as_uint(ce[k]);
-        }
-    }
-
     // ---- hard-negative budget (SSD_trainer.py:585-596) --------------------------------------
     const long long n_neg = (long long)P - n_pos_img;
     long long want = (n_pos_img == 0) ? (long long)prm.ratio : (long long)(prm.ratio * (double)n_pos_img);
@@ -316,20 +432,22 @@ __global__ void __launch_bounds__(TT) train_kernel(const TrainParams prm) {
     const long long kk = want < n_neg ? want : n_neg;
     unsigned thr_key = 0u;        // selected negatives: key > thr_key, plus `need` of those == thr_key
     unsigned need = 0u;
-    bool take_all = (kk >= n_neg);
+    const bool take_all = (kk >= n_neg);
     if (kk > 0 && !take_all) {
         // 4-pass MSD radix select of the kk-th largest key over the cluster
         unsigned prefix = 0u, remaining = (unsigned)kk;
         for (int pass = 0; pass < 4; ++pass) {
             const int shift = 24 - 8 * pass;
-            unsigned* h = st.hist[pass & 1];
-            for (int i = tid; i < 256; i += TT) h[i] = 0u;
-            __syncthreads();
-            const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+            if (pass > 0) {
+                unsigned* h = st.hist[pass & 1];
+                for (int i = tid; i < 256; i += TT) h[i] = 0u;
+                __syncthreads();
+                const unsigned himask = 0xffffffffu << (shift + 8);
 #pragma unroll
-            for (int k = 0; k < KP; ++k)
-                if (neg[k] && ((key[k] & himask) == prefix)) atomicAdd(&h[(key[k] >> shift) & 255u], 1u);
-            cluster.sync();
+                for (int k = 0; k < KP; ++k)
+                    if (neg[k] && ((key[k] & himask) == prefix)) atomicAdd(&h[(key[k] >> shift) & 255u], 1u);
+                cluster.sync();
+            }
             for (int i = tid; i < 256; i += TT) {
                 unsigned t = 0u;
                 for (int r = 0; r < cs; ++r) t += cluster.map_shared_rank(&st, r)->hist[pass & 1][i];
@@ -400,7 +518,6 @@ __global__ void __launch_bounds__(TT) train_kernel(const TrainParams prm) {
             const bool tie = kk > 0 && !take_all && neg[k] && key[k] == thr_key;
             if (!all_ties) {
                 const unsigned bal = __ballot_sync(FULL, tie);
-                const int lane = tid & 31, warp = tid >> 5;
                 __syncthreads();
                 if (lane == 0) st.iscratch[warp] = __popc(bal);
                 __syncthreads();
@@ -552,14 +669,14 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
 // host side
 // ---------------------------------------------------------------------------------------------
 
-template <int MODE, int CT>
+template <int MODE, int CT, bool PRUNE>
 static int launch_train(const TrainParams& prm, cudaStream_t stream) {
     // a fixed cluster of 8 balances best at SSD300 sizes (1092 priors per CTA); smaller P shrink it
     int cs = MAX_CS;
     while (cs > 1 && (cs / 2) * SLOTS >= prm.P && prm.P <= 2048) cs >>= 1;
     if (cs * SLOTS < prm.P) return SSDHOT_ERR_SHAPE;
     const size_t dyn = smem_bytes(prm.max_gt > 0 ? prm.max_gt : 1);
-    auto kern = train_kernel<MODE, CT>;
+    auto kern = train_kernel<MODE, CT, PRUNE>;
     static size_t configured = 0;      // per instantiation; sticky opt-in, raised outside graph capture
     if (dyn > 48 * 1024 && dyn > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -644,7 +761,10 @@ extern "C" int ssdhot_match_encode(const float* priors_cxcywh, const float* prio
     prm.thresh = iou_thresh; prm.inv_vc = 1.0f / var_center; prm.inv_vs = 1.0f / var_size;
     prm.loc_t = loc_t; prm.loc_pos_only = loc_positives_only; prm.cls_t = cls_t; prm.pos_mask = pos_mask;
     prm.matched32 = matched_gt; prm.matched_box = matched_cxcywh; prm.n_pos = n_pos; prm.flags = dev_flags;
-    return launch_train<MODE_MATCH, 0>(prm, (cudaStream_t)stream);
+    // the pruned sweep is exact for positives; negatives' matches need the exact-everywhere sweep
+    const bool prune = (!loc_t || loc_positives_only) && !matched_gt && !matched_cxcywh;
+    return prune ? launch_train<MODE_MATCH, 0, true>(prm, (cudaStream_t)stream)
+                 : launch_train<MODE_MATCH, 0, false>(prm, (cudaStream_t)stream);
 }
 
 extern "C" int ssdhot_compact_rows(const float* loc_t, const uint8_t* pos_mask, const int32_t* n_pos, int B, int P,
@@ -693,8 +813,8 @@ extern "C" int ssdhot_multibox_loss_fwd(const float* priors_cxcywh, const float*
     prm.cta_part = reinterpret_cast<double*>(work);
     int32_t* np = n_pos ? n_pos : reinterpret_cast<int32_t*>(prm.cta_part + (size_t)B * MAX_CS * 2);
     prm.n_pos = np; prm.sel_cls = sel_cls; prm.matched16 = matched_gt; prm.flags = dev_flags;
-    rc = (C == 6) ? launch_train<MODE_FUSED, 6>(prm, (cudaStream_t)stream)
-                  : launch_train<MODE_FUSED, 0>(prm, (cudaStream_t)stream);
+    rc = (C == 6) ? launch_train<MODE_FUSED, 6, true>(prm, (cudaStream_t)stream)
+                  : launch_train<MODE_FUSED, 0, true>(prm, (cudaStream_t)stream);
     if (rc) return rc;
     return finalize(prm, B * train_cluster_size(P), np, sums, (cudaStream_t)stream);
 }
@@ -712,8 +832,8 @@ extern "C" int ssdhot_mined_ce_fwd(const float* conf_all, const int64_t* cls_t, 
     prm.cta_part = reinterpret_cast<double*>(work);
     prm.n_pos = reinterpret_cast<int32_t*>(prm.cta_part + (size_t)B * MAX_CS * 2);
     prm.sel_cls = sel_cls;
-    int rc = (C == 6) ? launch_train<MODE_LOSS, 6>(prm, (cudaStream_t)stream)
-                      : launch_train<MODE_LOSS, 0>(prm, (cudaStream_t)stream);
+    int rc = (C == 6) ? launch_train<MODE_LOSS, 6, false>(prm, (cudaStream_t)stream)
+                      : launch_train<MODE_LOSS, 0, false>(prm, (cudaStream_t)stream);
     if (rc) return rc;
     return finalize(prm, B * train_cluster_size(P), prm.n_pos, sums, (cudaStream_t)stream);
 }

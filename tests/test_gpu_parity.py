@@ -393,3 +393,55 @@ def test_error_behaviour(env):
     assert L.ssdhot_decode(None, None, 4, 0.1, 0.2, None, None) == -1
     assert L.ssdhot_prior_tables(ps.priors.data_ptr(), 20000, ps.priors_xyxy.data_ptr(), ps.aux.data_ptr(), None) == -2
     assert L.ssdhot_decode(ps.priors.data_ptr() + 4, ps.priors.data_ptr(), 4, 0.1, 0.2, ps.aux.data_ptr(), None) == -5
+
+
+def test_many_classes_fallback_path(env):
+    """C = 21 (VOC-sized heads): the dense score array of one image no longer fits in shared memory,
+    so predict runs per (image, class) + merge; matching / loss run the generic-C code."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    gen = torch.Generator().manual_seed(21)
+    loc = torch.randn((2, 8732, 4), generator=gen).to(dev)
+    conf = torch.randn((2, 8732, 21), generator=gen)
+    conf[..., 0] += 5.0
+    conf = conf.to(dev)
+    want = O.postprocess(env["pri"], loc, conf, 0.02, 0.45, 100, False, nms_limit=True, with_index=True)
+    labels, scores, boxes, count, cand = s.predict_padded(ps, loc, conf, 0.02, 0.45, 100, want_cand=True)
+    for b in range(2):
+        k = int(count[b])
+        assert bit_equal(cand[b, :k].long(), want[b]["cand"]) and bit_equal(scores[b, :k], want[b]["scores"])
+        assert bit_equal(boxes[b, :k], want[b]["boxes"]) and bit_equal(labels[b, :k], want[b]["labels"])
+    from ssdhot import synth
+    targets = synth.make_targets(2, 3, 9, gen, n_fg=20)
+    tg = to_dev(targets, dev)
+    conf_t = torch.randn((2, 8732, 21), generator=gen).to(dev)
+    pos_o, locpm_o, cls_o = O.batch_targets(env["pri"], env["pri_xyxy"], tg, 300, 300, 0.5)
+    o_loc, n_img, total = O.loc_loss(loc, pos_o, locpm_o)
+    o_conf = O.mined_ce_loss(conf_t, cls_o, pos_o, n_img, total, 3.0)
+    l_loc, l_conf = s.multibox_loss(ps, loc, conf_t, targets, 0.5, 3.0)
+    assert abs(l_loc.item() - o_loc.item()) <= RTOL * abs(o_loc.item())
+    assert abs(l_conf.item() - o_conf.item()) <= RTOL * abs(o_conf.item())
+
+
+def test_pruned_sweep_equals_exact_sweep(env):
+    """The hot path prunes (prior, box) pairs that cannot matter; positives, classes, positives'
+    offsets and n_pos must be bit-identical to the exact-everywhere sweep -- including boxes outside
+    every prior's reach (fallback), tiny boxes and heavy crowding."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    from ssdhot import synth
+    gen = torch.Generator().manual_seed(5)
+    targets = synth.make_targets(24, 0, 40, gen)
+    f = lambda rows: torch.tensor(rows, dtype=torch.float32).reshape(-1, 4)
+    targets[1] = {"boxes": f([[310, 310, 330, 340], [-50, -40, -10, -5]]), "labels": torch.tensor([1, 2])}   # outside the image
+    targets[2] = {"boxes": f([[0, 0, 1, 1], [299, 299, 300, 300], [150, 150, 150.5, 150.5]]), "labels": torch.tensor([0, 1, 2])}
+    targets[3] = {"boxes": f([[100, 100, 100, 100]]), "labels": torch.tensor([3])}                         # NaN column only
+    packed = s.pack_targets(targets, dev)
+    for thr in (0.5, 0.2, 0.9):
+        exact = s.match_encode_batch(ps, packed, thr, (300, 300), want_loc="all", want_matched_idx=True)
+        pruned = s.match_encode_batch(ps, packed, thr, (300, 300), want_loc="positives")
+        assert bit_equal(pruned["pos_mask"], exact["pos_mask"]) and bit_equal(pruned["cls_t"], exact["cls_t"])
+        assert bit_equal(pruned["n_pos"], exact["n_pos"])
+        m = exact["pos_mask"]
+        assert bit_equal(pruned["loc_t"][m], exact["loc_t"][m])
+        tg = to_dev(targets, dev)
+        pos_o, _, cls_o = O.batch_targets(env["pri"], env["pri_xyxy"], tg, 300, 300, thr)
+        assert bit_equal(exact["pos_mask"], pos_o) and bit_equal(exact["cls_t"], cls_o)
