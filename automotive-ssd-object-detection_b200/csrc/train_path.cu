@@ -1,11 +1,14 @@
 // train_path.cu -- match + encode + mined multibox loss.
 //
-// Decomposition: one thread-block CLUSTER per image (8 CTAs of 256 threads), each CTA owns a
-// contiguous slice of the priors and each thread keeps KP of them in registers.  The image's
-// ground truth lives in shared memory with its per-box constants.  Column arg-max (best prior per
-// ground truth), the positive count and the hard-negative radix select are combined across the
-// cluster through distributed shared memory; nothing of shape [B,P] touches HBM unless the
-// caller asks for it.
+// Two kernels:
+//  * match_kernel -- one thread-block CLUSTER per image (8 CTAs of 256 threads); each CTA owns a
+//    contiguous slice of the priors, each thread keeps KP of them in registers, the image's ground
+//    truth lives in shared memory with its per-box constants, and the column arg-max (best prior
+//    per ground truth) is combined across the cluster through distributed shared memory.  On the
+//    fused-loss path its only output is a 2-byte code per prior (0 = negative, 1 + matched box).
+//  * loss_image_kernel -- one CTA of 1024 threads per image streams the class logits once
+//    (the HBM-bound part), forms softmax cross-entropy and smooth-L1 in registers and picks the
+//    hard negatives with a CTA-local 4-pass radix select; no [B,P] float tensor touches HBM.
 //
 // The CIoU sweep runs in one of two forms:
 //  * exact-everywhere (PRUNE = false): every (prior, box) pair is evaluated; needed only when the
@@ -27,7 +30,6 @@ constexpr int SLOTS = TT * KP;   // prior slots per CTA
 constexpr int MAX_CS = 8;        // portable cluster size
 constexpr float kPruneSlack = 0.999f;
 
-enum { MODE_MATCH = 0, MODE_LOSS = 1, MODE_FUSED = 2 };
 
 struct TrainParams {
     // priors
@@ -45,8 +47,9 @@ struct TrainParams {
     float* loc_t; int loc_pos_only; int64_t* cls_t; uint8_t* pos_mask; int32_t* matched32;
     float* matched_box; int32_t* n_pos;
     // loss outputs
-    double* cta_part;      // [B*CS][2]  (smooth-L1, CE) partial sums per CTA
     int8_t* sel_cls; int16_t* matched16;
+    uint16_t* code;        // [B,P] 0 = negative, 1 + matched box (fused path: match -> loss hand-off)
+    double* img_part;      // [B][2] per-image (smooth-L1, CE) sums
     int32_t* flags;
 };
 
@@ -157,8 +160,8 @@ __device__ __forceinline__ void publish_column(const ColBest cb, unsigned long l
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int MODE, int CT, bool PRUNE>
-__global__ void __launch_bounds__(TT) train_kernel(const TrainParams prm) {
+template <bool PRUNE>
+__global__ void __launch_bounds__(TT) match_kernel(const TrainParams prm) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ Static st;
 
@@ -172,14 +175,11 @@ __global__ void __launch_bounds__(TT) train_kernel(const TrainParams prm) {
     const int p0 = rank * chunk;
     const int p1 = min(P, p0 + chunk);
 
-    int g_begin = 0, G = 0;
-    if (MODE != MODE_LOSS) {
-        g_begin = prm.gt_offsets[b];
-        G = prm.gt_offsets[b + 1] - g_begin;
-        if (G > prm.max_gt) {
-            if (tid == 0 && rank == 0 && prm.flags) atomicOr(prm.flags, 1);
-            G = prm.max_gt;
-        }
+    const int g_begin = prm.gt_offsets[b];
+    int G = prm.gt_offsets[b + 1] - g_begin;
+    if (G > prm.max_gt) {
+        if (tid == 0 && rank == 0 && prm.flags) atomicOr(prm.flags, 1);
+        G = prm.max_gt;
     }
     Smem sm = carve(dyn, prm.max_gt > 0 ? prm.max_gt : 1);
 
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(TT) train_kernel(const TrainParams prm) {
 #pragma unroll
     for (int k = 0; k < KP; ++k) { best_g[k] = 0; best_v[k] = -INFINITY; pos[k] = false; cls[k] = 0; }
 
-    if (MODE != MODE_LOSS) {
+    {
         // ---- stage ground truth ------------------------------------------------------------
         if (tid == 0) { st.first_nan = INT_MAX; st.refill = 0; }
         for (int i = tid; i < SLOTS; i += TT) sm.forced[i] = INT_MAX;
@@ -338,7 +338,8 @@ __global__ void __launch_bounds__(TT) train_kernel(const TrainParams prm) {
             }
             my_pos += pos[k] ? 1 : 0;
             const long long row = (long long)b * P + p;
-            if (MODE == MODE_MATCH) {
+            if (prm.code) prm.code[row] = pos[k] ? (uint16_t)(best_g[k] + 1) : (uint16_t)0;
+            {
                 if (prm.pos_mask) prm.pos_mask[row] = pos[k] ? 1 : 0;
                 if (prm.cls_t) prm.cls_t[row] = (int64_t)cls[k];
                 if (prm.matched32) prm.matched32[row] = best_g[k];
@@ -357,73 +358,93 @@ __global__ void __launch_bounds__(TT) train_kernel(const TrainParams prm) {
         }
         const int cta_pos = block_sum<int>(my_pos, st.iscratch);
         if (tid == 0) st.npos_cta = cta_pos;
-    } else {
-        // ---- MODE_LOSS: targets are given --------------------------------------------------
-        int my_pos = 0;
-#pragma unroll
-        for (int k = 0; k < KP; ++k) {
-            const int p = p0 + k * TT + tid;
-            if (p < p1) {
-                const long long row = (long long)b * P + p;
-                pos[k] = prm.in_pos[row] != 0;
-                cls[k] = (int)prm.in_cls[row];
-                my_pos += pos[k] ? 1 : 0;
-            }
-        }
-        const int cta_pos = block_sum<int>(my_pos, st.iscratch);
-        if (tid == 0) st.npos_cta = cta_pos;
     }
 
-    // ---- per-prior losses (MODE_MATCH skips) -------------------------------------------------
-    float ce[KP];
-    unsigned key[KP];        // CE bits of negatives (CE >= 0, so the bit pattern orders them); 0 otherwise
-    bool neg[KP];
+    // ---- positives of the whole image (build_targets form only) ---------------------------
+    if (prm.n_pos) {
+        cluster.sync();
+        int n_pos_img = 0;
+        for (int r = 0; r < cs; ++r) n_pos_img += cluster.map_shared_rank(&st, r)->npos_cta;
+        if (rank == 0 && tid == 0) prm.n_pos[b] = n_pos_img;
+    }
+    cluster.sync();          // keep this CTA's shared memory alive until every peer has read it
+}
+
+// ---------------------------------------------------------------------------------------------
+// loss_image_kernel: CE + smooth-L1 + hard-negative mining of one image per CTA
+// ---------------------------------------------------------------------------------------------
+constexpr int LT = 1024;                       // threads
+constexpr int KQ = SSDHOT_MAX_PRIORS / LT;     // priors per thread (10 slots; 8732 uses 9)
+
+struct LossShared {
+    unsigned hist[256];
+    double dscratch[32];
+    int iscratch[32];
+    unsigned sel_digit, sel_need;
+};
+
+template <int CT, bool FROM_TARGETS>
+__global__ void __launch_bounds__(LT) loss_image_kernel(const TrainParams prm) {
+    __shared__ LossShared ls;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = prm.P;
+    const int g_begin = FROM_TARGETS ? 0 : prm.gt_offsets[b];
+
+    for (int i = tid; i < 256; i += LT) ls.hist[i] = 0u;
+    __syncthreads();
+
+    float ce[KQ];
+    unsigned key[KQ];        // CE bits of negatives (CE >= 0, so the bit pattern orders them); 0 otherwise
+    int tgt[KQ];             // -1 = negative (class 0), else target class of a positive
+    int mg[KQ];              // matched box of a positive
     double acc_loc = 0.0, acc_ce = 0.0;
-    if (MODE != MODE_MATCH) {
-        for (int i = tid; i < 256; i += TT) st.hist[0][i] = 0u;
-        __syncthreads();
+    int my_pos = 0;
 #pragma unroll
-        for (int k = 0; k < KP; ++k) {
-            const int p = p0 + k * TT + tid;
-            ce[k] = 0.0f; key[k] = 0u; neg[k] = false;
-            if (p >= p1) continue;
-            const long long row = (long long)b * P + p;
-            float mx, lg;
-            row_lse<CT>(prm.conf_all + row * prm.C, prm.C, mx, lg);
-            const float xc = __ldg(prm.conf_all + row * prm.C + cls[k]);
-            // -log_softmax[c] = -((x_c - max) - log(sum))  (ATen PersistentSoftmax.cuh, nll_loss)
-            ce[k] = -fsub(fsub(xc, mx), lg);
-            if (pos[k]) {
-                acc_ce += (double)ce[k];
-                if (MODE == MODE_FUSED) {
-                    const float4 ga = sm.gt_a[best_g[k]], gb = sm.gt_b[best_g[k]];
-                    const float4 gbox = make_float4(gb.y, gb.z, fsub(ga.z, ga.x), fsub(ga.w, ga.y));
-                    const float4 t = encode_offsets(gbox, ldg4(prm.pri + 4ll * p), prm.inv_vc, prm.inv_vs);
-                    const float4 l = ldg4(prm.loc_all + 4ll * row);
-                    const float d[4] = {fsub(l.x, t.x), fsub(l.y, t.y), fsub(l.z, t.z), fsub(l.w, t.w)};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float z = fabsf(d[j]);
-                        acc_loc += (double)(z < 1.0f ? fmul(fmul(0.5f, z), z) : fsub(z, 0.5f));
-                    }
-                }
-            } else {
-                neg[k] = true;
-                key[k] = __float_as_uint(ce[k]);
-                atomicAdd(&st.hist[0][key[k] >> 24], 1u);      // first radix pass rides along
+    for (int k = 0; k < KQ; ++k) {
+        const int p = k * LT + tid;
+        ce[k] = 0.0f; key[k] = 0u; tgt[k] = -1; mg[k] = -1;
+        if (p >= P) { tgt[k] = -2; continue; }            // -2: no prior in this slot
+        const long long row = (long long)b * P + p;
+        int cls = 0;
+        if (FROM_TARGETS) {
+            if (prm.in_pos[row] != 0) { tgt[k] = (int)prm.in_cls[row]; cls = tgt[k]; }
+        } else {
+            const int code = (int)prm.code[row];
+            if (code != 0) {
+                mg[k] = code - 1;
+                tgt[k] = (int)prm.gt_labels[g_begin + mg[k]] + 1;
+                cls = tgt[k];
             }
         }
+        float mx, lg;
+        row_lse<CT>(prm.conf_all + row * prm.C, prm.C, mx, lg);
+        const float xc = __ldg(prm.conf_all + row * prm.C + cls);
+        // -log_softmax[c] = -((x_c - max) - log(sum))  (ATen PersistentSoftmax.cuh, nll_loss)
+        ce[k] = -fsub(fsub(xc, mx), lg);
+        if (tgt[k] >= 0) {
+            my_pos += 1;
+            acc_ce += (double)ce[k];
+            if (!FROM_TARGETS && prm.loc_all) {
+                const float4 px = ldg4(prm.gt_boxes + 4ll * (g_begin + mg[k]));
+                const float x1 = fdiv(px.x, prm.norm_w), y1 = fdiv(px.y, prm.norm_h);
+                const float x2 = fdiv(px.z, prm.norm_w), y2 = fdiv(px.w, prm.norm_h);
+                const float4 gbox = make_float4(fmul(fadd(x1, x2), 0.5f), fmul(fadd(y1, y2), 0.5f), fsub(x2, x1), fsub(y2, y1));
+                const float4 t = encode_offsets(gbox, ldg4(prm.pri + 4ll * p), prm.inv_vc, prm.inv_vs);
+                const float4 l = ldg4(prm.loc_all + 4ll * row);
+                const float d[4] = {fsub(l.x, t.x), fsub(l.y, t.y), fsub(l.z, t.z), fsub(l.w, t.w)};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float z = fabsf(d[j]);
+                    acc_loc += (double)(z < 1.0f ? fmul(fmul(0.5f, z), z) : fsub(z, 0.5f));
+                }
+            }
+        } else {
+            key[k] = __float_as_uint(ce[k]);
+            atomicAdd(&ls.hist[key[k] >> 24], 1u);          // first radix pass rides along
+        }
     }
-
-    // ---- positives of the whole image (+ first histogram) -----------------------------------
-    cluster.sync();
-    int n_pos_img = 0;
-    for (int r = 0; r < cs; ++r) n_pos_img += cluster.map_shared_rank(&st, r)->npos_cta;
-    if (rank == 0 && tid == 0 && prm.n_pos) prm.n_pos[b] = n_pos_img;
-    if (MODE == MODE_MATCH) {
-        cluster.sync();      // keep this CTA's shared memory alive until every peer has read it
-        return;
-    }
+    const int n_pos_img = block_sum<int>(my_pos, ls.iscratch);      // (two barriers: hist is complete)
+    if (tid == 0 && prm.n_pos) prm.n_pos[b] = n_pos_img;
 
     // ---- hard-negative budget (SSD_trainer.py:585-596) --------------------------------------
     const long long n_neg = (long long)P - n_pos_img;
@@ -431,34 +452,27 @@ __global__ void __launch_bounds__(TT) train_kernel(const TrainParams prm) {
     if (want < 0) want = 0;
     const long long kk = want < n_neg ? want : n_neg;
     unsigned thr_key = 0u;        // selected negatives: key > thr_key, plus `need` of those == thr_key
-    unsigned need = 0u;
+    unsigned need = 0u, n_eq = 0u;
     const bool take_all = (kk >= n_neg);
     if (kk > 0 && !take_all) {
-        // 4-pass MSD radix select of the kk-th largest key over the cluster
+        // 4-pass MSD radix select of the kk-th largest key
         unsigned prefix = 0u, remaining = (unsigned)kk;
         for (int pass = 0; pass < 4; ++pass) {
             const int shift = 24 - 8 * pass;
             if (pass > 0) {
-                unsigned* h = st.hist[pass & 1];
-                for (int i = tid; i < 256; i += TT) h[i] = 0u;
+                for (int i = tid; i < 256; i += LT) ls.hist[i] = 0u;
                 __syncthreads();
                 const unsigned himask = 0xffffffffu << (shift + 8);
 #pragma unroll
-                for (int k = 0; k < KP; ++k)
-                    if (neg[k] && ((key[k] & himask) == prefix)) atomicAdd(&h[(key[k] >> shift) & 255u], 1u);
-                cluster.sync();
+                for (int k = 0; k < KQ; ++k)
+                    if (tgt[k] == -1 && ((key[k] & himask) == prefix)) atomicAdd(&ls.hist[(key[k] >> shift) & 255u], 1u);
+                __syncthreads();
             }
-            for (int i = tid; i < 256; i += TT) {
-                unsigned t = 0u;
-                for (int r = 0; r < cs; ++r) t += cluster.map_shared_rank(&st, r)->hist[pass & 1][i];
-                st.total[i] = t;
-            }
-            __syncthreads();
             if (tid < 32) {
                 // bins 255..0: lane l owns bins [255-8l-7 .. 255-8l]; find where the suffix count reaches `remaining`
                 unsigned mine = 0u;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) mine += st.total[255 - (tid * 8 + j)];
+                for (int j = 0; j < 8; ++j) mine += ls.hist[255 - (tid * 8 + j)];
                 unsigned incl = mine;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -470,83 +484,65 @@ __global__ void __launch_bounds__(TT) train_kernel(const TrainParams prm) {
                     unsigned run = excl;
                     for (int j = 0; j < 8; ++j) {
                         const int bin = 255 - (tid * 8 + j);
-                        const unsigned c = st.total[bin];
-                        if (run + c >= remaining) { st.sel_digit = (unsigned)bin; st.sel_need = remaining - run; break; }
+                        const unsigned c = ls.hist[bin];
+                        if (run + c >= remaining) { ls.sel_digit = (unsigned)bin; ls.sel_need = remaining - run; ls.iscratch[0] = (int)c; break; }
                         run += c;
                     }
                 }
             }
             __syncthreads();
-            prefix |= st.sel_digit << shift;
-            remaining = st.sel_need;
+            prefix |= ls.sel_digit << shift;
+            remaining = ls.sel_need;
+            n_eq = (unsigned)ls.iscratch[0];
+            __syncthreads();
         }
         thr_key = prefix;
         need = remaining;
     }
 
     // ---- sums (and the backward selection) --------------------------------------------------
-    int my_ties = 0;
     if (kk > 0) {
 #pragma unroll
-        for (int k = 0; k < KP; ++k) {
-            if (!neg[k]) continue;
-            if (take_all || key[k] > thr_key) acc_ce += (double)ce[k];
-            else if (key[k] == thr_key) my_ties += 1;
-        }
+        for (int k = 0; k < KQ; ++k)
+            if (tgt[k] == -1 && (take_all || key[k] > thr_key)) acc_ce += (double)ce[k];
     }
     if (prm.sel_cls) {
-        // which of the elements equal to the threshold are taken: the first `need` in prior order
-        int before = 0;          // ties owned by lower-ranked CTAs
-        bool all_ties = true;
-        if (kk > 0 && !take_all) {
-            const int cta_ties = block_sum<int>(my_ties, st.iscratch);
-            if (tid == 0) st.ties_cta = cta_ties;
-            cluster.sync();
-            int tot = 0;
-            for (int r = 0; r < cs; ++r) {
-                const int t = cluster.map_shared_rank(&st, r)->ties_cta;
-                if (r < rank) before += t;
-                tot += t;
-            }
-            all_ties = (unsigned)tot == need;
-        }
+        // of the negatives equal to the threshold value the first `need` in prior order are taken
+        const bool all_ties = take_all || kk == 0 || need == n_eq;
+        int before = 0;
 #pragma unroll
-        for (int k = 0; k < KP; ++k) {
-            const int p = p0 + k * TT + tid;
-            // ordered rank of this tie inside the CTA: slots are visited k-major, then by thread
-            int rank_in_cta = 0;
-            const bool tie = kk > 0 && !take_all && neg[k] && key[k] == thr_key;
+        for (int k = 0; k < KQ; ++k) {
+            const int p = k * LT + tid;
+            const bool tie = kk > 0 && !take_all && tgt[k] == -1 && key[k] == thr_key;
+            int rank_tie = 0;
             if (!all_ties) {
                 const unsigned bal = __ballot_sync(FULL, tie);
                 __syncthreads();
-                if (lane == 0) st.iscratch[warp] = __popc(bal);
+                if (lane == 0) ls.iscratch[warp] = __popc(bal);
                 __syncthreads();
-                for (int w = 0; w < warp; ++w) rank_in_cta += st.iscratch[w];
-                rank_in_cta += __popc(bal & ((1u << lane) - 1u));
                 int slot_total = 0;
-                for (int w = 0; w < (TT >> 5); ++w) slot_total += st.iscratch[w];
-                rank_in_cta += before;
+                for (int w = 0; w < LT / 32; ++w) { if (w < warp) rank_tie += ls.iscratch[w]; slot_total += ls.iscratch[w]; }
+                rank_tie += before + __popc(bal & ((1u << lane) - 1u));
                 before += slot_total;
             }
-            if (p >= p1) continue;
+            if (p >= P) continue;
             const long long row = (long long)b * P + p;
-            int8_t s = -1;
-            if (pos[k]) s = (int8_t)cls[k];
-            else if (kk > 0 && (take_all || key[k] > thr_key || (tie && (all_ties || (unsigned)rank_in_cta < need)))) s = 0;
-            prm.sel_cls[row] = s;
-            if (prm.matched16) prm.matched16[row] = pos[k] ? (int16_t)best_g[k] : (int16_t)-1;
+            int8_t sel = -1;
+            if (tgt[k] >= 0) sel = (int8_t)tgt[k];
+            else if (kk > 0 && (take_all || key[k] > thr_key || (tie && (all_ties || (unsigned)rank_tie < need)))) sel = 0;
+            prm.sel_cls[row] = sel;
+            if (prm.matched16) prm.matched16[row] = (int16_t)mg[k];
         }
     }
-    // the `need` threshold-valued elements are counted once, by rank 0
-    if (rank == 0 && tid == 0 && kk > 0 && !take_all) acc_ce += (double)need * (double)__uint_as_float(thr_key);
+    // the `need` threshold-valued negatives are counted once
+    if (tid == 0 && kk > 0 && !take_all) acc_ce += (double)need * (double)__uint_as_float(thr_key);
 
-    const double s_loc = block_sum<double>(acc_loc, st.dscratch);
-    const double s_ce = block_sum<double>(acc_ce, st.dscratch);
+    const double s_loc = block_sum<double>(acc_loc, ls.dscratch);
+    const double s_ce = block_sum<double>(acc_ce, ls.dscratch);
     if (tid == 0) {
-        prm.cta_part[2ll * blockIdx.x + 0] = s_loc;
-        prm.cta_part[2ll * blockIdx.x + 1] = s_ce;
+        prm.img_part[2ll * b + 0] = s_loc;
+        prm.img_part[2ll * b + 1] = s_ce;
     }
-    cluster.sync();          // peers may still be reading this CTA's histograms / counters
 }
 
 // Fixed-order final reduction: sums[0..1] = sum of the per-CTA partials, sums[2] = sum n_pos.
@@ -669,14 +665,19 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
 // host side
 // ---------------------------------------------------------------------------------------------
 
-template <int MODE, int CT, bool PRUNE>
-static int launch_train(const TrainParams& prm, cudaStream_t stream) {
-    // a fixed cluster of 8 balances best at SSD300 sizes (1092 priors per CTA); smaller P shrink it
+static int train_cluster_size(int P) {
     int cs = MAX_CS;
-    while (cs > 1 && (cs / 2) * SLOTS >= prm.P && prm.P <= 2048) cs >>= 1;
+    while (cs > 1 && (cs / 2) * SLOTS >= P && P <= 2048) cs >>= 1;
+    return cs;
+}
+
+template <bool PRUNE>
+static int launch_match(const TrainParams& prm, cudaStream_t stream) {
+    // a fixed cluster of 8 balances best at SSD300 sizes (1092 priors per CTA); small P shrink it
+    const int cs = train_cluster_size(prm.P);
     if (cs * SLOTS < prm.P) return SSDHOT_ERR_SHAPE;
     const size_t dyn = smem_bytes(prm.max_gt > 0 ? prm.max_gt : 1);
-    auto kern = train_kernel<MODE, CT, PRUNE>;
+    auto kern = match_kernel<PRUNE>;
     static size_t configured = 0;      // per instantiation; sticky opt-in, raised outside graph capture
     if (dyn > 48 * 1024 && dyn > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -701,11 +702,14 @@ static int launch_train(const TrainParams& prm, cudaStream_t stream) {
     return SSDHOT_OK;
 }
 
-int train_cluster_size(int P) {
-    int cs = MAX_CS;
-    while (cs > 1 && (cs / 2) * SLOTS >= P && P <= 2048) cs >>= 1;
-    return cs;
+template <bool FROM_TARGETS>
+static int launch_loss(const TrainParams& prm, cudaStream_t stream) {
+    if (prm.C == 6) loss_image_kernel<6, FROM_TARGETS><<<prm.B, LT, 0, stream>>>(prm);
+    else loss_image_kernel<0, FROM_TARGETS><<<prm.B, LT, 0, stream>>>(prm);
+    SSDHOT_CHECK_LAUNCH();
+    return SSDHOT_OK;
 }
+
 
 }  // namespace ssdhot
 
@@ -763,8 +767,7 @@ extern "C" int ssdhot_match_encode(const float* priors_cxcywh, const float* prio
     prm.matched32 = matched_gt; prm.matched_box = matched_cxcywh; prm.n_pos = n_pos; prm.flags = dev_flags;
     // the pruned sweep is exact for positives; negatives' matches need the exact-everywhere sweep
     const bool prune = (!loc_t || loc_positives_only) && !matched_gt && !matched_cxcywh;
-    return prune ? launch_train<MODE_MATCH, 0, true>(prm, (cudaStream_t)stream)
-                 : launch_train<MODE_MATCH, 0, false>(prm, (cudaStream_t)stream);
+    return prune ? launch_match<true>(prm, (cudaStream_t)stream) : launch_match<false>(prm, (cudaStream_t)stream);
 }
 
 extern "C" int ssdhot_compact_rows(const float* loc_t, const uint8_t* pos_mask, const int32_t* n_pos, int B, int P,
@@ -777,14 +780,17 @@ extern "C" int ssdhot_compact_rows(const float* loc_t, const uint8_t* pos_mask, 
     return SSDHOT_OK;
 }
 
-extern "C" unsigned long long ssdhot_loss_workspace_bytes(int B) {
-    if (B <= 0) return 0;
-    // per-CTA partial sums [B*8][2] doubles + n_pos [B] int32 (used when the caller passes none)
-    return (unsigned long long)B * MAX_CS * 2 * sizeof(double) + (unsigned long long)B * sizeof(int32_t) + 64;
+// workspace layout: img_part [B][2] double | n_pos [B] int32 (padded to 8) | code [B,P] uint16
+static size_t ws_npos_off(int B) { return (size_t)B * 2 * sizeof(double); }
+static size_t ws_code_off(int B) { return ws_npos_off(B) + (((size_t)B * sizeof(int32_t) + 15) & ~(size_t)15); }
+
+extern "C" unsigned long long ssdhot_loss_workspace_bytes(int B, int P) {
+    if (B <= 0 || P <= 0) return 0;
+    return (unsigned long long)(ws_code_off(B) + (size_t)B * P * sizeof(uint16_t) + 64);
 }
 
-static int finalize(const TrainParams& prm, int n_part, const int32_t* n_pos, double* sums, cudaStream_t stream) {
-    finalize_sums_kernel<<<1, 256, 0, stream>>>(prm.cta_part, n_part, n_pos, prm.B, sums);
+static int finalize(const TrainParams& prm, const int32_t* n_pos, double* sums, cudaStream_t stream) {
+    finalize_sums_kernel<<<1, 256, 0, stream>>>(prm.img_part, prm.B, n_pos, prm.B, sums);
     SSDHOT_CHECK_LAUNCH();
     return SSDHOT_OK;
 }
@@ -802,21 +808,26 @@ extern "C" int ssdhot_multibox_loss_fwd(const float* priors_cxcywh, const float*
     if (!loc_all || !conf_all || !sums || !work) return SSDHOT_ERR_NULL;
     if (C < 2 || C > SSDHOT_MAX_CLASSES) return SSDHOT_ERR_SHAPE;
     if (!(neg_pos_ratio >= 0.0)) return SSDHOT_ERR_VALUE;
-    if (!aligned16(loc_all) || (reinterpret_cast<uintptr_t>(conf_all) & 7u) || (reinterpret_cast<uintptr_t>(work) & 7u))
-        return SSDHOT_ERR_ALIGN;
+    if (!aligned16(loc_all) || (reinterpret_cast<uintptr_t>(conf_all) & 7u) || !aligned16(work)) return SSDHOT_ERR_ALIGN;
+    unsigned char* w = reinterpret_cast<unsigned char*>(work);
     TrainParams prm = {};
     prm.pri = priors_cxcywh; prm.pri_xyxy = priors_xyxy; prm.pri_aux = prior_aux; prm.P = P;
     prm.gt_boxes = gt_boxes; prm.gt_labels = gt_labels; prm.gt_offsets = gt_offsets;
     prm.B = B; prm.max_gt = max_gt; prm.norm_w = norm_w; prm.norm_h = norm_h;
     prm.thresh = iou_thresh; prm.inv_vc = 1.0f / var_center; prm.inv_vs = 1.0f / var_size;
     prm.loc_all = loc_all; prm.conf_all = conf_all; prm.C = C; prm.ratio = neg_pos_ratio;
-    prm.cta_part = reinterpret_cast<double*>(work);
-    int32_t* np = n_pos ? n_pos : reinterpret_cast<int32_t*>(prm.cta_part + (size_t)B * MAX_CS * 2);
-    prm.n_pos = np; prm.sel_cls = sel_cls; prm.matched16 = matched_gt; prm.flags = dev_flags;
-    rc = (C == 6) ? launch_train<MODE_FUSED, 6, true>(prm, (cudaStream_t)stream)
-                  : launch_train<MODE_FUSED, 0, true>(prm, (cudaStream_t)stream);
+    prm.img_part = reinterpret_cast<double*>(w);
+    prm.code = reinterpret_cast<uint16_t*>(w + ws_code_off(B));
+    prm.flags = dev_flags;
+    // 1) match: cluster per image, pruned sweep, 2-byte code per prior
+    rc = launch_match<true>(prm, (cudaStream_t)stream);
     if (rc) return rc;
-    return finalize(prm, B * train_cluster_size(P), np, sums, (cudaStream_t)stream);
+    // 2) loss: one CTA per image
+    int32_t* np = n_pos ? n_pos : reinterpret_cast<int32_t*>(w + ws_npos_off(B));
+    prm.n_pos = np; prm.sel_cls = sel_cls; prm.matched16 = matched_gt;
+    rc = launch_loss<false>(prm, (cudaStream_t)stream);
+    if (rc) return rc;
+    return finalize(prm, np, sums, (cudaStream_t)stream);
 }
 
 extern "C" int ssdhot_mined_ce_fwd(const float* conf_all, const int64_t* cls_t, const uint8_t* pos_mask,
@@ -825,17 +836,17 @@ extern "C" int ssdhot_mined_ce_fwd(const float* conf_all, const int64_t* cls_t, 
     if (!conf_all || !cls_t || !pos_mask || !sums || !work) return SSDHOT_ERR_NULL;
     if (P <= 0 || P > SSDHOT_MAX_PRIORS || B <= 0 || C < 2 || C > SSDHOT_MAX_CLASSES) return SSDHOT_ERR_SHAPE;
     if (!(neg_pos_ratio >= 0.0)) return SSDHOT_ERR_VALUE;
-    if ((reinterpret_cast<uintptr_t>(conf_all) & 7u) || (reinterpret_cast<uintptr_t>(work) & 7u)) return SSDHOT_ERR_ALIGN;
+    if ((reinterpret_cast<uintptr_t>(conf_all) & 7u) || !aligned16(work)) return SSDHOT_ERR_ALIGN;
+    unsigned char* w = reinterpret_cast<unsigned char*>(work);
     TrainParams prm = {};
     prm.P = P; prm.B = B; prm.max_gt = 0; prm.conf_all = conf_all; prm.C = C; prm.ratio = neg_pos_ratio;
     prm.in_cls = cls_t; prm.in_pos = pos_mask;
-    prm.cta_part = reinterpret_cast<double*>(work);
-    prm.n_pos = reinterpret_cast<int32_t*>(prm.cta_part + (size_t)B * MAX_CS * 2);
+    prm.img_part = reinterpret_cast<double*>(w);
+    prm.n_pos = reinterpret_cast<int32_t*>(w + ws_npos_off(B));
     prm.sel_cls = sel_cls;
-    int rc = (C == 6) ? launch_train<MODE_LOSS, 6, false>(prm, (cudaStream_t)stream)
-                      : launch_train<MODE_LOSS, 0, false>(prm, (cudaStream_t)stream);
+    int rc = launch_loss<true>(prm, (cudaStream_t)stream);
     if (rc) return rc;
-    return finalize(prm, B * train_cluster_size(P), prm.n_pos, sums, (cudaStream_t)stream);
+    return finalize(prm, prm.n_pos, sums, (cudaStream_t)stream);
 }
 
 extern "C" int ssdhot_multibox_loss_bwd(const float* priors_cxcywh, int P,

@@ -161,7 +161,7 @@ class _MinedCE(torch.autograd.Function):
         pos = pos_mask.to(torch.bool).contiguous()
         sums = torch.empty((3,), dtype=torch.float64, device=dev)
         sel = torch.empty((B, P), dtype=torch.int8, device=dev) if conf_all.requires_grad else None
-        work = _workspace("loss", dev, _lib.lib().ssdhot_loss_workspace_bytes(B))
+        work = _workspace("loss", dev, _lib.lib().ssdhot_loss_workspace_bytes(B, P))
         with torch.cuda.device(dev):
             rc = _lib.lib().ssdhot_mined_ce_fwd(conf.data_ptr(), cls.data_ptr(), pos.data_ptr(), B, P, C, float(ratio),
                                                 sums.data_ptr(), work.data_ptr(), _ptr(sel), _stream(dev))
@@ -204,7 +204,7 @@ class _FusedLoss(torch.autograd.Function):
         sums = torch.empty((3,), dtype=torch.float64, device=dev)
         sel = torch.empty((B, P), dtype=torch.int8, device=dev) if need_grad else None
         matched = torch.empty((B, P), dtype=torch.int16, device=dev) if need_grad else None
-        work = _workspace("loss", dev, _lib.lib().ssdhot_loss_workspace_bytes(B))
+        work = _workspace("loss", dev, _lib.lib().ssdhot_loss_workspace_bytes(B, P))
         with torch.cuda.device(dev):
             rc = _lib.lib().ssdhot_multibox_loss_fwd(
                 priors.priors.data_ptr(), priors.priors_xyxy.data_ptr(), priors.aux.data_ptr(), P,

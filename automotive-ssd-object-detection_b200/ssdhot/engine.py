@@ -31,7 +31,7 @@ class HotPathStep:
         dev = priors.device
         L = _lib.lib()
         self.sums = torch.zeros((3,), dtype=torch.float64, device=dev)
-        self.loss_work = torch.empty((int(L.ssdhot_loss_workspace_bytes(self.B)),), dtype=torch.uint8, device=dev)
+        self.loss_work = torch.empty((int(L.ssdhot_loss_workspace_bytes(self.B, priors.P)),), dtype=torch.uint8, device=dev)
         self.pred_work = torch.empty((int(L.ssdhot_predict_workspace_bytes(self.B, self.C, self.max_per_img)),),
                                      dtype=torch.uint8, device=dev)
         m = self.max_per_img

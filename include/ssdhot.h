@@ -107,10 +107,10 @@ SSDHOT_API int ssdhot_compact_rows(const float* loc_t, const uint8_t* pos_mask, 
  * (TR:577-598).  Nothing of shape [B,P] is materialised unless asked for.
  *   sums [3] double, OVERWRITTEN: { sum smooth-L1, sum CE (positives + mined), sum n_pos } --
  *   un-normalised, ready for one all-reduce; loss = sums[0..1] / max(sums[2], 1) (TR:105,600).
- *   work: scratch of ssdhot_loss_workspace_bytes(B) bytes.
+ *   work: scratch of ssdhot_loss_workspace_bytes(B, P) bytes, 16-byte aligned.
  *   Optional, for the backward pass: sel_cls [B,P] int8 (-1 = prior not in the loss, else its
  *   target class), matched_gt [B,P] int16 (positives only, -1 elsewhere), n_pos [B]. */
-SSDHOT_API unsigned long long ssdhot_loss_workspace_bytes(int B);
+SSDHOT_API unsigned long long ssdhot_loss_workspace_bytes(int B, int P);
 SSDHOT_API int ssdhot_multibox_loss_fwd(const float* priors_cxcywh, const float* priors_xyxy, const float* prior_aux, int P,
                              const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
                              int B, int max_gt, float norm_w, float norm_h,
