@@ -25,17 +25,22 @@
 
 namespace ssdhot {
 
-constexpr int CHUNK = 512;     // candidates ranked per round
+constexpr int CHUNK = 256;     // candidates ranked per round
 constexpr int TILE = 64;
 constexpr float kFilterSlack = 0.999f;   // see suppresses()
+constexpr int HBINS = 4096;    // score histogram: 16 octaves below 1.0 x 256 mantissa steps
+constexpr int HBASE = (127 - 16) << 8;
 
 struct UnitShared {
     unsigned hist[256];
     unsigned long long rowmask[TILE];   // bit j of rowmask[i]: tile member i suppresses tile member j (j > i)
-    unsigned long long supp;            // tile members suppressed by an earlier kept box
+    unsigned long long cmask[32];       // tile members per suppression group
     unsigned long long keepbits;
+    int ngroup[32];                     // survivors per suppression group
+    unsigned char suppf[TILE];          // tile member suppressed by an earlier survivor
     unsigned sel_prefix, sel_need, sel_eq;
     int counter;                        // gather cursor
+    int cut_bin, cut_count;
     int iscratch[32];
 };
 
@@ -68,6 +73,81 @@ __device__ __forceinline__ bool suppresses(const BoxC& S, const BoxC& c, float t
 }
 
 // ---- ranking helpers ---------------------------------------------------------------------------
+
+// histogram bin of an ord_encode()d score in (0, 1]: exponent and the top 8 mantissa bits,
+// clamped to 16 octaves below 1.0 (everything smaller shares bin 0)
+__device__ __forceinline__ int score_bin(unsigned key) {
+    const int v = (int)((key & 0x7fffffffu) >> 15) - HBASE;
+    return v < 0 ? 0 : (v >= HBINS ? HBINS - 1 : v);
+}
+__device__ __forceinline__ unsigned bin_floor_key(int bin) {      // smallest key that falls in `bin`
+    return bin <= 0 ? 1u : ((unsigned)(bin + HBASE) << 15) | 0x80000000u;
+}
+__device__ __forceinline__ void hist_add(unsigned* hist16, unsigned key) {
+    const int bin = score_bin(key);
+    atomicAdd(&hist16[bin >> 1], 1u << ((bin & 1) * 16));         // two 16-bit counters per word
+}
+
+// Find the lowest bin whose suffix count (candidates in this bin and above) is still <= cap:
+// us.cut_bin / us.cut_count (cut_count == 0 if even the top non-empty bin exceeds cap).  The bins
+// from the cut upwards are zeroed: they are consumed by the gather that follows.  1024 threads,
+// four bins each, thread 0 owns the top four.
+__device__ __forceinline__ void hist_cut(unsigned* hist16, int cap, UnitShared& us) {
+    __shared__ unsigned long long best[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int w0 = (1023 - tid) * 2;
+    const unsigned lo = hist16[w0], hi = hist16[w0 + 1];
+    const int c[4] = {(int)(hi >> 16), (int)(hi & 0xffffu), (int)(lo >> 16), (int)(lo & 0xffffu)};   // top first
+    const int mine = c[0] + c[1] + c[2] + c[3];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (tid == 0) { us.cut_bin = -1; us.cut_count = 0; }
+    if (lane == 31) us.iscratch[warp] = incl;
+    __syncthreads();
+    int run = incl - mine;                                  // candidates in bins above mine
+    for (int w = 0; w < warp; ++w) run += us.iscratch[w];
+    // cumulative counts grow monotonically going down, so "my lowest bin that still fits" is a valid
+    // proposal and the cut is the minimum proposal over all threads
+    const int top_bin = (1023 - tid) * 4 + 3;
+    int proposal = -1, prop_count = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        run += c[j];
+        if (run <= cap) { proposal = top_bin - j; prop_count = run; }
+    }
+    unsigned long long packed = proposal >= 0 ? (((unsigned long long)(unsigned)proposal << 32) | (unsigned)prop_count) : ~0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(FULL, packed, o);
+        packed = y < packed ? y : packed;
+    }
+    if (lane == 0) best[warp] = packed;
+    __syncthreads();
+    if (tid < 32) {
+        unsigned long long v = best[tid];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long y = __shfl_xor_sync(FULL, v, o);
+            v = y < v ? y : v;
+        }
+        if (tid == 0 && v != ~0ull) { us.cut_bin = (int)(v >> 32); us.cut_count = (int)(v & 0xffffffffu); }
+    }
+    __syncthreads();
+    const int cut = us.cut_bin;
+    if (cut >= 0) {                                         // consume the bins from the cut upwards
+        unsigned nlo = lo, nhi = hi;
+        const int b0 = (1023 - tid) * 4;
+        if (b0 + 0 >= cut) nlo &= 0xffff0000u;
+        if (b0 + 1 >= cut) nlo &= 0x0000ffffu;
+        if (b0 + 2 >= cut) nhi &= 0xffff0000u;
+        if (b0 + 3 >= cut) nhi &= 0x0000ffffu;
+        hist16[w0] = nlo; hist16[w0 + 1] = nhi;
+    }
+}
 
 // Radix select over the non-zero entries of dense[0..n): the K-th largest key.  Returns the key,
 // how many entries equal to it are needed (`need`) and how many exist (`eq`).
@@ -137,21 +217,24 @@ __device__ __forceinline__ void bitonic_desc(unsigned long long* keys, int n_pad
 
 // ---- the unit ------------------------------------------------------------------------------------
 // dense:   [n] keys (0 = absent), consumed (zeroed) as candidates are ranked
+// hist16:  packed 16-bit score histogram of the candidates (HIST only)
 // Fetch:   BoxC operator()(unsigned idx)      -- pixel box + constants of candidate idx
 // Group:   int operator()(unsigned idx)       -- suppression group (class) of candidate idx; only
 //                                                members of the same group suppress each other
 // Emit:    void operator()(int pos, unsigned long long key, unsigned idx, const BoxC&)
-// kept / kgroup: storage for the surviving boxes and their groups, capacity max_keep
+// kept:    the surviving boxes in output order, capacity max_keep (shared or global memory)
+// kidx:    [n_groups][max_keep] per-group lists of positions in `kept` (GROUPS only)
 // returns the number of survivors (valid in every thread)
 struct UnitBuffers {
-    unsigned* dense; unsigned long long* ckey; BoxC* cbox; unsigned char* cgroup;
-    BoxC* kept; unsigned char* kgroup;
+    unsigned* dense; unsigned* hist16; unsigned long long* ckey; BoxC* cbox; unsigned char* cgroup;
+    BoxC* kept; unsigned short* kidx;
 };
 
-template <int METRIC, int NT, bool GROUPS, typename Fetch, typename Group, typename Emit>
-__device__ int nms_unit(const UnitBuffers buf, int n, int n_cand, int max_keep, float thr, UnitShared& us,
+template <int METRIC, int NT, bool GROUPS, bool HIST, typename Fetch, typename Group, typename Emit>
+__device__ int nms_unit(const UnitBuffers buf, int n, int n_cand, int n_groups, int max_keep, float thr, UnitShared& us,
                         Fetch fetch, Group group_of, Emit emit) {
     constexpr int NW = NT / 32;
+    constexpr int SUB = NT / TILE;                 // threads cooperating on one tile member (16 or 8)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned* dense = buf.dense;
     unsigned long long* ckey = buf.ckey;
@@ -160,11 +243,19 @@ __device__ int nms_unit(const UnitBuffers buf, int n, int n_cand, int max_keep, 
     const float thr_lo = fmul(thr, kFilterSlack);
     int kept_n = 0;
     int remaining = n_cand;
+    bool use_hist = HIST && NT == 1024 && n < 65536;       // 16-bit bin counters, one thread per four bins
+    if (tid < 32) us.ngroup[tid] = 0;
     while (remaining > 0 && kept_n < max_keep) {
-        const int K = remaining < CHUNK ? remaining : CHUNK;
-        // ---- pull the K best remaining candidates ------------------------------------------
+        // ---- pull the next best candidates ---------------------------------------------------
+        int K = remaining < CHUNK ? remaining : CHUNK;
         unsigned tkey = 1u, need = 0u, eq = 0u;
-        const bool all = remaining <= CHUNK;
+        bool all = remaining <= CHUNK;
+        if (!all && use_hist) {
+            hist_cut(buf.hist16, CHUNK, us);
+            if (us.cut_count > 0) { K = us.cut_count; tkey = bin_floor_key(us.cut_bin); need = eq = 0u; all = true; }
+            else use_hist = false;                 // a single bin holds more than a chunk: exact select from here on
+            __syncthreads();
+        }
         if (!all) select_kth<NT>(dense, n, (unsigned)K, us, tkey, need, eq);
         if (tid == 0) us.counter = 0;
         __syncthreads();
@@ -207,62 +298,88 @@ __device__ int nms_unit(const UnitBuffers buf, int n, int n_cand, int max_keep, 
         for (int i = tid; i < K; i += NT) {
             const unsigned idx = 0xffffffffu - (unsigned)(ckey[i] & 0xffffffffull);
             cbox[i] = fetch(idx);
-            if (GROUPS) buf.cgroup[i] = (unsigned char)group_of(idx);
+            buf.cgroup[i] = GROUPS ? (unsigned char)group_of(idx) : (unsigned char)0;
         }
+        if (tid < TILE) { us.rowmask[tid] = 0ull; us.suppf[tid] = 0; }
         __syncthreads();
 
         // ---- greedy NMS over the sorted chunk, tile by tile ----------------------------------
+        // SUB threads share one tile member j: they split (a) the survivors of j's group and (b) the
+        // earlier tile members; (a) sets suppf[j], (b) sets bit j of rowmask[i].
         for (int t0 = 0; t0 < K && kept_n < max_keep; t0 += TILE) {
             const int m = (K - t0) < TILE ? (K - t0) : TILE;
-            if (tid < TILE) us.rowmask[tid] = 0ull;
-            if (tid == 0) us.supp = 0ull;
-            __syncthreads();
-            const int i_lo = t0 + (lane < m ? lane : 0), i_hi = t0 + (lane + 32 < m ? lane + 32 : 0);
-            const BoxC c_lo = cbox[i_lo];
-            const BoxC c_hi = cbox[i_hi];
-            const int g_lo = GROUPS ? (int)buf.cgroup[i_lo] : 0, g_hi = GROUPS ? (int)buf.cgroup[i_hi] : 0;
-            const int n_sup = kept_n + m;
-            for (int s = warp; s < n_sup; s += NW) {
-                const bool from_kept = s < kept_n;
-                const int si = s - kept_n;                     // tile index of the suppressor (if not kept)
-                const BoxC S = from_kept ? kept[s] : cbox[t0 + si];
-                const int sg = GROUPS ? (int)(from_kept ? buf.kgroup[s] : buf.cgroup[t0 + si]) : 0;
-                const bool v_lo = lane < m && (from_kept || si < lane) && sg == g_lo;
-                const bool v_hi = lane + 32 < m && (from_kept || si < lane + 32) && sg == g_hi;
-                const bool s_lo = v_lo && suppresses<METRIC>(S, c_lo, thr, thr_lo);
-                const bool s_hi = v_hi && suppresses<METRIC>(S, c_hi, thr, thr_lo);
-                const unsigned b_lo = __ballot_sync(FULL, s_lo), b_hi = __ballot_sync(FULL, s_hi);
-                if (lane == 0) {
-                    const unsigned long long bits = ((unsigned long long)b_hi << 32) | b_lo;
-                    if (from_kept) { if (bits) atomicOr(&us.supp, bits); }
-                    else us.rowmask[si] = bits;
+            const int j = tid / SUB, sub = tid % SUB;
+            if (j < m) {
+                const BoxC c = cbox[t0 + j];
+                const int g = (int)buf.cgroup[t0 + j];
+                bool hit = false;
+                if (GROUPS) {
+                    const unsigned short* list = buf.kidx + (size_t)g * max_keep;
+                    const int ng = us.ngroup[g];
+                    for (int i = sub; i < ng; i += SUB) hit |= suppresses<METRIC>(kept[list[i]], c, thr, thr_lo);
+                } else {
+                    for (int i = sub; i < kept_n; i += SUB) hit |= suppresses<METRIC>(kept[i], c, thr, thr_lo);
                 }
+                for (int i = sub; i < j; i += SUB) {
+                    if ((!GROUPS || (int)buf.cgroup[t0 + i] == g) && suppresses<METRIC>(cbox[t0 + i], c, thr, thr_lo))
+                        atomicOr(&us.rowmask[i], 1ull << j);
+                }
+                if (hit) us.suppf[j] = 1;            // benign race: every writer stores 1
             }
             __syncthreads();
-            if (tid == 0) {
-                const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
-                unsigned long long alive = ~us.supp & valid, keepb = 0ull;
-                int cnt = kept_n;
-                while (alive) {
-                    const int i = __ffsll((long long)alive) - 1;
-                    keepb |= 1ull << i;
-                    alive &= ~us.rowmask[i];
-                    alive &= ~(1ull << i);
-                    if (++cnt >= max_keep) break;
+            if (warp == 0) {
+                const bool in_lo = lane < m, in_hi = lane + 32 < m;
+                const unsigned s_lo = __ballot_sync(FULL, in_lo && us.suppf[lane] != 0);
+                const unsigned s_hi = __ballot_sync(FULL, in_hi && us.suppf[lane + 32] != 0);
+                const unsigned z_lo = __ballot_sync(FULL, in_lo && us.rowmask[lane] != 0ull);
+                const unsigned z_hi = __ballot_sync(FULL, in_hi && us.rowmask[lane + 32] != 0ull);
+                if (GROUPS) {
+                    const int g_lo = in_lo ? (int)buf.cgroup[t0 + lane] : -1, g_hi = in_hi ? (int)buf.cgroup[t0 + lane + 32] : -1;
+                    for (int g = 0; g < n_groups; ++g) {
+                        const unsigned a = __ballot_sync(FULL, g_lo == g), b2 = __ballot_sync(FULL, g_hi == g);
+                        if (lane == 0) us.cmask[g] = ((unsigned long long)b2 << 32) | a;
+                    }
                 }
-                us.keepbits = keepb;
+                if (lane == 0) {
+                    const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
+                    const unsigned long long supp = ((unsigned long long)s_hi << 32) | s_lo;
+                    const unsigned long long nz = ((unsigned long long)z_hi << 32) | z_lo;
+                    unsigned long long alive = ~supp & valid;
+                    // only members that suppress somebody need the serial walk, in index order
+                    unsigned long long pending = alive & nz;
+                    while (pending) {
+                        const int i = __ffsll((long long)pending) - 1;
+                        alive &= ~us.rowmask[i];
+                        pending &= alive & ~((2ull << i) - 1ull);
+                    }
+                    // truncate to the room that is left (lowest indices = highest scores first)
+                    int room = max_keep - kept_n;
+                    if (__popcll(alive) > room) {
+                        unsigned long long t = alive, keepb = 0ull;
+                        while (room-- > 0) { const int i = __ffsll((long long)t) - 1; keepb |= 1ull << i; t &= t - 1ull; }
+                        alive = keepb;
+                    }
+                    us.keepbits = alive;
+                }
             }
             __syncthreads();
             const unsigned long long keepb = us.keepbits;
             if (tid < m && ((keepb >> tid) & 1ull)) {
-                const int pos = kept_n + __popcll(keepb & ((1ull << tid) - 1ull));
+                const unsigned long long lower = keepb & ((1ull << tid) - 1ull);
+                const int pos = kept_n + __popcll(lower);
                 const BoxC bx = cbox[t0 + tid];
                 kept[pos] = bx;
-                if (GROUPS) buf.kgroup[pos] = buf.cgroup[t0 + tid];
+                if (GROUPS) {
+                    const int g = (int)buf.cgroup[t0 + tid];
+                    buf.kidx[(size_t)g * max_keep + us.ngroup[g] + __popcll(lower & us.cmask[g])] = (unsigned short)pos;
+                }
                 const unsigned long long key = ckey[t0 + tid];
                 emit(pos, key, 0xffffffffu - (unsigned)(key & 0xffffffffull), bx);
             }
+            if (tid >= NT - TILE) { us.rowmask[tid - (NT - TILE)] = 0ull; us.suppf[tid - (NT - TILE)] = 0; }
             kept_n += __popcll(keepb);
+            __syncthreads();
+            if (GROUPS && tid < n_groups) us.ngroup[tid] += __popcll(keepb & us.cmask[tid]);
             __syncthreads();
         }
         remaining -= K;
@@ -270,19 +387,20 @@ __device__ int nms_unit(const UnitBuffers buf, int n, int n_cand, int max_keep, 
     return kept_n;
 }
 
-// shared-memory carve-up of one unit: kept | cbox | ckey | dense | cgroup | kgroup
-__host__ __device__ inline size_t unit_smem_bytes(long long n, int max_keep) {
-    return (size_t)max_keep * sizeof(BoxC) + (size_t)CHUNK * (sizeof(BoxC) + 8) + (size_t)n * 4 + (size_t)CHUNK +
-           (size_t)max_keep + 16;
+// shared-memory carve-up of one unit: kept | cbox | ckey | dense | hist16 | kidx | cgroup
+__host__ __device__ inline size_t unit_smem_bytes(long long n, int max_keep, int n_groups, bool hist) {
+    return (size_t)max_keep * sizeof(BoxC) + (size_t)CHUNK * (sizeof(BoxC) + 8) + (size_t)n * 4 +
+           (hist ? (size_t)HBINS * 2 : 0) + (size_t)n_groups * max_keep * 2 + (size_t)CHUNK + 32;
 }
-__device__ __forceinline__ UnitBuffers carve_unit(unsigned char* dyn, long long n, int max_keep) {
+__device__ __forceinline__ UnitBuffers carve_unit(unsigned char* dyn, long long n, int max_keep, int n_groups, bool hist) {
     UnitBuffers b;
     b.kept = reinterpret_cast<BoxC*>(dyn);
     b.cbox = b.kept + max_keep;
     b.ckey = reinterpret_cast<unsigned long long*>(b.cbox + CHUNK);
     b.dense = reinterpret_cast<unsigned*>(b.ckey + CHUNK);
-    b.cgroup = reinterpret_cast<unsigned char*>(b.dense + n);
-    b.kgroup = b.cgroup + CHUNK;
+    b.hist16 = b.dense + n;
+    b.kidx = reinterpret_cast<unsigned short*>(b.hist16 + (hist ? HBINS / 2 : 0));
+    b.cgroup = reinterpret_cast<unsigned char*>(b.kidx + (size_t)n_groups * max_keep);
     return b;
 }
 
@@ -335,20 +453,34 @@ __global__ void __launch_bounds__(PT) predict_image_kernel(const PredictParams p
     const int b = blockIdx.x;
     const int n_fg = prm.C - 1, P = prm.P;
     const int n = P * n_fg;
-    const UnitBuffers buf = carve_unit(dyn, n, prm.max_keep);
+    const int n_groups = AGN ? 1 : n_fg;
+    const UnitBuffers buf = carve_unit(dyn, n, prm.max_keep, AGN ? 0 : n_groups, true);
+    for (int i = tid; i < HBINS / 2; i += PT) buf.hist16[i] = 0u;
+    __syncthreads();
 
+    // A score can only pass `s > thresh` if e_k > thr_pre * sum, thr_pre = thresh * (1 - 1e-5): the
+    // margin is two orders of magnitude above the rounding of the product and of the division, so
+    // rows / classes below it skip the IEEE division without changing any decision.
+    const float thr_pre = fmul(prm.score_thresh, 0.99999f);
     int mine = 0;
     const float* conf_b = prm.conf_all + (long long)b * P * prm.C;
     for (int p = tid; p < P; p += PT) {
         float e[CT > 0 ? CT : 32];
         const float sum = row_exps<CT>(conf_b + (long long)p * prm.C, prm.C, e);
+        const float gate = fmul(thr_pre, sum);
         const int nf = CT > 0 ? CT - 1 : n_fg;
 #pragma unroll
         for (int k = 0; k < nf; ++k) {
-            const float s = fdiv(e[k + 1], sum);           // softmax(conf)[..., 1:]  (SFS:388)
-            const bool on = s > prm.score_thresh;          // strict (SFS:402)
-            buf.dense[p * n_fg + k] = on ? ord_encode(s) : 0u;
-            mine += on ? 1 : 0;
+            unsigned key = 0u;
+            if (e[k + 1] > gate) {
+                const float s = fdiv(e[k + 1], sum);       // softmax(conf)[..., 1:]  (SFS:388)
+                if (s > prm.score_thresh) {                // strict (SFS:402)
+                    key = ord_encode(s);
+                    hist_add(buf.hist16, key);
+                    mine += 1;
+                }
+            }
+            buf.dense[p * n_fg + k] = key;
         }
     }
     const int n_cand = block_sum<int>(mine, us.iscratch);
@@ -370,7 +502,7 @@ __global__ void __launch_bounds__(PT) predict_image_kernel(const PredictParams p
         reinterpret_cast<float4*>(prm.out_boxes)[o + pos] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
         if (prm.out_cand) prm.out_cand[o + pos] = (int32_t)idx;
     };
-    const int kept_n = nms_unit<METRIC, PT, !AGN>(buf, n, n_cand, prm.max_keep, prm.nms_thresh, us, fetch, group_of, emit);
+    const int kept_n = nms_unit<METRIC, PT, !AGN, true>(buf, n, n_cand, n_groups, prm.max_keep, prm.nms_thresh, us, fetch, group_of, emit);
     if (tid == 0) prm.out_count[b] = kept_n;
 }
 
@@ -384,7 +516,7 @@ __global__ void __launch_bounds__(UT) predict_class_kernel(const PredictParams p
     const int n_fg = prm.C - 1;
     const int b = blockIdx.x / n_fg, c = blockIdx.x % n_fg;
     const int P = prm.P;
-    const UnitBuffers buf = carve_unit(dyn, P, prm.max_keep);
+    const UnitBuffers buf = carve_unit(dyn, P, prm.max_keep, 0, false);
 
     int mine = 0;
     const float* conf_b = prm.conf_all + (long long)b * P * prm.C;
@@ -432,7 +564,7 @@ __global__ void __launch_bounds__(UT) predict_class_kernel(const PredictParams p
         out_key[pos] = (key & 0xffffffff00000000ull) | (unsigned long long)(0xffffffffu - flat);
         out_box[pos] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
     };
-    const int kept_n = nms_unit<METRIC, UT, false>(buf, P, n_cand, prm.max_keep, prm.nms_thresh, us, fetch, group_of, emit);
+    const int kept_n = nms_unit<METRIC, UT, false, false>(buf, P, n_cand, 1, prm.max_keep, prm.nms_thresh, us, fetch, group_of, emit);
     if (tid == 0) prm.list_count[blockIdx.x] = kept_n;
 }
 
@@ -481,7 +613,7 @@ __global__ void __launch_bounds__(256) merge_lists_kernel(const unsigned long lo
 // ---- stand-alone NMS -------------------------------------------------------------------------------
 template <int METRIC>
 __global__ void __launch_bounds__(UT) nms_sets_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
-                                                      const int32_t* __restrict__ set_offsets, float thr, int max_keep,
+                                                      const int32_t* __restrict__ set_offsets, int n_max, float thr, int max_keep,
                                                       int64_t* __restrict__ keep, int32_t* __restrict__ keep_count,
                                                       BoxC* __restrict__ kept_all) {
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -493,8 +625,9 @@ __global__ void __launch_bounds__(UT) nms_sets_kernel(const float* __restrict__ 
     buf.cbox = reinterpret_cast<BoxC*>(dyn);
     buf.ckey = reinterpret_cast<unsigned long long*>(buf.cbox + CHUNK);
     buf.dense = reinterpret_cast<unsigned*>(buf.ckey + CHUNK);
+    buf.cgroup = reinterpret_cast<unsigned char*>(buf.dense + n_max);
     buf.kept = kept_all + begin;            // survivors of a stand-alone call are unbounded: global memory
-    buf.cgroup = nullptr; buf.kgroup = nullptr;
+    buf.kidx = nullptr; buf.hist16 = nullptr;
     for (int i = tid; i < n; i += UT) {
         const unsigned k = ord_encode(__ldg(scores + begin + i));
         buf.dense[i] = k == 0u ? 1u : k;
@@ -509,7 +642,7 @@ __global__ void __launch_bounds__(UT) nms_sets_kernel(const float* __restrict__ 
     int64_t* out = keep + begin;
     auto emit = [&](int pos, unsigned long long, unsigned idx, const BoxC&) { out[pos] = (int64_t)idx; };
     const int cap = (max_keep > 0 && max_keep < n) ? max_keep : n;
-    const int kept_n = nms_unit<METRIC, UT, false>(buf, n, n, cap, thr, us, fetch, group_of, emit);
+    const int kept_n = nms_unit<METRIC, UT, false, false>(buf, n, n, 1, cap, thr, us, fetch, group_of, emit);
     if (tid == 0) keep_count[blockIdx.x] = kept_n;
 }
 
@@ -528,7 +661,7 @@ static int set_smem(K kern, size_t bytes) {
     if (bytes > kMaxDynSmem) return SSDHOT_ERR_SHAPE;
     static std::mutex mu;
     static std::map<const void*, size_t> configured;
-    if (bytes > 48 * 1024) {
+    if (bytes > 40 * 1024) {      // static + dynamic shared memory share the 48 KB default limit
         std::lock_guard<std::mutex> lock(mu);
         size_t& have = configured[reinterpret_cast<const void*>(kern)];
         if (bytes > have) {
@@ -591,22 +724,23 @@ extern "C" int ssdhot_nms(const float* boxes, const float* scores, const int32_t
     if (n_sets <= 0 || total_boxes < 0 || max_set_size < 0) return SSDHOT_ERR_SHAPE;
     if (total_boxes > 0 && (!boxes || !scores || !keep || !work)) return SSDHOT_ERR_NULL;
     if (!al16(boxes) || !al16(work)) return SSDHOT_ERR_ALIGN;
-    const size_t dyn = (size_t)CHUNK * (sizeof(BoxC) + 8) + (size_t)(max_set_size > 0 ? max_set_size : 1) * 4;
+    const int n_max = max_set_size > 0 ? max_set_size : 1;
+    const size_t dyn = (size_t)CHUNK * (sizeof(BoxC) + 8) + (size_t)n_max * 4 + (size_t)CHUNK + 16;
     BoxC* kept_all = reinterpret_cast<BoxC*>(work);
     int rc;
     cudaStream_t s = (cudaStream_t)stream;
     switch (metric) {
         case SSDHOT_METRIC_DIOU:
             if ((rc = set_smem(nms_sets_kernel<SSDHOT_METRIC_DIOU>, dyn))) return rc;
-            nms_sets_kernel<SSDHOT_METRIC_DIOU><<<n_sets, UT, dyn, s>>>(boxes, scores, set_offsets, thresh, max_keep, keep, keep_count, kept_all);
+            nms_sets_kernel<SSDHOT_METRIC_DIOU><<<n_sets, UT, dyn, s>>>(boxes, scores, set_offsets, n_max, thresh, max_keep, keep, keep_count, kept_all);
             break;
         case SSDHOT_METRIC_CIOU:
             if ((rc = set_smem(nms_sets_kernel<SSDHOT_METRIC_CIOU>, dyn))) return rc;
-            nms_sets_kernel<SSDHOT_METRIC_CIOU><<<n_sets, UT, dyn, s>>>(boxes, scores, set_offsets, thresh, max_keep, keep, keep_count, kept_all);
+            nms_sets_kernel<SSDHOT_METRIC_CIOU><<<n_sets, UT, dyn, s>>>(boxes, scores, set_offsets, n_max, thresh, max_keep, keep, keep_count, kept_all);
             break;
         case SSDHOT_METRIC_IOU:
             if ((rc = set_smem(nms_sets_kernel<SSDHOT_METRIC_IOU>, dyn))) return rc;
-            nms_sets_kernel<SSDHOT_METRIC_IOU><<<n_sets, UT, dyn, s>>>(boxes, scores, set_offsets, thresh, max_keep, keep, keep_count, kept_all);
+            nms_sets_kernel<SSDHOT_METRIC_IOU><<<n_sets, UT, dyn, s>>>(boxes, scores, set_offsets, n_max, thresh, max_keep, keep, keep_count, kept_all);
             break;
         default: return SSDHOT_ERR_VALUE;
     }
@@ -643,8 +777,8 @@ extern "C" int ssdhot_predict(const float* priors_cxcywh, int P, const float* lo
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     // preferred: one CTA per image, all classes in one score-ordered stream
-    const size_t dyn_image = unit_smem_bytes((long long)P * (C - 1), max_per_img);
-    if (dyn_image <= kMaxDynSmem && C <= 32) {
+    const size_t dyn_image = unit_smem_bytes((long long)P * (C - 1), max_per_img, class_agnostic ? 0 : C - 1, true);
+    if (dyn_image <= kMaxDynSmem && C <= 32 && max_per_img < 65536) {
 #define SSDHOT_DISPATCH(M) rc = class_agnostic ? launch_predict_image<M, true>(prm, dyn_image, s) : launch_predict_image<M, false>(prm, dyn_image, s)
         if (metric == SSDHOT_METRIC_DIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_DIOU); }
         else if (metric == SSDHOT_METRIC_CIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_CIOU); }
@@ -661,7 +795,7 @@ extern "C" int ssdhot_predict(const float* priors_cxcywh, int P, const float* lo
     prm.list_box = reinterpret_cast<float4*>(w); w += (size_t)lists * max_per_img * 16;
     prm.list_key = reinterpret_cast<unsigned long long*>(w); w += (size_t)lists * max_per_img * 8;
     prm.list_count = reinterpret_cast<int*>(w);
-    const size_t dyn = unit_smem_bytes(P, max_per_img);
+    const size_t dyn = unit_smem_bytes(P, max_per_img, 0, false);
     if (metric == SSDHOT_METRIC_DIOU) rc = launch_predict_class<SSDHOT_METRIC_DIOU>(prm, dyn, s);
     else if (metric == SSDHOT_METRIC_CIOU) rc = launch_predict_class<SSDHOT_METRIC_CIOU>(prm, dyn, s);
     else rc = launch_predict_class<SSDHOT_METRIC_IOU>(prm, dyn, s);

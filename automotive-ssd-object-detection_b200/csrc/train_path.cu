@@ -48,6 +48,7 @@ struct TrainParams {
     float* matched_box; int32_t* n_pos;
     // loss outputs
     int8_t* sel_cls; int16_t* matched16;
+    float4* gt_rec;        // [B*max_gt][3]: (x1 y1 x2 y2), (area xc yc atan), (lim, label bits, -, -)
     uint16_t* code;        // [B,P] 0 = negative, 1 + matched box (fused path: match -> loss hand-off)
     double* img_part;      // [B][2] per-image (smooth-L1, CE) sums
     int32_t* flags;
@@ -161,7 +162,7 @@ __device__ __forceinline__ void publish_column(const ColBest cb, unsigned long l
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <bool PRUNE>
-__global__ void __launch_bounds__(TT) match_kernel(const TrainParams prm) {
+__global__ void __launch_bounds__(TT, PRUNE ? 4 : 2) match_kernel(const TrainParams prm) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ Static st;
 
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(TT) match_kernel(const TrainParams prm) {
     const int cs = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     const int b = blockIdx.x / cs;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int P = prm.P;
     const int chunk = (P + cs - 1) / cs;
     const int p0 = rank * chunk;
@@ -197,33 +198,16 @@ __global__ void __launch_bounds__(TT) match_kernel(const TrainParams prm) {
         for (int i = tid; i < SLOTS; i += TT) sm.forced[i] = INT_MAX;
         __syncthreads();
         for (int g = tid; g < G; g += TT) {
-            const float4 px = ldg4(prm.gt_boxes + 4ll * (g_begin + g));
-            const BoxC c = box_consts(fdiv(px.x, prm.norm_w), fdiv(px.y, prm.norm_h),
-                                      fdiv(px.z, prm.norm_w), fdiv(px.w, prm.norm_h), true);
-            sm.gt_a[g] = make_float4(c.x1, c.y1, c.x2, c.y2);
-            sm.gt_b[g] = make_float4(c.area, c.xc, c.yc, c.at);
-            sm.gt_label[g] = (int)prm.gt_labels[g_begin + g];
+            const float4* rec = prm.gt_rec + 3ll * ((long long)b * prm.max_gt + g);     // gt_prepare_kernel
+            const float4 ra = __ldg(rec), rb = __ldg(rec + 1), rc = __ldg(rec + 2);
+            sm.gt_a[g] = ra;
+            sm.gt_b[g] = rb;
+            sm.lim[g] = rc.x;
+            sm.gt_label[g] = __float_as_int(rc.y);
             sm.col[g] = 0ull;
-            sm.lim[g] = 1e-30f;      // overlap-only pruning until a seed raises it
-            if (c.at != c.at) atomicMin(&st.first_nan, g);
+            if (rb.w != rb.w) atomicMin(&st.first_nan, g);
         }
         __syncthreads();
-
-        if (PRUNE && P == 8732) {
-            // ---- seeds: a lower bound of every column maximum from ~30 well-placed priors ----
-            for (int g = warp; g < G; g += TT / 32) {
-                const float4 ga = sm.gt_a[g], gb = sm.gt_b[g];
-                const int lv = kSeedLevel[lane], side = kLevelSide[lv];
-                int ix = (int)floorf(gb.y * (float)side), iy = (int)floorf(gb.z * (float)side);
-                ix = min(max(ix, 0), side - 1);
-                iy = min(max(iy, 0), side - 1);
-                const int ps = kLevelOffset[lv] + (iy * side + ix) * kLevelShapes[lv] + kSeedShape[lane];
-                const float v = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, ps), gt_box(ga, gb));
-                const float cb0 = ord_decode(__reduce_max_sync(FULL, ord_encode(v)));   // NaN sorts to the top
-                if (lane == 0 && cb0 > 0.0f) sm.lim[g] = fmaxf(fmul(kPruneSlack, fminf(cb0, prm.thresh)), 1e-30f);
-            }
-            __syncthreads();
-        }
 
         // ---- CIoU sweep: row arg-max in registers, column arg-max per warp -> shared ---------
         float4 pb[KP];      // x1 y1 x2 y2 of this thread's priors
@@ -247,8 +231,11 @@ __global__ void __launch_bounds__(TT) match_kernel(const TrainParams prm) {
             for (int k = 0; k < KP; ++k) {
                 bool go = true;
                 if (PRUNE) {
+                    // no vertical overlap anywhere in the warp: intersection 0 < lim * union for all lanes
+                    const float hraw = fsub(fminf(pb[k].w, gc.y2), fmaxf(pb[k].y, gc.y1));
+                    if (!__any_sync(FULL, hraw > 0.0f)) continue;
                     const float w = fmaxf(fsub(fminf(pb[k].z, gc.x2), fmaxf(pb[k].x, gc.x1)), 0.0f);
-                    const float h = fmaxf(fsub(fminf(pb[k].w, gc.y2), fmaxf(pb[k].y, gc.y1)), 0.0f);
+                    const float h = fmaxf(hraw, 0.0f);
                     const float inter = fmul(w, h);
                     const float uni = fsub(fadd(pa[k], gc.area), inter);
                     go = !(inter < fmul(lim, uni));          // NaN-safe: anything odd takes the exact path
@@ -371,21 +358,67 @@ __global__ void __launch_bounds__(TT) match_kernel(const TrainParams prm) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// gt_prepare_kernel: one warp per ground-truth box -- normalised box, its CIoU constants, label and
+// the prune bound lim (header comment) from the ~30 seed priors.  Done once per box instead of
+// once per CTA of the image's cluster.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gt_prepare_kernel(const TrainParams prm, int want_seeds) {
+    const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= prm.B * prm.max_gt) return;
+    const int b = w / prm.max_gt, g = w % prm.max_gt;
+    const int g_begin = prm.gt_offsets[b];
+    if (g >= prm.gt_offsets[b + 1] - g_begin) return;
+    const float4 px = ldg4(prm.gt_boxes + 4ll * (g_begin + g));
+    const BoxC c = box_consts(fdiv(px.x, prm.norm_w), fdiv(px.y, prm.norm_h), fdiv(px.z, prm.norm_w), fdiv(px.w, prm.norm_h), true);
+    float lim = 1e-30f;          // overlap-only pruning unless a seed raises it
+    if (want_seeds && prm.P == 8732) {
+        const int lv = kSeedLevel[lane], side = kLevelSide[lv];
+        int ix = (int)floorf(c.xc * (float)side), iy = (int)floorf(c.yc * (float)side);
+        ix = min(max(ix, 0), side - 1);
+        iy = min(max(iy, 0), side - 1);
+        const int ps = kLevelOffset[lv] + (iy * side + ix) * kLevelShapes[lv] + kSeedShape[lane];
+        const float v = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, ps), c);
+        const float cb0 = ord_decode(__reduce_max_sync(FULL, ord_encode(v)));   // NaN sorts to the top
+        if (cb0 > 0.0f) lim = fmaxf(fmul(kPruneSlack, fminf(cb0, prm.thresh)), 1e-30f);
+    }
+    if (lane == 0) {
+        float4* rec = prm.gt_rec + 3ll * ((long long)b * prm.max_gt + g);
+        rec[0] = make_float4(c.x1, c.y1, c.x2, c.y2);
+        rec[1] = make_float4(c.area, c.xc, c.yc, c.at);
+        rec[2] = make_float4(lim, __int_as_float((int)prm.gt_labels[g_begin + g]), 0.f, 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // loss_image_kernel: CE + smooth-L1 + hard-negative mining of one image per CTA
 // ---------------------------------------------------------------------------------------------
-constexpr int LT = 1024;                       // threads
-constexpr int KQ = SSDHOT_MAX_PRIORS / LT;     // priors per thread (10 slots; 8732 uses 9)
+constexpr int LT = 768;                        // threads; 2 CTAs per SM keep every image of a 256-batch resident
 
 struct LossShared {
     unsigned hist[256];
     double dscratch[32];
     int iscratch[32];
-    unsigned sel_digit, sel_need;
+    unsigned sel_digit, sel_need, sel_eq;
 };
 
+// per-prior target of the loss kernel: -1 = negative, >= 0 target class of a positive (mg = matched box)
+template <bool FROM_TARGETS>
+__device__ __forceinline__ int load_target(const TrainParams& prm, long long row, int g_begin, int& mg) {
+    mg = -1;
+    if (FROM_TARGETS) return prm.in_pos[row] != 0 ? (int)prm.in_cls[row] : -1;
+    const int code = (int)prm.code[row];
+    if (code == 0) return -1;
+    mg = code - 1;
+    return (int)prm.gt_labels[g_begin + mg] + 1;
+}
+
+constexpr unsigned kNotNegative = 0xffffffffu;   // key of a positive prior (never a float >= 0 bit pattern)
+
 template <int CT, bool FROM_TARGETS>
-__global__ void __launch_bounds__(LT) loss_image_kernel(const TrainParams prm) {
+__global__ void __launch_bounds__(LT, 2) loss_image_kernel(const TrainParams prm) {
+    extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ LossShared ls;
+    unsigned* keys = reinterpret_cast<unsigned*>(dyn);     // [P] CE bits of negatives (CE >= 0: bit order = value order)
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = prm.P;
     const int g_begin = FROM_TARGETS ? 0 : prm.gt_offsets[b];
@@ -393,39 +426,25 @@ __global__ void __launch_bounds__(LT) loss_image_kernel(const TrainParams prm) {
     for (int i = tid; i < 256; i += LT) ls.hist[i] = 0u;
     __syncthreads();
 
-    float ce[KQ];
-    unsigned key[KQ];        // CE bits of negatives (CE >= 0, so the bit pattern orders them); 0 otherwise
-    int tgt[KQ];             // -1 = negative (class 0), else target class of a positive
-    int mg[KQ];              // matched box of a positive
     double acc_loc = 0.0, acc_ce = 0.0;
     int my_pos = 0;
-#pragma unroll
-    for (int k = 0; k < KQ; ++k) {
-        const int p = k * LT + tid;
-        ce[k] = 0.0f; key[k] = 0u; tgt[k] = -1; mg[k] = -1;
-        if (p >= P) { tgt[k] = -2; continue; }            // -2: no prior in this slot
+#pragma unroll 2
+    for (int p = tid; p < P; p += LT) {
         const long long row = (long long)b * P + p;
-        int cls = 0;
-        if (FROM_TARGETS) {
-            if (prm.in_pos[row] != 0) { tgt[k] = (int)prm.in_cls[row]; cls = tgt[k]; }
-        } else {
-            const int code = (int)prm.code[row];
-            if (code != 0) {
-                mg[k] = code - 1;
-                tgt[k] = (int)prm.gt_labels[g_begin + mg[k]] + 1;
-                cls = tgt[k];
-            }
-        }
+        int mg;
+        const int tgt = load_target<FROM_TARGETS>(prm, row, g_begin, mg);
+        const int cls = tgt < 0 ? 0 : tgt;
         float mx, lg;
         row_lse<CT>(prm.conf_all + row * prm.C, prm.C, mx, lg);
         const float xc = __ldg(prm.conf_all + row * prm.C + cls);
         // -log_softmax[c] = -((x_c - max) - log(sum))  (ATen PersistentSoftmax.cuh, nll_loss)
-        ce[k] = -fsub(fsub(xc, mx), lg);
-        if (tgt[k] >= 0) {
+        const float ce = -fsub(fsub(xc, mx), lg);
+        if (tgt >= 0) {
             my_pos += 1;
-            acc_ce += (double)ce[k];
+            acc_ce += (double)ce;
+            keys[p] = kNotNegative;
             if (!FROM_TARGETS && prm.loc_all) {
-                const float4 px = ldg4(prm.gt_boxes + 4ll * (g_begin + mg[k]));
+                const float4 px = ldg4(prm.gt_boxes + 4ll * (g_begin + mg));
                 const float x1 = fdiv(px.x, prm.norm_w), y1 = fdiv(px.y, prm.norm_h);
                 const float x2 = fdiv(px.z, prm.norm_w), y2 = fdiv(px.w, prm.norm_h);
                 const float4 gbox = make_float4(fmul(fadd(x1, x2), 0.5f), fmul(fadd(y1, y2), 0.5f), fsub(x2, x1), fsub(y2, y1));
@@ -439,11 +458,12 @@ __global__ void __launch_bounds__(LT) loss_image_kernel(const TrainParams prm) {
                 }
             }
         } else {
-            key[k] = __float_as_uint(ce[k]);
-            atomicAdd(&ls.hist[key[k] >> 24], 1u);          // first radix pass rides along
+            const unsigned key = __float_as_uint(ce);
+            keys[p] = key;
+            atomicAdd(&ls.hist[key >> 24], 1u);             // first radix pass rides along
         }
     }
-    const int n_pos_img = block_sum<int>(my_pos, ls.iscratch);      // (two barriers: hist is complete)
+    const int n_pos_img = block_sum<int>(my_pos, ls.iscratch);      // (two barriers: keys and hist are complete)
     if (tid == 0 && prm.n_pos) prm.n_pos[b] = n_pos_img;
 
     // ---- hard-negative budget (SSD_trainer.py:585-596) --------------------------------------
@@ -463,9 +483,10 @@ __global__ void __launch_bounds__(LT) loss_image_kernel(const TrainParams prm) {
                 for (int i = tid; i < 256; i += LT) ls.hist[i] = 0u;
                 __syncthreads();
                 const unsigned himask = 0xffffffffu << (shift + 8);
-#pragma unroll
-                for (int k = 0; k < KQ; ++k)
-                    if (tgt[k] == -1 && ((key[k] & himask) == prefix)) atomicAdd(&ls.hist[(key[k] >> shift) & 255u], 1u);
+                for (int p = tid; p < P; p += LT) {
+                    const unsigned key = keys[p];
+                    if (key != kNotNegative && ((key & himask) == prefix)) atomicAdd(&ls.hist[(key >> shift) & 255u], 1u);
+                }
                 __syncthreads();
             }
             if (tid < 32) {
@@ -485,7 +506,7 @@ __global__ void __launch_bounds__(LT) loss_image_kernel(const TrainParams prm) {
                     for (int j = 0; j < 8; ++j) {
                         const int bin = 255 - (tid * 8 + j);
                         const unsigned c = ls.hist[bin];
-                        if (run + c >= remaining) { ls.sel_digit = (unsigned)bin; ls.sel_need = remaining - run; ls.iscratch[0] = (int)c; break; }
+                        if (run + c >= remaining) { ls.sel_digit = (unsigned)bin; ls.sel_need = remaining - run; ls.sel_eq = c; break; }
                         run += c;
                     }
                 }
@@ -493,7 +514,7 @@ __global__ void __launch_bounds__(LT) loss_image_kernel(const TrainParams prm) {
             __syncthreads();
             prefix |= ls.sel_digit << shift;
             remaining = ls.sel_need;
-            n_eq = (unsigned)ls.iscratch[0];
+            n_eq = ls.sel_eq;
             __syncthreads();
         }
         thr_key = prefix;
@@ -502,18 +523,19 @@ __global__ void __launch_bounds__(LT) loss_image_kernel(const TrainParams prm) {
 
     // ---- sums (and the backward selection) --------------------------------------------------
     if (kk > 0) {
-#pragma unroll
-        for (int k = 0; k < KQ; ++k)
-            if (tgt[k] == -1 && (take_all || key[k] > thr_key)) acc_ce += (double)ce[k];
+        for (int p = tid; p < P; p += LT) {
+            const unsigned key = keys[p];
+            if (key != kNotNegative && (take_all || key > thr_key)) acc_ce += (double)__uint_as_float(key);
+        }
     }
     if (prm.sel_cls) {
         // of the negatives equal to the threshold value the first `need` in prior order are taken
         const bool all_ties = take_all || kk == 0 || need == n_eq;
         int before = 0;
-#pragma unroll
-        for (int k = 0; k < KQ; ++k) {
-            const int p = k * LT + tid;
-            const bool tie = kk > 0 && !take_all && tgt[k] == -1 && key[k] == thr_key;
+        for (int base = 0; base < P; base += LT) {
+            const int p = base + tid;
+            const unsigned key = p < P ? keys[p] : kNotNegative;
+            const bool tie = kk > 0 && !take_all && key != kNotNegative && key == thr_key;
             int rank_tie = 0;
             if (!all_ties) {
                 const unsigned bal = __ballot_sync(FULL, tie);
@@ -527,11 +549,13 @@ __global__ void __launch_bounds__(LT) loss_image_kernel(const TrainParams prm) {
             }
             if (p >= P) continue;
             const long long row = (long long)b * P + p;
+            int mg;
+            const int tgt = load_target<FROM_TARGETS>(prm, row, g_begin, mg);
             int8_t sel = -1;
-            if (tgt[k] >= 0) sel = (int8_t)tgt[k];
-            else if (kk > 0 && (take_all || key[k] > thr_key || (tie && (all_ties || (unsigned)rank_tie < need)))) sel = 0;
+            if (tgt >= 0) sel = (int8_t)tgt;
+            else if (kk > 0 && (take_all || key > thr_key || (tie && (all_ties || (unsigned)rank_tie < need)))) sel = 0;
             prm.sel_cls[row] = sel;
-            if (prm.matched16) prm.matched16[row] = (int16_t)mg[k];
+            if (prm.matched16) prm.matched16[row] = (int16_t)mg;
         }
     }
     // the `need` threshold-valued negatives are counted once
@@ -676,6 +700,11 @@ static int launch_match(const TrainParams& prm, cudaStream_t stream) {
     // a fixed cluster of 8 balances best at SSD300 sizes (1092 priors per CTA); small P shrink it
     const int cs = train_cluster_size(prm.P);
     if (cs * SLOTS < prm.P) return SSDHOT_ERR_SHAPE;
+    if (prm.max_gt > 0) {
+        const long long warps = (long long)prm.B * prm.max_gt;
+        gt_prepare_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(prm, PRUNE ? 1 : 0);
+        SSDHOT_CHECK_LAUNCH();
+    }
     const size_t dyn = smem_bytes(prm.max_gt > 0 ? prm.max_gt : 1);
     auto kern = match_kernel<PRUNE>;
     static size_t configured = 0;      // per instantiation; sticky opt-in, raised outside graph capture
@@ -704,8 +733,9 @@ static int launch_match(const TrainParams& prm, cudaStream_t stream) {
 
 template <bool FROM_TARGETS>
 static int launch_loss(const TrainParams& prm, cudaStream_t stream) {
-    if (prm.C == 6) loss_image_kernel<6, FROM_TARGETS><<<prm.B, LT, 0, stream>>>(prm);
-    else loss_image_kernel<0, FROM_TARGETS><<<prm.B, LT, 0, stream>>>(prm);
+    const size_t dyn = (size_t)prm.P * 4;       // <= 40 KB: no opt-in needed
+    if (prm.C == 6) loss_image_kernel<6, FROM_TARGETS><<<prm.B, LT, dyn, stream>>>(prm);
+    else loss_image_kernel<0, FROM_TARGETS><<<prm.B, LT, dyn, stream>>>(prm);
     SSDHOT_CHECK_LAUNCH();
     return SSDHOT_OK;
 }
@@ -753,12 +783,14 @@ extern "C" int ssdhot_match_encode(const float* priors_cxcywh, const float* prio
                                    float iou_thresh, float var_center, float var_size,
                                    float* loc_t, int loc_positives_only, int64_t* cls_t, uint8_t* pos_mask,
                                    int32_t* matched_gt, float* matched_cxcywh, int32_t* n_pos,
-                                   int32_t* dev_flags, ssdhot_stream_t stream) {
+                                   int32_t* dev_flags, void* work, ssdhot_stream_t stream) {
     int rc = check_gt_args(priors_cxcywh, priors_xyxy, prior_aux, P, gt_boxes, gt_labels, gt_offsets, B, max_gt,
                            norm_w, norm_h, var_center, var_size);
     if (rc) return rc;
-    if (!aligned16(loc_t) || !aligned16(matched_cxcywh)) return SSDHOT_ERR_ALIGN;
+    if (!aligned16(loc_t) || !aligned16(matched_cxcywh) || !aligned16(work)) return SSDHOT_ERR_ALIGN;
+    if (max_gt > 0 && !work) return SSDHOT_ERR_NULL;
     TrainParams prm = {};
+    prm.gt_rec = reinterpret_cast<float4*>(work);
     prm.pri = priors_cxcywh; prm.pri_xyxy = priors_xyxy; prm.pri_aux = prior_aux; prm.P = P;
     prm.gt_boxes = gt_boxes; prm.gt_labels = gt_labels; prm.gt_offsets = gt_offsets;
     prm.B = B; prm.max_gt = max_gt; prm.norm_w = norm_w; prm.norm_h = norm_h;
@@ -780,13 +812,19 @@ extern "C" int ssdhot_compact_rows(const float* loc_t, const uint8_t* pos_mask, 
     return SSDHOT_OK;
 }
 
-// workspace layout: img_part [B][2] double | n_pos [B] int32 (padded to 8) | code [B,P] uint16
+// workspace layout: img_part [B][2] double | n_pos [B] int32 | gt_rec [B*max_gt][3] float4 | code [B,P] uint16
 static size_t ws_npos_off(int B) { return (size_t)B * 2 * sizeof(double); }
-static size_t ws_code_off(int B) { return ws_npos_off(B) + (((size_t)B * sizeof(int32_t) + 15) & ~(size_t)15); }
+static size_t ws_rec_off(int B) { return ws_npos_off(B) + (((size_t)B * sizeof(int32_t) + 15) & ~(size_t)15); }
+static size_t ws_code_off(int B, int max_gt) { return ws_rec_off(B) + (size_t)B * (max_gt > 0 ? max_gt : 0) * 48; }
 
-extern "C" unsigned long long ssdhot_loss_workspace_bytes(int B, int P) {
-    if (B <= 0 || P <= 0) return 0;
-    return (unsigned long long)(ws_code_off(B) + (size_t)B * P * sizeof(uint16_t) + 64);
+extern "C" unsigned long long ssdhot_match_workspace_bytes(int B, int max_gt) {
+    if (B <= 0 || max_gt < 0) return 0;
+    return (unsigned long long)((size_t)B * max_gt * 48 + 64);
+}
+
+extern "C" unsigned long long ssdhot_loss_workspace_bytes(int B, int P, int max_gt) {
+    if (B <= 0 || P <= 0 || max_gt < 0) return 0;
+    return (unsigned long long)(ws_code_off(B, max_gt) + (size_t)B * P * sizeof(uint16_t) + 64);
 }
 
 static int finalize(const TrainParams& prm, const int32_t* n_pos, double* sums, cudaStream_t stream) {
@@ -817,7 +855,8 @@ extern "C" int ssdhot_multibox_loss_fwd(const float* priors_cxcywh, const float*
     prm.thresh = iou_thresh; prm.inv_vc = 1.0f / var_center; prm.inv_vs = 1.0f / var_size;
     prm.loc_all = loc_all; prm.conf_all = conf_all; prm.C = C; prm.ratio = neg_pos_ratio;
     prm.img_part = reinterpret_cast<double*>(w);
-    prm.code = reinterpret_cast<uint16_t*>(w + ws_code_off(B));
+    prm.gt_rec = reinterpret_cast<float4*>(w + ws_rec_off(B));
+    prm.code = reinterpret_cast<uint16_t*>(w + ws_code_off(B, max_gt));
     prm.flags = dev_flags;
     // 1) match: cluster per image, pruned sweep, 2-byte code per prior
     rc = launch_match<true>(prm, (cudaStream_t)stream);

@@ -24,9 +24,10 @@ PROTOTYPES = {
     "ssdhot_prior_tables": (i32, [vp, i32, vp, vp, vp]),
     "ssdhot_prior_aux": (i32, [vp, i32, vp, vp]),
     "ssdhot_match_encode": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, f32, f32, f32,
-                                  vp, i32, vp, vp, vp, vp, vp, vp, vp]),
+                                  vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "ssdhot_match_workspace_bytes": (u64, [i32, i32]),
     "ssdhot_compact_rows": (i32, [vp, vp, vp, i32, i32, vp, vp]),
-    "ssdhot_loss_workspace_bytes": (u64, [i32, i32]),
+    "ssdhot_loss_workspace_bytes": (u64, [i32, i32, i32]),
     "ssdhot_multibox_loss_fwd": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, vp, vp, i32,
                                        f32, f32, f32, f64, vp, vp, vp, vp, vp, vp, vp]),
     "ssdhot_mined_ce_fwd": (i32, [vp, vp, vp, i32, i32, i32, f64, vp, vp, vp, vp]),

@@ -88,13 +88,15 @@ def match_encode_batch(priors: PriorSet, packed: PackedTargets, iou_thresh: floa
     out["pos_mask"] = torch.empty((B, P), dtype=torch.bool, device=dev) if want_pos else None
     out["matched_gt"] = torch.empty((B, P), dtype=torch.int32, device=dev) if want_matched_idx else None
     out["matched_cxcywh"] = torch.empty((B, P, 4), dtype=torch.float32, device=dev) if want_matched_box else None
+    work = _workspace("match", dev, _lib.lib().ssdhot_match_workspace_bytes(B, packed.max_gt))
     with torch.cuda.device(dev):
         rc = _lib.lib().ssdhot_match_encode(
             priors.priors.data_ptr(), priors.priors_xyxy.data_ptr(), priors.aux.data_ptr(), P,
             packed.boxes.data_ptr(), packed.labels.data_ptr(), packed.offsets.data_ptr(), B, packed.max_gt,
             float(norm_wh[0]), float(norm_wh[1]), float(iou_thresh), priors.variances[0], priors.variances[1],
             _ptr(loc), 1 if want_loc == "positives" else 0, _ptr(out["cls_t"]), _ptr(out["pos_mask"]),
-            _ptr(out["matched_gt"]), _ptr(out["matched_cxcywh"]), out["n_pos"].data_ptr(), None, _stream(dev))
+            _ptr(out["matched_gt"]), _ptr(out["matched_cxcywh"]), out["n_pos"].data_ptr(), None, work.data_ptr(),
+            _stream(dev))
     _lib.check(rc, "ssdhot_match_encode")
     return out
 
@@ -161,7 +163,7 @@ class _MinedCE(torch.autograd.Function):
         pos = pos_mask.to(torch.bool).contiguous()
         sums = torch.empty((3,), dtype=torch.float64, device=dev)
         sel = torch.empty((B, P), dtype=torch.int8, device=dev) if conf_all.requires_grad else None
-        work = _workspace("loss", dev, _lib.lib().ssdhot_loss_workspace_bytes(B, P))
+        work = _workspace("loss", dev, _lib.lib().ssdhot_loss_workspace_bytes(B, P, 0))
         with torch.cuda.device(dev):
             rc = _lib.lib().ssdhot_mined_ce_fwd(conf.data_ptr(), cls.data_ptr(), pos.data_ptr(), B, P, C, float(ratio),
                                                 sums.data_ptr(), work.data_ptr(), _ptr(sel), _stream(dev))
@@ -204,7 +206,7 @@ class _FusedLoss(torch.autograd.Function):
         sums = torch.empty((3,), dtype=torch.float64, device=dev)
         sel = torch.empty((B, P), dtype=torch.int8, device=dev) if need_grad else None
         matched = torch.empty((B, P), dtype=torch.int16, device=dev) if need_grad else None
-        work = _workspace("loss", dev, _lib.lib().ssdhot_loss_workspace_bytes(B, P))
+        work = _workspace("loss", dev, _lib.lib().ssdhot_loss_workspace_bytes(B, P, packed.max_gt))
         with torch.cuda.device(dev):
             rc = _lib.lib().ssdhot_multibox_loss_fwd(
                 priors.priors.data_ptr(), priors.priors_xyxy.data_ptr(), priors.aux.data_ptr(), P,

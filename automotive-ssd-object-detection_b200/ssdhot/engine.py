@@ -21,7 +21,7 @@ class HotPathStep:
     def __init__(self, priors: PriorSet, batch: int, n_classes: int, iou_thresh: float = 0.5,
                  neg_pos_ratio: float = 3.0, score_thresh: float = 0.01, nms_thresh: float = 0.45,
                  max_per_img: int = 200, class_agnostic: bool = False, metric: str = "diou",
-                 norm_wh=(300.0, 300.0), train_half: bool = True, infer_half: bool = True):
+                 norm_wh=(300.0, 300.0), train_half: bool = True, infer_half: bool = True, max_gt: int = 64):
         self.ps, self.B, self.C = priors, int(batch), int(n_classes)
         self.iou_thresh, self.ratio = float(iou_thresh), float(neg_pos_ratio)
         self.score_thresh, self.nms_thresh = float(score_thresh), float(nms_thresh)
@@ -31,7 +31,8 @@ class HotPathStep:
         dev = priors.device
         L = _lib.lib()
         self.sums = torch.zeros((3,), dtype=torch.float64, device=dev)
-        self.loss_work = torch.empty((int(L.ssdhot_loss_workspace_bytes(self.B, priors.P)),), dtype=torch.uint8, device=dev)
+        self.max_gt = int(max_gt)
+        self.loss_work = torch.empty((int(L.ssdhot_loss_workspace_bytes(self.B, priors.P, self.max_gt)),), dtype=torch.uint8, device=dev)
         self.pred_work = torch.empty((int(L.ssdhot_predict_workspace_bytes(self.B, self.C, self.max_per_img)),),
                                      dtype=torch.uint8, device=dev)
         m = self.max_per_img
@@ -45,6 +46,8 @@ class HotPathStep:
     # -- raw launches -------------------------------------------------------------------------
     def launch_loss(self, loc: torch.Tensor, conf: torch.Tensor, gt: PackedTargets, stream: int) -> None:
         ps = self.ps
+        if gt.max_gt > self.max_gt:
+            raise _lib.SsdhotError(f"HotPathStep was planned for at most {self.max_gt} boxes per image, got {gt.max_gt}")
         rc = _lib.lib().ssdhot_multibox_loss_fwd(
             ps.priors.data_ptr(), ps.priors_xyxy.data_ptr(), ps.aux.data_ptr(), ps.P,
             gt.boxes.data_ptr(), gt.labels.data_ptr(), gt.offsets.data_ptr(), self.B, gt.max_gt,

@@ -85,14 +85,17 @@ SSDHOT_API int ssdhot_prior_aux(const float* priors_xyxy, int P, float* prior_au
  *   loc_positives_only != 0, the other rows are left untouched), cls_t [B,P] int64,
  *   pos_mask [B,P] bytes, matched_gt [B,P] int32 (index inside the image),
  *   matched_cxcywh [B,P,4], n_pos [B] int32.
- * An image whose box count exceeds max_gt sets bit 0 of *dev_flags (optional). */
+ * An image whose box count exceeds max_gt sets bit 0 of *dev_flags (optional).
+ *   work: scratch of ssdhot_match_workspace_bytes(B, max_gt) bytes. */
 SSDHOT_API int ssdhot_match_encode(const float* priors_cxcywh, const float* priors_xyxy, const float* prior_aux, int P,
                         const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
                         int B, int max_gt, float norm_w, float norm_h,
                         float iou_thresh, float var_center, float var_size,
                         float* loc_t, int loc_positives_only, int64_t* cls_t, uint8_t* pos_mask,
                         int32_t* matched_gt, float* matched_cxcywh, int32_t* n_pos,
-                        int32_t* dev_flags, ssdhot_stream_t stream);
+                        int32_t* dev_flags, void* work, ssdhot_stream_t stream);
+/* scratch for ssdhot_match_encode (per-box records: 48 bytes each), 16-byte aligned */
+SSDHOT_API unsigned long long ssdhot_match_workspace_bytes(int B, int max_gt);
 
 /* Ordered compaction loc_t[pos_mask] (TR:547): rows of loc_t [B,P,4] whose mask byte is set, in
  * (image, prior) order, written to out[sum(n_pos),4].  n_pos [B] as written by
@@ -107,10 +110,10 @@ SSDHOT_API int ssdhot_compact_rows(const float* loc_t, const uint8_t* pos_mask, 
  * (TR:577-598).  Nothing of shape [B,P] is materialised unless asked for.
  *   sums [3] double, OVERWRITTEN: { sum smooth-L1, sum CE (positives + mined), sum n_pos } --
  *   un-normalised, ready for one all-reduce; loss = sums[0..1] / max(sums[2], 1) (TR:105,600).
- *   work: scratch of ssdhot_loss_workspace_bytes(B, P) bytes, 16-byte aligned.
+ *   work: scratch of ssdhot_loss_workspace_bytes(B, P, max_gt) bytes, 16-byte aligned.
  *   Optional, for the backward pass: sel_cls [B,P] int8 (-1 = prior not in the loss, else its
  *   target class), matched_gt [B,P] int16 (positives only, -1 elsewhere), n_pos [B]. */
-SSDHOT_API unsigned long long ssdhot_loss_workspace_bytes(int B, int P);
+SSDHOT_API unsigned long long ssdhot_loss_workspace_bytes(int B, int P, int max_gt);
 SSDHOT_API int ssdhot_multibox_loss_fwd(const float* priors_cxcywh, const float* priors_xyxy, const float* prior_aux, int P,
                              const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
                              int B, int max_gt, float norm_w, float norm_h,
