@@ -1,23 +1,27 @@
 // infer_path.cu -- decode, score threshold, ranking and greedy DIoU/CIoU NMS
 // (SURVEY.md section 8a rows a6-a8).
 //
-// Unit of work = one IMAGE: one CTA of 1024 threads walks the image's candidates of ALL classes in
-// one global score order and applies class-aware greedy NMS, so the walk can stop as soon as
-// max_per_img boxes survive.  That is exactly the reference's result -- per-class greedy NMS, then
-// a global score sort and `keep[:max_per_img]` (SSD_from_scratch.py:439-465): a candidate's fate
-// depends only on higher-scored candidates of its own class, all of which precede it in the
-// global order, and survivors are produced in global score order -- but it never ranks or tests
-// the thousands of low-score candidates that cannot reach the output.
-//
-// The image's scores live in shared memory as a dense array of order-preserving keys indexed by
-// candidate id prior*(C-1)+class (0 = not a candidate), so thresholding needs no compaction and
-// equal scores are ordered by candidate id for free.  Candidates are consumed best-first in
-// chunks: a 4-pass radix select pulls the next CHUNK highest keys, a bitonic network sorts them,
-// their boxes are decoded, and greedy NMS walks the chunk in tiles of 64 -- every (kept box |
-// earlier tile member) x (tile member) predicate is evaluated in parallel into 64-bit suppression
-// masks (ballot), then one thread resolves the tile serially with bit operations.
-// When the dense array does not fit in shared memory (many classes) the same unit runs per
-// (image, class) and a merge kernel combines the per-class survivor lists.
+// predict = two kernels:
+//  * score_kernel -- the HBM-bound half.  The class logits are streamed once, 8 CTAs per image;
+//    softmax is evaluated in the operation order of eager torch-CUDA, every (prior, foreground
+//    class) pair is tested against the score threshold, and the survivors are appended to the
+//    image's candidate list as 64-bit keys (order-preserving score bits << 32 | ~candidate id), so
+//    sorting the keys descending orders by score and breaks ties by candidate id
+//    prior*(C-1)+class.  A warp compacts its "maybe" pairs first, so the IEEE division, threshold
+//    test and append run once per ~24 pairs instead of once per class.
+//  * nms_image_kernel -- one CTA of 1024 threads per image walks the image's candidates of ALL
+//    classes in one global score order and applies class-aware greedy NMS, so the walk stops as
+//    soon as max_per_img boxes survive.  That is exactly the reference's result -- per-class greedy
+//    NMS, then a global score sort and `keep[:max_per_img]` (SSD_from_scratch.py:439-465): a
+//    candidate's fate depends only on higher-scored candidates of its own class, all of which
+//    precede it in the global order, and survivors appear in global score order -- but the
+//    thousands of low-score candidates that cannot reach the output are never ranked or tested.
+//    Candidates are consumed best-first in chunks of <= 256: a score histogram gives the cut, the
+//    chunk is sorted by a bitonic network (warp shuffles + 6 shared-memory stages), its boxes are
+//    decoded, and greedy NMS walks it in tiles of 64: 16 threads per tile member test it against
+//    the survivors of its class and the earlier tile members (cheap IoU gate first, exact metric
+//    only for pairs that can matter), then one thread resolves the tile with 64-bit masks.
+// The stand-alone NMS entry point (mySSD.iou_nms) runs the same unit over a dense key array.
 #include <map>
 #include <mutex>
 
@@ -34,9 +38,8 @@ constexpr int HBASE = (127 - 16) << 8;
 struct UnitShared {
     unsigned hist[256];
     unsigned long long rowmask[TILE];   // bit j of rowmask[i]: tile member i suppresses tile member j (j > i)
-    unsigned long long cmask[32];       // tile members per suppression group
+    unsigned long long best[32];
     unsigned long long keepbits;
-    int ngroup[32];                     // survivors per suppression group
     unsigned char suppf[TILE];          // tile member suppressed by an earlier survivor
     unsigned sel_prefix, sel_need, sel_eq;
     int counter;                        // gather cursor
@@ -72,6 +75,28 @@ __device__ __forceinline__ bool suppresses(const BoxC& S, const BoxC& c, float t
     return !(m <= thr);
 }
 
+// ---- candidate sources ---------------------------------------------------------------------------
+// A source is the set of candidates of one unit: entry i carries a 32-bit order-preserving key
+// (0 = absent / consumed) and a candidate id.
+struct DenseSource {           // key array indexed by candidate id (stand-alone NMS; shared memory)
+    unsigned* keys; int n;
+    __device__ __forceinline__ int size() const { return n; }
+    __device__ __forceinline__ unsigned long long raw(int i) const { return keys[i]; }
+    __device__ __forceinline__ void consume(int i) const { keys[i] = 0u; }
+    static __device__ __forceinline__ unsigned key(unsigned long long r) { return (unsigned)r; }
+    static __device__ __forceinline__ unsigned long long sortkey(unsigned long long r, int i) {
+        return (r << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+    }
+};
+struct ListSource {            // compact list of (key << 32 | ~id) written by score_kernel (global memory)
+    unsigned long long* list; int n;
+    __device__ __forceinline__ int size() const { return n; }
+    __device__ __forceinline__ unsigned long long raw(int i) const { return list[i]; }
+    __device__ __forceinline__ void consume(int i) const { list[i] = 0ull; }
+    static __device__ __forceinline__ unsigned key(unsigned long long r) { return (unsigned)(r >> 32); }
+    static __device__ __forceinline__ unsigned long long sortkey(unsigned long long r, int) { return r; }
+};
+
 // ---- ranking helpers ---------------------------------------------------------------------------
 
 // histogram bin of an ord_encode()d score in (0, 1]: exponent and the top 8 mantissa bits,
@@ -93,7 +118,6 @@ __device__ __forceinline__ void hist_add(unsigned* hist16, unsigned key) {
 // from the cut upwards are zeroed: they are consumed by the gather that follows.  1024 threads,
 // four bins each, thread 0 owns the top four.
 __device__ __forceinline__ void hist_cut(unsigned* hist16, int cap, UnitShared& us) {
-    __shared__ unsigned long long best[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int w0 = (1023 - tid) * 2;
     const unsigned lo = hist16[w0], hi = hist16[w0 + 1];
@@ -125,10 +149,10 @@ __device__ __forceinline__ void hist_cut(unsigned* hist16, int cap, UnitShared& 
         const unsigned long long y = __shfl_xor_sync(FULL, packed, o);
         packed = y < packed ? y : packed;
     }
-    if (lane == 0) best[warp] = packed;
+    if (lane == 0) us.best[warp] = packed;
     __syncthreads();
     if (tid < 32) {
-        unsigned long long v = best[tid];
+        unsigned long long v = us.best[tid];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const unsigned long long y = __shfl_xor_sync(FULL, v, o);
@@ -149,10 +173,10 @@ __device__ __forceinline__ void hist_cut(unsigned* hist16, int cap, UnitShared& 
     }
 }
 
-// Radix select over the non-zero entries of dense[0..n): the K-th largest key.  Returns the key,
-// how many entries equal to it are needed (`need`) and how many exist (`eq`).
-template <int NT>
-__device__ __forceinline__ void select_kth(const unsigned* dense, int n, unsigned K, UnitShared& us,
+// Radix select of the K-th largest of the non-zero 32-bit keys keyfn(0..n).  Returns the key, how
+// many entries equal to it are needed (`need`) and how many exist (`eq`).
+template <int NT, typename KeyFn>
+__device__ __forceinline__ void select_kth(int n, KeyFn keyfn, unsigned K, UnitShared& us,
                                            unsigned& thr, unsigned& need, unsigned& eq) {
     const int tid = threadIdx.x;
     unsigned prefix = 0u, remaining = K, count_eq = 0u;
@@ -162,7 +186,7 @@ __device__ __forceinline__ void select_kth(const unsigned* dense, int n, unsigne
         for (int i = tid; i < 256; i += NT) us.hist[i] = 0u;
         __syncthreads();
         for (int i = tid; i < n; i += NT) {
-            const unsigned k = dense[i];
+            const unsigned k = keyfn(i);
             if (k != 0u && (k & himask) == prefix) atomicAdd(&us.hist[(k >> shift) & 255u], 1u);
         }
         __syncthreads();
@@ -196,47 +220,58 @@ __device__ __forceinline__ void select_kth(const unsigned* dense, int n, unsigne
     thr = prefix; need = remaining; eq = count_eq;
 }
 
-// In-place bitonic sort (descending) of n_pad (power of two <= CHUNK) 64-bit keys in shared memory.
-__device__ __forceinline__ void bitonic_desc(unsigned long long* keys, int n_pad) {
+// Bitonic sort (descending) of CHUNK = 256 64-bit keys held in shared memory, by the first 256
+// threads (one key each): compare-exchange distances < 32 run on registers through warp shuffles,
+// the six larger ones through shared memory.  Every thread of the CTA must call it.
+__device__ __forceinline__ void bitonic_desc_256(unsigned long long* keys) {
     const int tid = threadIdx.x;
-    for (int k = 2; k <= n_pad; k <<= 1) {
+    unsigned long long v = tid < CHUNK ? keys[tid] : 0ull;
+    for (int k = 2; k <= CHUNK; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            __syncthreads();
-            if (tid < n_pad) {
-                const int partner = tid ^ j;
-                if (partner > tid) {
-                    const unsigned long long a = keys[tid], b = keys[partner];
-                    const bool desc = (tid & k) == 0;
-                    if (desc ? (a < b) : (a > b)) { keys[tid] = b; keys[partner] = a; }
+            const bool desc = (tid & k) == 0;
+            const bool lower = (tid & j) == 0;             // this thread holds the lower-indexed element
+            const bool take_max = (lower == desc);         // descending run: lower index keeps the larger key
+            if (j >= 32) {
+                __syncthreads();
+                if (tid < CHUNK) keys[tid] = v;
+                __syncthreads();
+                if (tid < CHUNK) {
+                    const unsigned long long o = keys[tid ^ j];
+                    v = take_max ? (o > v ? o : v) : (o < v ? o : v);
                 }
+            } else if (tid < CHUNK) {
+                const unsigned long long o = __shfl_xor_sync(FULL, v, j);
+                v = take_max ? (o > v ? o : v) : (o < v ? o : v);
             }
         }
     }
     __syncthreads();
+    if (tid < CHUNK) keys[tid] = v;
+    __syncthreads();
 }
 
 // ---- the unit ------------------------------------------------------------------------------------
-// dense:   [n] keys (0 = absent), consumed (zeroed) as candidates are ranked
+// src:     the candidates (consumed as they are ranked)
 // hist16:  packed 16-bit score histogram of the candidates (HIST only)
-// Fetch:   BoxC operator()(unsigned idx)      -- pixel box + constants of candidate idx
-// Group:   int operator()(unsigned idx)       -- suppression group (class) of candidate idx; only
+// Fetch:   BoxC operator()(unsigned id)       -- pixel box + constants of candidate id
+// Group:   int operator()(unsigned id)        -- suppression group (class) of candidate id; only
 //                                                members of the same group suppress each other
-// Emit:    void operator()(int pos, unsigned long long key, unsigned idx, const BoxC&)
+// Emit:    void operator()(int pos, unsigned long long key, unsigned id, const BoxC&)
 // kept:    the surviving boxes in output order, capacity max_keep (shared or global memory)
-// kidx:    [n_groups][max_keep] per-group lists of positions in `kept` (GROUPS only)
+// kidx:    [n_groups][max_keep] per-group lists of positions in `kept`; ngroup / cmask [n_groups]
 // returns the number of survivors (valid in every thread)
 struct UnitBuffers {
-    unsigned* dense; unsigned* hist16; unsigned long long* ckey; BoxC* cbox; unsigned char* cgroup;
-    BoxC* kept; unsigned short* kidx;
+    unsigned* hist16; unsigned long long* ckey; BoxC* cbox; unsigned char* cgroup;
+    BoxC* kept; unsigned short* kidx; int* ngroup; unsigned long long* cmask;
 };
 
-template <int METRIC, int NT, bool GROUPS, bool HIST, typename Fetch, typename Group, typename Emit>
-__device__ int nms_unit(const UnitBuffers buf, int n, int n_cand, int n_groups, int max_keep, float thr, UnitShared& us,
-                        Fetch fetch, Group group_of, Emit emit) {
-    constexpr int NW = NT / 32;
+template <int METRIC, int NT, bool GROUPS, bool HIST, typename Src, typename Fetch, typename Group, typename Emit>
+__device__ int nms_unit(const Src src, const UnitBuffers buf, int n_cand, int n_groups, int max_keep, float thr,
+                        UnitShared& us, Fetch fetch, Group group_of, Emit emit) {
+    static_assert(NT >= CHUNK, "one thread per chunk entry in the sort");
     constexpr int SUB = NT / TILE;                 // threads cooperating on one tile member (16 or 8)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned* dense = buf.dense;
+    const int n = src.size();
     unsigned long long* ckey = buf.ckey;
     BoxC* cbox = buf.cbox;
     BoxC* kept = buf.kept;
@@ -244,7 +279,7 @@ __device__ int nms_unit(const UnitBuffers buf, int n, int n_cand, int n_groups, 
     int kept_n = 0;
     int remaining = n_cand;
     bool use_hist = HIST && NT == 1024 && n < 65536;       // 16-bit bin counters, one thread per four bins
-    if (tid < 32) us.ngroup[tid] = 0;
+    if (GROUPS) for (int g = tid; g < n_groups; g += NT) buf.ngroup[g] = 0;
     while (remaining > 0 && kept_n < max_keep) {
         // ---- pull the next best candidates ---------------------------------------------------
         int K = remaining < CHUNK ? remaining : CHUNK;
@@ -252,53 +287,43 @@ __device__ int nms_unit(const UnitBuffers buf, int n, int n_cand, int n_groups, 
         bool all = remaining <= CHUNK;
         if (!all && use_hist) {
             hist_cut(buf.hist16, CHUNK, us);
-            if (us.cut_count > 0) { K = us.cut_count; tkey = bin_floor_key(us.cut_bin); need = eq = 0u; all = true; }
+            if (us.cut_count > 0) { K = us.cut_count; tkey = bin_floor_key(us.cut_bin); all = true; }
             else use_hist = false;                 // a single bin holds more than a chunk: exact select from here on
             __syncthreads();
         }
-        if (!all) select_kth<NT>(dense, n, (unsigned)K, us, tkey, need, eq);
-        if (tid == 0) us.counter = 0;
-        __syncthreads();
-        if (all || need == eq) {
-            for (int i = tid; i < n; i += NT) {
-                const unsigned k = dense[i];
-                if (k != 0u && k >= tkey) {
-                    const int pos = atomicAdd(&us.counter, 1);
-                    ckey[pos] = ((unsigned long long)k << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
-                    dense[i] = 0u;
-                }
-            }
-        } else {
-            // more entries equal to the threshold key than needed: take the lowest ids first
-            int taken_eq = 0;
-            for (int base = 0; base < n; base += NT) {
-                const int i = base + tid;
-                const unsigned k = i < n ? dense[i] : 0u;
-                const bool is_eq = k != 0u && k == tkey;
-                const unsigned bal = __ballot_sync(FULL, is_eq);
-                __syncthreads();
-                if (lane == 0) us.iscratch[warp] = __popc(bal);
-                __syncthreads();
-                int before = taken_eq, tot = 0;
-                for (int w = 0; w < NW; ++w) { if (w < warp) before += us.iscratch[w]; tot += us.iscratch[w]; }
-                const int my_rank = before + __popc(bal & ((1u << lane) - 1u));
-                if (k != 0u && (k > tkey || (is_eq && (unsigned)my_rank < need))) {
-                    const int pos = atomicAdd(&us.counter, 1);
-                    ckey[pos] = ((unsigned long long)k << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
-                    dense[i] = 0u;
-                }
-                taken_eq += tot;
+        unsigned tie_floor = 0u;        // among entries with key == tkey only those with ~id >= tie_floor are taken
+        if (!all) {
+            select_kth<NT>(n, [&](int i) { return Src::key(src.raw(i)); }, (unsigned)K, us, tkey, need, eq);
+            if (need != eq) {
+                // more entries share the threshold score than are needed: take the lowest candidate ids
+                // (= the largest ~id, which is the low half of the sort key) -- a second select over ids
+                unsigned n2, e2;
+                select_kth<NT>(n, [&](int i) {
+                    const unsigned long long r = src.raw(i);
+                    return Src::key(r) == tkey ? (unsigned)(Src::sortkey(r, i) & 0xffffffffull) : 0u;
+                }, need, us, tie_floor, n2, e2);
             }
         }
-        int n_pad = 64;
-        while (n_pad < K) n_pad <<= 1;
+        if (tid == 0) us.counter = 0;
         __syncthreads();
-        for (int i = K + tid; i < n_pad; i += NT) ckey[i] = 0ull;
-        bitonic_desc(ckey, n_pad);
+        for (int i = tid; i < n; i += NT) {
+            const unsigned long long r = src.raw(i);
+            const unsigned k = Src::key(r);
+            if (k == 0u || k < tkey) continue;
+            const unsigned long long sk = Src::sortkey(r, i);
+            if (k == tkey && (unsigned)(sk & 0xffffffffull) < tie_floor) continue;
+            const int pos = atomicAdd(&us.counter, 1);
+            ckey[pos] = sk;
+            src.consume(i);
+        }
+        __syncthreads();
+        for (int i = K + tid; i < CHUNK; i += NT) ckey[i] = 0ull;
+        __syncthreads();
+        bitonic_desc_256(ckey);
         for (int i = tid; i < K; i += NT) {
-            const unsigned idx = 0xffffffffu - (unsigned)(ckey[i] & 0xffffffffull);
-            cbox[i] = fetch(idx);
-            buf.cgroup[i] = GROUPS ? (unsigned char)group_of(idx) : (unsigned char)0;
+            const unsigned id = 0xffffffffu - (unsigned)(ckey[i] & 0xffffffffull);
+            cbox[i] = fetch(id);
+            buf.cgroup[i] = GROUPS ? (unsigned char)group_of(id) : (unsigned char)0;
         }
         if (tid < TILE) { us.rowmask[tid] = 0ull; us.suppf[tid] = 0; }
         __syncthreads();
@@ -315,7 +340,7 @@ __device__ int nms_unit(const UnitBuffers buf, int n, int n_cand, int n_groups, 
                 bool hit = false;
                 if (GROUPS) {
                     const unsigned short* list = buf.kidx + (size_t)g * max_keep;
-                    const int ng = us.ngroup[g];
+                    const int ng = buf.ngroup[g];
                     for (int i = sub; i < ng; i += SUB) hit |= suppresses<METRIC>(kept[list[i]], c, thr, thr_lo);
                 } else {
                     for (int i = sub; i < kept_n; i += SUB) hit |= suppresses<METRIC>(kept[i], c, thr, thr_lo);
@@ -333,13 +358,6 @@ __device__ int nms_unit(const UnitBuffers buf, int n, int n_cand, int n_groups, 
                 const unsigned s_hi = __ballot_sync(FULL, in_hi && us.suppf[lane + 32] != 0);
                 const unsigned z_lo = __ballot_sync(FULL, in_lo && us.rowmask[lane] != 0ull);
                 const unsigned z_hi = __ballot_sync(FULL, in_hi && us.rowmask[lane + 32] != 0ull);
-                if (GROUPS) {
-                    const int g_lo = in_lo ? (int)buf.cgroup[t0 + lane] : -1, g_hi = in_hi ? (int)buf.cgroup[t0 + lane + 32] : -1;
-                    for (int g = 0; g < n_groups; ++g) {
-                        const unsigned a = __ballot_sync(FULL, g_lo == g), b2 = __ballot_sync(FULL, g_hi == g);
-                        if (lane == 0) us.cmask[g] = ((unsigned long long)b2 << 32) | a;
-                    }
-                }
                 if (lane == 0) {
                     const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
                     const unsigned long long supp = ((unsigned long long)s_hi << 32) | s_lo;
@@ -364,6 +382,15 @@ __device__ int nms_unit(const UnitBuffers buf, int n, int n_cand, int n_groups, 
             }
             __syncthreads();
             const unsigned long long keepb = us.keepbits;
+            if (GROUPS) {
+                // tile members per group (one thread per group; at most 64 byte loads each)
+                for (int g = tid; g < n_groups; g += NT) {
+                    unsigned long long mk = 0ull;
+                    for (int i = 0; i < m; ++i) mk |= (unsigned long long)((int)buf.cgroup[t0 + i] == g) << i;
+                    buf.cmask[g] = mk;
+                }
+                __syncthreads();
+            }
             if (tid < m && ((keepb >> tid) & 1ull)) {
                 const unsigned long long lower = keepb & ((1ull << tid) - 1ull);
                 const int pos = kept_n + __popcll(lower);
@@ -371,7 +398,7 @@ __device__ int nms_unit(const UnitBuffers buf, int n, int n_cand, int n_groups, 
                 kept[pos] = bx;
                 if (GROUPS) {
                     const int g = (int)buf.cgroup[t0 + tid];
-                    buf.kidx[(size_t)g * max_keep + us.ngroup[g] + __popcll(lower & us.cmask[g])] = (unsigned short)pos;
+                    buf.kidx[(size_t)g * max_keep + buf.ngroup[g] + __popcll(lower & buf.cmask[g])] = (unsigned short)pos;
                 }
                 const unsigned long long key = ckey[t0 + tid];
                 emit(pos, key, 0xffffffffu - (unsigned)(key & 0xffffffffull), bx);
@@ -379,235 +406,202 @@ __device__ int nms_unit(const UnitBuffers buf, int n, int n_cand, int n_groups, 
             if (tid >= NT - TILE) { us.rowmask[tid - (NT - TILE)] = 0ull; us.suppf[tid - (NT - TILE)] = 0; }
             kept_n += __popcll(keepb);
             __syncthreads();
-            if (GROUPS && tid < n_groups) us.ngroup[tid] += __popcll(keepb & us.cmask[tid]);
-            __syncthreads();
+            if (GROUPS) {
+                for (int g = tid; g < n_groups; g += NT) buf.ngroup[g] += __popcll(keepb & buf.cmask[g]);
+                __syncthreads();
+            }
         }
         remaining -= K;
     }
     return kept_n;
 }
 
-// shared-memory carve-up of one unit: kept | cbox | ckey | dense | hist16 | kidx | cgroup
-__host__ __device__ inline size_t unit_smem_bytes(long long n, int max_keep, int n_groups, bool hist) {
-    return (size_t)max_keep * sizeof(BoxC) + (size_t)CHUNK * (sizeof(BoxC) + 8) + (size_t)n * 4 +
-           (hist ? (size_t)HBINS * 2 : 0) + (size_t)n_groups * max_keep * 2 + (size_t)CHUNK + 32;
+// ---- predict: parameters ---------------------------------------------------------------------------
+struct PredictParams {
+    const float* pri; int P; const float* loc_all; const float* conf_all; int B, C;
+    float score_thresh, nms_thresh; int max_keep; float vc, vs, img_w, img_h;
+    unsigned long long* cand;       // [B][P*(C-1)] candidate keys
+    int* cand_count;                // [B]
+    int64_t* out_labels; float* out_scores; float* out_boxes; int32_t* out_cand; int32_t* out_count;
+};
+
+// exp(x_i - max) of one row and their sum in eager torch-CUDA order (persistent warp softmax:
+// lanes = min(next_pow2(C), 32); lane l accumulates elements l, l+32, ... in order; then butterfly
+// adds over xor offsets lanes/2 .. 1).  C == 6 is the reference's class count.
+__device__ __forceinline__ float row_exps6(const float* __restrict__ row, float* e) {
+    const float2 a = ldg2(row), b = ldg2(row + 2), c = ldg2(row + 4);
+    const float mx = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y)), fmaxf(c.x, c.y));
+    e[0] = expf(fsub(a.x, mx)); e[1] = expf(fsub(a.y, mx)); e[2] = expf(fsub(b.x, mx));
+    e[3] = expf(fsub(b.y, mx)); e[4] = expf(fsub(c.x, mx)); e[5] = expf(fsub(c.y, mx));
+    return fadd(fadd(fadd(e[0], e[4]), e[2]), fadd(fadd(e[1], e[5]), e[3]));
 }
-__device__ __forceinline__ UnitBuffers carve_unit(unsigned char* dyn, long long n, int max_keep, int n_groups, bool hist) {
+
+__device__ __forceinline__ float row_sum_generic(const float* __restrict__ row, int C, float& mx) {
+    int lanes = 1;
+    while (lanes < C && lanes < 32) lanes <<= 1;
+    mx = __ldg(row);
+    for (int i = 1; i < C; ++i) mx = fmaxf(mx, __ldg(row + i));
+    float part[32];
+    for (int l = 0; l < 32; ++l) part[l] = 0.0f;
+    for (int i = 0; i < C; ++i) part[i & (lanes - 1)] = fadd(part[i & (lanes - 1)], expf(fsub(__ldg(row + i), mx)));
+    for (int off = lanes >> 1; off > 0; off >>= 1)
+        for (int l = 0; l < off; ++l) part[l] = fadd(part[l], part[l + off]);
+    return part[0];
+}
+
+constexpr int ST = 256;        // threads of score_kernel
+constexpr int SCS = 8;         // CTAs per image
+constexpr int PT = 1024;       // threads of nms_image_kernel
+constexpr int UT = 512;        // threads of stand-alone NMS
+
+// A score can only pass `s > thresh` if e_k > thr_pre * sum, thr_pre = thresh * (1 - 1e-5): the
+// margin is two orders of magnitude above the rounding of the product and of the division, so
+// pairs below it skip the IEEE division without changing any decision.
+template <int CT>
+__global__ void __launch_bounds__(ST) score_kernel(const PredictParams prm) {
+    __shared__ float st_e[ST / 32][32 * 5], st_s[ST / 32][32 * 5];
+    __shared__ unsigned st_id[ST / 32][32 * 5];
+    const int b = blockIdx.x / SCS, part = blockIdx.x % SCS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = prm.P, n_fg = prm.C - 1;
+    const int rows = (P + SCS - 1) / SCS;
+    const int r0 = part * rows, r1 = min(P, r0 + rows);
+    const float thr_pre = fmul(prm.score_thresh, 0.99999f);
+    const float* conf_b = prm.conf_all + (long long)b * P * prm.C;
+    unsigned long long* list = prm.cand + (long long)b * P * n_fg;
+    int* count = prm.cand_count + b;
+    const unsigned lt = (1u << lane) - 1u;
+
+    for (int base = r0 + warp * 32; base < r1; base += ST) {      // warp-uniform trip count
+        const int p = base + lane;
+        const bool live = p < r1;
+        if (CT == 6) {
+            float e[6];
+            float sum = 1.0f;
+            bool f[5] = {false, false, false, false, false};
+            if (live) {
+                sum = row_exps6(conf_b + (long long)p * 6, e);
+                const float gate = fmul(thr_pre, sum);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) f[k] = e[k + 1] > gate;
+            }
+            // compact the "maybe" pairs of the warp into shared memory, class-major
+            int total = 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const unsigned bal = __ballot_sync(FULL, f[k]);
+                if (f[k]) {
+                    const int slot = total + __popc(bal & lt);
+                    st_e[warp][slot] = e[k + 1];
+                    st_s[warp][slot] = sum;
+                    st_id[warp][slot] = (unsigned)(p * 5 + k);
+                }
+                total += __popc(bal);
+            }
+            __syncwarp();
+            for (int it = 0; it < total; it += 32) {
+                const int i = it + lane;
+                bool ok = false;
+                unsigned long long key = 0ull;
+                if (i < total) {
+                    const float s = fdiv(st_e[warp][i], st_s[warp][i]);      // softmax(conf)[..., 1:]  (SFS:388)
+                    ok = s > prm.score_thresh;                               // strict (SFS:402)
+                    key = ((unsigned long long)(__float_as_uint(s) | 0x80000000u) << 32) |
+                          (unsigned long long)(0xffffffffu - st_id[warp][i]);
+                }
+                const unsigned bal = __ballot_sync(FULL, ok);
+                int dst = 0;
+                if (lane == 0 && bal) dst = atomicAdd(count, __popc(bal));
+                dst = __shfl_sync(FULL, dst, 0);
+                if (ok) list[dst + __popc(bal & lt)] = key;
+            }
+            __syncwarp();
+        } else {
+            float mx = 0.0f, sum = 1.0f;
+            if (live) sum = row_sum_generic(conf_b + (long long)p * prm.C, prm.C, mx);
+            const float gate = fmul(thr_pre, sum);
+            for (int k = 0; k < n_fg; ++k) {
+                bool ok = false;
+                unsigned long long key = 0ull;
+                if (live) {
+                    const float ek = expf(fsub(__ldg(conf_b + (long long)p * prm.C + k + 1), mx));
+                    if (ek > gate) {
+                        const float s = fdiv(ek, sum);
+                        ok = s > prm.score_thresh;
+                        key = ((unsigned long long)(__float_as_uint(s) | 0x80000000u) << 32) |
+                              (unsigned long long)(0xffffffffu - (unsigned)(p * n_fg + k));
+                    }
+                }
+                const unsigned bal = __ballot_sync(FULL, ok);
+                if (bal == 0u) continue;
+                int dst = 0;
+                if (lane == 0) dst = atomicAdd(count, __popc(bal));
+                dst = __shfl_sync(FULL, dst, 0);
+                if (ok) list[dst + __popc(bal & lt)] = key;
+            }
+        }
+    }
+}
+
+// shared-memory carve-up of one unit: kept | cbox | ckey | cmask | hist16 | ngroup | kidx | cgroup
+__host__ __device__ inline size_t unit_smem_bytes(int max_keep, int n_groups, bool hist) {
+    return (size_t)max_keep * sizeof(BoxC) + (size_t)CHUNK * (sizeof(BoxC) + 8) + (size_t)n_groups * 8 +
+           (hist ? (size_t)HBINS * 2 : 0) + (size_t)n_groups * 4 + (size_t)n_groups * max_keep * 2 + (size_t)CHUNK + 48;
+}
+__device__ __forceinline__ UnitBuffers carve_unit(unsigned char* dyn, int max_keep, int n_groups, bool hist) {
     UnitBuffers b;
     b.kept = reinterpret_cast<BoxC*>(dyn);
     b.cbox = b.kept + max_keep;
     b.ckey = reinterpret_cast<unsigned long long*>(b.cbox + CHUNK);
-    b.dense = reinterpret_cast<unsigned*>(b.ckey + CHUNK);
-    b.hist16 = b.dense + n;
-    b.kidx = reinterpret_cast<unsigned short*>(b.hist16 + (hist ? HBINS / 2 : 0));
+    b.cmask = b.ckey + CHUNK;
+    b.hist16 = reinterpret_cast<unsigned*>(b.cmask + n_groups);
+    b.ngroup = reinterpret_cast<int*>(b.hist16 + (hist ? HBINS / 2 : 0));
+    b.kidx = reinterpret_cast<unsigned short*>(b.ngroup + n_groups);
     b.cgroup = reinterpret_cast<unsigned char*>(b.kidx + (size_t)n_groups * max_keep);
     return b;
 }
 
-// ---- predict -------------------------------------------------------------------------------------
-struct PredictParams {
-    const float* pri; int P; const float* loc_all; const float* conf_all; int B, C;
-    float score_thresh, nms_thresh; int max_keep; float vc, vs, img_w, img_h;
-    // final outputs (per-image kernel)
-    int64_t* out_labels; float* out_scores; float* out_boxes; int32_t* out_cand; int32_t* out_count;
-    // per-class lists (fallback path)
-    unsigned long long* list_key;   // [B*units][max_keep]
-    float4* list_box;               // [B*units][max_keep]
-    int* list_count;                // [B*units]
-};
-
-// exp(x_i - max) of one row and their sum in eager torch-CUDA order (persistent warp softmax: one
-// element per lane, lanes = next_pow2(C), butterfly adds over xor offsets lanes/2 .. 1).  CT == 6 is
-// the reference's class count; CT == 0 handles any C <= 32 through `e` in local memory.
-template <int CT>
-__device__ __forceinline__ float row_exps(const float* __restrict__ row, int C, float* e) {
-    if (CT == 6) {
-        const float2 a = ldg2(row), b = ldg2(row + 2), c = ldg2(row + 4);
-        const float mx = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y)), fmaxf(c.x, c.y));
-        e[0] = expf(fsub(a.x, mx)); e[1] = expf(fsub(a.y, mx)); e[2] = expf(fsub(b.x, mx));
-        e[3] = expf(fsub(b.y, mx)); e[4] = expf(fsub(c.x, mx)); e[5] = expf(fsub(c.y, mx));
-        return fadd(fadd(fadd(e[0], e[4]), e[2]), fadd(fadd(e[1], e[5]), e[3]));
-    } else {
-        int lanes = 1;
-        while (lanes < C) lanes <<= 1;
-        float mx = __ldg(row);
-        for (int i = 1; i < C; ++i) mx = fmaxf(mx, __ldg(row + i));
-        float part[32];
-        for (int l = 0; l < 32; ++l) part[l] = 0.0f;
-        for (int i = 0; i < C; ++i) { e[i] = expf(fsub(__ldg(row + i), mx)); part[i] = e[i]; }
-        for (int off = lanes >> 1; off > 0; off >>= 1)
-            for (int l = 0; l < off; ++l) part[l] = fadd(part[l], part[l + off]);
-        return part[0];
-    }
-}
-
-constexpr int PT = 1024;   // threads of the per-image kernel
-constexpr int UT = 512;    // threads of the per-(image, class) fallback and of stand-alone NMS
-
-// One CTA per image, all classes in one score-ordered stream (class-aware unless AGN).
-template <int METRIC, bool AGN, int CT>
-__global__ void __launch_bounds__(PT) predict_image_kernel(const PredictParams prm) {
+// One CTA per image: rank the candidate list and walk it with class-aware greedy NMS.  Keys carry
+// the candidate id, so equal scores are always ordered by ascending id -- the list itself is in
+// arbitrary (atomic) order.
+template <int METRIC, bool AGN>
+__global__ void __launch_bounds__(PT) nms_image_kernel(const PredictParams prm) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ UnitShared us;
     const int tid = threadIdx.x;
     const int b = blockIdx.x;
     const int n_fg = prm.C - 1, P = prm.P;
-    const int n = P * n_fg;
-    const int n_groups = AGN ? 1 : n_fg;
-    const UnitBuffers buf = carve_unit(dyn, n, prm.max_keep, AGN ? 0 : n_groups, true);
+    const int n_groups = AGN ? 0 : n_fg;
+    const UnitBuffers buf = carve_unit(dyn, prm.max_keep, n_groups, true);
+    ListSource src;
+    src.list = prm.cand + (long long)b * P * n_fg;
+    src.n = prm.cand_count[b];
+
     for (int i = tid; i < HBINS / 2; i += PT) buf.hist16[i] = 0u;
     __syncthreads();
-
-    // A score can only pass `s > thresh` if e_k > thr_pre * sum, thr_pre = thresh * (1 - 1e-5): the
-    // margin is two orders of magnitude above the rounding of the product and of the division, so
-    // rows / classes below it skip the IEEE division without changing any decision.
-    const float thr_pre = fmul(prm.score_thresh, 0.99999f);
-    int mine = 0;
-    const float* conf_b = prm.conf_all + (long long)b * P * prm.C;
-    for (int p = tid; p < P; p += PT) {
-        float e[CT > 0 ? CT : 32];
-        const float sum = row_exps<CT>(conf_b + (long long)p * prm.C, prm.C, e);
-        const float gate = fmul(thr_pre, sum);
-        const int nf = CT > 0 ? CT - 1 : n_fg;
-#pragma unroll
-        for (int k = 0; k < nf; ++k) {
-            unsigned key = 0u;
-            if (e[k + 1] > gate) {
-                const float s = fdiv(e[k + 1], sum);       // softmax(conf)[..., 1:]  (SFS:388)
-                if (s > prm.score_thresh) {                // strict (SFS:402)
-                    key = ord_encode(s);
-                    hist_add(buf.hist16, key);
-                    mine += 1;
-                }
-            }
-            buf.dense[p * n_fg + k] = key;
-        }
-    }
-    const int n_cand = block_sum<int>(mine, us.iscratch);
+    if (src.n > CHUNK && src.n < 65536)
+        for (int i = tid; i < src.n; i += PT) hist_add(buf.hist16, (unsigned)(src.list[i] >> 32));
     __syncthreads();
 
     const float* loc_b = prm.loc_all + 4ll * b * P;
     const bool want_atan = METRIC == SSDHOT_METRIC_CIOU;
-    auto fetch = [&](unsigned idx) -> BoxC {
-        const unsigned p = idx / (unsigned)n_fg;
+    auto fetch = [&](unsigned id) -> BoxC {
+        const unsigned p = id / (unsigned)n_fg;
         const float4 box = decode_box(ldg4(loc_b + 4ll * p), ldg4(prm.pri + 4ll * p), prm.vc, prm.vs);
         const float4 px = to_pixel_xyxy(box, prm.img_w, prm.img_h);
         return box_consts(px.x, px.y, px.z, px.w, want_atan);
     };
-    auto group_of = [&](unsigned idx) -> int { return (int)(idx % (unsigned)n_fg); };
+    auto group_of = [&](unsigned id) -> int { return (int)(id % (unsigned)n_fg); };
     const long long o = (long long)b * prm.max_keep;
-    auto emit = [&](int pos, unsigned long long key, unsigned idx, const BoxC& bx) {
-        prm.out_labels[o + pos] = (int64_t)(idx % (unsigned)n_fg);
-        prm.out_scores[o + pos] = ord_decode((unsigned)(key >> 32));
+    auto emit = [&](int pos, unsigned long long key, unsigned id, const BoxC& bx) {
+        prm.out_labels[o + pos] = (int64_t)(id % (unsigned)n_fg);
+        prm.out_scores[o + pos] = __uint_as_float((unsigned)(key >> 32) & 0x7fffffffu);
         reinterpret_cast<float4*>(prm.out_boxes)[o + pos] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
-        if (prm.out_cand) prm.out_cand[o + pos] = (int32_t)idx;
+        if (prm.out_cand) prm.out_cand[o + pos] = (int32_t)id;
     };
-    const int kept_n = nms_unit<METRIC, PT, !AGN, true>(buf, n, n_cand, n_groups, prm.max_keep, prm.nms_thresh, us, fetch, group_of, emit);
+    const int kept_n = nms_unit<METRIC, PT, !AGN, true>(src, buf, src.n, n_groups, prm.max_keep, prm.nms_thresh, us,
+                                                       fetch, group_of, emit);
     if (tid == 0) prm.out_count[b] = kept_n;
-}
-
-// Fallback for class counts whose dense score array does not fit in shared memory: one CTA per
-// (image, class) (or per image when class-agnostic and it fits), lists merged afterwards.
-template <int METRIC>
-__global__ void __launch_bounds__(UT) predict_class_kernel(const PredictParams prm) {
-    extern __shared__ __align__(16) unsigned char dyn[];
-    __shared__ UnitShared us;
-    const int tid = threadIdx.x;
-    const int n_fg = prm.C - 1;
-    const int b = blockIdx.x / n_fg, c = blockIdx.x % n_fg;
-    const int P = prm.P;
-    const UnitBuffers buf = carve_unit(dyn, P, prm.max_keep, 0, false);
-
-    int mine = 0;
-    const float* conf_b = prm.conf_all + (long long)b * P * prm.C;
-    for (int p = tid; p < P; p += UT) {
-        const float* row = conf_b + (long long)p * prm.C;
-        float sum;
-        float ec;
-        if (prm.C <= 32) {
-            float e[32];
-            sum = row_exps<0>(row, prm.C, e);
-            ec = e[c + 1];
-        } else {
-            // C > 32: eager torch-CUDA keeps ceil(C/32) elements per lane, summed in order, then the butterfly
-            float mx = __ldg(row);
-            for (int i = 1; i < prm.C; ++i) mx = fmaxf(mx, __ldg(row + i));
-            float part[32];
-            for (int l = 0; l < 32; ++l) part[l] = 0.0f;
-            for (int i = 0; i < prm.C; ++i) part[i & 31] = fadd(part[i & 31], expf(fsub(__ldg(row + i), mx)));
-            for (int off = 16; off > 0; off >>= 1)
-                for (int l = 0; l < off; ++l) part[l] = fadd(part[l], part[l + off]);
-            sum = part[0];
-            ec = expf(fsub(__ldg(row + c + 1), mx));
-        }
-        const float s = fdiv(ec, sum);
-        const bool on = s > prm.score_thresh;
-        buf.dense[p] = on ? ord_encode(s) : 0u;
-        mine += on ? 1 : 0;
-    }
-    const int n_cand = block_sum<int>(mine, us.iscratch);
-    __syncthreads();
-
-    const float* loc_b = prm.loc_all + 4ll * b * P;
-    const bool want_atan = METRIC == SSDHOT_METRIC_CIOU;
-    auto fetch = [&](unsigned idx) -> BoxC {
-        const float4 box = decode_box(ldg4(loc_b + 4ll * idx), ldg4(prm.pri + 4ll * idx), prm.vc, prm.vs);
-        const float4 px = to_pixel_xyxy(box, prm.img_w, prm.img_h);
-        return box_consts(px.x, px.y, px.z, px.w, want_atan);
-    };
-    auto group_of = [&](unsigned) -> int { return 0; };
-    unsigned long long* out_key = prm.list_key + (long long)blockIdx.x * prm.max_keep;
-    float4* out_box = prm.list_box + (long long)blockIdx.x * prm.max_keep;
-    auto emit = [&](int pos, unsigned long long key, unsigned idx, const BoxC& bx) {
-        // re-key by the flat candidate id prior*(C-1)+class so that lists of different classes merge
-        const unsigned flat = idx * (unsigned)n_fg + (unsigned)c;
-        out_key[pos] = (key & 0xffffffff00000000ull) | (unsigned long long)(0xffffffffu - flat);
-        out_box[pos] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
-    };
-    const int kept_n = nms_unit<METRIC, UT, false, false>(buf, P, n_cand, 1, prm.max_keep, prm.nms_thresh, us, fetch, group_of, emit);
-    if (tid == 0) prm.list_count[blockIdx.x] = kept_n;
-}
-
-// Merge the per-class survivor lists of one image (each already score-descending) and keep the
-// max_keep best (SSD_from_scratch.py:461-474).  Rank of an element = its position in its own list
-// + the number of strictly larger keys in every other list (keys are unique).
-__global__ void __launch_bounds__(256) merge_lists_kernel(const unsigned long long* __restrict__ list_key,
-                                                          const float4* __restrict__ list_box,
-                                                          const int* __restrict__ list_count, int units, int max_keep, int n_fg,
-                                                          int64_t* __restrict__ out_labels, float* __restrict__ out_scores,
-                                                          float* __restrict__ out_boxes, int32_t* __restrict__ out_cand,
-                                                          int32_t* __restrict__ out_count) {
-    const int b = blockIdx.x;
-    const unsigned long long* keys = list_key + (long long)b * units * max_keep;
-    const float4* boxes = list_box + (long long)b * units * max_keep;
-    const int* counts = list_count + (long long)b * units;
-    int total = 0;
-    for (int u = 0; u < units; ++u) total += counts[u];
-    for (int e = threadIdx.x; e < units * max_keep; e += blockDim.x) {
-        const int u = e / max_keep, i = e % max_keep;
-        if (i >= counts[u]) continue;
-        const unsigned long long key = keys[(long long)u * max_keep + i];
-        int rank = i;
-        for (int v = 0; v < units; ++v) {
-            if (v == u) continue;
-            int lo = 0, hi = counts[v];          // first position whose key is < key
-            const unsigned long long* kv = keys + (long long)v * max_keep;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (kv[mid] > key) lo = mid + 1; else hi = mid;
-            }
-            rank += lo;
-        }
-        if (rank < max_keep) {
-            const long long o = (long long)b * max_keep + rank;
-            const unsigned flat = 0xffffffffu - (unsigned)(key & 0xffffffffull);
-            out_labels[o] = (int64_t)(flat % (unsigned)n_fg);
-            out_scores[o] = ord_decode((unsigned)(key >> 32));
-            reinterpret_cast<float4*>(out_boxes)[o] = boxes[(long long)u * max_keep + i];
-            if (out_cand) out_cand[o] = (int32_t)flat;
-        }
-    }
-    if (threadIdx.x == 0) out_count[b] = total < max_keep ? total : max_keep;
 }
 
 // ---- stand-alone NMS -------------------------------------------------------------------------------
@@ -621,28 +615,29 @@ __global__ void __launch_bounds__(UT) nms_sets_kernel(const float* __restrict__ 
     const int tid = threadIdx.x;
     const int begin = set_offsets[blockIdx.x];
     const int n = set_offsets[blockIdx.x + 1] - begin;
-    UnitBuffers buf;
+    UnitBuffers buf = {};
     buf.cbox = reinterpret_cast<BoxC*>(dyn);
     buf.ckey = reinterpret_cast<unsigned long long*>(buf.cbox + CHUNK);
-    buf.dense = reinterpret_cast<unsigned*>(buf.ckey + CHUNK);
-    buf.cgroup = reinterpret_cast<unsigned char*>(buf.dense + n_max);
+    DenseSource src;
+    src.keys = reinterpret_cast<unsigned*>(buf.ckey + CHUNK);
+    src.n = n;
+    buf.cgroup = reinterpret_cast<unsigned char*>(src.keys + n_max);
     buf.kept = kept_all + begin;            // survivors of a stand-alone call are unbounded: global memory
-    buf.kidx = nullptr; buf.hist16 = nullptr;
     for (int i = tid; i < n; i += UT) {
         const unsigned k = ord_encode(__ldg(scores + begin + i));
-        buf.dense[i] = k == 0u ? 1u : k;
+        src.keys[i] = k == 0u ? 1u : k;
     }
     __syncthreads();
     const bool want_atan = METRIC == SSDHOT_METRIC_CIOU;
-    auto fetch = [&](unsigned idx) -> BoxC {
-        const float4 bx = ldg4(boxes + 4ll * (begin + (long long)idx));
+    auto fetch = [&](unsigned id) -> BoxC {
+        const float4 bx = ldg4(boxes + 4ll * (begin + (long long)id));
         return box_consts(bx.x, bx.y, bx.z, bx.w, want_atan);
     };
     auto group_of = [&](unsigned) -> int { return 0; };
     int64_t* out = keep + begin;
-    auto emit = [&](int pos, unsigned long long, unsigned idx, const BoxC&) { out[pos] = (int64_t)idx; };
+    auto emit = [&](int pos, unsigned long long, unsigned id, const BoxC&) { out[pos] = (int64_t)id; };
     const int cap = (max_keep > 0 && max_keep < n) ? max_keep : n;
-    const int kept_n = nms_unit<METRIC, UT, false, false>(buf, n, n, 1, cap, thr, us, fetch, group_of, emit);
+    const int kept_n = nms_unit<METRIC, UT, false, false>(src, buf, n, 0, cap, thr, us, fetch, group_of, emit);
     if (tid == 0) keep_count[blockIdx.x] = kept_n;
 }
 
@@ -651,6 +646,11 @@ __global__ void decode_kernel(const float* __restrict__ loc, const float* __rest
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
     reinterpret_cast<float4*>(out)[i] = decode_box(ldg4(loc + 4ll * i), ldg4(pri + 4ll * i), vc, vs);
+}
+
+__global__ void zero_counts_kernel(int* __restrict__ counts, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) counts[i] = 0;
 }
 
 constexpr size_t kMaxDynSmem = 227 * 1024 - sizeof(UnitShared) - 1024;
@@ -674,24 +674,10 @@ static int set_smem(K kern, size_t bytes) {
 }
 
 template <int METRIC, bool AGN>
-static int launch_predict_image(const PredictParams& prm, size_t dyn, cudaStream_t stream) {
+static int launch_nms_image(const PredictParams& prm, size_t dyn, cudaStream_t stream) {
     int rc;
-    if (prm.C == 6) {
-        if ((rc = set_smem(predict_image_kernel<METRIC, AGN, 6>, dyn))) return rc;
-        predict_image_kernel<METRIC, AGN, 6><<<prm.B, PT, dyn, stream>>>(prm);
-    } else {
-        if ((rc = set_smem(predict_image_kernel<METRIC, AGN, 0>, dyn))) return rc;
-        predict_image_kernel<METRIC, AGN, 0><<<prm.B, PT, dyn, stream>>>(prm);
-    }
-    SSDHOT_CHECK_LAUNCH();
-    return SSDHOT_OK;
-}
-
-template <int METRIC>
-static int launch_predict_class(const PredictParams& prm, size_t dyn, cudaStream_t stream) {
-    int rc;
-    if ((rc = set_smem(predict_class_kernel<METRIC>, dyn))) return rc;
-    predict_class_kernel<METRIC><<<prm.B * (prm.C - 1), UT, dyn, stream>>>(prm);
+    if ((rc = set_smem(nms_image_kernel<METRIC, AGN>, dyn))) return rc;
+    nms_image_kernel<METRIC, AGN><<<prm.B, PT, dyn, stream>>>(prm);
     SSDHOT_CHECK_LAUNCH();
     return SSDHOT_OK;
 }
@@ -748,10 +734,12 @@ extern "C" int ssdhot_nms(const float* boxes, const float* scores, const int32_t
     return SSDHOT_OK;
 }
 
-extern "C" unsigned long long ssdhot_predict_workspace_bytes(int B, int C, int max_per_img) {
-    if (B <= 0 || C < 2 || max_per_img <= 0) return 64ull;
-    const unsigned long long lists = (unsigned long long)B * (C - 1);
-    return lists * max_per_img * (8ull + 16ull) + lists * 4ull + 256ull;
+// workspace layout: cand_count [B] int32 (padded to 16) | cand [B][P*(C-1)] uint64
+static size_t pw_cand_off(int B) { return ((size_t)B * 4 + 15) & ~(size_t)15; }
+
+extern "C" unsigned long long ssdhot_predict_workspace_bytes(int B, int P, int C) {
+    if (B <= 0 || P <= 0 || C < 2) return 64ull;
+    return (unsigned long long)(pw_cand_off(B) + (size_t)B * P * (C - 1) * 8 + 64);
 }
 
 extern "C" int ssdhot_predict(const float* priors_cxcywh, int P, const float* loc_all, const float* conf_all,
@@ -762,46 +750,35 @@ extern "C" int ssdhot_predict(const float* priors_cxcywh, int P, const float* lo
                               int32_t* out_count, void* work, ssdhot_stream_t stream) {
     if (!priors_cxcywh || !loc_all || !conf_all || !out_labels || !out_scores || !out_boxes || !out_count || !work)
         return SSDHOT_ERR_NULL;
-    if (P <= 0 || B <= 0 || C < 2 || C > SSDHOT_MAX_CLASSES || max_per_img <= 0) return SSDHOT_ERR_SHAPE;
+    if (P <= 0 || B <= 0 || C < 2 || C > SSDHOT_MAX_CLASSES || max_per_img <= 0 || max_per_img > 65535) return SSDHOT_ERR_SHAPE;
+    if ((long long)P * (C - 1) > 0x7fffffffll) return SSDHOT_ERR_SHAPE;
     // same validation as SSD_from_scratch.py:369-373
     if (!(score_thresh >= 0.0f && score_thresh < 1.0f) || !(nms_thresh > 0.0f && nms_thresh < 1.0f)) return SSDHOT_ERR_VALUE;
     if (metric != SSDHOT_METRIC_DIOU && metric != SSDHOT_METRIC_CIOU && metric != SSDHOT_METRIC_IOU) return SSDHOT_ERR_VALUE;
     if (!al16(priors_cxcywh) || !al16(loc_all) || !al16(out_boxes) || !al16(work) ||
         (reinterpret_cast<uintptr_t>(conf_all) & 7u)) return SSDHOT_ERR_ALIGN;
+    const size_t dyn = unit_smem_bytes(max_per_img, class_agnostic ? 0 : C - 1, true);
+    if (dyn > kMaxDynSmem) return SSDHOT_ERR_SHAPE;
     PredictParams prm = {};
     prm.pri = priors_cxcywh; prm.P = P; prm.loc_all = loc_all; prm.conf_all = conf_all; prm.B = B; prm.C = C;
     prm.score_thresh = score_thresh; prm.nms_thresh = nms_thresh; prm.max_keep = max_per_img;
     prm.vc = var_center; prm.vs = var_size; prm.img_w = img_w; prm.img_h = img_h;
     prm.out_labels = out_labels; prm.out_scores = out_scores; prm.out_boxes = out_boxes; prm.out_cand = out_cand;
     prm.out_count = out_count;
-    cudaStream_t s = (cudaStream_t)stream;
-    int rc;
-    // preferred: one CTA per image, all classes in one score-ordered stream
-    const size_t dyn_image = unit_smem_bytes((long long)P * (C - 1), max_per_img, class_agnostic ? 0 : C - 1, true);
-    if (dyn_image <= kMaxDynSmem && C <= 32 && max_per_img < 65536) {
-#define SSDHOT_DISPATCH(M) rc = class_agnostic ? launch_predict_image<M, true>(prm, dyn_image, s) : launch_predict_image<M, false>(prm, dyn_image, s)
-        if (metric == SSDHOT_METRIC_DIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_DIOU); }
-        else if (metric == SSDHOT_METRIC_CIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_CIOU); }
-        else { SSDHOT_DISPATCH(SSDHOT_METRIC_IOU); }
-#undef SSDHOT_DISPATCH
-        return rc;
-    }
-    // fallback (many classes): one CTA per (image, class), then a merge; class-agnostic NMS over a
-    // candidate set that does not fit in shared memory is not supported
-    if (class_agnostic) return SSDHOT_ERR_SHAPE;
-    const int units = C - 1;
-    const long long lists = (long long)B * units;
     unsigned char* w = reinterpret_cast<unsigned char*>(work);
-    prm.list_box = reinterpret_cast<float4*>(w); w += (size_t)lists * max_per_img * 16;
-    prm.list_key = reinterpret_cast<unsigned long long*>(w); w += (size_t)lists * max_per_img * 8;
-    prm.list_count = reinterpret_cast<int*>(w);
-    const size_t dyn = unit_smem_bytes(P, max_per_img, 0, false);
-    if (metric == SSDHOT_METRIC_DIOU) rc = launch_predict_class<SSDHOT_METRIC_DIOU>(prm, dyn, s);
-    else if (metric == SSDHOT_METRIC_CIOU) rc = launch_predict_class<SSDHOT_METRIC_CIOU>(prm, dyn, s);
-    else rc = launch_predict_class<SSDHOT_METRIC_IOU>(prm, dyn, s);
-    if (rc) return rc;
-    merge_lists_kernel<<<B, 256, 0, s>>>(prm.list_key, prm.list_box, prm.list_count, units, max_per_img, C - 1,
-                                         out_labels, out_scores, out_boxes, out_cand, out_count);
+    prm.cand_count = reinterpret_cast<int*>(w);
+    prm.cand = reinterpret_cast<unsigned long long*>(w + pw_cand_off(B));
+    cudaStream_t s = (cudaStream_t)stream;
+    zero_counts_kernel<<<(B + 255) / 256, 256, 0, s>>>(prm.cand_count, B);
     SSDHOT_CHECK_LAUNCH();
-    return SSDHOT_OK;
+    if (C == 6) score_kernel<6><<<B * SCS, ST, 0, s>>>(prm);
+    else score_kernel<0><<<B * SCS, ST, 0, s>>>(prm);
+    SSDHOT_CHECK_LAUNCH();
+    int rc;
+#define SSDHOT_DISPATCH(M) rc = class_agnostic ? launch_nms_image<M, true>(prm, dyn, s) : launch_nms_image<M, false>(prm, dyn, s)
+    if (metric == SSDHOT_METRIC_DIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_DIOU); }
+    else if (metric == SSDHOT_METRIC_CIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_CIOU); }
+    else { SSDHOT_DISPATCH(SSDHOT_METRIC_IOU); }
+#undef SSDHOT_DISPATCH
+    return rc;
 }

@@ -338,7 +338,7 @@ def predict_padded(model, loc_all: torch.Tensor, conf_all: torch.Tensor, score_t
     boxes = torch.empty((B, max_per_img, 4), dtype=torch.float32, device=dev)
     cand = torch.empty((B, max_per_img), dtype=torch.int32, device=dev) if want_cand else None
     count = torch.empty((B,), dtype=torch.int32, device=dev)
-    work = _workspace("predict", dev, _lib.lib().ssdhot_predict_workspace_bytes(B, C, max_per_img))
+    work = _workspace("predict", dev, _lib.lib().ssdhot_predict_workspace_bytes(B, P, C))
     with torch.cuda.device(dev):
         rc = _lib.lib().ssdhot_predict(priors.priors.data_ptr(), P, loc.data_ptr(), conf.data_ptr(), B, C,
                                        float(score_thresh), float(nms_thresh), int(max_per_img), 1 if class_agnostic else 0,

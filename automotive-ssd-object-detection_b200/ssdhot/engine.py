@@ -33,7 +33,7 @@ class HotPathStep:
         self.sums = torch.zeros((3,), dtype=torch.float64, device=dev)
         self.max_gt = int(max_gt)
         self.loss_work = torch.empty((int(L.ssdhot_loss_workspace_bytes(self.B, priors.P, self.max_gt)),), dtype=torch.uint8, device=dev)
-        self.pred_work = torch.empty((int(L.ssdhot_predict_workspace_bytes(self.B, self.C, self.max_per_img)),),
+        self.pred_work = torch.empty((int(L.ssdhot_predict_workspace_bytes(self.B, priors.P, self.C)),),
                                      dtype=torch.uint8, device=dev)
         m = self.max_per_img
         self.labels = torch.zeros((self.B, m), dtype=torch.int64, device=dev)

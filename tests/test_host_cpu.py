@@ -57,7 +57,7 @@ def test_validation_happens_before_launch_no_gpu_needed():
                             16, 16, 16, None, 16, 16, None) == -3          # nms_thresh must be > 0
     assert L.ssdhot_predict(16, 8732, 16, 16, 1, 1, 0.1, 0.5, 200, 0, 0, 0.1, 0.2, 300.0, 300.0,
                             16, 16, 16, None, 16, 16, None) == -2          # C >= 2
-    assert L.ssdhot_loss_workspace_bytes(256, 8732, 20) > 0 and L.ssdhot_match_workspace_bytes(256, 20) > 0 and L.ssdhot_predict_workspace_bytes(256, 6, 200) > 0
+    assert L.ssdhot_loss_workspace_bytes(256, 8732, 20) > 0 and L.ssdhot_match_workspace_bytes(256, 20) > 0 and L.ssdhot_predict_workspace_bytes(256, 8732, 6) > 0
     assert ssdhot.launch_count() == 0
 
 
