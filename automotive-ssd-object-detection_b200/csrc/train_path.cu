@@ -414,6 +414,118 @@ __device__ __forceinline__ int load_target(const TrainParams& prm, long long row
 
 constexpr unsigned kNotNegative = 0xffffffffu;   // key of a positive prior (never a float >= 0 bit pattern)
 
+// ---------------------------------------------------------------------------------------------
+// Exact hard-negative selection of one image, shared by both loss kernels.  `key_at(p)` is the CE
+// bit pattern of prior p if it is a negative (CE >= 0: bit order = value order) and kNotNegative
+// otherwise; ls.hist must already hold the histogram of key >> 24 over the negatives (the first
+// radix pass rides along with the pass that produced the keys).  `tgt_of(p, mg)` returns the
+// target class of a positive (and its matched box in mg) or -1.  Returns this thread's share of
+// the sum of the selected negatives' CE; writes sel_cls / matched16 when they are requested.
+// Every thread of the CTA must call it.
+// ---------------------------------------------------------------------------------------------
+template <int NT, typename KeyAt, typename TgtOf>
+__device__ __forceinline__ double mined_exact_tail(const TrainParams& prm, int b, int P, int n_pos_img, LossShared& ls,
+                                                   KeyAt key_at, TgtOf tgt_of) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double acc = 0.0;
+    // ---- hard-negative budget (SSD_trainer.py:585-596) --------------------------------------
+    const long long n_neg = (long long)P - n_pos_img;
+    long long want = (n_pos_img == 0) ? (long long)prm.ratio : (long long)(prm.ratio * (double)n_pos_img);
+    if (want < 0) want = 0;
+    const long long kk = want < n_neg ? want : n_neg;
+    unsigned thr_key = 0u;        // selected negatives: key > thr_key, plus `need` of those == thr_key
+    unsigned need = 0u, n_eq = 0u;
+    const bool take_all = (kk >= n_neg);
+    if (kk > 0 && !take_all) {
+        // 4-pass MSD radix select of the kk-th largest key
+        unsigned prefix = 0u, remaining = (unsigned)kk;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            if (pass > 0) {
+                for (int i = tid; i < 256; i += NT) ls.hist[i] = 0u;
+                __syncthreads();
+                const unsigned himask = 0xffffffffu << (shift + 8);
+                for (int p = tid; p < P; p += NT) {
+                    const unsigned key = key_at(p);
+                    if (key != kNotNegative && ((key & himask) == prefix)) atomicAdd(&ls.hist[(key >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+            }
+            if (tid < 32) {
+                // bins 255..0: lane l owns bins [255-8l-7 .. 255-8l]; find where the suffix count reaches `remaining`
+                unsigned mine = 0u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mine += ls.hist[255 - (tid * 8 + j)];
+                unsigned incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned y = __shfl_up_sync(FULL, incl, o);
+                    if (tid >= o) incl += y;
+                }
+                const unsigned excl = incl - mine;
+                if (excl < remaining && remaining <= incl) {
+                    unsigned run = excl;
+                    for (int j = 0; j < 8; ++j) {
+                        const int bin = 255 - (tid * 8 + j);
+                        const unsigned c = ls.hist[bin];
+                        if (run + c >= remaining) { ls.sel_digit = (unsigned)bin; ls.sel_need = remaining - run; ls.sel_eq = c; break; }
+                        run += c;
+                    }
+                }
+            }
+            __syncthreads();
+            prefix |= ls.sel_digit << shift;
+            remaining = ls.sel_need;
+            n_eq = ls.sel_eq;
+            __syncthreads();
+        }
+        thr_key = prefix;
+        need = remaining;
+    }
+
+    // ---- sums (and the backward selection) --------------------------------------------------
+    if (kk > 0) {
+        for (int p = tid; p < P; p += NT) {
+            const unsigned key = key_at(p);
+            if (key != kNotNegative && (take_all || key > thr_key)) acc += (double)__uint_as_float(key);
+        }
+    }
+    if (prm.sel_cls) {
+        // of the negatives equal to the threshold value the first `need` in prior order are taken
+        const bool all_ties = take_all || kk == 0 || need == n_eq;
+        int before = 0;
+        for (int base = 0; base < P; base += NT) {
+            const int p = base + tid;
+            const unsigned key = p < P ? key_at(p) : kNotNegative;
+            const bool tie = kk > 0 && !take_all && key != kNotNegative && key == thr_key;
+            int rank_tie = 0;
+            if (!all_ties) {
+                const unsigned bal = __ballot_sync(FULL, tie);
+                __syncthreads();
+                if (lane == 0) ls.iscratch[warp] = __popc(bal);
+                __syncthreads();
+                int slot_total = 0;
+                for (int w = 0; w < NT / 32; ++w) { if (w < warp) rank_tie += ls.iscratch[w]; slot_total += ls.iscratch[w]; }
+                rank_tie += before + __popc(bal & ((1u << lane) - 1u));
+                before += slot_total;
+            }
+            if (p >= P) continue;
+            const long long row = (long long)b * P + p;
+            int mg;
+            const int tgt = tgt_of(p, mg);
+            int8_t sel = -1;
+            if (tgt >= 0) sel = (int8_t)tgt;
+            else if (kk > 0 && (take_all || key > thr_key || (tie && (all_ties || (unsigned)rank_tie < need)))) sel = 0;
+            prm.sel_cls[row] = sel;
+            if (prm.matched16) prm.matched16[row] = (int16_t)mg;
+        }
+    }
+    // the `need` threshold-valued negatives are counted once
+    if (tid == 0 && kk > 0 && !take_all) acc += (double)need * (double)__uint_as_float(thr_key);
+
+    return acc;
+}
+
 template <int CT, bool FROM_TARGETS>
 __global__ void __launch_bounds__(LT, 2) loss_image_kernel(const TrainParams prm) {
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -458,7 +570,7 @@ __global__ void __launch_bounds__(LT, 2) loss_image_kernel(const TrainParams prm
                 }
             }
         } else {
-            const unsigned key = __float_as_uint(ce);
+            const unsigned key = __float_as_uint(ce) & 0x7fffffffu;      // -0.0 (sum == 1, target is the max) counts as 0
             keys[p] = key;
             atomicAdd(&ls.hist[key >> 24], 1u);             // first radix pass rides along
         }
@@ -466,103 +578,586 @@ __global__ void __launch_bounds__(LT, 2) loss_image_kernel(const TrainParams prm
     const int n_pos_img = block_sum<int>(my_pos, ls.iscratch);      // (two barriers: keys and hist are complete)
     if (tid == 0 && prm.n_pos) prm.n_pos[b] = n_pos_img;
 
-    // ---- hard-negative budget (SSD_trainer.py:585-596) --------------------------------------
+    acc_ce += mined_exact_tail<LT>(prm, b, P, n_pos_img, ls, [&](int p) { return keys[p]; },
+                                   [&](int p, int& mg) { return load_target<FROM_TARGETS>(prm, (long long)b * P + p, g_begin, mg); });
+
+    const double s_loc = block_sum<double>(acc_loc, ls.dscratch);
+    const double s_ce = block_sum<double>(acc_ce, ls.dscratch);
+    if (tid == 0) {
+        prm.img_part[2ll * b + 0] = s_loc;
+        prm.img_part[2ll * b + 1] = s_ce;
+    }
+}
+
+// =============================================================================================
+// train_image_kernel -- the SSD300 fast path: sparse matching + mined loss, ONE CTA PER IMAGE
+// =============================================================================================
+// Matching is box-centric.  The priors of SSD300 sit on six regular grids (SSD_from_scratch.py:
+// 289-323), so for a ground-truth box and one (level, shape) combination the priors whose IoU can
+// reach lim (the same bound the pruned sweep of match_kernel uses) form a small rectangle of
+// cells: IoU >= lim needs  inter >= max(lim * max(a_g, a_p), lim/(1+lim) * (a_g + a_p)),
+// inter <= w_ov * min(h_p, h_g) and w_ov <= (w_p + w_g)/2 - |cx_p - cx_g|  (the clamped prior is a
+// subset of the un-clamped one, and a_p >= w_p h_p / 4 because its centre lies inside the image).
+// Those ~400 cells per box (instead of 8732 priors) pass the same cheap IoU gate as before; the
+// ~35 survivors get the exact CIoU and update a packed (CIoU, ~box) maximum per prior in shared
+// memory plus the packed (CIoU, ~prior) maximum per box.  Boxes the rectangles cannot handle (not
+// finite, empty, or whose best CIoU is not positive) are swept densely, exactly like the refill of
+// match_kernel.  Results are bit-identical to the exact-everywhere sweep for every positive prior.
+//
+// The loss then streams the image's logits once.  Hard-negative mining only needs the k largest
+// cross-entropies of ~8.7k negatives, so the stream evaluates CE with ex2.approx / lg2.approx
+// (|error| <= 1e-5 + 1e-6 CE, see approx_ce6), a two-level histogram (4096 x 512 bins) brackets the
+// k-th largest approximate value in a 1024-ulp sub-bin, and only the negatives above that bracket
+// and the handful inside a +-3-error band around it are re-evaluated with the exact eager-CUDA
+// arithmetic: every negative above the band is certainly among the k hardest, every one below it
+// certainly not, and the band members are ranked exactly (ties: lower prior index first).  Images
+// where that does not apply (budget >= #negatives, an over-full band, non-finite bracket) take the
+// exact path of loss_image_kernel (mined_exact_tail).  The sums are therefore those of the exact
+// arithmetic in every case.
+constexpr int FT = 768;                      // threads; 2 CTAs per SM
+constexpr int FAST_MAX_GT = 64;
+constexpr int GT_ROUND = 32;                 // boxes enumerated per round
+constexpr int NSEG = GT_ROUND * 32;          // (box, level-shape) segments per round
+constexpr int PAIR_CAP = 2048;               // gate survivors staged for the exact pass (rest: inline)
+constexpr int POS_CAP = 2048;
+constexpr int SEL_CAP = 2048;
+constexpr int BAND_CAP = 1024;
+constexpr unsigned kOrdTwo = 0xC0000000u;    // ord_encode(2.0f): the forced-match value (SFS:747)
+constexpr int FUSED_SCRATCH = 20480;
+
+struct FusedStatic {
+    float4 gt_a[FAST_MAX_GT];                // x1 y1 x2 y2 (normalised)
+    float4 gt_b[FAST_MAX_GT];                // area xc yc atan
+    unsigned long long col[FAST_MAX_GT];     // (ord(ciou) << 32 | ~prior) best prior per box
+    float lim[FAST_MAX_GT];
+    int label[FAST_MAX_GT];
+    int champ[FAST_MAX_GT];
+    unsigned char kind[FAST_MAX_GT];         // 0 = rectangles, 1 = dense sweep, 2 = all-NaN column
+    LossShared ls;
+    int first_nan, n_dense, n_pair, n_poslist, n_sel, n_band;
+    unsigned r_bin, r_above;
+};
+
+__host__ __device__ inline size_t fused_smem_bytes(int P) {
+    return (size_t)P * 8 + FUSED_SCRATCH + (size_t)POS_CAP * 2 + (size_t)SEL_CAP * 2;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// Approximate -log_softmax(row)[0] of a 6-logit row.  d_i = x_i - max is the exact fp32 difference
+// the reference forms; each ex2.approx term is within 2.6e-7 absolute, the sum s in [1, 6] within
+// 4e-6 relative, ln(s) within 5e-6, so |result - exact CE| <= 6e-6 + 2e-7 CE  (bound used: 1e-5 + 1e-6 CE).
+__device__ __forceinline__ float approx_ce6(float x0, float x1, float x2, float x3, float x4, float x5) {
+    const float mx = fmaxf(fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)), fmaxf(x4, x5));
+    const float k = 1.4426950408889634f;
+    const float d0 = x0 - mx;
+    const float s = ((ex2_approx(d0 * k) + ex2_approx((x1 - mx) * k)) + (ex2_approx((x2 - mx) * k) + ex2_approx((x3 - mx) * k))) +
+                    (ex2_approx((x4 - mx) * k) + ex2_approx((x5 - mx) * k));
+    return fmaxf(lg2_approx(s) * 0.6931471805599453f - d0, 0.0f);
+}
+__device__ __forceinline__ float ce_error_bound(float ce) { return 1e-5f + 1e-6f * ce; }
+
+// exact CE of one row for target class cls, in eager torch-CUDA order (as loss_image_kernel)
+__device__ __forceinline__ float exact_ce6(const float* __restrict__ row, int cls) {
+    float mx, lg;
+    row_lse<6>(row, 6, mx, lg);
+    return -fsub(fsub(__ldg(row + cls), mx), lg);
+}
+
+// From the top bin downwards, find the bin in which the running count reaches k (1 <= k <= total).
+// count(bin) reads a bin; every thread of the CTA must call it; two barriers inside.
+template <int NT, int NBINS, typename CountFn>
+__device__ __forceinline__ void find_kth_from_top(CountFn count, unsigned k, FusedStatic& fs, unsigned& bin_out, unsigned& above_out) {
+    constexpr int BPT = (NBINS + NT - 1) / NT;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned c[BPT];
+    unsigned mine = 0u;
+#pragma unroll
+    for (int j = 0; j < BPT; ++j) {
+        const int bin = NBINS - 1 - (tid * BPT + j);
+        c[j] = bin >= 0 ? count(bin) : 0u;
+        mine += c[j];
+    }
+    unsigned incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += y;
+    }
+    __syncthreads();
+    if (lane == 31) fs.ls.iscratch[warp] = (int)incl;
+    __syncthreads();
+    unsigned excl = incl - mine;
+    for (int w = 0; w < warp; ++w) excl += (unsigned)fs.ls.iscratch[w];
+    if (excl < k && k <= excl + mine) {
+        unsigned run = excl;
+#pragma unroll
+        for (int j = 0; j < BPT; ++j) {
+            if (run < k && run + c[j] >= k) { fs.r_bin = (unsigned)(NBINS - 1 - (tid * BPT + j)); fs.r_above = run; }
+            run += c[j];
+        }
+    }
+    __syncthreads();
+    bin_out = fs.r_bin;
+    above_out = fs.r_above;
+}
+
+template <bool LOSS>
+__global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams prm) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ FusedStatic fs;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = prm.P;
+    unsigned long long* table = reinterpret_cast<unsigned long long*>(dyn);        // [P] (ord(ciou) << 32 | ~box); later (0, CE bits)
+    unsigned char* scratch = dyn + (size_t)P * 8;
+    uint16_t* pos_list = reinterpret_cast<uint16_t*>(scratch + FUSED_SCRATCH);
+    uint16_t* sel_list = pos_list + POS_CAP;
+    // matching view of the scratch
+    int* seg_start = reinterpret_cast<int*>(scratch);                              // [NSEG + 1] (+ pad to 4112 B)
+    unsigned* seg_info = reinterpret_cast<unsigned*>(scratch + 4112);              // [NSEG] i0 | j0<<6 | ni<<12 | side<<18 | shapes<<24
+    uint16_t* seg_base = reinterpret_cast<uint16_t*>(scratch + 4112 + 4096);       // [NSEG] first prior of the (level, shape)
+    unsigned* pair_list = reinterpret_cast<unsigned*>(scratch + 4112 + 4096 + 2048);   // [PAIR_CAP] prior | box << 16
+    // mining view of the scratch
+    unsigned* hist16 = reinterpret_cast<unsigned*>(scratch);                       // [2048] 4096 bins x 16 bit
+    unsigned* hist2 = hist16 + 2048;                                               // [512]
+    unsigned* band_v = hist2 + 512;                                                // [BAND_CAP] exact CE bits
+    uint16_t* band_p = reinterpret_cast<uint16_t*>(band_v + BAND_CAP);             // [BAND_CAP]
+
+    const int g_begin = prm.gt_offsets[b];
+    int G = prm.gt_offsets[b + 1] - g_begin;
+    if (G > prm.max_gt) {
+        if (tid == 0 && prm.flags) atomicOr(prm.flags, 1);
+        G = prm.max_gt;
+    }
+
+    // ---- 0. clear ------------------------------------------------------------------------------
+    if (tid == 0) { fs.first_nan = INT_MAX; fs.n_dense = 0; fs.n_poslist = 0; fs.n_sel = 0; fs.n_band = 0; }
+    __syncthreads();
+    {
+        ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
+        for (int i = tid; i < P / 2; i += FT) t2[i] = make_ulonglong2(0ull, 0ull);
+        if ((P & 1) && tid == 0) table[P - 1] = 0ull;
+    }
+    const float thresh = prm.thresh;
+
+    // ---- 1. matching, GT_ROUND boxes per round -----------------------------------------------------
+    for (int g0 = 0; g0 < G; g0 += GT_ROUND) {
+        const int gn = min(GT_ROUND, G - g0);
+        if (tid == 0) fs.n_pair = 0;
+        // 1a. one warp per box: constants, seed bound, candidate rectangles of the 30 (level, shape) combos
+        for (int gl = warp; gl < GT_ROUND; gl += FT / 32) {
+            int n = 0, base = 0;
+            unsigned info = 0u;
+            if (gl < gn) {
+                const int g = g0 + gl;
+                const float4 px = ldg4(prm.gt_boxes + 4ll * (g_begin + g));
+                const BoxC c = box_consts(fdiv(px.x, prm.norm_w), fdiv(px.y, prm.norm_h), fdiv(px.z, prm.norm_w), fdiv(px.w, prm.norm_h), true);
+                const float gw = fsub(c.x2, c.x1), gh = fsub(c.y2, c.y1);
+                int kind = 0;
+                if (c.at != c.at) kind = 2;
+                else if (!(gw > 0.0f && gh > 0.0f) || !(fabsf(c.x1) < 1e30f && fabsf(c.y1) < 1e30f && fabsf(c.x2) < 1e30f && fabsf(c.y2) < 1e30f)) kind = 1;
+                float lim = 1e-30f;
+                if (kind == 0) {
+                    const int lv = kSeedLevel[lane], side = kLevelSide[lv], shapes = kLevelShapes[lv], off = kLevelOffset[lv];
+                    const int shp = kSeedShape[lane];
+                    int ix = (int)floorf(c.xc * (float)side), iy = (int)floorf(c.yc * (float)side);
+                    ix = min(max(ix, 0), side - 1);
+                    iy = min(max(iy, 0), side - 1);
+                    const int ps = off + (iy * side + ix) * shapes + shp;
+                    const float v = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, ps), c);
+                    const float cb0 = ord_decode(__reduce_max_sync(FULL, ord_encode(v)));
+                    if (cb0 > 0.0f) lim = fmaxf(fmul(kPruneSlack, fminf(cb0, thresh)), 1e-30f);
+                    if (lane < 30) {
+                        const float4 sh = ldg4(prm.pri + 4ll * (off + shp));           // (w, h) of this level-shape
+                        const float w = sh.z, h = sh.w;
+                        const float l2 = 0.99f * lim;
+                        const float mw = fminf(w, gw), mh = fminf(h, gh);
+                        const float ak4 = 0.25f * w * h;
+                        const float req = fmaxf(l2 * fmaxf(c.area, ak4), l2 / (1.0f + l2) * (c.area + ak4));
+                        if (!(mw * mh < req)) {
+                            const float rx = 0.5f * (w + gw) - req / mh, ry = 0.5f * (h + gh) - req / mw;
+                            if (rx >= 0.0f && ry >= 0.0f) {
+                                const float fsd = (float)side;
+                                const int i0 = max(0, (int)ceilf(fmaxf((c.xc - rx) * fsd - 0.51f, -1.0f)));
+                                const int i1 = min(side - 1, (int)floorf(fminf((c.xc + rx) * fsd - 0.49f, fsd)));
+                                const int j0 = max(0, (int)ceilf(fmaxf((c.yc - ry) * fsd - 0.51f, -1.0f)));
+                                const int j1 = min(side - 1, (int)floorf(fminf((c.yc + ry) * fsd - 0.49f, fsd)));
+                                if (i1 >= i0 && j1 >= j0) {
+                                    const int ni = i1 - i0 + 1;
+                                    n = ni * (j1 - j0 + 1);
+                                    info = (unsigned)i0 | ((unsigned)j0 << 6) | ((unsigned)ni << 12) | ((unsigned)side << 18) | ((unsigned)shapes << 24);
+                                    base = off + shp;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (lane == 0) {
+                    fs.gt_a[g] = make_float4(c.x1, c.y1, c.x2, c.y2);
+                    fs.gt_b[g] = make_float4(c.area, c.xc, c.yc, c.at);
+                    fs.lim[g] = lim;
+                    fs.label[g] = (int)prm.gt_labels[g_begin + g];
+                    fs.col[g] = 0ull;
+                    fs.champ[g] = 0;
+                    fs.kind[g] = (unsigned char)kind;
+                    if (kind == 2) atomicMin(&fs.first_nan, g);
+                    if (kind == 1) atomicAdd(&fs.n_dense, 1);
+                }
+            }
+            seg_start[gl * 32 + lane] = n;
+            seg_info[gl * 32 + lane] = info;
+            seg_base[gl * 32 + lane] = (uint16_t)base;
+        }
+        __syncthreads();
+        // 1b. exclusive scan of the NSEG segment sizes (two per thread, threads 0..511)
+        {
+            int a = 0, c2 = 0;
+            if (tid < NSEG / 2) { a = seg_start[2 * tid]; c2 = seg_start[2 * tid + 1]; }
+            int incl = a + c2;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += y;
+            }
+            if (lane == 31) fs.ls.iscratch[warp] = incl;
+            __syncthreads();
+            int excl = incl - (a + c2);
+            for (int w = 0; w < warp; ++w) excl += fs.ls.iscratch[w];
+            if (tid < NSEG / 2) { seg_start[2 * tid] = excl; seg_start[2 * tid + 1] = excl + a; }
+            if (tid == NSEG / 2 - 1) seg_start[NSEG] = excl + a + c2;
+            __syncthreads();
+        }
+        // 1c. every candidate cell: cheap IoU gate; survivors are staged for the exact pass
+        const int T = seg_start[NSEG];
+        auto exact_pair = [&](int p, int g) {
+            const float v = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, p), gt_box(fs.gt_a[g], fs.gt_b[g]));
+            const unsigned o = ord_encode(v);
+            atomicMax(&table[p], ((unsigned long long)o << 32) | (unsigned long long)(0xffffffffu - (unsigned)g));
+            const unsigned long long ck = ((unsigned long long)o << 32) | (unsigned long long)(0xffffffffu - (unsigned)p);
+            if (ck > *reinterpret_cast<volatile unsigned long long*>(&fs.col[g])) atomicMax(&fs.col[g], ck);
+        };
+        for (int t0 = 0; t0 < T; t0 += FT) {
+            const int t = t0 + tid;
+            bool pass = false;
+            int p = 0, g = 0;
+            if (t < T) {
+                int lo = 0, hi = NSEG;                       // seg_start[lo] <= t < seg_start[hi]
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (seg_start[mid] <= t) lo = mid; else hi = mid;
+                }
+                const unsigned info = seg_info[lo];
+                const int local = t - seg_start[lo];
+                const int ni = (int)((info >> 12) & 63u), side = (int)((info >> 18) & 63u), shapes = (int)(info >> 24);
+                const int lj = local / ni, li = local - lj * ni;
+                p = (int)seg_base[lo] + (((int)((info >> 6) & 63u) + lj) * side + (int)(info & 63u) + li) * shapes;
+                g = g0 + (lo >> 5);
+                const float4 pb = ldg4(prm.pri_xyxy + 4ll * p);
+                const float pa = __ldg(prm.pri_aux + 4ll * p);
+                const float4 ga = fs.gt_a[g];
+                const float w = fmaxf(fsub(fminf(pb.z, ga.z), fmaxf(pb.x, ga.x)), 0.0f);
+                const float h = fmaxf(fsub(fminf(pb.w, ga.w), fmaxf(pb.y, ga.y)), 0.0f);
+                const float inter = fmul(w, h);
+                const float uni = fsub(fadd(pa, fs.gt_b[g].x), inter);
+                pass = !(inter < fmul(fs.lim[g], uni));      // NaN-safe: anything odd takes the exact path
+            }
+            const unsigned bal = __ballot_sync(FULL, pass);
+            if (bal) {
+                int dst = 0;
+                if (lane == 0) dst = atomicAdd(&fs.n_pair, __popc(bal));
+                dst = __shfl_sync(FULL, dst, 0) + __popc(bal & ((1u << lane) - 1u));
+                if (pass) {
+                    if (dst < PAIR_CAP) pair_list[dst] = (unsigned)p | ((unsigned)g << 16);
+                    else exact_pair(p, g);
+                }
+            }
+        }
+        __syncthreads();
+        // 1d. exact CIoU of the staged pairs
+        {
+            const int n_pair = min(fs.n_pair, PAIR_CAP);
+            for (int e = tid; e < n_pair; e += FT) {
+                const unsigned pr = pair_list[e];
+                exact_pair((int)(pr & 0xffffu), (int)(pr >> 16));
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();                   // (G == 0: the clear is complete)
+
+    // ---- 2. champions; dense sweep of the columns the rectangles could not settle ------------------
+    if (tid < G) {
+        const int g = tid;
+        if (fs.kind[g] == 0) {
+            const unsigned long long key = fs.col[g];
+            if ((unsigned)(key >> 32) > ord_encode(0.0f)) fs.champ[g] = (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
+            else { fs.kind[g] = 1; atomicAdd(&fs.n_dense, 1); }
+        }
+    }
+    __syncthreads();
+    if (fs.n_dense > 0) {
+        for (int g = 0; g < G; ++g) {
+            if (fs.kind[g] != 1) continue;              // CTA-uniform
+            const BoxC gc = gt_box(fs.gt_a[g], fs.gt_b[g]);
+            if (tid == 0) fs.col[g] = 0ull;
+            __syncthreads();
+            unsigned long long best = 0ull;
+            for (int p = tid; p < P; p += FT) {
+                const float v = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, p), gc);
+                const unsigned long long ck = ((unsigned long long)ord_encode(v) << 32) | (unsigned long long)(0xffffffffu - (unsigned)p);
+                best = ck > best ? ck : best;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long y = __shfl_xor_sync(FULL, best, o);
+                best = y > best ? y : best;
+            }
+            if (lane == 0) atomicMax(&fs.col[g], best);
+            __syncthreads();
+            const int champ = (int)(0xffffffffu - (unsigned)(fs.col[g] & 0xffffffffull));
+            if (tid == 0) fs.champ[g] = champ;
+            // rows: the champion's entry becomes 2.0 below (SFS:747 overwrites it); the others keep their CIoU
+            for (int p = tid; p < P; p += FT) {
+                if (p == champ) continue;
+                const float v = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, p), gc);
+                if (v >= thresh || v != v)
+                    atomicMax(&table[p], ((unsigned long long)ord_encode(v) << 32) | (unsigned long long)(0xffffffffu - (unsigned)g));
+            }
+        }
+        __syncthreads();
+    }
+    // forced matches: row champ[g], column g = 2.0; the lowest box index wins a shared champion
+    if (tid < G) atomicMax(&table[fs.champ[tid]], ((unsigned long long)kOrdTwo << 32) | (unsigned long long)(0xffffffffu - (unsigned)tid));
+    __syncthreads();
+    const int first_nan = fs.first_nan;
+    const unsigned ord_thr = ord_encode(thresh);
+    // prior p is positive iff its best entry is a number >= thresh (an all-NaN column makes every row but 0 NaN)
+    auto positive = [&](unsigned hi, int p) { return hi >= ord_thr && hi != 0xffffffffu && (first_nan == INT_MAX || p == 0); };
+
+    if (!LOSS) {
+        // ---- build_targets-shaped outputs (SSD_trainer.py:547): masks, classes, positives' offsets ------
+        int my_pos = 0;
+        for (int p = tid; p < P; p += FT) {
+            const unsigned long long slot = table[p];
+            const bool pos = G > 0 && positive((unsigned)(slot >> 32), p);
+            const int g = (int)(0xffffffffu - (unsigned)(slot & 0xffffffffull));
+            const long long row = (long long)b * P + p;
+            my_pos += pos ? 1 : 0;
+            if (prm.pos_mask) prm.pos_mask[row] = pos ? 1 : 0;
+            if (prm.cls_t) prm.cls_t[row] = pos ? (int64_t)(fs.label[g] + 1) : (int64_t)0;
+            if (prm.code) prm.code[row] = pos ? (uint16_t)(g + 1) : (uint16_t)0;
+            if (prm.loc_t && pos) {
+                const float4 ga = fs.gt_a[g], gb = fs.gt_b[g];
+                const float4 gbox = make_float4(gb.y, gb.z, fsub(ga.z, ga.x), fsub(ga.w, ga.y));
+                reinterpret_cast<float4*>(prm.loc_t)[row] = encode_offsets(gbox, ldg4(prm.pri + 4ll * p), prm.inv_vc, prm.inv_vs);
+            }
+        }
+        const int n_pos_img = block_sum<int>(my_pos, fs.ls.iscratch);
+        if (tid == 0 && prm.n_pos) prm.n_pos[b] = n_pos_img;
+        return;
+    }
+
+    // ---- 3. stream the logits: approximate CE of every negative, first-level histogram ------------
+    for (int i = tid; i < 2048 + 512; i += FT) hist16[i] = 0u;        // hist16 and hist2 (the scratch changes role)
+    __syncthreads();
+    const float* conf_b = prm.conf_all + (long long)b * P * 6;
+    double acc_loc = 0.0, acc_ce = 0.0;
+    int my_pos = 0;
+    // a positive prior: exact CE of its class, smooth-L1 of its offsets (TR:108, :577-580)
+    auto positive_terms = [&](int p, int g) {
+        const long long row = (long long)b * P + p;
+        acc_ce += (double)exact_ce6(conf_b + 6ll * p, fs.label[g] + 1);
+        const float4 ga = fs.gt_a[g], gb = fs.gt_b[g];
+        const float4 gbox = make_float4(gb.y, gb.z, fsub(ga.z, ga.x), fsub(ga.w, ga.y));
+        const float4 t = encode_offsets(gbox, ldg4(prm.pri + 4ll * p), prm.inv_vc, prm.inv_vs);
+        const float4 l = ldg4(prm.loc_all + 4ll * row);
+        const float d[4] = {fsub(l.x, t.x), fsub(l.y, t.y), fsub(l.z, t.z), fsub(l.w, t.w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float z = fabsf(d[j]);
+            acc_loc += (double)(z < 1.0f ? fmul(fmul(0.5f, z), z) : fsub(z, 0.5f));
+        }
+    };
+    {
+        const float4* src = reinterpret_cast<const float4*>(conf_b);
+        ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
+#pragma unroll 2
+        for (int q = tid; q < P / 2; q += FT) {
+            const float4 A = __ldg(src + 3 * q), Bv = __ldg(src + 3 * q + 1), Cv = __ldg(src + 3 * q + 2);
+            ulonglong2 slots = t2[q];
+            const int p0 = 2 * q;
+            const bool pos0 = G > 0 && positive((unsigned)(slots.x >> 32), p0);
+            const bool pos1 = G > 0 && positive((unsigned)(slots.y >> 32), p0 + 1);
+            const long long row = (long long)b * P + p0;
+            if (!pos0) {
+                const unsigned key = __float_as_uint(approx_ce6(A.x, A.y, A.z, A.w, Bv.x, Bv.y));
+                slots.x = (unsigned long long)key;
+                atomicAdd(&hist16[key >> 20], 1u << (((key >> 19) & 1u) * 16));
+            }
+            if (!pos1) {
+                const unsigned key = __float_as_uint(approx_ce6(Bv.z, Bv.w, Cv.x, Cv.y, Cv.z, Cv.w));
+                slots.y = (unsigned long long)key;
+                atomicAdd(&hist16[key >> 20], 1u << (((key >> 19) & 1u) * 16));
+            }
+            t2[q] = slots;
+            if (prm.sel_cls) {
+                const int g0 = (int)(0xffffffffu - (unsigned)(slots.x & 0xffffffffull));
+                const int g1 = (int)(0xffffffffu - (unsigned)(slots.y & 0xffffffffull));
+                prm.sel_cls[row] = pos0 ? (int8_t)(fs.label[g0] + 1) : (int8_t)-1;
+                prm.sel_cls[row + 1] = pos1 ? (int8_t)(fs.label[g1] + 1) : (int8_t)-1;
+                if (prm.matched16) { prm.matched16[row] = pos0 ? (int16_t)g0 : (int16_t)-1; prm.matched16[row + 1] = pos1 ? (int16_t)g1 : (int16_t)-1; }
+            }
+            if (pos0 || pos1) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (!(h ? pos1 : pos0)) continue;
+                    my_pos += 1;
+                    const int dst = atomicAdd(&fs.n_poslist, 1);
+                    if (dst < POS_CAP) pos_list[dst] = (uint16_t)(p0 + h);
+                    else positive_terms(p0 + h, (int)(0xffffffffu - (unsigned)((h ? slots.y : slots.x) & 0xffffffffull)));
+                }
+            }
+        }
+        if ((P & 1) && tid == 0) {                      // odd P: the last row (never SSD300)
+            const int p = P - 1;
+            const unsigned long long slot = table[p];
+            if (G > 0 && positive((unsigned)(slot >> 32), p)) {
+                my_pos += 1;
+                positive_terms(p, (int)(0xffffffffu - (unsigned)(slot & 0xffffffffull)));
+            } else {
+                const float* r = conf_b + 6ll * p;
+                const unsigned key = __float_as_uint(approx_ce6(r[0], r[1], r[2], r[3], r[4], r[5]));
+                table[p] = (unsigned long long)key;
+                atomicAdd(&hist16[key >> 20], 1u << (((key >> 19) & 1u) * 16));
+            }
+        }
+    }
+    const int n_pos_img = block_sum<int>(my_pos, fs.ls.iscratch);      // two barriers: slots, lists and hist16 are complete
+    if (tid == 0 && prm.n_pos) prm.n_pos[b] = n_pos_img;
+
+    // positives (dense: one list entry per thread)
+    {
+        const int n_list = min(fs.n_poslist, POS_CAP);
+        for (int e = tid; e < n_list; e += FT) {
+            const int p = (int)pos_list[e];
+            positive_terms(p, (int)(0xffffffffu - (unsigned)(table[p] & 0xffffffffull)));
+        }
+    }
+
+    // ---- 4. hard negatives -----------------------------------------------------------------------
     const long long n_neg = (long long)P - n_pos_img;
     long long want = (n_pos_img == 0) ? (long long)prm.ratio : (long long)(prm.ratio * (double)n_pos_img);
     if (want < 0) want = 0;
     const long long kk = want < n_neg ? want : n_neg;
-    unsigned thr_key = 0u;        // selected negatives: key > thr_key, plus `need` of those == thr_key
-    unsigned need = 0u, n_eq = 0u;
-    const bool take_all = (kk >= n_neg);
-    if (kk > 0 && !take_all) {
-        // 4-pass MSD radix select of the kk-th largest key
-        unsigned prefix = 0u, remaining = (unsigned)kk;
-        for (int pass = 0; pass < 4; ++pass) {
-            const int shift = 24 - 8 * pass;
-            if (pass > 0) {
-                for (int i = tid; i < 256; i += LT) ls.hist[i] = 0u;
-                __syncthreads();
-                const unsigned himask = 0xffffffffu << (shift + 8);
-                for (int p = tid; p < P; p += LT) {
-                    const unsigned key = keys[p];
-                    if (key != kNotNegative && ((key & himask) == prefix)) atomicAdd(&ls.hist[(key >> shift) & 255u], 1u);
+    bool exact_all = kk >= n_neg && kk > 0;
+    if (kk > 0 && !exact_all) {
+        unsigned b1, above1, b2, above2;
+        find_kth_from_top<FT, 4096>([&](int bin) { return (hist16[bin >> 1] >> ((bin & 1) * 16)) & 0xffffu; }, (unsigned)kk, fs, b1, above1);
+        for (int p = tid; p < P; p += FT) {
+            const unsigned long long slot = table[p];
+            const unsigned key = (unsigned)slot;
+            if ((slot >> 32) == 0ull && (key >> 19) == b1) atomicAdd(&hist2[(key >> 10) & 511u], 1u);
+        }
+        __syncthreads();
+        find_kth_from_top<FT, 512>([&](int bin) { return hist2[bin]; }, (unsigned)kk - above1, fs, b2, above2);
+        const unsigned lo_key = (b1 << 19) | (b2 << 10), hi_key = lo_key | 1023u;
+        const float t_lo = __uint_as_float(lo_key), t_hi = __uint_as_float(hi_key);
+        if (!(t_hi < 1e30f)) exact_all = true;          // inf / NaN bracket: CTA-uniform
+        else {
+            const float band_lo = t_lo - 3.0f * ce_error_bound(t_lo), band_hi = t_hi + 3.0f * ce_error_bound(t_hi);
+            // certain members (above the band) and band members, compacted
+            for (int base = 0; base < P; base += FT) {
+                const int p = base + tid;
+                bool sure = false, band = false;
+                if (p < P) {
+                    const unsigned long long slot = table[p];
+                    if ((slot >> 32) == 0ull) {
+                        const float ce = __uint_as_float((unsigned)slot);
+                        sure = ce > band_hi;
+                        band = !sure && ce >= band_lo;
+                    }
                 }
-                __syncthreads();
+                const unsigned bs = __ballot_sync(FULL, sure), bb = __ballot_sync(FULL, band);
+                const unsigned lt = (1u << lane) - 1u;
+                if (bs) {
+                    int dst = 0;
+                    if (lane == 0) dst = atomicAdd(&fs.n_sel, __popc(bs));
+                    dst = __shfl_sync(FULL, dst, 0) + __popc(bs & lt);
+                    if (sure) {
+                        if (dst < SEL_CAP) sel_list[dst] = (uint16_t)p;
+                        else {
+                            acc_ce += (double)exact_ce6(conf_b + 6ll * p, 0);
+                            if (prm.sel_cls) prm.sel_cls[(long long)b * P + p] = 0;
+                        }
+                    }
+                }
+                if (bb) {
+                    int dst = 0;
+                    if (lane == 0) dst = atomicAdd(&fs.n_band, __popc(bb));
+                    dst = __shfl_sync(FULL, dst, 0) + __popc(bb & lt);
+                    if (band && dst < BAND_CAP) band_p[dst] = (uint16_t)p;
+                }
             }
-            if (tid < 32) {
-                // bins 255..0: lane l owns bins [255-8l-7 .. 255-8l]; find where the suffix count reaches `remaining`
-                unsigned mine = 0u;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) mine += ls.hist[255 - (tid * 8 + j)];
-                unsigned incl = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned y = __shfl_up_sync(FULL, incl, o);
-                    if (tid >= o) incl += y;
+            __syncthreads();
+            const int n_sure = fs.n_sel, n_band = fs.n_band;
+            if (n_band > BAND_CAP) exact_all = true;     // (massive ties): CTA-uniform; the partial sums below are discarded
+            else {
+                for (int e = tid; e < min(n_sure, SEL_CAP); e += FT) {
+                    const int p = (int)sel_list[e];
+                    acc_ce += (double)exact_ce6(conf_b + 6ll * p, 0);
+                    if (prm.sel_cls) prm.sel_cls[(long long)b * P + p] = 0;
                 }
-                const unsigned excl = incl - mine;
-                if (excl < remaining && remaining <= incl) {
-                    unsigned run = excl;
-                    for (int j = 0; j < 8; ++j) {
-                        const int bin = 255 - (tid * 8 + j);
-                        const unsigned c = ls.hist[bin];
-                        if (run + c >= remaining) { ls.sel_digit = (unsigned)bin; ls.sel_need = remaining - run; ls.sel_eq = c; break; }
-                        run += c;
+                for (int e = tid; e < n_band; e += FT)
+                    band_v[e] = __float_as_uint(exact_ce6(conf_b + 6ll * (int)band_p[e], 0)) & 0x7fffffffu;
+                __syncthreads();
+                const int r = (int)kk - n_sure;          // members still to take from the band (1 <= r <= n_band)
+                for (int e = tid; e < n_band; e += FT) {
+                    const unsigned v = band_v[e];
+                    const int p = (int)band_p[e];
+                    int rank = 0;
+                    for (int j = 0; j < n_band; ++j) {
+                        const unsigned vj = band_v[j];
+                        rank += (vj > v || (vj == v && (int)band_p[j] < p)) ? 1 : 0;
+                    }
+                    if (rank < r) {
+                        acc_ce += (double)__uint_as_float(v);
+                        if (prm.sel_cls) prm.sel_cls[(long long)b * P + p] = 0;
                     }
                 }
             }
-            __syncthreads();
-            prefix |= ls.sel_digit << shift;
-            remaining = ls.sel_need;
-            n_eq = ls.sel_eq;
-            __syncthreads();
-        }
-        thr_key = prefix;
-        need = remaining;
-    }
-
-    // ---- sums (and the backward selection) --------------------------------------------------
-    if (kk > 0) {
-        for (int p = tid; p < P; p += LT) {
-            const unsigned key = keys[p];
-            if (key != kNotNegative && (take_all || key > thr_key)) acc_ce += (double)__uint_as_float(key);
         }
     }
-    if (prm.sel_cls) {
-        // of the negatives equal to the threshold value the first `need` in prior order are taken
-        const bool all_ties = take_all || kk == 0 || need == n_eq;
-        int before = 0;
-        for (int base = 0; base < P; base += LT) {
-            const int p = base + tid;
-            const unsigned key = p < P ? keys[p] : kNotNegative;
-            const bool tie = kk > 0 && !take_all && key != kNotNegative && key == thr_key;
-            int rank_tie = 0;
-            if (!all_ties) {
-                const unsigned bal = __ballot_sync(FULL, tie);
-                __syncthreads();
-                if (lane == 0) ls.iscratch[warp] = __popc(bal);
-                __syncthreads();
-                int slot_total = 0;
-                for (int w = 0; w < LT / 32; ++w) { if (w < warp) rank_tie += ls.iscratch[w]; slot_total += ls.iscratch[w]; }
-                rank_tie += before + __popc(bal & ((1u << lane) - 1u));
-                before += slot_total;
+    if (exact_all) {
+        // exact keys for every negative, then the exact radix selection (as loss_image_kernel)
+        acc_ce = 0.0;
+        __syncthreads();
+        for (int i = tid; i < 256; i += FT) fs.ls.hist[i] = 0u;
+        __syncthreads();
+        for (int p = tid; p < P; p += FT) {
+            const unsigned long long slot = table[p];
+            if ((slot >> 32) == 0ull) {
+                const unsigned key = __float_as_uint(exact_ce6(conf_b + 6ll * p, 0)) & 0x7fffffffu;
+                table[p] = (unsigned long long)key;
+                atomicAdd(&fs.ls.hist[key >> 24], 1u);
+            } else {
+                acc_ce += (double)exact_ce6(conf_b + 6ll * p, fs.label[(int)(0xffffffffu - (unsigned)(slot & 0xffffffffull))] + 1);
             }
-            if (p >= P) continue;
-            const long long row = (long long)b * P + p;
-            int mg;
-            const int tgt = load_target<FROM_TARGETS>(prm, row, g_begin, mg);
-            int8_t sel = -1;
-            if (tgt >= 0) sel = (int8_t)tgt;
-            else if (kk > 0 && (take_all || key > thr_key || (tie && (all_ties || (unsigned)rank_tie < need)))) sel = 0;
-            prm.sel_cls[row] = sel;
-            if (prm.matched16) prm.matched16[row] = (int16_t)mg;
         }
+        __syncthreads();
+        acc_ce += mined_exact_tail<FT>(prm, b, P, n_pos_img, fs.ls,
+                                       [&](int p) { const unsigned long long s = table[p]; return (s >> 32) == 0ull ? (unsigned)s : kNotNegative; },
+                                       [&](int p, int& mg) {
+                                           const unsigned long long s = table[p];
+                                           mg = -1;
+                                           if ((s >> 32) == 0ull) return -1;
+                                           mg = (int)(0xffffffffu - (unsigned)(s & 0xffffffffull));
+                                           return fs.label[mg] + 1;
+                                       });
     }
-    // the `need` threshold-valued negatives are counted once
-    if (tid == 0 && kk > 0 && !take_all) acc_ce += (double)need * (double)__uint_as_float(thr_key);
 
-    const double s_loc = block_sum<double>(acc_loc, ls.dscratch);
-    const double s_ce = block_sum<double>(acc_ce, ls.dscratch);
+    const double s_loc = block_sum<double>(acc_loc, fs.ls.dscratch);
+    const double s_ce = block_sum<double>(acc_ce, fs.ls.dscratch);
     if (tid == 0) {
         prm.img_part[2ll * b + 0] = s_loc;
         prm.img_part[2ll * b + 1] = s_ce;
@@ -740,10 +1335,51 @@ static int launch_loss(const TrainParams& prm, cudaStream_t stream) {
     return SSDHOT_OK;
 }
 
+template <bool LOSS>
+static int launch_train_image(const TrainParams& prm, cudaStream_t stream) {
+    const size_t dyn = fused_smem_bytes(prm.P);
+    auto kern = train_image_kernel<LOSS>;
+    static bool configured = false;    // sticky opt-in, raised outside graph capture by the first (warm-up) call
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    kern<<<prm.B, FT, dyn, stream>>>(prm);
+    SSDHOT_CHECK_LAUNCH();
+    return SSDHOT_OK;
+}
+
+// the box-centric kernel needs the SSD300 grid structure, at most FAST_MAX_GT boxes per image and a positive threshold
+static bool fast_path_ok(int prior_layout, int P, int max_gt, float iou_thresh) {
+    return prior_layout == SSDHOT_LAYOUT_SSD300 && P == 8732 && max_gt <= FAST_MAX_GT && iou_thresh > 0.0f;
+}
 
 }  // namespace ssdhot
 
 using namespace ssdhot;
+
+// Host-side check that `priors` (HOST memory) have the SSD300 structure train_image_kernel relies on:
+// levels of 38/19/10/5/3/1 cells with 4/6/6/6/4/4 shapes, cells row-major, shapes innermost
+// (SSD_from_scratch.py:289-323); centres (i + 0.5)/side within 1e-5; one (w, h) in (0, 1] per (level, shape).
+extern "C" int ssdhot_ssd300_layout_host(const float* priors_cxcywh_host, int P) {
+    if (!priors_cxcywh_host || P != 8732) return 0;
+    static const int side[6] = {38, 19, 10, 5, 3, 1}, shapes[6] = {4, 6, 6, 6, 4, 4};
+    int off = 0;
+    for (int l = 0; l < 6; ++l) {
+        for (int j = 0; j < side[l]; ++j)
+            for (int i = 0; i < side[l]; ++i)
+                for (int k = 0; k < shapes[l]; ++k) {
+                    const float* q = priors_cxcywh_host + 4ll * (off + (j * side[l] + i) * shapes[l] + k);
+                    const float* q0 = priors_cxcywh_host + 4ll * (off + k);
+                    const float cx = (float)((i + 0.5) / side[l]), cy = (float)((j + 0.5) / side[l]);
+                    if (!(q[0] - cx <= 1e-5f && cx - q[0] <= 1e-5f && q[1] - cy <= 1e-5f && cy - q[1] <= 1e-5f)) return 0;
+                    if (!(q[2] == q0[2] && q[3] == q0[3] && q[2] > 0.0f && q[2] <= 1.0f && q[3] > 0.0f && q[3] <= 1.0f)) return 0;
+                }
+        off += side[l] * side[l] * shapes[l];
+    }
+    return off == P ? 1 : 0;
+}
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -778,7 +1414,7 @@ static int check_gt_args(const float* pri, const float* pri_xyxy, const float* a
 }
 
 extern "C" int ssdhot_match_encode(const float* priors_cxcywh, const float* priors_xyxy, const float* prior_aux, int P,
-                                   const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
+                                   int prior_layout, const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
                                    int B, int max_gt, float norm_w, float norm_h,
                                    float iou_thresh, float var_center, float var_size,
                                    float* loc_t, int loc_positives_only, int64_t* cls_t, uint8_t* pos_mask,
@@ -799,6 +1435,7 @@ extern "C" int ssdhot_match_encode(const float* priors_cxcywh, const float* prio
     prm.matched32 = matched_gt; prm.matched_box = matched_cxcywh; prm.n_pos = n_pos; prm.flags = dev_flags;
     // the pruned sweep is exact for positives; negatives' matches need the exact-everywhere sweep
     const bool prune = (!loc_t || loc_positives_only) && !matched_gt && !matched_cxcywh;
+    if (prune && fast_path_ok(prior_layout, P, max_gt, iou_thresh)) return launch_train_image<false>(prm, (cudaStream_t)stream);
     return prune ? launch_match<true>(prm, (cudaStream_t)stream) : launch_match<false>(prm, (cudaStream_t)stream);
 }
 
@@ -834,7 +1471,7 @@ static int finalize(const TrainParams& prm, const int32_t* n_pos, double* sums, 
 }
 
 extern "C" int ssdhot_multibox_loss_fwd(const float* priors_cxcywh, const float* priors_xyxy, const float* prior_aux, int P,
-                                        const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
+                                        int prior_layout, const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
                                         int B, int max_gt, float norm_w, float norm_h,
                                         const float* loc_all, const float* conf_all, int C,
                                         float iou_thresh, float var_center, float var_size, double neg_pos_ratio,
@@ -858,11 +1495,19 @@ extern "C" int ssdhot_multibox_loss_fwd(const float* priors_cxcywh, const float*
     prm.gt_rec = reinterpret_cast<float4*>(w + ws_rec_off(B));
     prm.code = reinterpret_cast<uint16_t*>(w + ws_code_off(B, max_gt));
     prm.flags = dev_flags;
+    int32_t* np = n_pos ? n_pos : reinterpret_cast<int32_t*>(w + ws_npos_off(B));
+    if (C == 6 && aligned16(conf_all) && fast_path_ok(prior_layout, P, max_gt, iou_thresh)) {
+        // SSD300 fast path: box-centric matching + mined loss, one kernel, one CTA per image
+        prm.n_pos = np; prm.sel_cls = sel_cls; prm.matched16 = matched_gt; prm.code = nullptr;
+        rc = launch_train_image<true>(prm, (cudaStream_t)stream);
+        if (rc) return rc;
+        return finalize(prm, np, sums, (cudaStream_t)stream);
+    }
+    // generic priors / class counts:
     // 1) match: cluster per image, pruned sweep, 2-byte code per prior
     rc = launch_match<true>(prm, (cudaStream_t)stream);
     if (rc) return rc;
     // 2) loss: one CTA per image
-    int32_t* np = n_pos ? n_pos : reinterpret_cast<int32_t*>(w + ws_npos_off(B));
     prm.n_pos = np; prm.sel_cls = sel_cls; prm.matched16 = matched_gt;
     rc = launch_loss<false>(prm, (cudaStream_t)stream);
     if (rc) return rc;

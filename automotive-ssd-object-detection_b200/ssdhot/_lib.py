@@ -9,7 +9,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libssdhot.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lock = threading.Lock()
 _lib = None
@@ -23,12 +23,13 @@ PROTOTYPES = {
     "ssdhot_launch_count": (u64, []),
     "ssdhot_prior_tables": (i32, [vp, i32, vp, vp, vp]),
     "ssdhot_prior_aux": (i32, [vp, i32, vp, vp]),
-    "ssdhot_match_encode": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, f32, f32, f32,
+    "ssdhot_ssd300_layout_host": (i32, [vp, i32]),
+    "ssdhot_match_encode": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, i32, i32, f32, f32, f32, f32, f32,
                                   vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "ssdhot_match_workspace_bytes": (u64, [i32, i32]),
     "ssdhot_compact_rows": (i32, [vp, vp, vp, i32, i32, vp, vp]),
     "ssdhot_loss_workspace_bytes": (u64, [i32, i32, i32]),
-    "ssdhot_multibox_loss_fwd": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, vp, vp, i32,
+    "ssdhot_multibox_loss_fwd": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, i32, i32, f32, f32, vp, vp, i32,
                                        f32, f32, f32, f64, vp, vp, vp, vp, vp, vp, vp]),
     "ssdhot_mined_ce_fwd": (i32, [vp, vp, vp, i32, i32, i32, f64, vp, vp, vp, vp]),
     "ssdhot_multibox_loss_bwd": (i32, [vp, i32, vp, vp, i32, f32, f32, vp, vp, i32, f32, f32, vp, vp, vp, vp, vp, vp]),

@@ -91,7 +91,7 @@ def match_encode_batch(priors: PriorSet, packed: PackedTargets, iou_thresh: floa
     work = _workspace("match", dev, _lib.lib().ssdhot_match_workspace_bytes(B, packed.max_gt))
     with torch.cuda.device(dev):
         rc = _lib.lib().ssdhot_match_encode(
-            priors.priors.data_ptr(), priors.priors_xyxy.data_ptr(), priors.aux.data_ptr(), P,
+            priors.priors.data_ptr(), priors.priors_xyxy.data_ptr(), priors.aux.data_ptr(), P, priors.layout,
             packed.boxes.data_ptr(), packed.labels.data_ptr(), packed.offsets.data_ptr(), B, packed.max_gt,
             float(norm_wh[0]), float(norm_wh[1]), float(iou_thresh), priors.variances[0], priors.variances[1],
             _ptr(loc), 1 if want_loc == "positives" else 0, _ptr(out["cls_t"]), _ptr(out["pos_mask"]),
@@ -209,7 +209,7 @@ class _FusedLoss(torch.autograd.Function):
         work = _workspace("loss", dev, _lib.lib().ssdhot_loss_workspace_bytes(B, P, packed.max_gt))
         with torch.cuda.device(dev):
             rc = _lib.lib().ssdhot_multibox_loss_fwd(
-                priors.priors.data_ptr(), priors.priors_xyxy.data_ptr(), priors.aux.data_ptr(), P,
+                priors.priors.data_ptr(), priors.priors_xyxy.data_ptr(), priors.aux.data_ptr(), P, priors.layout,
                 packed.boxes.data_ptr(), packed.labels.data_ptr(), packed.offsets.data_ptr(), B, packed.max_gt,
                 float(norm_wh[0]), float(norm_wh[1]), loc.data_ptr(), conf.data_ptr(), C,
                 float(iou_thresh), priors.variances[0], priors.variances[1], float(ratio),

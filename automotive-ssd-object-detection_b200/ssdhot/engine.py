@@ -49,7 +49,7 @@ class HotPathStep:
         if gt.max_gt > self.max_gt:
             raise _lib.SsdhotError(f"HotPathStep was planned for at most {self.max_gt} boxes per image, got {gt.max_gt}")
         rc = _lib.lib().ssdhot_multibox_loss_fwd(
-            ps.priors.data_ptr(), ps.priors_xyxy.data_ptr(), ps.aux.data_ptr(), ps.P,
+            ps.priors.data_ptr(), ps.priors_xyxy.data_ptr(), ps.aux.data_ptr(), ps.P, ps.layout,
             gt.boxes.data_ptr(), gt.labels.data_ptr(), gt.offsets.data_ptr(), self.B, gt.max_gt,
             self.norm_wh[0], self.norm_wh[1], loc.data_ptr(), conf.data_ptr(), self.C,
             self.iou_thresh, ps.variances[0], ps.variances[1], self.ratio,

@@ -41,13 +41,17 @@ class PriorSet:
     (area, centre, atan(w/h)) that `complete_box_iou` would recompute for every image."""
 
     def __init__(self, priors: torch.Tensor, priors_xyxy: Optional[torch.Tensor] = None,
-                 variances: Tuple[float, float] = (0.1, 0.2), img_hw: Tuple[int, int] = (300, 300)):
+                 variances: Tuple[float, float] = (0.1, 0.2), img_hw: Tuple[int, int] = (300, 300),
+                 generic: bool = False):
         if not priors.is_cuda:
             raise _lib.SsdhotError("ssdhot needs CUDA tensors (no CPU fallback)")
         self.priors = priors.detach().to(torch.float32).contiguous()
         self.P = int(self.priors.shape[0])
         self.variances = (float(variances[0]), float(variances[1]))
         self.img_h, self.img_w = int(img_hw[0]), int(img_hw[1])
+        # SSD300 grid structure (checked once on a host copy) enables the box-centric matching kernel
+        host = self.priors.cpu().contiguous()
+        self.layout = 0 if generic else int(_lib.lib().ssdhot_ssd300_layout_host(host.data_ptr(), self.P))
         stream = torch.cuda.current_stream(self.priors.device).cuda_stream
         self.aux = torch.empty((self.P, 4), dtype=torch.float32, device=self.priors.device)
         with torch.cuda.device(self.priors.device):
@@ -65,8 +69,10 @@ class PriorSet:
         return self.priors.device
 
     @classmethod
-    def default(cls, device="cuda", variances=(0.1, 0.2)) -> "PriorSet":
-        return cls(default_boxes().to(device), None, variances)
+    def default(cls, device="cuda", variances=(0.1, 0.2), generic: bool = False) -> "PriorSet":
+        """The reference's 8732 default boxes.  generic=True withholds the SSD300 layout flag, which
+        routes matching through the layout-agnostic kernels (used by the parity tests)."""
+        return cls(default_boxes().to(device), None, variances, generic=generic)
 
     _cache = {}
 

@@ -35,7 +35,7 @@ extern "C" {
 #define SSDHOT_API
 #endif
 
-#define SSDHOT_ABI_VERSION 1
+#define SSDHOT_ABI_VERSION 2
 #define SSDHOT_MAX_PRIORS 10240   /* 8 CTAs x 256 threads x 5 priors per image cluster */
 #define SSDHOT_MAX_GT 2048        /* ground-truth boxes per image held in shared memory */
 #define SSDHOT_MAX_CLASSES 256
@@ -50,6 +50,13 @@ typedef enum {
 } ssdhot_status;
 
 typedef void* ssdhot_stream_t;   /* cudaStream_t */
+
+/* prior_layout argument of the matching entry points: 0 = arbitrary priors (generic kernels);
+ * 1 = the SSD300 grid structure of SFS:289-323 (levels 38/19/10/5/3/1, shapes innermost), as
+ * verified once by ssdhot_ssd300_layout_host -- enables the box-centric fast path.  Passing 1 for
+ * priors that do not have that structure gives wrong matches. */
+#define SSDHOT_LAYOUT_GENERIC 0
+#define SSDHOT_LAYOUT_SSD300 1
 
 /* metric used by the NMS predicates: the reference CODE uses DIoU (SFS:688); CIoU is offered
  * because README.md:17 / BASELINE.json name it. */
@@ -70,6 +77,9 @@ SSDHOT_API int ssdhot_prior_tables(const float* priors_cxcywh, int P, float* pri
                         ssdhot_stream_t stream);
 /* prior_aux only, from caller-owned (already clamped) xyxy priors such as mySSD.priors_xyxy. */
 SSDHOT_API int ssdhot_prior_aux(const float* priors_xyxy, int P, float* prior_aux, ssdhot_stream_t stream);
+/* HOST function on a HOST copy of the priors: 1 if they have the SSD300 structure
+ * (SSDHOT_LAYOUT_SSD300), else 0.  No GPU work. */
+SSDHOT_API int ssdhot_ssd300_layout_host(const float* priors_cxcywh_host, int P);
 
 /* ---- a2/a3: match + encode ----------------------------------------------------------------
  * Replaces the per-image loop of build_targets (TR:525-545) around mySSD.encode_ssd
@@ -88,7 +98,7 @@ SSDHOT_API int ssdhot_prior_aux(const float* priors_xyxy, int P, float* prior_au
  * An image whose box count exceeds max_gt sets bit 0 of *dev_flags (optional).
  *   work: scratch of ssdhot_match_workspace_bytes(B, max_gt) bytes. */
 SSDHOT_API int ssdhot_match_encode(const float* priors_cxcywh, const float* priors_xyxy, const float* prior_aux, int P,
-                        const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
+                        int prior_layout, const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
                         int B, int max_gt, float norm_w, float norm_h,
                         float iou_thresh, float var_center, float var_size,
                         float* loc_t, int loc_positives_only, int64_t* cls_t, uint8_t* pos_mask,
@@ -115,7 +125,7 @@ SSDHOT_API int ssdhot_compact_rows(const float* loc_t, const uint8_t* pos_mask, 
  *   target class), matched_gt [B,P] int16 (positives only, -1 elsewhere), n_pos [B]. */
 SSDHOT_API unsigned long long ssdhot_loss_workspace_bytes(int B, int P, int max_gt);
 SSDHOT_API int ssdhot_multibox_loss_fwd(const float* priors_cxcywh, const float* priors_xyxy, const float* prior_aux, int P,
-                             const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
+                             int prior_layout, const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
                              int B, int max_gt, float norm_w, float norm_h,
                              const float* loc_all, const float* conf_all, int C,
                              float iou_thresh, float var_center, float var_size, double neg_pos_ratio,

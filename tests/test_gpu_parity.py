@@ -53,7 +53,7 @@ def close(a, b, rtol=RTOL, atol=1e-6):
 # ------------------------------------------------------------------------------------------------
 def test_library_is_native_and_loaded(env):
     s = env["ssdhot"]
-    assert s.lib().ssdhot_abi_version() == 1
+    assert s.lib().ssdhot_abi_version() == 2
     before = s.launch_count()
     s.PriorSet.default(env["dev"])
     assert s.launch_count() == before + 1
@@ -445,3 +445,70 @@ def test_pruned_sweep_equals_exact_sweep(env):
         tg = to_dev(targets, dev)
         pos_o, _, cls_o = O.batch_targets(env["pri"], env["pri_xyxy"], tg, 300, 300, thr)
         assert bit_equal(exact["pos_mask"], pos_o) and bit_equal(exact["cls_t"], cls_o)
+
+
+def _raw_loss(s, ps, loc, conf, targets, thr, ratio):
+    """ssdhot_multibox_loss_fwd with every optional output -> (sums f64[3], sel i8[B,P], matched i16[B,P], n_pos i32[B])."""
+    from ssdhot import _lib
+    dev = loc.device
+    B, P, C = conf.shape
+    packed = s.pack_targets(targets, dev)
+    sums = torch.empty((3,), dtype=torch.float64, device=dev)
+    sel = torch.empty((B, P), dtype=torch.int8, device=dev)
+    matched = torch.empty((B, P), dtype=torch.int16, device=dev)
+    n_pos = torch.empty((B,), dtype=torch.int32, device=dev)
+    work = torch.empty((int(s.lib().ssdhot_loss_workspace_bytes(B, P, packed.max_gt)),), dtype=torch.uint8, device=dev)
+    rc = s.lib().ssdhot_multibox_loss_fwd(
+        ps.priors.data_ptr(), ps.priors_xyxy.data_ptr(), ps.aux.data_ptr(), P, ps.layout,
+        packed.boxes.data_ptr(), packed.labels.data_ptr(), packed.offsets.data_ptr(), B, packed.max_gt, 300.0, 300.0,
+        loc.data_ptr(), conf.data_ptr(), C, float(thr), 0.1, 0.2, float(ratio),
+        sums.data_ptr(), work.data_ptr(), sel.data_ptr(), matched.data_ptr(), n_pos.data_ptr(), None,
+        torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "ssdhot_multibox_loss_fwd")
+    torch.cuda.synchronize(dev)
+    return sums, sel, matched, n_pos
+
+
+def test_fast_train_path_equals_generic_path(env):
+    """The SSD300 fast path (box-centric matching over candidate rectangles, approximate CE +
+    error-band refinement for the mining) must pick exactly the positives, matched boxes and hard
+    negatives of the layout-agnostic exact kernels, and produce the same sums (same fp32 terms,
+    double accumulation in a different order -> 1e-12)."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    from ssdhot import synth
+    psg = s.PriorSet.default(dev, generic=True)
+    assert ps.layout == 1 and psg.layout == 0
+    gen = torch.Generator().manual_seed(77)
+    f = lambda rows: torch.tensor(rows, dtype=torch.float32).reshape(-1, 4)
+    cases = []
+    t_a = synth.make_targets(24, 0, 40, gen)
+    t_a[1] = {"boxes": f([[310, 310, 330, 340], [-50, -40, -10, -5]]), "labels": torch.tensor([1, 2])}
+    t_a[2] = {"boxes": f([[0, 0, 1, 1], [299, 299, 300, 300], [150, 150, 150.5, 150.5]]), "labels": torch.tensor([0, 1, 2])}
+    t_a[3] = {"boxes": f([[100, 100, 100, 100]]), "labels": torch.tensor([3])}
+    t_a[4] = {"boxes": f([[100, 100, 100, 100], [20, 30, 200, 250], [20, 30, 200, 250]]), "labels": torch.tensor([3, 1, 4])}
+    t_a[5] = {"boxes": f([[0, 0, 300, 300], [0, 0, 300, 10], [140, 0, 160, 300]]), "labels": torch.tensor([0, 1, 2])}
+    t_a[6] = {"boxes": f([[50, 50, 40, 90], [float("inf"), 0, 10, 10], [10, 10, 60, 60]]), "labels": torch.tensor([0, 1, 2])}
+    loc_a, conf_a = synth.make_heads(24, gen)
+    cases.append(("edges", t_a, loc_a, conf_a))
+    t_b = synth.make_targets(6, 64, 64, gen)
+    loc_b, conf_b = synth.make_heads(6, gen)
+    cases.append(("g64", t_b, loc_b, conf_b))
+    t_c = synth.make_targets(8, 1, 20, gen)
+    loc_c, conf_c = synth.make_heads(8, gen)
+    conf_big = conf_c * 30.0
+    conf_tie = torch.zeros_like(conf_c)
+    conf_tie[:, ::7] = conf_c[:, ::7].round()                 # many exact ties, a few distinct values
+    conf_bias = conf_c.clone()
+    conf_bias[..., 0] += 6.0
+    cases += [("big", t_c, loc_c, conf_big), ("ties", t_c, loc_c, conf_tie), ("bias", t_c, loc_c, conf_bias)]
+    for name, targets, loc, conf in cases:
+        lg, cg = loc.to(dev), conf.to(dev)
+        for thr in (0.5, 0.25):
+            for ratio in (3.0, 0.4, 0.0, 1e6):
+                fast = _raw_loss(s, ps, lg, cg, targets, thr, ratio)
+                slow = _raw_loss(s, psg, lg, cg, targets, thr, ratio)
+                tag = (name, thr, ratio)
+                assert bit_equal(fast[3], slow[3]), tag
+                assert bit_equal(fast[2], slow[2]), tag
+                assert bit_equal(fast[1], slow[1]), tag
+                assert torch.allclose(fast[0], slow[0], rtol=1e-12, atol=1e-9), (tag, fast[0], slow[0])

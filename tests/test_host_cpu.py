@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l and "ssdhot_" in l)
     assert exported == names, "exported symbols differ from the header"
-    assert handle.ssdhot_abi_version() == 1
+    assert handle.ssdhot_abi_version() == 2
     assert handle.ssdhot_status_string(-2).decode().startswith("a size")
 
 
@@ -168,3 +168,21 @@ def test_sharded_loss_equals_single_process_gloo_world2():
     assert out[0] == out[1]
     assert abs(out[0][0] - want_loc.item()) <= 1e-5 * abs(want_loc.item())
     assert abs(out[0][1] - want_conf.item()) <= 1e-5 * abs(want_conf.item())
+
+
+def test_ssd300_layout_check_host():
+    """ssdhot_ssd300_layout_host is a pure host function: true for the reference's default boxes,
+    false for anything that breaks the grid structure the box-centric matching kernel relies on."""
+    import ssdhot
+    L = ssdhot.lib()
+    pri = ssdhot.default_boxes().contiguous()
+    assert L.ssdhot_ssd300_layout_host(pri.data_ptr(), 8732) == 1
+    assert L.ssdhot_ssd300_layout_host(pri.data_ptr(), 8731) == 0
+    assert L.ssdhot_ssd300_layout_host(None, 8732) == 0
+    for idx, col, delta in ((5000, 0, 1e-3), (17, 2, 1e-4), (8731, 3, 0.5), (0, 1, -2e-5)):
+        bad = pri.clone()
+        bad[idx, col] += delta
+        assert L.ssdhot_ssd300_layout_host(bad.data_ptr(), 8732) == 0, (idx, col)
+    perm = pri.clone()
+    perm[[0, 1]] = perm[[1, 0]]            # two shapes of one cell swapped
+    assert L.ssdhot_ssd300_layout_host(perm.data_ptr(), 8732) == 0
