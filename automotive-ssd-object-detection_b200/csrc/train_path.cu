@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(TT, PRUNE ? 4 : 2) match_kernel(const TrainPar
                         pr.area = x.x; pr.xc = x.y; pr.yc = x.z; pr.at = x.w;
                         const float v = pair_ciou(pr, gc);
                         if (v > best_v[k]) { best_v[k] = v; best_g[k] = g; }
-                        if (valid[k] && v > cb.v) { cb.v = v; cb.p = (unsigned)(p0 + k * TT + tid); }
+                        if (valid[k] && (v > cb.v || cb.p == 0xffffffffu)) { cb.v = v; cb.p = (unsigned)(p0 + k * TT + tid); }   // (a column of -inf still has a champion)
                     }
                 }
             }
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(TT, PRUNE ? 4 : 2) match_kernel(const TrainPar
                         const int q = valid[k] ? p0 + k * TT + tid : p0;
                         const float v = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, q), gc);
                         if (v > best_v[k] || (v == best_v[k] && g < best_g[k])) { best_v[k] = v; best_g[k] = g; }
-                        if (valid[k] && v > cb.v) { cb.v = v; cb.p = (unsigned)q; }
+                        if (valid[k] && (v > cb.v || cb.p == 0xffffffffu)) { cb.v = v; cb.p = (unsigned)q; }
                     }
                     publish_column(cb, &sm.col[g]);
                 }

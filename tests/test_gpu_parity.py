@@ -512,3 +512,7 @@ def test_fast_train_path_equals_generic_path(env):
                 assert bit_equal(fast[2], slow[2]), tag
                 assert bit_equal(fast[1], slow[1]), tag
                 assert torch.allclose(fast[0], slow[0], rtol=1e-12, atol=1e-9), (tag, fast[0], slow[0])
+            # and both agree with the reference semantics (device-matched oracle), exotic boxes included
+            pos_o, _, cls_o = O.batch_targets(env["pri"], env["pri_xyxy"], to_dev(targets, dev), 300, 300, thr)
+            assert bit_equal(fast[1] > 0, pos_o), (name, thr)
+            assert bit_equal(fast[1].long().clamp_min(0)[pos_o], cls_o[pos_o]), (name, thr)
