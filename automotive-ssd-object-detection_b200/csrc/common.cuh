@@ -53,9 +53,8 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
     __syncthreads();
     if (lane == 0) scratch[warp] = v;
     __syncthreads();
-    T total = T(0);
-    for (int w = 0; w < nwarp; ++w) total += scratch[w];
-    return total;
+    // every warp folds the <= 32 partials in the same butterfly order: identical in all threads
+    return warp_sum(lane < nwarp ? scratch[lane] : T(0));
 }
 
 // 128-bit read-only loads.

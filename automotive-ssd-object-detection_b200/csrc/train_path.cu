@@ -595,10 +595,10 @@ __global__ void __launch_bounds__(LT, 2) loss_image_kernel(const TrainParams prm
 // Matching is box-centric.  The priors of SSD300 sit on six regular grids (SSD_from_scratch.py:
 // 289-323), so for a ground-truth box and one (level, shape) combination the priors whose IoU can
 // reach lim (the same bound the pruned sweep of match_kernel uses) form a small rectangle of
-// cells: IoU >= lim needs  inter >= max(lim * max(a_g, a_p), lim/(1+lim) * (a_g + a_p)),
-// inter <= w_ov * min(h_p, h_g) and w_ov <= (w_p + w_g)/2 - |cx_p - cx_g|  (the clamped prior is a
-// subset of the un-clamped one, and a_p >= w_p h_p / 4 because its centre lies inside the image).
-// Those ~400 cells per box (instead of 8732 priors) pass the same cheap IoU gate as before; the
+// cells: the 2-D IoU is at most each 1-D IoU, and IoU >= lim needs inter (1 + lim) >= lim (a_p + a_g)
+// with inter <= w_ov * min(h_p, h_g); both are evaluated with the exact clamped prior extents
+// (axis_hull: closed form for interior cells, the few border-clamped cells one by one).
+// Those ~60 cells per box (instead of 8732 priors) pass the same cheap IoU gate as before; the
 // ~35 survivors get the exact CIoU and update a packed (CIoU, ~box) maximum per prior in shared
 // memory plus the packed (CIoU, ~prior) maximum per box.  Boxes the rectangles cannot handle (not
 // finite, empty, or whose best CIoU is not positive) are swept densely, exactly like the refill of
@@ -606,8 +606,8 @@ __global__ void __launch_bounds__(LT, 2) loss_image_kernel(const TrainParams prm
 //
 // The loss then streams the image's logits once.  Hard-negative mining only needs the k largest
 // cross-entropies of ~8.7k negatives, so the stream evaluates CE with ex2.approx / lg2.approx
-// (|error| <= 1e-5 + 1e-6 CE, see approx_ce6), a two-level histogram (4096 x 512 bins) brackets the
-// k-th largest approximate value in a 1024-ulp sub-bin, and only the negatives above that bracket
+// (|error| <= 1e-5 + 1e-6 CE, see approx_ce6), a 4096-bin histogram brackets the k-th largest
+// approximate value in a bin 0.4 % wide, and only the negatives above that bracket
 // and the handful inside a +-3-error band around it are re-evaluated with the exact eager-CUDA
 // arithmetic: every negative above the band is certainly among the k hardest, every one below it
 // certainly not, and the band members are ranked exactly (ties: lower prior index first).  Images
@@ -658,6 +658,18 @@ __device__ __forceinline__ float approx_ce6(float x0, float x1, float x2, float 
 }
 __device__ __forceinline__ float ce_error_bound(float ce) { return 1e-5f + 1e-6f * ce; }
 
+// Histogram bin of a CE bit pattern: 16 octaves [2^-9, 2^7) x 256 mantissa steps = 4096 bins (a bin is 0.4 % wide,
+// ~30 of 8.7k negatives); smaller / larger values share the end bins, which the selection treats as "unresolved".
+constexpr int kCeBinBase = (127 - 9) << 8;
+__device__ __forceinline__ int ce_bin(unsigned key) {
+    const int v = (int)(key >> 15) - kCeBinBase;
+    return min(max(v, 0), 4095);
+}
+__device__ __forceinline__ void ce_hist_add(unsigned* hist16, unsigned key) {
+    const int bin = ce_bin(key);
+    atomicAdd(&hist16[bin >> 1], 1u << ((bin & 1) * 16));
+}
+
 // exact CE of one row for target class cls, in eager torch-CUDA order (as loss_image_kernel)
 __device__ __forceinline__ float exact_ce6(const float* __restrict__ row, int cls) {
     float mx, lg;
@@ -703,6 +715,38 @@ __device__ __forceinline__ void find_kth_from_top(CountFn count, unsigned k, Fus
     above_out = fs.r_above;
 }
 
+// Extent of the clamped prior interval of cell i on a grid of `side` cells: [max(0, c - w/2), min(1, c + w/2)], c = (i + .5)/side
+__device__ __forceinline__ float clamped_extent(int i, int side, float w) {
+    const float c = ((float)i + 0.5f) / (float)side;
+    return fminf(1.0f, c + 0.5f * w) - fmaxf(0.0f, c - 0.5f * w);
+}
+
+// Hull [lo, hi] of the cells whose (clamped) prior interval can satisfy  ov * A >= Bc * extent + Cc,  ov = its
+// overlap with [g1, g2]; empty if hi < lo.  Un-clamped cells have extent w and ov <= min(w, gw, (w + gw)/2 - |c - gc|),
+// which gives a closed-form centre range; the few cells the image border clamps are tested one by one
+// (their extents differ).  Every comparison is slackened, so the hull errs on the inclusive side.
+__device__ __forceinline__ void axis_hull(float g1, float g2, int side, float w, float A, float Bc, float Cc, int& lo, int& hi) {
+    const float fS = (float)side, gw = g2 - g1, gc = 0.5f * (g1 + g2);
+    lo = side;
+    hi = -1;
+    const float areq = (Bc * w + Cc) / A;
+    if (fminf(w, gw) >= areq) {
+        const float r = 0.5f * (w + gw) - areq;
+        const int ia = max(0, (int)ceilf(fmaxf((gc - r) * fS - 0.51f, -1.0f)));
+        const int ib = min(side - 1, (int)floorf(fminf((gc + r) * fS - 0.49f, fS)));
+        if (ia <= ib) { lo = ia; hi = ib; }
+    }
+    const int nb = min(side, max(0, (int)ceilf(0.5f * w * fS - 0.49f)));      // cells clamped at each border
+    auto test = [&](int i) {
+        const float c = ((float)i + 0.5f) / fS;
+        const float p1 = fmaxf(0.0f, c - 0.5f * w), p2 = fminf(1.0f, c + 0.5f * w);
+        const float ov = fminf(p2, g2) - fmaxf(p1, g1);
+        if (ov > 0.0f && ov * A >= (Bc * (p2 - p1) + Cc) * 0.999f) { lo = min(lo, i); hi = max(hi, i); }
+    };
+    if (g1 < w) for (int i = 0; i < nb; ++i) test(i);
+    if (g2 > 1.0f - w) for (int i = side - nb; i < side; ++i) test(i);
+}
+
 template <bool LOSS>
 __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams prm) {
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -720,8 +764,7 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     unsigned* pair_list = reinterpret_cast<unsigned*>(scratch + 4112 + 4096 + 2048);   // [PAIR_CAP] prior | box << 16
     // mining view of the scratch
     unsigned* hist16 = reinterpret_cast<unsigned*>(scratch);                       // [2048] 4096 bins x 16 bit
-    unsigned* hist2 = hist16 + 2048;                                               // [512]
-    unsigned* band_v = hist2 + 512;                                                // [BAND_CAP] exact CE bits
+    unsigned* band_v = hist16 + 2048;                                              // [BAND_CAP] exact CE bits
     uint16_t* band_p = reinterpret_cast<uint16_t*>(band_v + BAND_CAP);             // [BAND_CAP]
 
     const int g_begin = prm.gt_offsets[b];
@@ -772,18 +815,20 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                         const float4 sh = ldg4(prm.pri + 4ll * (off + shp));           // (w, h) of this level-shape
                         const float w = sh.z, h = sh.w;
                         const float l2 = 0.99f * lim;
-                        const float mw = fminf(w, gw), mh = fminf(h, gh);
-                        const float ak4 = 0.25f * w * h;
-                        const float req = fmaxf(l2 * fmaxf(c.area, ak4), l2 / (1.0f + l2) * (c.area + ak4));
-                        if (!(mw * mh < req)) {
-                            const float rx = 0.5f * (w + gw) - req / mh, ry = 0.5f * (h + gh) - req / mw;
-                            if (rx >= 0.0f && ry >= 0.0f) {
-                                const float fsd = (float)side;
-                                const int i0 = max(0, (int)ceilf(fmaxf((c.xc - rx) * fsd - 0.51f, -1.0f)));
-                                const int i1 = min(side - 1, (int)floorf(fminf((c.xc + rx) * fsd - 0.49f, fsd)));
-                                const int j0 = max(0, (int)ceilf(fmaxf((c.yc - ry) * fsd - 0.51f, -1.0f)));
-                                const int j1 = min(side - 1, (int)floorf(fminf((c.yc + ry) * fsd - 0.49f, fsd)));
-                                if (i1 >= i0 && j1 >= j0) {
+                        // rows whose 1-D IoU with the box can reach lim (2-D IoU <= each 1-D IoU) ...
+                        int j0, j1, i0, i1, a0, a1;
+                        axis_hull(c.y1, c.y2, side, h, 1.0f + l2, l2, l2 * gh, j0, j1);
+                        if (j1 >= j0) {
+                            // ... then columns / rows that can satisfy inter (1 + lim) >= lim (a_p + a_g) given the best
+                            // overlap and the smallest clamped extent the other axis offers
+                            const float hcmin = fminf(clamped_extent(j0, side, h), clamped_extent(j1, side, h));
+                            axis_hull(c.x1, c.x2, side, w, fminf(h, gh) * (1.0f + l2), l2 * hcmin, l2 * c.area, i0, i1);
+                            if (i1 >= i0) {
+                                const float wcmin = fminf(clamped_extent(i0, side, w), clamped_extent(i1, side, w));
+                                axis_hull(c.y1, c.y2, side, h, fminf(w, gw) * (1.0f + l2), l2 * wcmin, l2 * c.area, a0, a1);
+                                j0 = max(j0, a0);
+                                j1 = min(j1, a1);
+                                if (j1 >= j0) {
                                     const int ni = i1 - i0 + 1;
                                     n = ni * (j1 - j0 + 1);
                                     info = (unsigned)i0 | ((unsigned)j0 << 6) | ((unsigned)ni << 12) | ((unsigned)side << 18) | ((unsigned)shapes << 24);
@@ -959,7 +1004,7 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     }
 
     // ---- 3. stream the logits: approximate CE of every negative, first-level histogram ------------
-    for (int i = tid; i < 2048 + 512; i += FT) hist16[i] = 0u;        // hist16 and hist2 (the scratch changes role)
+    for (int i = tid; i < 2048; i += FT) hist16[i] = 0u;              // (the scratch changes role)
     __syncthreads();
     const float* conf_b = prm.conf_all + (long long)b * P * 6;
     double acc_loc = 0.0, acc_ce = 0.0;
@@ -993,12 +1038,12 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
             if (!pos0) {
                 const unsigned key = __float_as_uint(approx_ce6(A.x, A.y, A.z, A.w, Bv.x, Bv.y));
                 slots.x = (unsigned long long)key;
-                atomicAdd(&hist16[key >> 20], 1u << (((key >> 19) & 1u) * 16));
+                ce_hist_add(hist16, key);
             }
             if (!pos1) {
                 const unsigned key = __float_as_uint(approx_ce6(Bv.z, Bv.w, Cv.x, Cv.y, Cv.z, Cv.w));
                 slots.y = (unsigned long long)key;
-                atomicAdd(&hist16[key >> 20], 1u << (((key >> 19) & 1u) * 16));
+                ce_hist_add(hist16, key);
             }
             t2[q] = slots;
             if (prm.sel_cls) {
@@ -1029,7 +1074,7 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                 const float* r = conf_b + 6ll * p;
                 const unsigned key = __float_as_uint(approx_ce6(r[0], r[1], r[2], r[3], r[4], r[5]));
                 table[p] = (unsigned long long)key;
-                atomicAdd(&hist16[key >> 20], 1u << (((key >> 19) & 1u) * 16));
+                ce_hist_add(hist16, key);
             }
         }
     }
@@ -1052,18 +1097,11 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     const long long kk = want < n_neg ? want : n_neg;
     bool exact_all = kk >= n_neg && kk > 0;
     if (kk > 0 && !exact_all) {
-        unsigned b1, above1, b2, above2;
+        unsigned b1, above1;
         find_kth_from_top<FT, 4096>([&](int bin) { return (hist16[bin >> 1] >> ((bin & 1) * 16)) & 0xffffu; }, (unsigned)kk, fs, b1, above1);
-        for (int p = tid; p < P; p += FT) {
-            const unsigned long long slot = table[p];
-            const unsigned key = (unsigned)slot;
-            if ((slot >> 32) == 0ull && (key >> 19) == b1) atomicAdd(&hist2[(key >> 10) & 511u], 1u);
-        }
-        __syncthreads();
-        find_kth_from_top<FT, 512>([&](int bin) { return hist2[bin]; }, (unsigned)kk - above1, fs, b2, above2);
-        const unsigned lo_key = (b1 << 19) | (b2 << 10), hi_key = lo_key | 1023u;
+        const unsigned lo_key = (b1 + (unsigned)kCeBinBase) << 15, hi_key = lo_key | 0x7fffu;
         const float t_lo = __uint_as_float(lo_key), t_hi = __uint_as_float(hi_key);
-        if (!(t_hi < 1e30f)) exact_all = true;          // inf / NaN bracket: CTA-uniform
+        if (b1 == 0u || b1 == 4095u) exact_all = true;  // the k-th value lies outside the resolved range: CTA-uniform
         else {
             const float band_lo = t_lo - 3.0f * ce_error_bound(t_lo), band_hi = t_hi + 3.0f * ce_error_bound(t_hi);
             // certain members (above the band) and band members, compacted
