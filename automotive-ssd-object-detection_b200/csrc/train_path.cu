@@ -619,11 +619,11 @@ constexpr int FAST_MAX_GT = 64;
 constexpr int GT_ROUND = 32;                 // boxes enumerated per round
 constexpr int NSEG = GT_ROUND * 32;          // (box, level-shape) segments per round
 constexpr int PAIR_CAP = 2048;               // gate survivors staged for the exact pass (rest: inline)
-constexpr int POS_CAP = 2048;
-constexpr int SEL_CAP = 2048;
+constexpr int POS_PER_WARP = 80;             // per-warp list of positive priors (rest: handled inline)
+constexpr int SEL_PER_WARP = 168;            // per-warp list of certainly-mined negatives
 constexpr int BAND_CAP = 1024;
 constexpr unsigned kOrdTwo = 0xC0000000u;    // ord_encode(2.0f): the forced-match value (SFS:747)
-constexpr int FUSED_SCRATCH = 20480;
+constexpr int FUSED_SCRATCH = 4112 + 8192 + 4 * PAIR_CAP + 2 * NSEG;     // 22544
 
 struct FusedStatic {
     float4 gt_a[FAST_MAX_GT];                // x1 y1 x2 y2 (normalised)
@@ -634,12 +634,13 @@ struct FusedStatic {
     int champ[FAST_MAX_GT];
     unsigned char kind[FAST_MAX_GT];         // 0 = rectangles, 1 = dense sweep, 2 = all-NaN column
     LossShared ls;
-    int first_nan, n_dense, n_pair, n_poslist, n_sel, n_band;
+    int first_nan, n_dense, n_pair, n_work, n_band, n_sure;
+    int wcount[FT / 32];                     // per-warp list lengths (positives, then certain negatives)
     unsigned r_bin, r_above;
 };
 
 __host__ __device__ inline size_t fused_smem_bytes(int P) {
-    return (size_t)P * 8 + FUSED_SCRATCH + (size_t)POS_CAP * 2 + (size_t)SEL_CAP * 2;
+    return (size_t)P * 8 + FUSED_SCRATCH + (size_t)(FT / 32) * (POS_PER_WARP + SEL_PER_WARP) * 2;
 }
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -756,16 +757,18 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     unsigned long long* table = reinterpret_cast<unsigned long long*>(dyn);        // [P] (ord(ciou) << 32 | ~box); later (0, CE bits)
     unsigned char* scratch = dyn + (size_t)P * 8;
     uint16_t* pos_list = reinterpret_cast<uint16_t*>(scratch + FUSED_SCRATCH);
-    uint16_t* sel_list = pos_list + POS_CAP;
+    uint16_t* sel_list = pos_list + (FT / 32) * POS_PER_WARP;
     // matching view of the scratch
     int* seg_start = reinterpret_cast<int*>(scratch);                              // [NSEG + 1] (+ pad to 4112 B)
     unsigned* seg_info = reinterpret_cast<unsigned*>(scratch + 4112);              // [NSEG] i0 | j0<<6 | ni<<12 | side<<18 | shapes<<24
-    uint16_t* seg_base = reinterpret_cast<uint16_t*>(scratch + 4112 + 4096);       // [NSEG] first prior of the (level, shape)
-    unsigned* pair_list = reinterpret_cast<unsigned*>(scratch + 4112 + 4096 + 2048);   // [PAIR_CAP] prior | box << 16
+    unsigned* seg_base = reinterpret_cast<unsigned*>(scratch + 4112 + 4096);       // [NSEG] first prior of the (level, shape) | box << 16
+    unsigned* pair_list = reinterpret_cast<unsigned*>(scratch + 4112 + 8192);      // [PAIR_CAP] prior | box << 16
+    uint16_t* work_list = reinterpret_cast<uint16_t*>(scratch + 4112 + 8192 + 4 * PAIR_CAP);   // [NSEG] (box in round) << 5 | level-shape
     // mining view of the scratch
     unsigned* hist16 = reinterpret_cast<unsigned*>(scratch);                       // [2048] 4096 bins x 16 bit
     unsigned* band_v = hist16 + 2048;                                              // [BAND_CAP] exact CE bits
-    uint16_t* band_p = reinterpret_cast<uint16_t*>(band_v + BAND_CAP);             // [BAND_CAP]
+    unsigned* band_sorted = band_v + BAND_CAP;                                     // [BAND_CAP] the band's winners by rank
+    uint16_t* band_p = reinterpret_cast<uint16_t*>(band_sorted + BAND_CAP);        // [BAND_CAP]
 
     const int g_begin = prm.gt_offsets[b];
     int G = prm.gt_offsets[b + 1] - g_begin;
@@ -775,7 +778,7 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     }
 
     // ---- 0. clear ------------------------------------------------------------------------------
-    if (tid == 0) { fs.first_nan = INT_MAX; fs.n_dense = 0; fs.n_poslist = 0; fs.n_sel = 0; fs.n_band = 0; }
+    if (tid == 0) { fs.first_nan = INT_MAX; fs.n_dense = 0; fs.n_band = 0; }
     __syncthreads();
     {
         ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
@@ -788,71 +791,92 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     for (int g0 = 0; g0 < G; g0 += GT_ROUND) {
         const int gn = min(GT_ROUND, G - g0);
         if (tid == 0) fs.n_pair = 0;
-        // 1a. one warp per box: constants, seed bound, candidate rectangles of the 30 (level, shape) combos
-        for (int gl = warp; gl < GT_ROUND; gl += FT / 32) {
-            int n = 0, base = 0;
-            unsigned info = 0u;
-            if (gl < gn) {
-                const int g = g0 + gl;
-                const float4 px = ldg4(prm.gt_boxes + 4ll * (g_begin + g));
-                const BoxC c = box_consts(fdiv(px.x, prm.norm_w), fdiv(px.y, prm.norm_h), fdiv(px.z, prm.norm_w), fdiv(px.w, prm.norm_h), true);
-                const float gw = fsub(c.x2, c.x1), gh = fsub(c.y2, c.y1);
-                int kind = 0;
-                if (c.at != c.at) kind = 2;
-                else if (!(gw > 0.0f && gh > 0.0f) || !(fabsf(c.x1) < 1e30f && fabsf(c.y1) < 1e30f && fabsf(c.x2) < 1e30f && fabsf(c.y2) < 1e30f)) kind = 1;
-                float lim = 1e-30f;
-                if (kind == 0) {
-                    const int lv = kSeedLevel[lane], side = kLevelSide[lv], shapes = kLevelShapes[lv], off = kLevelOffset[lv];
-                    const int shp = kSeedShape[lane];
-                    int ix = (int)floorf(c.xc * (float)side), iy = (int)floorf(c.yc * (float)side);
-                    ix = min(max(ix, 0), side - 1);
-                    iy = min(max(iy, 0), side - 1);
-                    const int ps = off + (iy * side + ix) * shapes + shp;
-                    const float v = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, ps), c);
-                    const float cb0 = ord_decode(__reduce_max_sync(FULL, ord_encode(v)));
-                    if (cb0 > 0.0f) lim = fmaxf(fmul(kPruneSlack, fminf(cb0, thresh)), 1e-30f);
-                    if (lane < 30) {
-                        const float4 sh = ldg4(prm.pri + 4ll * (off + shp));           // (w, h) of this level-shape
-                        const float w = sh.z, h = sh.w;
-                        const float l2 = 0.99f * lim;
-                        // rows whose 1-D IoU with the box can reach lim (2-D IoU <= each 1-D IoU) ...
-                        int j0, j1, i0, i1, a0, a1;
-                        axis_hull(c.y1, c.y2, side, h, 1.0f + l2, l2, l2 * gh, j0, j1);
-                        if (j1 >= j0) {
-                            // ... then columns / rows that can satisfy inter (1 + lim) >= lim (a_p + a_g) given the best
-                            // overlap and the smallest clamped extent the other axis offers
-                            const float hcmin = fminf(clamped_extent(j0, side, h), clamped_extent(j1, side, h));
-                            axis_hull(c.x1, c.x2, side, w, fminf(h, gh) * (1.0f + l2), l2 * hcmin, l2 * c.area, i0, i1);
-                            if (i1 >= i0) {
-                                const float wcmin = fminf(clamped_extent(i0, side, w), clamped_extent(i1, side, w));
-                                axis_hull(c.y1, c.y2, side, h, fminf(w, gw) * (1.0f + l2), l2 * wcmin, l2 * c.area, a0, a1);
-                                j0 = max(j0, a0);
-                                j1 = min(j1, a1);
-                                if (j1 >= j0) {
-                                    const int ni = i1 - i0 + 1;
-                                    n = ni * (j1 - j0 + 1);
-                                    info = (unsigned)i0 | ((unsigned)j0 << 6) | ((unsigned)ni << 12) | ((unsigned)side << 18) | ((unsigned)shapes << 24);
-                                    base = off + shp;
-                                }
+        // 1a. one warp per box: constants, seed bound, and the (level, shape) combinations whose sizes can
+        //     reach IoU >= lim at all (1-D and area ratios, clamped extents >= half the nominal ones)
+        if (tid == 0) fs.n_work = 0;
+        __syncthreads();
+        for (int gl = warp; gl < gn; gl += FT / 32) {
+            const int g = g0 + gl;
+            const float4 px = ldg4(prm.gt_boxes + 4ll * (g_begin + g));
+            const BoxC c = box_consts(fdiv(px.x, prm.norm_w), fdiv(px.y, prm.norm_h), fdiv(px.z, prm.norm_w), fdiv(px.w, prm.norm_h), true);
+            const float gw = fsub(c.x2, c.x1), gh = fsub(c.y2, c.y1);
+            int kind = 0;
+            if (c.at != c.at) kind = 2;
+            else if (!(gw > 0.0f && gh > 0.0f) || !(fabsf(c.x1) < 1e30f && fabsf(c.y1) < 1e30f && fabsf(c.x2) < 1e30f && fabsf(c.y2) < 1e30f)) kind = 1;
+            float lim = 1e-30f;
+            if (kind == 0) {
+                const int lv = kSeedLevel[lane], side = kLevelSide[lv], shapes = kLevelShapes[lv], off = kLevelOffset[lv];
+                const int shp = kSeedShape[lane];
+                int ix = (int)floorf(c.xc * (float)side), iy = (int)floorf(c.yc * (float)side);
+                ix = min(max(ix, 0), side - 1);
+                iy = min(max(iy, 0), side - 1);
+                const int ps = off + (iy * side + ix) * shapes + shp;
+                const float v = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, ps), c);
+                const float cb0 = ord_decode(__reduce_max_sync(FULL, ord_encode(v)));
+                if (cb0 > 0.0f) lim = fmaxf(fmul(kPruneSlack, fminf(cb0, thresh)), 1e-30f);
+                const float4 sh = ldg4(prm.pri + 4ll * (off + shp));                   // (w, h) of this level-shape
+                const float w = sh.z, h = sh.w, l2 = 0.99f * lim;
+                const bool keep = lane < 30 && !(gw < l2 * 0.5f * w || w < l2 * gw || gh < l2 * 0.5f * h || h < l2 * gh ||
+                                                 c.area < l2 * 0.25f * w * h || w * h < l2 * c.area);
+                const unsigned bal = __ballot_sync(FULL, keep);
+                int dst = 0;
+                if (lane == 0 && bal) dst = atomicAdd(&fs.n_work, __popc(bal));
+                dst = __shfl_sync(FULL, dst, 0) + __popc(bal & ((1u << lane) - 1u));
+                if (keep) work_list[dst] = (uint16_t)((gl << 5) | lane);
+            }
+            if (lane == 0) {
+                fs.gt_a[g] = make_float4(c.x1, c.y1, c.x2, c.y2);
+                fs.gt_b[g] = make_float4(c.area, c.xc, c.yc, c.at);
+                fs.lim[g] = lim;
+                fs.label[g] = (int)prm.gt_labels[g_begin + g];
+                fs.col[g] = 0ull;
+                fs.champ[g] = 0;
+                fs.kind[g] = (unsigned char)kind;
+                if (kind == 2) atomicMin(&fs.first_nan, g);
+                if (kind == 1) atomicAdd(&fs.n_dense, 1);
+            }
+        }
+        __syncthreads();
+        // 1a'. one thread per surviving (box, level-shape): its rectangle of candidate cells
+        {
+            const int n_work = fs.n_work;
+            for (int e = tid; e < NSEG; e += FT) {
+                int n = 0;
+                unsigned info = 0u, base = 0u;
+                if (e < n_work) {
+                    const int wk = (int)work_list[e], g = g0 + (wk >> 5), combo = wk & 31;
+                    const int lv = kSeedLevel[combo], side = kLevelSide[lv], shapes = kLevelShapes[lv], off = kLevelOffset[lv];
+                    const int shp = kSeedShape[combo];
+                    const float4 sh = ldg4(prm.pri + 4ll * (off + shp));
+                    const float w = sh.z, h = sh.w, l2 = 0.99f * fs.lim[g];
+                    const float4 ga = fs.gt_a[g];
+                    const float gw = ga.z - ga.x, gh = ga.w - ga.y, ag = fs.gt_b[g].x;
+                    // rows whose 1-D IoU with the box can reach lim (2-D IoU <= each 1-D IoU) ...
+                    int j0, j1, i0, i1, a0, a1;
+                    axis_hull(ga.y, ga.w, side, h, 1.0f + l2, l2, l2 * gh, j0, j1);
+                    if (j1 >= j0) {
+                        // ... then columns / rows that can satisfy inter (1 + lim) >= lim (a_p + a_g) given the best
+                        // overlap and the smallest clamped extent the other axis offers
+                        const float hcmin = fminf(clamped_extent(j0, side, h), clamped_extent(j1, side, h));
+                        axis_hull(ga.x, ga.z, side, w, fminf(h, gh) * (1.0f + l2), l2 * hcmin, l2 * ag, i0, i1);
+                        if (i1 >= i0) {
+                            const float wcmin = fminf(clamped_extent(i0, side, w), clamped_extent(i1, side, w));
+                            axis_hull(ga.y, ga.w, side, h, fminf(w, gw) * (1.0f + l2), l2 * wcmin, l2 * ag, a0, a1);
+                            j0 = max(j0, a0);
+                            j1 = min(j1, a1);
+                            if (j1 >= j0) {
+                                const int ni = i1 - i0 + 1;
+                                n = ni * (j1 - j0 + 1);
+                                info = (unsigned)i0 | ((unsigned)j0 << 6) | ((unsigned)ni << 12) | ((unsigned)side << 18) | ((unsigned)shapes << 24);
+                                base = (unsigned)(off + shp) | ((unsigned)g << 16);
                             }
                         }
                     }
                 }
-                if (lane == 0) {
-                    fs.gt_a[g] = make_float4(c.x1, c.y1, c.x2, c.y2);
-                    fs.gt_b[g] = make_float4(c.area, c.xc, c.yc, c.at);
-                    fs.lim[g] = lim;
-                    fs.label[g] = (int)prm.gt_labels[g_begin + g];
-                    fs.col[g] = 0ull;
-                    fs.champ[g] = 0;
-                    fs.kind[g] = (unsigned char)kind;
-                    if (kind == 2) atomicMin(&fs.first_nan, g);
-                    if (kind == 1) atomicAdd(&fs.n_dense, 1);
-                }
+                seg_start[e] = n;
+                seg_info[e] = info;
+                seg_base[e] = base;
             }
-            seg_start[gl * 32 + lane] = n;
-            seg_info[gl * 32 + lane] = info;
-            seg_base[gl * 32 + lane] = (uint16_t)base;
         }
         __syncthreads();
         // 1b. exclusive scan of the NSEG segment sizes (two per thread, threads 0..511)
@@ -896,8 +920,9 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                 const int local = t - seg_start[lo];
                 const int ni = (int)((info >> 12) & 63u), side = (int)((info >> 18) & 63u), shapes = (int)(info >> 24);
                 const int lj = local / ni, li = local - lj * ni;
-                p = (int)seg_base[lo] + (((int)((info >> 6) & 63u) + lj) * side + (int)(info & 63u) + li) * shapes;
-                g = g0 + (lo >> 5);
+                const unsigned sb = seg_base[lo];
+                p = (int)(sb & 0xffffu) + (((int)((info >> 6) & 63u) + lj) * side + (int)(info & 63u) + li) * shapes;
+                g = (int)(sb >> 16);
                 const float4 pb = ldg4(prm.pri_xyxy + 4ll * p);
                 const float pa = __ldg(prm.pri_aux + 4ll * p);
                 const float4 ga = fs.gt_a[g];
@@ -1024,46 +1049,73 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
             acc_loc += (double)(z < 1.0f ? fmul(fmul(0.5f, z), z) : fsub(z, 0.5f));
         }
     };
+    // Lists are kept per warp (fixed-size segments, filled in prior order) and consumed in the canonical
+    // concatenation order, so every thread adds the same terms in the same order on every run.
+    auto list_locate = [&](int e, int per_warp, const uint16_t* lists, int& p) {
+        int run = 0;
+        for (int w = 0; w < FT / 32; ++w) {
+            const int c = fs.wcount[w];
+            if (e < run + c) { p = (int)lists[w * per_warp + (e - run)]; return true; }
+            run += c;
+        }
+        return false;
+    };
+    const unsigned lt = (1u << lane) - 1u;
     {
         const float4* src = reinterpret_cast<const float4*>(conf_b);
         ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
+        uint16_t* my_list = pos_list + warp * POS_PER_WARP;
+        int wpos = 0;                                    // warp-uniform
+        const int n_pairs = P / 2;
 #pragma unroll 2
-        for (int q = tid; q < P / 2; q += FT) {
-            const float4 A = __ldg(src + 3 * q), Bv = __ldg(src + 3 * q + 1), Cv = __ldg(src + 3 * q + 2);
-            ulonglong2 slots = t2[q];
+        for (int qb = warp * 32; qb < n_pairs; qb += FT) {
+            const int q = qb + lane;
+            const bool live = q < n_pairs;
             const int p0 = 2 * q;
-            const bool pos0 = G > 0 && positive((unsigned)(slots.x >> 32), p0);
-            const bool pos1 = G > 0 && positive((unsigned)(slots.y >> 32), p0 + 1);
-            const long long row = (long long)b * P + p0;
-            if (!pos0) {
-                const unsigned key = __float_as_uint(approx_ce6(A.x, A.y, A.z, A.w, Bv.x, Bv.y));
-                slots.x = (unsigned long long)key;
-                ce_hist_add(hist16, key);
-            }
-            if (!pos1) {
-                const unsigned key = __float_as_uint(approx_ce6(Bv.z, Bv.w, Cv.x, Cv.y, Cv.z, Cv.w));
-                slots.y = (unsigned long long)key;
-                ce_hist_add(hist16, key);
-            }
-            t2[q] = slots;
-            if (prm.sel_cls) {
-                const int g0 = (int)(0xffffffffu - (unsigned)(slots.x & 0xffffffffull));
-                const int g1 = (int)(0xffffffffu - (unsigned)(slots.y & 0xffffffffull));
-                prm.sel_cls[row] = pos0 ? (int8_t)(fs.label[g0] + 1) : (int8_t)-1;
-                prm.sel_cls[row + 1] = pos1 ? (int8_t)(fs.label[g1] + 1) : (int8_t)-1;
-                if (prm.matched16) { prm.matched16[row] = pos0 ? (int16_t)g0 : (int16_t)-1; prm.matched16[row + 1] = pos1 ? (int16_t)g1 : (int16_t)-1; }
-            }
-            if (pos0 || pos1) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (!(h ? pos1 : pos0)) continue;
-                    my_pos += 1;
-                    const int dst = atomicAdd(&fs.n_poslist, 1);
-                    if (dst < POS_CAP) pos_list[dst] = (uint16_t)(p0 + h);
-                    else positive_terms(p0 + h, (int)(0xffffffffu - (unsigned)((h ? slots.y : slots.x) & 0xffffffffull)));
+            bool pos0 = false, pos1 = false;
+            ulonglong2 slots = make_ulonglong2(0ull, 0ull);
+            if (live) {
+                const float4 A = __ldg(src + 3 * q), Bv = __ldg(src + 3 * q + 1), Cv = __ldg(src + 3 * q + 2);
+                slots = t2[q];
+                pos0 = G > 0 && positive((unsigned)(slots.x >> 32), p0);
+                pos1 = G > 0 && positive((unsigned)(slots.y >> 32), p0 + 1);
+                if (!pos0) {
+                    const unsigned key = __float_as_uint(approx_ce6(A.x, A.y, A.z, A.w, Bv.x, Bv.y));
+                    slots.x = (unsigned long long)key;
+                    ce_hist_add(hist16, key);
+                }
+                if (!pos1) {
+                    const unsigned key = __float_as_uint(approx_ce6(Bv.z, Bv.w, Cv.x, Cv.y, Cv.z, Cv.w));
+                    slots.y = (unsigned long long)key;
+                    ce_hist_add(hist16, key);
+                }
+                t2[q] = slots;
+                if (prm.sel_cls) {
+                    const long long row = (long long)b * P + p0;
+                    const int g0 = (int)(0xffffffffu - (unsigned)(slots.x & 0xffffffffull));
+                    const int g1 = (int)(0xffffffffu - (unsigned)(slots.y & 0xffffffffull));
+                    prm.sel_cls[row] = pos0 ? (int8_t)(fs.label[g0] + 1) : (int8_t)-1;
+                    prm.sel_cls[row + 1] = pos1 ? (int8_t)(fs.label[g1] + 1) : (int8_t)-1;
+                    if (prm.matched16) { prm.matched16[row] = pos0 ? (int16_t)g0 : (int16_t)-1; prm.matched16[row + 1] = pos1 ? (int16_t)g1 : (int16_t)-1; }
                 }
             }
+            if (__any_sync(FULL, pos0 || pos1)) {
+                const unsigned b0 = __ballot_sync(FULL, pos0), b1 = __ballot_sync(FULL, pos1);
+                int at = wpos + __popc(b0 & lt) + __popc(b1 & lt);
+                if (pos0) {
+                    if (at < POS_PER_WARP) my_list[at] = (uint16_t)p0;
+                    else positive_terms(p0, (int)(0xffffffffu - (unsigned)(slots.x & 0xffffffffull)));
+                    ++at;
+                }
+                if (pos1) {
+                    if (at < POS_PER_WARP) my_list[at] = (uint16_t)(p0 + 1);
+                    else positive_terms(p0 + 1, (int)(0xffffffffu - (unsigned)(slots.y & 0xffffffffull)));
+                }
+                wpos += __popc(b0) + __popc(b1);
+                my_pos += (pos0 ? 1 : 0) + (pos1 ? 1 : 0);
+            }
         }
+        if (lane == 0) fs.wcount[warp] = min(wpos, POS_PER_WARP);
         if ((P & 1) && tid == 0) {                      // odd P: the last row (never SSD300)
             const int p = P - 1;
             const unsigned long long slot = table[p];
@@ -1075,19 +1127,18 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                 const unsigned key = __float_as_uint(approx_ce6(r[0], r[1], r[2], r[3], r[4], r[5]));
                 table[p] = (unsigned long long)key;
                 ce_hist_add(hist16, key);
+                if (prm.sel_cls) { prm.sel_cls[(long long)b * P + p] = -1; if (prm.matched16) prm.matched16[(long long)b * P + p] = -1; }
             }
         }
     }
     const int n_pos_img = block_sum<int>(my_pos, fs.ls.iscratch);      // two barriers: slots, lists and hist16 are complete
-    if (tid == 0 && prm.n_pos) prm.n_pos[b] = n_pos_img;
+    if (tid == 0) { if (prm.n_pos) prm.n_pos[b] = n_pos_img; fs.n_sure = 0; }
 
-    // positives (dense: one list entry per thread)
-    {
-        const int n_list = min(fs.n_poslist, POS_CAP);
-        for (int e = tid; e < n_list; e += FT) {
-            const int p = (int)pos_list[e];
-            positive_terms(p, (int)(0xffffffffu - (unsigned)(table[p] & 0xffffffffull)));
-        }
+    // positives: one list entry per thread
+    for (int e = tid;; e += FT) {
+        int p;
+        if (!list_locate(e, POS_PER_WARP, pos_list, p)) break;
+        positive_terms(p, (int)(0xffffffffu - (unsigned)(table[p] & 0xffffffffull)));
     }
 
     // ---- 4. hard negatives -----------------------------------------------------------------------
@@ -1103,46 +1154,45 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
         const float t_lo = __uint_as_float(lo_key), t_hi = __uint_as_float(hi_key);
         if (b1 == 0u || b1 == 4095u) exact_all = true;  // the k-th value lies outside the resolved range: CTA-uniform
         else {
-            const float band_lo = t_lo - 3.0f * ce_error_bound(t_lo), band_hi = t_hi + 3.0f * ce_error_bound(t_hi);
-            // certain members (above the band) and band members, compacted
-            for (int base = 0; base < P; base += FT) {
-                const int p = base + tid;
+            const float band_lo = fmaxf(t_lo - 3.0f * ce_error_bound(t_lo), 0.0f), band_hi = t_hi + 3.0f * ce_error_bound(t_hi);
+            const unsigned band_lo_key = __float_as_uint(band_lo), band_hi_key = __float_as_uint(band_hi);
+            // certain members (above the band) -> per-warp lists; band members -> one short list
+            uint16_t* my_list = sel_list + warp * SEL_PER_WARP;
+            int wsel = 0;                                // warp-uniform
+            for (int base = warp * 32; base < P; base += FT) {
+                const int p = base + lane;
                 bool sure = false, band = false;
                 if (p < P) {
                     const unsigned long long slot = table[p];
-                    if ((slot >> 32) == 0ull) {
-                        const float ce = __uint_as_float((unsigned)slot);
-                        sure = ce > band_hi;
-                        band = !sure && ce >= band_lo;
-                    }
+                    const unsigned key = (unsigned)slot;         // CE >= 0: bit order = value order
+                    if ((slot >> 32) == 0ull && key >= band_lo_key) { sure = key > band_hi_key; band = !sure; }
                 }
-                const unsigned bs = __ballot_sync(FULL, sure), bb = __ballot_sync(FULL, band);
-                const unsigned lt = (1u << lane) - 1u;
-                if (bs) {
-                    int dst = 0;
-                    if (lane == 0) dst = atomicAdd(&fs.n_sel, __popc(bs));
-                    dst = __shfl_sync(FULL, dst, 0) + __popc(bs & lt);
+                if (__any_sync(FULL, sure || band)) {
+                    const unsigned bs = __ballot_sync(FULL, sure);
                     if (sure) {
-                        if (dst < SEL_CAP) sel_list[dst] = (uint16_t)p;
+                        const int at = wsel + __popc(bs & lt);
+                        if (at < SEL_PER_WARP) my_list[at] = (uint16_t)p;
                         else {
                             acc_ce += (double)exact_ce6(conf_b + 6ll * p, 0);
                             if (prm.sel_cls) prm.sel_cls[(long long)b * P + p] = 0;
                         }
                     }
-                }
-                if (bb) {
-                    int dst = 0;
-                    if (lane == 0) dst = atomicAdd(&fs.n_band, __popc(bb));
-                    dst = __shfl_sync(FULL, dst, 0) + __popc(bb & lt);
-                    if (band && dst < BAND_CAP) band_p[dst] = (uint16_t)p;
+                    wsel += __popc(bs);
+                    if (band) {
+                        const int dst = atomicAdd(&fs.n_band, 1);
+                        if (dst < BAND_CAP) band_p[dst] = (uint16_t)p;
+                    }
                 }
             }
+            __syncthreads();                             // the positives pass is done with wcount
+            if (lane == 0) { fs.wcount[warp] = min(wsel, SEL_PER_WARP); atomicAdd(&fs.n_sure, wsel); }
             __syncthreads();
-            const int n_sure = fs.n_sel, n_band = fs.n_band;
-            if (n_band > BAND_CAP) exact_all = true;     // (massive ties): CTA-uniform; the partial sums below are discarded
+            const int n_sure = fs.n_sure, n_band = fs.n_band;
+            if (n_band > BAND_CAP) exact_all = true;     // (massive ties): CTA-uniform; the partial sums are discarded below
             else {
-                for (int e = tid; e < min(n_sure, SEL_CAP); e += FT) {
-                    const int p = (int)sel_list[e];
+                for (int e = tid;; e += FT) {
+                    int p;
+                    if (!list_locate(e, SEL_PER_WARP, sel_list, p)) break;
                     acc_ce += (double)exact_ce6(conf_b + 6ll * p, 0);
                     if (prm.sel_cls) prm.sel_cls[(long long)b * P + p] = 0;
                 }
@@ -1159,10 +1209,12 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                         rank += (vj > v || (vj == v && (int)band_p[j] < p)) ? 1 : 0;
                     }
                     if (rank < r) {
-                        acc_ce += (double)__uint_as_float(v);
+                        band_sorted[rank] = v;           // ranks are distinct: (value, prior) is a total order
                         if (prm.sel_cls) prm.sel_cls[(long long)b * P + p] = 0;
                     }
                 }
+                __syncthreads();
+                for (int e = tid; e < r; e += FT) acc_ce += (double)__uint_as_float(band_sorted[e]);
             }
         }
     }
