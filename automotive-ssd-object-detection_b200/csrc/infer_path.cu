@@ -77,22 +77,29 @@ __device__ __forceinline__ bool suppresses(const BoxC& S, const BoxC& c, float t
 
 // ---- candidate sources ---------------------------------------------------------------------------
 // A source is the set of candidates of one unit: entry i carries a 32-bit order-preserving key
-// (0 = absent / consumed) and a candidate id.
+// (0 = absent / consumed) and a candidate id.  for_each visits every entry once, spread over the CTA.
 struct DenseSource {           // key array indexed by candidate id (stand-alone NMS; shared memory)
     unsigned* keys; int n;
-    __device__ __forceinline__ int size() const { return n; }
-    __device__ __forceinline__ unsigned long long raw(int i) const { return keys[i]; }
+    template <int NT, typename F>
+    __device__ __forceinline__ void for_each(F f) const { for (int i = threadIdx.x; i < n; i += NT) f(i, (unsigned long long)keys[i]); }
     __device__ __forceinline__ void consume(int i) const { keys[i] = 0u; }
+    __device__ __forceinline__ void replace(int i, unsigned long long r) const { keys[i] = (unsigned)r; }
     static __device__ __forceinline__ unsigned key(unsigned long long r) { return (unsigned)r; }
     static __device__ __forceinline__ unsigned long long sortkey(unsigned long long r, int i) {
         return (r << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
     }
 };
-struct ListSource {            // compact list of (key << 32 | ~id) written by score_kernel (global memory)
-    unsigned long long* list; int n;
-    __device__ __forceinline__ int size() const { return n; }
-    __device__ __forceinline__ unsigned long long raw(int i) const { return list[i]; }
-    __device__ __forceinline__ void consume(int i) const { list[i] = 0ull; }
+constexpr int SEGS = 32;       // list segments per image = warps of score_kernel per image = warps of nms_image_kernel
+struct SegSource {             // 32 per-warp segments of (key << 32 | ~id) written by score_kernel (global memory)
+    unsigned long long* base; const int* counts; int seg_cap;
+    template <int NT, typename F>
+    __device__ __forceinline__ void for_each(F f) const {
+        static_assert(NT == SEGS * 32, "one warp per segment");
+        const int seg = threadIdx.x >> 5, lane = threadIdx.x & 31, c = counts[seg];
+        for (int j = lane; j < c; j += 32) { const int i = seg * seg_cap + j; f(i, base[i]); }
+    }
+    __device__ __forceinline__ void consume(int i) const { base[i] = 0ull; }
+    __device__ __forceinline__ void replace(int i, unsigned long long r) const { base[i] = r; }
     static __device__ __forceinline__ unsigned key(unsigned long long r) { return (unsigned)(r >> 32); }
     static __device__ __forceinline__ unsigned long long sortkey(unsigned long long r, int) { return r; }
 };
@@ -173,10 +180,10 @@ __device__ __forceinline__ void hist_cut(unsigned* hist16, int cap, UnitShared& 
     }
 }
 
-// Radix select of the K-th largest of the non-zero 32-bit keys keyfn(0..n).  Returns the key, how
-// many entries equal to it are needed (`need`) and how many exist (`eq`).
-template <int NT, typename KeyFn>
-__device__ __forceinline__ void select_kth(int n, KeyFn keyfn, unsigned K, UnitShared& us,
+// Radix select of the K-th largest of the non-zero 32-bit keys keyfn(i, raw) over the entries of src.
+// Returns the key, how many entries equal to it are needed (`need`) and how many exist (`eq`).
+template <int NT, typename Src, typename KeyFn>
+__device__ __forceinline__ void select_kth(const Src& src, KeyFn keyfn, unsigned K, UnitShared& us,
                                            unsigned& thr, unsigned& need, unsigned& eq) {
     const int tid = threadIdx.x;
     unsigned prefix = 0u, remaining = K, count_eq = 0u;
@@ -185,10 +192,10 @@ __device__ __forceinline__ void select_kth(int n, KeyFn keyfn, unsigned K, UnitS
         const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
         for (int i = tid; i < 256; i += NT) us.hist[i] = 0u;
         __syncthreads();
-        for (int i = tid; i < n; i += NT) {
-            const unsigned k = keyfn(i);
+        src.template for_each<NT>([&](int i, unsigned long long r) {
+            const unsigned k = keyfn(i, r);
             if (k != 0u && (k & himask) == prefix) atomicAdd(&us.hist[(k >> shift) & 255u], 1u);
-        }
+        });
         __syncthreads();
         if (tid < 32) {
             unsigned mine = 0u;
@@ -262,23 +269,39 @@ __device__ __forceinline__ void bitonic_desc_256(unsigned long long* keys) {
 // returns the number of survivors (valid in every thread)
 struct UnitBuffers {
     unsigned* hist16; unsigned long long* ckey; BoxC* cbox; unsigned char* cgroup;
-    BoxC* kept; unsigned short* kidx; int* ngroup; unsigned long long* cmask;
+    BoxC* kept; unsigned short* kidx; int* ngroup; unsigned long long* cmask; int* cidx;
 };
 
-template <int METRIC, int NT, bool GROUPS, bool HIST, typename Src, typename Fetch, typename Group, typename Emit>
+template <int METRIC, int NT, bool GROUPS, bool HIST, bool APPROX, typename Src, typename Fetch, typename Group, typename Emit, typename ExactKey>
 __device__ int nms_unit(const Src src, const UnitBuffers buf, int n_cand, int n_groups, int max_keep, float thr,
-                        UnitShared& us, Fetch fetch, Group group_of, Emit emit) {
+                        UnitShared& us, Fetch fetch, Group group_of, Emit emit, ExactKey exact_key) {
     static_assert(NT >= CHUNK, "one thread per chunk entry in the sort");
     constexpr int SUB = NT / TILE;                 // threads cooperating on one tile member (16 or 8)
+    constexpr int KEY_MARGIN = 512;                // ulps: >= 3e-5 relative, 3x the worst error of an approximate score
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = src.size();
     unsigned long long* ckey = buf.ckey;
     BoxC* cbox = buf.cbox;
     BoxC* kept = buf.kept;
     const float thr_lo = fmul(thr, kFilterSlack);
     int kept_n = 0;
     int remaining = n_cand;
-    bool use_hist = HIST && NT == 1024 && n < 65536;       // 16-bit bin counters, one thread per four bins
+    bool use_hist = HIST && NT == 1024 && n_cand < 65536;  // 16-bit bin counters, one thread per four bins
+    // APPROX: the keys of the source are approximate scores (score_kernel) until make_exact() has run;
+    // exact scores are computed only for the candidates a chunk actually pulls.
+    bool keys_exact = !APPROX;
+    auto make_exact = [&]() {                      // every thread of the CTA
+        src.template for_each<NT>([&](int i, unsigned long long r) {
+            if (Src::key(r) == 0u) return;
+            const unsigned long long sk = Src::sortkey(r, i);
+            const unsigned id = 0xffffffffu - (unsigned)(sk & 0xffffffffull);
+            src.replace(i, ((unsigned long long)exact_key(id) << 32) | (sk & 0xffffffffull));
+        });
+        if (HIST) for (int i = tid; i < HBINS / 2; i += NT) buf.hist16[i] = 0u;
+        __syncthreads();
+        if (use_hist) src.template for_each<NT>([&](int, unsigned long long r) { if (Src::key(r) != 0u) hist_add(buf.hist16, Src::key(r)); });
+        __syncthreads();
+        keys_exact = true;
+    };
     if (GROUPS) for (int g = tid; g < n_groups; g += NT) buf.ngroup[g] = 0;
     while (remaining > 0 && kept_n < max_keep) {
         // ---- pull the next best candidates ---------------------------------------------------
@@ -286,39 +309,64 @@ __device__ int nms_unit(const Src src, const UnitBuffers buf, int n_cand, int n_
         unsigned tkey = 1u, need = 0u, eq = 0u;
         bool all = remaining <= CHUNK;
         if (!all && use_hist) {
-            hist_cut(buf.hist16, CHUNK, us);
+            hist_cut(buf.hist16, keys_exact ? CHUNK : CHUNK - 16, us);     // (room for the few margin strays)
             if (us.cut_count > 0) { K = us.cut_count; tkey = bin_floor_key(us.cut_bin); all = true; }
             else use_hist = false;                 // a single bin holds more than a chunk: exact select from here on
             __syncthreads();
         }
         unsigned tie_floor = 0u;        // among entries with key == tkey only those with ~id >= tie_floor are taken
         if (!all) {
-            select_kth<NT>(n, [&](int i) { return Src::key(src.raw(i)); }, (unsigned)K, us, tkey, need, eq);
+            if (APPROX && !keys_exact) make_exact();       // the exact selection needs exact keys (use_hist stays off)
+            select_kth<NT>(src, [&](int, unsigned long long r) { return Src::key(r); }, (unsigned)K, us, tkey, need, eq);
             if (need != eq) {
                 // more entries share the threshold score than are needed: take the lowest candidate ids
                 // (= the largest ~id, which is the low half of the sort key) -- a second select over ids
                 unsigned n2, e2;
-                select_kth<NT>(n, [&](int i) {
-                    const unsigned long long r = src.raw(i);
+                select_kth<NT>(src, [&](int i, unsigned long long r) {
                     return Src::key(r) == tkey ? (unsigned)(Src::sortkey(r, i) & 0xffffffffull) : 0u;
                 }, need, us, tie_floor, n2, e2);
             }
         }
+        const unsigned gkey = (keys_exact || tkey <= (unsigned)KEY_MARGIN) ? tkey : tkey - (unsigned)KEY_MARGIN;
         if (tid == 0) us.counter = 0;
         __syncthreads();
-        for (int i = tid; i < n; i += NT) {
-            const unsigned long long r = src.raw(i);
+        src.template for_each<NT>([&](int i, unsigned long long r) {
             const unsigned k = Src::key(r);
-            if (k == 0u || k < tkey) continue;
+            if (k == 0u || k < gkey) return;
             const unsigned long long sk = Src::sortkey(r, i);
-            if (k == tkey && (unsigned)(sk & 0xffffffffull) < tie_floor) continue;
+            if (keys_exact && k == tkey && (unsigned)(sk & 0xffffffffull) < tie_floor) return;
             const int pos = atomicAdd(&us.counter, 1);
-            ckey[pos] = sk;
-            src.consume(i);
+            if (pos < CHUNK) {
+                ckey[pos] = sk;
+                if (APPROX) buf.cidx[pos] = i;
+            }
+            if (keys_exact) src.consume(i);
+        });
+        __syncthreads();
+        if (APPROX && !keys_exact) {
+            const int gathered = us.counter;
+            if (gathered > CHUNK) {                // more margin strays than the slack: settle it with exact keys
+                __syncthreads();
+                make_exact();
+                continue;
+            }
+            // exact scores of the pulled candidates; one that falls below the cut stays in the pool
+            bool valid = false;
+            if (tid < CHUNK) {
+                unsigned long long out = 0ull;
+                if (tid < gathered) {
+                    const unsigned long long sk = ckey[tid];
+                    const unsigned ek = exact_key(0xffffffffu - (unsigned)(sk & 0xffffffffull));
+                    valid = ek >= tkey;
+                    if (valid) { out = ((unsigned long long)ek << 32) | (sk & 0xffffffffull); src.consume(buf.cidx[tid]); }
+                }
+                ckey[tid] = out;
+            }
+            K = __syncthreads_count(valid);
+        } else {
+            for (int i = K + tid; i < CHUNK; i += NT) ckey[i] = 0ull;
+            __syncthreads();
         }
-        __syncthreads();
-        for (int i = K + tid; i < CHUNK; i += NT) ckey[i] = 0ull;
-        __syncthreads();
         bitonic_desc_256(ckey);
         for (int i = tid; i < K; i += NT) {
             const unsigned id = 0xffffffffu - (unsigned)(ckey[i] & 0xffffffffull);
@@ -450,103 +498,131 @@ __device__ __forceinline__ float row_sum_generic(const float* __restrict__ row, 
 }
 
 constexpr int ST = 256;        // threads of score_kernel
-constexpr int SCS = 8;         // CTAs per image
+constexpr int SCS = SEGS / (ST / 32);   // CTAs per image: every warp owns one list segment
 constexpr int PT = 1024;       // threads of nms_image_kernel
 constexpr int UT = 512;        // threads of stand-alone NMS
 
-// A score can only pass `s > thresh` if e_k > thr_pre * sum, thr_pre = thresh * (1 - 1e-5): the
-// margin is two orders of magnitude above the rounding of the product and of the division, so
-// pairs below it skip the IEEE division without changing any decision.
+// rows of one list segment (even, so that a segment starts on a 48-byte row pair when C == 6)
+__host__ __device__ inline int seg_rows(int P) { return (((P + SEGS - 1) / SEGS) + 1) & ~1; }
+
+__device__ __forceinline__ float ex2_approx_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// exact softmax score of class k+1 of a 6-logit row, eager torch-CUDA order (SFS:388), as an order-preserving key
+__device__ __forceinline__ unsigned exact_score_key6(const float* __restrict__ row, int k) {
+    float e[6];
+    const float sum = row_exps6(row, e);
+    const float ek = k == 0 ? e[1] : k == 1 ? e[2] : k == 2 ? e[3] : k == 3 ? e[4] : e[5];
+    return __float_as_uint(fdiv(ek, sum)) | 0x80000000u;
+}
+
+// score_kernel: the HBM-bound half of predict.  Warp w of the image's SCS CTAs streams rows
+// [w * seg_rows, (w+1) * seg_rows) and appends the (prior, class) pairs that pass the score threshold to
+// its own segment of the candidate list -- no atomics, no shared memory, counts written at the end.
+// C == 6: softmax is evaluated with ex2.approx / rcp.approx (relative error <= 1.1e-5, see nms_unit's
+// KEY_MARGIN); the strict test `score > thresh` (SFS:402) is decided by the approximate score when it is
+// more than 1e-4 (relative) away from the threshold and by the exact eager-CUDA arithmetic otherwise, so
+// the candidate SET is exact; the keys are approximate and nms_image_kernel refines the ones it pulls.
 template <int CT>
 __global__ void __launch_bounds__(ST) score_kernel(const PredictParams prm) {
-    __shared__ float st_e[ST / 32][32 * 5], st_s[ST / 32][32 * 5];
-    __shared__ unsigned st_id[ST / 32][32 * 5];
     const int b = blockIdx.x / SCS, part = blockIdx.x % SCS;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg = part * (ST / 32) + warp;
     const int P = prm.P, n_fg = prm.C - 1;
-    const int rows = (P + SCS - 1) / SCS;
-    const int r0 = part * rows, r1 = min(P, r0 + rows);
-    const float thr_pre = fmul(prm.score_thresh, 0.99999f);
+    const int rows = seg_rows(P);
+    const int r0 = min(P, seg * rows), r1 = min(P, r0 + rows);
     const float* conf_b = prm.conf_all + (long long)b * P * prm.C;
-    unsigned long long* list = prm.cand + (long long)b * P * n_fg;
-    int* count = prm.cand_count + b;
+    unsigned long long* list = prm.cand + ((long long)b * SEGS + seg) * rows * n_fg;
     const unsigned lt = (1u << lane) - 1u;
-
-    for (int base = r0 + warp * 32; base < r1; base += ST) {      // warp-uniform trip count
-        const int p = base + lane;
-        const bool live = p < r1;
-        if (CT == 6) {
-            float e[6];
-            float sum = 1.0f;
-            bool f[5] = {false, false, false, false, false};
-            if (live) {
-                sum = row_exps6(conf_b + (long long)p * 6, e);
-                const float gate = fmul(thr_pre, sum);
+    int cnt = 0;                                            // warp-uniform
+    if (CT == 6) {
+        const float thr = prm.score_thresh, thr_hi = thr * 1.0001f, thr_lo = thr * 0.9999f;
+        const float4* src = reinterpret_cast<const float4*>(conf_b);
+        const int q1 = r1 >> 1;                             // P is even on this path
+#pragma unroll 2
+        for (int qb = r0 >> 1; qb < q1; qb += 32) {
+            const int q = qb + lane;
+            unsigned pass = 0u;                             // bit (h * 5 + k): row 2q+h, class k+1 is a candidate
+            float sc[10];
+            if (q < q1) {
+                const float4 A = __ldg(src + 3 * q), Bv = __ldg(src + 3 * q + 1), Cv = __ldg(src + 3 * q + 2);
+                const float x[2][6] = {{A.x, A.y, A.z, A.w, Bv.x, Bv.y}, {Bv.z, Bv.w, Cv.x, Cv.y, Cv.z, Cv.w}};
 #pragma unroll
-                for (int k = 0; k < 5; ++k) f[k] = e[k + 1] > gate;
-            }
-            // compact the "maybe" pairs of the warp into shared memory, class-major
-            int total = 0;
+                for (int h = 0; h < 2; ++h) {
+                    const float mx = fmaxf(fmaxf(fmaxf(x[h][0], x[h][1]), fmaxf(x[h][2], x[h][3])), fmaxf(x[h][4], x[h][5]));
+                    float e[6];
 #pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                const unsigned bal = __ballot_sync(FULL, f[k]);
-                if (f[k]) {
-                    const int slot = total + __popc(bal & lt);
-                    st_e[warp][slot] = e[k + 1];
-                    st_s[warp][slot] = sum;
-                    st_id[warp][slot] = (unsigned)(p * 5 + k);
+                    for (int i = 0; i < 6; ++i) e[i] = ex2_approx_ftz((x[h][i] - mx) * 1.4426950408889634f);
+                    const float rs = rcp_approx_ftz(((e[0] + e[1]) + (e[2] + e[3])) + (e[4] + e[5]));
+                    unsigned maybe = 0u;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const float s = e[k + 1] * rs;
+                        sc[h * 5 + k] = s;
+                        if (s > thr_hi) pass |= 1u << (h * 5 + k);
+                        else if (s >= thr_lo) maybe |= 1u << k;
+                    }
+                    if (maybe) {                            // within 1e-4 of the threshold: the exact arithmetic decides
+                        float ee[6];
+                        const float mxe = fmaxf(fmaxf(fmaxf(x[h][0], x[h][1]), fmaxf(x[h][2], x[h][3])), fmaxf(x[h][4], x[h][5]));
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) ee[i] = expf(fsub(x[h][i], mxe));
+                        const float sum = fadd(fadd(fadd(ee[0], ee[4]), ee[2]), fadd(fadd(ee[1], ee[5]), ee[3]));
+#pragma unroll
+                        for (int k = 0; k < 5; ++k)
+                            if (((maybe >> k) & 1u) && fdiv(ee[k + 1], sum) > thr) pass |= 1u << (h * 5 + k);
+                    }
                 }
-                total += __popc(bal);
             }
-            __syncwarp();
-            for (int it = 0; it < total; it += 32) {
-                const int i = it + lane;
-                bool ok = false;
-                unsigned long long key = 0ull;
-                if (i < total) {
-                    const float s = fdiv(st_e[warp][i], st_s[warp][i]);      // softmax(conf)[..., 1:]  (SFS:388)
-                    ok = s > prm.score_thresh;                               // strict (SFS:402)
-                    key = ((unsigned long long)(__float_as_uint(s) | 0x80000000u) << 32) |
-                          (unsigned long long)(0xffffffffu - st_id[warp][i]);
+            // append: lane l's entries follow those of lanes < l
+            const int mine = __popc(pass);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += y;
+            }
+            int at = cnt + incl - mine;
+            cnt += __shfl_sync(FULL, incl, 31);
+            if (pass) {
+                const unsigned id0 = (unsigned)(2 * q) * 5u;
+#pragma unroll
+                for (int j = 0; j < 10; ++j) {
+                    if ((pass >> j) & 1u) {
+                        list[at++] = ((unsigned long long)(__float_as_uint(sc[j]) | 0x80000000u) << 32) |
+                                     (unsigned long long)(0xffffffffu - (id0 + (unsigned)j));
+                    }
                 }
-                const unsigned bal = __ballot_sync(FULL, ok);
-                int dst = 0;
-                if (lane == 0 && bal) dst = atomicAdd(count, __popc(bal));
-                dst = __shfl_sync(FULL, dst, 0);
-                if (ok) list[dst + __popc(bal & lt)] = key;
             }
-            __syncwarp();
-        } else {
+        }
+    } else {
+        for (int base = r0; base < r1; base += 32) {
+            const int p = base + lane;
+            const bool live = p < r1;
             float mx = 0.0f, sum = 1.0f;
             if (live) sum = row_sum_generic(conf_b + (long long)p * prm.C, prm.C, mx);
-            const float gate = fmul(thr_pre, sum);
             for (int k = 0; k < n_fg; ++k) {
                 bool ok = false;
                 unsigned long long key = 0ull;
                 if (live) {
-                    const float ek = expf(fsub(__ldg(conf_b + (long long)p * prm.C + k + 1), mx));
-                    if (ek > gate) {
-                        const float s = fdiv(ek, sum);
-                        ok = s > prm.score_thresh;
-                        key = ((unsigned long long)(__float_as_uint(s) | 0x80000000u) << 32) |
-                              (unsigned long long)(0xffffffffu - (unsigned)(p * n_fg + k));
-                    }
+                    const float s = fdiv(expf(fsub(__ldg(conf_b + (long long)p * prm.C + k + 1), mx)), sum);
+                    ok = s > prm.score_thresh;
+                    key = ((unsigned long long)(__float_as_uint(s) | 0x80000000u) << 32) |
+                          (unsigned long long)(0xffffffffu - (unsigned)(p * n_fg + k));
                 }
                 const unsigned bal = __ballot_sync(FULL, ok);
-                if (bal == 0u) continue;
-                int dst = 0;
-                if (lane == 0) dst = atomicAdd(count, __popc(bal));
-                dst = __shfl_sync(FULL, dst, 0);
-                if (ok) list[dst + __popc(bal & lt)] = key;
+                if (ok) list[cnt + __popc(bal & lt)] = key;
+                cnt += __popc(bal);
             }
         }
     }
+    if (lane == 0) prm.cand_count[b * SEGS + seg] = cnt;
 }
 
-// shared-memory carve-up of one unit: kept | cbox | ckey | cmask | hist16 | ngroup | kidx | cgroup
+// shared-memory carve-up of one unit: kept | cbox | ckey | cmask | hist16 | ngroup | cidx | kidx | cgroup
 __host__ __device__ inline size_t unit_smem_bytes(int max_keep, int n_groups, bool hist) {
     return (size_t)max_keep * sizeof(BoxC) + (size_t)CHUNK * (sizeof(BoxC) + 8) + (size_t)n_groups * 8 +
-           (hist ? (size_t)HBINS * 2 : 0) + (size_t)n_groups * 4 + (size_t)n_groups * max_keep * 2 + (size_t)CHUNK + 48;
+           (hist ? (size_t)HBINS * 2 : 0) + (size_t)n_groups * 4 + (size_t)CHUNK * 4 + (size_t)n_groups * max_keep * 2 + (size_t)CHUNK + 48;
 }
 __device__ __forceinline__ UnitBuffers carve_unit(unsigned char* dyn, int max_keep, int n_groups, bool hist) {
     UnitBuffers b;
@@ -556,15 +632,16 @@ __device__ __forceinline__ UnitBuffers carve_unit(unsigned char* dyn, int max_ke
     b.cmask = b.ckey + CHUNK;
     b.hist16 = reinterpret_cast<unsigned*>(b.cmask + n_groups);
     b.ngroup = reinterpret_cast<int*>(b.hist16 + (hist ? HBINS / 2 : 0));
-    b.kidx = reinterpret_cast<unsigned short*>(b.ngroup + n_groups);
+    b.cidx = b.ngroup + n_groups;
+    b.kidx = reinterpret_cast<unsigned short*>(b.cidx + CHUNK);
     b.cgroup = reinterpret_cast<unsigned char*>(b.kidx + (size_t)n_groups * max_keep);
     return b;
 }
 
 // One CTA per image: rank the candidate list and walk it with class-aware greedy NMS.  Keys carry
 // the candidate id, so equal scores are always ordered by ascending id -- the list itself is in
-// arbitrary (atomic) order.
-template <int METRIC, bool AGN>
+// arbitrary order.  APPROX: the list holds approximate scores (score_kernel<6>).
+template <int METRIC, bool AGN, bool APPROX>
 __global__ void __launch_bounds__(PT) nms_image_kernel(const PredictParams prm) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ UnitShared us;
@@ -573,17 +650,20 @@ __global__ void __launch_bounds__(PT) nms_image_kernel(const PredictParams prm) 
     const int n_fg = prm.C - 1, P = prm.P;
     const int n_groups = AGN ? 0 : n_fg;
     const UnitBuffers buf = carve_unit(dyn, prm.max_keep, n_groups, true);
-    ListSource src;
-    src.list = prm.cand + (long long)b * P * n_fg;
-    src.n = prm.cand_count[b];
+    SegSource src;
+    src.seg_cap = seg_rows(P) * n_fg;
+    src.base = prm.cand + (long long)b * SEGS * src.seg_cap;
+    src.counts = prm.cand_count + b * SEGS;
+    const int n_cand = block_sum<int>(tid < SEGS ? src.counts[tid] : 0, us.iscratch);
 
     for (int i = tid; i < HBINS / 2; i += PT) buf.hist16[i] = 0u;
     __syncthreads();
-    if (src.n > CHUNK && src.n < 65536)
-        for (int i = tid; i < src.n; i += PT) hist_add(buf.hist16, (unsigned)(src.list[i] >> 32));
+    if (n_cand > CHUNK && n_cand < 65536)
+        src.for_each<PT>([&](int, unsigned long long r) { hist_add(buf.hist16, (unsigned)(r >> 32)); });
     __syncthreads();
 
     const float* loc_b = prm.loc_all + 4ll * b * P;
+    const float* conf_b = prm.conf_all + (long long)b * P * prm.C;
     const bool want_atan = METRIC == SSDHOT_METRIC_CIOU;
     auto fetch = [&](unsigned id) -> BoxC {
         const unsigned p = id / (unsigned)n_fg;
@@ -599,8 +679,9 @@ __global__ void __launch_bounds__(PT) nms_image_kernel(const PredictParams prm) 
         reinterpret_cast<float4*>(prm.out_boxes)[o + pos] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
         if (prm.out_cand) prm.out_cand[o + pos] = (int32_t)id;
     };
-    const int kept_n = nms_unit<METRIC, PT, !AGN, true>(src, buf, src.n, n_groups, prm.max_keep, prm.nms_thresh, us,
-                                                       fetch, group_of, emit);
+    auto exact_key = [&](unsigned id) -> unsigned { return exact_score_key6(conf_b + 6ll * (id / 5u), (int)(id % 5u)); };
+    const int kept_n = nms_unit<METRIC, PT, !AGN, true, APPROX>(src, buf, n_cand, n_groups, prm.max_keep, prm.nms_thresh, us,
+                                                               fetch, group_of, emit, exact_key);
     if (tid == 0) prm.out_count[b] = kept_n;
 }
 
@@ -637,7 +718,8 @@ __global__ void __launch_bounds__(UT) nms_sets_kernel(const float* __restrict__ 
     int64_t* out = keep + begin;
     auto emit = [&](int pos, unsigned long long, unsigned id, const BoxC&) { out[pos] = (int64_t)id; };
     const int cap = (max_keep > 0 && max_keep < n) ? max_keep : n;
-    const int kept_n = nms_unit<METRIC, UT, false, false>(src, buf, n, 0, cap, thr, us, fetch, group_of, emit);
+    const int kept_n = nms_unit<METRIC, UT, false, false, false>(src, buf, n, 0, cap, thr, us, fetch, group_of, emit,
+                                                                 [](unsigned) -> unsigned { return 0u; });
     if (tid == 0) keep_count[blockIdx.x] = kept_n;
 }
 
@@ -648,10 +730,6 @@ __global__ void decode_kernel(const float* __restrict__ loc, const float* __rest
     reinterpret_cast<float4*>(out)[i] = decode_box(ldg4(loc + 4ll * i), ldg4(pri + 4ll * i), vc, vs);
 }
 
-__global__ void zero_counts_kernel(int* __restrict__ counts, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) counts[i] = 0;
-}
 
 constexpr size_t kMaxDynSmem = 227 * 1024 - sizeof(UnitShared) - 1024;
 
@@ -673,11 +751,11 @@ static int set_smem(K kern, size_t bytes) {
     return SSDHOT_OK;
 }
 
-template <int METRIC, bool AGN>
+template <int METRIC, bool AGN, bool APPROX>
 static int launch_nms_image(const PredictParams& prm, size_t dyn, cudaStream_t stream) {
     int rc;
-    if ((rc = set_smem(nms_image_kernel<METRIC, AGN>, dyn))) return rc;
-    nms_image_kernel<METRIC, AGN><<<prm.B, PT, dyn, stream>>>(prm);
+    if ((rc = set_smem(nms_image_kernel<METRIC, AGN, APPROX>, dyn))) return rc;
+    nms_image_kernel<METRIC, AGN, APPROX><<<prm.B, PT, dyn, stream>>>(prm);
     SSDHOT_CHECK_LAUNCH();
     return SSDHOT_OK;
 }
@@ -734,12 +812,12 @@ extern "C" int ssdhot_nms(const float* boxes, const float* scores, const int32_t
     return SSDHOT_OK;
 }
 
-// workspace layout: cand_count [B] int32 (padded to 16) | cand [B][P*(C-1)] uint64
-static size_t pw_cand_off(int B) { return ((size_t)B * 4 + 15) & ~(size_t)15; }
+// workspace layout: cand_count [B][SEGS] int32 | cand [B][SEGS][seg_rows(P)*(C-1)] uint64
+static size_t pw_cand_off(int B) { return ((size_t)B * SEGS * 4 + 15) & ~(size_t)15; }
 
 extern "C" unsigned long long ssdhot_predict_workspace_bytes(int B, int P, int C) {
     if (B <= 0 || P <= 0 || C < 2) return 64ull;
-    return (unsigned long long)(pw_cand_off(B) + (size_t)B * P * (C - 1) * 8 + 64);
+    return (unsigned long long)(pw_cand_off(B) + (size_t)B * SEGS * seg_rows(P) * (C - 1) * 8 + 64);
 }
 
 extern "C" int ssdhot_predict(const float* priors_cxcywh, int P, const float* loc_all, const float* conf_all,
@@ -769,13 +847,15 @@ extern "C" int ssdhot_predict(const float* priors_cxcywh, int P, const float* lo
     prm.cand_count = reinterpret_cast<int*>(w);
     prm.cand = reinterpret_cast<unsigned long long*>(w + pw_cand_off(B));
     cudaStream_t s = (cudaStream_t)stream;
-    zero_counts_kernel<<<(B + 255) / 256, 256, 0, s>>>(prm.cand_count, B);
-    SSDHOT_CHECK_LAUNCH();
-    if (C == 6) score_kernel<6><<<B * SCS, ST, 0, s>>>(prm);
+    // C == 6 with 48-byte-aligned row pairs: approximate scores, refined by the NMS kernel; otherwise exact scores
+    const bool approx = C == 6 && (P % 2) == 0 && al16(conf_all);
+    if (approx) score_kernel<6><<<B * SCS, ST, 0, s>>>(prm);
     else score_kernel<0><<<B * SCS, ST, 0, s>>>(prm);
     SSDHOT_CHECK_LAUNCH();
     int rc;
-#define SSDHOT_DISPATCH(M) rc = class_agnostic ? launch_nms_image<M, true>(prm, dyn, s) : launch_nms_image<M, false>(prm, dyn, s)
+#define SSDHOT_DISPATCH(M)                                                                                            \
+    rc = approx ? (class_agnostic ? launch_nms_image<M, true, true>(prm, dyn, s) : launch_nms_image<M, false, true>(prm, dyn, s))  \
+                : (class_agnostic ? launch_nms_image<M, true, false>(prm, dyn, s) : launch_nms_image<M, false, false>(prm, dyn, s))
     if (metric == SSDHOT_METRIC_DIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_DIOU); }
     else if (metric == SSDHOT_METRIC_CIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_CIOU); }
     else { SSDHOT_DISPATCH(SSDHOT_METRIC_IOU); }

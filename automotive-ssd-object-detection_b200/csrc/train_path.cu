@@ -1135,10 +1135,13 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     if (tid == 0) { if (prm.n_pos) prm.n_pos[b] = n_pos_img; fs.n_sure = 0; }
 
     // positives: one list entry per thread
-    for (int e = tid;; e += FT) {
-        int p;
-        if (!list_locate(e, POS_PER_WARP, pos_list, p)) break;
-        positive_terms(p, (int)(0xffffffffu - (unsigned)(table[p] & 0xffffffffull)));
+    {
+        const int total = __reduce_add_sync(FULL, lane < FT / 32 ? fs.wcount[lane] : 0);
+        for (int e = tid; e < total; e += FT) {
+            int p;
+            if (!list_locate(e, POS_PER_WARP, pos_list, p)) break;
+            positive_terms(p, (int)(0xffffffffu - (unsigned)(table[p] & 0xffffffffull)));
+        }
     }
 
     // ---- 4. hard negatives -----------------------------------------------------------------------
@@ -1190,7 +1193,8 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
             const int n_sure = fs.n_sure, n_band = fs.n_band;
             if (n_band > BAND_CAP) exact_all = true;     // (massive ties): CTA-uniform; the partial sums are discarded below
             else {
-                for (int e = tid;; e += FT) {
+                const int total = __reduce_add_sync(FULL, lane < FT / 32 ? fs.wcount[lane] : 0);
+                for (int e = tid; e < total; e += FT) {
                     int p;
                     if (!list_locate(e, SEL_PER_WARP, sel_list, p)) break;
                     acc_ce += (double)exact_ce6(conf_b + 6ll * p, 0);
