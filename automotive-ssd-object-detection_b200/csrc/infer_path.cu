@@ -94,9 +94,12 @@ struct SegSource {             // 32 per-warp segments of (key << 32 | ~id) writ
     unsigned long long* base; const int* counts; int seg_cap;
     template <int NT, typename F>
     __device__ __forceinline__ void for_each(F f) const {
-        static_assert(NT == SEGS * 32, "one warp per segment");
-        const int seg = threadIdx.x >> 5, lane = threadIdx.x & 31, c = counts[seg];
-        for (int j = lane; j < c; j += 32) { const int i = seg * seg_cap + j; f(i, base[i]); }
+        static_assert((SEGS * 32) % NT == 0, "whole segments per warp");
+        const int lane = threadIdx.x & 31;
+        for (int seg = threadIdx.x >> 5; seg < SEGS; seg += NT / 32) {
+            const int c = counts[seg];
+            for (int j = lane; j < c; j += 32) { const int i = seg * seg_cap + j; f(i, base[i]); }
+        }
     }
     __device__ __forceinline__ void consume(int i) const { base[i] = 0ull; }
     __device__ __forceinline__ void replace(int i, unsigned long long r) const { base[i] = r; }
@@ -122,14 +125,24 @@ __device__ __forceinline__ void hist_add(unsigned* hist16, unsigned key) {
 
 // Find the lowest bin whose suffix count (candidates in this bin and above) is still <= cap:
 // us.cut_bin / us.cut_count (cut_count == 0 if even the top non-empty bin exceeds cap).  The bins
-// from the cut upwards are zeroed: they are consumed by the gather that follows.  1024 threads,
-// four bins each, thread 0 owns the top four.
+// from the cut upwards are zeroed: they are consumed by the gather that follows.  Thread 0 owns the
+// top HBINS / NT bins, thread 1 the next ones, ...
+template <int NT>
 __device__ __forceinline__ void hist_cut(unsigned* hist16, int cap, UnitShared& us) {
+    constexpr int WPT = (HBINS / 2) / NT;                   // words (two bins each) per thread
+    static_assert(WPT >= 1 && WPT * NT * 2 == HBINS, "thread count must divide the histogram");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int w0 = (1023 - tid) * 2;
-    const unsigned lo = hist16[w0], hi = hist16[w0 + 1];
-    const int c[4] = {(int)(hi >> 16), (int)(hi & 0xffffu), (int)(lo >> 16), (int)(lo & 0xffffu)};   // top first
-    const int mine = c[0] + c[1] + c[2] + c[3];
+    const int w0 = (NT - 1 - tid) * WPT;
+    unsigned wv[WPT];
+    int c[2 * WPT];                                         // top bin first
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < WPT; ++j) {
+        wv[j] = hist16[w0 + WPT - 1 - j];
+        c[2 * j] = (int)(wv[j] >> 16);
+        c[2 * j + 1] = (int)(wv[j] & 0xffffu);
+        mine += c[2 * j] + c[2 * j + 1];
+    }
     int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -143,10 +156,10 @@ __device__ __forceinline__ void hist_cut(unsigned* hist16, int cap, UnitShared& 
     for (int w = 0; w < warp; ++w) run += us.iscratch[w];
     // cumulative counts grow monotonically going down, so "my lowest bin that still fits" is a valid
     // proposal and the cut is the minimum proposal over all threads
-    const int top_bin = (1023 - tid) * 4 + 3;
+    const int top_bin = (w0 + WPT) * 2 - 1;
     int proposal = -1, prop_count = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 2 * WPT; ++j) {
         run += c[j];
         if (run <= cap) { proposal = top_bin - j; prop_count = run; }
     }
@@ -159,7 +172,7 @@ __device__ __forceinline__ void hist_cut(unsigned* hist16, int cap, UnitShared& 
     if (lane == 0) us.best[warp] = packed;
     __syncthreads();
     if (tid < 32) {
-        unsigned long long v = us.best[tid];
+        unsigned long long v = tid < NT / 32 ? us.best[tid] : ~0ull;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const unsigned long long y = __shfl_xor_sync(FULL, v, o);
@@ -170,13 +183,14 @@ __device__ __forceinline__ void hist_cut(unsigned* hist16, int cap, UnitShared& 
     __syncthreads();
     const int cut = us.cut_bin;
     if (cut >= 0) {                                         // consume the bins from the cut upwards
-        unsigned nlo = lo, nhi = hi;
-        const int b0 = (1023 - tid) * 4;
-        if (b0 + 0 >= cut) nlo &= 0xffff0000u;
-        if (b0 + 1 >= cut) nlo &= 0x0000ffffu;
-        if (b0 + 2 >= cut) nhi &= 0xffff0000u;
-        if (b0 + 3 >= cut) nhi &= 0x0000ffffu;
-        hist16[w0] = nlo; hist16[w0 + 1] = nhi;
+#pragma unroll
+        for (int j = 0; j < WPT; ++j) {
+            const int wi = w0 + WPT - 1 - j;
+            unsigned v = wv[j];
+            if (2 * wi + 1 >= cut) v &= 0x0000ffffu;
+            if (2 * wi >= cut) v &= 0xffff0000u;
+            hist16[wi] = v;
+        }
     }
 }
 
@@ -227,33 +241,34 @@ __device__ __forceinline__ void select_kth(const Src& src, KeyFn keyfn, unsigned
     thr = prefix; need = remaining; eq = count_eq;
 }
 
-// Bitonic sort (descending) of CHUNK = 256 64-bit keys held in shared memory, by the first 256
-// threads (one key each): compare-exchange distances < 32 run on registers through warp shuffles,
-// the six larger ones through shared memory.  Every thread of the CTA must call it.
-__device__ __forceinline__ void bitonic_desc_256(unsigned long long* keys) {
+// Bitonic sort (descending) of N 64-bit keys held in shared memory, by the first N threads (one key
+// each): compare-exchange distances < 32 run on registers through warp shuffles, the larger ones
+// through shared memory.  Every thread of the CTA must call it.
+template <int N>
+__device__ __forceinline__ void bitonic_desc(unsigned long long* keys) {
     const int tid = threadIdx.x;
-    unsigned long long v = tid < CHUNK ? keys[tid] : 0ull;
-    for (int k = 2; k <= CHUNK; k <<= 1) {
+    unsigned long long v = tid < N ? keys[tid] : 0ull;
+    for (int k = 2; k <= N; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             const bool desc = (tid & k) == 0;
             const bool lower = (tid & j) == 0;             // this thread holds the lower-indexed element
             const bool take_max = (lower == desc);         // descending run: lower index keeps the larger key
             if (j >= 32) {
                 __syncthreads();
-                if (tid < CHUNK) keys[tid] = v;
+                if (tid < N) keys[tid] = v;
                 __syncthreads();
-                if (tid < CHUNK) {
+                if (tid < N) {
                     const unsigned long long o = keys[tid ^ j];
                     v = take_max ? (o > v ? o : v) : (o < v ? o : v);
                 }
-            } else if (tid < CHUNK) {
+            } else if (tid < N) {
                 const unsigned long long o = __shfl_xor_sync(FULL, v, j);
                 v = take_max ? (o > v ? o : v) : (o < v ? o : v);
             }
         }
     }
     __syncthreads();
-    if (tid < CHUNK) keys[tid] = v;
+    if (tid < N) keys[tid] = v;
     __syncthreads();
 }
 
@@ -309,7 +324,7 @@ __device__ int nms_unit(const Src src, const UnitBuffers buf, int n_cand, int n_
         unsigned tkey = 1u, need = 0u, eq = 0u;
         bool all = remaining <= CHUNK;
         if (!all && use_hist) {
-            hist_cut(buf.hist16, keys_exact ? CHUNK : CHUNK - 16, us);     // (room for the few margin strays)
+            hist_cut<NT == 1024 ? 1024 : 512>(buf.hist16, keys_exact ? CHUNK : CHUNK - 16, us);     // (room for the few margin strays)
             if (us.cut_count > 0) { K = us.cut_count; tkey = bin_floor_key(us.cut_bin); all = true; }
             else use_hist = false;                 // a single bin holds more than a chunk: exact select from here on
             __syncthreads();
@@ -367,7 +382,7 @@ __device__ int nms_unit(const Src src, const UnitBuffers buf, int n_cand, int n_
             for (int i = K + tid; i < CHUNK; i += NT) ckey[i] = 0ull;
             __syncthreads();
         }
-        bitonic_desc_256(ckey);
+        bitonic_desc<CHUNK>(ckey);
         for (int i = tid; i < K; i += NT) {
             const unsigned id = 0xffffffffu - (unsigned)(ckey[i] & 0xffffffffull);
             cbox[i] = fetch(id);
@@ -619,69 +634,296 @@ __global__ void __launch_bounds__(ST) score_kernel(const PredictParams prm) {
     if (lane == 0) prm.cand_count[b * SEGS + seg] = cnt;
 }
 
-// shared-memory carve-up of one unit: kept | cbox | ckey | cmask | hist16 | ngroup | cidx | kidx | cgroup
-__host__ __device__ inline size_t unit_smem_bytes(int max_keep, int n_groups, bool hist) {
-    return (size_t)max_keep * sizeof(BoxC) + (size_t)CHUNK * (sizeof(BoxC) + 8) + (size_t)n_groups * 8 +
-           (hist ? (size_t)HBINS * 2 : 0) + (size_t)n_groups * 4 + (size_t)CHUNK * 4 + (size_t)n_groups * max_keep * 2 + (size_t)CHUNK + 48;
+// shared-memory carve-up of the stand-alone unit (nms_sets_kernel carves by hand)
+// ---- predict: per-image ranking + class-aware greedy NMS -------------------------------------------
+// One CTA of 512 threads per image (two or three CTAs per SM, so a batch of 256 is one wave).  Per round:
+//   pull    the best <= 496 unconsumed candidates: score histogram -> cut -> gather -> exact scores of
+//           the pulled ones (the list holds approximate scores when APPROX) -> bitonic sort;
+//   decode  their boxes (SFS:419-425);
+//   order   class-local positions: position m of entry j among the round's entries of its class;
+//   test    entry j against the survivors of its class from earlier rounds and against the earlier
+//           entries of its class in this round -- bit m of row i = "i suppresses the entry at position m";
+//   resolve one warp per class walks its rows in score order (only rows that are alive and suppress
+//           something), the classes in parallel;
+//   emit    survivors in global score order until max_per_img boxes are out.
+// The first round pulls ~1.5 max_per_img candidates, which is enough for typical inputs; further rounds
+// run only while fewer than max_per_img boxes have survived and candidates remain.  This is exactly the
+// reference's per-class NMS + global sort + truncation (SFS:439-465): a candidate's fate depends only on
+// higher-scored candidates of its own class, all of which precede it in the global order.
+constexpr int CH = 512;        // candidates per round
+constexpr int MW = CH / 64;    // 64-bit words of a class-local bit row
+
+struct ImgBuffers {
+    unsigned long long* ckey;      // [CH] sort keys of the round
+    unsigned long long* mat;       // [CH][MW] suppression rows (bits = class-local positions)
+    unsigned long long* aliveW;    // [n_groups][MW] class-local alive bits
+    unsigned long long* nzW;       // [n_groups][MW] class-local "row suppresses something" bits
+    BoxC* cbox;                    // [CH]
+    BoxC* kept;                    // [max_keep] survivors in output order
+    unsigned* hist16;              // [HBINS / 2]
+    int* cidx;                     // [CH] list index of a pulled candidate
+    int* coff;                     // [n_groups + 1] offsets of the class lists inside clist
+    int* ngroup;                   // [n_groups] survivors per class so far
+    int* wcnt;                     // [16][n_groups] per-warp class counts of the round
+    unsigned short* clist;         // [CH] round entries grouped by class, score order inside a class
+    unsigned short* cpos;          // [CH] class-local position of entry j
+    unsigned short* kidx;          // [n_groups][max_keep] positions in `kept` of each class's survivors
+    unsigned char* cgroup;         // [CH]
+};
+__host__ __device__ inline size_t img_smem_bytes(int max_keep, int n_groups) {
+    const int ng = n_groups > 0 ? n_groups : 1;
+    return (size_t)CH * 8 + (size_t)CH * MW * 8 + (size_t)ng * MW * 16 + (size_t)CH * sizeof(BoxC) + (size_t)max_keep * sizeof(BoxC) +
+           (size_t)HBINS * 2 + (size_t)CH * 4 + (size_t)(ng + 1) * 4 + (size_t)ng * 4 + (size_t)16 * ng * 4 +
+           (size_t)CH * 2 * 2 + (size_t)ng * max_keep * 2 + (size_t)CH + 64;
 }
-__device__ __forceinline__ UnitBuffers carve_unit(unsigned char* dyn, int max_keep, int n_groups, bool hist) {
-    UnitBuffers b;
-    b.kept = reinterpret_cast<BoxC*>(dyn);
-    b.cbox = b.kept + max_keep;
-    b.ckey = reinterpret_cast<unsigned long long*>(b.cbox + CHUNK);
-    b.cmask = b.ckey + CHUNK;
-    b.hist16 = reinterpret_cast<unsigned*>(b.cmask + n_groups);
-    b.ngroup = reinterpret_cast<int*>(b.hist16 + (hist ? HBINS / 2 : 0));
-    b.cidx = b.ngroup + n_groups;
-    b.kidx = reinterpret_cast<unsigned short*>(b.cidx + CHUNK);
-    b.cgroup = reinterpret_cast<unsigned char*>(b.kidx + (size_t)n_groups * max_keep);
+__device__ __forceinline__ ImgBuffers carve_img(unsigned char* dyn, int max_keep, int n_groups) {
+    const int ng = n_groups > 0 ? n_groups : 1;
+    ImgBuffers b;
+    b.ckey = reinterpret_cast<unsigned long long*>(dyn);
+    b.mat = b.ckey + CH;
+    b.aliveW = b.mat + (size_t)CH * MW;
+    b.nzW = b.aliveW + (size_t)ng * MW;
+    b.cbox = reinterpret_cast<BoxC*>(b.nzW + (size_t)ng * MW);
+    b.kept = b.cbox + CH;
+    b.hist16 = reinterpret_cast<unsigned*>(b.kept + max_keep);
+    b.cidx = reinterpret_cast<int*>(b.hist16 + HBINS / 2);
+    b.coff = b.cidx + CH;
+    b.ngroup = b.coff + ng + 1;
+    b.wcnt = b.ngroup + ng;
+    b.clist = reinterpret_cast<unsigned short*>(b.wcnt + 16 * ng);
+    b.cpos = b.clist + CH;
+    b.kidx = b.cpos + CH;
+    b.cgroup = reinterpret_cast<unsigned char*>(b.kidx + (size_t)ng * max_keep);
     return b;
 }
 
-// One CTA per image: rank the candidate list and walk it with class-aware greedy NMS.  Keys carry
-// the candidate id, so equal scores are always ordered by ascending id -- the list itself is in
-// arbitrary order.  APPROX: the list holds approximate scores (score_kernel<6>).
+constexpr int IT = 512;        // threads of nms_image_kernel
+
 template <int METRIC, bool AGN, bool APPROX>
-__global__ void __launch_bounds__(PT) nms_image_kernel(const PredictParams prm) {
+__global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams prm) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ UnitShared us;
-    const int tid = threadIdx.x;
+    constexpr int KEY_MARGIN = 512;                // ulps: >= 3e-5 relative, 3x the worst error of an approximate score
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x;
-    const int n_fg = prm.C - 1, P = prm.P;
-    const int n_groups = AGN ? 0 : n_fg;
-    const UnitBuffers buf = carve_unit(dyn, prm.max_keep, n_groups, true);
+    const int n_fg = prm.C - 1, P = prm.P, max_keep = prm.max_keep;
+    const int n_groups = AGN ? 1 : n_fg;
+    const ImgBuffers buf = carve_img(dyn, max_keep, n_groups);
     SegSource src;
     src.seg_cap = seg_rows(P) * n_fg;
     src.base = prm.cand + (long long)b * SEGS * src.seg_cap;
     src.counts = prm.cand_count + b * SEGS;
     const int n_cand = block_sum<int>(tid < SEGS ? src.counts[tid] : 0, us.iscratch);
-
-    for (int i = tid; i < HBINS / 2; i += PT) buf.hist16[i] = 0u;
-    __syncthreads();
-    if (n_cand > CHUNK && n_cand < 65536)
-        src.for_each<PT>([&](int, unsigned long long r) { hist_add(buf.hist16, (unsigned)(r >> 32)); });
-    __syncthreads();
-
+    const float thr = prm.nms_thresh, thr_lo = fmul(thr, kFilterSlack);
     const float* loc_b = prm.loc_all + 4ll * b * P;
     const float* conf_b = prm.conf_all + (long long)b * P * prm.C;
     const bool want_atan = METRIC == SSDHOT_METRIC_CIOU;
-    auto fetch = [&](unsigned id) -> BoxC {
-        const unsigned p = id / (unsigned)n_fg;
-        const float4 box = decode_box(ldg4(loc_b + 4ll * p), ldg4(prm.pri + 4ll * p), prm.vc, prm.vs);
-        const float4 px = to_pixel_xyxy(box, prm.img_w, prm.img_h);
-        return box_consts(px.x, px.y, px.z, px.w, want_atan);
-    };
-    auto group_of = [&](unsigned id) -> int { return (int)(id % (unsigned)n_fg); };
-    const long long o = (long long)b * prm.max_keep;
-    auto emit = [&](int pos, unsigned long long key, unsigned id, const BoxC& bx) {
-        prm.out_labels[o + pos] = (int64_t)(id % (unsigned)n_fg);
-        prm.out_scores[o + pos] = __uint_as_float((unsigned)(key >> 32) & 0x7fffffffu);
-        reinterpret_cast<float4*>(prm.out_boxes)[o + pos] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
-        if (prm.out_cand) prm.out_cand[o + pos] = (int32_t)id;
-    };
+    const long long o = (long long)b * max_keep;
+    const unsigned lt = (1u << lane) - 1u;
     auto exact_key = [&](unsigned id) -> unsigned { return exact_score_key6(conf_b + 6ll * (id / 5u), (int)(id % 5u)); };
-    const int kept_n = nms_unit<METRIC, PT, !AGN, true, APPROX>(src, buf, n_cand, n_groups, prm.max_keep, prm.nms_thresh, us,
-                                                               fetch, group_of, emit, exact_key);
+
+    bool use_hist = n_cand > CH && n_cand < 65536;          // 16-bit bin counters
+    bool keys_exact = !APPROX;
+    for (int i = tid; i < HBINS / 2; i += IT) buf.hist16[i] = 0u;
+    for (int g = tid; g < n_groups; g += IT) buf.ngroup[g] = 0;
+    __syncthreads();
+    if (use_hist) src.for_each<IT>([&](int, unsigned long long r) { hist_add(buf.hist16, SegSource::key(r)); });
+    __syncthreads();
+    auto make_exact = [&]() {                               // every thread: replace all approximate keys by exact ones
+        src.for_each<IT>([&](int i, unsigned long long r) {
+            if (SegSource::key(r) == 0u) return;
+            src.replace(i, ((unsigned long long)exact_key(0xffffffffu - (unsigned)(r & 0xffffffffull)) << 32) | (r & 0xffffffffull));
+        });
+        for (int i = tid; i < HBINS / 2; i += IT) buf.hist16[i] = 0u;
+        __syncthreads();
+        if (use_hist) src.for_each<IT>([&](int, unsigned long long r) { if (SegSource::key(r) != 0u) hist_add(buf.hist16, SegSource::key(r)); });
+        __syncthreads();
+        keys_exact = true;
+    };
+
+    int kept_n = 0, remaining = n_cand;
+    bool first = true;
+    while (remaining > 0 && kept_n < max_keep) {
+        // ---- pull ----------------------------------------------------------------------------------
+        int K = remaining < CH ? remaining : CH;
+        unsigned tkey = 1u, need = 0u, eq = 0u, tie_floor = 0u;
+        bool all = remaining <= CH;
+        if (!all && use_hist) {
+            int cap = keys_exact ? CH : CH - 16;            // (room for the few margin strays)
+            if (first) cap = min(cap, max(64, max_keep + (max_keep >> 1) + 16));
+            hist_cut<IT>(buf.hist16, cap, us);
+            if (us.cut_count > 0) { K = us.cut_count; tkey = bin_floor_key(us.cut_bin); all = true; }
+            else use_hist = false;                          // a single bin holds more than the cap: exact select from here on
+            __syncthreads();
+        }
+        if (!all) {
+            if (APPROX && !keys_exact) make_exact();
+            select_kth<IT>(src, [&](int, unsigned long long r) { return SegSource::key(r); }, (unsigned)K, us, tkey, need, eq);
+            if (need != eq) {                               // ties at the cut: the lowest candidate ids (largest ~id) first
+                unsigned n2, e2;
+                select_kth<IT>(src, [&](int, unsigned long long r) { return SegSource::key(r) == tkey ? (unsigned)(r & 0xffffffffull) : 0u; },
+                               need, us, tie_floor, n2, e2);
+            }
+        }
+        const unsigned gkey = (keys_exact || tkey <= (unsigned)KEY_MARGIN) ? tkey : tkey - (unsigned)KEY_MARGIN;
+        if (tid == 0) us.counter = 0;
+        __syncthreads();
+        src.for_each<IT>([&](int i, unsigned long long r) {
+            const unsigned k = SegSource::key(r);
+            if (k == 0u || k < gkey) return;
+            if (keys_exact && k == tkey && (unsigned)(r & 0xffffffffull) < tie_floor) return;
+            const int pos = atomicAdd(&us.counter, 1);
+            if (pos < CH) { buf.ckey[pos] = r; buf.cidx[pos] = i; }
+            if (keys_exact) src.consume(i);
+        });
+        __syncthreads();
+        if (APPROX && !keys_exact) {
+            const int gathered = us.counter;
+            if (gathered > CH) {                            // more margin strays than the slack: settle it with exact keys
+                __syncthreads();
+                make_exact();
+                continue;
+            }
+            bool valid = false;                             // exact scores; a candidate that falls below the cut stays in the pool
+            unsigned long long out = 0ull;
+            if (tid < gathered) {
+                const unsigned long long sk = buf.ckey[tid];
+                const unsigned ek = exact_key(0xffffffffu - (unsigned)(sk & 0xffffffffull));
+                valid = ek >= tkey;
+                if (valid) { out = ((unsigned long long)ek << 32) | (sk & 0xffffffffull); src.consume(buf.cidx[tid]); }
+            }
+            buf.ckey[tid] = out;
+            K = __syncthreads_count(valid);
+        } else {
+            if (tid >= K) buf.ckey[tid] = 0ull;
+            __syncthreads();
+        }
+        first = false;
+        if (K == 0) continue;                               // (only margin strays: the next cut is lower)
+        bitonic_desc<CH>(buf.ckey);
+
+        // ---- decode + class-local order --------------------------------------------------------------
+        int my_g = -1;
+        if (tid < K) {
+            const unsigned id = 0xffffffffu - (unsigned)(buf.ckey[tid] & 0xffffffffull);
+            const unsigned p = id / (unsigned)n_fg;
+            const float4 box = decode_box(ldg4(loc_b + 4ll * p), ldg4(prm.pri + 4ll * p), prm.vc, prm.vs);
+            const float4 px = to_pixel_xyxy(box, prm.img_w, prm.img_h);
+            buf.cbox[tid] = box_consts(px.x, px.y, px.z, px.w, want_atan);
+            my_g = AGN ? 0 : (int)(id % (unsigned)n_fg);
+            buf.cgroup[tid] = (unsigned char)my_g;
+        }
+        for (int i = tid; i < 16 * n_groups; i += IT) buf.wcnt[i] = 0;
+        for (int i = tid; i < n_groups * MW; i += IT) buf.nzW[i] = 0ull;
+        {
+            ulonglong2* m2 = reinterpret_cast<ulonglong2*>(buf.mat);
+            for (int i = tid; i < K * MW / 2; i += IT) m2[i] = make_ulonglong2(0ull, 0ull);
+        }
+        __syncthreads();
+        const unsigned peers = __match_any_sync(FULL, my_g);            // lanes of this warp with the same class
+        const int local_rank = __popc(peers & lt);
+        if (my_g >= 0 && local_rank == 0) buf.wcnt[warp * n_groups + my_g] = __popc(peers);
+        __syncthreads();
+        if (tid < n_groups) {                                           // class totals -> offsets (n_groups <= 255 < IT)
+            int tot = 0;
+            for (int w = 0; w < 16; ++w) tot += buf.wcnt[w * n_groups + tid];
+            us.hist[tid] = (unsigned)tot;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int g = 0; g < n_groups; ++g) { buf.coff[g] = run; run += (int)us.hist[g]; }
+            buf.coff[n_groups] = run;
+        }
+        int my_m = 0;
+        if (my_g >= 0) {
+            for (int w = 0; w < warp; ++w) my_m += buf.wcnt[w * n_groups + my_g];
+            my_m += local_rank;
+            buf.cpos[tid] = (unsigned short)my_m;
+        }
+        __syncthreads();
+        if (my_g >= 0) buf.clist[buf.coff[my_g] + my_m] = (unsigned short)tid;
+        for (int i = tid; i < n_groups * MW; i += IT) {                 // alive = every position the class has this round
+            const int g = i / MW, w = i % MW, n_c = buf.coff[g + 1] - buf.coff[g];
+            const int bits = min(max(n_c - 64 * w, 0), 64);
+            buf.aliveW[i] = bits == 64 ? ~0ull : ((1ull << bits) - 1ull);
+        }
+        __syncthreads();
+
+        // ---- pair tests --------------------------------------------------------------------------------
+        {
+            const int parts = K <= IT / 2 ? (K <= IT / 4 ? 4 : 2) : 1;    // threads sharing one entry
+            const int j = tid / parts, sub = tid % parts;
+            if (j < K) {
+                const BoxC c = buf.cbox[j];
+                const int g = (int)buf.cgroup[j], m = (int)buf.cpos[j];
+                bool hit = false;
+                const unsigned short* kl = buf.kidx + (size_t)g * max_keep;
+                const int ng = buf.ngroup[g];
+                for (int i = sub; i < ng; i += parts) hit |= suppresses<METRIC>(buf.kept[kl[i]], c, thr, thr_lo);
+                if (hit) atomicAnd(&buf.aliveW[g * MW + (m >> 6)], ~(1ull << (m & 63)));
+                const unsigned short* cl = buf.clist + buf.coff[g];
+                for (int mm = sub; mm < m; mm += parts) {
+                    const int i = (int)cl[mm];
+                    if (suppresses<METRIC>(buf.cbox[i], c, thr, thr_lo)) {
+                        atomicOr(&buf.mat[(size_t)i * MW + (m >> 6)], 1ull << (m & 63));
+                        atomicOr(&buf.nzW[g * MW + (mm >> 6)], 1ull << (mm & 63));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- resolve: one warp per class, rows in score order ----------------------------------------------
+        for (int g = warp; g < n_groups; g += IT / 32) {
+            const int n_c = buf.coff[g + 1] - buf.coff[g];
+            if (n_c == 0) continue;
+            const int words = (n_c + 63) >> 6;
+            const unsigned short* cl = buf.clist + buf.coff[g];
+            unsigned long long a = lane < MW ? buf.aliveW[g * MW + lane] : 0ull;
+            for (int w0 = 0; w0 < words; ++w0) {
+                unsigned long long pend = __shfl_sync(FULL, a, w0) & buf.nzW[g * MW + w0];
+                while (pend) {
+                    const int bit = __ffsll((long long)pend) - 1;
+                    const int i = (int)cl[w0 * 64 + bit];
+                    if (lane < MW) a &= ~buf.mat[(size_t)i * MW + lane];
+                    pend = __shfl_sync(FULL, a, w0) & buf.nzW[g * MW + w0] & ~((2ull << bit) - 1ull);
+                }
+            }
+            if (lane < MW) buf.aliveW[g * MW + lane] = a;
+        }
+        __syncthreads();
+
+        // ---- emit survivors in global score order ------------------------------------------------------------
+        bool alive = false;
+        if (my_g >= 0) alive = (buf.aliveW[my_g * MW + (my_m >> 6)] >> (my_m & 63)) & 1ull;
+        const unsigned ab = __ballot_sync(FULL, alive);
+        if (lane == 0) us.iscratch[warp] = __popc(ab);
+        __syncthreads();
+        int before = __popc(ab & lt), total_alive = 0;
+        for (int w = 0; w < IT / 32; ++w) { const int c = us.iscratch[w]; if (w < warp) before += c; total_alive += c; }
+        const int pos = kept_n + before;
+        if (alive && pos < max_keep) {
+            const BoxC bx = buf.cbox[tid];
+            buf.kept[pos] = bx;
+            // survivors of the class ahead of this one in the round: alive positions below m
+            int crank = 0;
+            for (int w = 0; w < (my_m >> 6); ++w) crank += __popcll(buf.aliveW[my_g * MW + w]);
+            crank += __popcll(buf.aliveW[my_g * MW + (my_m >> 6)] & ((1ull << (my_m & 63)) - 1ull));
+            buf.kidx[(size_t)my_g * max_keep + buf.ngroup[my_g] + crank] = (unsigned short)pos;
+            const unsigned long long key = buf.ckey[tid];
+            const unsigned id = 0xffffffffu - (unsigned)(key & 0xffffffffull);
+            prm.out_labels[o + pos] = (int64_t)(id % (unsigned)n_fg);
+            prm.out_scores[o + pos] = __uint_as_float((unsigned)(key >> 32) & 0x7fffffffu);
+            reinterpret_cast<float4*>(prm.out_boxes)[o + pos] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
+            if (prm.out_cand) prm.out_cand[o + pos] = (int32_t)id;
+        }
+        __syncthreads();
+        if (alive && pos < max_keep) atomicAdd(&buf.ngroup[my_g], 1);
+        kept_n = min(max_keep, kept_n + total_alive);
+        remaining -= K;
+        __syncthreads();
+    }
     if (tid == 0) prm.out_count[b] = kept_n;
 }
 
@@ -755,7 +997,7 @@ template <int METRIC, bool AGN, bool APPROX>
 static int launch_nms_image(const PredictParams& prm, size_t dyn, cudaStream_t stream) {
     int rc;
     if ((rc = set_smem(nms_image_kernel<METRIC, AGN, APPROX>, dyn))) return rc;
-    nms_image_kernel<METRIC, AGN, APPROX><<<prm.B, PT, dyn, stream>>>(prm);
+    nms_image_kernel<METRIC, AGN, APPROX><<<prm.B, IT, dyn, stream>>>(prm);
     SSDHOT_CHECK_LAUNCH();
     return SSDHOT_OK;
 }
@@ -835,7 +1077,7 @@ extern "C" int ssdhot_predict(const float* priors_cxcywh, int P, const float* lo
     if (metric != SSDHOT_METRIC_DIOU && metric != SSDHOT_METRIC_CIOU && metric != SSDHOT_METRIC_IOU) return SSDHOT_ERR_VALUE;
     if (!al16(priors_cxcywh) || !al16(loc_all) || !al16(out_boxes) || !al16(work) ||
         (reinterpret_cast<uintptr_t>(conf_all) & 7u)) return SSDHOT_ERR_ALIGN;
-    const size_t dyn = unit_smem_bytes(max_per_img, class_agnostic ? 0 : C - 1, true);
+    const size_t dyn = img_smem_bytes(max_per_img, class_agnostic ? 1 : C - 1);
     if (dyn > kMaxDynSmem) return SSDHOT_ERR_SHAPE;
     PredictParams prm = {};
     prm.pri = priors_cxcywh; prm.P = P; prm.loc_all = loc_all; prm.conf_all = conf_all; prm.B = B; prm.C = C;
