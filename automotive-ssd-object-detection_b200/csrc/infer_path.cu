@@ -800,7 +800,9 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
         }
         first = false;
         if (K == 0) continue;                               // (only margin strays: the next cut is lower)
-        bitonic_desc<CH>(buf.ckey);
+        if (K <= 128) bitonic_desc<128>(buf.ckey);           // (entries beyond K are zero and stay behind)
+        else if (K <= 256) bitonic_desc<256>(buf.ckey);
+        else bitonic_desc<CH>(buf.ckey);
 
         // ---- decode + class-local order --------------------------------------------------------------
         int my_g = -1;
@@ -851,23 +853,32 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
         __syncthreads();
 
         // ---- pair tests --------------------------------------------------------------------------------
+        // Entry j of class-local position m is tested against m earlier entries, so entries j and K-1-j
+        // (class positions ~m and ~n_c - m) form one work unit of near-constant size; the units are spread
+        // over all threads, `parts` threads striding through each unit's inner loops.
         {
-            const int parts = K <= IT / 2 ? (K <= IT / 4 ? 4 : 2) : 1;    // threads sharing one entry
-            const int j = tid / parts, sub = tid % parts;
-            if (j < K) {
-                const BoxC c = buf.cbox[j];
-                const int g = (int)buf.cgroup[j], m = (int)buf.cpos[j];
-                bool hit = false;
-                const unsigned short* kl = buf.kidx + (size_t)g * max_keep;
-                const int ng = buf.ngroup[g];
-                for (int i = sub; i < ng; i += parts) hit |= suppresses<METRIC>(buf.kept[kl[i]], c, thr, thr_lo);
-                if (hit) atomicAnd(&buf.aliveW[g * MW + (m >> 6)], ~(1ull << (m & 63)));
-                const unsigned short* cl = buf.clist + buf.coff[g];
-                for (int mm = sub; mm < m; mm += parts) {
-                    const int i = (int)cl[mm];
-                    if (suppresses<METRIC>(buf.cbox[i], c, thr, thr_lo)) {
-                        atomicOr(&buf.mat[(size_t)i * MW + (m >> 6)], 1ull << (m & 63));
-                        atomicOr(&buf.nzW[g * MW + (mm >> 6)], 1ull << (mm & 63));
+            const int units = (K + 1) >> 1;
+            const int parts = max(1, IT / units);
+            const int u = tid / parts, sub = tid % parts;
+            if (u < units) {
+#pragma unroll 1
+                for (int side = 0; side < 2; ++side) {
+                    const int j = side == 0 ? u : K - 1 - u;
+                    if (side == 1 && j == u) break;
+                    const BoxC c = buf.cbox[j];
+                    const int g = (int)buf.cgroup[j], m = (int)buf.cpos[j];
+                    bool hit = false;
+                    const unsigned short* kl = buf.kidx + (size_t)g * max_keep;
+                    const int ng = buf.ngroup[g];
+                    for (int i = sub; i < ng; i += parts) hit |= suppresses<METRIC>(buf.kept[kl[i]], c, thr, thr_lo);
+                    if (hit) atomicAnd(&buf.aliveW[g * MW + (m >> 6)], ~(1ull << (m & 63)));
+                    const unsigned short* cl = buf.clist + buf.coff[g];
+                    for (int mm = sub; mm < m; mm += parts) {
+                        const int i = (int)cl[mm];
+                        if (suppresses<METRIC>(buf.cbox[i], c, thr, thr_lo)) {
+                            atomicOr(&buf.mat[(size_t)i * MW + (m >> 6)], 1ull << (m & 63));
+                            atomicOr(&buf.nzW[g * MW + (mm >> 6)], 1ull << (mm & 63));
+                        }
                     }
                 }
             }
