@@ -539,7 +539,7 @@ __device__ __forceinline__ unsigned exact_score_key6(const float* __restrict__ r
 // more than 1e-4 (relative) away from the threshold and by the exact eager-CUDA arithmetic otherwise, so
 // the candidate SET is exact; the keys are approximate and nms_image_kernel refines the ones it pulls.
 template <int CT>
-__global__ void __launch_bounds__(ST) score_kernel(const PredictParams prm) {
+__global__ void __launch_bounds__(ST, 6) score_kernel(const PredictParams prm) {
     const int b = blockIdx.x / SCS, part = blockIdx.x % SCS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int seg = part * (ST / 32) + warp;

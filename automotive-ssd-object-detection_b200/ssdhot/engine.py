@@ -21,13 +21,15 @@ class HotPathStep:
     def __init__(self, priors: PriorSet, batch: int, n_classes: int, iou_thresh: float = 0.5,
                  neg_pos_ratio: float = 3.0, score_thresh: float = 0.01, nms_thresh: float = 0.45,
                  max_per_img: int = 200, class_agnostic: bool = False, metric: str = "diou",
-                 norm_wh=(300.0, 300.0), train_half: bool = True, infer_half: bool = True, max_gt: int = 64):
+                 norm_wh=(300.0, 300.0), train_half: bool = True, infer_half: bool = True, max_gt: int = 64,
+                 concurrent: bool = True):
         self.ps, self.B, self.C = priors, int(batch), int(n_classes)
         self.iou_thresh, self.ratio = float(iou_thresh), float(neg_pos_ratio)
         self.score_thresh, self.nms_thresh = float(score_thresh), float(nms_thresh)
         self.max_per_img, self.agnostic, self.metric = int(max_per_img), bool(class_agnostic), METRICS[metric]
         self.norm_wh = (float(norm_wh[0]), float(norm_wh[1]))
         self.train_half, self.infer_half = train_half, infer_half
+        self.concurrent, self._fork = bool(concurrent), None
         dev = priors.device
         L = _lib.lib()
         self.sums = torch.zeros((3,), dtype=torch.float64, device=dev)
@@ -68,15 +70,25 @@ class HotPathStep:
 
     def run(self, loc: torch.Tensor, conf_train: torch.Tensor, conf_infer: torch.Tensor, gt: PackedTargets,
             use_graph: bool = False) -> None:
-        """Both halves on the current stream.  With use_graph the launches are captured once per
-        distinct set of input buffers and replayed afterwards."""
+        """Both halves, issued from the current stream (the predict half forks onto a second stream when
+        `concurrent`, since the halves share nothing but read-only inputs).  With use_graph the launches
+        are captured once per distinct set of input buffers and replayed afterwards."""
         dev = self.ps.device
         if not use_graph:
-            s = torch.cuda.current_stream(dev).cuda_stream
+            cur = torch.cuda.current_stream(dev)
+            if self.train_half and self.infer_half and self.concurrent:
+                # the two halves are independent: fork the predict half onto a second stream and join
+                if self._fork is None:
+                    self._fork = torch.cuda.Stream(dev)
+                self._fork.wait_stream(cur)
+                self.launch_loss(loc, conf_train, gt, cur.cuda_stream)
+                self.launch_predict(loc, conf_infer, self._fork.cuda_stream)
+                cur.wait_stream(self._fork)
+                return
             if self.train_half:
-                self.launch_loss(loc, conf_train, gt, s)
+                self.launch_loss(loc, conf_train, gt, cur.cuda_stream)
             if self.infer_half:
-                self.launch_predict(loc, conf_infer, s)
+                self.launch_predict(loc, conf_infer, cur.cuda_stream)
             return
         key = (loc.data_ptr(), conf_train.data_ptr(), conf_infer.data_ptr(), gt.boxes.data_ptr(), gt.max_gt)
         g = self._graphs.get(key)

@@ -37,6 +37,9 @@ CFG = 3
 N_SETS = 4             # rotating input sets: 4 x 89.5 MB > 126 MB L2, so no step re-reads a hot L2
 P, C = 8732, 6
 METRIC = "images/s for match+mined loss and decode+DIoU-NMS at bs=256 per GPU"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of each half's kernels at this workload, from the
+# `ncu --set full` capture summarised in profiles/ (train_image_kernel; score_kernel + nms_image_kernel)
+TRAFFIC = {"match_loss": 56.7e6, "decode_nms": 53.8e6 + 13.7e6 + 32.1e6, "source": "profiles/r01_final_ncu_full_summary.txt"}
 
 
 def peaks():
@@ -169,7 +172,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ssdhot", choices=["ssdhot", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying a CUDA graph")
+    ap.add_argument("--serial", action="store_true", help="run the two halves back to back on one stream instead of forked")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-large-batch", action="store_true", help="skip the extra B=2048 roofline measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -200,7 +205,7 @@ def main():
                          gt=ssdhot.pack_targets(cfg["targets"], dev)))
     ps = ssdhot.PriorSet.default(dev)
     step = HotPathStep(ps, BATCH, C, spec["iou_thresh"], spec["ratio"], spec["score_thresh"], spec["nms_thresh"],
-                       spec["max_per_img"])
+                       spec["max_per_img"], concurrent=not args.serial)
     use_graph = not args.no_graph
 
     def one_step(i):
@@ -269,10 +274,13 @@ def main():
     dom_is_pred = ms_pred >= ms_loss
     dom_ms, dom_bytes = (ms_pred, bytes_pred) if dom_is_pred else (ms_loss, bytes_loss)
     roofline = {
-        "bound": "hbm", "kernel": "predict_unit_kernel (decode+threshold+rank+NMS)" if dom_is_pred else
-        "train_kernel<FUSED> (match+encode+mined loss)",
+        "bound": "hbm", "kernel": "score_kernel + nms_image_kernel (decode + threshold + rank + NMS)" if dom_is_pred else
+        "train_image_kernel + finalize_sums_kernel (match + encode + mined loss)",
         "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-        "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+        "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": TRAFFIC["decode_nms" if dom_is_pred else "match_loss"],
+        "traffic_source": TRAFFIC["source"], "peak_source": peak_src,
+        "note": "algorithmic bytes = SURVEY.md 8(d) figure of the whole half (conf_all + loc_all + GT / outputs); the "
+                "kernels are instruction-issue and latency bound at this batch size, not DRAM bound (profiles/)",
         "parts": {
             "match_loss": {"ms": ms_loss, "algorithmic_bytes": bytes_loss, "achieved": bytes_loss / (ms_loss * 1e-3) / 1e9,
                            "frac": bytes_loss / (ms_loss * 1e-3) / 1e9 / peak, "images_per_s": BATCH / (ms_loss * 1e-3)},
@@ -280,6 +288,42 @@ def main():
                            "frac": bytes_pred / (ms_pred * 1e-3) / 1e9 / peak, "images_per_s": BATCH / (ms_pred * 1e-3)},
         },
     }
+
+    # ---- the same halves at B = 2048 per GPU (wave quantisation and launch latency amortised) -------------
+    large = None
+    if not args.skip_large_batch and rank == 0:
+        LB = 2048
+        cfg_l = synth.config(CFG, batch=LB, seed_offset=977)
+        big = dict(loc=cfg_l["loc_all"].to(dev), conf_t=cfg_l["conf_train"].to(dev), conf_i=cfg_l["conf_infer"].to(dev),
+                   gt=ssdhot.pack_targets(cfg_l["targets"], dev))
+        step_l = HotPathStep(ps, LB, C, spec["iou_thresh"], spec["ratio"], spec["score_thresh"], spec["nms_thresh"],
+                             spec["max_per_img"])
+        st = torch.cuda.current_stream(dev).cuda_stream
+
+        def time_large(train: bool, iters: int = 12):
+            f = (lambda: step_l.launch_loss(big["loc"], big["conf_t"], big["gt"], st)) if train else \
+                (lambda: step_l.launch_predict(big["loc"], big["conf_i"], st))
+            for _ in range(3):
+                f()
+            torch.cuda.synchronize(dev)
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+            for a, b in evs:
+                a.record(); f(); b.record()
+            torch.cuda.synchronize(dev)
+            return statistics.median(a.elapsed_time(b) for a, b in evs)
+
+        ml, mp = time_large(True), time_large(False)
+        g_l = statistics.mean(float(t["boxes"].shape[0]) for t in cfg_l["targets"])
+        k_l = float(step_l.count.float().mean().item())
+        bl, bp = LB * (349296 + 24 * g_l + 12), LB * (349296 + 28 * k_l + 4)
+        large = {"per_gpu_batch": LB, "l2": "one input set of 1.1 GB per half (>> 126 MB L2)",
+                 "match_loss": {"ms": ml, "achieved": bl / (ml * 1e-3) / 1e9, "frac": bl / (ml * 1e-3) / 1e9 / peak,
+                                "images_per_s": LB / (ml * 1e-3)},
+                 "decode_nms": {"ms": mp, "achieved": bp / (mp * 1e-3) / 1e9, "frac": bp / (mp * 1e-3) / 1e9 / peak,
+                                "images_per_s": LB / (mp * 1e-3)}}
+        del big, step_l, cfg_l
+        torch.cuda.empty_cache()
+    roofline["large_batch"] = large
 
     # ---- end to end through the drop-in API, host buffers ------------------------------------------
     pinned = []
@@ -340,7 +384,8 @@ def main():
                                    "nms 0.45 / max 200), P=8732, C=6, G~U{1..20}",
                        "global_batch": BATCH * world, "per_gpu_batch": BATCH,
                        "l2": f"inputs rotate over {N_SETS} sets of 89.5 MB (> 126 MB L2) so no step re-reads a warm L2",
-                       "cuda_graph": use_graph, "parallelism": f"image-sharded x{world}, all-reduce of 3 doubles"},
+                       "cuda_graph": use_graph, "halves": "serial" if args.serial else "forked (independent halves on two streams)",
+                       "parallelism": f"image-sharded x{world}, all-reduce of 3 doubles"},
             "parts": {"match_loss_images_per_s": BATCH * world / (ms_loss * 1e-3),
                       "decode_nms_images_per_s": BATCH * world / (ms_pred * 1e-3)},
             "roofline": roofline,
