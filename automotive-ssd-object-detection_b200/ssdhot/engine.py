@@ -22,7 +22,7 @@ class HotPathStep:
                  neg_pos_ratio: float = 3.0, score_thresh: float = 0.01, nms_thresh: float = 0.45,
                  max_per_img: int = 200, class_agnostic: bool = False, metric: str = "diou",
                  norm_wh=(300.0, 300.0), train_half: bool = True, infer_half: bool = True, max_gt: int = 64,
-                 concurrent: bool = True):
+                 concurrent: bool = True, group=None):
         self.ps, self.B, self.C = priors, int(batch), int(n_classes)
         self.iou_thresh, self.ratio = float(iou_thresh), float(neg_pos_ratio)
         self.score_thresh, self.nms_thresh = float(score_thresh), float(nms_thresh)
@@ -30,6 +30,7 @@ class HotPathStep:
         self.norm_wh = (float(norm_wh[0]), float(norm_wh[1]))
         self.train_half, self.infer_half = train_half, infer_half
         self.concurrent, self._fork = bool(concurrent), None
+        self.group = group          # process group (True = default) whose ranks share the batch: sums are all-reduced in run()
         dev = priors.device
         L = _lib.lib()
         self.sums = torch.zeros((3,), dtype=torch.float64, device=dev)
@@ -83,10 +84,12 @@ class HotPathStep:
                 self._fork.wait_stream(cur)
                 self.launch_loss(loc, conf_train, gt, cur.cuda_stream)
                 self.launch_predict(loc, conf_infer, self._fork.cuda_stream)
+                self._reduce()                                   # overlaps the predict half
                 cur.wait_stream(self._fork)
                 return
             if self.train_half:
                 self.launch_loss(loc, conf_train, gt, cur.cuda_stream)
+                self._reduce()
             if self.infer_half:
                 self.launch_predict(loc, conf_infer, cur.cuda_stream)
             return
@@ -104,6 +107,11 @@ class HotPathStep:
             torch.cuda.current_stream(dev).wait_stream(side)
             self._graphs[key] = g
         g.replay()
+
+    def _reduce(self) -> None:
+        """The sharded path's only exchange: all-reduce [sum smooth-L1, sum CE, sum positives] in place."""
+        if self.group is not None:
+            _dist.combine_sums(self.sums, None if self.group is True else self.group)
 
     def losses(self, group=None):
         """(loc_loss, conf_loss) of the last run; all-reduces the three sums first when sharded."""

@@ -212,7 +212,7 @@ def main():
         s = sets[i % N_SETS]
         step.run(s["loc"], s["conf_t"], s["conf_i"], s["gt"], use_graph=use_graph)
         if group is not None:
-            D.combine_sums(step.sums)
+            D.combine_sums(step.sums)       # outside the graph: a captured NCCL collective hung at process exit on this stack
 
     def barrier():
         if world > 1:
