@@ -52,6 +52,7 @@ struct TrainParams {
     uint16_t* code;        // [B,P] 0 = negative, 1 + matched box (fused path: match -> loss hand-off)
     double* img_part;      // [B][2] per-image (smooth-L1, CE) sums
     int32_t* flags;
+    unsigned long long* timeline;   // debug: [B][16] %globaltimer stamps of the fused kernel's phases (or null)
 };
 
 // SSD300 pyramid (SSD_from_scratch.py:289-290): used only to pick seed priors, never for results
@@ -618,12 +619,13 @@ constexpr int FT = 768;                      // threads; 2 CTAs per SM
 constexpr int FAST_MAX_GT = 64;
 constexpr int GT_ROUND = 32;                 // boxes enumerated per round
 constexpr int NSEG = GT_ROUND * 32;          // (box, level-shape) segments per round
-constexpr int PAIR_CAP = 2048;               // gate survivors staged for the exact pass (rest: inline)
+constexpr int PAIR_CAP = 1536;               // listed gate survivors of an image (rest: settled inline, box recomputed)
+constexpr int MT_LOSS = 256;                 // threads (warps 0..7) that match while the others stream the logits
 constexpr int POS_PER_WARP = 80;             // per-warp list of positive priors (rest: handled inline)
 constexpr int SEL_PER_WARP = 168;            // per-warp list of certainly-mined negatives
 constexpr int BAND_CAP = 1024;
 constexpr unsigned kOrdTwo = 0xC0000000u;    // ord_encode(2.0f): the forced-match value (SFS:747)
-constexpr int FUSED_SCRATCH = 4112 + 8192 + 4 * PAIR_CAP + 2 * NSEG;     // 22544
+constexpr int FUSED_SCRATCH = 4112 + 8192 + 8 * PAIR_CAP + 2 * NSEG;     // 26640: matching view; the mining lists reuse it
 
 struct FusedStatic {
     float4 gt_a[FAST_MAX_GT];                // x1 y1 x2 y2 (normalised)
@@ -634,13 +636,13 @@ struct FusedStatic {
     int champ[FAST_MAX_GT];
     unsigned char kind[FAST_MAX_GT];         // 0 = rectangles, 1 = dense sweep, 2 = all-NaN column
     LossShared ls;
-    int first_nan, n_dense, n_pair, n_work, n_band, n_sure;
-    int wcount[FT / 32];                     // per-warp list lengths (positives, then certain negatives)
+    int first_nan, n_dense, n_pair, n_work, n_band, n_sure, pair_overflow, n_pos_img;
+    int wcount[FT / 32], wcount2[FT / 32];   // per-warp list lengths: positives, certainly-mined negatives
     unsigned r_bin, r_above;
 };
 
 __host__ __device__ inline size_t fused_smem_bytes(int P) {
-    return (size_t)P * 8 + FUSED_SCRATCH + (size_t)(FT / 32) * (POS_PER_WARP + SEL_PER_WARP) * 2;
+    return (size_t)P * 8 + FUSED_SCRATCH + 8192;         // table | scratch | CE histogram
 }
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -748,54 +750,59 @@ __device__ __forceinline__ void axis_hull(float g1, float g2, int side, float w,
     if (g2 > 1.0f - w) for (int i = side - nb; i < side; ++i) test(i);
 }
 
-template <bool LOSS>
-__global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams prm) {
-    extern __shared__ __align__(16) unsigned char dyn[];
-    __shared__ FusedStatic fs;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define SSDHOT_STAMP(k) do { if (prm.timeline && (threadIdx.x & 31) == 0) { if (threadIdx.x == 0 || (k) == 2) prm.timeline[(long long)blockIdx.x * 16 + (k)] = globaltimer_ns(); } } while (0)
+
+// Barrier of the threads that run the matching: the whole CTA (MT == FT) or its first MT threads (named barrier 1),
+// while the remaining warps stream the logits.
+template <int MT>
+__device__ __forceinline__ void role_sync() {
+    if (MT == FT) __syncthreads();
+    else asm volatile("bar.sync 1, %0;" ::"n"(MT) : "memory");
+}
+
+// Shared-memory views of the fused kernel.  The table has one 64-bit slot per prior: the HIGH word is the best
+// ord(CIoU) any box reached at that prior (matching, 32-bit atomicMax), the LOW word is written by the logit
+// stream (CE bits of the prior as a negative) and, once a prior is known to be positive, replaced by
+// 0x80000000 | (63 - matched box) -- so the two roles never touch the same word.
+struct FusedViews {
+    unsigned* lo;              // lo[2p]
+    unsigned* hi;              // hi[2p]  (= lo + 1)
+    int* seg_start;            // [NSEG + 1]
+    unsigned* seg_info;        // [NSEG] i0 | j0<<6 | ni<<12 | side<<18 | shapes<<24
+    unsigned* seg_base;        // [NSEG] first prior of the (level, shape) | box << 16
+    unsigned* pair_pg;         // [PAIR_CAP] prior | box << 16 : every pair that passed the IoU gate (all rounds)
+    unsigned* pair_ov;         // [PAIR_CAP] ord(CIoU) of that pair
+    uint16_t* work_list;       // [NSEG] (box in round) << 5 | level-shape
+};
+
+// ---- matching (sections 1 and 2 of the kernel), run by the first MT threads of the CTA --------------------
+template <int MT>
+__device__ __forceinline__ void match_phase(const TrainParams& prm, FusedStatic& fs, const FusedViews& v, int G, int g_begin) {
+    const int mtid = threadIdx.x, lane = mtid & 31, mwarp = mtid >> 5;
     const int P = prm.P;
-    unsigned long long* table = reinterpret_cast<unsigned long long*>(dyn);        // [P] (ord(ciou) << 32 | ~box); later (0, CE bits)
-    unsigned char* scratch = dyn + (size_t)P * 8;
-    uint16_t* pos_list = reinterpret_cast<uint16_t*>(scratch + FUSED_SCRATCH);
-    uint16_t* sel_list = pos_list + (FT / 32) * POS_PER_WARP;
-    // matching view of the scratch
-    int* seg_start = reinterpret_cast<int*>(scratch);                              // [NSEG + 1] (+ pad to 4112 B)
-    unsigned* seg_info = reinterpret_cast<unsigned*>(scratch + 4112);              // [NSEG] i0 | j0<<6 | ni<<12 | side<<18 | shapes<<24
-    unsigned* seg_base = reinterpret_cast<unsigned*>(scratch + 4112 + 4096);       // [NSEG] first prior of the (level, shape) | box << 16
-    unsigned* pair_list = reinterpret_cast<unsigned*>(scratch + 4112 + 8192);      // [PAIR_CAP] prior | box << 16
-    uint16_t* work_list = reinterpret_cast<uint16_t*>(scratch + 4112 + 8192 + 4 * PAIR_CAP);   // [NSEG] (box in round) << 5 | level-shape
-    // mining view of the scratch
-    unsigned* hist16 = reinterpret_cast<unsigned*>(scratch);                       // [2048] 4096 bins x 16 bit
-    unsigned* band_v = hist16 + 2048;                                              // [BAND_CAP] exact CE bits
-    unsigned* band_sorted = band_v + BAND_CAP;                                     // [BAND_CAP] the band's winners by rank
-    uint16_t* band_p = reinterpret_cast<uint16_t*>(band_sorted + BAND_CAP);        // [BAND_CAP]
-
-    const int g_begin = prm.gt_offsets[b];
-    int G = prm.gt_offsets[b + 1] - g_begin;
-    if (G > prm.max_gt) {
-        if (tid == 0 && prm.flags) atomicOr(prm.flags, 1);
-        G = prm.max_gt;
-    }
-
-    // ---- 0. clear ------------------------------------------------------------------------------
-    if (tid == 0) { fs.first_nan = INT_MAX; fs.n_dense = 0; fs.n_band = 0; }
-    __syncthreads();
-    {
-        ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
-        for (int i = tid; i < P / 2; i += FT) t2[i] = make_ulonglong2(0ull, 0ull);
-        if ((P & 1) && tid == 0) table[P - 1] = 0ull;
-    }
     const float thresh = prm.thresh;
-
-    // ---- 1. matching, GT_ROUND boxes per round -----------------------------------------------------
+    // record a pair whose CIoU may matter: best value per prior (high word), best prior per box, list entry
+    auto settle_pair = [&](int p, int g, int slot) {
+        const float val = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, p), gt_box(fs.gt_a[g], fs.gt_b[g]));
+        const unsigned o = ord_encode(val);
+        atomicMax(&v.hi[2 * p], o);
+        const unsigned long long ck = ((unsigned long long)o << 32) | (unsigned long long)(0xffffffffu - (unsigned)p);
+        if (ck > *reinterpret_cast<volatile unsigned long long*>(&fs.col[g])) atomicMax(&fs.col[g], ck);
+        if (slot < PAIR_CAP) v.pair_ov[slot] = o;
+    };
     for (int g0 = 0; g0 < G; g0 += GT_ROUND) {
         const int gn = min(GT_ROUND, G - g0);
-        if (tid == 0) fs.n_pair = 0;
+        if (mtid == 0) fs.n_work = 0;
+        const int round_begin = min(fs.n_pair, PAIR_CAP);       // (stable: the previous round ended with a barrier)
+        role_sync<MT>();
         // 1a. one warp per box: constants, seed bound, and the (level, shape) combinations whose sizes can
         //     reach IoU >= lim at all (1-D and area ratios, clamped extents >= half the nominal ones)
-        if (tid == 0) fs.n_work = 0;
-        __syncthreads();
-        for (int gl = warp; gl < gn; gl += FT / 32) {
+        for (int gl = mwarp; gl < gn; gl += MT / 32) {
             const int g = g0 + gl;
             const float4 px = ldg4(prm.gt_boxes + 4ll * (g_begin + g));
             const BoxC c = box_consts(fdiv(px.x, prm.norm_w), fdiv(px.y, prm.norm_h), fdiv(px.z, prm.norm_w), fdiv(px.w, prm.norm_h), true);
@@ -811,8 +818,8 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                 ix = min(max(ix, 0), side - 1);
                 iy = min(max(iy, 0), side - 1);
                 const int ps = off + (iy * side + ix) * shapes + shp;
-                const float v = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, ps), c);
-                const float cb0 = ord_decode(__reduce_max_sync(FULL, ord_encode(v)));
+                const float val = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, ps), c);
+                const float cb0 = ord_decode(__reduce_max_sync(FULL, ord_encode(val)));
                 if (cb0 > 0.0f) lim = fmaxf(fmul(kPruneSlack, fminf(cb0, thresh)), 1e-30f);
                 const float4 sh = ldg4(prm.pri + 4ll * (off + shp));                   // (w, h) of this level-shape
                 const float w = sh.z, h = sh.w, l2 = 0.99f * lim;
@@ -822,7 +829,7 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                 int dst = 0;
                 if (lane == 0 && bal) dst = atomicAdd(&fs.n_work, __popc(bal));
                 dst = __shfl_sync(FULL, dst, 0) + __popc(bal & ((1u << lane) - 1u));
-                if (keep) work_list[dst] = (uint16_t)((gl << 5) | lane);
+                if (keep) v.work_list[dst] = (uint16_t)((gl << 5) | lane);
             }
             if (lane == 0) {
                 fs.gt_a[g] = make_float4(c.x1, c.y1, c.x2, c.y2);
@@ -836,15 +843,16 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                 if (kind == 1) atomicAdd(&fs.n_dense, 1);
             }
         }
-        __syncthreads();
+        role_sync<MT>();
+        SSDHOT_STAMP(11);
         // 1a'. one thread per surviving (box, level-shape): its rectangle of candidate cells
         {
             const int n_work = fs.n_work;
-            for (int e = tid; e < NSEG; e += FT) {
+            for (int e = mtid; e < NSEG; e += MT) {
                 int n = 0;
                 unsigned info = 0u, base = 0u;
                 if (e < n_work) {
-                    const int wk = (int)work_list[e], g = g0 + (wk >> 5), combo = wk & 31;
+                    const int wk = (int)v.work_list[e], g = g0 + (wk >> 5), combo = wk & 31;
                     const int lv = kSeedLevel[combo], side = kLevelSide[lv], shapes = kLevelShapes[lv], off = kLevelOffset[lv];
                     const int shp = kSeedShape[combo];
                     const float4 sh = ldg4(prm.pri + 4ll * (off + shp));
@@ -873,54 +881,59 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                         }
                     }
                 }
-                seg_start[e] = n;
-                seg_info[e] = info;
-                seg_base[e] = base;
+                v.seg_start[e] = n;
+                v.seg_info[e] = info;
+                v.seg_base[e] = base;
             }
         }
-        __syncthreads();
-        // 1b. exclusive scan of the NSEG segment sizes (two per thread, threads 0..511)
+        role_sync<MT>();
+        // 1b. exclusive scan of the NSEG segment sizes (EPT consecutive entries per thread)
         {
-            int a = 0, c2 = 0;
-            if (tid < NSEG / 2) { a = seg_start[2 * tid]; c2 = seg_start[2 * tid + 1]; }
-            int incl = a + c2;
+            constexpr int EPT = (NSEG + MT - 1) / MT;
+            int cnt[EPT], sum = 0;
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                const int e = mtid * EPT + k;
+                cnt[k] = e < NSEG ? v.seg_start[e] : 0;
+                sum += cnt[k];
+            }
+            int incl = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int y = __shfl_up_sync(FULL, incl, o);
                 if (lane >= o) incl += y;
             }
-            if (lane == 31) fs.ls.iscratch[warp] = incl;
-            __syncthreads();
-            int excl = incl - (a + c2);
-            for (int w = 0; w < warp; ++w) excl += fs.ls.iscratch[w];
-            if (tid < NSEG / 2) { seg_start[2 * tid] = excl; seg_start[2 * tid + 1] = excl + a; }
-            if (tid == NSEG / 2 - 1) seg_start[NSEG] = excl + a + c2;
-            __syncthreads();
+            if (lane == 31) fs.ls.iscratch[mwarp] = incl;
+            role_sync<MT>();
+            int run = incl - sum;
+            for (int w = 0; w < mwarp; ++w) run += fs.ls.iscratch[w];
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                const int e = mtid * EPT + k;
+                if (e < NSEG) v.seg_start[e] = run;
+                run += cnt[k];
+            }
+            if (mtid == MT - 1) v.seg_start[NSEG] = run;        // (the last thread's range ends at or beyond NSEG)
+            role_sync<MT>();
         }
-        // 1c. every candidate cell: cheap IoU gate; survivors are staged for the exact pass
-        const int T = seg_start[NSEG];
-        auto exact_pair = [&](int p, int g) {
-            const float v = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, p), gt_box(fs.gt_a[g], fs.gt_b[g]));
-            const unsigned o = ord_encode(v);
-            atomicMax(&table[p], ((unsigned long long)o << 32) | (unsigned long long)(0xffffffffu - (unsigned)g));
-            const unsigned long long ck = ((unsigned long long)o << 32) | (unsigned long long)(0xffffffffu - (unsigned)p);
-            if (ck > *reinterpret_cast<volatile unsigned long long*>(&fs.col[g])) atomicMax(&fs.col[g], ck);
-        };
-        for (int t0 = 0; t0 < T; t0 += FT) {
-            const int t = t0 + tid;
+        SSDHOT_STAMP(12);
+        // 1c. every candidate cell: cheap IoU gate; survivors join the pair list
+        const int T = v.seg_start[NSEG];
+        for (int t0 = 0; t0 < T; t0 += MT) {
+            const int t = t0 + mtid;
             bool pass = false;
             int p = 0, g = 0;
             if (t < T) {
                 int lo = 0, hi = NSEG;                       // seg_start[lo] <= t < seg_start[hi]
                 while (hi - lo > 1) {
                     const int mid = (lo + hi) >> 1;
-                    if (seg_start[mid] <= t) lo = mid; else hi = mid;
+                    if (v.seg_start[mid] <= t) lo = mid; else hi = mid;
                 }
-                const unsigned info = seg_info[lo];
-                const int local = t - seg_start[lo];
+                const unsigned info = v.seg_info[lo];
+                const int local = t - v.seg_start[lo];
                 const int ni = (int)((info >> 12) & 63u), side = (int)((info >> 18) & 63u), shapes = (int)(info >> 24);
                 const int lj = local / ni, li = local - lj * ni;
-                const unsigned sb = seg_base[lo];
+                const unsigned sb = v.seg_base[lo];
                 p = (int)(sb & 0xffffu) + (((int)((info >> 6) & 63u) + lj) * side + (int)(info & 63u) + li) * shapes;
                 g = (int)(sb >> 16);
                 const float4 pb = ldg4(prm.pri_xyxy + 4ll * p);
@@ -938,44 +951,50 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                 if (lane == 0) dst = atomicAdd(&fs.n_pair, __popc(bal));
                 dst = __shfl_sync(FULL, dst, 0) + __popc(bal & ((1u << lane) - 1u));
                 if (pass) {
-                    if (dst < PAIR_CAP) pair_list[dst] = (unsigned)p | ((unsigned)g << 16);
-                    else exact_pair(p, g);
+                    if (dst < PAIR_CAP) v.pair_pg[dst] = (unsigned)p | ((unsigned)g << 16);
+                    else { settle_pair(p, g, dst); fs.pair_overflow = 1; }   // unlisted: its box is recovered by recomputation
                 }
             }
         }
-        __syncthreads();
-        // 1d. exact CIoU of the staged pairs
+        role_sync<MT>();
+        SSDHOT_STAMP(13);
+        // 1d. exact CIoU of this round's listed pairs
         {
-            const int n_pair = min(fs.n_pair, PAIR_CAP);
-            for (int e = tid; e < n_pair; e += FT) {
-                const unsigned pr = pair_list[e];
-                exact_pair((int)(pr & 0xffffu), (int)(pr >> 16));
+            const int round_end = min(fs.n_pair, PAIR_CAP);
+            for (int e = round_begin + mtid; e < round_end; e += MT) {
+                const unsigned pr = v.pair_pg[e];
+                settle_pair((int)(pr & 0xffffu), (int)(pr >> 16), e);
             }
         }
-        __syncthreads();
+        role_sync<MT>();
     }
-    __syncthreads();                   // (G == 0: the clear is complete)
 
+    SSDHOT_STAMP(14);
     // ---- 2. champions; dense sweep of the columns the rectangles could not settle ------------------
-    if (tid < G) {
-        const int g = tid;
+    if (mtid < G) {
+        const int g = mtid;
         if (fs.kind[g] == 0) {
             const unsigned long long key = fs.col[g];
             if ((unsigned)(key >> 32) > ord_encode(0.0f)) fs.champ[g] = (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
             else { fs.kind[g] = 1; atomicAdd(&fs.n_dense, 1); }
         }
     }
-    __syncthreads();
+    role_sync<MT>();
+    auto list_pair = [&](int p, int g, unsigned o) {         // a pair found outside the rectangles
+        const int dst = atomicAdd(&fs.n_pair, 1);
+        if (dst < PAIR_CAP) { v.pair_pg[dst] = (unsigned)p | ((unsigned)g << 16); v.pair_ov[dst] = o; }
+        else fs.pair_overflow = 1;
+    };
     if (fs.n_dense > 0) {
         for (int g = 0; g < G; ++g) {
-            if (fs.kind[g] != 1) continue;              // CTA-uniform
+            if (fs.kind[g] != 1) continue;              // uniform over the role
             const BoxC gc = gt_box(fs.gt_a[g], fs.gt_b[g]);
-            if (tid == 0) fs.col[g] = 0ull;
-            __syncthreads();
+            if (mtid == 0) fs.col[g] = 0ull;
+            role_sync<MT>();
             unsigned long long best = 0ull;
-            for (int p = tid; p < P; p += FT) {
-                const float v = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, p), gc);
-                const unsigned long long ck = ((unsigned long long)ord_encode(v) << 32) | (unsigned long long)(0xffffffffu - (unsigned)p);
+            for (int p = mtid; p < P; p += MT) {
+                const float val = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, p), gc);
+                const unsigned long long ck = ((unsigned long long)ord_encode(val) << 32) | (unsigned long long)(0xffffffffu - (unsigned)p);
                 best = ck > best ? ck : best;
             }
 #pragma unroll
@@ -984,34 +1003,151 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                 best = y > best ? y : best;
             }
             if (lane == 0) atomicMax(&fs.col[g], best);
-            __syncthreads();
+            role_sync<MT>();
             const int champ = (int)(0xffffffffu - (unsigned)(fs.col[g] & 0xffffffffull));
-            if (tid == 0) fs.champ[g] = champ;
+            if (mtid == 0) fs.champ[g] = champ;
             // rows: the champion's entry becomes 2.0 below (SFS:747 overwrites it); the others keep their CIoU
-            for (int p = tid; p < P; p += FT) {
+            for (int p = mtid; p < P; p += MT) {
                 if (p == champ) continue;
-                const float v = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, p), gc);
-                if (v >= thresh || v != v)
-                    atomicMax(&table[p], ((unsigned long long)ord_encode(v) << 32) | (unsigned long long)(0xffffffffu - (unsigned)g));
+                const float val = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, p), gc);
+                if (val != val) atomicMax(&v.hi[2 * p], 0xffffffffu);
+                else if (val >= thresh) { atomicMax(&v.hi[2 * p], ord_encode(val)); list_pair(p, g, ord_encode(val)); }
             }
         }
-        __syncthreads();
+        role_sync<MT>();
     }
-    // forced matches: row champ[g], column g = 2.0; the lowest box index wins a shared champion
-    if (tid < G) atomicMax(&table[fs.champ[tid]], ((unsigned long long)kOrdTwo << 32) | (unsigned long long)(0xffffffffu - (unsigned)tid));
+    // forced matches: row champ[g], column g = 2.0 (the lowest box index wins a shared champion: resolved with the list)
+    if (mtid < G) {
+        atomicMax(&v.hi[2 * fs.champ[mtid]], kOrdTwo);
+        list_pair(fs.champ[mtid], mtid, kOrdTwo);
+    }
+    role_sync<MT>();
+}
+
+template <bool LOSS>
+__global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams prm) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ FusedStatic fs;
+    SSDHOT_STAMP(0);
+    constexpr int MT = LOSS ? MT_LOSS : FT;                  // threads that run the matching
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = prm.P;
+    unsigned long long* table = reinterpret_cast<unsigned long long*>(dyn);
+    unsigned char* scratch = dyn + (size_t)P * 8;
+    unsigned* hist16 = reinterpret_cast<unsigned*>(scratch + FUSED_SCRATCH);       // [2048] 4096 bins x 16 bit (own region)
+    FusedViews v;
+    v.lo = reinterpret_cast<unsigned*>(table);
+    v.hi = v.lo + 1;
+    v.seg_start = reinterpret_cast<int*>(scratch);
+    v.seg_info = reinterpret_cast<unsigned*>(scratch + 4112);
+    v.seg_base = reinterpret_cast<unsigned*>(scratch + 4112 + 4096);
+    v.pair_pg = reinterpret_cast<unsigned*>(scratch + 4112 + 8192);
+    v.pair_ov = v.pair_pg + PAIR_CAP;
+    v.work_list = reinterpret_cast<uint16_t*>(v.pair_ov + PAIR_CAP);
+    // after the matching the scratch holds the lists of the mining
+    uint16_t* pos_list = reinterpret_cast<uint16_t*>(scratch);                     // [FT/32][POS_PER_WARP]
+    uint16_t* sel_list = pos_list + (FT / 32) * POS_PER_WARP;                      // [FT/32][SEL_PER_WARP]
+    unsigned* band_v = reinterpret_cast<unsigned*>(sel_list + (FT / 32) * SEL_PER_WARP);   // [BAND_CAP] exact CE bits
+    unsigned* band_sorted = band_v + BAND_CAP;                                     // [BAND_CAP] the band's winners by rank
+    uint16_t* band_p = reinterpret_cast<uint16_t*>(band_sorted + BAND_CAP);        // [BAND_CAP]
+
+    const int g_begin = prm.gt_offsets[b];
+    int G = prm.gt_offsets[b + 1] - g_begin;
+    if (G > prm.max_gt) {
+        if (tid == 0 && prm.flags) atomicOr(prm.flags, 1);
+        G = prm.max_gt;
+    }
+
+    // ---- 0. clear ------------------------------------------------------------------------------
+    if (tid == 0) { fs.first_nan = INT_MAX; fs.n_dense = 0; fs.n_band = 0; fs.n_pair = 0; fs.pair_overflow = 0; fs.n_pos_img = 0; fs.n_sure = 0; }
+    {
+        ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
+        for (int i = tid; i < P / 2; i += FT) t2[i] = make_ulonglong2(0ull, 0ull);
+        if ((P & 1) && tid == 0) table[P - 1] = 0ull;
+        if (LOSS) for (int i = tid; i < 2048; i += FT) hist16[i] = 0u;
+    }
     __syncthreads();
+    const float thresh = prm.thresh;
+    const float* conf_b = prm.conf_all + (long long)b * P * 6;
+
+    // ---- 1, 2 (warps 0..7): matching  ||  3 (the other warps): approximate CE of every prior ----------------
+    SSDHOT_STAMP(1);
+    if (tid < MT) {
+        match_phase<MT>(prm, fs, v, G, g_begin);
+        SSDHOT_STAMP(3);
+    } else if (LOSS) {
+        const float4* src = reinterpret_cast<const float4*>(conf_b);
+        const int n_pairs = P / 2;
+#pragma unroll 2
+        for (int q = tid - MT; q < n_pairs; q += FT - MT) {
+            const float4 A = __ldg(src + 3 * q), Bv = __ldg(src + 3 * q + 1), Cv = __ldg(src + 3 * q + 2);
+            const unsigned k0 = __float_as_uint(approx_ce6(A.x, A.y, A.z, A.w, Bv.x, Bv.y));
+            const unsigned k1 = __float_as_uint(approx_ce6(Bv.z, Bv.w, Cv.x, Cv.y, Cv.z, Cv.w));
+            v.lo[4 * q] = k0;
+            v.lo[4 * q + 2] = k1;
+            ce_hist_add(hist16, k0);
+            ce_hist_add(hist16, k1);
+        }
+        if ((P & 1) && tid == MT) {                          // odd P: the last row (never SSD300)
+            const float* r = conf_b + 6ll * (P - 1);
+            const unsigned k = __float_as_uint(approx_ce6(r[0], r[1], r[2], r[3], r[4], r[5]));
+            v.lo[2 * (P - 1)] = k;
+            ce_hist_add(hist16, k);
+        }
+        if (tid == FT - 32) SSDHOT_STAMP(2);                 // (the last stream warp)
+    }
+    __syncthreads();
+    SSDHOT_STAMP(4);
+
+    // ---- 2'. which box each positive prior matched ---------------------------------------------------
     const int first_nan = fs.first_nan;
     const unsigned ord_thr = ord_encode(thresh);
     // prior p is positive iff its best entry is a number >= thresh (an all-NaN column makes every row but 0 NaN)
     auto positive = [&](unsigned hi, int p) { return hi >= ord_thr && hi != 0xffffffffu && (first_nan == INT_MAX || p == 0); };
+    // A positive's low word becomes 0x80000000 | (63 - box); atomicMax keeps the lowest box among equal maxima
+    // (torch's arg-max).  The first claimer sees the old low word: the CE key the stream wrote, which leaves the histogram.
+    auto claim = [&](int p, int g) {
+        const unsigned old = atomicMax(&v.lo[2 * p], 0x80000000u | (unsigned)(63 - g));
+        if (!(old >> 31)) {
+            atomicAdd(&fs.n_pos_img, 1);
+            if (LOSS) {
+                const int bin = ce_bin(old);
+                atomicSub(&hist16[bin >> 1], 1u << ((bin & 1) * 16));
+            }
+        }
+    };
+    {
+        const int n_list = min(fs.n_pair, PAIR_CAP);
+        for (int e = tid; e < n_list; e += FT) {
+            const unsigned pr = v.pair_pg[e];
+            const int p = (int)(pr & 0xffffu);
+            const unsigned hi = v.hi[2 * p];
+            if (v.pair_ov[e] == hi && positive(hi, p)) claim(p, (int)(pr >> 16));
+        }
+    }
+    __syncthreads();
+    if (fs.pair_overflow) {
+        // (rare: more gate survivors than the list holds) a positive whose winning pair was not listed recomputes it
+        for (int p = tid; p < P; p += FT) {
+            const unsigned hi = v.hi[2 * p];
+            if (!positive(hi, p) || (v.lo[2 * p] >> 31)) continue;
+            const BoxC pr = load_prior(prm.pri_xyxy, prm.pri_aux, p);
+            for (int g = 0; g < G; ++g) {
+                const unsigned o = fs.champ[g] == p ? kOrdTwo : ord_encode(pair_ciou(pr, gt_box(fs.gt_a[g], fs.gt_b[g])));
+                if (o == hi) { claim(p, g); break; }
+            }
+        }
+        __syncthreads();
+    }
+    auto matched_box = [&](unsigned lo) { return 63 - (int)(lo & 63u); };
 
     if (!LOSS) {
         // ---- build_targets-shaped outputs (SSD_trainer.py:547): masks, classes, positives' offsets ------
         int my_pos = 0;
         for (int p = tid; p < P; p += FT) {
-            const unsigned long long slot = table[p];
-            const bool pos = G > 0 && positive((unsigned)(slot >> 32), p);
-            const int g = (int)(0xffffffffu - (unsigned)(slot & 0xffffffffull));
+            const unsigned lo = v.lo[2 * p];
+            const bool pos = (lo >> 31) != 0u;
+            const int g = matched_box(lo);
             const long long row = (long long)b * P + p;
             my_pos += pos ? 1 : 0;
             if (prm.pos_mask) prm.pos_mask[row] = pos ? 1 : 0;
@@ -1028,12 +1164,35 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
         return;
     }
 
-    // ---- 3. stream the logits: approximate CE of every negative, first-level histogram ------------
-    for (int i = tid; i < 2048; i += FT) hist16[i] = 0u;              // (the scratch changes role)
-    __syncthreads();
-    const float* conf_b = prm.conf_all + (long long)b * P * 6;
+    SSDHOT_STAMP(5);
+    // ---- 3'. hard-negative budget and bracket (the number of positives is the number of first claims) ------
+    const int n_pos_img = fs.n_pos_img;
+    if (tid == 0 && prm.n_pos) prm.n_pos[b] = n_pos_img;
+    const long long n_neg = (long long)P - n_pos_img;
+    long long want = (n_pos_img == 0) ? (long long)prm.ratio : (long long)(prm.ratio * (double)n_pos_img);
+    if (want < 0) want = 0;
+    const long long kk = want < n_neg ? want : n_neg;
+    bool exact_all = kk >= n_neg && kk > 0;
+    bool fast = kk > 0 && !exact_all;
+    unsigned band_lo_key = 0xffffffffu, band_hi_key = 0xffffffffu;
+    if (fast) {
+        unsigned b1, above1;
+        find_kth_from_top<FT, 4096>([&](int bin) { return (hist16[bin >> 1] >> ((bin & 1) * 16)) & 0xffffu; }, (unsigned)kk, fs, b1, above1);
+        if (b1 == 0u || b1 == 4095u) { exact_all = true; fast = false; }   // the k-th value lies outside the resolved range: CTA-uniform
+        else {
+            const unsigned lo_key = (b1 + (unsigned)kCeBinBase) << 15, hi_key = lo_key | 0x7fffu;
+            const float t_lo = __uint_as_float(lo_key), t_hi = __uint_as_float(hi_key);
+            band_lo_key = __float_as_uint(fmaxf(t_lo - 3.0f * ce_error_bound(t_lo), 0.0f));
+            band_hi_key = __float_as_uint(t_hi + 3.0f * ce_error_bound(t_hi));
+        }
+    }
+
+    SSDHOT_STAMP(6);
+    // ---- 4. one scan of the slots (the scratch changes role): positives and certainly-mined negatives go to
+    //         per-warp lists in prior order, the few negatives inside the error band to one short list.
+    //         The lists are consumed in the canonical concatenation order, so every thread adds the same
+    //         terms in the same order on every run.
     double acc_loc = 0.0, acc_ce = 0.0;
-    int my_pos = 0;
     // a positive prior: exact CE of its class, smooth-L1 of its offsets (TR:108, :577-580)
     auto positive_terms = [&](int p, int g) {
         const long long row = (long long)b * P + p;
@@ -1049,179 +1208,103 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
             acc_loc += (double)(z < 1.0f ? fmul(fmul(0.5f, z), z) : fsub(z, 0.5f));
         }
     };
-    // Lists are kept per warp (fixed-size segments, filled in prior order) and consumed in the canonical
-    // concatenation order, so every thread adds the same terms in the same order on every run.
-    auto list_locate = [&](int e, int per_warp, const uint16_t* lists, int& p) {
-        int run = 0;
-        for (int w = 0; w < FT / 32; ++w) {
-            const int c = fs.wcount[w];
-            if (e < run + c) { p = (int)lists[w * per_warp + (e - run)]; return true; }
-            run += c;
-        }
-        return false;
+    auto mined_term = [&](int p) {
+        acc_ce += (double)exact_ce6(conf_b + 6ll * p, 0);
+        if (prm.sel_cls) prm.sel_cls[(long long)b * P + p] = 0;
     };
     const unsigned lt = (1u << lane) - 1u;
     {
-        const float4* src = reinterpret_cast<const float4*>(conf_b);
-        ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
-        uint16_t* my_list = pos_list + warp * POS_PER_WARP;
-        int wpos = 0;                                    // warp-uniform
-        const int n_pairs = P / 2;
-#pragma unroll 2
-        for (int qb = warp * 32; qb < n_pairs; qb += FT) {
-            const int q = qb + lane;
-            const bool live = q < n_pairs;
-            const int p0 = 2 * q;
-            bool pos0 = false, pos1 = false;
-            ulonglong2 slots = make_ulonglong2(0ull, 0ull);
-            if (live) {
-                const float4 A = __ldg(src + 3 * q), Bv = __ldg(src + 3 * q + 1), Cv = __ldg(src + 3 * q + 2);
-                slots = t2[q];
-                pos0 = G > 0 && positive((unsigned)(slots.x >> 32), p0);
-                pos1 = G > 0 && positive((unsigned)(slots.y >> 32), p0 + 1);
-                if (!pos0) {
-                    const unsigned key = __float_as_uint(approx_ce6(A.x, A.y, A.z, A.w, Bv.x, Bv.y));
-                    slots.x = (unsigned long long)key;
-                    ce_hist_add(hist16, key);
-                }
-                if (!pos1) {
-                    const unsigned key = __float_as_uint(approx_ce6(Bv.z, Bv.w, Cv.x, Cv.y, Cv.z, Cv.w));
-                    slots.y = (unsigned long long)key;
-                    ce_hist_add(hist16, key);
-                }
-                t2[q] = slots;
-                if (prm.sel_cls) {
-                    const long long row = (long long)b * P + p0;
-                    const int g0 = (int)(0xffffffffu - (unsigned)(slots.x & 0xffffffffull));
-                    const int g1 = (int)(0xffffffffu - (unsigned)(slots.y & 0xffffffffull));
-                    prm.sel_cls[row] = pos0 ? (int8_t)(fs.label[g0] + 1) : (int8_t)-1;
-                    prm.sel_cls[row + 1] = pos1 ? (int8_t)(fs.label[g1] + 1) : (int8_t)-1;
-                    if (prm.matched16) { prm.matched16[row] = pos0 ? (int16_t)g0 : (int16_t)-1; prm.matched16[row + 1] = pos1 ? (int16_t)g1 : (int16_t)-1; }
-                }
+        uint16_t* my_pos = pos_list + warp * POS_PER_WARP;
+        uint16_t* my_sel = sel_list + warp * SEL_PER_WARP;
+        int wpos = 0, wsel = 0;                          // warp-uniform
+        for (int base = warp * 32; base < P; base += FT) {
+            const int p = base + lane;
+            const unsigned lo = p < P ? v.lo[2 * p] : 0u;
+            const bool pos = (lo >> 31) != 0u;
+            const bool cand = !pos && lo >= band_lo_key;          // (p >= P: lo = 0 < any band key when the fast path is on;
+            const bool sure = cand && lo > band_hi_key;           //  off: the keys are 0xffffffff and nothing qualifies)
+            const bool band = cand && !sure && fast;
+            if (prm.sel_cls && p < P) {
+                const long long row = (long long)b * P + p;
+                prm.sel_cls[row] = pos ? (int8_t)(fs.label[matched_box(lo)] + 1) : (int8_t)-1;
+                if (prm.matched16) prm.matched16[row] = pos ? (int16_t)matched_box(lo) : (int16_t)-1;
             }
-            if (__any_sync(FULL, pos0 || pos1)) {
-                const unsigned b0 = __ballot_sync(FULL, pos0), b1 = __ballot_sync(FULL, pos1);
-                int at = wpos + __popc(b0 & lt) + __popc(b1 & lt);
-                if (pos0) {
-                    if (at < POS_PER_WARP) my_list[at] = (uint16_t)p0;
-                    else positive_terms(p0, (int)(0xffffffffu - (unsigned)(slots.x & 0xffffffffull)));
-                    ++at;
+            if (__any_sync(FULL, pos || cand)) {
+                const unsigned bp = __ballot_sync(FULL, pos), bs = __ballot_sync(FULL, sure && fast);
+                if (pos) {
+                    const int at = wpos + __popc(bp & lt);
+                    if (at < POS_PER_WARP) my_pos[at] = (uint16_t)p;
+                    else positive_terms(p, matched_box(lo));
                 }
-                if (pos1) {
-                    if (at < POS_PER_WARP) my_list[at] = (uint16_t)(p0 + 1);
-                    else positive_terms(p0 + 1, (int)(0xffffffffu - (unsigned)(slots.y & 0xffffffffull)));
+                if (sure && fast) {
+                    const int at = wsel + __popc(bs & lt);
+                    if (at < SEL_PER_WARP) my_sel[at] = (uint16_t)p;
+                    else mined_term(p);
                 }
-                wpos += __popc(b0) + __popc(b1);
-                my_pos += (pos0 ? 1 : 0) + (pos1 ? 1 : 0);
+                wpos += __popc(bp);
+                wsel += __popc(bs);
+                if (band) {
+                    const int dst = atomicAdd(&fs.n_band, 1);
+                    if (dst < BAND_CAP) band_p[dst] = (uint16_t)p;
+                }
             }
         }
-        if (lane == 0) fs.wcount[warp] = min(wpos, POS_PER_WARP);
-        if ((P & 1) && tid == 0) {                      // odd P: the last row (never SSD300)
-            const int p = P - 1;
-            const unsigned long long slot = table[p];
-            if (G > 0 && positive((unsigned)(slot >> 32), p)) {
-                my_pos += 1;
-                positive_terms(p, (int)(0xffffffffu - (unsigned)(slot & 0xffffffffull)));
-            } else {
-                const float* r = conf_b + 6ll * p;
-                const unsigned key = __float_as_uint(approx_ce6(r[0], r[1], r[2], r[3], r[4], r[5]));
-                table[p] = (unsigned long long)key;
-                ce_hist_add(hist16, key);
-                if (prm.sel_cls) { prm.sel_cls[(long long)b * P + p] = -1; if (prm.matched16) prm.matched16[(long long)b * P + p] = -1; }
-            }
+        if (lane == 0) {
+            fs.wcount[warp] = min(wpos, POS_PER_WARP);
+            fs.wcount2[warp] = min(wsel, SEL_PER_WARP);
+            atomicAdd(&fs.n_sure, wsel);
         }
     }
-    const int n_pos_img = block_sum<int>(my_pos, fs.ls.iscratch);      // two barriers: slots, lists and hist16 are complete
-    if (tid == 0) { if (prm.n_pos) prm.n_pos[b] = n_pos_img; fs.n_sure = 0; }
-
-    // positives: one list entry per thread
+    __syncthreads();
+    SSDHOT_STAMP(7);
     {
-        const int total = __reduce_add_sync(FULL, lane < FT / 32 ? fs.wcount[lane] : 0);
-        for (int e = tid; e < total; e += FT) {
-            int p;
-            if (!list_locate(e, POS_PER_WARP, pos_list, p)) break;
-            positive_terms(p, (int)(0xffffffffu - (unsigned)(table[p] & 0xffffffffull)));
-        }
-    }
-
-    // ---- 4. hard negatives -----------------------------------------------------------------------
-    const long long n_neg = (long long)P - n_pos_img;
-    long long want = (n_pos_img == 0) ? (long long)prm.ratio : (long long)(prm.ratio * (double)n_pos_img);
-    if (want < 0) want = 0;
-    const long long kk = want < n_neg ? want : n_neg;
-    bool exact_all = kk >= n_neg && kk > 0;
-    if (kk > 0 && !exact_all) {
-        unsigned b1, above1;
-        find_kth_from_top<FT, 4096>([&](int bin) { return (hist16[bin >> 1] >> ((bin & 1) * 16)) & 0xffffu; }, (unsigned)kk, fs, b1, above1);
-        const unsigned lo_key = (b1 + (unsigned)kCeBinBase) << 15, hi_key = lo_key | 0x7fffu;
-        const float t_lo = __uint_as_float(lo_key), t_hi = __uint_as_float(hi_key);
-        if (b1 == 0u || b1 == 4095u) exact_all = true;  // the k-th value lies outside the resolved range: CTA-uniform
-        else {
-            const float band_lo = fmaxf(t_lo - 3.0f * ce_error_bound(t_lo), 0.0f), band_hi = t_hi + 3.0f * ce_error_bound(t_hi);
-            const unsigned band_lo_key = __float_as_uint(band_lo), band_hi_key = __float_as_uint(band_hi);
-            // certain members (above the band) -> per-warp lists; band members -> one short list
-            uint16_t* my_list = sel_list + warp * SEL_PER_WARP;
-            int wsel = 0;                                // warp-uniform
-            for (int base = warp * 32; base < P; base += FT) {
-                const int p = base + lane;
-                bool sure = false, band = false;
-                if (p < P) {
-                    const unsigned long long slot = table[p];
-                    const unsigned key = (unsigned)slot;         // CE >= 0: bit order = value order
-                    if ((slot >> 32) == 0ull && key >= band_lo_key) { sure = key > band_hi_key; band = !sure; }
+        const int n_sure = fs.n_sure, n_band = fs.n_band;
+        if (fast && n_band > BAND_CAP) { exact_all = true; fast = false; }   // (massive ties): CTA-uniform
+        // one pass over the three lists: positives | certain negatives | band members
+        const int tot_pos = __reduce_add_sync(FULL, lane < FT / 32 ? fs.wcount[lane] : 0);
+        const int tot_sel = fast ? __reduce_add_sync(FULL, lane < FT / 32 ? fs.wcount2[lane] : 0) : 0;
+        const int tot_band = fast ? n_band : 0;
+        for (int e = tid; e < tot_pos + tot_sel + tot_band; e += FT) {
+            if (e < tot_pos + tot_sel) {
+                const bool is_pos = e < tot_pos;
+                const int* wc = is_pos ? fs.wcount : fs.wcount2;
+                const uint16_t* lists = is_pos ? pos_list : sel_list;
+                const int per_warp = is_pos ? POS_PER_WARP : SEL_PER_WARP;
+                int run = 0, p = -1;
+                const int ee = is_pos ? e : e - tot_pos;
+                for (int w = 0; w < FT / 32; ++w) {
+                    const int c = wc[w];
+                    if (ee < run + c) { p = (int)lists[w * per_warp + (ee - run)]; break; }
+                    run += c;
                 }
-                if (__any_sync(FULL, sure || band)) {
-                    const unsigned bs = __ballot_sync(FULL, sure);
-                    if (sure) {
-                        const int at = wsel + __popc(bs & lt);
-                        if (at < SEL_PER_WARP) my_list[at] = (uint16_t)p;
-                        else {
-                            acc_ce += (double)exact_ce6(conf_b + 6ll * p, 0);
-                            if (prm.sel_cls) prm.sel_cls[(long long)b * P + p] = 0;
-                        }
-                    }
-                    wsel += __popc(bs);
-                    if (band) {
-                        const int dst = atomicAdd(&fs.n_band, 1);
-                        if (dst < BAND_CAP) band_p[dst] = (uint16_t)p;
-                    }
-                }
+                if (is_pos) positive_terms(p, matched_box(v.lo[2 * p]));
+                else mined_term(p);
+            } else {
+                const int eb = e - tot_pos - tot_sel;
+                band_v[eb] = __float_as_uint(exact_ce6(conf_b + 6ll * (int)band_p[eb], 0)) & 0x7fffffffu;
             }
-            __syncthreads();                             // the positives pass is done with wcount
-            if (lane == 0) { fs.wcount[warp] = min(wsel, SEL_PER_WARP); atomicAdd(&fs.n_sure, wsel); }
+        }
+        if (fast) {
             __syncthreads();
-            const int n_sure = fs.n_sure, n_band = fs.n_band;
-            if (n_band > BAND_CAP) exact_all = true;     // (massive ties): CTA-uniform; the partial sums are discarded below
-            else {
-                const int total = __reduce_add_sync(FULL, lane < FT / 32 ? fs.wcount[lane] : 0);
-                for (int e = tid; e < total; e += FT) {
-                    int p;
-                    if (!list_locate(e, SEL_PER_WARP, sel_list, p)) break;
-                    acc_ce += (double)exact_ce6(conf_b + 6ll * p, 0);
+            const int r = (int)kk - n_sure;              // members still to take from the band (1 <= r <= n_band)
+            for (int e = tid; e < n_band; e += FT) {
+                const unsigned val = band_v[e];
+                const int p = (int)band_p[e];
+                int rank = 0;
+                for (int j = 0; j < n_band; ++j) {
+                    const unsigned vj = band_v[j];
+                    rank += (vj > val || (vj == val && (int)band_p[j] < p)) ? 1 : 0;
+                }
+                if (rank < r) {
+                    band_sorted[rank] = val;             // ranks are distinct: (value, prior) is a total order
                     if (prm.sel_cls) prm.sel_cls[(long long)b * P + p] = 0;
                 }
-                for (int e = tid; e < n_band; e += FT)
-                    band_v[e] = __float_as_uint(exact_ce6(conf_b + 6ll * (int)band_p[e], 0)) & 0x7fffffffu;
-                __syncthreads();
-                const int r = (int)kk - n_sure;          // members still to take from the band (1 <= r <= n_band)
-                for (int e = tid; e < n_band; e += FT) {
-                    const unsigned v = band_v[e];
-                    const int p = (int)band_p[e];
-                    int rank = 0;
-                    for (int j = 0; j < n_band; ++j) {
-                        const unsigned vj = band_v[j];
-                        rank += (vj > v || (vj == v && (int)band_p[j] < p)) ? 1 : 0;
-                    }
-                    if (rank < r) {
-                        band_sorted[rank] = v;           // ranks are distinct: (value, prior) is a total order
-                        if (prm.sel_cls) prm.sel_cls[(long long)b * P + p] = 0;
-                    }
-                }
-                __syncthreads();
-                for (int e = tid; e < r; e += FT) acc_ce += (double)__uint_as_float(band_sorted[e]);
             }
+            __syncthreads();
+            for (int e = tid; e < r; e += FT) acc_ce += (double)__uint_as_float(band_sorted[e]);
         }
     }
+    SSDHOT_STAMP(8);
     if (exact_all) {
         // exact keys for every negative, then the exact radix selection (as loss_image_kernel)
         acc_ce = 0.0;
@@ -1229,23 +1312,23 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
         for (int i = tid; i < 256; i += FT) fs.ls.hist[i] = 0u;
         __syncthreads();
         for (int p = tid; p < P; p += FT) {
-            const unsigned long long slot = table[p];
-            if ((slot >> 32) == 0ull) {
+            const unsigned lo = v.lo[2 * p];
+            if (!(lo >> 31)) {
                 const unsigned key = __float_as_uint(exact_ce6(conf_b + 6ll * p, 0)) & 0x7fffffffu;
-                table[p] = (unsigned long long)key;
+                v.lo[2 * p] = key;
                 atomicAdd(&fs.ls.hist[key >> 24], 1u);
             } else {
-                acc_ce += (double)exact_ce6(conf_b + 6ll * p, fs.label[(int)(0xffffffffu - (unsigned)(slot & 0xffffffffull))] + 1);
+                acc_ce += (double)exact_ce6(conf_b + 6ll * p, fs.label[matched_box(lo)] + 1);
             }
         }
         __syncthreads();
         acc_ce += mined_exact_tail<FT>(prm, b, P, n_pos_img, fs.ls,
-                                       [&](int p) { const unsigned long long s = table[p]; return (s >> 32) == 0ull ? (unsigned)s : kNotNegative; },
+                                       [&](int p) { const unsigned lo = v.lo[2 * p]; return (lo >> 31) ? kNotNegative : lo; },
                                        [&](int p, int& mg) {
-                                           const unsigned long long s = table[p];
+                                           const unsigned lo = v.lo[2 * p];
                                            mg = -1;
-                                           if ((s >> 32) == 0ull) return -1;
-                                           mg = (int)(0xffffffffu - (unsigned)(s & 0xffffffffull));
+                                           if (!(lo >> 31)) return -1;
+                                           mg = matched_box(lo);
                                            return fs.label[mg] + 1;
                                        });
     }
@@ -1255,6 +1338,7 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     if (tid == 0) {
         prm.img_part[2ll * b + 0] = s_loc;
         prm.img_part[2ll * b + 1] = s_ce;
+        if (prm.timeline) { prm.timeline[(long long)b * 16 + 9] = globaltimer_ns(); unsigned sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); prm.timeline[(long long)b * 16 + 10] = sm; }
     }
 }
 
@@ -1429,8 +1513,12 @@ static int launch_loss(const TrainParams& prm, cudaStream_t stream) {
     return SSDHOT_OK;
 }
 
+static unsigned long long* g_timeline = nullptr;   // debug hook (ssdhot_debug_timeline)
+
 template <bool LOSS>
-static int launch_train_image(const TrainParams& prm, cudaStream_t stream) {
+static int launch_train_image(const TrainParams& prm_in, cudaStream_t stream) {
+    TrainParams prm = prm_in;
+    prm.timeline = g_timeline;
     const size_t dyn = fused_smem_bytes(prm.P);
     auto kern = train_image_kernel<LOSS>;
     static bool configured = false;    // sticky opt-in, raised outside graph capture by the first (warm-up) call
@@ -1456,6 +1544,13 @@ using namespace ssdhot;
 // Host-side check that `priors` (HOST memory) have the SSD300 structure train_image_kernel relies on:
 // levels of 38/19/10/5/3/1 cells with 4/6/6/6/4/4 shapes, cells row-major, shapes innermost
 // (SSD_from_scratch.py:289-323); centres (i + 0.5)/side within 1e-5; one (w, h) in (0, 1] per (level, shape).
+// Debug hook: device buffer of B x 16 uint64 that the fused train kernel fills with %globaltimer stamps of its
+// phases (null = off, the default).  Not part of the drop-in surface.
+extern "C" int ssdhot_debug_timeline(void* dev_buffer) {
+    g_timeline = reinterpret_cast<unsigned long long*>(dev_buffer);
+    return SSDHOT_OK;
+}
+
 extern "C" int ssdhot_ssd300_layout_host(const float* priors_cxcywh_host, int P) {
     if (!priors_cxcywh_host || P != 8732) return 0;
     static const int side[6] = {38, 19, 10, 5, 3, 1}, shapes[6] = {4, 6, 6, 6, 4, 4};

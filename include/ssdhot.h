@@ -65,6 +65,9 @@ typedef void* ssdhot_stream_t;   /* cudaStream_t */
 #define SSDHOT_METRIC_IOU 2
 
 SSDHOT_API int ssdhot_abi_version(void);
+/* debug: device buffer [B][16] uint64 receiving %globaltimer stamps of ssdhot_multibox_loss_fwd's fused kernel
+ * phases (NULL switches it off, the default); tools/timeline.py prints them */
+SSDHOT_API int ssdhot_debug_timeline(void* dev_buffer);
 SSDHOT_API const char* ssdhot_status_string(int status);
 /* number of kernels this library has launched so far in this process (bench.py gpu_launches) */
 SSDHOT_API unsigned long long ssdhot_launch_count(void);
