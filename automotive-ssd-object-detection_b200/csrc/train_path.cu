@@ -620,7 +620,7 @@ constexpr int FAST_MAX_GT = 64;
 constexpr int GT_ROUND = 32;                 // boxes enumerated per round
 constexpr int NSEG = GT_ROUND * 32;          // (box, level-shape) segments per round
 constexpr int PAIR_CAP = 1536;               // listed gate survivors of an image (rest: settled inline, box recomputed)
-constexpr int MT_LOSS = 256;                 // threads (warps 0..7) that match while the others stream the logits
+constexpr int MT_LOSS = 512;                 // threads (warps 0..15) that match while the others stream the logits
 constexpr int POS_PER_WARP = 80;             // per-warp list of positive priors (rest: handled inline)
 constexpr int SEL_PER_WARP = 168;            // per-warp list of certainly-mined negatives
 constexpr int BAND_CAP = 1024;
@@ -635,6 +635,10 @@ struct FusedStatic {
     int label[FAST_MAX_GT];
     int champ[FAST_MAX_GT];
     unsigned char kind[FAST_MAX_GT];         // 0 = rectangles, 1 = dense sweep, 2 = all-NaN column
+    // the 30 (level, shape) combinations: grid side, shapes per cell, first prior (level offset + shape), (w, h)
+    int cb_side[32], cb_shapes[32], cb_base[32];
+    float cb_w[32], cb_h[32], cb_inv[32];      // (w, h) of the shape, 1 / side
+    float4 gt_px[FAST_MAX_GT];                // the image's boxes as given (prefetched while the table is cleared)
     LossShared ls;
     int first_nan, n_dense, n_pair, n_work, n_band, n_sure, pair_overflow, n_pos_img;
     int wcount[FT / 32], wcount2[FT / 32];   // per-warp list lengths: positives, certainly-mined negatives
@@ -719,8 +723,9 @@ __device__ __forceinline__ void find_kth_from_top(CountFn count, unsigned k, Fus
 }
 
 // Extent of the clamped prior interval of cell i on a grid of `side` cells: [max(0, c - w/2), min(1, c + w/2)], c = (i + .5)/side
-__device__ __forceinline__ float clamped_extent(int i, int side, float w) {
-    const float c = ((float)i + 0.5f) / (float)side;
+// (bound arithmetic only: approximate reciprocals are fine, every comparison built on it is slackened)
+__device__ __forceinline__ float clamped_extent(int i, float inv_side, float w) {
+    const float c = ((float)i + 0.5f) * inv_side;
     return fminf(1.0f, c + 0.5f * w) - fmaxf(0.0f, c - 0.5f * w);
 }
 
@@ -728,11 +733,11 @@ __device__ __forceinline__ float clamped_extent(int i, int side, float w) {
 // overlap with [g1, g2]; empty if hi < lo.  Un-clamped cells have extent w and ov <= min(w, gw, (w + gw)/2 - |c - gc|),
 // which gives a closed-form centre range; the few cells the image border clamps are tested one by one
 // (their extents differ).  Every comparison is slackened, so the hull errs on the inclusive side.
-__device__ __forceinline__ void axis_hull(float g1, float g2, int side, float w, float A, float Bc, float Cc, int& lo, int& hi) {
+__device__ __forceinline__ void axis_hull(float g1, float g2, int side, float inv_side, float w, float A, float Bc, float Cc, int& lo, int& hi) {
     const float fS = (float)side, gw = g2 - g1, gc = 0.5f * (g1 + g2);
     lo = side;
     hi = -1;
-    const float areq = (Bc * w + Cc) / A;
+    const float areq = __fdividef(Bc * w + Cc, A) * 0.9999f;
     if (fminf(w, gw) >= areq) {
         const float r = 0.5f * (w + gw) - areq;
         const int ia = max(0, (int)ceilf(fmaxf((gc - r) * fS - 0.51f, -1.0f)));
@@ -741,7 +746,7 @@ __device__ __forceinline__ void axis_hull(float g1, float g2, int side, float w,
     }
     const int nb = min(side, max(0, (int)ceilf(0.5f * w * fS - 0.49f)));      // cells clamped at each border
     auto test = [&](int i) {
-        const float c = ((float)i + 0.5f) / fS;
+        const float c = ((float)i + 0.5f) * inv_side;
         const float p1 = fmaxf(0.0f, c - 0.5f * w), p2 = fminf(1.0f, c + 0.5f * w);
         const float ov = fminf(p2, g2) - fmaxf(p1, g1);
         if (ov > 0.0f && ov * A >= (Bc * (p2 - p1) + Cc) * 0.999f) { lo = min(lo, i); hi = max(hi, i); }
@@ -800,42 +805,60 @@ __device__ __forceinline__ void match_phase(const TrainParams& prm, FusedStatic&
         if (mtid == 0) fs.n_work = 0;
         const int round_begin = min(fs.n_pair, PAIR_CAP);       // (stable: the previous round ended with a barrier)
         role_sync<MT>();
-        // 1a. one warp per box: constants, seed bound, and the (level, shape) combinations whose sizes can
-        //     reach IoU >= lim at all (1-D and area ratios, clamped extents >= half the nominal ones)
-        for (int gl = mwarp; gl < gn; gl += MT / 32) {
-            const int g = g0 + gl;
-            const float4 px = ldg4(prm.gt_boxes + 4ll * (g_begin + g));
+        // 1a. half a warp per box: constants, seed bound (two of the 30 seed priors per lane), and the
+        //     (level, shape) combinations whose sizes can reach IoU >= lim at all (1-D and area ratios; a
+        //     clamped extent is at least half the nominal one)
+        for (int gl = 2 * mwarp + (lane >> 4); gl < ((gn + 1) & ~1); gl += 2 * (MT / 32)) {     // warp-uniform trip count
+            const bool live = gl < gn;
+            const int g = g0 + (live ? gl : gn - 1);
+            const float4 px = fs.gt_px[g];
             const BoxC c = box_consts(fdiv(px.x, prm.norm_w), fdiv(px.y, prm.norm_h), fdiv(px.z, prm.norm_w), fdiv(px.w, prm.norm_h), true);
             const float gw = fsub(c.x2, c.x1), gh = fsub(c.y2, c.y1);
             int kind = 0;
             if (c.at != c.at) kind = 2;
             else if (!(gw > 0.0f && gh > 0.0f) || !(fabsf(c.x1) < 1e30f && fabsf(c.y1) < 1e30f && fabsf(c.x2) < 1e30f && fabsf(c.y2) < 1e30f)) kind = 1;
             float lim = 1e-30f;
+            unsigned keep = 0u;                              // bit h: combination (lane & 15) + 16 h stays
+            unsigned best = 0u;
             if (kind == 0) {
-                const int lv = kSeedLevel[lane], side = kLevelSide[lv], shapes = kLevelShapes[lv], off = kLevelOffset[lv];
-                const int shp = kSeedShape[lane];
-                int ix = (int)floorf(c.xc * (float)side), iy = (int)floorf(c.yc * (float)side);
-                ix = min(max(ix, 0), side - 1);
-                iy = min(max(iy, 0), side - 1);
-                const int ps = off + (iy * side + ix) * shapes + shp;
-                const float val = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, ps), c);
-                const float cb0 = ord_decode(__reduce_max_sync(FULL, ord_encode(val)));
-                if (cb0 > 0.0f) lim = fmaxf(fmul(kPruneSlack, fminf(cb0, thresh)), 1e-30f);
-                const float4 sh = ldg4(prm.pri + 4ll * (off + shp));                   // (w, h) of this level-shape
-                const float w = sh.z, h = sh.w, l2 = 0.99f * lim;
-                const bool keep = lane < 30 && !(gw < l2 * 0.5f * w || w < l2 * gw || gh < l2 * 0.5f * h || h < l2 * gh ||
-                                                 c.area < l2 * 0.25f * w * h || w * h < l2 * c.area);
-                const unsigned bal = __ballot_sync(FULL, keep);
-                int dst = 0;
-                if (lane == 0 && bal) dst = atomicAdd(&fs.n_work, __popc(bal));
-                dst = __shfl_sync(FULL, dst, 0) + __popc(bal & ((1u << lane) - 1u));
-                if (keep) v.work_list[dst] = (uint16_t)((gl << 5) | lane);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int combo = (lane & 15) + 16 * h;  // 30, 31 repeat 0, 1 as seeds
+                    const int side = fs.cb_side[combo], shapes = fs.cb_shapes[combo];
+                    int ix = (int)floorf(c.xc * (float)side), iy = (int)floorf(c.yc * (float)side);
+                    ix = min(max(ix, 0), side - 1);
+                    iy = min(max(iy, 0), side - 1);
+                    const int ps = fs.cb_base[combo] + (iy * side + ix) * shapes;
+                    best = max(best, ord_encode(pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, ps), c)));
+                }
             }
-            if (lane == 0) {
+            // (the two halves of a warp hold different boxes: the shuffles below must run in every lane)
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+            if (kind == 0) {
+                const float cb0 = ord_decode(best);
+                if (cb0 > 0.0f) lim = fmaxf(fmul(kPruneSlack, fminf(cb0, thresh)), 1e-30f);
+                const float l2 = 0.99f * lim;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int combo = (lane & 15) + 16 * h;
+                    const float w = fs.cb_w[combo], hh = fs.cb_h[combo];
+                    if (combo < 30 && !(gw < l2 * 0.5f * w || w < l2 * gw || gh < l2 * 0.5f * hh || hh < l2 * gh ||
+                                        c.area < l2 * 0.25f * w * hh || w * hh < l2 * c.area)) keep |= 1u << h;
+                }
+            }
+            if (!live) keep = 0u;
+            const unsigned b0 = __ballot_sync(FULL, keep & 1u), b1 = __ballot_sync(FULL, keep & 2u);
+            int dst = 0;
+            if (lane == 0 && (b0 | b1)) dst = atomicAdd(&fs.n_work, __popc(b0) + __popc(b1));
+            dst = __shfl_sync(FULL, dst, 0);
+            const unsigned ltm = (1u << lane) - 1u;
+            if (keep & 1u) v.work_list[dst + __popc(b0 & ltm)] = (uint16_t)((gl << 5) | (lane & 15));
+            if (keep & 2u) v.work_list[dst + __popc(b0) + __popc(b1 & ltm)] = (uint16_t)((gl << 5) | ((lane & 15) + 16));
+            if (live && (lane & 15) == 0) {
                 fs.gt_a[g] = make_float4(c.x1, c.y1, c.x2, c.y2);
                 fs.gt_b[g] = make_float4(c.area, c.xc, c.yc, c.at);
                 fs.lim[g] = lim;
-                fs.label[g] = (int)prm.gt_labels[g_begin + g];
                 fs.col[g] = 0ull;
                 fs.champ[g] = 0;
                 fs.kind[g] = (unsigned char)kind;
@@ -853,30 +876,29 @@ __device__ __forceinline__ void match_phase(const TrainParams& prm, FusedStatic&
                 unsigned info = 0u, base = 0u;
                 if (e < n_work) {
                     const int wk = (int)v.work_list[e], g = g0 + (wk >> 5), combo = wk & 31;
-                    const int lv = kSeedLevel[combo], side = kLevelSide[lv], shapes = kLevelShapes[lv], off = kLevelOffset[lv];
-                    const int shp = kSeedShape[combo];
-                    const float4 sh = ldg4(prm.pri + 4ll * (off + shp));
-                    const float w = sh.z, h = sh.w, l2 = 0.99f * fs.lim[g];
+                    const int side = fs.cb_side[combo], shapes = fs.cb_shapes[combo];
+                    const float w = fs.cb_w[combo], h = fs.cb_h[combo], l2 = 0.99f * fs.lim[g];
+                    const float inv_side = fs.cb_inv[combo];
                     const float4 ga = fs.gt_a[g];
                     const float gw = ga.z - ga.x, gh = ga.w - ga.y, ag = fs.gt_b[g].x;
                     // rows whose 1-D IoU with the box can reach lim (2-D IoU <= each 1-D IoU) ...
                     int j0, j1, i0, i1, a0, a1;
-                    axis_hull(ga.y, ga.w, side, h, 1.0f + l2, l2, l2 * gh, j0, j1);
+                    axis_hull(ga.y, ga.w, side, inv_side, h, 1.0f + l2, l2, l2 * gh, j0, j1);
                     if (j1 >= j0) {
                         // ... then columns / rows that can satisfy inter (1 + lim) >= lim (a_p + a_g) given the best
                         // overlap and the smallest clamped extent the other axis offers
-                        const float hcmin = fminf(clamped_extent(j0, side, h), clamped_extent(j1, side, h));
-                        axis_hull(ga.x, ga.z, side, w, fminf(h, gh) * (1.0f + l2), l2 * hcmin, l2 * ag, i0, i1);
+                        const float hcmin = fminf(clamped_extent(j0, inv_side, h), clamped_extent(j1, inv_side, h));
+                        axis_hull(ga.x, ga.z, side, inv_side, w, fminf(h, gh) * (1.0f + l2), l2 * hcmin, l2 * ag, i0, i1);
                         if (i1 >= i0) {
-                            const float wcmin = fminf(clamped_extent(i0, side, w), clamped_extent(i1, side, w));
-                            axis_hull(ga.y, ga.w, side, h, fminf(w, gw) * (1.0f + l2), l2 * wcmin, l2 * ag, a0, a1);
+                            const float wcmin = fminf(clamped_extent(i0, inv_side, w), clamped_extent(i1, inv_side, w));
+                            axis_hull(ga.y, ga.w, side, inv_side, h, fminf(w, gw) * (1.0f + l2), l2 * wcmin, l2 * ag, a0, a1);
                             j0 = max(j0, a0);
                             j1 = min(j1, a1);
                             if (j1 >= j0) {
                                 const int ni = i1 - i0 + 1;
                                 n = ni * (j1 - j0 + 1);
                                 info = (unsigned)i0 | ((unsigned)j0 << 6) | ((unsigned)ni << 12) | ((unsigned)side << 18) | ((unsigned)shapes << 24);
-                                base = (unsigned)(off + shp) | ((unsigned)g << 16);
+                                base = (unsigned)fs.cb_base[combo] | ((unsigned)g << 16);
                             }
                         }
                     }
@@ -1060,6 +1082,16 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
 
     // ---- 0. clear ------------------------------------------------------------------------------
     if (tid == 0) { fs.first_nan = INT_MAX; fs.n_dense = 0; fs.n_band = 0; fs.n_pair = 0; fs.pair_overflow = 0; fs.n_pos_img = 0; fs.n_sure = 0; }
+    if (tid >= 32 && tid < 32 + G) {
+        fs.gt_px[tid - 32] = ldg4(prm.gt_boxes + 4ll * (g_begin + tid - 32));
+        fs.label[tid - 32] = (int)prm.gt_labels[g_begin + tid - 32];
+    }
+    if (tid < 32) {
+        const int lv = kSeedLevel[tid], base = kLevelOffset[lv] + kSeedShape[tid];
+        const float4 sh = ldg4(prm.pri + 4ll * base);       // (w, h) of this level-shape: the same in every cell (checked on the host)
+        fs.cb_side[tid] = kLevelSide[lv]; fs.cb_shapes[tid] = kLevelShapes[lv]; fs.cb_base[tid] = base;
+        fs.cb_w[tid] = sh.z; fs.cb_h[tid] = sh.w; fs.cb_inv[tid] = 1.0f / (float)kLevelSide[lv];
+    }
     {
         ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
         for (int i = tid; i < P / 2; i += FT) t2[i] = make_ulonglong2(0ull, 0ull);
@@ -1216,37 +1248,55 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     {
         uint16_t* my_pos = pos_list + warp * POS_PER_WARP;
         uint16_t* my_sel = sel_list + warp * SEL_PER_WARP;
+        const ulonglong2* t2 = reinterpret_cast<const ulonglong2*>(table);
         int wpos = 0, wsel = 0;                          // warp-uniform
-        for (int base = warp * 32; base < P; base += FT) {
-            const int p = base + lane;
-            const unsigned lo = p < P ? v.lo[2 * p] : 0u;
-            const bool pos = (lo >> 31) != 0u;
-            const bool cand = !pos && lo >= band_lo_key;          // (p >= P: lo = 0 < any band key when the fast path is on;
-            const bool sure = cand && lo > band_hi_key;           //  off: the keys are 0xffffffff and nothing qualifies)
-            const bool band = cand && !sure && fast;
+        for (int base = warp * 64; base < P; base += 2 * FT) {          // two adjacent slots per lane (P is even here)
+            const int p = base + 2 * lane;
+            unsigned lo[2] = {0u, 0u};
+            if (p < P) { const ulonglong2 sl = t2[p >> 1]; lo[0] = (unsigned)sl.x; lo[1] = (unsigned)sl.y; }
+            bool pos[2], sure[2], band[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                pos[h] = (lo[h] >> 31) != 0u;
+                const bool cand = !pos[h] && lo[h] >= band_lo_key;   // (p >= P: lo = 0 is below any band key; fast path off:
+                sure[h] = cand && lo[h] > band_hi_key && fast;       //  the keys are 0xffffffff and nothing qualifies)
+                band[h] = cand && !sure[h] && fast;
+            }
             if (prm.sel_cls && p < P) {
                 const long long row = (long long)b * P + p;
-                prm.sel_cls[row] = pos ? (int8_t)(fs.label[matched_box(lo)] + 1) : (int8_t)-1;
-                if (prm.matched16) prm.matched16[row] = pos ? (int16_t)matched_box(lo) : (int16_t)-1;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    prm.sel_cls[row + h] = pos[h] ? (int8_t)(fs.label[matched_box(lo[h])] + 1) : (int8_t)-1;
+                    if (prm.matched16) prm.matched16[row + h] = pos[h] ? (int16_t)matched_box(lo[h]) : (int16_t)-1;
+                }
             }
-            if (__any_sync(FULL, pos || cand)) {
-                const unsigned bp = __ballot_sync(FULL, pos), bs = __ballot_sync(FULL, sure && fast);
-                if (pos) {
-                    const int at = wpos + __popc(bp & lt);
-                    if (at < POS_PER_WARP) my_pos[at] = (uint16_t)p;
-                    else positive_terms(p, matched_box(lo));
+            if (__any_sync(FULL, pos[0] || pos[1] || sure[0] || sure[1] || band[0] || band[1])) {
+                const unsigned bp0 = __ballot_sync(FULL, pos[0]), bp1 = __ballot_sync(FULL, pos[1]);
+                const unsigned bs0 = __ballot_sync(FULL, sure[0]), bs1 = __ballot_sync(FULL, sure[1]);
+                int at = wpos + __popc(bp0 & lt) + __popc(bp1 & lt);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (pos[h]) {
+                        if (at < POS_PER_WARP) my_pos[at] = (uint16_t)(p + h);
+                        else positive_terms(p + h, matched_box(lo[h]));
+                        ++at;
+                    }
                 }
-                if (sure && fast) {
-                    const int at = wsel + __popc(bs & lt);
-                    if (at < SEL_PER_WARP) my_sel[at] = (uint16_t)p;
-                    else mined_term(p);
+                at = wsel + __popc(bs0 & lt) + __popc(bs1 & lt);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (sure[h]) {
+                        if (at < SEL_PER_WARP) my_sel[at] = (uint16_t)(p + h);
+                        else mined_term(p + h);
+                        ++at;
+                    }
+                    if (band[h]) {
+                        const int dst = atomicAdd(&fs.n_band, 1);
+                        if (dst < BAND_CAP) band_p[dst] = (uint16_t)(p + h);
+                    }
                 }
-                wpos += __popc(bp);
-                wsel += __popc(bs);
-                if (band) {
-                    const int dst = atomicAdd(&fs.n_band, 1);
-                    if (dst < BAND_CAP) band_p[dst] = (uint16_t)p;
-                }
+                wpos += __popc(bp0) + __popc(bp1);
+                wsel += __popc(bs0) + __popc(bs1);
             }
         }
         if (lane == 0) {
