@@ -3,6 +3,14 @@
 
 namespace ssdhot {
 unsigned long long g_launches = 0ull;
+unsigned long long* g_timeline = nullptr;
+}
+
+// Debug hook: device buffer of (units x 16) uint64 that the per-image kernels (train_image_kernel,
+// nms_image_kernel) fill with %globaltimer stamps of their phases (null = off, the default).
+extern "C" int ssdhot_debug_timeline(void* dev_buffer) {
+    ssdhot::g_timeline = reinterpret_cast<unsigned long long*>(dev_buffer);
+    return SSDHOT_OK;
 }
 
 extern "C" int ssdhot_abi_version(void) { return SSDHOT_ABI_VERSION; }

@@ -62,6 +62,13 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
 extern unsigned long long g_launches;   // host-side counter (abi.cu)
+extern unsigned long long* g_timeline;  // debug hook (ssdhot_debug_timeline, abi.cu): device buffer [units][16] or null
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 }  // namespace ssdhot
 

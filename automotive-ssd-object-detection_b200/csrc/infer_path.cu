@@ -54,13 +54,17 @@ struct UnitShared {
 // -- four orders of magnitude above fp32 rounding -- and survives without the two IEEE divisions.
 // Pairs that pass (or whose union is not positive, where the exact test may yield NaN) take the
 // exact path, so the decision is bit-identical to evaluating the metric everywhere.
-template <int METRIC>
-__device__ __forceinline__ bool suppresses(const BoxC& S, const BoxC& c, float thr, float thr_lo) {
+// The cheap half of the predicate: false = the pair certainly does not suppress (IoU < thr by a margin).
+__device__ __forceinline__ bool iou_gate(const BoxC& S, const BoxC& c, float thr_lo, float& inter, float& uni) {
     const float w = fmaxf(fsub(fminf(S.x2, c.x2), fmaxf(S.x1, c.x1)), 0.0f);
     const float h = fmaxf(fsub(fminf(S.y2, c.y2), fmaxf(S.y1, c.y1)), 0.0f);
-    const float inter = fmul(w, h);
-    const float uni = fsub(fadd(S.area, c.area), inter);
-    if (inter < fmul(thr_lo, uni)) return false;
+    inter = fmul(w, h);
+    uni = fsub(fadd(S.area, c.area), inter);
+    return !(inter < fmul(thr_lo, uni));
+}
+// The exact half (two IEEE divisions), for pairs that passed the gate.
+template <int METRIC>
+__device__ __forceinline__ bool suppresses_exact(const BoxC& S, const BoxC& c, float inter, float uni, float thr) {
     const float iou = fdiv(inter, uni);
     float m = iou;
     if (METRIC != SSDHOT_METRIC_IOU) {
@@ -73,6 +77,12 @@ __device__ __forceinline__ bool suppresses(const BoxC& S, const BoxC& c, float t
         }
     }
     return !(m <= thr);
+}
+template <int METRIC>
+__device__ __forceinline__ bool suppresses(const BoxC& S, const BoxC& c, float thr, float thr_lo) {
+    float inter, uni;
+    if (!iou_gate(S, c, thr_lo, inter, uni)) return false;
+    return suppresses_exact<METRIC>(S, c, inter, uni, thr);
 }
 
 // ---- candidate sources ---------------------------------------------------------------------------
@@ -98,7 +108,13 @@ struct SegSource {             // 32 per-warp segments of (key << 32 | ~id) writ
         const int lane = threadIdx.x & 31;
         for (int seg = threadIdx.x >> 5; seg < SEGS; seg += NT / 32) {
             const int c = counts[seg];
-            for (int j = lane; j < c; j += 32) { const int i = seg * seg_cap + j; f(i, base[i]); }
+            for (int j = lane; j < c; j += 128) {             // four independent loads in flight per lane
+                unsigned long long r[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) r[k] = j + 32 * k < c ? base[seg * seg_cap + j + 32 * k] : 0ull;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (j + 32 * k < c) f(seg * seg_cap + j + 32 * k, r[k]);
+            }
         }
     }
     __device__ __forceinline__ void consume(int i) const { base[i] = 0ull; }
@@ -486,6 +502,7 @@ struct PredictParams {
     unsigned long long* cand;       // [B][P*(C-1)] candidate keys
     int* cand_count;                // [B]
     int64_t* out_labels; float* out_scores; float* out_boxes; int32_t* out_cand; int32_t* out_count;
+    unsigned long long* timeline;   // debug (ssdhot_debug_timeline) or null
 };
 
 // exp(x_i - max) of one row and their sum in eager torch-CUDA order (persistent warp softmax:
@@ -669,12 +686,13 @@ struct ImgBuffers {
     unsigned short* cpos;          // [CH] class-local position of entry j
     unsigned short* kidx;          // [n_groups][max_keep] positions in `kept` of each class's survivors
     unsigned char* cgroup;         // [CH]
+    unsigned short* cmask;         // [CH] cells of a 4 x 4 grid over the image that the box touches (pair pre-filter)
 };
 __host__ __device__ inline size_t img_smem_bytes(int max_keep, int n_groups) {
     const int ng = n_groups > 0 ? n_groups : 1;
     return (size_t)CH * 8 + (size_t)CH * MW * 8 + (size_t)ng * MW * 16 + (size_t)CH * sizeof(BoxC) + (size_t)max_keep * sizeof(BoxC) +
            (size_t)HBINS * 2 + (size_t)CH * 4 + (size_t)(ng + 1) * 4 + (size_t)ng * 4 + (size_t)16 * ng * 4 +
-           (size_t)CH * 2 * 2 + (size_t)ng * max_keep * 2 + (size_t)CH + 64;
+           (size_t)CH * 2 * 3 + (size_t)ng * max_keep * 2 + (size_t)CH + 64;
 }
 __device__ __forceinline__ ImgBuffers carve_img(unsigned char* dyn, int max_keep, int n_groups) {
     const int ng = n_groups > 0 ? n_groups : 1;
@@ -692,12 +710,40 @@ __device__ __forceinline__ ImgBuffers carve_img(unsigned char* dyn, int max_keep
     b.wcnt = b.ngroup + ng;
     b.clist = reinterpret_cast<unsigned short*>(b.wcnt + 16 * ng);
     b.cpos = b.clist + CH;
-    b.kidx = b.cpos + CH;
+    b.cmask = b.cpos + CH;
+    b.kidx = b.cmask + CH;
     b.cgroup = reinterpret_cast<unsigned char*>(b.kidx + (size_t)ng * max_keep);
     return b;
 }
 
 constexpr int IT = 512;        // threads of nms_image_kernel
+
+// ---- cold paths of nms_image_kernel, kept out of line so that the code every image runs stays compact -------
+// Replace every approximate key of the list by the exact one and rebuild the score histogram (every thread of the CTA).
+__device__ __noinline__ void nms_make_exact(const SegSource src, unsigned* hist16, const float* conf_b, bool use_hist) {
+    src.for_each<IT>([&](int i, unsigned long long r) {
+        if (SegSource::key(r) == 0u) return;
+        const unsigned id = 0xffffffffu - (unsigned)(r & 0xffffffffull);
+        src.replace(i, ((unsigned long long)exact_score_key6(conf_b + 6ll * (id / 5u), (int)(id % 5u)) << 32) | (r & 0xffffffffull));
+    });
+    for (int i = threadIdx.x; i < HBINS / 2; i += IT) hist16[i] = 0u;
+    __syncthreads();
+    if (use_hist) src.for_each<IT>([&](int, unsigned long long r) { if (SegSource::key(r) != 0u) hist_add(hist16, SegSource::key(r)); });
+    __syncthreads();
+}
+// Exact cut for the K best entries when the histogram cannot give one (a single bin holds more than a round).
+__device__ __noinline__ void nms_select_cut(const SegSource src, UnitShared& us, int K, unsigned* tkey_out, unsigned* tie_floor_out) {
+    unsigned tkey, need, eq, tie_floor = 0u;
+    select_kth<IT>(src, [&](int, unsigned long long r) { return SegSource::key(r); }, (unsigned)K, us, tkey, need, eq);
+    if (need != eq) {                               // ties at the cut: the lowest candidate ids (largest ~id) first
+        unsigned n2, e2;
+        select_kth<IT>(src, [&](int, unsigned long long r) { return SegSource::key(r) == tkey ? (unsigned)(r & 0xffffffffull) : 0u; },
+                       need, us, tie_floor, n2, e2);
+    }
+    *tkey_out = tkey;
+    *tie_floor_out = tie_floor;
+}
+#define SSDHOT_NSTAMP(k) do { if (prm.timeline && threadIdx.x == 0 && first) prm.timeline[(long long)blockIdx.x * 16 + (k)] = globaltimer_ns(); } while (0)
 
 template <int METRIC, bool AGN, bool APPROX>
 __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams prm) {
@@ -713,6 +759,8 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
     src.seg_cap = seg_rows(P) * n_fg;
     src.base = prm.cand + (long long)b * SEGS * src.seg_cap;
     src.counts = prm.cand_count + b * SEGS;
+    bool first = true;
+    SSDHOT_NSTAMP(0);
     const int n_cand = block_sum<int>(tid < SEGS ? src.counts[tid] : 0, us.iscratch);
     const float thr = prm.nms_thresh, thr_lo = fmul(thr, kFilterSlack);
     const float* loc_b = prm.loc_all + 4ll * b * P;
@@ -729,24 +777,14 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
     __syncthreads();
     if (use_hist) src.for_each<IT>([&](int, unsigned long long r) { hist_add(buf.hist16, SegSource::key(r)); });
     __syncthreads();
-    auto make_exact = [&]() {                               // every thread: replace all approximate keys by exact ones
-        src.for_each<IT>([&](int i, unsigned long long r) {
-            if (SegSource::key(r) == 0u) return;
-            src.replace(i, ((unsigned long long)exact_key(0xffffffffu - (unsigned)(r & 0xffffffffull)) << 32) | (r & 0xffffffffull));
-        });
-        for (int i = tid; i < HBINS / 2; i += IT) buf.hist16[i] = 0u;
-        __syncthreads();
-        if (use_hist) src.for_each<IT>([&](int, unsigned long long r) { if (SegSource::key(r) != 0u) hist_add(buf.hist16, SegSource::key(r)); });
-        __syncthreads();
-        keys_exact = true;
-    };
+    auto make_exact = [&]() { nms_make_exact(src, buf.hist16, conf_b, use_hist); keys_exact = true; };
 
+    SSDHOT_NSTAMP(1);
     int kept_n = 0, remaining = n_cand;
-    bool first = true;
     while (remaining > 0 && kept_n < max_keep) {
         // ---- pull ----------------------------------------------------------------------------------
         int K = remaining < CH ? remaining : CH;
-        unsigned tkey = 1u, need = 0u, eq = 0u, tie_floor = 0u;
+        unsigned tkey = 1u, tie_floor = 0u;
         bool all = remaining <= CH;
         if (!all && use_hist) {
             int cap = keys_exact ? CH : CH - 16;            // (room for the few margin strays)
@@ -758,13 +796,9 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
         }
         if (!all) {
             if (APPROX && !keys_exact) make_exact();
-            select_kth<IT>(src, [&](int, unsigned long long r) { return SegSource::key(r); }, (unsigned)K, us, tkey, need, eq);
-            if (need != eq) {                               // ties at the cut: the lowest candidate ids (largest ~id) first
-                unsigned n2, e2;
-                select_kth<IT>(src, [&](int, unsigned long long r) { return SegSource::key(r) == tkey ? (unsigned)(r & 0xffffffffull) : 0u; },
-                               need, us, tie_floor, n2, e2);
-            }
+            nms_select_cut(src, us, K, &tkey, &tie_floor);
         }
+        SSDHOT_NSTAMP(2);
         const unsigned gkey = (keys_exact || tkey <= (unsigned)KEY_MARGIN) ? tkey : tkey - (unsigned)KEY_MARGIN;
         if (tid == 0) us.counter = 0;
         __syncthreads();
@@ -777,6 +811,7 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
             if (keys_exact) src.consume(i);
         });
         __syncthreads();
+        SSDHOT_NSTAMP(3);
         if (APPROX && !keys_exact) {
             const int gathered = us.counter;
             if (gathered > CH) {                            // more margin strays than the slack: settle it with exact keys
@@ -798,20 +833,36 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
             if (tid >= K) buf.ckey[tid] = 0ull;
             __syncthreads();
         }
-        first = false;
-        if (K == 0) continue;                               // (only margin strays: the next cut is lower)
+        SSDHOT_NSTAMP(4);
+        if (K == 0) { first = false; continue; }                               // (only margin strays: the next cut is lower)
         if (K <= 128) bitonic_desc<128>(buf.ckey);           // (entries beyond K are zero and stay behind)
         else if (K <= 256) bitonic_desc<256>(buf.ckey);
         else bitonic_desc<CH>(buf.ckey);
 
+        SSDHOT_NSTAMP(5);
+        if (prm.timeline && tid == 0 && first) prm.timeline[(long long)blockIdx.x * 16 + 13] = (unsigned long long)K;
         // ---- decode + class-local order --------------------------------------------------------------
         int my_g = -1;
+        BoxC my_box = {};
+        unsigned my_cells = 0u;
         if (tid < K) {
             const unsigned id = 0xffffffffu - (unsigned)(buf.ckey[tid] & 0xffffffffull);
             const unsigned p = id / (unsigned)n_fg;
             const float4 box = decode_box(ldg4(loc_b + 4ll * p), ldg4(prm.pri + 4ll * p), prm.vc, prm.vs);
             const float4 px = to_pixel_xyxy(box, prm.img_w, prm.img_h);
-            buf.cbox[tid] = box_consts(px.x, px.y, px.z, px.w, want_atan);
+            my_box = box_consts(px.x, px.y, px.z, px.w, want_atan);
+            {   // which quarter-columns / quarter-rows of the image the (clamped) box reaches: boxes that share no cell
+                // have an empty intersection, so the pair test can skip them on a 16-bit AND
+                const float qx = 4.0f / prm.img_w, qy = 4.0f / prm.img_h;
+                const int cx0 = min(3, max(0, (int)(px.x * qx))), cx1 = min(3, max(0, (int)(px.z * qx)));
+                const int cy0 = min(3, max(0, (int)(px.y * qy))), cy1 = min(3, max(0, (int)(px.w * qy)));
+                const unsigned xm = ((2u << cx1) - 1u) & ~((1u << cx0) - 1u);
+                unsigned m16 = 0u;
+                for (int r = cy0; r <= cy1; ++r) m16 |= xm << (4 * r);
+                // an empty (or NaN) box has union 0 with another empty box: IoU = NaN, which suppresses (SFS:690) -- always test it
+                if (!(fmul(fsub(px.z, px.x), fsub(px.w, px.y)) > 0.0f)) m16 = 0xffffu;
+                my_cells = m16;
+            }
             my_g = AGN ? 0 : (int)(id % (unsigned)n_fg);
             buf.cgroup[tid] = (unsigned char)my_g;
         }
@@ -844,7 +895,11 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
             buf.cpos[tid] = (unsigned short)my_m;
         }
         __syncthreads();
-        if (my_g >= 0) buf.clist[buf.coff[my_g] + my_m] = (unsigned short)tid;
+        if (my_g >= 0) {                                                // boxes and cell masks in class order
+            const int at = buf.coff[my_g] + my_m;
+            buf.cbox[at] = my_box;
+            buf.cmask[at] = (unsigned short)my_cells;
+        }
         for (int i = tid; i < n_groups * MW; i += IT) {                 // alive = every position the class has this round
             const int g = i / MW, w = i % MW, n_c = buf.coff[g + 1] - buf.coff[g];
             const int bits = min(max(n_c - 64 * w, 0), 64);
@@ -852,10 +907,20 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
         }
         __syncthreads();
 
+        SSDHOT_NSTAMP(6);
         // ---- pair tests --------------------------------------------------------------------------------
-        // Entry j of class-local position m is tested against m earlier entries, so entries j and K-1-j
-        // (class positions ~m and ~n_c - m) form one work unit of near-constant size; the units are spread
-        // over all threads, `parts` threads striding through each unit's inner loops.
+        // (a) later rounds only: entry j against the survivors of its class from earlier rounds
+        if (kept_n > 0 && tid < K) {
+            const unsigned short* kl = buf.kidx + (size_t)my_g * max_keep;
+            const int ng = buf.ngroup[my_g];
+            bool hit = false;
+            for (int i = 0; i < ng && !hit; ++i) hit = suppresses<METRIC>(buf.kept[kl[i]], my_box, thr, thr_lo);
+            if (hit) atomicAnd(reinterpret_cast<unsigned*>(buf.aliveW + my_g * MW) + (my_m >> 5), ~(1u << (my_m & 31)));
+        }
+        // (b) entry j (class position m) against the earlier entries of its class.  Entries j and K-1-j (class
+        //     positions ~m and ~n_c - m) form one work unit of near-constant size; `parts` threads stride through
+        //     each unit's inner loops.  Boxes and cell masks sit in class order, so the candidates of (g, m) are the
+        //     contiguous run cbox[coff[g] .. coff[g] + m).  Bit m of row aq (rows in class order) = "aq suppresses m".
         {
             const int units = (K + 1) >> 1;
             const int parts = max(1, IT / units);
@@ -865,19 +930,14 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
                 for (int side = 0; side < 2; ++side) {
                     const int j = side == 0 ? u : K - 1 - u;
                     if (side == 1 && j == u) break;
-                    const BoxC c = buf.cbox[j];
-                    const int g = (int)buf.cgroup[j], m = (int)buf.cpos[j];
-                    bool hit = false;
-                    const unsigned short* kl = buf.kidx + (size_t)g * max_keep;
-                    const int ng = buf.ngroup[g];
-                    for (int i = sub; i < ng; i += parts) hit |= suppresses<METRIC>(buf.kept[kl[i]], c, thr, thr_lo);
-                    if (hit) atomicAnd(&buf.aliveW[g * MW + (m >> 6)], ~(1ull << (m & 63)));
-                    const unsigned short* cl = buf.clist + buf.coff[g];
-                    for (int mm = sub; mm < m; mm += parts) {
-                        const int i = (int)cl[mm];
-                        if (suppresses<METRIC>(buf.cbox[i], c, thr, thr_lo)) {
-                            atomicOr(&buf.mat[(size_t)i * MW + (m >> 6)], 1ull << (m & 63));
-                            atomicOr(&buf.nzW[g * MW + (mm >> 6)], 1ull << (mm & 63));
+                    const int g = (int)buf.cgroup[j], m = (int)buf.cpos[j], cbase = buf.coff[g];
+                    const BoxC c = buf.cbox[cbase + m];
+                    const unsigned my_cells2 = buf.cmask[cbase + m];
+                    for (int aq = sub; aq < m; aq += parts) {
+                        if ((buf.cmask[cbase + aq] & my_cells2) == 0u) continue;        // no common cell: empty intersection
+                        if (suppresses<METRIC>(buf.cbox[cbase + aq], c, thr, thr_lo)) {
+                            atomicOr(reinterpret_cast<unsigned*>(buf.mat + (size_t)(cbase + aq) * MW) + (m >> 5), 1u << (m & 31));
+                            atomicOr(reinterpret_cast<unsigned*>(buf.nzW + g * MW) + (aq >> 5), 1u << (aq & 31));
                         }
                     }
                 }
@@ -885,26 +945,41 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
         }
         __syncthreads();
 
+        SSDHOT_NSTAMP(7);
         // ---- resolve: one warp per class, rows in score order ----------------------------------------------
         for (int g = warp; g < n_groups; g += IT / 32) {
-            const int n_c = buf.coff[g + 1] - buf.coff[g];
+            const int cbase = buf.coff[g], n_c = buf.coff[g + 1] - cbase;
             if (n_c == 0) continue;
             const int words = (n_c + 63) >> 6;
-            const unsigned short* cl = buf.clist + buf.coff[g];
+            if (words == 1) {                                   // the usual case: everything in the registers of one lane
+                if (lane == 0) {
+                    unsigned long long a = buf.aliveW[g * MW];
+                    const unsigned long long nz = buf.nzW[g * MW];
+                    unsigned long long pend = a & nz;
+                    while (pend) {
+                        const int bit = __ffsll((long long)pend) - 1;
+                        a &= ~buf.mat[(size_t)(cbase + bit) * MW];
+                        pend = a & nz & ~((2ull << bit) - 1ull);
+                    }
+                    buf.aliveW[g * MW] = a;
+                }
+                continue;
+            }
             unsigned long long a = lane < MW ? buf.aliveW[g * MW + lane] : 0ull;
             for (int w0 = 0; w0 < words; ++w0) {
-                unsigned long long pend = __shfl_sync(FULL, a, w0) & buf.nzW[g * MW + w0];
+                const unsigned long long nz = buf.nzW[g * MW + w0];
+                unsigned long long pend = __shfl_sync(FULL, a, w0) & nz;
                 while (pend) {
                     const int bit = __ffsll((long long)pend) - 1;
-                    const int i = (int)cl[w0 * 64 + bit];
-                    if (lane < MW) a &= ~buf.mat[(size_t)i * MW + lane];
-                    pend = __shfl_sync(FULL, a, w0) & buf.nzW[g * MW + w0] & ~((2ull << bit) - 1ull);
+                    if (lane < MW) a &= ~buf.mat[(size_t)(cbase + w0 * 64 + bit) * MW + lane];
+                    pend = __shfl_sync(FULL, a, w0) & nz & ~((2ull << bit) - 1ull);
                 }
             }
             if (lane < MW) buf.aliveW[g * MW + lane] = a;
         }
         __syncthreads();
 
+        SSDHOT_NSTAMP(8);
         // ---- emit survivors in global score order ------------------------------------------------------------
         bool alive = false;
         if (my_g >= 0) alive = (buf.aliveW[my_g * MW + (my_m >> 6)] >> (my_m & 63)) & 1ull;
@@ -915,7 +990,7 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
         for (int w = 0; w < IT / 32; ++w) { const int c = us.iscratch[w]; if (w < warp) before += c; total_alive += c; }
         const int pos = kept_n + before;
         if (alive && pos < max_keep) {
-            const BoxC bx = buf.cbox[tid];
+            const BoxC bx = my_box;
             buf.kept[pos] = bx;
             // survivors of the class ahead of this one in the round: alive positions below m
             int crank = 0;
@@ -934,8 +1009,10 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
         kept_n = min(max_keep, kept_n + total_alive);
         remaining -= K;
         __syncthreads();
+        SSDHOT_NSTAMP(9);
+        first = false;
     }
-    if (tid == 0) prm.out_count[b] = kept_n;
+    if (tid == 0) { prm.out_count[b] = kept_n; if (prm.timeline) { prm.timeline[(long long)b * 16 + 10] = globaltimer_ns(); unsigned sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); prm.timeline[(long long)b * 16 + 11] = sm; prm.timeline[(long long)b * 16 + 12] = (unsigned long long)n_cand; } }
 }
 
 // ---- stand-alone NMS -------------------------------------------------------------------------------
@@ -1096,6 +1173,7 @@ extern "C" int ssdhot_predict(const float* priors_cxcywh, int P, const float* lo
     prm.vc = var_center; prm.vs = var_size; prm.img_w = img_w; prm.img_h = img_h;
     prm.out_labels = out_labels; prm.out_scores = out_scores; prm.out_boxes = out_boxes; prm.out_cand = out_cand;
     prm.out_count = out_count;
+    prm.timeline = g_timeline;
     unsigned char* w = reinterpret_cast<unsigned char*>(work);
     prm.cand_count = reinterpret_cast<int*>(w);
     prm.cand = reinterpret_cast<unsigned long long*>(w + pw_cand_off(B));

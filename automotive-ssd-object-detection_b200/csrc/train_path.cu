@@ -755,11 +755,6 @@ __device__ __forceinline__ void axis_hull(float g1, float g2, int side, float in
     if (g2 > 1.0f - w) for (int i = side - nb; i < side; ++i) test(i);
 }
 
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
 #define SSDHOT_STAMP(k) do { if (prm.timeline && (threadIdx.x & 31) == 0) { if (threadIdx.x == 0 || (k) == 2) prm.timeline[(long long)blockIdx.x * 16 + (k)] = globaltimer_ns(); } } while (0)
 
 // Barrier of the threads that run the matching: the whole CTA (MT == FT) or its first MT threads (named barrier 1),
@@ -1563,8 +1558,6 @@ static int launch_loss(const TrainParams& prm, cudaStream_t stream) {
     return SSDHOT_OK;
 }
 
-static unsigned long long* g_timeline = nullptr;   // debug hook (ssdhot_debug_timeline)
-
 template <bool LOSS>
 static int launch_train_image(const TrainParams& prm_in, cudaStream_t stream) {
     TrainParams prm = prm_in;
@@ -1594,13 +1587,6 @@ using namespace ssdhot;
 // Host-side check that `priors` (HOST memory) have the SSD300 structure train_image_kernel relies on:
 // levels of 38/19/10/5/3/1 cells with 4/6/6/6/4/4 shapes, cells row-major, shapes innermost
 // (SSD_from_scratch.py:289-323); centres (i + 0.5)/side within 1e-5; one (w, h) in (0, 1] per (level, shape).
-// Debug hook: device buffer of B x 16 uint64 that the fused train kernel fills with %globaltimer stamps of its
-// phases (null = off, the default).  Not part of the drop-in surface.
-extern "C" int ssdhot_debug_timeline(void* dev_buffer) {
-    g_timeline = reinterpret_cast<unsigned long long*>(dev_buffer);
-    return SSDHOT_OK;
-}
-
 extern "C" int ssdhot_ssd300_layout_host(const float* priors_cxcywh_host, int P) {
     if (!priors_cxcywh_host || P != 8732) return 0;
     static const int side[6] = {38, 19, 10, 5, 3, 1}, shapes[6] = {4, 6, 6, 6, 4, 4};
