@@ -669,6 +669,7 @@ __global__ void __launch_bounds__(ST, 6) score_kernel(const PredictParams prm) {
 // higher-scored candidates of its own class, all of which precede it in the global order.
 constexpr int CH = 512;        // candidates per round
 constexpr int MW = CH / 64;    // 64-bit words of a class-local bit row
+constexpr int PAIRS_CAP = 2048; // listed gate survivors of a round (rest: settled inline)
 
 struct ImgBuffers {
     unsigned long long* ckey;      // [CH] sort keys of the round
@@ -687,11 +688,12 @@ struct ImgBuffers {
     unsigned short* kidx;          // [n_groups][max_keep] positions in `kept` of each class's survivors
     unsigned char* cgroup;         // [CH]
     unsigned short* cmask;         // [CH] cells of a 4 x 4 grid over the image that the box touches (pair pre-filter)
+    unsigned* plist;               // [PAIRS_CAP] pairs that passed the IoU gate: aq | m << 9 | class << 18
 };
 __host__ __device__ inline size_t img_smem_bytes(int max_keep, int n_groups) {
     const int ng = n_groups > 0 ? n_groups : 1;
     return (size_t)CH * 8 + (size_t)CH * MW * 8 + (size_t)ng * MW * 16 + (size_t)CH * sizeof(BoxC) + (size_t)max_keep * sizeof(BoxC) +
-           (size_t)HBINS * 2 + (size_t)CH * 4 + (size_t)(ng + 1) * 4 + (size_t)ng * 4 + (size_t)16 * ng * 4 +
+           (size_t)HBINS * 2 + (size_t)CH * 4 + (size_t)PAIRS_CAP * 4 + (size_t)(ng + 1) * 4 + (size_t)ng * 4 + (size_t)16 * ng * 4 +
            (size_t)CH * 2 * 3 + (size_t)ng * max_keep * 2 + (size_t)CH + 64;
 }
 __device__ __forceinline__ ImgBuffers carve_img(unsigned char* dyn, int max_keep, int n_groups) {
@@ -705,7 +707,8 @@ __device__ __forceinline__ ImgBuffers carve_img(unsigned char* dyn, int max_keep
     b.kept = b.cbox + CH;
     b.hist16 = reinterpret_cast<unsigned*>(b.kept + max_keep);
     b.cidx = reinterpret_cast<int*>(b.hist16 + HBINS / 2);
-    b.coff = b.cidx + CH;
+    b.plist = reinterpret_cast<unsigned*>(b.cidx + CH);
+    b.coff = reinterpret_cast<int*>(b.plist + PAIRS_CAP);
     b.ngroup = b.coff + ng + 1;
     b.wcnt = b.ngroup + ng;
     b.clist = reinterpret_cast<unsigned short*>(b.wcnt + 16 * ng);
@@ -920,7 +923,20 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
         // (b) entry j (class position m) against the earlier entries of its class.  Entries j and K-1-j (class
         //     positions ~m and ~n_c - m) form one work unit of near-constant size; `parts` threads stride through
         //     each unit's inner loops.  Boxes and cell masks sit in class order, so the candidates of (g, m) are the
-        //     contiguous run cbox[coff[g] .. coff[g] + m).  Bit m of row aq (rows in class order) = "aq suppresses m".
+        //     contiguous run cbox[coff[g] .. coff[g] + m).  The loop only runs the cheap tests (common cell, IoU gate);
+        //     the ~3 % of pairs that pass are listed and get the exact metric in a second, dense pass -- in one
+        //     divergent loop every warp would execute the exact path in most iterations.
+        if (tid == 0) us.counter = 0;
+        __syncthreads();
+        auto settle = [&](int g, int cbase, int aq, int m) {          // bit m of row aq (rows in class order) = "aq suppresses m"
+            const BoxC S = buf.cbox[cbase + aq], c = buf.cbox[cbase + m];
+            float inter, uni;
+            iou_gate(S, c, thr_lo, inter, uni);
+            if (suppresses_exact<METRIC>(S, c, inter, uni, thr)) {
+                atomicOr(reinterpret_cast<unsigned*>(buf.mat + (size_t)(cbase + aq) * MW) + (m >> 5), 1u << (m & 31));
+                atomicOr(reinterpret_cast<unsigned*>(buf.nzW + g * MW) + (aq >> 5), 1u << (aq & 31));
+            }
+        };
         {
             const int units = (K + 1) >> 1;
             const int parts = max(1, IT / units);
@@ -935,12 +951,22 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
                     const unsigned my_cells2 = buf.cmask[cbase + m];
                     for (int aq = sub; aq < m; aq += parts) {
                         if ((buf.cmask[cbase + aq] & my_cells2) == 0u) continue;        // no common cell: empty intersection
-                        if (suppresses<METRIC>(buf.cbox[cbase + aq], c, thr, thr_lo)) {
-                            atomicOr(reinterpret_cast<unsigned*>(buf.mat + (size_t)(cbase + aq) * MW) + (m >> 5), 1u << (m & 31));
-                            atomicOr(reinterpret_cast<unsigned*>(buf.nzW + g * MW) + (aq >> 5), 1u << (aq & 31));
-                        }
+                        float inter, uni;
+                        if (!iou_gate(buf.cbox[cbase + aq], c, thr_lo, inter, uni)) continue;
+                        const int slot = atomicAdd(&us.counter, 1);
+                        if (slot < PAIRS_CAP) buf.plist[slot] = (unsigned)aq | ((unsigned)m << 9) | ((unsigned)g << 18);
+                        else settle(g, cbase, aq, m);
                     }
                 }
+            }
+        }
+        __syncthreads();
+        {
+            const int n_list = min(us.counter, PAIRS_CAP);
+            for (int e = tid; e < n_list; e += IT) {
+                const unsigned pr = buf.plist[e];
+                const int g = (int)(pr >> 18);
+                settle(g, buf.coff[g], (int)(pr & 511u), (int)((pr >> 9) & 511u));
             }
         }
         __syncthreads();

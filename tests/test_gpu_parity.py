@@ -516,3 +516,57 @@ def test_fast_train_path_equals_generic_path(env):
             pos_o, _, cls_o = O.batch_targets(env["pri"], env["pri_xyxy"], to_dev(targets, dev), 300, 300, thr)
             assert bit_equal(fast[1] > 0, pos_o), (name, thr)
             assert bit_equal(fast[1].long().clamp_min(0)[pos_o], cls_o[pos_o]), (name, thr)
+
+
+def test_predict_threshold_edge_is_exact(env):
+    """score_kernel ranks with approximate softmax scores but must take the candidate SET from the exact
+    arithmetic: thresholds placed exactly on, one ulp below and one ulp above real scores flip exactly the
+    candidates the strict `score > thresh` of the reference (SFS:402) flips."""
+    s, dev, ps, pri = env["ssdhot"], env["dev"], env["ps"], env["pri"]
+    gen = torch.Generator().manual_seed(314)
+    loc = torch.randn((1, 8732, 4), generator=gen).to(dev)
+    conf = torch.randn((1, 8732, 6), generator=gen)
+    conf[..., 0] += 3.0
+    conf = conf.to(dev)
+    scores = conf[0].softmax(-1)[:, 1:].reshape(-1)
+    srt = torch.sort(scores, descending=True).values
+    for rank in (50, 400, 3000):
+        sv = srt[rank]
+        for thr in (sv, torch.nextafter(sv, sv.new_tensor(0.0)), torch.nextafter(sv, sv.new_tensor(1.0))):
+            thr = float(thr)
+            n_ref = int((scores > thr).sum())
+            want = O.postprocess(pri, loc, conf, thr, 0.45, 8732 * 5 // 64, False, nms_limit=True, with_index=True)
+            *_, count, cand = s.predict_padded(ps, loc, conf, thr, 0.45, 8732 * 5 // 64, want_cand=True)
+            assert bit_equal(cand[0, : int(count[0])].long(), want[0]["cand"]), (rank, thr, n_ref)
+    # NMS off (threshold close to 1): every candidate survives, so the output count IS the candidate count
+    for rank in (20, 150):
+        sv = srt[rank]
+        for thr, expect in ((float(sv), rank), (float(torch.nextafter(sv, sv.new_tensor(0.0))), rank + 1)):
+            dup = int((srt == sv).sum())                     # (exact duplicates of the probe score would shift the count)
+            if dup != 1:
+                continue
+            *_, count = s.predict_padded(ps, loc, conf, thr, 0.999999, 600)
+            assert int(count[0]) == expect, (rank, thr, int(count[0]), expect)
+
+
+def test_predict_multi_round_suppression(env):
+    """Heavy suppression: decoded boxes are the priors themselves (loc = 0) and one class takes nearly all the
+    score mass, so neighbouring priors of a cell suppress each other and the first pull of ~1.5 max_per_img
+    candidates does not yield max_per_img survivors -- the later rounds (tests against earlier survivors,
+    per-class lists) must reproduce the reference's greedy order exactly."""
+    s, dev, ps, pri = env["ssdhot"], env["dev"], env["ps"], env["pri"]
+    gen = torch.Generator().manual_seed(2718)
+    loc = (0.05 * torch.randn((3, 8732, 4), generator=gen)).to(dev)
+    conf = torch.randn((3, 8732, 6), generator=gen)
+    conf[0, :, 2] += 4.0                                     # image 0: almost everything is class 1 (one long class list)
+    conf[1, :, 1:] += 1.0                                    # image 1: all classes busy
+    conf[2, :, 0] += 8.0                                     # image 2: sparse
+    conf = conf.to(dev)
+    for thr, nms, keep, agn in ((0.05, 0.3, 200, False), (0.02, 0.45, 400, False), (0.05, 0.3, 150, True)):
+        want = O.postprocess(pri, loc, conf, thr, nms, keep, agn, nms_limit=True, with_index=True)
+        labels, scores, boxes, count, cand = s.predict_padded(ps, loc, conf, thr, nms, keep, agn, want_cand=True)
+        for b in range(3):
+            k = int(count[b])
+            assert bit_equal(cand[b, :k].long(), want[b]["cand"]), (thr, nms, keep, agn, b, k, want[b]["cand"].numel())
+            assert bit_equal(scores[b, :k], want[b]["scores"]) and bit_equal(boxes[b, :k], want[b]["boxes"])
+            assert bit_equal(labels[b, :k], want[b]["labels"])
