@@ -99,7 +99,7 @@ struct DenseSource {           // key array indexed by candidate id (stand-alone
         return (r << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
     }
 };
-constexpr int SEGS = 32;       // list segments per image = warps of score_kernel per image = warps of nms_image_kernel
+constexpr int SEGS = 16;       // list segments per image = warps of score_kernel per image = warps of nms_image_kernel
 struct SegSource {             // 32 per-warp segments of (key << 32 | ~id) written by score_kernel (global memory)
     unsigned long long* base; const int* counts; int seg_cap;
     template <int NT, typename F>
@@ -556,7 +556,7 @@ __device__ __forceinline__ unsigned exact_score_key6(const float* __restrict__ r
 // more than 1e-4 (relative) away from the threshold and by the exact eager-CUDA arithmetic otherwise, so
 // the candidate SET is exact; the keys are approximate and nms_image_kernel refines the ones it pulls.
 template <int CT>
-__global__ void __launch_bounds__(ST, 6) score_kernel(const PredictParams prm) {
+__global__ void __launch_bounds__(ST, 4) score_kernel(const PredictParams prm) {
     const int b = blockIdx.x / SCS, part = blockIdx.x % SCS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int seg = part * (ST / 32) + warp;
@@ -571,13 +571,22 @@ __global__ void __launch_bounds__(ST, 6) score_kernel(const PredictParams prm) {
         const float thr = prm.score_thresh, thr_hi = thr * 1.0001f, thr_lo = thr * 0.9999f;
         const float4* src = reinterpret_cast<const float4*>(conf_b);
         const int q1 = r1 >> 1;                             // P is even on this path
-#pragma unroll 2
+        // software pipeline: the three 16-byte loads of the next row pair are in flight while this one is scored
+        float4 nA = make_float4(0.f, 0.f, 0.f, 0.f), nB = nA, nC = nA;
+        {
+            const int q = (r0 >> 1) + lane;
+            if (q < q1) { nA = __ldg(src + 3 * q); nB = __ldg(src + 3 * q + 1); nC = __ldg(src + 3 * q + 2); }
+        }
         for (int qb = r0 >> 1; qb < q1; qb += 32) {
             const int q = qb + lane;
             unsigned pass = 0u;                             // bit (h * 5 + k): row 2q+h, class k+1 is a candidate
             float sc[10];
+            const float4 A = nA, Bv = nB, Cv = nC;
+            {
+                const int qn = q + 32;
+                if (qn < q1) { nA = __ldg(src + 3 * qn); nB = __ldg(src + 3 * qn + 1); nC = __ldg(src + 3 * qn + 2); }
+            }
             if (q < q1) {
-                const float4 A = __ldg(src + 3 * q), Bv = __ldg(src + 3 * q + 1), Cv = __ldg(src + 3 * q + 2);
                 const float x[2][6] = {{A.x, A.y, A.z, A.w, Bv.x, Bv.y}, {Bv.z, Bv.w, Cv.x, Cv.y, Cv.z, Cv.w}};
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {

@@ -181,7 +181,7 @@ SSDHOT_API int ssdhot_nms(const float* boxes, const float* scores, const int32_t
  *   out_labels [B,max_per_img] int64 (0-based foreground id), out_scores [B,max_per_img],
  *   out_boxes [B,max_per_img,4] pixel xyxy, out_cand [B,max_per_img] int32 (optional: flat
  *   candidate id prior*(C-1)+class), out_count [B] int32 valid entries per image.
- * work: ssdhot_predict_workspace_bytes(B, P, C) bytes (32 candidate-list segments per image), 16-byte aligned. */
+ * work: ssdhot_predict_workspace_bytes(B, P, C) bytes (16 candidate-list segments per image), 16-byte aligned. */
 SSDHOT_API unsigned long long ssdhot_predict_workspace_bytes(int B, int P, int C);
 SSDHOT_API int ssdhot_predict(const float* priors_cxcywh, int P, const float* loc_all, const float* conf_all,
                    int B, int C, float score_thresh, float nms_thresh, int max_per_img,
