@@ -61,6 +61,27 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor on the
+// stream is still running; it must call pdl_wait() before touching anything the predecessor writes.  The
+// predecessor calls pdl_trigger() once the dependent grid may be scheduled.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 extern unsigned long long g_launches;   // host-side counter (abi.cu)
 extern unsigned long long* g_timeline;  // debug hook (ssdhot_debug_timeline, abi.cu): device buffer [units][16] or null
 

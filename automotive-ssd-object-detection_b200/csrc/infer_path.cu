@@ -557,6 +557,7 @@ __device__ __forceinline__ unsigned exact_score_key6(const float* __restrict__ r
 // the candidate SET is exact; the keys are approximate and nms_image_kernel refines the ones it pulls.
 template <int CT>
 __global__ void __launch_bounds__(ST, 4) score_kernel(const PredictParams prm) {
+    pdl_trigger();                                 // nms_image_kernel's CTAs may be scheduled as SMs free up (they wait for this grid)
     const int b = blockIdx.x / SCS, part = blockIdx.x % SCS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int seg = part * (ST / 32) + warp;
@@ -772,6 +773,9 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
     src.base = prm.cand + (long long)b * SEGS * src.seg_cap;
     src.counts = prm.cand_count + b * SEGS;
     bool first = true;
+    for (int i = tid; i < HBINS / 2; i += IT) buf.hist16[i] = 0u;
+    for (int g = tid; g < n_groups; g += IT) buf.ngroup[g] = 0;
+    pdl_wait();                                    // score_kernel's lists and counts are complete from here on
     SSDHOT_NSTAMP(0);
     const int n_cand = block_sum<int>(tid < SEGS ? src.counts[tid] : 0, us.iscratch);
     const float thr = prm.nms_thresh, thr_lo = fmul(thr, kFilterSlack);
@@ -784,8 +788,6 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
 
     bool use_hist = n_cand > CH && n_cand < 65536;          // 16-bit bin counters
     bool keys_exact = !APPROX;
-    for (int i = tid; i < HBINS / 2; i += IT) buf.hist16[i] = 0u;
-    for (int g = tid; g < n_groups; g += IT) buf.ngroup[g] = 0;
     __syncthreads();
     if (use_hist) src.for_each<IT>([&](int, unsigned long long r) { hist_add(buf.hist16, SegSource::key(r)); });
     __syncthreads();
@@ -1120,8 +1122,10 @@ template <int METRIC, bool AGN, bool APPROX>
 static int launch_nms_image(const PredictParams& prm, size_t dyn, cudaStream_t stream) {
     int rc;
     if ((rc = set_smem(nms_image_kernel<METRIC, AGN, APPROX>, dyn))) return rc;
-    nms_image_kernel<METRIC, AGN, APPROX><<<prm.B, IT, dyn, stream>>>(prm);
-    SSDHOT_CHECK_LAUNCH();
+    // PDL: the CTAs may start (shared-memory carve-up, histogram clear) while score_kernel drains
+    cudaError_t e = launch_pdl(nms_image_kernel<METRIC, AGN, APPROX>, dim3(prm.B), dim3(IT), dyn, stream, prm);
+    ++g_launches;
+    if (e != cudaSuccess) return (int)e;
     return SSDHOT_OK;
 }
 

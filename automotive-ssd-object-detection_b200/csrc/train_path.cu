@@ -1045,6 +1045,7 @@ template <bool LOSS>
 __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams prm) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ FusedStatic fs;
+    pdl_trigger();                                 // finalize_sums_kernel may be scheduled early (it waits for this grid)
     SSDHOT_STAMP(0);
     constexpr int MT = LOSS ? MT_LOSS : FT;                  // threads that run the matching
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1392,6 +1393,7 @@ __global__ void __launch_bounds__(256) finalize_sums_kernel(const double* __rest
                                                             const int32_t* __restrict__ n_pos, int B,
                                                             double* __restrict__ sums) {
     __shared__ double scratch[32];
+    pdl_wait();                                    // (launched with PDL: the producers' partial sums are complete from here on)
     double a = 0.0, c = 0.0, n = 0.0;
     for (int i = threadIdx.x; i < n_part; i += blockDim.x) { a += cta_part[2ll * i]; c += cta_part[2ll * i + 1]; }
     for (int i = threadIdx.x; i < B; i += blockDim.x) n += (double)n_pos[i];
@@ -1690,8 +1692,9 @@ extern "C" unsigned long long ssdhot_loss_workspace_bytes(int B, int P, int max_
 }
 
 static int finalize(const TrainParams& prm, const int32_t* n_pos, double* sums, cudaStream_t stream) {
-    finalize_sums_kernel<<<1, 256, 0, stream>>>(prm.img_part, prm.B, n_pos, prm.B, sums);
-    SSDHOT_CHECK_LAUNCH();
+    cudaError_t e = launch_pdl(finalize_sums_kernel, dim3(1), dim3(256), 0, stream, (const double*)prm.img_part, prm.B, n_pos, prm.B, sums);
+    ++g_launches;
+    if (e != cudaSuccess) return (int)e;
     return SSDHOT_OK;
 }
 
