@@ -53,3 +53,35 @@ def losses_from_sums(sums: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     total = sums[2].clamp_min(1.0)
     out = (sums[:2] / total).to(torch.float32)
     return out[0], out[1]
+
+
+class SumsReducer:
+    """Overlaps the sharded path's one exchange with the next step: `submit(sums)` snapshots the three partial sums
+    on the current stream and all-reduces the snapshot on a side stream, so the kernels of the next step do not
+    wait for the collective's launch latency; `result()` returns the newest reduced sums (the current stream then
+    waits for that collective only)."""
+
+    def __init__(self, device, group=None, depth: int = 2):
+        self.group, self.depth, self.n = group, int(depth), 0
+        self.side = torch.cuda.Stream(device)
+        self.bufs = [torch.zeros((3,), dtype=torch.float64, device=device) for _ in range(self.depth)]
+        self.copied = [torch.cuda.Event() for _ in range(self.depth)]
+        self.reduced = [torch.cuda.Event() for _ in range(self.depth)]
+
+    def submit(self, sums: torch.Tensor) -> None:
+        i = self.n % self.depth
+        cur = torch.cuda.current_stream(sums.device)
+        if self.n >= self.depth:
+            cur.wait_event(self.reduced[i])            # the snapshot slot is free again
+        self.bufs[i].copy_(sums)
+        self.copied[i].record(cur)
+        self.side.wait_event(self.copied[i])
+        with torch.cuda.stream(self.side):
+            combine_sums(self.bufs[i], self.group)
+            self.reduced[i].record(self.side)
+        self.n += 1
+
+    def result(self) -> torch.Tensor:
+        i = (self.n - 1) % self.depth
+        torch.cuda.current_stream(self.bufs[i].device).wait_event(self.reduced[i])
+        return self.bufs[i]

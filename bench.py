@@ -207,12 +207,14 @@ def main():
     step = HotPathStep(ps, BATCH, C, spec["iou_thresh"], spec["ratio"], spec["score_thresh"], spec["nms_thresh"],
                        spec["max_per_img"], concurrent=not args.serial)
     use_graph = not args.no_graph
+    reducer = D.SumsReducer(dev) if group is not None else None
 
     def one_step(i):
         s = sets[i % N_SETS]
         step.run(s["loc"], s["conf_t"], s["conf_i"], s["gt"], use_graph=use_graph)
-        if group is not None:
-            D.combine_sums(step.sums)       # outside the graph: a captured NCCL collective hung at process exit on this stack
+        if reducer is not None:
+            reducer.submit(step.sums)       # every step's [sum loc, sum CE, sum positives] is all-reduced, on a side stream
+                                            # (outside the graph: a captured NCCL collective hung at process exit on this stack)
 
     def barrier():
         if world > 1:
@@ -385,7 +387,7 @@ def main():
                        "global_batch": BATCH * world, "per_gpu_batch": BATCH,
                        "l2": f"inputs rotate over {N_SETS} sets of 89.5 MB (> 126 MB L2) so no step re-reads a warm L2",
                        "cuda_graph": use_graph, "halves": "serial" if args.serial else "forked (independent halves on two streams)",
-                       "parallelism": f"image-sharded x{world}, all-reduce of 3 doubles"},
+                       "parallelism": f"image-sharded x{world}, all-reduce of 3 doubles per step" + (" on a side stream" if world > 1 else "")},
             "parts": {"match_loss_images_per_s": BATCH * world / (ms_loss * 1e-3),
                       "decode_nms_images_per_s": BATCH * world / (ms_pred * 1e-3)},
             "roofline": roofline,
