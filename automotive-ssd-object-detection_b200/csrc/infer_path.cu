@@ -1195,6 +1195,18 @@ extern "C" int ssdhot_predict(const float* priors_cxcywh, int P, const float* lo
                               float img_w, float img_h,
                               int64_t* out_labels, float* out_scores, float* out_boxes, int32_t* out_cand,
                               int32_t* out_count, void* work, ssdhot_stream_t stream) {
+    return ssdhot_predict_stages(priors_cxcywh, P, loc_all, conf_all, B, C, score_thresh, nms_thresh, max_per_img, class_agnostic,
+                                 metric, var_center, var_size, img_w, img_h, out_labels, out_scores, out_boxes, out_cand, out_count,
+                                 work, SSDHOT_STAGE_SCORES | SSDHOT_STAGE_NMS, stream);
+}
+
+extern "C" int ssdhot_predict_stages(const float* priors_cxcywh, int P, const float* loc_all, const float* conf_all,
+                                     int B, int C, float score_thresh, float nms_thresh, int max_per_img,
+                                     int class_agnostic, int metric, float var_center, float var_size,
+                                     float img_w, float img_h,
+                                     int64_t* out_labels, float* out_scores, float* out_boxes, int32_t* out_cand,
+                                     int32_t* out_count, void* work, int stages, ssdhot_stream_t stream) {
+    if ((stages & ~(SSDHOT_STAGE_SCORES | SSDHOT_STAGE_NMS)) != 0 || stages == 0) return SSDHOT_ERR_VALUE;
     if (!priors_cxcywh || !loc_all || !conf_all || !out_labels || !out_scores || !out_boxes || !out_count || !work)
         return SSDHOT_ERR_NULL;
     if (P <= 0 || B <= 0 || C < 2 || C > SSDHOT_MAX_CLASSES || max_per_img <= 0 || max_per_img > 65535) return SSDHOT_ERR_SHAPE;
@@ -1219,9 +1231,12 @@ extern "C" int ssdhot_predict(const float* priors_cxcywh, int P, const float* lo
     cudaStream_t s = (cudaStream_t)stream;
     // C == 6 with 48-byte-aligned row pairs: approximate scores, refined by the NMS kernel; otherwise exact scores
     const bool approx = C == 6 && (P % 2) == 0 && al16(conf_all);
-    if (approx) score_kernel<6><<<B * SCS, ST, 0, s>>>(prm);
-    else score_kernel<0><<<B * SCS, ST, 0, s>>>(prm);
-    SSDHOT_CHECK_LAUNCH();
+    if (stages & SSDHOT_STAGE_SCORES) {
+        if (approx) score_kernel<6><<<B * SCS, ST, 0, s>>>(prm);
+        else score_kernel<0><<<B * SCS, ST, 0, s>>>(prm);
+        SSDHOT_CHECK_LAUNCH();
+    }
+    if (!(stages & SSDHOT_STAGE_NMS)) return SSDHOT_OK;
     int rc;
 #define SSDHOT_DISPATCH(M)                                                                                            \
     rc = approx ? (class_agnostic ? launch_nms_image<M, true, true>(prm, dyn, s) : launch_nms_image<M, false, true>(prm, dyn, s))  \

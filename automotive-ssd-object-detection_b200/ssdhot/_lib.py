@@ -40,6 +40,8 @@ PROTOTYPES = {
     "ssdhot_predict_workspace_bytes": (u64, [i32, i32, i32]),
     "ssdhot_predict": (i32, [vp, i32, vp, vp, i32, i32, f32, f32, i32, i32, i32, f32, f32, f32, f32,
                              vp, vp, vp, vp, vp, vp, vp]),
+    "ssdhot_predict_stages": (i32, [vp, i32, vp, vp, i32, i32, f32, f32, i32, i32, i32, f32, f32, f32, f32,
+                                    vp, vp, vp, vp, vp, vp, i32, vp]),
 }
 
 

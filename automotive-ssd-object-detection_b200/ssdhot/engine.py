@@ -59,15 +59,16 @@ class HotPathStep:
             self.sums.data_ptr(), self.loss_work.data_ptr(), None, None, self.n_pos.data_ptr(), None, stream)
         _lib.check(rc, "ssdhot_multibox_loss_fwd")
 
-    def launch_predict(self, loc: torch.Tensor, conf: torch.Tensor, stream: int) -> None:
+    def launch_predict(self, loc: torch.Tensor, conf: torch.Tensor, stream: int, stages: int = 3) -> None:
+        """stages: 1 = score_kernel only (fills the candidate lists), 2 = nms_image_kernel only, 3 = both."""
         ps = self.ps
-        rc = _lib.lib().ssdhot_predict(
+        rc = _lib.lib().ssdhot_predict_stages(
             ps.priors.data_ptr(), ps.P, loc.data_ptr(), conf.data_ptr(), self.B, self.C,
             self.score_thresh, self.nms_thresh, self.max_per_img, 1 if self.agnostic else 0, self.metric,
             ps.variances[0], ps.variances[1], float(ps.img_w), float(ps.img_h),
             self.labels.data_ptr(), self.scores.data_ptr(), self.boxes.data_ptr(), None,
-            self.count.data_ptr(), self.pred_work.data_ptr(), stream)
-        _lib.check(rc, "ssdhot_predict")
+            self.count.data_ptr(), self.pred_work.data_ptr(), int(stages), stream)
+        _lib.check(rc, "ssdhot_predict_stages")
 
     def run(self, loc: torch.Tensor, conf_train: torch.Tensor, conf_infer: torch.Tensor, gt: PackedTargets,
             use_graph: bool = False) -> None:

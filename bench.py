@@ -291,6 +291,26 @@ def main():
         },
     }
 
+    # ---- the HBM-bound streaming kernel of predict on its own (score_kernel: logits in, candidate lists out) -----
+    def time_score_kernel(stp, inputs, batch, iters=16):
+        """inputs: (loc, conf) pairs rotated over the launches (together larger than L2)."""
+        st_ = torch.cuda.current_stream(dev).cuda_stream
+        for i in range(3):
+            stp.launch_predict(*inputs[i % len(inputs)], st_, stages=1)
+        torch.cuda.synchronize(dev)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for i, (a, b) in enumerate(evs):
+            a.record(); stp.launch_predict(*inputs[i % len(inputs)], st_, stages=1); b.record()
+        torch.cuda.synchronize(dev)
+        ms_k = statistics.median(a.elapsed_time(b) for a, b in evs)
+        n_cand = float(stp.pred_work[: batch * 16 * 4].view(torch.int32).sum().item())      # 16 list segments per image
+        nbytes = batch * P * C * 4 + 8.0 * n_cand                                           # logits in, 8-byte keys out
+        return {"per_gpu_batch": batch, "ms": ms_k, "algorithmic_bytes": nbytes, "achieved": nbytes / (ms_k * 1e-3) / 1e9,
+                "frac": nbytes / (ms_k * 1e-3) / 1e9 / peak, "candidates_per_image": n_cand / batch}
+
+    kernels = {"score_kernel": {"b256": time_score_kernel(step, [(x["loc"], x["conf_i"]) for x in sets], BATCH)}}
+    roofline["kernels"] = kernels
+
     # ---- the same halves at B = 2048 per GPU (wave quantisation and launch latency amortised) -------------
     large = None
     if not args.skip_large_batch and rank == 0:
@@ -315,6 +335,7 @@ def main():
             return statistics.median(a.elapsed_time(b) for a, b in evs)
 
         ml, mp = time_large(True), time_large(False)
+        kernels["score_kernel"]["b2048"] = time_score_kernel(step_l, [(big["loc"], big["conf_i"])], LB, iters=10)
         g_l = statistics.mean(float(t["boxes"].shape[0]) for t in cfg_l["targets"])
         k_l = float(step_l.count.float().mean().item())
         bl, bp = LB * (349296 + 24 * g_l + 12), LB * (349296 + 28 * k_l + 4)

@@ -190,6 +190,19 @@ SSDHOT_API int ssdhot_predict(const float* priors_cxcywh, int P, const float* lo
                    int64_t* out_labels, float* out_scores, float* out_boxes, int32_t* out_cand,
                    int32_t* out_count, void* work, ssdhot_stream_t stream);
 
+/* The two stages of ssdhot_predict separately (same arguments): SSDHOT_STAGE_SCORES streams the logits and fills the
+ * candidate lists in `work` (score_kernel, the HBM-bound stage); SSDHOT_STAGE_NMS ranks them and runs the greedy NMS
+ * (nms_image_kernel) -- it consumes the lists, so it needs a fresh SCORES stage before every call.  ssdhot_predict is
+ * stages = SCORES | NMS.  Used by bench.py to time the streaming kernel against the HBM roofline on its own. */
+#define SSDHOT_STAGE_SCORES 1
+#define SSDHOT_STAGE_NMS 2
+SSDHOT_API int ssdhot_predict_stages(const float* priors_cxcywh, int P, const float* loc_all, const float* conf_all,
+                          int B, int C, float score_thresh, float nms_thresh, int max_per_img,
+                          int class_agnostic, int metric, float var_center, float var_size,
+                          float img_w, float img_h,
+                          int64_t* out_labels, float* out_scores, float* out_boxes, int32_t* out_cand,
+                          int32_t* out_count, void* work, int stages, ssdhot_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
