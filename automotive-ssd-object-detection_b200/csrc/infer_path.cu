@@ -2,26 +2,24 @@
 // (SURVEY.md section 8a rows a6-a8).
 //
 // predict = two kernels:
-//  * score_kernel -- the HBM-bound half.  The class logits are streamed once, 8 CTAs per image;
-//    softmax is evaluated in the operation order of eager torch-CUDA, every (prior, foreground
-//    class) pair is tested against the score threshold, and the survivors are appended to the
-//    image's candidate list as 64-bit keys (order-preserving score bits << 32 | ~candidate id), so
-//    sorting the keys descending orders by score and breaks ties by candidate id
-//    prior*(C-1)+class.  A warp compacts its "maybe" pairs first, so the IEEE division, threshold
-//    test and append run once per ~24 pairs instead of once per class.
-//  * nms_image_kernel -- one CTA of 1024 threads per image walks the image's candidates of ALL
-//    classes in one global score order and applies class-aware greedy NMS, so the walk stops as
-//    soon as max_per_img boxes survive.  That is exactly the reference's result -- per-class greedy
-//    NMS, then a global score sort and `keep[:max_per_img]` (SSD_from_scratch.py:439-465): a
-//    candidate's fate depends only on higher-scored candidates of its own class, all of which
-//    precede it in the global order, and survivors appear in global score order -- but the
-//    thousands of low-score candidates that cannot reach the output are never ranked or tested.
-//    Candidates are consumed best-first in chunks of <= 256: a score histogram gives the cut, the
-//    chunk is sorted by a bitonic network (warp shuffles + 6 shared-memory stages), its boxes are
-//    decoded, and greedy NMS walks it in tiles of 64: 16 threads per tile member test it against
-//    the survivors of its class and the earlier tile members (cheap IoU gate first, exact metric
-//    only for pairs that can matter), then one thread resolves the tile with 64-bit masks.
-// The stand-alone NMS entry point (mySSD.iou_nms) runs the same unit over a dense key array.
+//  * score_kernel -- the HBM-bound stage.  The class logits are streamed once (two CTAs x 8 warps per image,
+//    16-byte loads, software-pipelined); every (prior, foreground class) pair is tested against the score
+//    threshold and the survivors are appended to the warp's own segment of the image's candidate list as
+//    64-bit keys (order-preserving score bits << 32 | ~candidate id), so sorting the keys descending orders
+//    by score and breaks ties by candidate id prior*(C-1)+class.  For C == 6 the scores are approximate
+//    (ex2.approx / rcp.approx); decisions within 1e-4 of the threshold are re-made with the exact eager-CUDA
+//    arithmetic, so the candidate set is exact.
+//  * nms_image_kernel -- one CTA of 512 threads per image walks the image's candidates of ALL classes in
+//    one global score order and applies class-aware greedy NMS, so the walk stops as soon as max_per_img
+//    boxes survive.  That is exactly the reference's result -- per-class greedy NMS, then a global score
+//    sort and `keep[:max_per_img]` (SSD_from_scratch.py:439-465): a candidate's fate depends only on
+//    higher-scored candidates of its own class, all of which precede it in the global order, and survivors
+//    appear in global score order -- but the thousands of low-score candidates that cannot reach the output
+//    are never ranked or tested.  Rounds of <= 512 candidates: score histogram -> cut -> gather -> exact
+//    scores of the pulled candidates -> bitonic sort -> decode -> class-local order -> pair tests (IoU gate,
+//    then the exact metric for the few pairs that pass) into class-local bit rows -> per-class resolve.
+// The stand-alone NMS entry point (mySSD.iou_nms, nms_sets_kernel / nms_unit) handles arbitrary set sizes
+// and unbounded survivor counts with tiles of 64 and a CTA-local radix select.
 #include <map>
 #include <mutex>
 

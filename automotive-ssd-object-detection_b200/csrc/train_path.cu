@@ -1,12 +1,15 @@
 // train_path.cu -- match + encode + mined multibox loss.
 //
-// Two kernels:
+// The SSD300 fast path is ONE kernel, train_image_kernel (second half of this file): box-centric matching over
+// candidate rectangles beside the logit stream, approximate-then-exact hard-negative mining, one CTA per image.
+// The layout-agnostic path (any priors / class count / > 64 boxes per image, and encode_ssd's "every prior"
+// outputs) is two kernels:
 //  * match_kernel -- one thread-block CLUSTER per image (8 CTAs of 256 threads); each CTA owns a
 //    contiguous slice of the priors, each thread keeps KP of them in registers, the image's ground
 //    truth lives in shared memory with its per-box constants, and the column arg-max (best prior
 //    per ground truth) is combined across the cluster through distributed shared memory.  On the
 //    fused-loss path its only output is a 2-byte code per prior (0 = negative, 1 + matched box).
-//  * loss_image_kernel -- one CTA of 1024 threads per image streams the class logits once
+//  * loss_image_kernel -- one CTA of 768 threads per image streams the class logits once
 //    (the HBM-bound part), forms softmax cross-entropy and smooth-L1 in registers and picks the
 //    hard negatives with a CTA-local 4-pass radix select; no [B,P] float tensor touches HBM.
 //
