@@ -929,12 +929,10 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
             for (int i = 0; i < ng && !hit; ++i) hit = suppresses<METRIC>(buf.kept[kl[i]], my_box, thr, thr_lo);
             if (hit) atomicAnd(reinterpret_cast<unsigned*>(buf.aliveW + my_g * MW) + (my_m >> 5), ~(1u << (my_m & 31)));
         }
-        // (b) entry j (class position m) against the earlier entries of its class.  Entries j and K-1-j (class
-        //     positions ~m and ~n_c - m) form one work unit of near-constant size; `parts` threads stride through
-        //     each unit's inner loops.  Boxes and cell masks sit in class order, so the candidates of (g, m) are the
-        //     contiguous run cbox[coff[g] .. coff[g] + m).  The loop only runs the cheap tests (common cell, IoU gate);
-        //     the ~3 % of pairs that pass are listed and get the exact metric in a second, dense pass -- in one
-        //     divergent loop every warp would execute the exact path in most iterations.
+        // (b) every entry against the earlier entries of its class (boxes and cell masks sit in class order).  The loop
+        //     only runs the cheap tests (common cell, IoU gate); the ~3 % of pairs that pass are listed and get the
+        //     exact metric in a second, dense pass -- in one divergent loop every warp would execute the exact path
+        //     in most iterations.
         if (tid == 0) us.counter = 0;
         __syncthreads();
         auto settle = [&](int g, int cbase, int aq, int m) {          // bit m of row aq (rows in class order) = "aq suppresses m"
@@ -947,24 +945,47 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
             }
         };
         {
-            const int units = (K + 1) >> 1;
-            const int parts = max(1, IT / units);
-            const int u = tid / parts, sub = tid % parts;
-            if (u < units) {
-#pragma unroll 1
-                for (int side = 0; side < 2; ++side) {
-                    const int j = side == 0 ? u : K - 1 - u;
-                    if (side == 1 && j == u) break;
-                    const int g = (int)buf.cgroup[j], m = (int)buf.cpos[j], cbase = buf.coff[g];
-                    const BoxC c = buf.cbox[cbase + m];
-                    const unsigned my_cells2 = buf.cmask[cbase + m];
-                    for (int aq = sub; aq < m; aq += parts) {
-                        if ((buf.cmask[cbase + aq] & my_cells2) == 0u) continue;        // no common cell: empty intersection
+            // All (earlier, later) pairs of class positions, class after class, form one index space of
+            // T = sum n_c (n_c - 1) / 2 tests; every thread takes a contiguous run of ceil(T / IT) of them and walks it
+            // (later position m, earlier position aq: aq = 0 .. m-1, then m + 1, then the next class), so the work is
+            // balanced no matter how large individual boxes or classes are.
+            int T = 0;
+            for (int g = 0; g < n_groups; ++g) { const int n_c = buf.coff[g + 1] - buf.coff[g]; T += n_c * (n_c - 1) / 2; }
+            const int W = (T + IT - 1) / IT;
+            int t = tid * W;
+            const int t_end = min(T, t + W);
+            if (t < t_end) {
+                int g = 0, n_c = 0, r = t;
+                for (;; ++g) {                                          // the class that owns test t
+                    n_c = buf.coff[g + 1] - buf.coff[g];
+                    const int pairs = n_c * (n_c - 1) / 2;
+                    if (r < pairs) break;
+                    r -= pairs;
+                }
+                int m = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)r)) * 0.5f);      // r = m (m - 1) / 2 + aq, 0 <= aq < m
+                while (m * (m - 1) / 2 > r) --m;
+                while ((m + 1) * m / 2 <= r) ++m;
+                int aq = r - m * (m - 1) / 2;
+                int cbase = buf.coff[g];
+                BoxC c = buf.cbox[cbase + m];
+                unsigned cells = buf.cmask[cbase + m];
+                for (; t < t_end; ++t) {
+                    if ((buf.cmask[cbase + aq] & cells) != 0u) {        // a common cell (else: empty intersection)
                         float inter, uni;
-                        if (!iou_gate(buf.cbox[cbase + aq], c, thr_lo, inter, uni)) continue;
-                        const int slot = atomicAdd(&us.counter, 1);
-                        if (slot < PAIRS_CAP) buf.plist[slot] = (unsigned)aq | ((unsigned)m << 9) | ((unsigned)g << 18);
-                        else settle(g, cbase, aq, m);
+                        if (iou_gate(buf.cbox[cbase + aq], c, thr_lo, inter, uni)) {
+                            const int slot = atomicAdd(&us.counter, 1);
+                            if (slot < PAIRS_CAP) buf.plist[slot] = (unsigned)aq | ((unsigned)m << 9) | ((unsigned)g << 18);
+                            else settle(g, cbase, aq, m);
+                        }
+                    }
+                    if (++aq == m) {                                    // next later position / next class
+                        aq = 0;
+                        if (++m == n_c && t + 1 < t_end) {
+                            do { ++g; n_c = buf.coff[g + 1] - buf.coff[g]; } while (n_c < 2);
+                            cbase = buf.coff[g];
+                            m = 1;
+                        }
+                        if (t + 1 < t_end) { c = buf.cbox[cbase + m]; cells = buf.cmask[cbase + m]; }
                     }
                 }
             }
