@@ -35,6 +35,7 @@ PROTOTYPES = {
     "ssdhot_mined_ce_fwd": (i32, [vp, vp, vp, i32, i32, i32, f64, vp, vp, vp, vp]),
     "ssdhot_multibox_loss_bwd": (i32, [vp, i32, vp, vp, i32, f32, f32, vp, vp, i32, f32, f32, vp, vp, vp, vp, vp, vp]),
     "ssdhot_decode": (i32, [vp, vp, i32, f32, f32, vp, vp]),
+    "ssdhot_pack_heads": (i32, [vp, i32, i32, vp, vp]),
     "ssdhot_nms_workspace_bytes": (u64, [i64]),
     "ssdhot_nms": (i32, [vp, vp, vp, i32, i64, i32, f32, i32, i32, vp, vp, vp, vp]),
     "ssdhot_predict_workspace_bytes": (u64, [i32, i32, i32]),

@@ -378,6 +378,38 @@ def predict(model, images: Optional[torch.Tensor], score_thresh: float = 0.2, nm
 
 
 # ------------------------------------------------------------------------------------------------
+# head-output packing (the tail of mySSD.forward)
+# ------------------------------------------------------------------------------------------------
+_LEVELS = ((38, 4), (19, 6), (10, 6), (5, 6), (3, 4), (1, 4))
+
+
+def pack_heads(loc_heads: Sequence[torch.Tensor], conf_heads: Sequence[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Drop-in for the tail of mySSD.forward (SSD_from_scratch.py:249-269): the six NCHW outputs of the box heads
+    [B, A*4, H, W] and of the class heads [B, A*C, H, W] -> (loc_all [B,8732,4], conf_all [B,8732,C]), one launch per
+    branch instead of 12 permute().contiguous() + 2 cat."""
+    import ctypes
+    outs = []
+    for heads, what in ((loc_heads, "loc"), (conf_heads, "conf")):
+        if len(heads) != len(_LEVELS):
+            raise ValueError(f"expected {len(_LEVELS)} {what} head outputs, got {len(heads)}")
+        dev = _need_cuda(*heads)
+        B = int(heads[0].shape[0])
+        D = int(heads[0].shape[1]) // _LEVELS[0][1]
+        hs = []
+        for h, (side, shapes) in zip(heads, _LEVELS):
+            if tuple(h.shape) != (B, shapes * D, side, side):
+                raise ValueError(f"{what} head of the {side}x{side} level has shape {tuple(h.shape)}, expected {(B, shapes * D, side, side)}")
+            hs.append(h.detach().to(torch.float32).contiguous())
+        out = torch.empty((B, 8732, D), dtype=torch.float32, device=dev)
+        ptrs = (ctypes.c_void_p * len(hs))(*[h.data_ptr() for h in hs])
+        with torch.cuda.device(dev):
+            rc = _lib.lib().ssdhot_pack_heads(ctypes.cast(ptrs, ctypes.c_void_p), B, D, out.data_ptr(), _stream(dev))
+        _lib.check(rc, "ssdhot_pack_heads")
+        outs.append(out)
+    return outs[0], outs[1]
+
+
+# ------------------------------------------------------------------------------------------------
 # patching the reference in place
 # ------------------------------------------------------------------------------------------------
 def patch(model=None, trainer_module=None):

@@ -190,6 +190,13 @@ SSDHOT_API int ssdhot_predict(const float* priors_cxcywh, int P, const float* lo
                    int64_t* out_labels, float* out_scores, float* out_boxes, int32_t* out_cand,
                    int32_t* out_count, void* work, ssdhot_stream_t stream);
 
+/* ---- f.3 (first step): head-output packing ---------------------------------------------------------
+ * The tail of mySSD.forward (SFS:249-269): the six NCHW head outputs [B, shapes_l * D, side_l, side_l] of one branch
+ * (D = 4 box offsets, or D = C class logits; levels 38/19/10/5/3/1 with 4/6/6/6/4/4 shapes) -> out [B, 8732, D], the
+ * layout every other entry point reads -- one launch instead of 6 permute().contiguous() + view + cat, every byte read
+ * and written once.  heads_host is a HOST array of the six DEVICE pointers. */
+SSDHOT_API int ssdhot_pack_heads(const float* const* heads_host, int B, int D, float* out, ssdhot_stream_t stream);
+
 /* The two stages of ssdhot_predict separately (same arguments): SSDHOT_STAGE_SCORES streams the logits and fills the
  * candidate lists in `work` (score_kernel, the HBM-bound stage); SSDHOT_STAGE_NMS ranks them and runs the greedy NMS
  * (nms_image_kernel) -- it consumes the lists, so it needs a fresh SCORES stage before every call.  ssdhot_predict is

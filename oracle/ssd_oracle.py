@@ -48,6 +48,19 @@ PRIORS_XYXY_SHA256 = "308e341f2bdeed01516e5f802eeb2de321414055e7e187bf25415ddfb4
 
 
 # --------------------------------------------------------------------------------------
+# f.3 head-output packing (the tail of mySSD.forward)                          SFS:249-269
+# --------------------------------------------------------------------------------------
+def pack_heads(loc_heads: Sequence[torch.Tensor], conf_heads: Sequence[torch.Tensor], num_classes: int):
+    """Six NCHW head outputs per branch -> (loc_all [B,8732,4], conf_all [B,8732,C]) exactly as the reference writes it:
+    permute(0,2,3,1).contiguous() per level (SFS:249-262), flatten + cat (SFS:265-266), view (SFS:268-269)."""
+    loc_list = [o.permute(0, 2, 3, 1).contiguous() for o in loc_heads]
+    cls_list = [o.permute(0, 2, 3, 1).contiguous() for o in conf_heads]
+    loc_output = torch.cat([o.view(o.size(0), -1) for o in loc_list], 1)
+    cls_output = torch.cat([o.view(o.size(0), -1) for o in cls_list], 1)
+    return loc_output.view(loc_output.size(0), -1, 4), cls_output.view(cls_output.size(0), -1, num_classes)
+
+
+# --------------------------------------------------------------------------------------
 # a1. default boxes                                                     SFS:275-331, :32-35
 # --------------------------------------------------------------------------------------
 def default_boxes(s_min: float = 0.2, s_max: float = 0.9) -> torch.Tensor:

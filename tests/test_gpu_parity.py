@@ -570,3 +570,21 @@ def test_predict_multi_round_suppression(env):
             assert bit_equal(cand[b, :k].long(), want[b]["cand"]), (thr, nms, keep, agn, b, k, want[b]["cand"].numel())
             assert bit_equal(scores[b, :k], want[b]["scores"]) and bit_equal(boxes[b, :k], want[b]["boxes"])
             assert bit_equal(labels[b, :k], want[b]["labels"])
+
+
+def test_pack_heads_matches_reference_layout(env):
+    """ssdhot.pack_heads == the tail of mySSD.forward (permute(0,2,3,1).contiguous() x 12, cat x 2; SFS:249-269),
+    bit for bit (pure data movement), for the reference's 6 classes and a VOC-sized head, contiguous or not."""
+    s, dev = env["ssdhot"], env["dev"]
+    gen = torch.Generator().manual_seed(99)
+    levels = ((38, 4), (19, 6), (10, 6), (5, 6), (3, 4), (1, 4))
+    for B, C in ((3, 6), (2, 21), (1, 2)):
+        loc_heads = [torch.randn((B, a * 4, n, n), generator=gen).to(dev) for n, a in levels]
+        conf_heads = [torch.randn((B, a * C, n, n), generator=gen).to(dev) for n, a in levels]
+        conf_heads[1] = conf_heads[1].to(memory_format=torch.channels_last)          # a non-contiguous producer
+        want_loc, want_conf = O.pack_heads(loc_heads, conf_heads, C)
+        got_loc, got_conf = s.pack_heads(loc_heads, conf_heads)
+        assert got_loc.shape == (B, 8732, 4) and got_conf.shape == (B, 8732, C)
+        assert bit_equal(got_loc, want_loc) and bit_equal(got_conf, want_conf)
+    with pytest.raises(ValueError):
+        s.pack_heads(loc_heads[:5], conf_heads)

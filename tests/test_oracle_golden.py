@@ -118,3 +118,23 @@ def test_mined_negative_budget():
     assert O.mined_negative_budget(5000, 3732, 3.0) == 3732
     assert O.mined_negative_budget(3, 100, 0.2) == 0
     assert O.mined_negative_budget(8732, 0, 3.0) == 0
+
+
+def test_pack_heads_restatement_layout():
+    """oracle.pack_heads (SFS:249-269): element (b, level offset + (y*W + x)*A + a, j) of the packed tensor is element
+    (b, a*D + j, y, x) of that level's NCHW head output."""
+    gen = torch.Generator().manual_seed(5)
+    levels = ((38, 4), (19, 6), (10, 6), (5, 6), (3, 4), (1, 4))
+    C = 6
+    loc_heads = [torch.randn((2, a * 4, n, n), generator=gen) for n, a in levels]
+    conf_heads = [torch.randn((2, a * C, n, n), generator=gen) for n, a in levels]
+    loc_all, conf_all = O.pack_heads(loc_heads, conf_heads, C)
+    assert loc_all.shape == (2, 8732, 4) and conf_all.shape == (2, 8732, C)
+    off = 0
+    for (n, a), lh, ch in zip(levels, loc_heads, conf_heads):
+        for (y, x, k) in ((0, 0, 0), (n - 1, n // 2, a - 1), (n // 2, n - 1, a // 2)):
+            p = off + (y * n + x) * a + k
+            assert torch.equal(loc_all[:, p, :], lh[:, k * 4:(k + 1) * 4, y, x])
+            assert torch.equal(conf_all[:, p, :], ch[:, k * C:(k + 1) * C, y, x])
+        off += n * n * a
+    assert off == 8732
