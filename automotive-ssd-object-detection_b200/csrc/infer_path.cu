@@ -24,6 +24,7 @@
 #include <mutex>
 
 #include "boxmath.cuh"
+#include "heads.cuh"
 
 namespace ssdhot {
 
@@ -501,16 +502,16 @@ struct PredictParams {
     int* cand_count;                // [B]
     int64_t* out_labels; float* out_scores; float* out_boxes; int32_t* out_cand; int32_t* out_count;
     unsigned long long* timeline;   // debug (ssdhot_debug_timeline) or null
+    HeadView loc_h, conf_h;         // head sources (SRC_LEVEL_ROWS / SRC_LEVEL_PLANES) instead of loc_all / conf_all
 };
 
 // exp(x_i - max) of one row and their sum in eager torch-CUDA order (persistent warp softmax:
 // lanes = min(next_pow2(C), 32); lane l accumulates elements l, l+32, ... in order; then butterfly
 // adds over xor offsets lanes/2 .. 1).  C == 6 is the reference's class count.
-__device__ __forceinline__ float row_exps6(const float* __restrict__ row, float* e) {
-    const float2 a = ldg2(row), b = ldg2(row + 2), c = ldg2(row + 4);
-    const float mx = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y)), fmaxf(c.x, c.y));
-    e[0] = expf(fsub(a.x, mx)); e[1] = expf(fsub(a.y, mx)); e[2] = expf(fsub(b.x, mx));
-    e[3] = expf(fsub(b.y, mx)); e[4] = expf(fsub(c.x, mx)); e[5] = expf(fsub(c.y, mx));
+__device__ __forceinline__ float row_exps6(const float* x, float* e) {       // x: the six logits (registers)
+    const float mx = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(x[4], x[5]));
+#pragma unroll
+    for (int i = 0; i < 6; ++i) e[i] = expf(fsub(x[i], mx));
     return fadd(fadd(fadd(e[0], e[4]), e[2]), fadd(fadd(e[1], e[5]), e[3]));
 }
 
@@ -539,9 +540,11 @@ __device__ __forceinline__ float ex2_approx_ftz(float x) { float y; asm("ex2.app
 __device__ __forceinline__ float rcp_approx_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // exact softmax score of class k+1 of a 6-logit row, eager torch-CUDA order (SFS:388), as an order-preserving key
-__device__ __forceinline__ unsigned exact_score_key6(const float* __restrict__ row, int k) {
-    float e[6];
-    const float sum = row_exps6(row, e);
+template <int SRC>
+__device__ __forceinline__ unsigned exact_score_key6(const HeadReader<SRC, 6>& rd, int p, int k) {
+    float x[6], e[6];
+    rd.row(p, x);
+    const float sum = row_exps6(x, e);
     const float ek = k == 0 ? e[1] : k == 1 ? e[2] : k == 2 ? e[3] : k == 3 ? e[4] : e[5];
     return __float_as_uint(fdiv(ek, sum)) | 0x80000000u;
 }
@@ -553,40 +556,49 @@ __device__ __forceinline__ unsigned exact_score_key6(const float* __restrict__ r
 // KEY_MARGIN); the strict test `score > thresh` (SFS:402) is decided by the approximate score when it is
 // more than 1e-4 (relative) away from the threshold and by the exact eager-CUDA arithmetic otherwise, so
 // the candidate SET is exact; the keys are approximate and nms_image_kernel refines the ones it pulls.
-template <int CT>
+template <int CT, int SRC>
 __global__ void __launch_bounds__(ST, 4) score_kernel(const PredictParams prm) {
     pdl_trigger();                                 // nms_image_kernel's CTAs may be scheduled as SMs free up (they wait for this grid)
     const int b = blockIdx.x / SCS, part = blockIdx.x % SCS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ HeadTable htab;                     // per-level bases of this image (head sources only)
+    if (SRC != SRC_PACKED) {
+        head_table_fill<SRC, 6>(htab, prm.conf_h, b, threadIdx.x);
+        __syncthreads();
+    }
     const int seg = part * (ST / 32) + warp;
     const int P = prm.P, n_fg = prm.C - 1;
     const int rows = seg_rows(P);
     const int r0 = min(P, seg * rows), r1 = min(P, r0 + rows);
-    const float* conf_b = prm.conf_all + (long long)b * P * prm.C;
+    const float* conf_b = SRC == SRC_PACKED ? prm.conf_all + (long long)b * P * prm.C : nullptr;
     unsigned long long* list = prm.cand + ((long long)b * SEGS + seg) * rows * n_fg;
     const unsigned lt = (1u << lane) - 1u;
     int cnt = 0;                                            // warp-uniform
     if (CT == 6) {
         const float thr = prm.score_thresh, thr_hi = thr * 1.0001f, thr_lo = thr * 0.9999f;
-        const float4* src = reinterpret_cast<const float4*>(conf_b);
+        const HeadReader<SRC, 6> rd = {conf_b, &htab};
         const int q1 = r1 >> 1;                             // P is even on this path
-        // software pipeline: the three 16-byte loads of the next row pair are in flight while this one is scored
-        float4 nA = make_float4(0.f, 0.f, 0.f, 0.f), nB = nA, nC = nA;
+        // software pipeline: the loads of the next row pair (three 16-byte loads when rows are contiguous) are in
+        // flight while this one is scored
+        float nx[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) nx[j] = 0.f;
         {
             const int q = (r0 >> 1) + lane;
-            if (q < q1) { nA = __ldg(src + 3 * q); nB = __ldg(src + 3 * q + 1); nC = __ldg(src + 3 * q + 2); }
+            if (q < q1) rd.pair(q, nx);
         }
         for (int qb = r0 >> 1; qb < q1; qb += 32) {
             const int q = qb + lane;
             unsigned pass = 0u;                             // bit (h * 5 + k): row 2q+h, class k+1 is a candidate
             float sc[10];
-            const float4 A = nA, Bv = nB, Cv = nC;
+            float x[2][6];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) x[j / 6][j % 6] = nx[j];
             {
                 const int qn = q + 32;
-                if (qn < q1) { nA = __ldg(src + 3 * qn); nB = __ldg(src + 3 * qn + 1); nC = __ldg(src + 3 * qn + 2); }
+                if (qn < q1) rd.pair(qn, nx);
             }
             if (q < q1) {
-                const float x[2][6] = {{A.x, A.y, A.z, A.w, Bv.x, Bv.y}, {Bv.z, Bv.w, Cv.x, Cv.y, Cv.z, Cv.w}};
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const float mx = fmaxf(fmaxf(fmaxf(x[h][0], x[h][1]), fmaxf(x[h][2], x[h][3])), fmaxf(x[h][4], x[h][5]));
@@ -731,11 +743,12 @@ constexpr int IT = 512;        // threads of nms_image_kernel
 
 // ---- cold paths of nms_image_kernel, kept out of line so that the code every image runs stays compact -------
 // Replace every approximate key of the list by the exact one and rebuild the score histogram (every thread of the CTA).
-__device__ __noinline__ void nms_make_exact(const SegSource src, unsigned* hist16, const float* conf_b, bool use_hist) {
+template <int SRC>
+__device__ __noinline__ void nms_make_exact(const SegSource src, unsigned* hist16, const HeadReader<SRC, 6> conf_rd, bool use_hist) {
     src.for_each<IT>([&](int i, unsigned long long r) {
         if (SegSource::key(r) == 0u) return;
         const unsigned id = 0xffffffffu - (unsigned)(r & 0xffffffffull);
-        src.replace(i, ((unsigned long long)exact_score_key6(conf_b + 6ll * (id / 5u), (int)(id % 5u)) << 32) | (r & 0xffffffffull));
+        src.replace(i, ((unsigned long long)exact_score_key6(conf_rd, (int)(id / 5u), (int)(id % 5u)) << 32) | (r & 0xffffffffull));
     });
     for (int i = threadIdx.x; i < HBINS / 2; i += IT) hist16[i] = 0u;
     __syncthreads();
@@ -756,10 +769,11 @@ __device__ __noinline__ void nms_select_cut(const SegSource src, UnitShared& us,
 }
 #define SSDHOT_NSTAMP(k) do { if (prm.timeline && threadIdx.x == 0 && first) prm.timeline[(long long)blockIdx.x * 16 + (k)] = globaltimer_ns(); } while (0)
 
-template <int METRIC, bool AGN, bool APPROX>
+template <int METRIC, bool AGN, bool APPROX, int SRC>
 __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams prm) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ UnitShared us;
+    __shared__ HeadTable loc_tab, conf_tab;        // per-level bases of this image (head sources only)
     constexpr int KEY_MARGIN = 512;                // ulps: >= 3e-5 relative, 3x the worst error of an approximate score
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x;
@@ -777,19 +791,23 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
     SSDHOT_NSTAMP(0);
     const int n_cand = block_sum<int>(tid < SEGS ? src.counts[tid] : 0, us.iscratch);
     const float thr = prm.nms_thresh, thr_lo = fmul(thr, kFilterSlack);
-    const float* loc_b = prm.loc_all + 4ll * b * P;
-    const float* conf_b = prm.conf_all + (long long)b * P * prm.C;
+    if (SRC != SRC_PACKED) {                       // (published by the __syncthreads() below)
+        head_table_fill<SRC, 4>(loc_tab, prm.loc_h, b, tid);
+        head_table_fill<SRC, 6>(conf_tab, prm.conf_h, b, tid - 32);
+    }
+    const HeadReader<SRC, 4> loc_rd = {SRC == SRC_PACKED ? prm.loc_all + 4ll * b * P : nullptr, &loc_tab};
+    const HeadReader<SRC, 6> conf_rd = {SRC == SRC_PACKED ? prm.conf_all + (long long)b * P * prm.C : nullptr, &conf_tab};
     const bool want_atan = METRIC == SSDHOT_METRIC_CIOU;
     const long long o = (long long)b * max_keep;
     const unsigned lt = (1u << lane) - 1u;
-    auto exact_key = [&](unsigned id) -> unsigned { return exact_score_key6(conf_b + 6ll * (id / 5u), (int)(id % 5u)); };
+    auto exact_key = [&](unsigned id) -> unsigned { return exact_score_key6(conf_rd, (int)(id / 5u), (int)(id % 5u)); };
 
     bool use_hist = n_cand > CH && n_cand < 65536;          // 16-bit bin counters
     bool keys_exact = !APPROX;
     __syncthreads();
     if (use_hist) src.for_each<IT>([&](int, unsigned long long r) { hist_add(buf.hist16, SegSource::key(r)); });
     __syncthreads();
-    auto make_exact = [&]() { nms_make_exact(src, buf.hist16, conf_b, use_hist); keys_exact = true; };
+    auto make_exact = [&]() { nms_make_exact<SRC>(src, buf.hist16, conf_rd, use_hist); keys_exact = true; };
 
     SSDHOT_NSTAMP(1);
     int kept_n = 0, remaining = n_cand;
@@ -860,7 +878,9 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
         if (tid < K) {
             const unsigned id = 0xffffffffu - (unsigned)(buf.ckey[tid] & 0xffffffffull);
             const unsigned p = id / (unsigned)n_fg;
-            const float4 box = decode_box(ldg4(loc_b + 4ll * p), ldg4(prm.pri + 4ll * p), prm.vc, prm.vs);
+            float lv[4];
+            loc_rd.row((int)p, lv);
+            const float4 box = decode_box(make_float4(lv[0], lv[1], lv[2], lv[3]), ldg4(prm.pri + 4ll * p), prm.vc, prm.vs);
             const float4 px = to_pixel_xyxy(box, prm.img_w, prm.img_h);
             my_box = box_consts(px.x, px.y, px.z, px.w, want_atan);
             {   // which quarter-columns / quarter-rows of the image the (clamped) box reaches: boxes that share no cell
@@ -1137,12 +1157,12 @@ static int set_smem(K kern, size_t bytes) {
     return SSDHOT_OK;
 }
 
-template <int METRIC, bool AGN, bool APPROX>
+template <int METRIC, bool AGN, bool APPROX, int SRC = SRC_PACKED>
 static int launch_nms_image(const PredictParams& prm, size_t dyn, cudaStream_t stream) {
     int rc;
-    if ((rc = set_smem(nms_image_kernel<METRIC, AGN, APPROX>, dyn))) return rc;
+    if ((rc = set_smem(nms_image_kernel<METRIC, AGN, APPROX, SRC>, dyn))) return rc;
     // PDL: the CTAs may start (shared-memory carve-up, histogram clear) while score_kernel drains
-    cudaError_t e = launch_pdl(nms_image_kernel<METRIC, AGN, APPROX>, dim3(prm.B), dim3(IT), dyn, stream, prm);
+    cudaError_t e = launch_pdl(nms_image_kernel<METRIC, AGN, APPROX, SRC>, dim3(prm.B), dim3(IT), dyn, stream, prm);
     ++g_launches;
     if (e != cudaSuccess) return (int)e;
     return SSDHOT_OK;
@@ -1219,50 +1239,89 @@ extern "C" int ssdhot_predict(const float* priors_cxcywh, int P, const float* lo
                                  work, SSDHOT_STAGE_SCORES | SSDHOT_STAGE_NMS, stream);
 }
 
+// Shared back end of ssdhot_predict_stages (src = SRC_PACKED) and ssdhot_predict_heads (per-level sources).
+static int predict_launch(PredictParams& prm, int src, int class_agnostic, int metric, void* work, int stages, cudaStream_t s) {
+    const int B = prm.B, C = prm.C, P = prm.P;
+    if ((stages & ~(SSDHOT_STAGE_SCORES | SSDHOT_STAGE_NMS)) != 0 || stages == 0) return SSDHOT_ERR_VALUE;
+    if (!prm.pri || !prm.out_labels || !prm.out_scores || !prm.out_boxes || !prm.out_count || !work) return SSDHOT_ERR_NULL;
+    if (P <= 0 || B <= 0 || C < 2 || C > SSDHOT_MAX_CLASSES || prm.max_keep <= 0 || prm.max_keep > 65535) return SSDHOT_ERR_SHAPE;
+    if ((long long)P * (C - 1) > 0x7fffffffll) return SSDHOT_ERR_SHAPE;
+    // same validation as SSD_from_scratch.py:369-373
+    if (!(prm.score_thresh >= 0.0f && prm.score_thresh < 1.0f) || !(prm.nms_thresh > 0.0f && prm.nms_thresh < 1.0f)) return SSDHOT_ERR_VALUE;
+    if (metric != SSDHOT_METRIC_DIOU && metric != SSDHOT_METRIC_CIOU && metric != SSDHOT_METRIC_IOU) return SSDHOT_ERR_VALUE;
+    if (!al16(prm.pri) || !al16(prm.out_boxes) || !al16(work)) return SSDHOT_ERR_ALIGN;
+    const size_t dyn = img_smem_bytes(prm.max_keep, class_agnostic ? 1 : C - 1);
+    if (dyn > kMaxDynSmem) return SSDHOT_ERR_SHAPE;
+    prm.timeline = g_timeline;
+    unsigned char* w = reinterpret_cast<unsigned char*>(work);
+    prm.cand_count = reinterpret_cast<int*>(w);
+    prm.cand = reinterpret_cast<unsigned long long*>(w + pw_cand_off(B));
+    // C == 6 with 48-byte-aligned row pairs: approximate scores, refined by the NMS kernel; otherwise exact scores
+    const bool approx = src != SRC_PACKED || (C == 6 && (P % 2) == 0 && al16(prm.conf_all));
+    if (stages & SSDHOT_STAGE_SCORES) {
+        if (src == SRC_LEVEL_ROWS) score_kernel<6, SRC_LEVEL_ROWS><<<B * SCS, ST, 0, s>>>(prm);
+        else if (src == SRC_LEVEL_PLANES) score_kernel<6, SRC_LEVEL_PLANES><<<B * SCS, ST, 0, s>>>(prm);
+        else if (approx) score_kernel<6, SRC_PACKED><<<B * SCS, ST, 0, s>>>(prm);
+        else score_kernel<0, SRC_PACKED><<<B * SCS, ST, 0, s>>>(prm);
+        SSDHOT_CHECK_LAUNCH();
+    }
+    if (!(stages & SSDHOT_STAGE_NMS)) return SSDHOT_OK;
+    int rc;
+#define SSDHOT_DISPATCH_SRC(M, S)                                                                                      \
+    rc = class_agnostic ? launch_nms_image<M, true, true, S>(prm, dyn, s) : launch_nms_image<M, false, true, S>(prm, dyn, s)
+#define SSDHOT_DISPATCH(M)                                                                                            \
+    if (src == SRC_LEVEL_ROWS) { SSDHOT_DISPATCH_SRC(M, SRC_LEVEL_ROWS); }                                            \
+    else if (src == SRC_LEVEL_PLANES) { SSDHOT_DISPATCH_SRC(M, SRC_LEVEL_PLANES); }                                   \
+    else rc = approx ? (class_agnostic ? launch_nms_image<M, true, true>(prm, dyn, s) : launch_nms_image<M, false, true>(prm, dyn, s))  \
+                     : (class_agnostic ? launch_nms_image<M, true, false>(prm, dyn, s) : launch_nms_image<M, false, false>(prm, dyn, s))
+    if (metric == SSDHOT_METRIC_DIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_DIOU); }
+    else if (metric == SSDHOT_METRIC_CIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_CIOU); }
+    else { SSDHOT_DISPATCH(SSDHOT_METRIC_IOU); }
+#undef SSDHOT_DISPATCH
+#undef SSDHOT_DISPATCH_SRC
+    return rc;
+}
+
 extern "C" int ssdhot_predict_stages(const float* priors_cxcywh, int P, const float* loc_all, const float* conf_all,
                                      int B, int C, float score_thresh, float nms_thresh, int max_per_img,
                                      int class_agnostic, int metric, float var_center, float var_size,
                                      float img_w, float img_h,
                                      int64_t* out_labels, float* out_scores, float* out_boxes, int32_t* out_cand,
                                      int32_t* out_count, void* work, int stages, ssdhot_stream_t stream) {
-    if ((stages & ~(SSDHOT_STAGE_SCORES | SSDHOT_STAGE_NMS)) != 0 || stages == 0) return SSDHOT_ERR_VALUE;
-    if (!priors_cxcywh || !loc_all || !conf_all || !out_labels || !out_scores || !out_boxes || !out_count || !work)
-        return SSDHOT_ERR_NULL;
-    if (P <= 0 || B <= 0 || C < 2 || C > SSDHOT_MAX_CLASSES || max_per_img <= 0 || max_per_img > 65535) return SSDHOT_ERR_SHAPE;
-    if ((long long)P * (C - 1) > 0x7fffffffll) return SSDHOT_ERR_SHAPE;
-    // same validation as SSD_from_scratch.py:369-373
-    if (!(score_thresh >= 0.0f && score_thresh < 1.0f) || !(nms_thresh > 0.0f && nms_thresh < 1.0f)) return SSDHOT_ERR_VALUE;
-    if (metric != SSDHOT_METRIC_DIOU && metric != SSDHOT_METRIC_CIOU && metric != SSDHOT_METRIC_IOU) return SSDHOT_ERR_VALUE;
-    if (!al16(priors_cxcywh) || !al16(loc_all) || !al16(out_boxes) || !al16(work) ||
-        (reinterpret_cast<uintptr_t>(conf_all) & 7u)) return SSDHOT_ERR_ALIGN;
-    const size_t dyn = img_smem_bytes(max_per_img, class_agnostic ? 1 : C - 1);
-    if (dyn > kMaxDynSmem) return SSDHOT_ERR_SHAPE;
+    if (!loc_all || !conf_all) return SSDHOT_ERR_NULL;
+    if (!al16(loc_all) || (reinterpret_cast<uintptr_t>(conf_all) & 7u)) return SSDHOT_ERR_ALIGN;
     PredictParams prm = {};
     prm.pri = priors_cxcywh; prm.P = P; prm.loc_all = loc_all; prm.conf_all = conf_all; prm.B = B; prm.C = C;
     prm.score_thresh = score_thresh; prm.nms_thresh = nms_thresh; prm.max_keep = max_per_img;
     prm.vc = var_center; prm.vs = var_size; prm.img_w = img_w; prm.img_h = img_h;
     prm.out_labels = out_labels; prm.out_scores = out_scores; prm.out_boxes = out_boxes; prm.out_cand = out_cand;
     prm.out_count = out_count;
-    prm.timeline = g_timeline;
-    unsigned char* w = reinterpret_cast<unsigned char*>(work);
-    prm.cand_count = reinterpret_cast<int*>(w);
-    prm.cand = reinterpret_cast<unsigned long long*>(w + pw_cand_off(B));
-    cudaStream_t s = (cudaStream_t)stream;
-    // C == 6 with 48-byte-aligned row pairs: approximate scores, refined by the NMS kernel; otherwise exact scores
-    const bool approx = C == 6 && (P % 2) == 0 && al16(conf_all);
-    if (stages & SSDHOT_STAGE_SCORES) {
-        if (approx) score_kernel<6><<<B * SCS, ST, 0, s>>>(prm);
-        else score_kernel<0><<<B * SCS, ST, 0, s>>>(prm);
-        SSDHOT_CHECK_LAUNCH();
+    return predict_launch(prm, SRC_PACKED, class_agnostic, metric, work, stages, (cudaStream_t)stream);
+}
+
+// predict straight from the six head outputs of each branch (SSD300 layout, C == 6): see heads.cuh.
+extern "C" int ssdhot_predict_heads(const float* priors_cxcywh, const float* const* loc_heads_host,
+                                    const float* const* conf_heads_host, int head_layout, int B, int C,
+                                    float score_thresh, float nms_thresh, int max_per_img,
+                                    int class_agnostic, int metric, float var_center, float var_size,
+                                    float img_w, float img_h,
+                                    int64_t* out_labels, float* out_scores, float* out_boxes, int32_t* out_cand,
+                                    int32_t* out_count, void* work, int stages, ssdhot_stream_t stream) {
+    if (!loc_heads_host || !conf_heads_host) return SSDHOT_ERR_NULL;
+    if (head_layout != SSDHOT_HEADS_NHWC && head_layout != SSDHOT_HEADS_NCHW) return SSDHOT_ERR_VALUE;
+    if (C != 6) return SSDHOT_ERR_SHAPE;                       // other class counts: ssdhot_pack_heads + ssdhot_predict
+    PredictParams prm = {};
+    for (int l = 0; l < kHeadLevels; ++l) {
+        if (!loc_heads_host[l] || !conf_heads_host[l]) return SSDHOT_ERR_NULL;
+        if (!al16(loc_heads_host[l]) || !al16(conf_heads_host[l])) return SSDHOT_ERR_ALIGN;
+        prm.loc_h.base[l] = loc_heads_host[l];
+        prm.conf_h.base[l] = conf_heads_host[l];
     }
-    if (!(stages & SSDHOT_STAGE_NMS)) return SSDHOT_OK;
-    int rc;
-#define SSDHOT_DISPATCH(M)                                                                                            \
-    rc = approx ? (class_agnostic ? launch_nms_image<M, true, true>(prm, dyn, s) : launch_nms_image<M, false, true>(prm, dyn, s))  \
-                : (class_agnostic ? launch_nms_image<M, true, false>(prm, dyn, s) : launch_nms_image<M, false, false>(prm, dyn, s))
-    if (metric == SSDHOT_METRIC_DIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_DIOU); }
-    else if (metric == SSDHOT_METRIC_CIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_CIOU); }
-    else { SSDHOT_DISPATCH(SSDHOT_METRIC_IOU); }
-#undef SSDHOT_DISPATCH
-    return rc;
+    prm.pri = priors_cxcywh; prm.P = 8732; prm.B = B; prm.C = C;
+    prm.score_thresh = score_thresh; prm.nms_thresh = nms_thresh; prm.max_keep = max_per_img;
+    prm.vc = var_center; prm.vs = var_size; prm.img_w = img_w; prm.img_h = img_h;
+    prm.out_labels = out_labels; prm.out_scores = out_scores; prm.out_boxes = out_boxes; prm.out_cand = out_cand;
+    prm.out_count = out_count;
+    return predict_launch(prm, head_layout == SSDHOT_HEADS_NHWC ? SRC_LEVEL_ROWS : SRC_LEVEL_PLANES, class_agnostic, metric, work,
+                          stages, (cudaStream_t)stream);
 }

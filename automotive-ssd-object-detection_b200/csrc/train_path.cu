@@ -24,6 +24,7 @@
 //    Positives, their matched boxes and the forced champions are therefore bit-identical to the
 //    exact sweep while ~98 % of the pairs cost 13 instructions instead of ~75.
 #include "boxmath.cuh"
+#include "heads.cuh"
 
 namespace ssdhot {
 
@@ -56,6 +57,7 @@ struct TrainParams {
     double* img_part;      // [B][2] per-image (smooth-L1, CE) sums
     int32_t* flags;
     unsigned long long* timeline;   // debug: [B][16] %globaltimer stamps of the fused kernel's phases (or null)
+    HeadView loc_h, conf_h;         // head sources (SRC_LEVEL_ROWS / SRC_LEVEL_PLANES) instead of loc_all / conf_all
 };
 
 // SSD300 pyramid (SSD_from_scratch.py:289-290): used only to pick seed priors, never for results
@@ -687,6 +689,20 @@ __device__ __forceinline__ float exact_ce6(const float* __restrict__ row, int cl
     return -fsub(fsub(__ldg(row + cls), mx), lg);
 }
 
+// the same from a head source (heads.cuh): row p of the image
+template <int SRC>
+__device__ __forceinline__ float exact_ce6(const HeadReader<SRC, 6>& rd, int p, int cls) {
+    if (SRC == SRC_PACKED) return exact_ce6(rd.packed + 6ll * p, cls);
+    float x[6];
+    rd.row(p, x);
+    const float mx = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(x[4], x[5]));
+    const float e0 = expf(fsub(x[0], mx)), e1 = expf(fsub(x[1], mx)), e2 = expf(fsub(x[2], mx));
+    const float e3 = expf(fsub(x[3], mx)), e4 = expf(fsub(x[4], mx)), e5 = expf(fsub(x[5], mx));
+    const float lg = logf(fadd(fadd(fadd(e0, e4), e2), fadd(fadd(e1, e5), e3)));    // 8-lane butterfly order (row_lse)
+    const float xc = cls == 0 ? x[0] : cls == 1 ? x[1] : cls == 2 ? x[2] : cls == 3 ? x[3] : cls == 4 ? x[4] : x[5];
+    return -fsub(fsub(xc, mx), lg);
+}
+
 // From the top bin downwards, find the bin in which the running count reaches k (1 <= k <= total).
 // count(bin) reads a bin; every thread of the CTA must call it; two barriers inside.
 template <int NT, int NBINS, typename CountFn>
@@ -1044,10 +1060,11 @@ __device__ __forceinline__ void match_phase(const TrainParams& prm, FusedStatic&
     role_sync<MT>();
 }
 
-template <bool LOSS>
+template <bool LOSS, int SRC>
 __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams prm) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ FusedStatic fs;
+    __shared__ HeadTable loc_tab, conf_tab;        // per-level bases of this image (head sources only)
     pdl_trigger();                                 // finalize_sums_kernel may be scheduled early (it waits for this grid)
     SSDHOT_STAMP(0);
     constexpr int MT = LOSS ? MT_LOSS : FT;                  // threads that run the matching
@@ -1080,6 +1097,10 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     }
 
     // ---- 0. clear ------------------------------------------------------------------------------
+    if (SRC != SRC_PACKED && LOSS) {
+        head_table_fill<SRC, 4>(loc_tab, prm.loc_h, b, tid - 64);
+        head_table_fill<SRC, 6>(conf_tab, prm.conf_h, b, tid - 96);
+    }
     if (tid == 0) { fs.first_nan = INT_MAX; fs.n_dense = 0; fs.n_band = 0; fs.n_pair = 0; fs.pair_overflow = 0; fs.n_pos_img = 0; fs.n_sure = 0; }
     if (tid >= 32 && tid < 32 + G) {
         fs.gt_px[tid - 32] = ldg4(prm.gt_boxes + 4ll * (g_begin + tid - 32));
@@ -1099,7 +1120,8 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     }
     __syncthreads();
     const float thresh = prm.thresh;
-    const float* conf_b = prm.conf_all + (long long)b * P * 6;
+    const HeadReader<SRC, 4> loc_rd = {SRC == SRC_PACKED && LOSS ? prm.loc_all + 4ll * b * P : nullptr, &loc_tab};
+    const HeadReader<SRC, 6> conf_rd = {SRC == SRC_PACKED && LOSS ? prm.conf_all + (long long)b * P * 6 : nullptr, &conf_tab};
 
     // ---- 1, 2 (warps 0..7): matching  ||  3 (the other warps): approximate CE of every prior ----------------
     SSDHOT_STAMP(1);
@@ -1107,20 +1129,21 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
         match_phase<MT>(prm, fs, v, G, g_begin);
         SSDHOT_STAMP(3);
     } else if (LOSS) {
-        const float4* src = reinterpret_cast<const float4*>(conf_b);
         const int n_pairs = P / 2;
 #pragma unroll 2
         for (int q = tid - MT; q < n_pairs; q += FT - MT) {
-            const float4 A = __ldg(src + 3 * q), Bv = __ldg(src + 3 * q + 1), Cv = __ldg(src + 3 * q + 2);
-            const unsigned k0 = __float_as_uint(approx_ce6(A.x, A.y, A.z, A.w, Bv.x, Bv.y));
-            const unsigned k1 = __float_as_uint(approx_ce6(Bv.z, Bv.w, Cv.x, Cv.y, Cv.z, Cv.w));
+            float x[12];
+            conf_rd.pair(q, x);
+            const unsigned k0 = __float_as_uint(approx_ce6(x[0], x[1], x[2], x[3], x[4], x[5]));
+            const unsigned k1 = __float_as_uint(approx_ce6(x[6], x[7], x[8], x[9], x[10], x[11]));
             v.lo[4 * q] = k0;
             v.lo[4 * q + 2] = k1;
             ce_hist_add(hist16, k0);
             ce_hist_add(hist16, k1);
         }
         if ((P & 1) && tid == MT) {                          // odd P: the last row (never SSD300)
-            const float* r = conf_b + 6ll * (P - 1);
+            float r[6];
+            conf_rd.row(P - 1, r);
             const unsigned k = __float_as_uint(approx_ce6(r[0], r[1], r[2], r[3], r[4], r[5]));
             v.lo[2 * (P - 1)] = k;
             ce_hist_add(hist16, k);
@@ -1227,12 +1250,13 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     // a positive prior: exact CE of its class, smooth-L1 of its offsets (TR:108, :577-580)
     auto positive_terms = [&](int p, int g) {
         const long long row = (long long)b * P + p;
-        acc_ce += (double)exact_ce6(conf_b + 6ll * p, fs.label[g] + 1);
+        acc_ce += (double)exact_ce6(conf_rd, p, fs.label[g] + 1);
         const float4 ga = fs.gt_a[g], gb = fs.gt_b[g];
         const float4 gbox = make_float4(gb.y, gb.z, fsub(ga.z, ga.x), fsub(ga.w, ga.y));
         const float4 t = encode_offsets(gbox, ldg4(prm.pri + 4ll * p), prm.inv_vc, prm.inv_vs);
-        const float4 l = ldg4(prm.loc_all + 4ll * row);
-        const float d[4] = {fsub(l.x, t.x), fsub(l.y, t.y), fsub(l.z, t.z), fsub(l.w, t.w)};
+        float l[4];
+        loc_rd.row(p, l);
+        const float d[4] = {fsub(l[0], t.x), fsub(l[1], t.y), fsub(l[2], t.z), fsub(l[3], t.w)};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float z = fabsf(d[j]);
@@ -1240,7 +1264,7 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
         }
     };
     auto mined_term = [&](int p) {
-        acc_ce += (double)exact_ce6(conf_b + 6ll * p, 0);
+        acc_ce += (double)exact_ce6(conf_rd, p, 0);
         if (prm.sel_cls) prm.sel_cls[(long long)b * P + p] = 0;
     };
     const unsigned lt = (1u << lane) - 1u;
@@ -1330,7 +1354,7 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                 else mined_term(p);
             } else {
                 const int eb = e - tot_pos - tot_sel;
-                band_v[eb] = __float_as_uint(exact_ce6(conf_b + 6ll * (int)band_p[eb], 0)) & 0x7fffffffu;
+                band_v[eb] = __float_as_uint(exact_ce6(conf_rd, (int)band_p[eb], 0)) & 0x7fffffffu;
             }
         }
         if (fast) {
@@ -1363,11 +1387,11 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
         for (int p = tid; p < P; p += FT) {
             const unsigned lo = v.lo[2 * p];
             if (!(lo >> 31)) {
-                const unsigned key = __float_as_uint(exact_ce6(conf_b + 6ll * p, 0)) & 0x7fffffffu;
+                const unsigned key = __float_as_uint(exact_ce6(conf_rd, p, 0)) & 0x7fffffffu;
                 v.lo[2 * p] = key;
                 atomicAdd(&fs.ls.hist[key >> 24], 1u);
             } else {
-                acc_ce += (double)exact_ce6(conf_b + 6ll * p, fs.label[matched_box(lo)] + 1);
+                acc_ce += (double)exact_ce6(conf_rd, p, fs.label[matched_box(lo)] + 1);
             }
         }
         __syncthreads();
@@ -1563,12 +1587,12 @@ static int launch_loss(const TrainParams& prm, cudaStream_t stream) {
     return SSDHOT_OK;
 }
 
-template <bool LOSS>
+template <bool LOSS, int SRC = SRC_PACKED>
 static int launch_train_image(const TrainParams& prm_in, cudaStream_t stream) {
     TrainParams prm = prm_in;
     prm.timeline = g_timeline;
     const size_t dyn = fused_smem_bytes(prm.P);
-    auto kern = train_image_kernel<LOSS>;
+    auto kern = train_image_kernel<LOSS, SRC>;
     static bool configured = false;    // sticky opt-in, raised outside graph capture by the first (warm-up) call
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -1741,6 +1765,49 @@ extern "C" int ssdhot_multibox_loss_fwd(const float* priors_cxcywh, const float*
     // 2) loss: one CTA per image
     prm.n_pos = np; prm.sel_cls = sel_cls; prm.matched16 = matched_gt;
     rc = launch_loss<false>(prm, (cudaStream_t)stream);
+    if (rc) return rc;
+    return finalize(prm, np, sums, (cudaStream_t)stream);
+}
+
+// match + mined loss straight from the six head outputs of each branch (heads.cuh): the SSD300 fast path only.
+extern "C" int ssdhot_multibox_loss_heads_fwd(const float* priors_cxcywh, const float* priors_xyxy, const float* prior_aux,
+                                              int prior_layout, const float* gt_boxes, const int64_t* gt_labels,
+                                              const int32_t* gt_offsets, int B, int max_gt, float norm_w, float norm_h,
+                                              const float* const* loc_heads_host, const float* const* conf_heads_host,
+                                              int head_layout, int C,
+                                              float iou_thresh, float var_center, float var_size, double neg_pos_ratio,
+                                              double* sums, void* work, int8_t* sel_cls, int16_t* matched_gt, int32_t* n_pos,
+                                              int32_t* dev_flags, ssdhot_stream_t stream) {
+    const int P = 8732;
+    int rc = check_gt_args(priors_cxcywh, priors_xyxy, prior_aux, P, gt_boxes, gt_labels, gt_offsets, B, max_gt,
+                           norm_w, norm_h, var_center, var_size);
+    if (rc) return rc;
+    if (!loc_heads_host || !conf_heads_host || !sums || !work) return SSDHOT_ERR_NULL;
+    if (head_layout != SSDHOT_HEADS_NHWC && head_layout != SSDHOT_HEADS_NCHW) return SSDHOT_ERR_VALUE;
+    if (!(neg_pos_ratio >= 0.0)) return SSDHOT_ERR_VALUE;
+    // other class counts, priors or box counts: ssdhot_pack_heads + ssdhot_multibox_loss_fwd
+    if (C != 6 || !fast_path_ok(prior_layout, P, max_gt, iou_thresh)) return SSDHOT_ERR_SHAPE;
+    if (!aligned16(work)) return SSDHOT_ERR_ALIGN;
+    unsigned char* w = reinterpret_cast<unsigned char*>(work);
+    TrainParams prm = {};
+    for (int l = 0; l < kHeadLevels; ++l) {
+        if (!loc_heads_host[l] || !conf_heads_host[l]) return SSDHOT_ERR_NULL;
+        if (!aligned16(loc_heads_host[l]) || !aligned16(conf_heads_host[l])) return SSDHOT_ERR_ALIGN;
+        prm.loc_h.base[l] = loc_heads_host[l];
+        prm.conf_h.base[l] = conf_heads_host[l];
+    }
+    prm.pri = priors_cxcywh; prm.pri_xyxy = priors_xyxy; prm.pri_aux = prior_aux; prm.P = P;
+    prm.gt_boxes = gt_boxes; prm.gt_labels = gt_labels; prm.gt_offsets = gt_offsets;
+    prm.B = B; prm.max_gt = max_gt; prm.norm_w = norm_w; prm.norm_h = norm_h;
+    prm.thresh = iou_thresh; prm.inv_vc = 1.0f / var_center; prm.inv_vs = 1.0f / var_size;
+    prm.C = C; prm.ratio = neg_pos_ratio;
+    prm.img_part = reinterpret_cast<double*>(w);
+    prm.gt_rec = reinterpret_cast<float4*>(w + ws_rec_off(B));
+    prm.flags = dev_flags;
+    int32_t* np = n_pos ? n_pos : reinterpret_cast<int32_t*>(w + ws_npos_off(B));
+    prm.n_pos = np; prm.sel_cls = sel_cls; prm.matched16 = matched_gt; prm.code = nullptr;
+    rc = head_layout == SSDHOT_HEADS_NHWC ? launch_train_image<true, SRC_LEVEL_ROWS>(prm, (cudaStream_t)stream)
+                                          : launch_train_image<true, SRC_LEVEL_PLANES>(prm, (cudaStream_t)stream);
     if (rc) return rc;
     return finalize(prm, np, sums, (cudaStream_t)stream);
 }

@@ -43,6 +43,10 @@ PROTOTYPES = {
                              vp, vp, vp, vp, vp, vp, vp]),
     "ssdhot_predict_stages": (i32, [vp, i32, vp, vp, i32, i32, f32, f32, i32, i32, i32, f32, f32, f32, f32,
                                     vp, vp, vp, vp, vp, vp, i32, vp]),
+    "ssdhot_predict_heads": (i32, [vp, vp, vp, i32, i32, i32, f32, f32, i32, i32, i32, f32, f32, f32, f32,
+                                   vp, vp, vp, vp, vp, vp, i32, vp]),
+    "ssdhot_multibox_loss_heads_fwd": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, vp, vp, i32, i32,
+                                             f32, f32, f32, f64, vp, vp, vp, vp, vp, vp, vp]),
 }
 
 

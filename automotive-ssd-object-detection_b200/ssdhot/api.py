@@ -410,6 +410,126 @@ def pack_heads(loc_heads: Sequence[torch.Tensor], conf_heads: Sequence[torch.Ten
 
 
 # ------------------------------------------------------------------------------------------------
+# the hot path straight from the head outputs (no permute / cat / pack pass at all)
+# ------------------------------------------------------------------------------------------------
+HEADS_NCHW, HEADS_NHWC = 0, 1
+
+
+def _head_args(loc_heads: Sequence[torch.Tensor], conf_heads: Sequence[torch.Tensor]):
+    """Validate the 2 x 6 head outputs ([B, A*D, side, side] each, SFS:249-262) and return
+    (device, B, C, layout, keep-alive tensors, ctypes pointer arrays).  Heads that are channels_last in memory are read as
+    NHWC rows, everything else as NCHW planes; a head that is neither (or not 16-byte aligned) is made contiguous."""
+    import ctypes
+    if len(loc_heads) != len(_LEVELS) or len(conf_heads) != len(_LEVELS):
+        raise ValueError(f"expected {len(_LEVELS)} loc and conf head outputs, got {len(loc_heads)} and {len(conf_heads)}")
+    dev = _need_cuda(*loc_heads, *conf_heads)
+    B = int(conf_heads[0].shape[0])
+    C = int(conf_heads[0].shape[1]) // _LEVELS[0][1]
+    for heads, D, what in ((loc_heads, 4, "loc"), (conf_heads, C, "conf")):
+        for h, (side, shapes) in zip(heads, _LEVELS):
+            if tuple(h.shape) != (B, shapes * D, side, side):
+                raise ValueError(f"{what} head of the {side}x{side} level has shape {tuple(h.shape)}, expected {(B, shapes * D, side, side)}")
+    every = list(loc_heads) + list(conf_heads)
+    nhwc = all(h.is_contiguous(memory_format=torch.channels_last) for h in every) and not all(h.is_contiguous() for h in every)
+    fmt = torch.channels_last if nhwc else torch.contiguous_format
+    keep = []
+    for h in every:
+        t = h.detach().to(torch.float32).contiguous(memory_format=fmt)
+        if t.data_ptr() % 16:
+            t = t.clone(memory_format=fmt)
+        keep.append(t)
+    loc_ptrs = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in keep[:6]])
+    conf_ptrs = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in keep[6:]])
+    return dev, B, C, (HEADS_NHWC if nhwc else HEADS_NCHW), keep, ctypes.cast(loc_ptrs, ctypes.c_void_p), ctypes.cast(conf_ptrs, ctypes.c_void_p), (loc_ptrs, conf_ptrs)
+
+
+def predict_heads_padded(model, loc_heads: Sequence[torch.Tensor], conf_heads: Sequence[torch.Tensor], score_thresh: float = 0.2,
+                         nms_thresh: float = 0.5, max_per_img: int = 100, class_agnostic: bool = False,
+                         metric: str = "diou", want_cand: bool = False):
+    """predict_padded from the six head outputs of each branch instead of (loc_all, conf_all): the tail of mySSD.forward
+    (12 permute().contiguous() + 2 cat, SFS:249-269) never runs -- score_kernel / nms_image_kernel address the heads
+    directly.  Same results as predict_padded(model, *pack_heads(loc_heads, conf_heads), ...), bit for bit.
+    Class counts other than 6 are packed first (ssdhot_pack_heads) and take the packed entry point."""
+    if not (0.0 <= score_thresh < 1.0):
+        raise ValueError(f"Score threshold should be greater than 0 and less than 1, recieved {score_thresh}.")
+    if not (0.0 < nms_thresh < 1.0):
+        raise ValueError(f"NMS threshold should be greater than 0 and less than 1, recieved {nms_thresh}.")
+    priors = PriorSet.of(model)
+    dev, B, C, layout, keep, loc_p, conf_p, _alive = _head_args(loc_heads, conf_heads)
+    assert priors.P == 8732
+    assert C >= 2
+    if C != 6:
+        return predict_padded(model, *pack_heads(loc_heads, conf_heads), score_thresh, nms_thresh, max_per_img, class_agnostic,
+                              metric, want_cand)
+    labels = torch.empty((B, max_per_img), dtype=torch.int64, device=dev)
+    scores = torch.empty((B, max_per_img), dtype=torch.float32, device=dev)
+    boxes = torch.empty((B, max_per_img, 4), dtype=torch.float32, device=dev)
+    cand = torch.empty((B, max_per_img), dtype=torch.int32, device=dev) if want_cand else None
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    work = _workspace("predict", dev, _lib.lib().ssdhot_predict_workspace_bytes(B, 8732, C))
+    with torch.cuda.device(dev):
+        rc = _lib.lib().ssdhot_predict_heads(priors.priors.data_ptr(), loc_p, conf_p, layout, B, C,
+                                             float(score_thresh), float(nms_thresh), int(max_per_img), 1 if class_agnostic else 0,
+                                             METRICS[metric], priors.variances[0], priors.variances[1],
+                                             float(priors.img_w), float(priors.img_h),
+                                             labels.data_ptr(), scores.data_ptr(), boxes.data_ptr(), _ptr(cand),
+                                             count.data_ptr(), work.data_ptr(), 3, _stream(dev))
+    _lib.check(rc, "ssdhot_predict_heads")
+    for t in keep:
+        t.record_stream(torch.cuda.current_stream(dev))
+    if want_cand:
+        return labels, scores, boxes, count, cand
+    return labels, scores, boxes, count
+
+
+@torch.no_grad()
+def predict_heads(model, loc_heads: Sequence[torch.Tensor], conf_heads: Sequence[torch.Tensor], score_thresh: float = 0.2,
+                  nms_thresh: float = 0.5, max_per_img: int = 100, class_agnostic: bool = False,
+                  metric: str = "diou") -> List[Dict[str, torch.Tensor]]:
+    """mySSD.predict (SFS:338-476) fed with the head outputs: List[Dict] exactly as predict returns."""
+    labels, scores, boxes, count = predict_heads_padded(model, loc_heads, conf_heads, score_thresh, nms_thresh, max_per_img,
+                                                        class_agnostic, metric)
+    ks = count.tolist()
+    return [{"labels": l[:k], "scores": s[:k], "boxes": b[:k]}
+            for l, s, b, k in zip(labels.unbind(0), scores.unbind(0), boxes.unbind(0), ks)]
+
+
+@torch.no_grad()
+def multibox_loss_heads(model, loc_heads: Sequence[torch.Tensor], conf_heads: Sequence[torch.Tensor], targets,
+                        iou_thresh: float = 0.5, neg_pos_ratio: float = 3.0, H: int = 300, W: int = 300, group=None,
+                        return_sums: bool = False):
+    """multibox_loss (forward) from the six head outputs of each branch: the evaluation-step losses of SSD_test_step
+    (SSD_trainer.py:226-231) without ever forming loc_all / conf_all.  Same sums as multibox_loss on the packed tensors,
+    bit for bit.  Inputs the head kernel does not cover (C != 6, more than 64 boxes per image, non-SSD300 priors) are packed
+    first and take the packed entry point."""
+    if not (0.0 < iou_thresh < 1.0):
+        raise ValueError(f"Score threshold should be greater than 0 and less than 1, recieved {iou_thresh}.")
+    priors = PriorSet.of(model)
+    packed = targets if isinstance(targets, PackedTargets) else pack_targets(targets, priors.device)
+    dev, B, C, layout, keep, loc_p, conf_p, _alive = _head_args(loc_heads, conf_heads)
+    if C != 6 or priors.layout != 1 or packed.max_gt > 64:           # (1 = SSDHOT_LAYOUT_SSD300)
+        return multibox_loss(model, *pack_heads(loc_heads, conf_heads), targets, iou_thresh, neg_pos_ratio, H, W, group, return_sums)
+    sums = torch.empty((3,), dtype=torch.float64, device=dev)
+    work = _workspace("loss", dev, _lib.lib().ssdhot_loss_workspace_bytes(B, 8732, packed.max_gt))
+    with torch.cuda.device(dev):
+        rc = _lib.lib().ssdhot_multibox_loss_heads_fwd(
+            priors.priors.data_ptr(), priors.priors_xyxy.data_ptr(), priors.aux.data_ptr(), priors.layout,
+            packed.boxes.data_ptr(), packed.labels.data_ptr(), packed.offsets.data_ptr(), B, packed.max_gt,
+            float(W), float(H), loc_p, conf_p, layout, C,
+            float(iou_thresh), priors.variances[0], priors.variances[1], float(neg_pos_ratio),
+            sums.data_ptr(), work.data_ptr(), None, None, None, None, _stream(dev))
+    _lib.check(rc, "ssdhot_multibox_loss_heads_fwd")
+    for t in keep:
+        t.record_stream(torch.cuda.current_stream(dev))
+    if group is not None:
+        _dist.combine_sums(sums, None if group is True else group)
+    losses = (sums[:2] / sums[2].clamp_min(1.0)).to(torch.float32)
+    if return_sums:
+        return losses[0], losses[1], sums
+    return losses[0], losses[1]
+
+
+# ------------------------------------------------------------------------------------------------
 # patching the reference in place
 # ------------------------------------------------------------------------------------------------
 def patch(model=None, trainer_module=None):

@@ -17,6 +17,15 @@ from .api import METRICS, PackedTargets
 from .priors import PriorSet
 
 
+class HeadSet:
+    """The 2 x 6 head outputs of a batch (SFS:249-262) with their pointer arrays prepared once, for the head-direct
+    launches of HotPathStep (no permute / cat / pack pass).  layout: api.HEADS_NCHW or api.HEADS_NHWC."""
+
+    def __init__(self, loc_heads, conf_heads):
+        from .api import _head_args
+        (self.device, self.B, self.C, self.layout, self.tensors, self.loc_ptr, self.conf_ptr, self._alive) = _head_args(loc_heads, conf_heads)
+
+
 class HotPathStep:
     def __init__(self, priors: PriorSet, batch: int, n_classes: int, iou_thresh: float = 0.5,
                  neg_pos_ratio: float = 3.0, score_thresh: float = 0.01, nms_thresh: float = 0.45,
@@ -58,6 +67,30 @@ class HotPathStep:
             self.iou_thresh, ps.variances[0], ps.variances[1], self.ratio,
             self.sums.data_ptr(), self.loss_work.data_ptr(), None, None, self.n_pos.data_ptr(), None, stream)
         _lib.check(rc, "ssdhot_multibox_loss_fwd")
+
+    def launch_loss_heads(self, heads: HeadSet, gt: PackedTargets, stream: int) -> None:
+        """launch_loss reading the head outputs directly (train_image_kernel with a per-level source)."""
+        ps = self.ps
+        if gt.max_gt > self.max_gt:
+            raise _lib.SsdhotError(f"HotPathStep was planned for at most {self.max_gt} boxes per image, got {gt.max_gt}")
+        rc = _lib.lib().ssdhot_multibox_loss_heads_fwd(
+            ps.priors.data_ptr(), ps.priors_xyxy.data_ptr(), ps.aux.data_ptr(), ps.layout,
+            gt.boxes.data_ptr(), gt.labels.data_ptr(), gt.offsets.data_ptr(), self.B, gt.max_gt,
+            self.norm_wh[0], self.norm_wh[1], heads.loc_ptr, heads.conf_ptr, heads.layout, self.C,
+            self.iou_thresh, ps.variances[0], ps.variances[1], self.ratio,
+            self.sums.data_ptr(), self.loss_work.data_ptr(), None, None, self.n_pos.data_ptr(), None, stream)
+        _lib.check(rc, "ssdhot_multibox_loss_heads_fwd")
+
+    def launch_predict_heads(self, heads: HeadSet, stream: int, stages: int = 3) -> None:
+        """launch_predict reading the head outputs directly (score_kernel / nms_image_kernel with a per-level source)."""
+        ps = self.ps
+        rc = _lib.lib().ssdhot_predict_heads(
+            ps.priors.data_ptr(), heads.loc_ptr, heads.conf_ptr, heads.layout, self.B, self.C,
+            self.score_thresh, self.nms_thresh, self.max_per_img, 1 if self.agnostic else 0, self.metric,
+            ps.variances[0], ps.variances[1], float(ps.img_w), float(ps.img_h),
+            self.labels.data_ptr(), self.scores.data_ptr(), self.boxes.data_ptr(), None,
+            self.count.data_ptr(), self.pred_work.data_ptr(), int(stages), stream)
+        _lib.check(rc, "ssdhot_predict_heads")
 
     def launch_predict(self, loc: torch.Tensor, conf: torch.Tensor, stream: int, stages: int = 3) -> None:
         """stages: 1 = score_kernel only (fills the candidate lists), 2 = nms_image_kernel only, 3 = both."""

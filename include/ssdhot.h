@@ -210,6 +210,38 @@ SSDHOT_API int ssdhot_predict_stages(const float* priors_cxcywh, int P, const fl
                           int64_t* out_labels, float* out_scores, float* out_boxes, int32_t* out_cand,
                           int32_t* out_count, void* work, int stages, ssdhot_stream_t stream);
 
+/* The hot path straight from the head outputs (SSD_from_scratch.py:249-269): instead of the packed
+ * loc_all / conf_all, the six per-level tensors of each branch (levels 38/19/10/5/3/1 with 4/6/6/6/4/4 shapes; HOST
+ * arrays of six DEVICE pointers, each 16-byte aligned).  head_layout:
+ *   SSDHOT_HEADS_NCHW  [B, A_l*D, H_l, W_l] contiguous, exactly what the conv heads return (SFS:249-262);
+ *   SSDHOT_HEADS_NHWC  [B, H_l, W_l, A_l*D] contiguous = permute(0,2,3,1) of a channels_last head output.
+ * Neither the 12 permute().contiguous() nor the 2 cat of mySSD.forward run: the streaming kernels address row p of
+ * level l directly.  SSD300 layout (P = 8732) and C == 6 only (SSDHOT_ERR_SHAPE otherwise: use ssdhot_pack_heads and the
+ * packed entry points).  Results are bit-identical to the packed entry points on the packed tensors.  `work` as for
+ * ssdhot_predict (ssdhot_predict_workspace_bytes(B, 8732, C)); all other arguments as ssdhot_predict_stages. */
+#define SSDHOT_HEADS_NCHW 0
+#define SSDHOT_HEADS_NHWC 1
+SSDHOT_API int ssdhot_predict_heads(const float* priors_cxcywh, const float* const* loc_heads_host,
+                         const float* const* conf_heads_host, int head_layout, int B, int C,
+                         float score_thresh, float nms_thresh, int max_per_img,
+                         int class_agnostic, int metric, float var_center, float var_size,
+                         float img_w, float img_h,
+                         int64_t* out_labels, float* out_scores, float* out_boxes, int32_t* out_cand,
+                         int32_t* out_count, void* work, int stages, ssdhot_stream_t stream);
+
+/* ssdhot_multibox_loss_fwd from the head outputs (see ssdhot_predict_heads for the two layouts).  SSD300 fast path only:
+ * prior_layout == SSDHOT_LAYOUT_SSD300, C == 6, max_gt <= 64, iou_thresh > 0 -- SSDHOT_ERR_SHAPE otherwise (pack the heads
+ * and call ssdhot_multibox_loss_fwd).  sums / sel_cls / matched_gt / n_pos are bit-identical to ssdhot_multibox_loss_fwd on
+ * the packed tensors; `work` as there (ssdhot_loss_workspace_bytes(B, 8732, max_gt)). */
+SSDHOT_API int ssdhot_multibox_loss_heads_fwd(const float* priors_cxcywh, const float* priors_xyxy, const float* prior_aux,
+                         int prior_layout, const float* gt_boxes, const int64_t* gt_labels,
+                         const int32_t* gt_offsets, int B, int max_gt, float norm_w, float norm_h,
+                         const float* const* loc_heads_host, const float* const* conf_heads_host,
+                         int head_layout, int C,
+                         float iou_thresh, float var_center, float var_size, double neg_pos_ratio,
+                         double* sums, void* work, int8_t* sel_cls, int16_t* matched_gt, int32_t* n_pos,
+                         int32_t* dev_flags, ssdhot_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

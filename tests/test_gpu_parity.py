@@ -588,3 +588,92 @@ def test_pack_heads_matches_reference_layout(env):
         assert bit_equal(got_loc, want_loc) and bit_equal(got_conf, want_conf)
     with pytest.raises(ValueError):
         s.pack_heads(loc_heads[:5], conf_heads)
+
+
+# ------------------------------------------------------------------------------------------------
+# head-direct entry points: the kernels read the six head outputs of each branch
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("name", PREDICT)
+def test_predict_from_heads(env, name, channels_last):
+    """predict_heads(heads) == predict(pack(heads)) == the reference's detections: keep lists, labels, scores and boxes
+    bit for bit against the device-matched oracle, for NCHW heads (as the conv heads return them) and channels_last ones."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    g = U.load(name)
+    loc_all, conf = U.predict_inputs(g)
+    st, nt, mx, ag = float(g["score_thresh"]), float(g["nms_thresh"]), int(g["max_per_img"]), bool(g["class_agnostic"])
+    lg, cg = loc_all.to(dev), conf.to(dev)
+    loc_heads, conf_heads = U.unpack_heads(lg, channels_last), U.unpack_heads(cg, channels_last)
+    back_loc, back_conf = O.pack_heads(loc_heads, conf_heads, cg.shape[-1])
+    assert bit_equal(back_loc, lg) and bit_equal(back_conf, cg)                 # the helper inverts the reference's packing
+    want = O.postprocess(env["pri"], lg, cg, st, nt, mx, ag, nms_limit=True, with_index=True)
+    gold = U.split_predictions(g)
+    before = s.launch_count()
+    got = s.predict_heads(ps, loc_heads, conf_heads, st, nt, mx, ag)
+    assert s.launch_count() == before + 2                                       # score_kernel + nms_image_kernel, no pack pass
+    labels, scores, boxes, count, cand = s.predict_heads_padded(ps, loc_heads, conf_heads, st, nt, mx, ag, want_cand=True)
+    pl, psc, pb, pc, pcand = s.predict_padded(ps, lg, cg, st, nt, mx, ag, want_cand=True)
+    assert bit_equal(count, pc)
+    for b, (a, w, r) in enumerate(zip(got, want, gold)):
+        k = int(count[b])
+        assert bit_equal(cand[b, :k], pcand[b, :k]) and bit_equal(scores[b, :k], psc[b, :k]) and bit_equal(boxes[b, :k], pb[b, :k])
+        assert bit_equal(cand[b, :k].long(), w["cand"]), f"keep list, image {b}"
+        assert bit_equal(a["labels"], w["labels"]) and bit_equal(a["scores"], w["scores"]) and bit_equal(a["boxes"], w["boxes"])
+        assert bit_equal(a["labels"], r["labels"])
+        assert close(a["scores"], r["scores"]) and close(a["boxes"], r["boxes"], atol=BOX_ATOL)
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("name", TRAIN)
+def test_losses_from_heads(env, name, channels_last):
+    """multibox_loss_heads(heads) == multibox_loss(pack(heads)): the three sums bit for bit, and the losses within 1e-5 of
+    the reference's (golden fixtures)."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    g = U.load(name)
+    targets, loc_all, conf = U.train_inputs(g)
+    thr, ratio = float(g["iou_thresh"]), float(g["ratio"])
+    lg, cg = loc_all.to(dev), conf.to(dev)
+    loc_heads, conf_heads = U.unpack_heads(lg, channels_last), U.unpack_heads(cg, channels_last)
+    _, _, sums_packed = s.multibox_loss(ps, lg, cg, targets, thr, ratio, return_sums=True)
+    l_loc, l_conf, sums = s.multibox_loss_heads(ps, loc_heads, conf_heads, targets, thr, ratio, return_sums=True)
+    assert bit_equal(sums, sums_packed)
+    assert abs(l_loc.item() - float(g["loc_loss"])) <= RTOL * abs(float(g["loc_loss"]))
+    assert abs(l_conf.item() - float(g["conf_loss"])) <= RTOL * abs(float(g["conf_loss"]))
+
+
+def test_heads_edge_cases(env):
+    """Head-direct paths on the inputs that leave the fast paths: every candidate passes (threshold 0), the exact
+    mining tail (budget >= negatives), images without boxes, and a class count the head kernels do not cover."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    cfg = s.synth.config(5, batch=2)
+    lg, cg = cfg["loc_all"].to(dev), cfg["conf_infer"].to(dev)
+    for cl in (False, True):
+        lh, ch = U.unpack_heads(lg, cl), U.unpack_heads(cg, cl)
+        for st, agn, metric in ((0.0, False, "diou"), (0.0, True, "ciou"), (0.3, False, "iou")):
+            a = s.predict_heads_padded(ps, lh, ch, st, 0.45, 200, agn, metric, want_cand=True)
+            b = s.predict_padded(ps, lg, cg, st, 0.45, 200, agn, metric, want_cand=True)
+            n = b[3]
+            assert bit_equal(a[3], n)
+            for i in range(lg.shape[0]):
+                k = int(n[i])
+                assert all(bit_equal(x[i, :k], y[i, :k]) for x, y in zip((a[0], a[1], a[2], a[4]), (b[0], b[1], b[2], b[4])))
+        ct = cfg["conf_train"].to(dev)
+        cht = U.unpack_heads(ct, cl)
+        targets = list(cfg["targets"])
+        targets[1] = {"boxes": torch.zeros((0, 4)), "labels": torch.zeros((0,), dtype=torch.int64)}
+        for ratio in (3.0, 1e6, 0.0):
+            want = s.multibox_loss(ps, lg, ct, targets, 0.5, ratio, return_sums=True)[2]
+            got = s.multibox_loss_heads(ps, lh, cht, targets, 0.5, ratio, return_sums=True)[2]
+            assert bit_equal(got, want), (cl, ratio)
+    # C = 21: packed first, then the packed kernels
+    gen = torch.Generator().manual_seed(5)
+    loc21 = torch.randn((2, 8732, 4), generator=gen).to(dev)
+    conf21 = torch.randn((2, 8732, 21), generator=gen).to(dev)
+    a = s.predict_heads_padded(ps, U.unpack_heads(loc21), U.unpack_heads(conf21), 0.2, 0.5, 50)
+    b = s.predict_padded(ps, loc21, conf21, 0.2, 0.5, 50)
+    assert all(bit_equal(x, y) for x, y in ((a[3], b[3]),)) and int(b[3].sum()) > 0
+    for i in range(2):
+        k = int(b[3][i])
+        assert bit_equal(a[1][i, :k], b[1][i, :k]) and bit_equal(a[2][i, :k], b[2][i, :k])
+    with pytest.raises(ValueError):
+        s.predict_heads(ps, U.unpack_heads(loc21)[:5], U.unpack_heads(conf21), 0.2, 0.5, 50)
