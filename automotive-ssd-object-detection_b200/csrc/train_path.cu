@@ -1532,6 +1532,87 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
     }
 }
 
+
+// loss_bwd_kernel on the head layouts (heads.cuh): reads the head outputs and writes the gradients in the same six
+// tensors' layout, so autograd never needs a packed [B,P,D] gradient.  One thread per prior; in the NCHW layout the
+// thread index enumerates (level, shape, cell) with the cell fastest, so a warp reads and writes runs of one plane.
+__device__ __forceinline__ const float* head_pick(const HeadView& hv, int l) {
+    const float* q = hv.base[0];
+#pragma unroll
+    for (int i = 1; i < kHeadLevels; ++i) if (l == i) q = hv.base[i];
+    return q;
+}
+template <int SRC>
+__global__ void __launch_bounds__(256) loss_bwd_heads_kernel(const float* __restrict__ pri,
+                                                             const float* __restrict__ gt_boxes, const int32_t* __restrict__ gt_offsets,
+                                                             int B, float norm_w, float norm_h,
+                                                             const HeadView loc_h, const HeadView conf_h,
+                                                             float inv_vc, float inv_vs,
+                                                             const int8_t* __restrict__ sel, const int16_t* __restrict__ matched,
+                                                             const double* __restrict__ scales,
+                                                             const HeadView g_loc_h, const HeadView g_conf_h, int want_loc, int want_conf) {
+    constexpr int P = 8732;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)B * P) return;
+    const int b = (int)(t / P), u = (int)(t % P);
+    const int l = head_level(u), r = u - head_level_off(l), hw = head_level_hw(l), A = head_level_six(l) ? 6 : 4;
+    int cell, a;
+    if (SRC == SRC_LEVEL_PLANES) { a = r / hw; cell = r - a * hw; }     // cell fastest across threads
+    else { cell = r / A; a = r - cell * A; }
+    const int p = head_level_off(l) + cell * A + a;
+    const long long row = (long long)b * P + p;
+    // element j of this prior's row in a branch with D values per prior: first + j * stride
+    auto first = [&](int D) -> long long {
+        return SRC == SRC_LEVEL_PLANES ? ((long long)b * A * D + a * D) * hw + cell : ((long long)b * hw * A + (p - head_level_off(l))) * D;
+    };
+    const int stride = SRC == SRC_LEVEL_PLANES ? hw : 1;
+    const int s = sel[row];
+    const float k_loc = (float)scales[0], k_conf = (float)scales[1];
+    if (want_conf) {
+        const long long f = first(6);
+        float* out = const_cast<float*>(head_pick(g_conf_h, l)) + f;
+        if (s < 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) out[(long long)i * stride] = 0.0f;
+        } else {
+            const float* in = head_pick(conf_h, l) + f;
+            float x[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) x[i] = __ldg(in + (long long)i * stride);
+            float mx = x[0];
+#pragma unroll
+            for (int i = 1; i < 6; ++i) mx = fmaxf(mx, x[i]);
+            float sum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) sum += expf(x[i] - mx);
+            const float inv = 1.0f / sum;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const float pr = expf(x[i] - mx) * inv;
+                out[(long long)i * stride] = k_conf * (pr - (i == s ? 1.0f : 0.0f));
+            }
+        }
+    }
+    if (want_loc) {
+        const long long f = first(4);
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        const int m = matched[row];
+        if (m >= 0) {
+            const float4 px = ldg4(gt_boxes + 4ll * (gt_offsets[b] + m));
+            const float x1 = fdiv(px.x, norm_w), y1 = fdiv(px.y, norm_h), x2 = fdiv(px.z, norm_w), y2 = fdiv(px.w, norm_h);
+            const float4 gbox = make_float4(fmul(fadd(x1, x2), 0.5f), fmul(fadd(y1, y2), 0.5f), fsub(x2, x1), fsub(y2, y1));
+            const float4 tg = encode_offsets(gbox, ldg4(pri + 4ll * p), inv_vc, inv_vs);
+            const float* in = head_pick(loc_h, l) + f;
+            const float tt[4] = {tg.x, tg.y, tg.z, tg.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) g[j] = k_loc * fminf(fmaxf(__ldg(in + (long long)j * stride) - tt[j], -1.f), 1.f);
+        }
+        float* out = const_cast<float*>(head_pick(g_loc_h, l)) + f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[(long long)j * stride] = g[j];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1847,6 +1928,46 @@ extern "C" int ssdhot_multibox_loss_bwd(const float* priors_cxcywh, int P,
     loss_bwd_kernel<0><<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         priors_cxcywh, P, gt_boxes, gt_offsets, rows, norm_w, norm_h, loc_all, conf_all, C,
         1.0f / var_center, 1.0f / var_size, sel_cls, matched_gt, scales, grad_loc, grad_conf);
+    SSDHOT_CHECK_LAUNCH();
+    return SSDHOT_OK;
+}
+
+// ssdhot_multibox_loss_bwd on the head layouts: the head outputs in, the gradients out, both as six per-level tensors.
+extern "C" int ssdhot_multibox_loss_heads_bwd(const float* priors_cxcywh, const float* gt_boxes, const int32_t* gt_offsets, int B,
+                                              float norm_w, float norm_h,
+                                              const float* const* loc_heads_host, const float* const* conf_heads_host,
+                                              int head_layout, int C, float var_center, float var_size,
+                                              const int8_t* sel_cls, const int16_t* matched_gt, const double* scales,
+                                              float* const* grad_loc_heads_host, float* const* grad_conf_heads_host,
+                                              ssdhot_stream_t stream) {
+    if (!sel_cls || !scales || (!grad_loc_heads_host && !grad_conf_heads_host)) return SSDHOT_ERR_NULL;
+    if (grad_conf_heads_host && !conf_heads_host) return SSDHOT_ERR_NULL;
+    if (grad_loc_heads_host && (!loc_heads_host || !matched_gt || !priors_cxcywh || !gt_offsets || !gt_boxes)) return SSDHOT_ERR_NULL;
+    if (head_layout != SSDHOT_HEADS_NHWC && head_layout != SSDHOT_HEADS_NCHW) return SSDHOT_ERR_VALUE;
+    if (B <= 0 || C != 6) return SSDHOT_ERR_SHAPE;
+    if (!aligned16(priors_cxcywh) || !aligned16(gt_boxes)) return SSDHOT_ERR_ALIGN;
+    HeadView lh = {}, ch = {}, glh = {}, gch = {};
+    for (int l = 0; l < kHeadLevels; ++l) {
+        if (grad_loc_heads_host) {
+            if (!loc_heads_host[l] || !grad_loc_heads_host[l]) return SSDHOT_ERR_NULL;
+            lh.base[l] = loc_heads_host[l]; glh.base[l] = grad_loc_heads_host[l];
+        }
+        if (grad_conf_heads_host) {
+            if (!conf_heads_host[l] || !grad_conf_heads_host[l]) return SSDHOT_ERR_NULL;
+            ch.base[l] = conf_heads_host[l]; gch.base[l] = grad_conf_heads_host[l];
+        }
+    }
+    const long long rows = (long long)B * 8732;
+    const unsigned grid = (unsigned)((rows + 255) / 256);
+    const int wl = grad_loc_heads_host ? 1 : 0, wc = grad_conf_heads_host ? 1 : 0;
+    if (head_layout == SSDHOT_HEADS_NHWC)
+        loss_bwd_heads_kernel<SRC_LEVEL_ROWS><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            priors_cxcywh, gt_boxes, gt_offsets, B, norm_w, norm_h, lh, ch, 1.0f / var_center, 1.0f / var_size, sel_cls, matched_gt,
+            scales, glh, gch, wl, wc);
+    else
+        loss_bwd_heads_kernel<SRC_LEVEL_PLANES><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            priors_cxcywh, gt_boxes, gt_offsets, B, norm_w, norm_h, lh, ch, 1.0f / var_center, 1.0f / var_size, sel_cls, matched_gt,
+            scales, glh, gch, wl, wc);
     SSDHOT_CHECK_LAUNCH();
     return SSDHOT_OK;
 }

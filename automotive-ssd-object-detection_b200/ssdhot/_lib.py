@@ -47,6 +47,7 @@ PROTOTYPES = {
                                    vp, vp, vp, vp, vp, vp, i32, vp]),
     "ssdhot_multibox_loss_heads_fwd": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, vp, vp, i32, i32,
                                              f32, f32, f32, f64, vp, vp, vp, vp, vp, vp, vp]),
+    "ssdhot_multibox_loss_heads_bwd": (i32, [vp, vp, vp, i32, f32, f32, vp, vp, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp]),
 }
 
 

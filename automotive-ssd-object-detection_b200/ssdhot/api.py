@@ -494,39 +494,90 @@ def predict_heads(model, loc_heads: Sequence[torch.Tensor], conf_heads: Sequence
             for l, s, b, k in zip(labels.unbind(0), scores.unbind(0), boxes.unbind(0), ks)]
 
 
-@torch.no_grad()
+class _FusedLossHeads(torch.autograd.Function):
+    """_FusedLoss on the head layouts: forward = ssdhot_multibox_loss_heads_fwd, backward = ssdhot_multibox_loss_heads_bwd,
+    which writes the gradients as twelve tensors laid out like the inputs."""
+
+    @staticmethod
+    def forward(ctx, priors: PriorSet, packed: PackedTargets, iou_thresh, ratio, norm_wh, group, *heads):
+        dev, B, C, layout, keep, loc_p, conf_p, alive = _head_args(heads[:6], heads[6:])
+        need_grad = any(h.requires_grad for h in heads)
+        sums = torch.empty((3,), dtype=torch.float64, device=dev)
+        sel = torch.empty((B, 8732), dtype=torch.int8, device=dev) if need_grad else None
+        matched = torch.empty((B, 8732), dtype=torch.int16, device=dev) if need_grad else None
+        work = _workspace("loss", dev, _lib.lib().ssdhot_loss_workspace_bytes(B, 8732, packed.max_gt))
+        with torch.cuda.device(dev):
+            rc = _lib.lib().ssdhot_multibox_loss_heads_fwd(
+                priors.priors.data_ptr(), priors.priors_xyxy.data_ptr(), priors.aux.data_ptr(), priors.layout,
+                packed.boxes.data_ptr(), packed.labels.data_ptr(), packed.offsets.data_ptr(), B, packed.max_gt,
+                float(norm_wh[0]), float(norm_wh[1]), loc_p, conf_p, layout, C,
+                float(iou_thresh), priors.variances[0], priors.variances[1], float(ratio),
+                sums.data_ptr(), work.data_ptr(), _ptr(sel), _ptr(matched), None, None, _stream(dev))
+        _lib.check(rc, "ssdhot_multibox_loss_heads_fwd")
+        for t in keep:
+            t.record_stream(torch.cuda.current_stream(dev))
+        if group is not None:
+            _dist.combine_sums(sums, None if group is True else group)
+        total = sums[2].clamp_min(1.0)
+        if need_grad:
+            ctx.save_for_backward(sel, matched, total, packed.boxes, packed.offsets, *keep)
+            ctx.meta = (priors, norm_wh, layout, B, C)
+        losses = (sums[:2] / total).to(torch.float32)
+        ctx.mark_non_differentiable(sums)
+        return losses[0], losses[1], sums
+
+    @staticmethod
+    def backward(ctx, g_loc, g_conf, _g_sums):
+        import ctypes
+        sel, matched, total, gt_boxes, gt_offsets, *keep = ctx.saved_tensors
+        priors, norm_wh, layout, B, C = ctx.meta
+        dev = sel.device
+        scales = torch.stack((g_loc.to(torch.float64) / total, g_conf.to(torch.float64) / total))
+        want_loc, want_conf = any(ctx.needs_input_grad[6:12]), any(ctx.needs_input_grad[12:18])
+        d_loc = [torch.empty_like(t) for t in keep[:6]] if want_loc else None
+        d_conf = [torch.empty_like(t) for t in keep[6:]] if want_conf else None
+
+        def arr(ts):
+            if ts is None:
+                return None, None
+            a = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in ts])
+            return a, ctypes.cast(a, ctypes.c_void_p)
+        (a0, lp), (a1, cp), (a2, glp), (a3, gcp) = arr(keep[:6]), arr(keep[6:]), arr(d_loc), arr(d_conf)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().ssdhot_multibox_loss_heads_bwd(
+                priors.priors.data_ptr(), gt_boxes.data_ptr(), gt_offsets.data_ptr(), B, float(norm_wh[0]), float(norm_wh[1]),
+                lp, cp, layout, C, priors.variances[0], priors.variances[1], sel.data_ptr(), matched.data_ptr(),
+                scales.data_ptr(), glp, gcp, _stream(dev))
+        _lib.check(rc, "ssdhot_multibox_loss_heads_bwd")
+        grads = (d_loc or [None] * 6) + (d_conf or [None] * 6)
+        return (None,) * 6 + tuple(grads)
+
+
 def multibox_loss_heads(model, loc_heads: Sequence[torch.Tensor], conf_heads: Sequence[torch.Tensor], targets,
                         iou_thresh: float = 0.5, neg_pos_ratio: float = 3.0, H: int = 300, W: int = 300, group=None,
                         return_sums: bool = False):
-    """multibox_loss (forward) from the six head outputs of each branch: the evaluation-step losses of SSD_test_step
-    (SSD_trainer.py:226-231) without ever forming loc_all / conf_all.  Same sums as multibox_loss on the packed tensors,
-    bit for bit.  Inputs the head kernel does not cover (C != 6, more than 64 boxes per image, non-SSD300 priors) are packed
-    first and take the packed entry point."""
+    """multibox_loss from the six head outputs of each branch: the post-backbone training step (SSD_trainer.py:92-117)
+    without ever forming loc_all / conf_all -- differentiable w.r.t. the twelve head tensors, whose gradients come back in
+    the heads' own memory layout.  Same sums as multibox_loss on the packed tensors, bit for bit.  Inputs the head kernel
+    does not cover (C != 6, more than 64 boxes per image, non-SSD300 priors) go through the forward's own permute + cat
+    (differentiable) and the packed entry point."""
     if not (0.0 < iou_thresh < 1.0):
         raise ValueError(f"Score threshold should be greater than 0 and less than 1, recieved {iou_thresh}.")
     priors = PriorSet.of(model)
-    packed = targets if isinstance(targets, PackedTargets) else pack_targets(targets, priors.device)
-    dev, B, C, layout, keep, loc_p, conf_p, _alive = _head_args(loc_heads, conf_heads)
+    packed = pack_targets(targets, priors.device)
+    if len(loc_heads) != len(_LEVELS) or len(conf_heads) != len(_LEVELS):
+        raise ValueError(f"expected {len(_LEVELS)} loc and conf head outputs, got {len(loc_heads)} and {len(conf_heads)}")
+    C = int(conf_heads[0].shape[1]) // _LEVELS[0][1]
     if C != 6 or priors.layout != 1 or packed.max_gt > 64:           # (1 = SSDHOT_LAYOUT_SSD300)
-        return multibox_loss(model, *pack_heads(loc_heads, conf_heads), targets, iou_thresh, neg_pos_ratio, H, W, group, return_sums)
-    sums = torch.empty((3,), dtype=torch.float64, device=dev)
-    work = _workspace("loss", dev, _lib.lib().ssdhot_loss_workspace_bytes(B, 8732, packed.max_gt))
-    with torch.cuda.device(dev):
-        rc = _lib.lib().ssdhot_multibox_loss_heads_fwd(
-            priors.priors.data_ptr(), priors.priors_xyxy.data_ptr(), priors.aux.data_ptr(), priors.layout,
-            packed.boxes.data_ptr(), packed.labels.data_ptr(), packed.offsets.data_ptr(), B, packed.max_gt,
-            float(W), float(H), loc_p, conf_p, layout, C,
-            float(iou_thresh), priors.variances[0], priors.variances[1], float(neg_pos_ratio),
-            sums.data_ptr(), work.data_ptr(), None, None, None, None, _stream(dev))
-    _lib.check(rc, "ssdhot_multibox_loss_heads_fwd")
-    for t in keep:
-        t.record_stream(torch.cuda.current_stream(dev))
-    if group is not None:
-        _dist.combine_sums(sums, None if group is True else group)
-    losses = (sums[:2] / sums[2].clamp_min(1.0)).to(torch.float32)
+        B = int(conf_heads[0].shape[0])
+        loc_all = torch.cat([h.permute(0, 2, 3, 1).contiguous().view(B, -1, 4) for h in loc_heads], 1)       # SFS:249-269
+        conf_all = torch.cat([h.permute(0, 2, 3, 1).contiguous().view(B, -1, C) for h in conf_heads], 1)
+        return multibox_loss(model, loc_all, conf_all, packed, iou_thresh, neg_pos_ratio, H, W, group, return_sums)
+    l_loc, l_conf, sums = _FusedLossHeads.apply(priors, packed, float(iou_thresh), float(neg_pos_ratio), (W, H), group,
+                                                *loc_heads, *conf_heads)
     if return_sums:
-        return losses[0], losses[1], sums
-    return losses[0], losses[1]
+        return l_loc, l_conf, sums
+    return l_loc, l_conf
 
 
 # ------------------------------------------------------------------------------------------------

@@ -242,6 +242,17 @@ SSDHOT_API int ssdhot_multibox_loss_heads_fwd(const float* priors_cxcywh, const 
                          double* sums, void* work, int8_t* sel_cls, int16_t* matched_gt, int32_t* n_pos,
                          int32_t* dev_flags, ssdhot_stream_t stream);
 
+/* ssdhot_multibox_loss_bwd on the head layouts: reads the head outputs, writes the gradients as six per-level tensors
+ * of the same layout as the inputs (HOST arrays of DEVICE pointers; either gradient array may be NULL).  sel_cls /
+ * matched_gt [B,8732] as written by ssdhot_multibox_loss_heads_fwd.  Values equal ssdhot_multibox_loss_bwd's. */
+SSDHOT_API int ssdhot_multibox_loss_heads_bwd(const float* priors_cxcywh, const float* gt_boxes, const int32_t* gt_offsets, int B,
+                         float norm_w, float norm_h,
+                         const float* const* loc_heads_host, const float* const* conf_heads_host,
+                         int head_layout, int C, float var_center, float var_size,
+                         const int8_t* sel_cls, const int16_t* matched_gt, const double* scales,
+                         float* const* grad_loc_heads_host, float* const* grad_conf_heads_host,
+                         ssdhot_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -677,3 +677,33 @@ def test_heads_edge_cases(env):
         assert bit_equal(a[1][i, :k], b[1][i, :k]) and bit_equal(a[2][i, :k], b[2][i, :k])
     with pytest.raises(ValueError):
         s.predict_heads(ps, U.unpack_heads(loc21)[:5], U.unpack_heads(conf21), 0.2, 0.5, 50)
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_heads_backward_matches_autograd(env, channels_last):
+    """Gradients of multibox_loss_heads w.r.t. the twelve head tensors == torch autograd through the reference's own
+    permute + cat tail (SFS:249-269) and loss (TR:104-108, :551-600), within 1e-5; delivered in the heads' memory format."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    g = U.load("train_cfg2_thr04.npz")
+    targets, loc_all, conf = U.train_inputs(g)
+    thr, ratio = float(g["iou_thresh"]), float(g["ratio"])
+    tg = to_dev(targets, dev)
+    mine = [h.requires_grad_(True) for h in U.unpack_heads(loc_all.to(dev), channels_last) + U.unpack_heads(conf.to(dev), channels_last)]
+    ref = [h.detach().clone().requires_grad_(True) for h in mine]
+    l_loc, l_conf = s.multibox_loss_heads(ps, mine[:6], mine[6:], targets, thr, ratio)
+    (l_loc * 1.5 + l_conf * 0.7).backward()
+    lb, cb = O.pack_heads(ref[:6], ref[6:], 6)
+    pos_o, locpm_o, cls_o = O.batch_targets(env["pri"], env["pri_xyxy"], tg, 300, 300, thr)
+    o_loc, n_img, total = O.loc_loss(lb, pos_o, locpm_o)
+    o_conf = O.mined_ce_loss(cb, cls_o, pos_o, n_img, total, ratio)
+    (o_loc * 1.5 + o_conf * 0.7).backward()
+    assert abs(l_loc.item() - o_loc.item()) <= RTOL * abs(o_loc.item()) and abs(l_conf.item() - o_conf.item()) <= RTOL * abs(o_conf.item())
+    for a, b in zip(mine, ref):
+        assert a.grad is not None and a.grad.shape == a.shape
+        assert a.grad.is_contiguous(memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+        assert close(a.grad, b.grad, atol=1e-7)
+    # only the class branch needs a gradient
+    only = [h.detach().clone().requires_grad_(i >= 6) for i, h in enumerate(mine)]
+    l_loc, l_conf = s.multibox_loss_heads(ps, only[:6], only[6:], targets, thr, ratio)
+    (l_loc + l_conf).backward()
+    assert all(h.grad is None for h in only[:6]) and all(h.grad is not None for h in only[6:])
