@@ -115,4 +115,72 @@ struct HeadReader {
     }
 };
 
+
+// ---- SRC_LEVEL_PLANES streaming order -------------------------------------------------------------------------------
+// The streaming kernels visit the row pairs (rows p, p+1 = shapes 2s, 2s+1 of one cell) of an image; in the NCHW layout
+// they do it plane-wise: a "chunk" is 32 consecutive cells of one (level, shape pair) region, lane = cell, so each of the
+// 12 loads of a chunk reads 128 contiguous bytes of one channel plane.  15 regions (level, s), 147 chunks per image:
+//   level 0: 2 x 46 chunks | level 1: 3 x 12 | level 2: 3 x 4 | level 3: 3 x 1 | level 4: 2 x 1 | level 5: 2 x 1
+constexpr int kPlaneChunks = 147;
+__constant__ int kRegChunk0[16] = {0, 46, 92, 104, 116, 128, 132, 136, 140, 141, 142, 143, 144, 145, 146, 147};
+__constant__ int kRegLevel[15] = {0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 5, 5};
+__constant__ int kRegPair[15] = {0, 1, 0, 1, 2, 0, 1, 2, 0, 1, 2, 0, 1, 0, 1};
+
+// One (level, shape pair) region of an image's D = 6 branch, prepared once per CTA in shared memory.
+struct PlaneRegion {
+    const float* ptr0;     // cell 0 of the first plane of the pair's 12 channels
+    int hw;                // cells = plane stride
+    int pbase;             // first row of the pair in cell 0: level offset + 2 s
+    int shapes;            // rows per cell (4 or 6)
+    int chunk0, chunk1;    // the region's chunks are [chunk0, chunk1)
+    int pad;
+};
+struct PlaneRegions { PlaneRegion r[15]; };
+
+__device__ __forceinline__ void plane_regions_fill(PlaneRegions& t, const HeadView& hv, int b, int tid) {
+    if ((unsigned)tid < 15u) {
+        const int l = kRegLevel[tid], s = kRegPair[tid], hw = head_level_hw(l), shapes = head_level_six(l) ? 6 : 4;
+        const float* img = hv.base[0];
+#pragma unroll
+        for (int i = 1; i < kHeadLevels; ++i) if (l == i) img = hv.base[i];
+        PlaneRegion r;
+        r.ptr0 = img + ((long long)b * shapes * 6 + 12 * s) * hw;
+        r.hw = hw; r.pbase = head_level_off(l) + 2 * s; r.shapes = shapes;
+        r.chunk0 = kRegChunk0[tid]; r.chunk1 = kRegChunk0[tid + 1]; r.pad = 0;
+        t.r[tid] = r;
+    }
+}
+
+// the 12 values of a row pair: plane stride known at compile time, so the loads take immediate offsets
+template <int HW>
+__device__ __forceinline__ void plane_load12_hw(const float* q, float* x) {
+#pragma unroll
+    for (int j = 0; j < 12; ++j) x[j] = __ldg(q + j * HW);
+}
+__device__ __forceinline__ void plane_load12(const float* q, int hw, float* x) {       // hw is warp-uniform
+    if (hw == 1444) plane_load12_hw<1444>(q, x);
+    else if (hw == 361) plane_load12_hw<361>(q, x);
+    else if (hw == 100) plane_load12_hw<100>(q, x);
+    else if (hw == 25) plane_load12_hw<25>(q, x);
+    else if (hw == 9) plane_load12_hw<9>(q, x);
+    else plane_load12_hw<1>(q, x);
+}
+
+// Walks the chunks k0, k0 + step, ... of an image (warp-uniform); load() fetches this lane's pair of the current chunk.
+struct PlaneWalk {
+    const PlaneRegions* t;
+    int reg;
+    __device__ __forceinline__ PlaneWalk(const PlaneRegions* tab) : t(tab), reg(0) {}
+    // -> this lane's cell exists; p0 = first row of its pair.  (A lane past the end of the region reads the region's last
+    // cell, so the loads need no predicate.)
+    __device__ __forceinline__ bool load(int k, int lane, float* x, int& p0) {
+        while (k >= t->r[reg].chunk1) ++reg;
+        const PlaneRegion r = t->r[reg];
+        const int cell = (k - r.chunk0) * 32 + lane;
+        p0 = r.pbase + cell * r.shapes;
+        plane_load12(r.ptr0 + min(cell, r.hw - 1), r.hw, x);
+        return cell < r.hw;
+    }
+};
+
 }  // namespace ssdhot

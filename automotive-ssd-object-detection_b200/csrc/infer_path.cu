@@ -535,6 +535,9 @@ constexpr int UT = 512;        // threads of stand-alone NMS
 
 // rows of one list segment (even, so that a segment starts on a 48-byte row pair when C == 6)
 __host__ __device__ inline int seg_rows(int P) { return (((P + SEGS - 1) / SEGS) + 1) & ~1; }
+// rows a list segment has room for: the plane-wise order of the NCHW head source (heads.cuh) hands a warp up to
+// 10 chunks of 32 row pairs
+__host__ __device__ inline int seg_cap_rows(int P) { return P == 8732 ? 640 : seg_rows(P); }
 
 __device__ __forceinline__ float ex2_approx_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -562,8 +565,10 @@ __global__ void __launch_bounds__(ST, 4) score_kernel(const PredictParams prm) {
     const int b = blockIdx.x / SCS, part = blockIdx.x % SCS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ HeadTable htab;                     // per-level bases of this image (head sources only)
+    __shared__ PlaneRegions regions;               // (NCHW heads)
     if (SRC != SRC_PACKED) {
-        head_table_fill<SRC, 6>(htab, prm.conf_h, b, threadIdx.x);
+        if (SRC == SRC_LEVEL_PLANES) plane_regions_fill(regions, prm.conf_h, b, threadIdx.x);
+        else head_table_fill<SRC, 6>(htab, prm.conf_h, b, threadIdx.x);
         __syncthreads();
     }
     const int seg = part * (ST / 32) + warp;
@@ -571,34 +576,44 @@ __global__ void __launch_bounds__(ST, 4) score_kernel(const PredictParams prm) {
     const int rows = seg_rows(P);
     const int r0 = min(P, seg * rows), r1 = min(P, r0 + rows);
     const float* conf_b = SRC == SRC_PACKED ? prm.conf_all + (long long)b * P * prm.C : nullptr;
-    unsigned long long* list = prm.cand + ((long long)b * SEGS + seg) * rows * n_fg;
+    unsigned long long* list = prm.cand + ((long long)b * SEGS + seg) * seg_cap_rows(P) * n_fg;
     const unsigned lt = (1u << lane) - 1u;
     int cnt = 0;                                            // warp-uniform
     if (CT == 6) {
         const float thr = prm.score_thresh, thr_hi = thr * 1.0001f, thr_lo = thr * 0.9999f;
         const HeadReader<SRC, 6> rd = {conf_b, &htab};
-        const int q1 = r1 >> 1;                             // P is even on this path
+        const int q0 = r0 >> 1, q1 = r1 >> 1;               // P is even on this path
+        // iteration `it` of this warp: 32 row pairs -- consecutive pairs of the segment's row range, or (NCHW planes) chunk
+        // seg + 16 * it of the plane-wise order (heads.cuh).  -> this lane has a pair; p0 = its first row
+        const int n_it = SRC == SRC_LEVEL_PLANES ? (kPlaneChunks - seg + SEGS - 1) / SEGS : (q1 - q0 + 31) >> 5;
+        PlaneWalk walk(&regions);
+        auto load_it = [&](int it, float* xx, int& p0) -> bool {
+            if (SRC == SRC_LEVEL_PLANES) {
+                return walk.load(seg + SEGS * it, lane, xx, p0);
+            } else {
+                const int q = q0 + 32 * it + lane;
+                p0 = 2 * q;
+                if (q < q1) rd.pair(q, xx);
+                return q < q1;
+            }
+        };
         // software pipeline: the loads of the next row pair (three 16-byte loads when rows are contiguous) are in
         // flight while this one is scored
         float nx[12];
 #pragma unroll
         for (int j = 0; j < 12; ++j) nx[j] = 0.f;
-        {
-            const int q = (r0 >> 1) + lane;
-            if (q < q1) rd.pair(q, nx);
-        }
-        for (int qb = r0 >> 1; qb < q1; qb += 32) {
-            const int q = qb + lane;
-            unsigned pass = 0u;                             // bit (h * 5 + k): row 2q+h, class k+1 is a candidate
+        int n_p0 = 0;
+        bool n_live = n_it > 0 && load_it(0, nx, n_p0);
+        for (int it = 0; it < n_it; ++it) {
+            unsigned pass = 0u;                             // bit (h * 5 + k): row p0+h, class k+1 is a candidate
             float sc[10];
             float x[2][6];
 #pragma unroll
             for (int j = 0; j < 12; ++j) x[j / 6][j % 6] = nx[j];
-            {
-                const int qn = q + 32;
-                if (qn < q1) rd.pair(qn, nx);
-            }
-            if (q < q1) {
+            const bool live = n_live;
+            const int p0 = n_p0;
+            n_live = it + 1 < n_it && load_it(it + 1, nx, n_p0);
+            if (live) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const float mx = fmaxf(fmaxf(fmaxf(x[h][0], x[h][1]), fmaxf(x[h][2], x[h][3])), fmaxf(x[h][4], x[h][5]));
@@ -637,7 +652,7 @@ __global__ void __launch_bounds__(ST, 4) score_kernel(const PredictParams prm) {
             int at = cnt + incl - mine;
             cnt += __shfl_sync(FULL, incl, 31);
             if (pass) {
-                const unsigned id0 = (unsigned)(2 * q) * 5u;
+                const unsigned id0 = (unsigned)p0 * 5u;
 #pragma unroll
                 for (int j = 0; j < 10; ++j) {
                     if ((pass >> j) & 1u) {
@@ -781,7 +796,7 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
     const int n_groups = AGN ? 1 : n_fg;
     const ImgBuffers buf = carve_img(dyn, max_keep, n_groups);
     SegSource src;
-    src.seg_cap = seg_rows(P) * n_fg;
+    src.seg_cap = seg_cap_rows(P) * n_fg;
     src.base = prm.cand + (long long)b * SEGS * src.seg_cap;
     src.counts = prm.cand_count + b * SEGS;
     bool first = true;
@@ -1220,12 +1235,12 @@ extern "C" int ssdhot_nms(const float* boxes, const float* scores, const int32_t
     return SSDHOT_OK;
 }
 
-// workspace layout: cand_count [B][SEGS] int32 | cand [B][SEGS][seg_rows(P)*(C-1)] uint64
+// workspace layout: cand_count [B][SEGS] int32 | cand [B][SEGS][seg_cap_rows(P)*(C-1)] uint64
 static size_t pw_cand_off(int B) { return ((size_t)B * SEGS * 4 + 15) & ~(size_t)15; }
 
 extern "C" unsigned long long ssdhot_predict_workspace_bytes(int B, int P, int C) {
     if (B <= 0 || P <= 0 || C < 2) return 64ull;
-    return (unsigned long long)(pw_cand_off(B) + (size_t)B * SEGS * seg_rows(P) * (C - 1) * 8 + 64);
+    return (unsigned long long)(pw_cand_off(B) + (size_t)B * SEGS * seg_cap_rows(P) * (C - 1) * 8 + 64);
 }
 
 extern "C" int ssdhot_predict(const float* priors_cxcywh, int P, const float* loc_all, const float* conf_all,

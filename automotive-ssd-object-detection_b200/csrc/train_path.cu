@@ -1065,6 +1065,7 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ FusedStatic fs;
     __shared__ HeadTable loc_tab, conf_tab;        // per-level bases of this image (head sources only)
+    __shared__ PlaneRegions regions;               // (NCHW heads: the stream's plane-wise order)
     pdl_trigger();                                 // finalize_sums_kernel may be scheduled early (it waits for this grid)
     SSDHOT_STAMP(0);
     constexpr int MT = LOSS ? MT_LOSS : FT;                  // threads that run the matching
@@ -1100,6 +1101,7 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     if (SRC != SRC_PACKED && LOSS) {
         head_table_fill<SRC, 4>(loc_tab, prm.loc_h, b, tid - 64);
         head_table_fill<SRC, 6>(conf_tab, prm.conf_h, b, tid - 96);
+        if (SRC == SRC_LEVEL_PLANES) plane_regions_fill(regions, prm.conf_h, b, tid - 128);
     }
     if (tid == 0) { fs.first_nan = INT_MAX; fs.n_dense = 0; fs.n_band = 0; fs.n_pair = 0; fs.pair_overflow = 0; fs.n_pos_img = 0; fs.n_sure = 0; }
     if (tid >= 32 && tid < 32 + G) {
@@ -1130,16 +1132,34 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
         SSDHOT_STAMP(3);
     } else if (LOSS) {
         const int n_pairs = P / 2;
+        if (SRC == SRC_LEVEL_PLANES) {
+            // NCHW heads: plane-wise order (heads.cuh), a chunk of 32 cells per warp and iteration
 #pragma unroll 2
-        for (int q = tid - MT; q < n_pairs; q += FT - MT) {
-            float x[12];
-            conf_rd.pair(q, x);
-            const unsigned k0 = __float_as_uint(approx_ce6(x[0], x[1], x[2], x[3], x[4], x[5]));
-            const unsigned k1 = __float_as_uint(approx_ce6(x[6], x[7], x[8], x[9], x[10], x[11]));
-            v.lo[4 * q] = k0;
-            v.lo[4 * q + 2] = k1;
-            ce_hist_add(hist16, k0);
-            ce_hist_add(hist16, k1);
+            PlaneWalk walk(&regions);
+            for (int k = (tid - MT) >> 5; k < kPlaneChunks; k += (FT - MT) >> 5) {
+                float x[12];
+                int p0;
+                if (walk.load(k, lane, x, p0)) {
+                    const unsigned k0 = __float_as_uint(approx_ce6(x[0], x[1], x[2], x[3], x[4], x[5]));
+                    const unsigned k1 = __float_as_uint(approx_ce6(x[6], x[7], x[8], x[9], x[10], x[11]));
+                    v.lo[2 * p0] = k0;
+                    v.lo[2 * p0 + 2] = k1;
+                    ce_hist_add(hist16, k0);
+                    ce_hist_add(hist16, k1);
+                }
+            }
+        } else {
+#pragma unroll 2
+            for (int q = tid - MT; q < n_pairs; q += FT - MT) {
+                float x[12];
+                conf_rd.pair(q, x);
+                const unsigned k0 = __float_as_uint(approx_ce6(x[0], x[1], x[2], x[3], x[4], x[5]));
+                const unsigned k1 = __float_as_uint(approx_ce6(x[6], x[7], x[8], x[9], x[10], x[11]));
+                v.lo[4 * q] = k0;
+                v.lo[4 * q + 2] = k1;
+                ce_hist_add(hist16, k0);
+                ce_hist_add(hist16, k1);
+            }
         }
         if ((P & 1) && tid == MT) {                          // odd P: the last row (never SSD300)
             float r[6];

@@ -58,7 +58,7 @@ ref = {}
 for train in (True, False):
     half = "match_loss" if train else "decode_nms"
     out[half] = {}
-    for mode in ("packed", "pack+packed", "torch+packed", "nchw", "nhwc"):
+    for mode in os.environ.get("MODES", "packed,pack+packed,torch+packed,nchw,nhwc").split(","):
         for i in range(4):
             run(mode, train, i)
         torch.cuda.synchronize()
@@ -71,6 +71,8 @@ for train in (True, False):
         if mode == "packed":
             ref[half] = (step.sums.clone(), step.count.clone(), step.scores.clone())
         # all modes end on the same input set: identical results
+        if half not in ref:
+            continue
         same = bool((step.sums == ref[half][0]).all()) if train else bool((step.count == ref[half][1]).all() and (step.scores == ref[half][2]).all())
         out[half][mode + "_same_result"] = same
 print(json.dumps(out))
