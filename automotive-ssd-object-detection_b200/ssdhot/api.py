@@ -366,6 +366,10 @@ def predict(model, images: Optional[torch.Tensor], score_thresh: float = 0.2, nm
         model.eval()                                   # side effect of the reference (:375)
     if (pre_loc_all is not None) and (pre_conf_all is not None):
         loc_all, conf_all = pre_loc_all, pre_conf_all
+    elif _has_ssd_heads(model):
+        # the model's own backbone and heads, but no permute / cat tail: the kernels read the head outputs directly
+        loc_heads, conf_heads = forward_heads(model, images)
+        return predict_heads(model, loc_heads, conf_heads, score_thresh, nms_thresh, max_per_img, class_agnostic, metric)
     else:
         loc_all, conf_all = model(images)
     if hasattr(model, "num_classes"):
@@ -413,6 +417,27 @@ def pack_heads(loc_heads: Sequence[torch.Tensor], conf_heads: Sequence[torch.Ten
 # the hot path straight from the head outputs (no permute / cat / pack pass at all)
 # ------------------------------------------------------------------------------------------------
 HEADS_NCHW, HEADS_NHWC = 0, 1
+_SSD_TRUNK = ("VGG16_UpTo_conv4_3", "VGG16_extras", "extra_conv6", "extra_conv7", "extra_conv8_2", "extra_conv9_2",
+              "extra_conv10_2", "extra_conv11_2", "box_head", "cls_head")
+
+
+def _has_ssd_heads(model) -> bool:
+    return all(hasattr(model, name) for name in _SSD_TRUNK)
+
+
+def forward_heads(model, x: torch.Tensor) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
+    """mySSD.forward up to the head convolutions (SFS:236-262), through the model's own modules, WITHOUT the
+    permute(0,2,3,1).contiguous() x 12 + cat x 2 tail (SFS:249-269): -> (six box-head outputs [B, A*4, H, W], six
+    class-head outputs [B, A*C, H, W]) for predict_heads / multibox_loss_heads.  model(x) == pack_heads(*forward_heads(model, x)).
+    The backbone and the heads stay PyTorch modules (out of this path's scope)."""
+    f0 = model.VGG16_UpTo_conv4_3(x)
+    f1 = model.extra_conv7(model.extra_conv6(model.VGG16_extras(f0)))
+    f2 = model.extra_conv8_2(f1)
+    f3 = model.extra_conv9_2(f2)
+    f4 = model.extra_conv10_2(f3)
+    f5 = model.extra_conv11_2(f4)
+    feats = (f0, f1, f2, f3, f4, f5)
+    return [h(f) for h, f in zip(model.box_head, feats)], [h(f) for h, f in zip(model.cls_head, feats)]
 
 
 def _head_args(loc_heads: Sequence[torch.Tensor], conf_heads: Sequence[torch.Tensor]):
@@ -454,8 +479,8 @@ def predict_heads_padded(model, loc_heads: Sequence[torch.Tensor], conf_heads: S
         raise ValueError(f"Score threshold should be greater than 0 and less than 1, recieved {score_thresh}.")
     if not (0.0 < nms_thresh < 1.0):
         raise ValueError(f"NMS threshold should be greater than 0 and less than 1, recieved {nms_thresh}.")
-    priors = PriorSet.of(model)
     dev, B, C, layout, keep, loc_p, conf_p, _alive = _head_args(loc_heads, conf_heads)
+    priors = PriorSet.of(model)
     assert priors.P == 8732
     assert C >= 2
     if C != 6:

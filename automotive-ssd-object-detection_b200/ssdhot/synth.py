@@ -116,3 +116,21 @@ def pack_targets(targets: List[Dict[str, torch.Tensor]]) -> Tuple[torch.Tensor, 
     boxes = torch.cat([t["boxes"].reshape(-1, 4).to(torch.float32) for t in targets], 0)
     labels = torch.cat([t["labels"].reshape(-1).to(torch.int64) for t in targets], 0)
     return boxes.contiguous(), labels.contiguous(), offs
+
+
+LEVELS = ((38, 4), (19, 6), (10, 6), (5, 6), (3, 4), (1, 4))      # (side, shapes per cell) of the six SSD300 feature maps
+
+
+def heads_from_packed(all_rows: torch.Tensor, channels_last: bool = False) -> List[torch.Tensor]:
+    """Synthetic head outputs: the six tensors [B, A*D, H, W] whose reference packing (permute(0,2,3,1) + view + cat,
+    SSD_from_scratch.py:249-269) is `all_rows` [B, 8732, D] -- pure data movement.  channels_last=True returns them in
+    channels_last memory format (what a channels_last conv head produces)."""
+    B, _, D = all_rows.shape
+    out, off = [], 0
+    for side, shapes in LEVELS:
+        n = side * side * shapes
+        h = all_rows[:, off:off + n, :].reshape(B, side, side, shapes * D).permute(0, 3, 1, 2)
+        out.append(h.contiguous(memory_format=torch.channels_last) if channels_last else h.contiguous())
+        off += n
+    assert off == 8732
+    return out

@@ -344,6 +344,58 @@ def main():
         },
     }
 
+    # ---- the same halves fed by the head outputs: no permute / cat / pack pass ---------------
+    def time_heads():
+        from ssdhot.engine import HeadSet
+        st_ = torch.cuda.current_stream(dev).cuda_stream
+        out = {"note": "CUDA-event time of each half at this batch when the kernels read the six head outputs of each branch "
+                       "directly (NCHW as the conv heads return them / channels_last), vs ssdhot_pack_heads + the packed kernels "
+                       "and vs the reference's own permute + cat tail (SFS:249-269) + the packed kernels", "unit": "ms"}
+        views = []
+        for sset in sets[:3]:
+            v = {}
+            for name, cl in (("nchw", False), ("nhwc", True)):
+                lh = synth.heads_from_packed(sset["loc"], cl)
+                cth, cih = synth.heads_from_packed(sset["conf_t"], cl), synth.heads_from_packed(sset["conf_i"], cl)
+                v[name] = dict(lh=lh, cth=cth, cih=cih, train=HeadSet(lh, cth), infer=HeadSet(lh, cih))
+            views.append(v)
+
+        def torch_tail(heads, D):
+            return torch.cat([h.permute(0, 2, 3, 1).contiguous().view(h.shape[0], -1, D) for h in heads], 1)
+
+        def run(mode, train, i):
+            sset, v = sets[i % len(views)], views[i % len(views)]
+            if mode in ("nchw", "nhwc"):
+                step.launch_loss_heads(v[mode]["train"], sset["gt"], st_) if train else step.launch_predict_heads(v[mode]["infer"], st_)
+                return
+            h = v["nchw"]
+            if mode == "pack_then_packed":
+                loc, conf = ssdhot.pack_heads(h["lh"], h["cth"] if train else h["cih"])
+            else:
+                loc, conf = torch_tail(h["lh"], 4), torch_tail(h["cth"] if train else h["cih"], C)
+            step.launch_loss(loc, conf, sset["gt"], st_) if train else step.launch_predict(loc, conf, st_)
+
+        for train in (True, False):
+            res = {}
+            for mode in ("nchw", "nhwc", "pack_then_packed", "torch_tail_then_packed"):
+                for i in range(3):
+                    run(mode, train, i)
+                torch.cuda.synchronize(dev)
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(24)]
+                for i, (a, b) in enumerate(evs):
+                    a.record()
+                    run(mode, train, i)
+                    b.record()
+                torch.cuda.synchronize(dev)
+                res[mode] = statistics.median(a.elapsed_time(b) for a, b in evs)
+            res["packed_kernels_only"] = ms_loss if train else ms_pred
+            out["match_loss" if train else "decode_nms"] = res
+        del views
+        torch.cuda.empty_cache()
+        return out
+
+    heads = time_heads() if rank == 0 else None
+
     # ---- the HBM-bound streaming kernel of predict on its own (score_kernel: logits in, candidate lists out) -----
     def time_score_kernel(stp, inputs, batch, iters=16):
         """inputs: (loc, conf) pairs rotated over the launches (together larger than L2)."""
@@ -465,6 +517,7 @@ def main():
             "parts": {"match_loss_images_per_s": BATCH * world / (ms_loss * 1e-3),
                       "decode_nms_images_per_s": BATCH * world / (ms_pred * 1e-3)},
             "roofline": roofline,
+            "heads": heads,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h_holder.get("bytes", 0), "steps": e2e_steps,

@@ -76,20 +76,5 @@ def unpack_bits(bits: np.ndarray, n: int) -> torch.Tensor:
     return torch.from_numpy(np.unpackbits(bits, axis=-1)[..., :n].astype(bool))
 
 
-LEVELS = ((38, 4), (19, 6), (10, 6), (5, 6), (3, 4), (1, 4))
-
-
-def unpack_heads(all_rows: torch.Tensor, channels_last: bool = False) -> List[torch.Tensor]:
-    """Inverse of the tail of mySSD.forward (SFS:249-269): [B, 8732, D] -> the six head outputs [B, A*D, H, W] whose
-    permute(0,2,3,1).view(B,-1,D) + cat is `all_rows` (pure data movement).  channels_last=True returns the same
-    tensors in channels_last memory format (what a channels_last conv head produces)."""
-    B, _, D = all_rows.shape
-    out, off = [], 0
-    for side, shapes in LEVELS:
-        n = side * side * shapes
-        h = all_rows[:, off:off + n, :].reshape(B, side, side, shapes * D).permute(0, 3, 1, 2)
-        h = h.contiguous(memory_format=torch.channels_last) if channels_last else h.contiguous()
-        out.append(h)
-        off += n
-    assert off == 8732
-    return out
+LEVELS = synth.LEVELS
+unpack_heads = synth.heads_from_packed      # [B, 8732, D] -> the six head outputs whose reference packing it is

@@ -707,3 +707,37 @@ def test_heads_backward_matches_autograd(env, channels_last):
     l_loc, l_conf = s.multibox_loss_heads(ps, only[:6], only[6:], targets, thr, ratio)
     (l_loc + l_conf).backward()
     assert all(h.grad is None for h in only[:6]) and all(h.grad is not None for h in only[6:])
+
+
+def test_predict_images_goes_through_the_heads(env):
+    """predict(model, images) on a model with mySSD's module names runs the model's trunk and heads, then the head-direct
+    kernels (no permute / cat / pack): same detections as predict on the model's own (loc_all, conf_all)."""
+    from test_host_cpu import _TinySSD
+    s, dev = env["ssdhot"], env["dev"]
+    torch.manual_seed(11)
+    model = _TinySSD().to(dev).eval()
+    model.register_buffer("priors", s.default_boxes().to(dev))
+    x = torch.randn(3, 3, 300, 300, device=dev)
+    with torch.no_grad():
+        loc_all, conf_all = model(x)
+        conf_all = conf_all * 8.0                                   # (the stub's logits are nearly flat)
+        for h in model.cls_head:
+            h.weight.mul_(8.0); h.bias.mul_(8.0)
+    want = s.predict(model, None, 0.15, 0.45, 50, pre_loc_all=loc_all, pre_conf_all=conf_all)
+    before = s.launch_count()
+    got = s.predict(model, x, 0.15, 0.45, 50)
+    assert s.launch_count() == before + 2
+    assert sum(int(w["labels"].numel()) for w in want) > 0
+    for a, w in zip(got, want):
+        assert bit_equal(a["labels"], w["labels"]) and close(a["scores"], w["scores"]) and close(a["boxes"], w["boxes"], atol=BOX_ATOL)
+    # channels_last model: the heads come out NHWC and are read as rows
+    model_cl = model.to(memory_format=torch.channels_last)
+    x_cl = x.contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        loc_cl, conf_cl = model_cl(x_cl)
+        lh, ch = s.forward_heads(model_cl, x_cl)
+    assert all(h.is_contiguous(memory_format=torch.channels_last) for h in lh + ch)
+    want_cl = s.predict(model_cl, None, 0.15, 0.45, 50, pre_loc_all=loc_cl, pre_conf_all=conf_cl)
+    got_cl = s.predict(model_cl, x_cl, 0.15, 0.45, 50)
+    for a, w in zip(got_cl, want_cl):
+        assert bit_equal(a["labels"], w["labels"]) and close(a["scores"], w["scores"]) and close(a["boxes"], w["boxes"], atol=BOX_ATOL)
