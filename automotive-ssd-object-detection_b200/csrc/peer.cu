@@ -1,0 +1,142 @@
+// peer.cu -- the sharded path's one exchange as a kernel over NVLink peer memory.
+//
+// A training / evaluation step of the image-sharded path all-reduces three doubles, [sum smooth-L1, sum CE, sum
+// positives] (SSD_trainer.py:105,108,600).  A library collective for 24 bytes costs a host-side call per step that is
+// longer than the step's kernels (~93 us at B = 256) and cannot sit inside the step's CUDA graph on this stack.
+// peer_allreduce_kernel does the exchange itself: every rank owns a 512-byte mailbox in its own HBM, mapped into the
+// other ranks' address spaces through CUDA IPC (NVLink 5 / NVSwitch peer access).  One warp per rank:
+//   1. lane r stores this rank's three sums into slot [parity][rank] of rank r's mailbox (peer stores), fences, then
+//      stores the step's sequence number as the slot's tag;
+//   2. lane r polls slot [parity][r] of the OWN mailbox until its tag is the sequence number, then reads the sums;
+//   3. the world's sums are added in rank order (identical bits on every rank) and written back in place.
+// The sequence number lives in device memory and is advanced by the kernel, so the launch is a plain graph node that
+// can be replayed.  Two parities suffice: a rank can only reach step s+2 after every rank has finished reading step s
+// (stream order).  A rank that waits longer than ~2 s (a peer that never launched) raises bit 2 of dev_flags and
+// writes NaN instead of hanging the GPU.
+#include "common.cuh"
+
+namespace ssdhot {
+
+constexpr int kPeerMax = SSDHOT_PEER_MAX_RANKS;     // 8: one NVSwitch domain
+constexpr int kMailboxDoubles = 2 * kPeerMax * 4;    // [parity][rank][sum loc, sum CE, sum pos, tag]
+
+struct PeerSlots {
+    double* box[kPeerMax];      // box[r] = rank r's mailbox as mapped in THIS process (box[rank] = the local one)
+};
+
+__global__ void __launch_bounds__(32) peer_allreduce_kernel(double* __restrict__ sums, const PeerSlots ps, int rank, int world,
+                                                            unsigned long long* __restrict__ seq_counter, int32_t* __restrict__ flags) {
+    pdl_wait();                                     // (may be launched with PDL behind finalize_sums_kernel)
+    const int lane = threadIdx.x;
+    const unsigned long long seq = *seq_counter + 1ull;
+    const int par = (int)(seq & 1ull);
+    const double a = sums[0], c = sums[1], n = sums[2];
+    __syncwarp();
+    if (lane < world) {
+        double* q = ps.box[0];
+#pragma unroll
+        for (int i = 1; i < kPeerMax; ++i) if (lane == i) q = ps.box[i];
+        volatile double* dst = q + (par * kPeerMax + rank) * 4;
+        dst[0] = a; dst[1] = c; dst[2] = n;
+        __threadfence_system();
+        reinterpret_cast<volatile unsigned long long*>(dst)[3] = seq;
+    }
+    double ra = 0.0, rc = 0.0, rn = 0.0;
+    if (lane < world) {
+        double* mine = ps.box[0];
+#pragma unroll
+        for (int i = 1; i < kPeerMax; ++i) if (rank == i) mine = ps.box[i];
+        volatile double* src = mine + (par * kPeerMax + lane) * 4;
+        volatile unsigned long long* tag = reinterpret_cast<volatile unsigned long long*>(src) + 3;
+        const unsigned long long t0 = globaltimer_ns();
+        bool ok = true;
+        while (*tag != seq) {
+            if (globaltimer_ns() - t0 > 2000000000ull) { ok = false; break; }
+            __nanosleep(64);
+        }
+        __threadfence_system();
+        if (ok) { ra = src[0]; rc = src[1]; rn = src[2]; }
+        else {
+            if (flags) atomicOr(flags, 2);
+            ra = rc = rn = __longlong_as_double(0x7ff8000000000000ll);
+        }
+    }
+    double A = 0.0, C = 0.0, N = 0.0;               // rank order: the same additions on every rank
+    for (int r = 0; r < world; ++r) {
+        A += __shfl_sync(FULL, ra, r);
+        C += __shfl_sync(FULL, rc, r);
+        N += __shfl_sync(FULL, rn, r);
+    }
+    if (lane == 0) { sums[0] = A; sums[1] = C; sums[2] = N; *seq_counter = seq; }
+}
+
+}  // namespace ssdhot
+
+using namespace ssdhot;
+
+extern "C" unsigned long long ssdhot_peer_mailbox_bytes(void) { return (unsigned long long)kMailboxDoubles * sizeof(double) + 64; }
+
+// A mailbox (plus the sequence counter in its last 64 bytes) in this rank's HBM, zero-filled, from cudaMalloc so that it
+// can be exported with CUDA IPC.
+extern "C" int ssdhot_peer_alloc(void** mailbox_out) {
+    if (!mailbox_out) return SSDHOT_ERR_NULL;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)ssdhot_peer_mailbox_bytes());
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset(p, 0, (size_t)ssdhot_peer_mailbox_bytes());
+    if (e != cudaSuccess) { cudaFree(p); return (int)e; }
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(p); return (int)e; }
+    *mailbox_out = p;
+    return SSDHOT_OK;
+}
+extern "C" int ssdhot_peer_free(void* mailbox) {
+    if (!mailbox) return SSDHOT_OK;
+    cudaError_t e = cudaFree(mailbox);
+    return e == cudaSuccess ? SSDHOT_OK : (int)e;
+}
+// 64-byte CUDA IPC handle of a mailbox (HOST buffer), to be sent to the other ranks of the node.
+extern "C" int ssdhot_peer_export(const void* mailbox, void* handle64_host) {
+    if (!mailbox || !handle64_host) return SSDHOT_ERR_NULL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(mailbox));
+    if (e != cudaSuccess) return (int)e;
+    memcpy(handle64_host, &h, 64);
+    return SSDHOT_OK;
+}
+// Map another rank's mailbox (its exported handle) into this process; enables peer access over NVLink.
+extern "C" int ssdhot_peer_open(const void* handle64_host, void** mailbox_out) {
+    if (!handle64_host || !mailbox_out) return SSDHOT_ERR_NULL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64_host, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return (int)e;
+    *mailbox_out = p;
+    return SSDHOT_OK;
+}
+extern "C" int ssdhot_peer_close(void* mapped_mailbox) {
+    if (!mapped_mailbox) return SSDHOT_OK;
+    cudaError_t e = cudaIpcCloseMemHandle(mapped_mailbox);
+    return e == cudaSuccess ? SSDHOT_OK : (int)e;
+}
+
+// All-reduce (sum) sums[3] in place across the `world` ranks whose mailboxes are mailboxes_host[0..world) (HOST array
+// of DEVICE pointers as mapped in this process; entry `rank` is the local mailbox).  Asynchronous on `stream`,
+// capturable in a CUDA graph.  Every rank must call it the same number of times.
+extern "C" int ssdhot_allreduce_sums_peer(double* sums, void* const* mailboxes_host, int rank, int world, int32_t* dev_flags,
+                                          ssdhot_stream_t stream) {
+    if (!sums || !mailboxes_host) return SSDHOT_ERR_NULL;
+    if (world < 1 || world > kPeerMax || rank < 0 || rank >= world) return SSDHOT_ERR_SHAPE;
+    PeerSlots ps = {};
+    for (int r = 0; r < world; ++r) {
+        if (!mailboxes_host[r]) return SSDHOT_ERR_NULL;
+        ps.box[r] = reinterpret_cast<double*>(mailboxes_host[r]);
+    }
+    unsigned long long* seq = reinterpret_cast<unsigned long long*>(ps.box[rank] + kMailboxDoubles);
+    cudaError_t e = launch_pdl(peer_allreduce_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, sums, ps, rank, world, seq, dev_flags);
+    ++g_launches;
+    if (e != cudaSuccess) return (int)e;
+    return SSDHOT_OK;
+}

@@ -48,6 +48,13 @@ PROTOTYPES = {
     "ssdhot_multibox_loss_heads_fwd": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, vp, vp, i32, i32,
                                              f32, f32, f32, f64, vp, vp, vp, vp, vp, vp, vp]),
     "ssdhot_multibox_loss_heads_bwd": (i32, [vp, vp, vp, i32, f32, f32, vp, vp, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp]),
+    "ssdhot_peer_mailbox_bytes": (u64, []),
+    "ssdhot_peer_alloc": (i32, [vp]),
+    "ssdhot_peer_free": (i32, [vp]),
+    "ssdhot_peer_export": (i32, [vp, vp]),
+    "ssdhot_peer_open": (i32, [vp, vp]),
+    "ssdhot_peer_close": (i32, [vp]),
+    "ssdhot_allreduce_sums_peer": (i32, [vp, vp, i32, i32, vp, vp]),
 }
 
 

@@ -217,7 +217,7 @@ class _FusedLoss(torch.autograd.Function):
         _lib.check(rc, "ssdhot_multibox_loss_fwd")
         if group is not None:
             # the only exchange of the sharded path: [sum smooth-L1, sum CE, sum positives]
-            _dist.combine_sums(sums, None if group is True else group)
+            _dist.reduce_sums(sums, group)
         total = sums[2].clamp_min(1.0)
         if need_grad:
             ctx.save_for_backward(loc, conf, sel, matched, total, packed.boxes, packed.offsets)
@@ -542,7 +542,7 @@ class _FusedLossHeads(torch.autograd.Function):
         for t in keep:
             t.record_stream(torch.cuda.current_stream(dev))
         if group is not None:
-            _dist.combine_sums(sums, None if group is True else group)
+            _dist.reduce_sums(sums, group)
         total = sums[2].clamp_min(1.0)
         if need_grad:
             ctx.save_for_backward(sel, matched, total, packed.boxes, packed.offsets, *keep)

@@ -39,7 +39,8 @@ class HotPathStep:
         self.norm_wh = (float(norm_wh[0]), float(norm_wh[1]))
         self.train_half, self.infer_half = train_half, infer_half
         self.concurrent, self._fork = bool(concurrent), None
-        self.group = group          # process group (True = default) whose ranks share the batch: sums are all-reduced in run()
+        self.group = group          # ranks that share the batch: a torch.distributed group (True = default) or a dist.PeerSums;
+                                    # the three sums are all-reduced inside run()
         dev = priors.device
         L = _lib.lib()
         self.sums = torch.zeros((3,), dtype=torch.float64, device=dev)
@@ -144,12 +145,12 @@ class HotPathStep:
 
     def _reduce(self) -> None:
         """The sharded path's only exchange: all-reduce [sum smooth-L1, sum CE, sum positives] in place."""
-        if self.group is not None:
-            _dist.combine_sums(self.sums, None if self.group is True else self.group)
+        if self.group is not None:                      # (a PeerSums is one kernel and becomes part of the step's CUDA graph)
+            _dist.reduce_sums(self.sums, self.group)
 
     def losses(self, group=None):
         """(loc_loss, conf_loss) of the last run; all-reduces the three sums first when sharded."""
         sums = self.sums.clone()
         if group is not None:
-            _dist.combine_sums(sums, None if group is True else group)
+            _dist.reduce_sums(sums, group)
         return _dist.losses_from_sums(sums)

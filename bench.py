@@ -226,6 +226,8 @@ def main():
     ap.add_argument("--impl", default="ssdhot", choices=["ssdhot", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying a CUDA graph")
     ap.add_argument("--serial", action="store_true", help="run the two halves back to back on one stream instead of forked")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: all-reduce of the three loss sums by the peer-memory kernel (in the CUDA graph) or by NCCL")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-large-batch", action="store_true", help="skip the extra B=2048 roofline measurement")
     args = ap.parse_args()
@@ -257,17 +259,36 @@ def main():
         sets.append(dict(loc=cfg["loc_all"].to(dev), conf_t=cfg["conf_train"].to(dev), conf_i=cfg["conf_infer"].to(dev),
                          gt=ssdhot.pack_targets(cfg["targets"], dev)))
     ps = ssdhot.PriorSet.default(dev)
+    # the sharded path's one exchange: every step's [sum loc, sum CE, sum positives] is all-reduced.  Default: the peer-memory
+    # kernel (csrc/peer.cu) as a node of the step's CUDA graph; --collective nccl (or a box without CUDA IPC between the
+    # ranks): torch.distributed all-reduce on a side stream, outside the graph (a captured NCCL collective hung at process
+    # exit on this stack)
+    peer, reducer, collective = None, None, "none"
+    if group is not None:
+        if args.collective == "peer":
+            try:
+                peer = D.PeerSums(dev)
+                collective = "peer-memory kernel over NVLink (ssdhot_allreduce_sums_peer), inside the step's CUDA graph"
+            except Exception as e:              # noqa: BLE001
+                print(f"[bench] rank {rank}: PeerSums unavailable ({e}); using NCCL", file=sys.stderr)
+        ok = torch.tensor([1 if (peer is not None or args.collective != "peer") else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if args.collective == "peer" and int(ok.item()) == 0:
+            if peer is not None:
+                peer.close()
+            peer = None
+        if peer is None:
+            reducer = D.SumsReducer(dev)
+            collective = "NCCL all-reduce (torch.distributed) on a side stream, outside the CUDA graph"
     step = HotPathStep(ps, BATCH, C, spec["iou_thresh"], spec["ratio"], spec["score_thresh"], spec["nms_thresh"],
-                       spec["max_per_img"], concurrent=not args.serial)
+                       spec["max_per_img"], concurrent=not args.serial, group=peer)
     use_graph = not args.no_graph
-    reducer = D.SumsReducer(dev) if group is not None else None
 
     def one_step(i):
         s = sets[i % N_SETS]
         step.run(s["loc"], s["conf_t"], s["conf_i"], s["gt"], use_graph=use_graph)
         if reducer is not None:
-            reducer.submit(step.sums)       # every step's [sum loc, sum CE, sum positives] is all-reduced, on a side stream
-                                            # (outside the graph: a captured NCCL collective hung at process exit on this stack)
+            reducer.submit(step.sums)
 
     def barrier():
         if world > 1:
@@ -467,7 +488,8 @@ def main():
         loc = h["loc"].to(dev, non_blocking=True)
         conf_t = h["conf_t"].to(dev, non_blocking=True)
         conf_i = h["conf_i"].to(dev, non_blocking=True)
-        l_loc, l_conf = ssdhot.multibox_loss(ps, loc, conf_t, h["targets"], spec["iou_thresh"], spec["ratio"], group=group)
+        l_loc, l_conf = ssdhot.multibox_loss(ps, loc, conf_t, h["targets"], spec["iou_thresh"], spec["ratio"],
+                                             group=peer if peer is not None else group)
         labels, scores, boxes, count = ssdhot.predict_padded(ps, loc, conf_i, spec["score_thresh"], spec["nms_thresh"],
                                                              spec["max_per_img"])
         out = (torch.stack((l_loc, l_conf)).cpu(), labels.cpu(), scores.cpu(), boxes.cpu(), count.cpu())
@@ -513,7 +535,7 @@ def main():
                        "global_batch": BATCH * world, "per_gpu_batch": BATCH,
                        "l2": f"inputs rotate over {N_SETS} sets of 89.5 MB (> 126 MB L2) so no step re-reads a warm L2",
                        "cuda_graph": use_graph, "halves": "serial" if args.serial else "forked (independent halves on two streams)",
-                       "parallelism": f"image-sharded x{world}, all-reduce of 3 doubles per step" + (" on a side stream" if world > 1 else "")},
+                       "parallelism": f"image-sharded x{world}, all-reduce of 3 doubles per step" + (f": {collective}" if world > 1 else "")},
             "parts": {"match_loss_images_per_s": BATCH * world / (ms_loss * 1e-3),
                       "decode_nms_images_per_s": BATCH * world / (ms_pred * 1e-3)},
             "roofline": roofline,
@@ -527,6 +549,11 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
+        if peer is not None:
+            if peer.timed_out():
+                print(f"[bench] rank {rank}: a peer all-reduce timed out", file=sys.stderr)
+            dist.barrier()
+            peer.close()
         dist.destroy_process_group()
 
 

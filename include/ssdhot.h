@@ -253,6 +253,26 @@ SSDHOT_API int ssdhot_multibox_loss_heads_bwd(const float* priors_cxcywh, const 
                          float* const* grad_loc_heads_host, float* const* grad_conf_heads_host,
                          ssdhot_stream_t stream);
 
+/* ---- e: the sharded path's exchange over NVLink peer memory -----------------------------------------------------
+ * The only collective of the image-sharded path is the all-reduce (sum) of sums[3] = [sum smooth-L1, sum CE, sum
+ * positives] (SSD_trainer.py:105,108,600).  ssdhot_allreduce_sums_peer does it in ONE 32-thread kernel over peer
+ * memory: every rank owns a mailbox (ssdhot_peer_alloc) that the other ranks of the node map through CUDA IPC
+ * (ssdhot_peer_export on the owner, ssdhot_peer_open on the others; the 64-byte handles travel over any host channel,
+ * e.g. torch.distributed.all_gather).  The kernel stores this rank's sums into every mailbox, waits for the others'
+ * and adds them in rank order, so all ranks end with identical bits; it keeps its step counter in device memory and can
+ * therefore be captured in a CUDA graph and replayed.  mailboxes_host: HOST array of `world` DEVICE pointers as mapped
+ * in the calling process (entry `rank` = the local mailbox).  Every rank must issue the same number of calls; a rank
+ * that waits more than ~2 s sets bit 2 of *dev_flags (if given) and produces NaN.  world <= SSDHOT_PEER_MAX_RANKS. */
+#define SSDHOT_PEER_MAX_RANKS 8
+SSDHOT_API unsigned long long ssdhot_peer_mailbox_bytes(void);
+SSDHOT_API int ssdhot_peer_alloc(void** mailbox_out);
+SSDHOT_API int ssdhot_peer_free(void* mailbox);
+SSDHOT_API int ssdhot_peer_export(const void* mailbox, void* handle64_host);
+SSDHOT_API int ssdhot_peer_open(const void* handle64_host, void** mailbox_out);
+SSDHOT_API int ssdhot_peer_close(void* mapped_mailbox);
+SSDHOT_API int ssdhot_allreduce_sums_peer(double* sums, void* const* mailboxes_host, int rank, int world, int32_t* dev_flags,
+                               ssdhot_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

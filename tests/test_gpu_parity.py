@@ -741,3 +741,77 @@ def test_predict_images_goes_through_the_heads(env):
     got_cl = s.predict(model_cl, x_cl, 0.15, 0.45, 50)
     for a, w in zip(got_cl, want_cl):
         assert bit_equal(a["labels"], w["labels"]) and close(a["scores"], w["scores"]) and close(a["boxes"], w["boxes"], atol=BOX_ATOL)
+
+
+def test_peer_allreduce_protocol_virtual_ranks(env):
+    """ssdhot_allreduce_sums_peer (csrc/peer.cu) with three ranks inside this process, one stream each, sharing their
+    mailboxes directly (no IPC): 60 back-to-back steps, eager and replayed from CUDA graphs, always give the sum in rank
+    order on every rank -- sequence tags, parity double-buffering and the in-place result all exercised."""
+    s, dev = env["ssdhot"], env["dev"]
+    from ssdhot.dist import PeerSums
+    world, steps = 3, 60
+    ranks = PeerSums.virtual(world, dev)
+    streams = [torch.cuda.Stream(dev) for _ in range(world)]
+    gen = torch.Generator().manual_seed(4)
+    vals = torch.rand((steps, world, 3), generator=gen, dtype=torch.float64) * 1e3
+    want = vals[:, 0, :].clone()
+    for r in range(1, world):
+        want = want + vals[:, r, :]                                   # rank order
+    dvals = vals.to(dev)
+    bufs = [torch.zeros((3,), dtype=torch.float64, device=dev) for _ in range(world)]
+    outs = [torch.zeros((steps, 3), dtype=torch.float64, device=dev) for _ in range(world)]
+    torch.cuda.synchronize(dev)
+    before = s.launch_count()
+    for i in range(steps):
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                bufs[r].copy_(dvals[i, r])
+                ranks[r].allreduce(bufs[r])
+                outs[r][i].copy_(bufs[r])
+    torch.cuda.synchronize(dev)
+    assert s.launch_count() == before + steps * world
+    for r in range(world):
+        assert not ranks[r].timed_out()
+        assert bit_equal(outs[r], want), r
+    # the same from CUDA graphs (one per rank), replayed in a skewed order
+    graphs = []
+    for r in range(world):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(streams[r]):
+            streams[r].synchronize()
+            with torch.cuda.graph(g, stream=streams[r]):
+                bufs[r].mul_(2.0)
+                ranks[r].allreduce(bufs[r])
+        graphs.append(g)
+    torch.cuda.synchronize(dev)
+    for r in range(world):
+        bufs[r].copy_(dvals[0, r])
+    expect = [want[0].clone()]
+    torch.cuda.synchronize(dev)
+    for it in range(5):
+        for r in (2, 0, 1):
+            with torch.cuda.stream(streams[r]):
+                graphs[r].replay()
+        torch.cuda.synchronize(dev)
+        # every rank doubled its buffer, then all-reduced: buf_r(new) = sum_r 2 * buf_r(old); all ranks hold the same value
+        if it == 0:
+            cur = 2.0 * dvals[0, 0].cpu()
+            for r in range(1, world):
+                cur = cur + 2.0 * dvals[0, r].cpu()
+        else:
+            prev = cur
+            cur = 2.0 * prev
+            for r in range(1, world):
+                cur = cur + 2.0 * prev
+        for r in range(world):
+            assert bit_equal(bufs[r], cur), (it, r)
+    assert not any(p.timed_out() for p in ranks)
+    # a lone rank (world 1) is the identity
+    solo = PeerSums.virtual(1, dev)[0]
+    x = torch.tensor([1.5, 2.5, 3.0], dtype=torch.float64, device=dev)
+    solo.allreduce(x)
+    assert bit_equal(x, torch.tensor([1.5, 2.5, 3.0], dtype=torch.float64))
+    solo.close()
+    for p in ranks[1:]:
+        p.close()
+    ranks[0].close()
