@@ -3,33 +3,39 @@
 // A training / evaluation step of the image-sharded path all-reduces three doubles, [sum smooth-L1, sum CE, sum
 // positives] (SSD_trainer.py:105,108,600).  A library collective for 24 bytes costs a host-side call per step that is
 // longer than the step's kernels (~93 us at B = 256) and cannot sit inside the step's CUDA graph on this stack.
-// peer_allreduce_kernel does the exchange itself: every rank owns a 512-byte mailbox in its own HBM, mapped into the
+// peer_allreduce_kernel does the exchange itself: every rank owns a 1 KB mailbox in its own HBM, mapped into the
 // other ranks' address spaces through CUDA IPC (NVLink 5 / NVSwitch peer access).  One warp per rank:
-//   1. lane r stores this rank's three sums into slot [parity][rank] of rank r's mailbox (peer stores), fences, then
-//      stores the step's sequence number as the slot's tag;
-//   2. lane r polls slot [parity][r] of the OWN mailbox until its tag is the sequence number, then reads the sums;
+//   1. lane r stores this rank's three sums into slot [generation][rank] of rank r's mailbox (peer stores), fences,
+//      then stores the step's sequence number as the slot's tag;
+//   2. lane r polls slot [generation][r] of the OWN mailbox until its tag is the sequence number, then reads the sums;
 //   3. the world's sums are added in rank order (identical bits on every rank) and written back in place.
 // The sequence number lives in device memory and is advanced by the kernel, so the launch is a plain graph node that
-// can be replayed.  Two parities suffice: a rank can only reach step s+2 after every rank has finished reading step s
-// (stream order).  A rank that waits longer than ~2 s (a peer that never launched) raises bit 2 of dev_flags and
-// writes NaN instead of hanging the GPU.
+// can be replayed.  A rank that waits longer than ~10 s (a peer that never launched) raises bit 2 of dev_flags and
+// writes NaN instead of hanging the GPU; later calls then do not wait at all.
+// lag = 1 delivers the reduced sums of the PREVIOUS call instead (zeros on the first call): step 2 then collects slots
+// that were posted a whole step earlier, so it practically never waits and the ranks are not re-synchronised every step
+// (they may drift one step apart) -- the overlap a side-stream collective gives, without the host work.
+// Four slot generations (seq mod 4): a rank can be at most one call ahead of the slowest reader of its slots (it needs
+// every peer's post of call s to finish call s + lag), so the generation it overwrites was read at least two calls ago.
 #include "common.cuh"
 
 namespace ssdhot {
 
 constexpr int kPeerMax = SSDHOT_PEER_MAX_RANKS;     // 8: one NVSwitch domain
-constexpr int kMailboxDoubles = 2 * kPeerMax * 4;    // [parity][rank][sum loc, sum CE, sum pos, tag]
+constexpr int kGenerations = 4;
+constexpr unsigned long long kPeerTimeoutNs = 10000000000ull;   // 10 s: ranks of one job are expected to arrive far closer together
+constexpr int kMailboxDoubles = kGenerations * kPeerMax * 4;    // [generation][rank][sum loc, sum CE, sum pos, tag]
 
 struct PeerSlots {
     double* box[kPeerMax];      // box[r] = rank r's mailbox as mapped in THIS process (box[rank] = the local one)
 };
 
-__global__ void __launch_bounds__(32) peer_allreduce_kernel(double* __restrict__ sums, const PeerSlots ps, int rank, int world,
+__global__ void __launch_bounds__(32) peer_allreduce_kernel(double* __restrict__ sums, const PeerSlots ps, int rank, int world, int lag,
                                                             unsigned long long* __restrict__ seq_counter, int32_t* __restrict__ flags) {
     pdl_wait();                                     // (may be launched with PDL behind finalize_sums_kernel)
     const int lane = threadIdx.x;
     const unsigned long long seq = *seq_counter + 1ull;
-    const int par = (int)(seq & 1ull);
+    const int par = (int)(seq % kGenerations);
     const double a = sums[0], c = sums[1], n = sums[2];
     __syncwarp();
     if (lane < world) {
@@ -42,16 +48,19 @@ __global__ void __launch_bounds__(32) peer_allreduce_kernel(double* __restrict__
         reinterpret_cast<volatile unsigned long long*>(dst)[3] = seq;
     }
     double ra = 0.0, rc = 0.0, rn = 0.0;
-    if (lane < world) {
+    const unsigned long long want = seq - (unsigned long long)lag;       // the call whose sums are delivered now
+    const int wpar = (int)(want % kGenerations);
+    if (lane < world && want > 0ull) {
         double* mine = ps.box[0];
 #pragma unroll
         for (int i = 1; i < kPeerMax; ++i) if (rank == i) mine = ps.box[i];
-        volatile double* src = mine + (par * kPeerMax + lane) * 4;
+        volatile double* src = mine + (wpar * kPeerMax + lane) * 4;
         volatile unsigned long long* tag = reinterpret_cast<volatile unsigned long long*>(src) + 3;
         const unsigned long long t0 = globaltimer_ns();
         bool ok = true;
-        while (*tag != seq) {
-            if (globaltimer_ns() - t0 > 2000000000ull) { ok = false; break; }
+        const bool gave_up_before = flags && (*reinterpret_cast<volatile int32_t*>(flags) & 2);    // then do not wait again
+        while (*tag != want) {
+            if (gave_up_before || globaltimer_ns() - t0 > kPeerTimeoutNs) { ok = false; break; }
             __nanosleep(64);
         }
         __threadfence_system();
@@ -123,19 +132,21 @@ extern "C" int ssdhot_peer_close(void* mapped_mailbox) {
 }
 
 // All-reduce (sum) sums[3] in place across the `world` ranks whose mailboxes are mailboxes_host[0..world) (HOST array
-// of DEVICE pointers as mapped in this process; entry `rank` is the local mailbox).  Asynchronous on `stream`,
-// capturable in a CUDA graph.  Every rank must call it the same number of times.
-extern "C" int ssdhot_allreduce_sums_peer(double* sums, void* const* mailboxes_host, int rank, int world, int32_t* dev_flags,
+// of DEVICE pointers as mapped in this process; entry `rank` is the local mailbox).  lag = 0: the sums of this call;
+// lag = 1: the reduced sums of the previous call (zeros on the first).  Asynchronous on `stream`, capturable in a CUDA
+// graph.  Every rank must call it the same number of times with the same lag.
+extern "C" int ssdhot_allreduce_sums_peer(double* sums, void* const* mailboxes_host, int rank, int world, int lag, int32_t* dev_flags,
                                           ssdhot_stream_t stream) {
     if (!sums || !mailboxes_host) return SSDHOT_ERR_NULL;
     if (world < 1 || world > kPeerMax || rank < 0 || rank >= world) return SSDHOT_ERR_SHAPE;
+    if (lag != 0 && lag != 1) return SSDHOT_ERR_VALUE;
     PeerSlots ps = {};
     for (int r = 0; r < world; ++r) {
         if (!mailboxes_host[r]) return SSDHOT_ERR_NULL;
         ps.box[r] = reinterpret_cast<double*>(mailboxes_host[r]);
     }
     unsigned long long* seq = reinterpret_cast<unsigned long long*>(ps.box[rank] + kMailboxDoubles);
-    cudaError_t e = launch_pdl(peer_allreduce_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, sums, ps, rank, world, seq, dev_flags);
+    cudaError_t e = launch_pdl(peer_allreduce_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, sums, ps, rank, world, lag, seq, dev_flags);
     ++g_launches;
     if (e != cudaSuccess) return (int)e;
     return SSDHOT_OK;

@@ -97,14 +97,16 @@ class SumsReducer:
 
 class PeerSums:
     """The sharded path's exchange as ONE kernel over NVLink peer memory (csrc/peer.cu, ssdhot_allreduce_sums_peer):
-    every rank owns a 512-byte mailbox that the other ranks map through CUDA IPC; `allreduce(sums)` stores this rank's
+    every rank owns a 1 KB mailbox that the other ranks map through CUDA IPC; `allreduce(sums)` stores this rank's
     three sums into every mailbox, waits for the others' and adds them in rank order.  Unlike a library collective it
     costs no host work beyond one kernel launch and can be captured in the step's CUDA graph (HotPathStep(group=PeerSums)).
     All ranks of `group` must sit on one node (one NVSwitch domain, at most 8 ranks) and call allreduce the same number
-    of times."""
+    of times.  lag=1: allreduce delivers the reduced sums of the PREVIOUS call (zeros on the first), which were posted a
+    step earlier -- no waiting, no per-step re-synchronisation of the ranks; call it once more at the end for the last step."""
 
-    def __init__(self, device, group=None, _virtual=None):
+    def __init__(self, device, group=None, lag: int = 0, _virtual=None):
         import ctypes
+        self.lag = int(lag)
         from . import _lib
         self._lib, self._ct = _lib, ctypes
         L = _lib.lib()
@@ -144,7 +146,7 @@ class PeerSums:
         self._boxes_ptr = ctypes.cast(self._boxes, ctypes.c_void_p)
 
     @classmethod
-    def virtual(cls, world: int, device):
+    def virtual(cls, world: int, device, lag: int = 0):
         """`world` ranks inside ONE process on one GPU (each to be driven from its own stream): the protocol without IPC."""
         import ctypes
         from . import _lib
@@ -154,7 +156,7 @@ class PeerSums:
                 p = ctypes.c_void_p()
                 _lib.check(_lib.lib().ssdhot_peer_alloc(ctypes.byref(p)), "ssdhot_peer_alloc")
                 boxes.append(p.value)
-        ranks = [cls(device, _virtual=(r, world, boxes)) for r in range(world)]
+        ranks = [cls(device, lag=lag, _virtual=(r, world, boxes)) for r in range(world)]
         ranks[0]._virtual_boxes = boxes                 # freed by ranks[0].close()
         return ranks
 
@@ -166,7 +168,7 @@ class PeerSums:
             stream = torch.cuda.current_stream(sums.device).cuda_stream
         with torch.cuda.device(self.device):
             rc = self._lib.lib().ssdhot_allreduce_sums_peer(sums.data_ptr(), self._boxes_ptr, self.rank, self.world,
-                                                            self.flags.data_ptr(), stream)
+                                                            self.lag, self.flags.data_ptr(), stream)
         self._lib.check(rc, "ssdhot_allreduce_sums_peer")
         return sums
 

@@ -228,6 +228,8 @@ def main():
     ap.add_argument("--serial", action="store_true", help="run the two halves back to back on one stream instead of forked")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N > 1: all-reduce of the three loss sums by the peer-memory kernel (in the CUDA graph) or by NCCL")
+    ap.add_argument("--collective-lag", type=int, default=1, choices=[0, 1],
+                    help="peer collective: 0 = each step waits for its own reduced sums, 1 = they arrive during the next step")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-large-batch", action="store_true", help="skip the extra B=2048 roofline measurement")
     args = ap.parse_args()
@@ -267,8 +269,10 @@ def main():
     if group is not None:
         if args.collective == "peer":
             try:
-                peer = D.PeerSums(dev)
-                collective = "peer-memory kernel over NVLink (ssdhot_allreduce_sums_peer), inside the step's CUDA graph"
+                peer = D.PeerSums(dev, lag=args.collective_lag)
+                collective = ("peer-memory kernel over NVLink (ssdhot_allreduce_sums_peer), inside the step's CUDA graph" +
+                              ("; the reduced sums of step s are delivered during step s+1 (lag 1), so the ranks are not "
+                               "re-synchronised every step" if args.collective_lag else ""))
             except Exception as e:              # noqa: BLE001
                 print(f"[bench] rank {rank}: PeerSums unavailable ({e}); using NCCL", file=sys.stderr)
         ok = torch.tensor([1 if (peer is not None or args.collective != "peer") else 0], device=dev)
@@ -474,6 +478,7 @@ def main():
         torch.cuda.empty_cache()
     roofline["large_batch"] = large
 
+    barrier()       # (rank 0 alone measured the extra sections above; the e2e steps below exchange sums again)
     # ---- end to end through the drop-in API, host buffers ------------------------------------------
     pinned = []
     for cfg in host_sets[:2]:

@@ -261,8 +261,11 @@ SSDHOT_API int ssdhot_multibox_loss_heads_bwd(const float* priors_cxcywh, const 
  * e.g. torch.distributed.all_gather).  The kernel stores this rank's sums into every mailbox, waits for the others'
  * and adds them in rank order, so all ranks end with identical bits; it keeps its step counter in device memory and can
  * therefore be captured in a CUDA graph and replayed.  mailboxes_host: HOST array of `world` DEVICE pointers as mapped
- * in the calling process (entry `rank` = the local mailbox).  Every rank must issue the same number of calls; a rank
- * that waits more than ~2 s sets bit 2 of *dev_flags (if given) and produces NaN.  world <= SSDHOT_PEER_MAX_RANKS. */
+ * in the calling process (entry `rank` = the local mailbox).  lag = 0: sums becomes the all-reduced sums of this call.
+ * lag = 1: sums becomes the all-reduced sums of the PREVIOUS call (zeros on the first call) -- the slots it collects were
+ * posted a step earlier, so the kernel does not wait and the ranks are not re-synchronised every step.  Every rank must
+ * issue the same number of calls with the same lag; a rank that waits more than ~10 s sets bit 2 of *dev_flags (if given)
+ * and produces NaN.  world <= SSDHOT_PEER_MAX_RANKS. */
 #define SSDHOT_PEER_MAX_RANKS 8
 SSDHOT_API unsigned long long ssdhot_peer_mailbox_bytes(void);
 SSDHOT_API int ssdhot_peer_alloc(void** mailbox_out);
@@ -270,7 +273,7 @@ SSDHOT_API int ssdhot_peer_free(void* mailbox);
 SSDHOT_API int ssdhot_peer_export(const void* mailbox, void* handle64_host);
 SSDHOT_API int ssdhot_peer_open(const void* handle64_host, void** mailbox_out);
 SSDHOT_API int ssdhot_peer_close(void* mapped_mailbox);
-SSDHOT_API int ssdhot_allreduce_sums_peer(double* sums, void* const* mailboxes_host, int rank, int world, int32_t* dev_flags,
+SSDHOT_API int ssdhot_allreduce_sums_peer(double* sums, void* const* mailboxes_host, int rank, int world, int lag, int32_t* dev_flags,
                                ssdhot_stream_t stream);
 
 #ifdef __cplusplus

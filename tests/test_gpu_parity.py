@@ -806,6 +806,23 @@ def test_peer_allreduce_protocol_virtual_ranks(env):
         for r in range(world):
             assert bit_equal(bufs[r], cur), (it, r)
     assert not any(p.timed_out() for p in ranks)
+    # lag = 1: call i delivers the reduced sums of call i - 1 (zeros first); the ranks may run a call apart
+    lagged = PeerSums.virtual(world, dev, lag=1)
+    outs = [torch.full((steps, 3), -1.0, dtype=torch.float64, device=dev) for _ in range(world)]
+    for i in range(steps):
+        for r in ((0, 1, 2) if i % 2 == 0 else (2, 1, 0)):
+            with torch.cuda.stream(streams[r]):
+                bufs[r].copy_(dvals[i, r])
+                lagged[r].allreduce(bufs[r])
+                outs[r][i].copy_(bufs[r])
+    torch.cuda.synchronize(dev)
+    shifted = torch.cat((torch.zeros((1, 3), dtype=torch.float64), want[:-1]), 0)
+    for r in range(world):
+        assert not lagged[r].timed_out()
+        assert bit_equal(outs[r], shifted), r
+    for p in lagged[1:]:
+        p.close()
+    lagged[0].close()
     # a lone rank (world 1) is the identity
     solo = PeerSums.virtual(1, dev)[0]
     x = torch.tensor([1.5, 2.5, 3.0], dtype=torch.float64, device=dev)

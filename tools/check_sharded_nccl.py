@@ -34,6 +34,14 @@ for _ in range(3):
 torch.cuda.synchronize(dev)
 peer_rel = max(((p - sums).abs() / sums.abs().clamp_min(1e-300)).max().item() for p in peer_sums) if peer_sums else 0.0
 peer_ok = peer is None or (peer_rel <= 1e-12 and not peer.timed_out())
+if peer is not None:                              # lag 1: the second call delivers the first call's reduced sums
+    lagged = D.PeerSums(dev, lag=1)
+    first = lagged.allreduce(sums.clone() * 0 + (rank + 1.0))
+    second = lagged.allreduce(torch.zeros_like(sums))
+    torch.cuda.synchronize(dev)
+    peer_ok = peer_ok and bool((first == 0).all()) and bool((second == world * (world + 1) / 2.0).all()) and not lagged.timed_out()
+    dist.barrier()
+    lagged.close()
 out = {"world": world, "images": per_rank * world, "loc_loss": l_loc.item(), "conf_loss": l_conf.item(), "sums": sums.tolist()}
 if rank == 0:
     f_loc, f_conf, f_sums = ssdhot.multibox_loss(ps, cfg["loc_all"].to(dev), cfg["conf_train"].to(dev), cfg["targets"],
