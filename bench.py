@@ -59,7 +59,7 @@ class ClockSampler(threading.Thread):
                   "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     SMI_NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
-    def __init__(self, index: int, period_s: float = 0.001):
+    def __init__(self, index: int, period_s: float = 0.005):
         super().__init__(daemon=True)
         self.index, self.period, self.samples, self.reasons, self.stop_flag = index, period_s, [], set(), False
         self.max_mhz, self.nv, self.smi, self.err = None, None, None, None
@@ -123,7 +123,8 @@ class ClockSampler(threading.Thread):
         self.stop_flag = True
         source = "nvml"
         if self.nv is not None:
-            self.join(timeout=2.0)
+            if self.ident is not None:
+                self.join(timeout=2.0)
         elif self.smi is not None:
             source = "nvidia-smi -lms 10"
             time.sleep(0.05)
@@ -230,6 +231,7 @@ def main():
                     help="N > 1: all-reduce of the three loss sums by the peer-memory kernel (in the CUDA graph) or by NCCL")
     ap.add_argument("--collective-lag", type=int, default=1, choices=[0, 1],
                     help="peer collective: 0 = each step waits for its own reduced sums, 1 = they arrive during the next step")
+    ap.add_argument("--quick", action="store_true", help="diagnostics: only the main timed loop (no halves, roofline, heads, e2e)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-large-batch", action="store_true", help="skip the extra B=2048 roofline measurement")
     args = ap.parse_args()
@@ -310,7 +312,8 @@ def main():
         one_step(i)
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    if not os.environ.get("BENCH_NO_SAMPLER"):
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -319,9 +322,24 @@ def main():
     barrier()
     clocks = sampler.result()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    per_rank_ms = [float(ms.item())]
     if world > 1:
+        every = [torch.zeros_like(ms) for _ in range(world)]
+        dist.all_gather(every, ms)
+        per_rank_ms = [float(t.item()) for t in every]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "n_gpus": world, "value": BATCH * world * args.steps / (ms_total / 1e3),
+                              "ms_per_step": ms_total / args.steps, "per_rank_ms_per_step": [t / args.steps for t in per_rank_ms],
+                              "collective": collective, "clocks": clocks}))
+        if world > 1:
+            dist.barrier()
+            if peer is not None:
+                peer.close()
+            dist.destroy_process_group()
+        return
     ms_per_step = ms_total / args.steps
     value = BATCH * world * args.steps / (ms_total / 1e3)
 
@@ -550,6 +568,7 @@ def main():
                     "d2h_bytes_per_step": d2h_holder.get("bytes", 0), "steps": e2e_steps,
                     "api": "ssdhot.multibox_loss + ssdhot.predict_padded from pinned host tensors"},
             "gpu_launches": launches_per_step * args.steps,
+            "per_rank_ms_per_step": [t / args.steps for t in per_rank_ms],
             "clocks": clocks,
         }
         print(json.dumps(line))
