@@ -310,11 +310,15 @@ def main():
 
     for i in range(args.warmup):
         one_step(i)
+    sampler = ClockSampler(local)           # (opens NVML: slow and uneven across ranks, so before the barrier)
     barrier()
-    sampler = ClockSampler(local)
     if not os.environ.get("BENCH_NO_SAMPLER"):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        # device-side rendezvous: the ranks leave the host barrier milliseconds apart, and a rank whose timed region
+        # started early would spend that skew waiting for its peers' first sums inside the region
+        dist.all_reduce(torch.zeros((1,), device=dev))
     e0.record()
     for i in range(args.steps):
         one_step(i)
