@@ -59,7 +59,7 @@ class ClockSampler(threading.Thread):
                   "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     SMI_NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
-    def __init__(self, index: int, period_s: float = 0.005):
+    def __init__(self, index: int, period_s: float = 0.002):
         super().__init__(daemon=True)
         self.index, self.period, self.samples, self.reasons, self.stop_flag = index, period_s, [], set(), False
         self.max_mhz, self.nv, self.smi, self.err = None, None, None, None

@@ -5,8 +5,9 @@ for p in (ROOT, os.path.join(ROOT, "automotive-ssd-object-detection_b200")):
     sys.path.insert(0, p)
 import torch, ssdhot
 from ssdhot import synth
-from ssdhot.engine import HotPathStep
+from ssdhot.engine import HeadSet, HotPathStep
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+source = sys.argv[2] if len(sys.argv) > 2 else "packed"          # packed | nchw | nhwc
 dev = torch.device("cuda:0")
 cfg = synth.config(3, batch=batch)
 ps = ssdhot.PriorSet.default(dev)
@@ -14,12 +15,18 @@ loc, ct = cfg["loc_all"].to(dev), cfg["conf_train"].to(dev)
 gt = ssdhot.pack_targets(cfg["targets"], dev)
 step = HotPathStep(ps, batch, 6, cfg["iou_thresh"], cfg["ratio"])
 st = torch.cuda.current_stream(dev).cuda_stream
-for _ in range(3): step.launch_loss(loc, ct, gt, st)
+if source != "packed":
+    heads = HeadSet(synth.heads_from_packed(loc, source == "nhwc"), synth.heads_from_packed(ct, source == "nhwc"))
+    launch = lambda: step.launch_loss_heads(heads, gt, st)
+else:
+    launch = lambda: step.launch_loss(loc, ct, gt, st)
+for _ in range(3): launch()
 tl = torch.zeros((batch, 16), dtype=torch.int64, device=dev)
 ssdhot.lib().ssdhot_debug_timeline(tl.data_ptr())
-step.launch_loss(loc, ct, gt, st)
+launch()
 torch.cuda.synchronize()
 ssdhot.lib().ssdhot_debug_timeline(None)
+print("source:", source)
 t = tl.cpu().double()
 t0 = t[:, 0].min()
 names = {0: "start", 1: "cleared", 11: "1a done", 12: "1a'+1b done", 13: "1c done", 14: "1d done", 3: "match done", 2: "stream done",
