@@ -39,7 +39,7 @@ P, C = 8732, 6
 METRIC = "images/s for match+mined loss and decode+DIoU-NMS at bs=256 per GPU"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each half's kernels at this workload, from the
 # `ncu --set full` capture summarised in profiles/ (train_image_kernel; score_kernel + nms_image_kernel)
-TRAFFIC = {"match_loss": 57.1e6 + 0.5e6, "decode_nms": (53.8e6 + 0.4e6) + (31.9e6 + 0.01e6), "source": "profiles/r01_final_ncu_full_summary.txt"}
+TRAFFIC = {"match_loss": 57.24e6 + 0.78e6, "decode_nms": (53.73e6 + 0.60e6) + (31.74e6 + 0.01e6), "source": "profiles/r01_final2_ncu_full_summary.txt"}
 
 
 def peaks():
