@@ -536,6 +536,47 @@ def main():
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = BATCH * world * e2e_steps / float(t_e2e.item())
 
+    # ---- BASELINE cfg 1: one image, 5 boxes (the web app's case, app_files/ssd_demo_app.py:288): latency ------------
+    single = None
+    if rank == 0:
+        c1 = synth.config(1)
+        loc1, ct1, ci1 = c1["loc_all"].to(dev), c1["conf_train"].to(dev), c1["conf_infer"].to(dev)
+        gt1 = ssdhot.pack_targets(c1["targets"], dev)
+        step1 = HotPathStep(ps, 1, C, c1["iou_thresh"], c1["ratio"], c1["score_thresh"], c1["nms_thresh"], c1["max_per_img"])
+        st1 = torch.cuda.current_stream(dev).cuda_stream
+
+        def lat(fn, n=50):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize(dev)
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+            for a, b in evs:
+                a.record()
+                fn()
+                b.record()
+            torch.cuda.synchronize(dev)
+            return 1e3 * statistics.median(a.elapsed_time(b) for a, b in evs)
+
+        def host_lat(fn, n=50):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize(dev)
+            ts = []
+            for _ in range(n):
+                t_a = time.perf_counter()
+                fn()
+                ts.append(time.perf_counter() - t_a)
+            return 1e6 * statistics.median(ts)
+
+        single = {
+            "workload": "cfg1: B=1, 5 GT boxes, match+mined loss then predict(0.01, 0.45, 200)", "unit": "us",
+            "kernels_match_loss": lat(lambda: step1.launch_loss(loc1, ct1, gt1, st1)),
+            "kernels_decode_nms": lat(lambda: step1.launch_predict(loc1, ci1, st1)),
+            "api_predict_list_of_dicts_wall": host_lat(lambda: ssdhot.predict(ps, None, c1["score_thresh"], c1["nms_thresh"], c1["max_per_img"],
+                                                                                pre_loc_all=loc1, pre_conf_all=ci1)),
+            "api_multibox_loss_item_wall": host_lat(lambda: [t.item() for t in ssdhot.multibox_loss(ps, loc1, ct1, gt1, c1["iou_thresh"], c1["ratio"])]),
+        }
+
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ---------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
@@ -567,6 +608,7 @@ def main():
                       "decode_nms_images_per_s": BATCH * world / (ms_pred * 1e-3)},
             "roofline": roofline,
             "heads": heads,
+            "single_image": single,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h_holder.get("bytes", 0), "steps": e2e_steps,

@@ -712,10 +712,9 @@ def test_heads_backward_matches_autograd(env, channels_last):
 def test_predict_images_goes_through_the_heads(env):
     """predict(model, images) on a model with mySSD's module names runs the model's trunk and heads, then the head-direct
     kernels (no permute / cat / pack): same detections as predict on the model's own (loc_all, conf_all)."""
-    from test_host_cpu import _TinySSD
     s, dev = env["ssdhot"], env["dev"]
     torch.manual_seed(11)
-    model = _TinySSD().to(dev).eval()
+    model = U.TinySSD().to(dev).eval()
     model.register_buffer("priors", s.default_boxes().to(dev))
     x = torch.randn(3, 3, 300, 300, device=dev)
     with torch.no_grad():

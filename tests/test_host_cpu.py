@@ -188,44 +188,12 @@ def test_ssd300_layout_check_host():
     assert L.ssdhot_ssd300_layout_host(perm.data_ptr(), 8732) == 0
 
 
-class _TinySSD(torch.nn.Module):
-    """A stand-in with mySSD's module names and feature-map sizes (SFS:120-231) but 8-channel trunks, so that the head
-    plumbing can be checked on the CPU without the VGG weights."""
-
-    def __init__(self, num_classes=6):
-        super().__init__()
-        nn = torch.nn
-        self.num_classes = num_classes
-
-        def down(cin, cout, size):
-            return nn.Sequential(nn.Conv2d(cin, cout, 1), nn.AdaptiveAvgPool2d(size), nn.ReLU())
-        self.VGG16_UpTo_conv4_3 = down(3, 8, 38)
-        self.VGG16_extras = down(8, 8, 19)
-        self.extra_conv6 = nn.Sequential(nn.Conv2d(8, 8, 1), nn.ReLU())
-        self.extra_conv7 = nn.Sequential(nn.Conv2d(8, 8, 1), nn.ReLU())
-        self.extra_conv8_2 = down(8, 8, 10)
-        self.extra_conv9_2 = down(8, 8, 5)
-        self.extra_conv10_2 = down(8, 8, 3)
-        self.extra_conv11_2 = down(8, 8, 1)
-        shapes = (4, 6, 6, 6, 4, 4)
-        self.box_head = nn.ModuleList([nn.Conv2d(8, a * 4, 3, padding=1) for a in shapes])
-        self.cls_head = nn.ModuleList([nn.Conv2d(8, a * num_classes, 3, padding=1) for a in shapes])
-
-    def forward(self, x):                                   # the reference's forward, tail included (SFS:234-271)
-        f0 = self.VGG16_UpTo_conv4_3(x)
-        f1 = self.extra_conv7(self.extra_conv6(self.VGG16_extras(f0)))
-        f2 = self.extra_conv8_2(f1); f3 = self.extra_conv9_2(f2); f4 = self.extra_conv10_2(f3); f5 = self.extra_conv11_2(f4)
-        feats = (f0, f1, f2, f3, f4, f5)
-        return O.pack_heads([h(f) for h, f in zip(self.box_head, feats)], [h(f) for h, f in zip(self.cls_head, feats)],
-                            self.num_classes)
-
-
 def test_forward_heads_is_forward_without_the_tail():
     """ssdhot.forward_heads returns the twelve head outputs whose reference packing (SFS:249-269) is model(x), and
     tests/_util.unpack_heads inverts that packing -- all pure PyTorch, checked on the CPU."""
     import ssdhot
     torch.manual_seed(3)
-    model = _TinySSD().eval()
+    model = U.TinySSD().eval()
     x = torch.randn(2, 3, 300, 300)
     with torch.no_grad():
         loc_all, conf_all = model(x)
