@@ -58,6 +58,31 @@ def test_validation_happens_before_launch_no_gpu_needed():
     assert L.ssdhot_predict(16, 8732, 16, 16, 1, 1, 0.1, 0.5, 200, 0, 0, 0.1, 0.2, 300.0, 300.0,
                             16, 16, 16, None, 16, 16, None) == -2          # C >= 2
     assert L.ssdhot_loss_workspace_bytes(256, 8732, 20) > 0 and L.ssdhot_match_workspace_bytes(256, 20) > 0 and L.ssdhot_predict_workspace_bytes(256, 8732, 6) > 0
+    # head-direct entry points: six 16-byte-aligned pointers per branch, a known layout, C == 6
+    six = (ctypes.c_void_p * 6)(*([16] * 6))
+    five = (ctypes.c_void_p * 6)(*([16] * 5 + [None]))
+    odd = (ctypes.c_void_p * 6)(*([16] * 5 + [20]))
+    ptr = lambda a: ctypes.cast(a, ctypes.c_void_p)
+    heads = lambda loc, conf, layout, C: L.ssdhot_predict_heads(16, ptr(loc), ptr(conf), layout, 1, C, 0.1, 0.45, 200, 0, 0, 0.1, 0.2,
+                                                                  300.0, 300.0, 16, 16, 16, None, 16, 16, 3, None)
+    assert heads(six, six, 7, 6) == -3                                      # unknown layout
+    assert heads(six, six, 0, 21) == -2                                     # other class counts: pack first
+    assert heads(six, five, 0, 6) == -1 and heads(six, odd, 1, 6) == -5     # missing / misaligned head
+    assert L.ssdhot_predict_heads(16, None, ptr(six), 0, 1, 6, 0.1, 0.45, 200, 0, 0, 0.1, 0.2, 300.0, 300.0,
+                                  16, 16, 16, None, 16, 16, 3, None) == -1
+    assert L.ssdhot_multibox_loss_heads_fwd(16, 16, 16, 1, 16, 16, 16, 1, 4, 300.0, 300.0, ptr(six), ptr(six), 0, 21,
+                                            0.5, 0.1, 0.2, 3.0, 16, 16, None, None, None, None, None) == -2
+    assert L.ssdhot_multibox_loss_heads_fwd(16, 16, 16, 0, 16, 16, 16, 1, 4, 300.0, 300.0, ptr(six), ptr(six), 0, 6,
+                                            0.5, 0.1, 0.2, 3.0, 16, 16, None, None, None, None, None) == -2    # needs the SSD300 layout
+    assert L.ssdhot_multibox_loss_heads_bwd(16, 16, 16, 1, 300.0, 300.0, ptr(six), ptr(six), 5, 6, 0.1, 0.2, 16, 16, 16,
+                                            ptr(six), ptr(six), None) == -3
+    # peer all-reduce: rank / world / lag are checked before anything is launched
+    one = (ctypes.c_void_p * 1)(16)
+    assert L.ssdhot_allreduce_sums_peer(16, ptr(one), 0, 9, 0, None, None) == -2
+    assert L.ssdhot_allreduce_sums_peer(16, ptr(one), 1, 1, 0, None, None) == -2
+    assert L.ssdhot_allreduce_sums_peer(16, ptr(one), 0, 1, 2, None, None) == -3
+    assert L.ssdhot_allreduce_sums_peer(None, ptr(one), 0, 1, 0, None, None) == -1
+    assert L.ssdhot_peer_mailbox_bytes() >= 4 * 8 * 4 * 8 + 8
     assert ssdhot.launch_count() == 0
 
 
