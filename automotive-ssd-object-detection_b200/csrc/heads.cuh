@@ -89,14 +89,6 @@ struct HeadReader {
             }
         }
     }
-    __device__ __forceinline__ float elem(int p, int j) const {
-        if (SRC == SRC_LEVEL_PLANES) {
-            int hw;
-            const float* q = plane0(p, hw);
-            return __ldg(q + (long long)j * hw);
-        }
-        return __ldg(row_ptr(p) + j);
-    }
     // the 2*D values of rows 2q and 2q+1 (same cell, shapes a and a+1; 16-byte loads where rows are contiguous)
     __device__ __forceinline__ void pair(int q, float* x) const {
         if (SRC == SRC_LEVEL_PLANES) {
