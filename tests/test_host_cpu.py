@@ -233,3 +233,25 @@ def test_forward_heads_is_forward_without_the_tail():
             assert u.is_contiguous(memory_format=torch.channels_last if cl else torch.contiguous_format)
     with pytest.raises(ValueError):
         ssdhot.predict_heads(model, loc_heads[:5], conf_heads)           # validation precedes the CUDA requirement
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/SSD_from_scratch.py"), reason="the reference tree is only mounted in the build container")
+def test_forward_heads_against_the_real_reference_model():
+    """With the unmodified reference class (random weights, CPU): mySSD.forward(x) == the reference packing of
+    ssdhot.forward_heads(model, x), bit for bit -- forward_heads names the reference's own modules (SFS:236-262) correctly and
+    leaves out nothing but the permute / cat tail (SFS:249-269)."""
+    import importlib.util
+    import ssdhot
+    spec = importlib.util.spec_from_file_location("_ref_ssd_from_scratch", "/root/reference/SSD_from_scratch.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    torch.manual_seed(0)
+    model = ref.mySSD({"a": 0, "b": 1, "c": 2, "d": 3, "e": 4}).eval()
+    x = torch.randn(1, 3, 300, 300)
+    with torch.no_grad():
+        loc_all, conf_all = model(x)
+        loc_heads, conf_heads = ssdhot.forward_heads(model, x)
+    assert loc_all.shape == (1, 8732, 4) and conf_all.shape == (1, 8732, 6)
+    back_loc, back_conf = O.pack_heads(loc_heads, conf_heads, 6)
+    assert torch.equal(back_loc, loc_all) and torch.equal(back_conf, conf_all)
+    assert torch.equal(model.priors, ssdhot.default_boxes())
