@@ -143,6 +143,37 @@ class HotPathStep:
             self._graphs[key] = g
         g.replay()
 
+    def run_heads(self, train_heads: HeadSet, infer_heads: HeadSet, gt: PackedTargets, use_graph: bool = False) -> None:
+        """run() fed by the head outputs (HeadSet: NCHW or channels_last) instead of loc_all / conf_all: both halves read the
+        six tensors of each branch directly, the predict half forked onto a second stream; use_graph captures the launches
+        once per distinct pair of HeadSets."""
+        dev = self.ps.device
+        if not use_graph:
+            cur = torch.cuda.current_stream(dev)
+            if self._fork is None:
+                self._fork = torch.cuda.Stream(dev)
+            self._fork.wait_stream(cur)
+            self.launch_loss_heads(train_heads, gt, cur.cuda_stream)
+            self.launch_predict_heads(infer_heads, self._fork.cuda_stream)
+            self._reduce()
+            cur.wait_stream(self._fork)
+            return
+        key = ("heads", id(train_heads), id(infer_heads), gt.boxes.data_ptr(), gt.max_gt)
+        g = self._graphs.get(key)
+        if g is None:
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self.run_heads(train_heads, infer_heads, gt)         # warm (sets smem attributes)
+                side.synchronize()
+                with torch.cuda.graph(g, stream=side):
+                    self.run_heads(train_heads, infer_heads, gt)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self._graphs[key] = g
+            self._keep = getattr(self, "_keep", []) + [train_heads, infer_heads]      # the graph holds their pointers
+        g.replay()
+
     def _reduce(self) -> None:
         """The sharded path's only exchange: all-reduce [sum smooth-L1, sum CE, sum positives] in place."""
         if self.group is not None:                      # (a PeerSums is one kernel and becomes part of the step's CUDA graph)

@@ -437,6 +437,22 @@ def main():
                 res[mode] = statistics.median(a.elapsed_time(b) for a, b in evs)
             res["packed_kernels_only"] = ms_loss if train else ms_pred
             out["match_loss" if train else "decode_nms"] = res
+        # the whole step (both halves forked, one CUDA graph per input set) from the heads, timed like `value`
+        if group is None:
+            whole = {}
+            for mode in ("nchw", "nhwc"):
+                for i in range(6):
+                    step.run_heads(views[i % len(views)][mode]["train"], views[i % len(views)][mode]["infer"], sets[i % len(views)]["gt"], use_graph=use_graph)
+                torch.cuda.synchronize(dev)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n = max(30, min(args.steps, 200))
+                a.record()
+                for i in range(n):
+                    step.run_heads(views[i % len(views)][mode]["train"], views[i % len(views)][mode]["infer"], sets[i % len(views)]["gt"], use_graph=use_graph)
+                b.record()
+                torch.cuda.synchronize(dev)
+                whole[mode] = {"ms_per_step": a.elapsed_time(b) / n, "images_per_s": BATCH * n / (a.elapsed_time(b) * 1e-3)}
+            out["whole_step"] = whole
         del views
         torch.cuda.empty_cache()
         return out

@@ -831,3 +831,30 @@ def test_peer_allreduce_protocol_virtual_ranks(env):
     for p in ranks[1:]:
         p.close()
     ranks[0].close()
+
+
+def test_hot_path_step_from_heads_equals_packed(env):
+    """HotPathStep.run_heads (both halves forked, eager and replayed from a CUDA graph) leaves the same sums and padded
+    detections as HotPathStep.run on the packed tensors."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    from ssdhot.engine import HeadSet, HotPathStep
+    cfg = s.synth.config(2, batch=8)
+    loc, ct, ci = cfg["loc_all"].to(dev), cfg["conf_train"].to(dev), cfg["conf_infer"].to(dev)
+    gt = s.pack_targets(cfg["targets"], dev)
+    step = HotPathStep(ps, 8, 6, cfg["iou_thresh"], cfg["ratio"], cfg["score_thresh"], cfg["nms_thresh"], cfg["max_per_img"])
+    step.run(loc, ct, ci, gt)
+    torch.cuda.synchronize(dev)
+    want = (step.sums.clone(), step.count.clone(), step.labels.clone(), step.scores.clone(), step.boxes.clone())
+    for cl in (False, True):
+        lh = s.synth.heads_from_packed(loc, cl)
+        train, infer = HeadSet(lh, s.synth.heads_from_packed(ct, cl)), HeadSet(lh, s.synth.heads_from_packed(ci, cl))
+        for use_graph in (False, True, True):
+            for t in (step.sums, step.count, step.scores):
+                t.zero_()
+            step.run_heads(train, infer, gt, use_graph=use_graph)
+            torch.cuda.synchronize(dev)
+            assert bit_equal(step.sums, want[0]) and bit_equal(step.count, want[1])
+            for b in range(8):
+                k = int(want[1][b])
+                assert bit_equal(step.labels[b, :k], want[2][b, :k]) and bit_equal(step.scores[b, :k], want[3][b, :k])
+                assert bit_equal(step.boxes[b, :k], want[4][b, :k])
