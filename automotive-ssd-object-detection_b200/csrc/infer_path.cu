@@ -18,6 +18,9 @@
 //    are never ranked or tested.  Rounds of <= 512 candidates: score histogram -> cut -> gather -> exact
 //    scores of the pulled candidates -> bitonic sort -> decode -> class-local order -> pair tests (IoU gate,
 //    then the exact metric for the few pairs that pass) into class-local bit rows -> per-class resolve.
+// Both kernels are templated on the source of the head outputs (heads.cuh): the packed [B,8732,D] tensors, or the six
+// per-level tensors of each branch as channels_last rows or NCHW planes (ssdhot_predict_heads) -- same candidate ids,
+// same lists, bit-identical results.
 // The stand-alone NMS entry point (mySSD.iou_nms, nms_sets_kernel / nms_unit) handles arbitrary set sizes
 // and unbounded survivor counts with tiles of 64 and a CTA-local radix select.
 #include <map>
