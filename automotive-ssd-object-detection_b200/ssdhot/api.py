@@ -440,32 +440,44 @@ def forward_heads(model, x: torch.Tensor) -> Tuple[List[torch.Tensor], List[torc
     return [h(f) for h, f in zip(model.box_head, feats)], [h(f) for h, f in zip(model.cls_head, feats)]
 
 
-def _head_args(loc_heads: Sequence[torch.Tensor], conf_heads: Sequence[torch.Tensor]):
-    """Validate the 2 x 6 head outputs ([B, A*D, side, side] each, SFS:249-262) and return
-    (device, B, C, layout, keep-alive tensors, ctypes pointer arrays).  Heads that are channels_last in memory are read as
-    NHWC rows, everything else as NCHW planes; a head that is neither (or not 16-byte aligned) is made contiguous."""
-    import ctypes
-    if len(loc_heads) != len(_LEVELS) or len(conf_heads) != len(_LEVELS):
-        raise ValueError(f"expected {len(_LEVELS)} loc and conf head outputs, got {len(loc_heads)} and {len(conf_heads)}")
-    dev = _need_cuda(*loc_heads, *conf_heads)
-    B = int(conf_heads[0].shape[0])
-    C = int(conf_heads[0].shape[1]) // _LEVELS[0][1]
-    for heads, D, what in ((loc_heads, 4, "loc"), (conf_heads, C, "conf")):
-        for h, (side, shapes) in zip(heads, _LEVELS):
-            if tuple(h.shape) != (B, shapes * D, side, side):
-                raise ValueError(f"{what} head of the {side}x{side} level has shape {tuple(h.shape)}, expected {(B, shapes * D, side, side)}")
-    every = list(loc_heads) + list(conf_heads)
-    nhwc = all(h.is_contiguous(memory_format=torch.channels_last) for h in every) and not all(h.is_contiguous() for h in every)
-    fmt = torch.channels_last if nhwc else torch.contiguous_format
-    keep = []
-    for h in every:
-        t = h.detach().to(torch.float32).contiguous(memory_format=fmt)
-        if t.data_ptr() % 16:
-            t = t.clone(memory_format=fmt)
-        keep.append(t)
-    loc_ptrs = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in keep[:6]])
-    conf_ptrs = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in keep[6:]])
-    return dev, B, C, (HEADS_NHWC if nhwc else HEADS_NCHW), keep, ctypes.cast(loc_ptrs, ctypes.c_void_p), ctypes.cast(conf_ptrs, ctypes.c_void_p), (loc_ptrs, conf_ptrs)
+class HeadSet:
+    """The 2 x 6 head outputs of a batch ([B, A*D, side, side] each, SFS:249-262), validated, with the two HOST arrays of
+    DEVICE pointers the head-direct entry points take (ssdhot_predict_heads, ssdhot_multibox_loss_heads_fwd/_bwd).
+    Heads that are channels_last in memory are read as NHWC rows (layout HEADS_NHWC), everything else as NCHW planes
+    (HEADS_NCHW); a head that is neither (or is not 16-byte aligned) is made contiguous first.  The object keeps the
+    tensors alive; prepare it once when the same buffers are launched repeatedly (HotPathStep.launch_*_heads)."""
+
+    def __init__(self, loc_heads: Sequence[torch.Tensor], conf_heads: Sequence[torch.Tensor]):
+        import ctypes
+        if len(loc_heads) != len(_LEVELS) or len(conf_heads) != len(_LEVELS):
+            raise ValueError(f"expected {len(_LEVELS)} loc and conf head outputs, got {len(loc_heads)} and {len(conf_heads)}")
+        self.device = _need_cuda(*loc_heads, *conf_heads)
+        self.B = int(conf_heads[0].shape[0])
+        self.C = int(conf_heads[0].shape[1]) // _LEVELS[0][1]
+        for heads, D, what in ((loc_heads, 4, "loc"), (conf_heads, self.C, "conf")):
+            for h, (side, shapes) in zip(heads, _LEVELS):
+                if tuple(h.shape) != (self.B, shapes * D, side, side):
+                    raise ValueError(f"{what} head of the {side}x{side} level has shape {tuple(h.shape)}, "
+                                     f"expected {(self.B, shapes * D, side, side)}")
+        every = list(loc_heads) + list(conf_heads)
+        nhwc = all(h.is_contiguous(memory_format=torch.channels_last) for h in every) and not all(h.is_contiguous() for h in every)
+        fmt = torch.channels_last if nhwc else torch.contiguous_format
+        self.layout = HEADS_NHWC if nhwc else HEADS_NCHW
+        self.tensors = []
+        for h in every:
+            t = h.detach().to(torch.float32).contiguous(memory_format=fmt)
+            if t.data_ptr() % 16:
+                t = t.clone(memory_format=fmt)
+            self.tensors.append(t)
+        self._loc_array = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in self.tensors[:6]])
+        self._conf_array = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in self.tensors[6:]])
+        self.loc_ptr = ctypes.cast(self._loc_array, ctypes.c_void_p)
+        self.conf_ptr = ctypes.cast(self._conf_array, ctypes.c_void_p)
+
+    def used_on(self, stream: "torch.cuda.Stream") -> None:
+        """Tell the caching allocator that `stream` reads the (possibly re-laid-out) tensors."""
+        for t in self.tensors:
+            t.record_stream(stream)
 
 
 def predict_heads_padded(model, loc_heads: Sequence[torch.Tensor], conf_heads: Sequence[torch.Tensor], score_thresh: float = 0.2,
@@ -479,13 +491,14 @@ def predict_heads_padded(model, loc_heads: Sequence[torch.Tensor], conf_heads: S
         raise ValueError(f"Score threshold should be greater than 0 and less than 1, recieved {score_thresh}.")
     if not (0.0 < nms_thresh < 1.0):
         raise ValueError(f"NMS threshold should be greater than 0 and less than 1, recieved {nms_thresh}.")
-    dev, B, C, layout, keep, loc_p, conf_p, _alive = _head_args(loc_heads, conf_heads)
+    hs = loc_heads if isinstance(loc_heads, HeadSet) else HeadSet(loc_heads, conf_heads)
+    dev, B, C = hs.device, hs.B, hs.C
     priors = PriorSet.of(model)
     assert priors.P == 8732
     assert C >= 2
     if C != 6:
-        return predict_padded(model, *pack_heads(loc_heads, conf_heads), score_thresh, nms_thresh, max_per_img, class_agnostic,
-                              metric, want_cand)
+        return predict_padded(model, *pack_heads(hs.tensors[:6], hs.tensors[6:]), score_thresh, nms_thresh, max_per_img,
+                              class_agnostic, metric, want_cand)
     labels = torch.empty((B, max_per_img), dtype=torch.int64, device=dev)
     scores = torch.empty((B, max_per_img), dtype=torch.float32, device=dev)
     boxes = torch.empty((B, max_per_img, 4), dtype=torch.float32, device=dev)
@@ -493,15 +506,14 @@ def predict_heads_padded(model, loc_heads: Sequence[torch.Tensor], conf_heads: S
     count = torch.empty((B,), dtype=torch.int32, device=dev)
     work = _workspace("predict", dev, _lib.lib().ssdhot_predict_workspace_bytes(B, 8732, C))
     with torch.cuda.device(dev):
-        rc = _lib.lib().ssdhot_predict_heads(priors.priors.data_ptr(), loc_p, conf_p, layout, B, C,
+        rc = _lib.lib().ssdhot_predict_heads(priors.priors.data_ptr(), hs.loc_ptr, hs.conf_ptr, hs.layout, B, C,
                                              float(score_thresh), float(nms_thresh), int(max_per_img), 1 if class_agnostic else 0,
                                              METRICS[metric], priors.variances[0], priors.variances[1],
                                              float(priors.img_w), float(priors.img_h),
                                              labels.data_ptr(), scores.data_ptr(), boxes.data_ptr(), _ptr(cand),
                                              count.data_ptr(), work.data_ptr(), 3, _stream(dev))
     _lib.check(rc, "ssdhot_predict_heads")
-    for t in keep:
-        t.record_stream(torch.cuda.current_stream(dev))
+    hs.used_on(torch.cuda.current_stream(dev))
     if want_cand:
         return labels, scores, boxes, count, cand
     return labels, scores, boxes, count
@@ -525,7 +537,8 @@ class _FusedLossHeads(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, priors: PriorSet, packed: PackedTargets, iou_thresh, ratio, norm_wh, group, *heads):
-        dev, B, C, layout, keep, loc_p, conf_p, alive = _head_args(heads[:6], heads[6:])
+        hs = HeadSet(heads[:6], heads[6:])
+        dev, B, C, layout, keep = hs.device, hs.B, hs.C, hs.layout, hs.tensors
         need_grad = any(h.requires_grad for h in heads)
         sums = torch.empty((3,), dtype=torch.float64, device=dev)
         sel = torch.empty((B, 8732), dtype=torch.int8, device=dev) if need_grad else None
@@ -535,12 +548,11 @@ class _FusedLossHeads(torch.autograd.Function):
             rc = _lib.lib().ssdhot_multibox_loss_heads_fwd(
                 priors.priors.data_ptr(), priors.priors_xyxy.data_ptr(), priors.aux.data_ptr(), priors.layout,
                 packed.boxes.data_ptr(), packed.labels.data_ptr(), packed.offsets.data_ptr(), B, packed.max_gt,
-                float(norm_wh[0]), float(norm_wh[1]), loc_p, conf_p, layout, C,
+                float(norm_wh[0]), float(norm_wh[1]), hs.loc_ptr, hs.conf_ptr, layout, C,
                 float(iou_thresh), priors.variances[0], priors.variances[1], float(ratio),
                 sums.data_ptr(), work.data_ptr(), _ptr(sel), _ptr(matched), None, None, _stream(dev))
         _lib.check(rc, "ssdhot_multibox_loss_heads_fwd")
-        for t in keep:
-            t.record_stream(torch.cuda.current_stream(dev))
+        hs.used_on(torch.cuda.current_stream(dev))
         if group is not None:
             _dist.reduce_sums(sums, group)
         total = sums[2].clamp_min(1.0)

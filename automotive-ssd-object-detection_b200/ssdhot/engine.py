@@ -13,17 +13,8 @@ import torch
 
 from . import _lib
 from . import dist as _dist
-from .api import METRICS, PackedTargets
+from .api import METRICS, HeadSet, PackedTargets  # noqa: F401  (HeadSet: the head-direct launches below)
 from .priors import PriorSet
-
-
-class HeadSet:
-    """The 2 x 6 head outputs of a batch (SFS:249-262) with their pointer arrays prepared once, for the head-direct
-    launches of HotPathStep (no permute / cat / pack pass).  layout: api.HEADS_NCHW or api.HEADS_NHWC."""
-
-    def __init__(self, loc_heads, conf_heads):
-        from .api import _head_args
-        (self.device, self.B, self.C, self.layout, self.tensors, self.loc_ptr, self.conf_ptr, self._alive) = _head_args(loc_heads, conf_heads)
 
 
 class HotPathStep:
