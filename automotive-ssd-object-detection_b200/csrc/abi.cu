@@ -1,9 +1,32 @@
 // abi.cu -- library-level entry points of libssdhot.so (include/ssdhot.h).
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace ssdhot {
 unsigned long long g_launches = 0ull;
 unsigned long long* g_timeline = nullptr;
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (device, kernel): the opt-in is tracked per current device
+// under a mutex, raised once per pair (never lowered), and therefore never re-issued inside a graph capture after the first
+// (warm-up) call on that device.
+int ensure_dyn_smem(const void* kern, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> configured;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = configured[std::make_pair(dev, kern)];
+    if (bytes > have) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+        have = bytes;
+    }
+    return SSDHOT_OK;
+}
 }
 
 // Debug hook: device buffer of (units x 16) uint64 that the per-image kernels (train_image_kernel,

@@ -82,6 +82,7 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
     return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
+int ensure_dyn_smem(const void* kern, size_t bytes);   // per-(device, kernel) opt-in to > 48 KB of dynamic shared memory (abi.cu)
 extern unsigned long long g_launches;   // host-side counter (abi.cu)
 extern unsigned long long* g_timeline;  // debug hook (ssdhot_debug_timeline, abi.cu): device buffer [units][16] or null
 

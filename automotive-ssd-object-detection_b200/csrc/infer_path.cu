@@ -23,9 +23,6 @@
 // same lists, bit-identical results.
 // The stand-alone NMS entry point (mySSD.iou_nms, nms_sets_kernel / nms_unit) handles arbitrary set sizes
 // and unbounded survivor counts with tiles of 64 and a CTA-local radix select.
-#include <map>
-#include <mutex>
-
 #include "boxmath.cuh"
 #include "heads.cuh"
 
@@ -1159,19 +1156,9 @@ constexpr size_t kMaxDynSmem = 227 * 1024 - sizeof(UnitShared) - 1024;
 
 template <typename K>
 static int set_smem(K kern, size_t bytes) {
-    // the opt-in is sticky per kernel, so it is raised once and never inside a graph capture
     if (bytes > kMaxDynSmem) return SSDHOT_ERR_SHAPE;
-    static std::mutex mu;
-    static std::map<const void*, size_t> configured;
-    if (bytes > 40 * 1024) {      // static + dynamic shared memory share the 48 KB default limit
-        std::lock_guard<std::mutex> lock(mu);
-        size_t& have = configured[reinterpret_cast<const void*>(kern)];
-        if (bytes > have) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
-            if (e != cudaSuccess) return (int)e;
-            have = kMaxDynSmem;
-        }
-    }
+    if (bytes > 40 * 1024)        // static + dynamic shared memory share the 48 KB default limit
+        return ensure_dyn_smem(reinterpret_cast<const void*>(kern), kMaxDynSmem);
     return SSDHOT_OK;
 }
 

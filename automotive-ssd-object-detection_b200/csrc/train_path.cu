@@ -1657,11 +1657,9 @@ static int launch_match(const TrainParams& prm, cudaStream_t stream) {
     }
     const size_t dyn = smem_bytes(prm.max_gt > 0 ? prm.max_gt : 1);
     auto kern = match_kernel<PRUNE>;
-    static size_t configured = 0;      // per instantiation; sticky opt-in, raised outside graph capture
-    if (dyn > 48 * 1024 && dyn > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        if (e != cudaSuccess) return (int)e;
-        configured = dyn;
+    if (dyn > 48 * 1024) {
+        const int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), dyn);
+        if (rc) return rc;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(prm.B * cs));
@@ -1696,11 +1694,9 @@ static int launch_train_image(const TrainParams& prm_in, cudaStream_t stream) {
     prm.timeline = g_timeline;
     const size_t dyn = fused_smem_bytes(prm.P);
     auto kern = train_image_kernel<LOSS, SRC>;
-    static bool configured = false;    // sticky opt-in, raised outside graph capture by the first (warm-up) call
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
+    {
+        const int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), dyn);   // sticky per device; first raised by the warm-up call
+        if (rc) return rc;
     }
     kern<<<prm.B, FT, dyn, stream>>>(prm);
     SSDHOT_CHECK_LAUNCH();
@@ -1840,6 +1836,7 @@ extern "C" int ssdhot_multibox_loss_fwd(const float* priors_cxcywh, const float*
     if (rc) return rc;
     if (!loc_all || !conf_all || !sums || !work) return SSDHOT_ERR_NULL;
     if (C < 2 || C > SSDHOT_MAX_CLASSES) return SSDHOT_ERR_SHAPE;
+    if (sel_cls && C > SSDHOT_MAX_CLASSES_BWD) return SSDHOT_ERR_SHAPE;       // sel_cls holds the target class in an int8
     if (!(neg_pos_ratio >= 0.0)) return SSDHOT_ERR_VALUE;
     if (!aligned16(loc_all) || (reinterpret_cast<uintptr_t>(conf_all) & 7u) || !aligned16(work)) return SSDHOT_ERR_ALIGN;
     unsigned char* w = reinterpret_cast<unsigned char*>(work);
@@ -1920,6 +1917,7 @@ extern "C" int ssdhot_mined_ce_fwd(const float* conf_all, const int64_t* cls_t, 
                                    double* sums, void* work, int8_t* sel_cls, ssdhot_stream_t stream) {
     if (!conf_all || !cls_t || !pos_mask || !sums || !work) return SSDHOT_ERR_NULL;
     if (P <= 0 || P > SSDHOT_MAX_PRIORS || B <= 0 || C < 2 || C > SSDHOT_MAX_CLASSES) return SSDHOT_ERR_SHAPE;
+    if (sel_cls && C > SSDHOT_MAX_CLASSES_BWD) return SSDHOT_ERR_SHAPE;       // sel_cls holds the target class in an int8
     if (!(neg_pos_ratio >= 0.0)) return SSDHOT_ERR_VALUE;
     if ((reinterpret_cast<uintptr_t>(conf_all) & 7u) || !aligned16(work)) return SSDHOT_ERR_ALIGN;
     unsigned char* w = reinterpret_cast<unsigned char*>(work);
@@ -1944,7 +1942,7 @@ extern "C" int ssdhot_multibox_loss_bwd(const float* priors_cxcywh, int P,
     if (!sel_cls || !scales || (!grad_loc && !grad_conf)) return SSDHOT_ERR_NULL;
     if (grad_conf && !conf_all) return SSDHOT_ERR_NULL;
     if (grad_loc && (!loc_all || !matched_gt || !priors_cxcywh || !gt_offsets)) return SSDHOT_ERR_NULL;
-    if (P <= 0 || B <= 0 || C < 2 || C > SSDHOT_MAX_CLASSES) return SSDHOT_ERR_SHAPE;
+    if (P <= 0 || B <= 0 || C < 2 || C > SSDHOT_MAX_CLASSES_BWD) return SSDHOT_ERR_SHAPE;
     if (!aligned16(loc_all) || !aligned16(grad_loc) || !aligned16(priors_cxcywh) || !aligned16(gt_boxes)) return SSDHOT_ERR_ALIGN;
     const long long rows = (long long)B * P;
     loss_bwd_kernel<0><<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(

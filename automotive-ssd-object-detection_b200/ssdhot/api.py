@@ -9,6 +9,7 @@ from __future__ import annotations
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
+import torch.utils.data
 
 from . import _lib
 from . import dist as _dist
@@ -39,34 +40,123 @@ def _need_cuda(*tensors: torch.Tensor) -> torch.device:
 
 
 class PackedTargets:
-    """Ragged ground truth of a batch as three device tensors (hard part 9):
-    boxes [sumG,4] f32 pixel xyxy, labels [sumG] i64, offsets [B+1] i32; max_gt known on the host."""
+    """Ragged ground truth of a batch (hard part 9): boxes [sumG,4] f32 pixel xyxy, labels [sumG] i64,
+    offsets [B+1] i32 -- three views of ONE byte buffer laid out [offsets | pad to 16 B | boxes | labels], so that a batch's
+    ground truth crosses PCIe as a single copy (`to(device)`) instead of the reference's three tiny copies per image
+    (SSD_trainer.py:66-69).  max_gt and the per-image counts are known on the host."""
 
-    def __init__(self, boxes: torch.Tensor, labels: torch.Tensor, offsets: torch.Tensor, max_gt: int, n_img: int):
+    def __init__(self, boxes: torch.Tensor, labels: torch.Tensor, offsets: torch.Tensor, max_gt: int, n_img: int,
+                 buffer: Optional[torch.Tensor] = None, counts: Optional[Sequence[int]] = None):
         self.boxes, self.labels, self.offsets, self.max_gt, self.n_img = boxes, labels, offsets, int(max_gt), int(n_img)
+        self.buffer, self.counts = buffer, (list(counts) if counts is not None else None)
+
+    @staticmethod
+    def layout(n_img: int, total: int) -> Tuple[int, int, int]:
+        """-> (byte offset of boxes, byte offset of labels, buffer bytes); at least one (unused) row is always present."""
+        rows = max(int(total), 1)
+        box_off = (4 * (n_img + 1) + 15) & ~15
+        lab_off = box_off + 16 * rows
+        return box_off, lab_off, lab_off + 8 * rows
+
+    @classmethod
+    def from_buffer(cls, buffer: torch.Tensor, n_img: int, total: int, max_gt: int, counts=None) -> "PackedTargets":
+        box_off, lab_off, nbytes = cls.layout(n_img, total)
+        rows = max(int(total), 1)
+        offsets = buffer[: 4 * (n_img + 1)].view(torch.int32)
+        boxes = buffer[box_off:lab_off].view(torch.float32).view(rows, 4)
+        labels = buffer[lab_off:nbytes].view(torch.int64)
+        return cls(boxes, labels, offsets, max_gt, n_img, buffer, counts)
+
+    @property
+    def device(self) -> torch.device:
+        return self.boxes.device
+
+    @property
+    def total(self) -> int:
+        return int(sum(self.counts)) if self.counts is not None else int(self.boxes.shape[0])
+
+    def to(self, device, non_blocking: bool = True) -> "PackedTargets":
+        """The whole batch's ground truth in ONE copy (cudaMemcpyAsync from pinned memory when the buffer is pinned)."""
+        device = torch.device(device)
+        if self.boxes.device == device or (device.type == "cuda" and device.index is None and self.boxes.is_cuda):
+            return self
+        if self.buffer is None:
+            return PackedTargets(self.boxes.to(device, non_blocking=non_blocking), self.labels.to(device, non_blocking=non_blocking),
+                                 self.offsets.to(device, non_blocking=non_blocking), self.max_gt, self.n_img, None, self.counts)
+        return PackedTargets.from_buffer(self.buffer.to(device, non_blocking=non_blocking), self.n_img, self.total, self.max_gt, self.counts)
+
+    def pin_memory(self) -> "PackedTargets":            # (torch.utils.data.DataLoader(pin_memory=True) calls this on custom batches)
+        if self.buffer is None or self.buffer.is_pinned() or self.buffer.is_cuda:
+            return self
+        return PackedTargets.from_buffer(self.buffer.pin_memory(), self.n_img, self.total, self.max_gt, self.counts)
+
+    def record_stream(self, stream) -> None:
+        for t in ((self.buffer,) if self.buffer is not None else (self.boxes, self.labels, self.offsets)):
+            if t.is_cuda:
+                t.record_stream(stream)
+
+    def as_list(self) -> List[Dict[str, torch.Tensor]]:
+        """The reference's List[Dict] form (views, no copies): what collate_detection's second output used to be."""
+        counts = self.counts if self.counts is not None else (self.offsets[1:] - self.offsets[:-1]).tolist()
+        out, at = [], 0
+        for c in counts:
+            out.append({"boxes": self.boxes[at:at + c], "labels": self.labels[at:at + c]})
+            at += c
+        return out
 
 
-def pack_targets(targets: Sequence[Dict[str, torch.Tensor]], device) -> PackedTargets:
-    """List[Dict] (collate_detection, SSD_trainer.py:806-813) -> PackedTargets on `device`.
-    Works for CPU or CUDA member tensors; one concatenation + (for CPU input) one H2D copy each."""
-    if isinstance(targets, PackedTargets):
-        return targets
-    device = torch.device(device)
+def _pack_host(targets: Sequence[Dict[str, torch.Tensor]], pinned: bool) -> PackedTargets:
     counts = [int(t["boxes"].shape[0]) if t["boxes"].numel() else 0 for t in targets]
+    n_img, total = len(counts), sum(counts)
+    _, _, nbytes = PackedTargets.layout(n_img, total)
+    buf = torch.zeros((nbytes,), dtype=torch.uint8, pin_memory=pinned)
+    packed = PackedTargets.from_buffer(buf, n_img, total, max(counts) if counts else 0, counts)
     offs = [0]
     for c in counts:
         offs.append(offs[-1] + c)
-    offsets = torch.tensor(offs, dtype=torch.int32).to(device, non_blocking=True)
+    packed.offsets.copy_(torch.tensor(offs, dtype=torch.int32))
     live = [i for i, c in enumerate(counts) if c > 0]
-    if not live:
-        boxes = torch.zeros((1, 4), dtype=torch.float32, device=device)   # never read (max_gt = 0)
-        labels = torch.zeros((1,), dtype=torch.int64, device=device)
-    else:
-        boxes = torch.cat([targets[i]["boxes"].as_subclass(torch.Tensor).reshape(-1, 4) for i in live], 0)
-        labels = torch.cat([targets[i]["labels"].reshape(-1) for i in live], 0)
-        boxes = boxes.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
-        labels = labels.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
-    return PackedTargets(boxes, labels, offsets, max(counts) if counts else 0, len(counts))
+    if live:
+        torch.cat([targets[i]["boxes"].as_subclass(torch.Tensor).reshape(-1, 4).to(torch.float32) for i in live], 0, out=packed.boxes[:total])
+        torch.cat([targets[i]["labels"].as_subclass(torch.Tensor).reshape(-1).to(torch.int64) for i in live], 0, out=packed.labels[:total])
+    return packed
+
+
+def pack_targets(targets: Sequence[Dict[str, torch.Tensor]], device) -> PackedTargets:
+    """List[Dict] (collate_detection, SSD_trainer.py:806-813) -> PackedTargets on `device`.  CPU member tensors are packed
+    into one pinned host buffer and cross to the device in ONE copy; member tensors that already live on a CUDA device are
+    concatenated there (only the B+1 offsets come from the host).  A PackedTargets is moved (one copy) or returned as is."""
+    device = torch.device(device)
+    if isinstance(targets, PackedTargets):
+        return targets.to(device)
+    if any(t["boxes"].is_cuda for t in targets):
+        counts = [int(t["boxes"].shape[0]) if t["boxes"].numel() else 0 for t in targets]
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        offsets = torch.tensor(offs, dtype=torch.int32).to(device, non_blocking=True)
+        live = [i for i, c in enumerate(counts) if c > 0]
+        if not live:
+            boxes = torch.zeros((1, 4), dtype=torch.float32, device=device)   # never read (max_gt = 0)
+            labels = torch.zeros((1,), dtype=torch.int64, device=device)
+        else:
+            boxes = torch.cat([targets[i]["boxes"].as_subclass(torch.Tensor).reshape(-1, 4).to(device=device, dtype=torch.float32) for i in live], 0)
+            labels = torch.cat([targets[i]["labels"].reshape(-1).to(device=device, dtype=torch.int64) for i in live], 0)
+        return PackedTargets(boxes.contiguous(), labels.contiguous(), offsets, max(counts) if counts else 0, len(counts), None, counts)
+    return _pack_host(targets, pinned=device.type == "cuda" and torch.cuda.is_available()).to(device)
+
+
+def collate_detection(batch):
+    """Drop-in for SSD_trainer.collate_detection (SSD_trainer.py:806-813): list of (img, target) -> (images [B,C,H,W],
+    PackedTargets).  The ground truth of the whole batch is packed ONCE, here, into a single (pinned, when this process may
+    pin) host buffer [offsets | boxes | labels]; `targets.to(device)` -- which the ssdhot step functions, build_targets and
+    multibox_loss do themselves -- is then one cudaMemcpyAsync instead of the reference's 3 copies per image
+    (SSD_trainer.py:66-69).  `targets.as_list()` gives the reference's List[Dict] back."""
+    imgs = [img for img, _ in batch]
+    tgts = [tgt for _, tgt in batch]
+    in_worker = torch.utils.data.get_worker_info() is not None       # (a DataLoader worker must not touch CUDA; the loader's
+    pinned = torch.cuda.is_available() and not in_worker             #  pin_memory thread pins the buffer through pin_memory())
+    return torch.stack(imgs, dim=0), _pack_host(tgts, pinned)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -195,6 +285,14 @@ def CELoss_w_neg_mining(conf_all: torch.Tensor, cls_t: torch.Tensor, pos_mask: t
     return _MinedCE.apply(conf_all, cls_t, pos_mask, total_pos, float(neg_pos_ratio))
 
 
+def _check_group_for_grad(group, need_grad: bool) -> None:
+    """A lagged PeerSums delivers the PREVIOUS call's reduced sums: fine for logging an eval step, wrong for a training
+    step, whose backward is scaled by 1 / (positives of THIS batch) (SSD_trainer.py:105-130)."""
+    if need_grad and isinstance(group, _dist.PeerSums) and group.lag != 0:
+        raise _lib.SsdhotError("a differentiable loss needs the sums of its own batch: use PeerSums(lag=0) (lag=1 delivers the "
+                               "previous call's sums and would mis-scale the gradients)")
+
+
 class _FusedLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, loc_all, conf_all, priors: PriorSet, packed: PackedTargets, iou_thresh, ratio, norm_wh, group):
@@ -217,6 +315,7 @@ class _FusedLoss(torch.autograd.Function):
         _lib.check(rc, "ssdhot_multibox_loss_fwd")
         if group is not None:
             # the only exchange of the sharded path: [sum smooth-L1, sum CE, sum positives]
+            _check_group_for_grad(group, need_grad)
             _dist.reduce_sums(sums, group)
         total = sums[2].clamp_min(1.0)
         if need_grad:
@@ -554,6 +653,7 @@ class _FusedLossHeads(torch.autograd.Function):
         _lib.check(rc, "ssdhot_multibox_loss_heads_fwd")
         hs.used_on(torch.cuda.current_stream(dev))
         if group is not None:
+            _check_group_for_grad(group, need_grad)
             _dist.reduce_sums(sums, group)
         total = sums[2].clamp_min(1.0)
         if need_grad:
@@ -620,10 +720,12 @@ def multibox_loss_heads(model, loc_heads: Sequence[torch.Tensor], conf_heads: Se
 # ------------------------------------------------------------------------------------------------
 # patching the reference in place
 # ------------------------------------------------------------------------------------------------
-def patch(model=None, trainer_module=None):
+def patch(model=None, trainer_module=None, steps: bool = True):
     """Route a reference `mySSD` instance and/or the imported `SSD_trainer` module through ssdhot:
-    model.encode_ssd / decode_ssd / iou_nms / predict and trainer.build_targets /
-    trainer.CELoss_w_neg_mining keep their signatures."""
+    model.encode_ssd / decode_ssd / iou_nms / predict and trainer.build_targets / CELoss_w_neg_mining /
+    collate_detection keep their signatures.  With `steps` the module's SSD_train_step /
+    SSD_test_step are replaced by the fused forms (ssdhot/trainer.py: one launch for targets + both losses, straight
+    from the head outputs); the reference's own step functions also run unchanged on the patched callables."""
     import types
     if model is not None:
         model.encode_ssd = types.MethodType(lambda self, *a, **k: encode_ssd(self, *a, **k), model)
@@ -631,6 +733,11 @@ def patch(model=None, trainer_module=None):
         model.decode_ssd = decode_ssd
         model.iou_nms = iou_nms
     if trainer_module is not None:
+        from . import trainer as _trainer
         trainer_module.build_targets = build_targets
         trainer_module.CELoss_w_neg_mining = CELoss_w_neg_mining
+        trainer_module.collate_detection = collate_detection
+        if steps:
+            trainer_module.SSD_train_step = _trainer.SSD_train_step
+            trainer_module.SSD_test_step = _trainer.make_test_step(trainer_module if hasattr(trainer_module, "MeanAveragePrecision") else None)
     return model

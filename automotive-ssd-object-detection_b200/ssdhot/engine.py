@@ -45,7 +45,7 @@ class HotPathStep:
         self.boxes = torch.zeros((self.B, m, 4), dtype=torch.float32, device=dev)
         self.count = torch.zeros((self.B,), dtype=torch.int32, device=dev)
         self.n_pos = torch.zeros((self.B,), dtype=torch.int32, device=dev)
-        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self._graphs: Dict[tuple, tuple] = {}      # key -> (graph, tensors kept alive), in LRU order
 
     # -- raw launches -------------------------------------------------------------------------
     def launch_loss(self, loc: torch.Tensor, conf: torch.Tensor, gt: PackedTargets, stream: int) -> None:
@@ -119,20 +119,34 @@ class HotPathStep:
             if self.infer_half:
                 self.launch_predict(loc, conf_infer, cur.cuda_stream)
             return
-        key = (loc.data_ptr(), conf_train.data_ptr(), conf_infer.data_ptr(), gt.boxes.data_ptr(), gt.max_gt)
-        g = self._graphs.get(key)
-        if g is None:
+        tensors = (loc, conf_train, conf_infer, gt.boxes, gt.labels, gt.offsets)
+        g = self._graph_for(("packed",) + tuple(t.data_ptr() for t in tensors) + (gt.max_gt,), tensors,
+                            lambda: self.run(loc, conf_train, conf_infer, gt))
+        g.replay()
+
+    GRAPH_CACHE = 16
+
+    def _graph_for(self, key, keep_alive, issue) -> "torch.cuda.CUDAGraph":
+        """The captured step for this exact set of input buffers.  The key holds EVERY captured pointer and the cache entry
+        keeps the tensors alive next to the graph, so an address cannot be recycled by the caching allocator while a graph
+        still points at it; the cache is bounded (least recently used entry dropped)."""
+        hit = self._graphs.pop(key, None)
+        if hit is None:
+            dev = self.ps.device
             g = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
-                self.run(loc, conf_train, conf_infer, gt)            # warm (sets smem attributes)
+                issue()                                              # warm (sets the shared-memory opt-ins)
                 side.synchronize()
                 with torch.cuda.graph(g, stream=side):
-                    self.run(loc, conf_train, conf_infer, gt)
+                    issue()
             torch.cuda.current_stream(dev).wait_stream(side)
-            self._graphs[key] = g
-        g.replay()
+            hit = (g, keep_alive)
+            while len(self._graphs) >= self.GRAPH_CACHE:
+                self._graphs.pop(next(iter(self._graphs)))
+        self._graphs[key] = hit                                      # (re-inserted last = most recently used)
+        return hit[0]
 
     def run_heads(self, train_heads: HeadSet, infer_heads: HeadSet, gt: PackedTargets, use_graph: bool = False) -> None:
         """run() fed by the head outputs (HeadSet: NCHW or channels_last) instead of loc_all / conf_all: both halves read the
@@ -149,20 +163,10 @@ class HotPathStep:
             self._reduce()
             cur.wait_stream(self._fork)
             return
-        key = ("heads", id(train_heads), id(infer_heads), gt.boxes.data_ptr(), gt.max_gt)
-        g = self._graphs.get(key)
-        if g is None:
-            g = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream(dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                self.run_heads(train_heads, infer_heads, gt)         # warm (sets smem attributes)
-                side.synchronize()
-                with torch.cuda.graph(g, stream=side):
-                    self.run_heads(train_heads, infer_heads, gt)
-            torch.cuda.current_stream(dev).wait_stream(side)
-            self._graphs[key] = g
-            self._keep = getattr(self, "_keep", []) + [train_heads, infer_heads]      # the graph holds their pointers
+        tensors = tuple(train_heads.tensors) + tuple(infer_heads.tensors) + (gt.boxes, gt.labels, gt.offsets)
+        g = self._graph_for(("heads", train_heads.layout, infer_heads.layout) + tuple(t.data_ptr() for t in tensors) + (gt.max_gt,),
+                            tensors + (train_heads, infer_heads),    # (the HeadSets own the host pointer arrays the launches read)
+                            lambda: self.run_heads(train_heads, infer_heads, gt))
         g.replay()
 
     def _reduce(self) -> None:

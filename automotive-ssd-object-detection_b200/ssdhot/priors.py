@@ -74,21 +74,25 @@ class PriorSet:
         routes matching through the layout-agnostic kernels (used by the parity tests)."""
         return cls(default_boxes().to(device), None, variances, generic=generic)
 
-    _cache = {}
+    _cache = {}            # (buffer address, device, variances) -> PriorSet, least recently used first; at most CACHE entries
+    CACHE = 8
 
     @classmethod
     def of(cls, model) -> "PriorSet":
-        """PriorSet of a reference `mySSD` (uses its `priors` / `priors_xyxy` buffers and variances),
-        cached per buffer; a PriorSet is returned unchanged."""
+        """PriorSet of a reference `mySSD` (uses its `priors` / `priors_xyxy` buffers and variances), cached per buffer --
+        several models (a train and an eval copy, say) alternate without re-deriving their tables; a PriorSet is returned
+        unchanged.  A cached entry keeps the model's prior buffer alive, so its address cannot be recycled under the key."""
         if isinstance(model, PriorSet):
             return model
         pri = model.priors
         key = (pri.data_ptr(), pri.device, getattr(model, "variance_center", 0.1), getattr(model, "variance_size", 0.2))
-        hit = cls._cache.get(key)
+        hit = cls._cache.pop(key, None)
         if hit is None:
             hit = cls(pri, getattr(model, "priors_xyxy", None),
                       (getattr(model, "variance_center", 0.1), getattr(model, "variance_size", 0.2)),
                       (getattr(model, "img_h", 300), getattr(model, "img_w", 300)))
-            cls._cache.clear()
-            cls._cache[key] = hit
+            hit.source = pri
+            while len(cls._cache) >= cls.CACHE:
+                cls._cache.pop(next(iter(cls._cache)))
+        cls._cache[key] = hit
         return hit

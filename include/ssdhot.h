@@ -39,6 +39,7 @@ extern "C" {
 #define SSDHOT_MAX_PRIORS 10240   /* 8 CTAs x 256 threads x 5 priors per image cluster */
 #define SSDHOT_MAX_GT 2048        /* ground-truth boxes per image held in shared memory */
 #define SSDHOT_MAX_CLASSES 256
+#define SSDHOT_MAX_CLASSES_BWD 127   /* with sel_cls (the backward's int8 class record): SSDHOT_ERR_SHAPE beyond it */
 
 typedef enum {
     SSDHOT_OK = 0,

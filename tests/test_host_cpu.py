@@ -76,6 +76,12 @@ def test_validation_happens_before_launch_no_gpu_needed():
                                             0.5, 0.1, 0.2, 3.0, 16, 16, None, None, None, None, None) == -2    # needs the SSD300 layout
     assert L.ssdhot_multibox_loss_heads_bwd(16, 16, 16, 1, 300.0, 300.0, ptr(six), ptr(six), 5, 6, 0.1, 0.2, 16, 16, 16,
                                             ptr(six), ptr(six), None) == -3
+    # the backward's class record sel_cls is an int8: more than 127 classes are refused when it is requested (forward-only is fine up to 256)
+    fwd = lambda C, sel: L.ssdhot_multibox_loss_fwd(16, 16, 16, 8732, 0, 16, 16, 16, 1, 4, 300.0, 300.0, 16, 16, C,
+                                                     0.5, 0.1, 0.2, 3.0, 16, 20, sel, None, None, None, None)
+    assert fwd(200, 16) == -2 and fwd(200, None) == -5 and fwd(127, 16) == -5      # (-5: past the shape checks, stopped by the misaligned workspace)
+    assert L.ssdhot_mined_ce_fwd(16, 16, 16, 1, 8732, 128, 3.0, 16, 16, 16, None) == -2
+    assert L.ssdhot_multibox_loss_bwd(16, 8732, 16, 16, 1, 300.0, 300.0, 16, 16, 128, 0.1, 0.2, 16, 16, 16, 16, 16, None) == -2
     # peer all-reduce: rank / world / lag are checked before anything is launched
     one = (ctypes.c_void_p * 1)(16)
     assert L.ssdhot_allreduce_sums_peer(16, ptr(one), 0, 9, 0, None, None) == -2
@@ -126,6 +132,43 @@ def test_pack_targets_ragged_and_empty():
     from ssdhot import synth
     b, l, o = synth.pack_targets(t)
     assert torch.equal(b, p.boxes) and torch.equal(l, p.labels) and torch.equal(o, p.offsets)
+
+
+def test_collate_detection_packs_one_buffer():
+    """SSD_trainer.collate_detection drop-in (TR:806-813): images stacked, the ragged ground truth in ONE byte buffer
+    [offsets | boxes | labels] whose views are what the kernels read; as_list() gives the reference's List[Dict] back."""
+    import ssdhot
+    g = torch.Generator().manual_seed(5)
+    counts = [3, 0, 1, 7, 0]
+    batch = []
+    for c in counts:
+        tgt = {"boxes": torch.rand((c, 4), generator=g) * 300, "labels": torch.randint(0, 5, (c,), generator=g),
+               "image_id": torch.tensor([len(batch)])}
+        batch.append((torch.rand((3, 8, 8), generator=g), tgt))
+    images, packed = ssdhot.collate_detection(batch)
+    assert images.shape == (5, 3, 8, 8) and torch.equal(images[3], batch[3][0])
+    assert isinstance(packed, ssdhot.PackedTargets) and packed.n_img == 5 and packed.max_gt == 7 and packed.counts == counts
+    assert packed.offsets.tolist() == [0, 3, 3, 4, 11, 11] and packed.offsets.dtype == torch.int32
+    box_off, lab_off, nbytes = ssdhot.PackedTargets.layout(5, 11)
+    assert packed.buffer.numel() == nbytes and box_off % 16 == 0 and lab_off % 8 == 0
+    base = packed.buffer.data_ptr()
+    assert packed.offsets.data_ptr() == base and packed.boxes.data_ptr() == base + box_off and packed.labels.data_ptr() == base + lab_off
+    back = packed.as_list()
+    for (_, tgt), got in zip(batch, back):
+        assert torch.equal(got["boxes"], tgt["boxes"].reshape(-1, 4)) and torch.equal(got["labels"], tgt["labels"])
+    # the same content as pack_targets of the reference's collate output, and idempotent
+    ref = ssdhot.pack_targets([t for _, t in batch], "cpu")
+    assert torch.equal(ref.boxes, packed.boxes) and torch.equal(ref.labels, packed.labels) and torch.equal(ref.offsets, packed.offsets)
+    assert ssdhot.pack_targets(packed, "cpu") is packed
+    # a batch without a single box
+    _, empty = ssdhot.collate_detection([(torch.zeros((3, 4, 4)), {"boxes": torch.zeros((0, 4)), "labels": torch.zeros((0,), dtype=torch.int64)})] * 2)
+    assert empty.offsets.tolist() == [0, 0, 0] and empty.max_gt == 0 and empty.total == 0 and len(empty.as_list()) == 2
+    assert empty.as_list()[0]["boxes"].shape == (0, 4)
+    # through a DataLoader (worker processes collate, the loader's pin thread would pin): same batches
+    ds = [b for b in batch]
+    loader = torch.utils.data.DataLoader(ds, batch_size=2, collate_fn=ssdhot.collate_detection, num_workers=0)
+    got = [(im.shape[0], pk.offsets.tolist()) for im, pk in loader]
+    assert got == [(2, [0, 3, 3]), (2, [0, 1, 8]), (1, [0, 0])]
 
 
 def test_synth_is_deterministic_and_shaped():
