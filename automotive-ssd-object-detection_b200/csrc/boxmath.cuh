@@ -89,14 +89,21 @@ __device__ __forceinline__ float4 decode_box(float4 l, float4 p, float vc, float
     return o;
 }
 
-// cxcywh (normalised) -> clamped pixel xyxy (SSD_from_scratch.py:422-425).
+// torch.clamp(v, 0, 1): NaN propagates (ATen clamp = min(max(v, lo), hi) with NaN-propagating min / max), unlike fminf / fmaxf.
+__device__ __forceinline__ float clamp01_nan(float v) {
+    const float c = fminf(fmaxf(v, 0.0f), 1.0f);
+    return (v != v) ? v : c;
+}
+
+// cxcywh (normalised) -> clamped pixel xyxy (SSD_from_scratch.py:422-425).  A NaN coordinate stays NaN (its box then has a
+// NaN area, fails no IoU gate and suppresses / is suppressed exactly as in the reference, SFS:690).
 __device__ __forceinline__ float4 to_pixel_xyxy(float4 c, float img_w, float img_h) {
     const float hw = fmul(0.5f, c.z), hh = fmul(0.5f, c.w);
     float4 o;
-    o.x = fmul(fminf(fmaxf(fsub(c.x, hw), 0.0f), 1.0f), img_w);
-    o.y = fmul(fminf(fmaxf(fsub(c.y, hh), 0.0f), 1.0f), img_h);
-    o.z = fmul(fminf(fmaxf(fadd(c.x, hw), 0.0f), 1.0f), img_w);
-    o.w = fmul(fminf(fmaxf(fadd(c.y, hh), 0.0f), 1.0f), img_h);
+    o.x = fmul(clamp01_nan(fsub(c.x, hw)), img_w);
+    o.y = fmul(clamp01_nan(fsub(c.y, hh)), img_h);
+    o.z = fmul(clamp01_nan(fadd(c.x, hw)), img_w);
+    o.w = fmul(clamp01_nan(fadd(c.y, hh)), img_h);
     return o;
 }
 

@@ -668,7 +668,10 @@ __device__ __forceinline__ float approx_ce6(float x0, float x1, float x2, float 
     const float d0 = x0 - mx;
     const float s = ((ex2_approx(d0 * k) + ex2_approx((x1 - mx) * k)) + (ex2_approx((x2 - mx) * k) + ex2_approx((x3 - mx) * k))) +
                     (ex2_approx((x4 - mx) * k) + ex2_approx((x5 - mx) * k));
-    return fmaxf(lg2_approx(s) * 0.6931471805599453f - d0, 0.0f);
+    const float ce = lg2_approx(s) * 0.6931471805599453f - d0;
+    // a NaN / +-Inf logit makes the exact CE NaN or +Inf, which torch.topk ranks above every number (TR:597): keep it non-finite
+    // here (fmaxf would turn NaN into 0) so that its key lands in the top, unresolved bin and the exact arithmetic decides
+    return (ce != ce) ? __int_as_float(0x7fffffff) : fmaxf(ce, 0.0f);
 }
 __device__ __forceinline__ float ce_error_bound(float ce) { return 1e-5f + 1e-6f * ce; }
 

@@ -60,6 +60,58 @@ def predict_inputs(g):
     return loc, conf
 
 
+def _patched(t: torch.Tensor, idx: np.ndarray, val: np.ndarray) -> torch.Tensor:
+    t = t.clone()
+    i = torch.from_numpy(idx.astype(np.int64))
+    if i.numel():
+        t[i[:, 0], i[:, 1], i[:, 2]] = torch.from_numpy(val.copy())
+    return t
+
+
+def nonfinite_predict_inputs(g):
+    """(loc, conf) of nonfinite.npz's predict half: cfg 3, two images, de-duplicated scores, then the NaN / Inf patches."""
+    cfg = synth.config(3, batch=2)
+    conf = _patched(cfg["conf_infer"], g["pred_dedup_idx"], g["pred_dedup_val"])
+    return _patched(cfg["loc_all"], g["pred_loc_idx"], g["pred_loc_val"]), _patched(conf, g["pred_conf_idx"], g["pred_conf_val"])
+
+
+def nonfinite_loss_cases(g):
+    """Yields (name, loc, conf, targets, cfg, (want_loc_loss, want_conf_loss)) for the loss half of nonfinite.npz (cfg 1)."""
+    cfg = synth.config(1)
+    assert sha(cfg["loc_all"]) == str(g["loss_loc_sha"]) and sha(cfg["conf_train"]) == str(g["loss_conf_sha"])
+    starts = g["loss_case_start"]
+    for k, name in enumerate(g["loss_case_names"]):
+        idx, val = g["loss_idx"][starts[k]:starts[k + 1]], g["loss_val"][starts[k]:starts[k + 1]]
+        which = str(g["loss_case_which"][k])
+        loc = _patched(cfg["loc_all"], idx, val) if which == "loc" else cfg["loc_all"]
+        conf = _patched(cfg["conf_train"], idx, val) if which == "conf" else cfg["conf_train"]
+        yield str(name), loc, conf, cfg["targets"], cfg, (float(g["loss_want"][k][0]), float(g["loss_want"][k][1]))
+
+
+def same_float(a: float, b: float, rel: float = 1e-5) -> bool:
+    """Equality of two loss values that may be NaN or infinite."""
+    if a != a or b != b:
+        return a != a and b != b
+    if a in (float("inf"), float("-inf")) or b in (float("inf"), float("-inf")):
+        return a == b
+    return abs(a - b) <= rel * max(abs(a), abs(b), 1e-30)
+
+
+def equal_nan(a: torch.Tensor, b: torch.Tensor) -> bool:
+    """torch.equal that treats NaN == NaN (same shape, same dtype, same values)."""
+    return a.shape == b.shape and a.dtype == b.dtype and bool(torch.isclose(a, b, rtol=0.0, atol=0.0, equal_nan=True).all())
+
+
+def split_rows(counts, labels, scores, boxes):
+    ends = np.cumsum(counts)
+    out = []
+    for i, e in enumerate(ends):
+        s = e - counts[i]
+        out.append({"labels": torch.from_numpy(labels[s:e].astype(np.int64)), "scores": torch.from_numpy(scores[s:e].copy()),
+                    "boxes": torch.from_numpy(boxes[s:e].copy()).reshape(-1, 4)})
+    return out
+
+
 def split_predictions(g):
     counts = g["counts"]
     ends = np.cumsum(counts)

@@ -858,3 +858,82 @@ def test_hot_path_step_from_heads_equals_packed(env):
                 k = int(want[1][b])
                 assert bit_equal(step.labels[b, :k], want[2][b, :k]) and bit_equal(step.scores[b, :k], want[3][b, :k])
                 assert bit_equal(step.boxes[b, :k], want[4][b, :k])
+
+
+def test_nonfinite_head_outputs(env):
+    """NaN / +-Inf rows in loc_all / conf_all (tests/golden/nonfinite.npz, produced by the reference; SURVEY.md section 7
+    hard part 3): candidates, keep lists and labels bit-exact, NaN boxes stay NaN (torch.clamp propagates them) and suppress
+    their class, NaN / Inf cross-entropies are mined first -- packed tensors and both head layouts, fast and generic paths."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    g = U.load("nonfinite.npz")
+    loc, conf = U.nonfinite_predict_inputs(g)
+    lg, cg = loc.to(dev), conf.to(dev)
+    for agn, pre in ((False, "pred"), (True, "agn")):
+        gold = U.split_rows(g[pre + "_counts"], g[pre + "_labels"], g[pre + "_scores"], g[pre + "_boxes"])
+        want = O.postprocess(env["pri"], lg, cg, 0.01, 0.45, 200, agn, nms_limit=True)
+        got = s.predict(ps, None, 0.01, 0.45, 200, agn, pre_loc_all=lg, pre_conf_all=cg)
+        heads = [s.predict_heads(ps, U.unpack_heads(lg, cl), U.unpack_heads(cg, cl), 0.01, 0.45, 200, agn) for cl in (False, True)]
+        n_nan = 0
+        for b, (a, w, r) in enumerate(zip(got, want, gold)):
+            assert bit_equal(a["labels"], r["labels"]), f"labels / keep list vs the reference, image {b}"
+            assert close(a["scores"], r["scores"]) and close(a["boxes"], r["boxes"], atol=BOX_ATOL)
+            assert bool((torch.isnan(a["boxes"].cpu()) == torch.isnan(r["boxes"])).all())
+            assert bit_equal(a["labels"], w["labels"]) and bit_equal(a["scores"], w["scores"]) and bit_equal(a["boxes"], w["boxes"])
+            for h in heads:
+                assert bit_equal(h[b]["labels"], a["labels"]) and bit_equal(h[b]["scores"], a["scores"]) and bit_equal(h[b]["boxes"], a["boxes"])
+            n_nan += int(torch.isnan(a["boxes"]).any())
+        assert n_nan >= 1
+    generic = s.PriorSet.default(dev, generic=True)
+    for name, loc1, conf1, targets, cfg, (w_loc, w_conf) in U.nonfinite_loss_cases(g):
+        l1, c1 = loc1.to(dev), conf1.to(dev)
+        for tag, pset in (("fast", ps), ("generic", generic)):
+            l_loc, l_conf = s.multibox_loss(pset, l1, c1, targets, cfg["iou_thresh"], cfg["ratio"])
+            assert U.same_float(l_loc.item(), w_loc) and U.same_float(l_conf.item(), w_conf), (name, tag, l_loc.item(), w_loc, l_conf.item(), w_conf)
+        for cl in (False, True):
+            h_loc, h_conf = s.multibox_loss_heads(ps, U.unpack_heads(l1, cl), U.unpack_heads(c1, cl), targets, cfg["iou_thresh"], cfg["ratio"])
+            assert U.same_float(h_loc.item(), w_loc) and U.same_float(h_conf.item(), w_conf), (name, cl)
+        # the drop-in pieces on the reference's own targets
+        pos, loc_pm, cls = s.build_targets(ps, targets, 300, 300, cfg["iou_thresh"], "cuda")
+        total = pos.sum().clamp_min(1).float()
+        ce = s.CELoss_w_neg_mining(c1, cls, pos, pos.sum(1), total, cfg["ratio"])
+        assert U.same_float(ce.item(), w_conf), (name, ce.item(), w_conf)
+
+
+def test_full_size_stress_config(env):
+    """BASELINE cfg 5 at FULL size (B = 1024, 64 boxes per image, score threshold 0.0 so that all 8732 x 5 pairs of every
+    image enter NMS): the whole batch runs through the kernels; 8 randomly chosen images are compared with the device-matched
+    oracle (matches, class targets, offsets, per-image loss sums, keep lists, scores, boxes), the rest through the
+    size-independent properties (sharded sums == whole-batch sums, counts, score order)."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    from ssdhot import synth
+    B = 1024
+    cfg = synth.config(5)
+    assert cfg["batch"] == B and all(t["boxes"].shape[0] == 64 for t in cfg["targets"])
+    lg, ct = cfg["loc_all"].to(dev), cfg["conf_train"].to(dev)
+    packed = s.pack_targets(cfg["targets"], dev)
+    pick = sorted(torch.randperm(B, generator=torch.Generator().manual_seed(55))[:8].tolist())
+    # ---- match + encode + mined loss ----
+    r = s.match_encode_batch(ps, packed, 0.5, (300, 300), want_loc="positives")
+    l_loc, l_conf, sums = s.multibox_loss(ps, lg, ct, packed, 0.5, 3.0, return_sums=True)
+    assert int(r["n_pos"].sum()) == int(sums[2].item())
+    part = torch.zeros((3,), dtype=torch.float64, device=dev)
+    for lo in range(0, B, 256):                                        # four shards: the sums add up (cfg 4's property)
+        part += s.multibox_loss(ps, lg[lo:lo + 256], ct[lo:lo + 256], cfg["targets"][lo:lo + 256], 0.5, 3.0, return_sums=True)[2]
+    assert close(part[:2], sums[:2], rtol=1e-12) and part[2].item() == sums[2].item()
+    for b in pick:
+        tg = to_dev(cfg["targets"][b:b + 1], dev)
+        pos_o, locpm_o, cls_o = O.batch_targets(env["pri"], env["pri_xyxy"], tg, 300, 300, 0.5)
+        assert bit_equal(r["pos_mask"][b:b + 1], pos_o) and bit_equal(r["cls_t"][b:b + 1], cls_o), f"image {b}"
+        assert bit_equal(r["loc_t"][b][r["pos_mask"][b]], locpm_o)
+        o_loc, o_conf = O.train_half(env["pri"], env["pri_xyxy"], lg[b:b + 1], ct[b:b + 1], tg, 0.5, 3.0)
+        i_loc, i_conf = s.multibox_loss(ps, lg[b:b + 1], ct[b:b + 1], cfg["targets"][b:b + 1], 0.5, 3.0)
+        assert close(i_loc, o_loc) and close(i_conf, o_conf), f"image {b}"
+    # ---- decode + threshold 0.0 + DIoU-NMS ----
+    ci = cfg["conf_infer"].to(dev)
+    labels, scores, boxes, count, cand = s.predict_padded(ps, lg, ci, 0.0, 0.45, 200, want_cand=True)
+    assert int(count.min()) == 200 and int(count.max()) == 200         # 43,660 candidates per image: the cap is always reached
+    assert bool((scores[:, 1:] <= scores[:, :-1]).all())               # score-descending
+    want = O.postprocess(env["pri"], lg[pick], ci[pick], 0.0, 0.45, 200, False, nms_limit=True, with_index=True)
+    for k, b in enumerate(pick):
+        assert bit_equal(cand[b, :200].long(), want[k]["cand"]), f"keep list, image {b}"
+        assert bit_equal(labels[b], want[k]["labels"]) and bit_equal(scores[b], want[k]["scores"]) and bit_equal(boxes[b], want[k]["boxes"])

@@ -138,3 +138,21 @@ def test_pack_heads_restatement_layout():
             assert torch.equal(conf_all[:, p, :], ch[:, k * C:(k + 1) * C, y, x])
         off += n * n * a
     assert off == 8732
+
+
+def test_nonfinite_head_outputs_bitwise():
+    """NaN / +-Inf in loc_all / conf_all (tests/golden/make_golden_nonfinite.py ran the reference): the restatement keeps the
+    reference's propagation rules -- torch.clamp / maximum / minimum keep NaN, NaN > thresh is False, `d <= thr` is False
+    for a NaN box, torch.topk ranks NaN / Inf cross-entropies first."""
+    g = U.load("nonfinite.npz")
+    pri, xyxy = O.prior_tables()
+    loc, conf = U.nonfinite_predict_inputs(g)
+    for agn, pre in ((False, "pred"), (True, "agn")):
+        want = U.split_rows(g[pre + "_counts"], g[pre + "_labels"], g[pre + "_scores"], g[pre + "_boxes"])
+        got = O.postprocess(pri, loc, conf, 0.01, 0.45, 200, agn)
+        assert sum(int(torch.isnan(w["boxes"]).any()) for w in want) >= 1
+        for a, b in zip(got, want):
+            assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["scores"], b["scores"]) and U.equal_nan(a["boxes"], b["boxes"])
+    for name, loc1, conf1, targets, cfg, (w_loc, w_conf) in U.nonfinite_loss_cases(g):
+        l_loc, l_conf = O.train_half(pri, xyxy, loc1, conf1, targets, cfg["iou_thresh"], cfg["ratio"])
+        assert U.same_float(l_loc.item(), w_loc, 0.0) and U.same_float(l_conf.item(), w_conf, 0.0), (name, l_loc.item(), w_loc, l_conf.item(), w_conf)

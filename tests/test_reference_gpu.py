@@ -128,6 +128,7 @@ def test_reference_step_functions_run_through_patch(env):
             h.weight.mul_(40.0)
             h.bias.normal_()
     loader = _loader(synth, 2, 2, seed=3)
+    train_loader = _loader(synth, 2, 4, seed=4)
     thr = _calibrated_thresh(base, loader, dev)
     state = copy.deepcopy(base.state_dict())
     originals = {k: getattr(tr, k) for k in ("build_targets", "CELoss_w_neg_mining", "collate_detection", "SSD_train_step", "SSD_test_step")}
@@ -152,15 +153,27 @@ def test_reference_step_functions_run_through_patch(env):
             tr.MeanAveragePrecision = orig_cls
         return out, captured
 
+    def param_distance(a, b):
+        """Relative L2 distance of two parameter UPDATES (state after training minus the common initial state), all tensors
+        together: a tensor whose gradient is pure rounding noise (a conv bias in front of a batch-norm) cannot dominate."""
+        num = den = 0.0
+        for k, v in b.items():
+            if "num_batches_tracked" not in k:
+                num += float(((a[k] - v).double() ** 2).sum())
+                den += float(((v - state[k].to(v.device)).double() ** 2).sum())
+        return (num / max(den, 1e-300)) ** 0.5
+
     def run_train(m):
         opt = torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.0)
-        out = tr.SSD_train_step(model=m, dataloader=_fresh(loader), optimizer=opt, iou_thresh=0.5, neg_pos_ratio=3.0, device="cuda")
+        out = tr.SSD_train_step(model=m, dataloader=_fresh(train_loader), optimizer=opt, iou_thresh=0.5, neg_pos_ratio=3.0, device="cuda")
         return out, {k: v.detach().clone() for k, v in m.state_dict().items() if v.dtype.is_floating_point}
 
     try:
         # --- unpatched reference ----------------------------------------------------------------------------------
         ref_eval, ref_preds = run_eval(new_model())
         ref_train, ref_params = run_train(new_model())
+        _, again = run_train(new_model())           # the reference against itself: the run-to-run noise of two SGD steps
+        noise = param_distance(again, ref_params)   # through a VGG-16 with batch-norm in train mode (cuDNN's backward is not bit-reproducible)
         results = {}
         for mode, steps in (("dropins", False), ("fused", True)):
             for k, v in originals.items():
@@ -191,13 +204,8 @@ def test_reference_step_functions_run_through_patch(env):
         for key in ("training loss", "localization loss", "classification loss"):
             assert close(trn[key], ref_train[key], 1e-4), (mode, key, trn[key], ref_train[key])     # (batch 2 sees the weights of step 1)
         assert set(trn.keys()) == set(ref_train.keys()) and set(trn["timing"].keys()) == set(ref_train["timing"].keys())
-        worst = 0.0
-        for k, v in ref_params.items():
-            if "num_batches_tracked" in k:
-                continue
-            d = (params[k] - v).abs().max().item()
-            worst = max(worst, d / max(v.abs().max().item(), 1e-6))
-        assert worst < 1e-3, (mode, worst)      # two SGD steps through a VGG-16: cuDNN's backward is not bit-reproducible
+        worst = param_distance(params, ref_params)
+        assert worst <= max(1e-3, 20.0 * noise), (mode, worst, noise)
 
 
 def test_patched_model_methods_keep_reference_call_forms(env):
