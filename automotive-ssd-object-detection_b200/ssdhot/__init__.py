@@ -13,7 +13,7 @@ __version__ = "0.1.0"
 
 from ._lib import SsdhotError, launch_count, lib  # noqa: F401
 from .priors import PriorSet, default_boxes  # noqa: F401
-from .api import (CELoss_w_neg_mining, HeadSet, PackedTargets, build_targets, collate_detection, decode_ssd, encode_ssd, forward_heads, iou_nms,  # noqa: F401
+from .api import (CELoss_w_neg_mining, HeadSet, PackedTargets, build_targets, collate_detection, decode_ssd, eval_step, encode_ssd, forward_heads, iou_nms,  # noqa: F401
                   match_encode_batch, multibox_loss, multibox_loss_heads, nms_sets, pack_heads, pack_targets, patch, predict,
                   predict_heads, predict_heads_padded, predict_padded, smooth_l1_positive_loss)
 from .trainer import SSD_test_step, SSD_train_step  # noqa: F401

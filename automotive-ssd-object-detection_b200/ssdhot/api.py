@@ -480,6 +480,37 @@ def predict(model, images: Optional[torch.Tensor], score_thresh: float = 0.2, nm
             for l, s, b, k in zip(labels.unbind(0), scores.unbind(0), boxes.unbind(0), ks)]
 
 
+_eval_fork: Dict[torch.device, "torch.cuda.Stream"] = {}
+
+
+@torch.no_grad()
+def eval_step(model, loc_all: torch.Tensor, conf_all: torch.Tensor, targets, iou_thresh: float = 0.5, neg_pos_ratio: float = 3.0,
+              score_thresh: float = 0.05, nms_thresh: float = 0.5, max_per_img: int = 100, class_agnostic: bool = False,
+              H: int = 300, W: int = 300, group=None, metric: str = "diou"):
+    """The post-backbone part of one SSD_test_step batch (SSD_trainer.py:214-256) on ONE pair of head outputs: targets + both
+    losses (one launch) and predict (two launches), which share nothing but the read-only inputs and therefore run on two
+    streams.  -> (loc_loss, conf_loss, labels [B,max] i64, scores [B,max], boxes [B,max,4], count [B] i32), all on the
+    device, no host synchronisation."""
+    dev = _need_cuda(loc_all, conf_all)
+    cur = torch.cuda.current_stream(dev)
+    side = _eval_fork.get(dev)
+    if side is None:
+        side = _eval_fork[dev] = torch.cuda.Stream(dev)
+    priors = PriorSet.of(model)
+    packed = pack_targets(targets, dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        labels, scores, boxes, count = predict_padded(priors, loc_all, conf_all, score_thresh, nms_thresh, max_per_img,
+                                                      class_agnostic, metric)
+    l_loc, l_conf = multibox_loss(priors, loc_all, conf_all, packed, iou_thresh, neg_pos_ratio, H, W, group)
+    cur.wait_stream(side)
+    for t in (loc_all, conf_all):
+        t.record_stream(side)
+    for t in (labels, scores, boxes, count):
+        t.record_stream(cur)
+    return l_loc, l_conf, labels, scores, boxes, count
+
+
 # ------------------------------------------------------------------------------------------------
 # head-output packing (the tail of mySSD.forward)
 # ------------------------------------------------------------------------------------------------

@@ -40,8 +40,10 @@ P, C = 8732, 6
 METRIC = "images/s for match+mined loss and decode+DIoU-NMS at bs=256 per GPU"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each half's kernels at this workload, from the
 # `ncu --set full` capture summarised in profiles/ (train_image_kernel; score_kernel + nms_image_kernel)
-WORKLOAD = ("cfg3: B=256/GPU eval-step post-backbone path (match+mined loss, then predict thr 0.01 / nms 0.45 / max 200), "
-            "P=8732, C=6, G~U{1..20}")
+WORKLOAD = ("cfg3: B=256/GPU eval-step post-backbone path on one (loc_all, conf_all) pair per batch, as SSD_test_step runs it "
+            "(match+mined loss, then predict thr 0.01 / nms 0.45 / max 200), P=8732, C=6, G~U{1..20}")
+TRAIN_KERNELS = "train_image_kernel + finalize_sums_kernel (match + encode + mined loss)"
+PREDICT_KERNELS = "score_kernel + nms_image_kernel (decode + threshold + rank + NMS)"
 TRAFFIC = {"match_loss": 57.24e6 + 0.78e6, "decode_nms": (53.73e6 + 0.60e6) + (31.74e6 + 0.01e6), "source": "profiles/r01_final2_ncu_full_summary.txt"}
 
 
@@ -167,7 +169,7 @@ def cpu_arm():
         mdl = R.model("cpu")
 
         def train(cfg, n):
-            R.train_half(cfg["loc_all"][:n], cfg["conf_train"][:n], cfg["targets"][:n], cfg["iou_thresh"], cfg["ratio"], mdl)
+            R.train_half(cfg["loc_all"][:n], cfg["conf_infer"][:n], cfg["targets"][:n], cfg["iou_thresh"], cfg["ratio"], mdl)
 
         def pred(cfg, n):
             R.predict_half(cfg["loc_all"][:n], cfg["conf_infer"][:n], cfg["score_thresh"], cfg["nms_thresh"], cfg["max_per_img"], False, mdl)
@@ -180,7 +182,7 @@ def port_arm():
     pri, pri_xyxy = O.prior_tables()
 
     def train(cfg, n):
-        O.train_half(pri, pri_xyxy, cfg["loc_all"][:n], cfg["conf_train"][:n], cfg["targets"][:n], cfg["iou_thresh"], cfg["ratio"])
+        O.train_half(pri, pri_xyxy, cfg["loc_all"][:n], cfg["conf_infer"][:n], cfg["targets"][:n], cfg["iou_thresh"], cfg["ratio"])
 
     def pred(cfg, n):
         O.postprocess(pri, cfg["loc_all"][:n], cfg["conf_infer"][:n], cfg["score_thresh"], cfg["nms_thresh"], cfg["max_per_img"], False)
@@ -270,11 +272,13 @@ def main():
     ap.add_argument("--serial", action="store_true", help="run the two halves back to back on one stream instead of forked")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N > 1: all-reduce of the three loss sums by the peer-memory kernel (in the CUDA graph) or by NCCL")
-    ap.add_argument("--collective-lag", type=int, default=1, choices=[0, 1],
-                    help="peer collective: 0 = each step waits for its own reduced sums, 1 = they arrive during the next step")
+    ap.add_argument("--collective-lag", type=int, default=0, choices=[0, 1],
+                    help="peer collective: 0 = each step waits for its own reduced sums (what a training step needs; the headline), "
+                         "1 = they arrive during the next step (eval-step logging only; also measured and printed as `lag1`)")
     ap.add_argument("--quick", action="store_true", help="diagnostics: only the main timed loop (no halves, roofline, heads, e2e)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-large-batch", action="store_true", help="skip the extra B=2048 roofline measurement")
+    ap.add_argument("--skip-strong", action="store_true", help="skip the strong-scaling cfg 4 section (B = 4096 over the job)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -294,6 +298,9 @@ def main():
     group = True if world > 1 else None
 
     # ---- synthetic inputs: N_SETS independent batches per rank, resident in HBM -------------------
+    # one (loc_all, conf_all) pair per batch feeds both halves, as in SSD_test_step (SSD_trainer.py:208-256); conf = cfg 3's
+    # inference logits (background biased, ~6.6 k candidates per image).  `conf_t` (no bias) only serves the `separate_conf`
+    # variant: the round-1 workload, where the loss half read its own logits.
     spec = None
     sets = []
     host_sets = []
@@ -301,92 +308,116 @@ def main():
         cfg = synth.config(CFG, batch=BATCH, seed_offset=rank * N_SETS + i)
         spec = spec or {k: cfg[k] for k in ("iou_thresh", "ratio", "score_thresh", "nms_thresh", "max_per_img")}
         host_sets.append(cfg)
-        sets.append(dict(loc=cfg["loc_all"].to(dev), conf_t=cfg["conf_train"].to(dev), conf_i=cfg["conf_infer"].to(dev),
+        sets.append(dict(loc=cfg["loc_all"].to(dev), conf=cfg["conf_infer"].to(dev), conf_t=cfg["conf_train"].to(dev),
                          gt=ssdhot.pack_targets(cfg["targets"], dev)))
     ps = ssdhot.PriorSet.default(dev)
     # the sharded path's one exchange: every step's [sum loc, sum CE, sum positives] is all-reduced.  Default: the peer-memory
-    # kernel (csrc/peer.cu) as a node of the step's CUDA graph; --collective nccl (or a box without CUDA IPC between the
-    # ranks): torch.distributed all-reduce on a side stream, outside the graph (a captured NCCL collective hung at process
-    # exit on this stack)
-    peer, reducer, collective = None, None, "none"
+    # kernel (csrc/peer.cu) as a node of the step's CUDA graph, lag 0 (every step waits for its own reduced sums);
+    # --collective nccl (or a box without CUDA IPC between the ranks): torch.distributed all-reduce on a side stream, outside
+    # the graph (a captured NCCL collective hung at process exit on this stack)
+    peer, peer_lag1, reducer, collective = None, None, None, "none"
     if group is not None:
         if args.collective == "peer":
             try:
                 peer = D.PeerSums(dev, lag=args.collective_lag)
-                collective = ("peer-memory kernel over NVLink (ssdhot_allreduce_sums_peer), inside the step's CUDA graph" +
-                              ("; the reduced sums of step s are delivered during step s+1 (lag 1), so the ranks are not "
-                               "re-synchronised every step" if args.collective_lag else ""))
+                peer_lag1 = D.PeerSums(dev, lag=1) if args.collective_lag == 0 else None
+                collective = ("peer-memory kernel over NVLink (ssdhot_allreduce_sums_peer), inside the step's CUDA graph, " +
+                              ("lag 1: the reduced sums of step s are delivered during step s+1" if args.collective_lag else
+                               "lag 0: every step waits for its own reduced sums"))
             except Exception as e:              # noqa: BLE001
                 print(f"[bench] rank {rank}: PeerSums unavailable ({e}); using NCCL", file=sys.stderr)
         ok = torch.tensor([1 if (peer is not None or args.collective != "peer") else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if args.collective == "peer" and int(ok.item()) == 0:
-            if peer is not None:
-                peer.close()
-            peer = None
+            for pr in (peer, peer_lag1):
+                if pr is not None:
+                    pr.close()
+            peer = peer_lag1 = None
         if peer is None:
             reducer = D.SumsReducer(dev)
             collective = "NCCL all-reduce (torch.distributed) on a side stream, outside the CUDA graph"
-    step = HotPathStep(ps, BATCH, C, spec["iou_thresh"], spec["ratio"], spec["score_thresh"], spec["nms_thresh"],
-                       spec["max_per_img"], concurrent=not args.serial, group=peer)
-    use_graph = not args.no_graph
 
-    def one_step(i):
-        s = sets[i % N_SETS]
-        step.run(s["loc"], s["conf_t"], s["conf_i"], s["gt"], use_graph=use_graph)
-        if reducer is not None:
-            reducer.submit(step.sums)
+    def make_step(grp):
+        return HotPathStep(ps, BATCH, C, spec["iou_thresh"], spec["ratio"], spec["score_thresh"], spec["nms_thresh"],
+                           spec["max_per_img"], concurrent=not args.serial, group=grp)
+    step = make_step(peer)
+    use_graph = not args.no_graph
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def timed_loop(stp, n_steps, separate=False, use_reducer=True):
+        """n_steps steps, CUDA events on the launching stream -> (ms total, max over ranks; per-rank list)."""
+        def one(i):
+            s = sets[i % N_SETS]
+            stp.run(s["loc"], s["conf_t"] if separate else s["conf"], s["conf"], s["gt"], use_graph=use_graph)
+            if reducer is not None and use_reducer:
+                reducer.submit(stp.sums)
+        for i in range(args.warmup):
+            one(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            # device-side rendezvous: the ranks leave the host barrier milliseconds apart, and a rank whose timed region
+            # started early would spend that skew waiting for its peers' first sums inside the region
+            dist.all_reduce(torch.zeros((1,), device=dev))
+        e0.record()
+        for i in range(n_steps):
+            one(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        per_rank = [float(ms.item())]
+        if world > 1:
+            every = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(every, ms)
+            per_rank = [float(t.item()) for t in every]
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), per_rank
+
     # launches per step (counted once, without the graph)
     s0 = sets[0]
     torch.cuda.synchronize(dev)
     n0 = ssdhot.launch_count()
-    step.run(s0["loc"], s0["conf_t"], s0["conf_i"], s0["gt"], use_graph=False)
+    step.run(s0["loc"], s0["conf"], s0["conf"], s0["gt"], use_graph=False)
     launches_per_step = ssdhot.launch_count() - n0
 
-    for i in range(args.warmup):
-        one_step(i)
+    # ---- the headline: EXACTLY --steps steps, then a sustained region of >= 0.25 s under the same clock sampler ---------
     sampler = ClockSampler(local)           # (opens NVML: slow and uneven across ranks, so before the barrier)
-    barrier()
     if not os.environ.get("BENCH_NO_SAMPLER"):
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
-        # device-side rendezvous: the ranks leave the host barrier milliseconds apart, and a rank whose timed region
-        # started early would spend that skew waiting for its peers' first sums inside the region
-        dist.all_reduce(torch.zeros((1,), device=dev))
-    e0.record()
-    for i in range(args.steps):
-        one_step(i)
-    e1.record()
-    barrier()
+    ms_total, per_rank_ms = timed_loop(step, args.steps)
+    ms_per_step = ms_total / args.steps
+    value = BATCH * world * args.steps / (ms_total / 1e3)
+    n_long = max(args.steps, int(250.0 / max(ms_per_step, 1e-3)) + 1)
+    ms_long, _ = timed_loop(step, n_long)
     clocks = sampler.result()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    per_rank_ms = [float(ms.item())]
-    if world > 1:
-        every = [torch.zeros_like(ms) for _ in range(world)]
-        dist.all_gather(every, ms)
-        per_rank_ms = [float(t.item()) for t in every]
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    sustained = {"steps": n_long, "ms_per_step": ms_long / n_long, "value": BATCH * world * n_long / (ms_long / 1e3),
+                 "note": "the same loop run long enough (>= 0.25 s) for the clock sampler to cover it; `clocks` spans both regions"}
     if args.quick:
         if rank == 0:
-            print(json.dumps({"quick": True, "n_gpus": world, "value": BATCH * world * args.steps / (ms_total / 1e3),
-                              "ms_per_step": ms_total / args.steps, "per_rank_ms_per_step": [t / args.steps for t in per_rank_ms],
+            print(json.dumps({"quick": True, "n_gpus": world, "value": value, "ms_per_step": ms_per_step, "sustained": sustained,
+                              "per_rank_ms_per_step": [t / args.steps for t in per_rank_ms],
                               "collective": collective, "clocks": clocks}))
         if world > 1:
             dist.barrier()
-            if peer is not None:
-                peer.close()
+            for pr in (peer, peer_lag1):
+                if pr is not None:
+                    pr.close()
             dist.destroy_process_group()
         return
-    ms_per_step = ms_total / args.steps
-    value = BATCH * world * args.steps / (ms_total / 1e3)
+    # the round-1 workload (the loss half reads its own, unbiased logits: two conf tensors per step) for continuity
+    ms_sep, _ = timed_loop(step, args.steps, separate=True)
+    separate = {"ms_per_step": ms_sep / args.steps, "value": BATCH * world * args.steps / (ms_sep / 1e3),
+                "note": "round-1 workload: conf_train for the loss half, conf_infer for predict (two logit tensors per step)"}
+    lag1 = None
+    if peer_lag1 is not None:
+        step_l1 = make_step(peer_lag1)
+        ms_l1, _ = timed_loop(step_l1, args.steps)
+        lag1 = {"ms_per_step": ms_l1 / args.steps, "value": BATCH * world * args.steps / (ms_l1 / 1e3),
+                "note": "peer collective with lag 1 (reduced sums arrive one step late: eval-step logging only, not a training step)"}
 
     # ---- per-half kernel time (CUDA events around each half, same rotation, direct launches) -------
     def time_half(train: bool, iters: int):
@@ -394,15 +425,13 @@ def main():
         st = torch.cuda.current_stream(dev).cuda_stream
         for i in range(3):
             s = sets[i % N_SETS]
-            step.launch_loss(s["loc"], s["conf_t"], s["gt"], st) if train else step.launch_predict(s["loc"], s["conf_i"], st)
+            step.launch_loss(s["loc"], s["conf"], s["gt"], st) if train else step.launch_predict(s["loc"], s["conf"], st)
         torch.cuda.synchronize(dev)
         for i, (a, b) in enumerate(evs):
             s = sets[i % N_SETS]
-            other = sets[(i + 1) % N_SETS]
             a.record()
-            step.launch_loss(s["loc"], s["conf_t"], s["gt"], st) if train else step.launch_predict(s["loc"], s["conf_i"], st)
+            step.launch_loss(s["loc"], s["conf"], s["gt"], st) if train else step.launch_predict(s["loc"], s["conf"], st)
             b.record()
-            _ = other
         torch.cuda.synchronize(dev)
         return statistics.mean(a.elapsed_time(b) for a, b in evs)
 
@@ -417,13 +446,12 @@ def main():
     dom_is_pred = ms_pred >= ms_loss
     dom_ms, dom_bytes = (ms_pred, bytes_pred) if dom_is_pred else (ms_loss, bytes_loss)
     roofline = {
-        "bound": "hbm", "kernel": "score_kernel + nms_image_kernel (decode + threshold + rank + NMS)" if dom_is_pred else
-        "train_image_kernel + finalize_sums_kernel (match + encode + mined loss)",
+        "bound": "hbm", "kernel": PREDICT_KERNELS if dom_is_pred else TRAIN_KERNELS,
         "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
         "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": TRAFFIC["decode_nms" if dom_is_pred else "match_loss"],
         "traffic_source": TRAFFIC["source"], "peak_source": peak_src,
-        "note": "algorithmic bytes = SURVEY.md 8(d) figure of the whole half (conf_all + loc_all + GT / outputs); the "
-                "kernels are instruction-issue and latency bound at this batch size, not DRAM bound (profiles/)",
+        "note": "algorithmic bytes = SURVEY.md 8(d) figure of the whole half (conf_all + loc_all + GT / outputs) over the CUDA-event "
+                "time of that half run alone; reported for the slower half (both under `parts`)",
         "parts": {
             "match_loss": {"ms": ms_loss, "algorithmic_bytes": bytes_loss, "achieved": bytes_loss / (ms_loss * 1e-3) / 1e9,
                            "frac": bytes_loss / (ms_loss * 1e-3) / 1e9 / peak, "images_per_s": BATCH / (ms_loss * 1e-3)},
@@ -443,9 +471,8 @@ def main():
         for sset in sets[:3]:
             v = {}
             for name, cl in (("nchw", False), ("nhwc", True)):
-                lh = synth.heads_from_packed(sset["loc"], cl)
-                cth, cih = synth.heads_from_packed(sset["conf_t"], cl), synth.heads_from_packed(sset["conf_i"], cl)
-                v[name] = dict(lh=lh, cth=cth, cih=cih, train=HeadSet(lh, cth), infer=HeadSet(lh, cih))
+                lh, ch = synth.heads_from_packed(sset["loc"], cl), synth.heads_from_packed(sset["conf"], cl)
+                v[name] = dict(lh=lh, ch=ch, hs=HeadSet(lh, ch))
             views.append(v)
 
         def torch_tail(heads, D):
@@ -454,13 +481,13 @@ def main():
         def run(mode, train, i):
             sset, v = sets[i % len(views)], views[i % len(views)]
             if mode in ("nchw", "nhwc"):
-                step.launch_loss_heads(v[mode]["train"], sset["gt"], st_) if train else step.launch_predict_heads(v[mode]["infer"], st_)
+                step.launch_loss_heads(v[mode]["hs"], sset["gt"], st_) if train else step.launch_predict_heads(v[mode]["hs"], st_)
                 return
             h = v["nchw"]
             if mode == "pack_then_packed":
-                loc, conf = ssdhot.pack_heads(h["lh"], h["cth"] if train else h["cih"])
+                loc, conf = ssdhot.pack_heads(h["lh"], h["ch"])
             else:
-                loc, conf = torch_tail(h["lh"], 4), torch_tail(h["cth"] if train else h["cih"], C)
+                loc, conf = torch_tail(h["lh"], 4), torch_tail(h["ch"], C)
             step.launch_loss(loc, conf, sset["gt"], st_) if train else step.launch_predict(loc, conf, st_)
 
         for train in (True, False):
@@ -483,13 +510,13 @@ def main():
             whole = {}
             for mode in ("nchw", "nhwc"):
                 for i in range(6):
-                    step.run_heads(views[i % len(views)][mode]["train"], views[i % len(views)][mode]["infer"], sets[i % len(views)]["gt"], use_graph=use_graph)
+                    step.run_heads(views[i % len(views)][mode]["hs"], views[i % len(views)][mode]["hs"], sets[i % len(views)]["gt"], use_graph=use_graph)
                 torch.cuda.synchronize(dev)
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 n = max(30, min(args.steps, 200))
                 a.record()
                 for i in range(n):
-                    step.run_heads(views[i % len(views)][mode]["train"], views[i % len(views)][mode]["infer"], sets[i % len(views)]["gt"], use_graph=use_graph)
+                    step.run_heads(views[i % len(views)][mode]["hs"], views[i % len(views)][mode]["hs"], sets[i % len(views)]["gt"], use_graph=use_graph)
                 b.record()
                 torch.cuda.synchronize(dev)
                 whole[mode] = {"ms_per_step": a.elapsed_time(b) / n, "images_per_s": BATCH * n / (a.elapsed_time(b) * 1e-3)}
@@ -517,7 +544,7 @@ def main():
         return {"per_gpu_batch": batch, "ms": ms_k, "algorithmic_bytes": nbytes, "achieved": nbytes / (ms_k * 1e-3) / 1e9,
                 "frac": nbytes / (ms_k * 1e-3) / 1e9 / peak, "candidates_per_image": n_cand / batch}
 
-    kernels = {"score_kernel": {"b256": time_score_kernel(step, [(x["loc"], x["conf_i"]) for x in sets], BATCH)}}
+    kernels = {"score_kernel": {"b256": time_score_kernel(step, [(x["loc"], x["conf"]) for x in sets], BATCH)}}
     roofline["kernels"] = kernels
 
     # ---- the same halves at B = 2048 per GPU (wave quantisation and launch latency amortised) -------------
@@ -525,15 +552,14 @@ def main():
     if not args.skip_large_batch and rank == 0:
         LB = 2048
         cfg_l = synth.config(CFG, batch=LB, seed_offset=977)
-        big = dict(loc=cfg_l["loc_all"].to(dev), conf_t=cfg_l["conf_train"].to(dev), conf_i=cfg_l["conf_infer"].to(dev),
-                   gt=ssdhot.pack_targets(cfg_l["targets"], dev))
+        big = dict(loc=cfg_l["loc_all"].to(dev), conf=cfg_l["conf_infer"].to(dev), gt=ssdhot.pack_targets(cfg_l["targets"], dev))
         step_l = HotPathStep(ps, LB, C, spec["iou_thresh"], spec["ratio"], spec["score_thresh"], spec["nms_thresh"],
                              spec["max_per_img"])
         st = torch.cuda.current_stream(dev).cuda_stream
 
         def time_large(train: bool, iters: int = 12):
-            f = (lambda: step_l.launch_loss(big["loc"], big["conf_t"], big["gt"], st)) if train else \
-                (lambda: step_l.launch_predict(big["loc"], big["conf_i"], st))
+            f = (lambda: step_l.launch_loss(big["loc"], big["conf"], big["gt"], st)) if train else \
+                (lambda: step_l.launch_predict(big["loc"], big["conf"], st))
             for _ in range(3):
                 f()
             torch.cuda.synchronize(dev)
@@ -544,11 +570,11 @@ def main():
             return statistics.median(a.elapsed_time(b) for a, b in evs)
 
         ml, mp = time_large(True), time_large(False)
-        kernels["score_kernel"]["b2048"] = time_score_kernel(step_l, [(big["loc"], big["conf_i"])], LB, iters=10)
+        kernels["score_kernel"]["b2048"] = time_score_kernel(step_l, [(big["loc"], big["conf"])], LB, iters=10)
         g_l = statistics.mean(float(t["boxes"].shape[0]) for t in cfg_l["targets"])
         k_l = float(step_l.count.float().mean().item())
         bl, bp = LB * (349296 + 24 * g_l + 12), LB * (349296 + 28 * k_l + 4)
-        large = {"per_gpu_batch": LB, "l2": "one input set of 1.1 GB per half (>> 126 MB L2)",
+        large = {"per_gpu_batch": LB, "l2": "one input set of 0.7 GB (>> 126 MB L2)",
                  "match_loss": {"ms": ml, "achieved": bl / (ml * 1e-3) / 1e9, "frac": bl / (ml * 1e-3) / 1e9 / peak,
                                 "images_per_s": LB / (ml * 1e-3)},
                  "decode_nms": {"ms": mp, "achieved": bp / (mp * 1e-3) / 1e9, "frac": bp / (mp * 1e-3) / 1e9 / peak,
@@ -557,70 +583,113 @@ def main():
         torch.cuda.empty_cache()
     roofline["large_batch"] = large
 
-    barrier()       # (rank 0 alone measured the extra sections above; the e2e steps below exchange sums again)
+    barrier()       # (rank 0 alone measured the extra sections above; the sections below exchange sums again)
+    # ---- strong scaling on BASELINE cfg 4: B = 4096 match + mined loss over the whole job, exchange inside the timed step ----
+    strong = None
+    if not args.skip_strong and 8 % world == 0:
+        strong = strong_cfg4(ssdhot, synth, D, dist, ps, dev, rank, world, peer, spec, barrier)
+
     # ---- end to end through the drop-in API, host buffers ------------------------------------------
+    # one step = ssdhot.eval_step on one (loc_all, conf_all) pair + the batch's ground truth as collate_detection packs it
+    # (one pinned buffer); every step copies its own inputs host -> device and reads its own results back; the copies of
+    # step i+1 are issued on a second stream before step i's kernels and read-back, so the PCIe transfer overlaps them
+    # (double buffering, as a data loader would)
     pinned = []
     for cfg in host_sets[:2]:
-        pinned.append(dict(loc=cfg["loc_all"].pin_memory(), conf_t=cfg["conf_train"].pin_memory(),
-                           conf_i=cfg["conf_infer"].pin_memory(), targets=cfg["targets"]))
-    gt_bytes = sum(t["boxes"].numel() * 4 + t["labels"].numel() * 8 for t in host_sets[0]["targets"]) + 4 * (BATCH + 1)
-    h2d = BATCH * P * (4 + C + C) * 4 + gt_bytes
+        _, packed = ssdhot.collate_detection([(torch.zeros((1,)), t) for t in cfg["targets"]])
+        pinned.append(dict(loc=cfg["loc_all"].pin_memory(), conf=cfg["conf_infer"].pin_memory(), conf_t=cfg["conf_train"].pin_memory(),
+                           gt=packed.pin_memory()))
+    copy_stream = torch.cuda.Stream(dev)
     d2h_holder = {}
 
-    # Every step copies its own inputs host -> device and reads its own results back; the copy of step i+1 is issued on a
-    # second stream before step i's kernels and read-back, so the PCIe transfer overlaps them (double buffering, as a
-    # data loader would).
-    copy_stream = torch.cuda.Stream(dev)
+    def h2d_probe():
+        """A bare loop of the step's H2D copies (one cudaMemcpyAsync per buffer) on every rank at once: the ceiling the host
+        side of e2e can reach on this box at this N (PCIe / NUMA), next to which e2e is read."""
+        h = pinned[0]
+        nbytes = sum(t.numel() * t.element_size() for t in (h["loc"], h["conf"], h["gt"].buffer))
+        dst = [torch.empty_like(h["loc"], device=dev), torch.empty_like(h["conf"], device=dev), torch.empty_like(h["gt"].buffer, device=dev)]
+        for _ in range(2):
+            for d, t in zip(dst, (h["loc"], h["conf"], h["gt"].buffer)):
+                d.copy_(t, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        n = 10
+        for _ in range(n):
+            for d, t in zip(dst, (h["loc"], h["conf"], h["gt"].buffer)):
+                d.copy_(t, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        gbs = torch.tensor([nbytes * n / (time.perf_counter() - t0) / 1e9], dtype=torch.float64, device=dev)
+        every = [gbs.clone() for _ in range(world)]
+        if world > 1:
+            dist.all_gather(every, gbs)
+        per_rank = [float(t.item()) for t in every]
+        return {"bytes_per_step": nbytes, "per_rank_gbs": per_rank, "sum_gbs": sum(per_rank),
+                "ceiling_images_per_s": BATCH * sum(per_rank) * 1e9 / nbytes,
+                "note": "bare cudaMemcpyAsync loop of one step's inputs from pinned memory, all ranks at once"}
 
-    def stage(i):
+    def stage(i, separate):
         h = pinned[i % len(pinned)]
         with torch.cuda.stream(copy_stream):
             loc = h["loc"].to(dev, non_blocking=True)
-            conf_t = h["conf_t"].to(dev, non_blocking=True)
-            conf_i = h["conf_i"].to(dev, non_blocking=True)
-            gt = ssdhot.pack_targets(h["targets"], dev)
+            conf = h["conf"].to(dev, non_blocking=True)
+            conf_t = h["conf_t"].to(dev, non_blocking=True) if separate else None
+            gt = h["gt"].to(dev)                        # ONE copy: [offsets | boxes | labels]
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return loc, conf_t, conf_i, gt, ev
+        return loc, conf, conf_t, gt, ev
 
     def e2e_compute(staged):
-        loc, conf_t, conf_i, gt, ev = staged
+        loc, conf, conf_t, gt, ev = staged
         cur = torch.cuda.current_stream(dev)
         cur.wait_event(ev)
-        for t in (loc, conf_t, conf_i, gt.boxes, gt.labels, gt.offsets):
-            t.record_stream(cur)
-        l_loc, l_conf = ssdhot.multibox_loss(ps, loc, conf_t, gt, spec["iou_thresh"], spec["ratio"],
-                                             group=peer if peer is not None else group)
-        labels, scores, boxes, count = ssdhot.predict_padded(ps, loc, conf_i, spec["score_thresh"], spec["nms_thresh"],
-                                                             spec["max_per_img"])
+        for t in (loc, conf, conf_t):
+            if t is not None:
+                t.record_stream(cur)
+        gt.record_stream(cur)
+        grp = peer if peer is not None else group
+        if conf_t is None:
+            l_loc, l_conf, labels, scores, boxes, count = ssdhot.eval_step(ps, loc, conf, gt, spec["iou_thresh"], spec["ratio"],
+                                                                           spec["score_thresh"], spec["nms_thresh"], spec["max_per_img"],
+                                                                           group=grp)
+        else:
+            l_loc, l_conf = ssdhot.multibox_loss(ps, loc, conf_t, gt, spec["iou_thresh"], spec["ratio"], group=grp)
+            labels, scores, boxes, count = ssdhot.predict_padded(ps, loc, conf, spec["score_thresh"], spec["nms_thresh"],
+                                                                 spec["max_per_img"])
         out = (torch.stack((l_loc, l_conf)).cpu(), labels.cpu(), scores.cpu(), boxes.cpu(), count.cpu())
         d2h_holder["bytes"] = sum(t.numel() * t.element_size() for t in out)
         return out
 
-    def e2e_run(n):
-        nxt = stage(0)
+    def e2e_run(n, separate):
+        nxt = stage(0, separate)
         for i in range(n):
             cur_staged = nxt
             if i + 1 < n:
-                nxt = stage(i + 1)
+                nxt = stage(i + 1, separate)
             e2e_compute(cur_staged)
 
+    def e2e_measure(separate):
+        e2e_run(3, separate)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(e2e_steps, separate)
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return BATCH * world * e2e_steps / float(t.item())
+
+    probe = h2d_probe()
     e2e_steps = max(3, min(args.steps, 20))
-    e2e_run(3)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_run(e2e_steps)
-    torch.cuda.synchronize(dev)
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = BATCH * world * e2e_steps / float(t_e2e.item())
+    gt_bytes = pinned[0]["gt"].buffer.numel()
+    h2d = BATCH * P * (4 + C) * 4 + gt_bytes
+    e2e_value = e2e_measure(False)
+    e2e_sep = e2e_measure(True)
 
     # ---- BASELINE cfg 1: one image, 5 boxes (the web app's case, app_files/ssd_demo_app.py:288): latency ------------
     single = None
     if rank == 0:
         c1 = synth.config(1)
-        loc1, ct1, ci1 = c1["loc_all"].to(dev), c1["conf_train"].to(dev), c1["conf_infer"].to(dev)
+        loc1, ci1 = c1["loc_all"].to(dev), c1["conf_infer"].to(dev)
         gt1 = ssdhot.pack_targets(c1["targets"], dev)
         step1 = HotPathStep(ps, 1, C, c1["iou_thresh"], c1["ratio"], c1["score_thresh"], c1["nms_thresh"], c1["max_per_img"])
         st1 = torch.cuda.current_stream(dev).cuda_stream
@@ -650,11 +719,11 @@ def main():
 
         single = {
             "workload": "cfg1: B=1, 5 GT boxes, match+mined loss then predict(0.01, 0.45, 200)", "unit": "us",
-            "kernels_match_loss": lat(lambda: step1.launch_loss(loc1, ct1, gt1, st1)),
+            "kernels_match_loss": lat(lambda: step1.launch_loss(loc1, ci1, gt1, st1)),
             "kernels_decode_nms": lat(lambda: step1.launch_predict(loc1, ci1, st1)),
             "api_predict_list_of_dicts_wall": host_lat(lambda: ssdhot.predict(ps, None, c1["score_thresh"], c1["nms_thresh"], c1["max_per_img"],
                                                                                 pre_loc_all=loc1, pre_conf_all=ci1)),
-            "api_multibox_loss_item_wall": host_lat(lambda: [t.item() for t in ssdhot.multibox_loss(ps, loc1, ct1, gt1, c1["iou_thresh"], c1["ratio"])]),
+            "api_multibox_loss_item_wall": host_lat(lambda: [t.item() for t in ssdhot.multibox_loss(ps, loc1, ci1, gt1, c1["iou_thresh"], c1["ratio"])]),
         }
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ---------------------------------
@@ -665,7 +734,7 @@ def main():
         kind, *arm = cpu_arm()
         cfg = host_sets[0]
         cpu_reference_step(cfg, arm, 2, 1)
-        n_train, n_pred = 256, 32          # ~1 s + ~15 s of CPU work on the 16-core box (bounded sample)
+        n_train, n_pred = 256, 32          # ~0.5 s + ~8 s of CPU work on the 16-core box (bounded sample)
         a, b = cpu_reference_step(cfg, arm, n_train, n_pred)
         cpu = {"value": cpu_images_per_s(a, n_train, b, n_pred), "unit": "images/s", "cores": cores, "kind": kind,
                "sample": f"{n_train} images match+loss ({a:.2f} s) + {n_pred} images predict ({b:.2f} s), {CPU_KIND_NOTE[kind]}, "
@@ -690,26 +759,117 @@ def main():
                        "parallelism": f"image-sharded x{world}, all-reduce of 3 doubles per step" + (f": {collective}" if world > 1 else "")},
             "parts": {"match_loss_images_per_s": BATCH * world / (ms_loss * 1e-3),
                       "decode_nms_images_per_s": BATCH * world / (ms_pred * 1e-3)},
+            "sustained": sustained,
+            "separate_conf": separate,
+            "lag1": lag1,
+            "strong_cfg4": strong,
             "roofline": roofline,
             "heads": heads,
             "single_image": single,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h_holder.get("bytes", 0), "steps": e2e_steps,
-                    "api": "ssdhot.multibox_loss + ssdhot.predict_padded from pinned host tensors; the H2D copy of step i+1 overlaps "
-                           "the kernels and read-back of step i (two streams)"},
+                    "d2h_bytes_per_step": d2h_holder.get("bytes", 0), "steps": e2e_steps, "h2d_copies_per_step": 3,
+                    "api": "ssdhot.eval_step (= SSD_test_step's post-backbone part: one loc_all, one conf_all, ground truth packed by "
+                           "ssdhot.collate_detection into one pinned buffer) from pinned host tensors; the H2D copies of step i+1 overlap "
+                           "the kernels and read-back of step i (two streams)",
+                    "h2d_probe": probe,
+                    "separate_conf": {"value": e2e_sep, "h2d_bytes_per_step": h2d + BATCH * P * C * 4, "h2d_copies_per_step": 4,
+                                      "note": "round-1 workload: ssdhot.multibox_loss(conf_train) + ssdhot.predict_padded(conf_infer)"}},
             "gpu_launches": launches_per_step * args.steps,
             "per_rank_ms_per_step": [t / args.steps for t in per_rank_ms],
             "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:
-        if peer is not None:
-            if peer.timed_out():
+        for pr in (peer, peer_lag1):
+            if pr is not None and pr.timed_out():
                 print(f"[bench] rank {rank}: a peer all-reduce timed out", file=sys.stderr)
-            dist.barrier()
-            peer.close()
+        dist.barrier()
+        for pr in (peer, peer_lag1):
+            if pr is not None:
+                pr.close()
         dist.destroy_process_group()
+
+
+def strong_cfg4(ssdhot, synth, D, dist, ps, dev, rank, world, peer, spec, barrier):
+    """BASELINE cfg 4: one batch of 4096 images (G ~ U{1..20}), match + mined loss only, split over the job's ranks in
+    contiguous image slices, the all-reduce of the three sums INSIDE the timed step (lag 0).  The batch is generated as 8
+    blocks of 512 images (seeds independent of N) so that every N in {1, 2, 4, 8} sees the same 4096 images; rank r owns
+    blocks [r * 8 / N, (r + 1) * 8 / N).  `sharded_check`: rank 0 also runs the WHOLE batch alone and compares its sums with
+    the reduced sums of the sharded run (the logic of tools/check_sharded_nccl.py, now part of the driver-run record)."""
+    from ssdhot.engine import HotPathStep
+    TOTAL, BLOCK = 4096, 512
+    per = 8 // world
+    mine = range(rank * per, (rank + 1) * per)
+
+    def block(k):
+        return synth.config(4, batch=BLOCK, seed_offset=500 + k)
+
+    def to_dev(cfgs):
+        loc = torch.cat([c["loc_all"] for c in cfgs], 0).to(dev)
+        conf = torch.cat([c["conf_infer"] for c in cfgs], 0).to(dev)
+        gt = ssdhot.pack_targets([t for c in cfgs for t in c["targets"]], dev)
+        return loc, conf, gt
+
+    my_cfgs = [block(k) for k in mine]
+    loc, conf, gt = to_dev(my_cfgs)
+    n_local = loc.shape[0]
+    grp = None
+    if world > 1:
+        grp = peer if peer is not None and peer.lag == 0 else (D.PeerSums(dev, lag=0) if peer is not None else True)
+    stp = HotPathStep(ps, n_local, C, spec["iou_thresh"], spec["ratio"], infer_half=False, group=grp)
+    st = torch.cuda.current_stream(dev)
+
+    def one():
+        stp.launch_loss(loc, conf, gt, st.cuda_stream)
+        stp._reduce()
+
+    for _ in range(5):
+        one()
+    barrier()
+    if world > 1:
+        dist.all_reduce(torch.zeros((1,), device=dev))
+    n = 30
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        one()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    sharded_sums = stp.sums.clone()
+    out = {"workload": "cfg4: B=4096, G~U{1..20}, match + mined loss, all-reduce of the 3 sums inside the timed step (lag 0)",
+           "scaling": "strong", "global_batch": TOTAL, "per_gpu_batch": n_local, "ms_per_step": float(ms.item()),
+           "images_per_s": TOTAL / (float(ms.item()) * 1e-3),
+           "l2": f"one input set of {n_local * 349296 / 1e6:.0f} MB per rank" + (" (> 126 MB L2)" if n_local * 349296 > 126e6 else " (fits the 126 MB L2: re-read warm)"),
+           "note": "speed-up over N = 1 = this line's images_per_s / the N = 1 run's (the driver has both lines)"}
+    check = None
+    if rank == 0:
+        if world > 1:
+            del loc, conf, gt
+            rest = [block(k) for k in range(8) if k not in mine]
+            order = sorted(list(mine) + [k for k in range(8) if k not in mine])
+            cfgs = {k: c for k, c in zip(list(mine) + [k for k in range(8) if k not in mine], my_cfgs + rest)}
+            f_loc, f_conf, f_gt = to_dev([cfgs[k] for k in order])
+            whole = HotPathStep(ps, TOTAL, C, spec["iou_thresh"], spec["ratio"], infer_half=False)
+            whole.launch_loss(f_loc, f_conf, f_gt, st.cuda_stream)
+            torch.cuda.synchronize(dev)
+            single_sums = whole.sums.clone()
+        else:
+            single_sums = sharded_sums
+        a, b = sharded_sums.cpu(), single_sums.cpu()
+        rel = float(((a - b).abs() / b.abs().clamp_min(1e-300)).max())
+        check = {"ok": bool(rel <= 1e-9 and a[2].item() == b[2].item()), "max_rel_err": rel,
+                 "sums_sharded": a.tolist(), "sums_single_gpu": b.tolist(),
+                 "what": "[sum smooth-L1, sum CE, sum positives] of the 4096-image batch: reduced over the ranks vs one GPU alone"}
+    out["sharded_check"] = check
+    if world > 1 and isinstance(grp, D.PeerSums) and grp is not peer:
+        barrier()
+        grp.close()
+    barrier()
+    return out
 
 
 if __name__ == "__main__":
