@@ -559,19 +559,10 @@ __device__ __forceinline__ unsigned exact_score_key6(const HeadReader<SRC, 6>& r
 // KEY_MARGIN); the strict test `score > thresh` (SFS:402) is decided by the approximate score when it is
 // more than 1e-4 (relative) away from the threshold and by the exact eager-CUDA arithmetic otherwise, so
 // the candidate SET is exact; the keys are approximate and nms_image_kernel refines the ones it pulls.
+// One warp's share of the stream: list segment `seg` of image b (htab / regions: the CTA's head tables, already filled).
 template <int CT, int SRC>
-__global__ void __launch_bounds__(ST, 4) score_kernel(const PredictParams prm) {
-    pdl_trigger();                                 // nms_image_kernel's CTAs may be scheduled as SMs free up (they wait for this grid)
-    const int b = blockIdx.x / SCS, part = blockIdx.x % SCS;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ HeadTable htab;                     // per-level bases of this image (head sources only)
-    __shared__ PlaneRegions regions;               // (NCHW heads)
-    if (SRC != SRC_PACKED) {
-        if (SRC == SRC_LEVEL_PLANES) plane_regions_fill(regions, prm.conf_h, b, threadIdx.x);
-        else head_table_fill<SRC, 6>(htab, prm.conf_h, b, threadIdx.x);
-        __syncthreads();
-    }
-    const int seg = part * (ST / 32) + warp;
+__device__ __forceinline__ void score_segment(const PredictParams& prm, int b, int seg, int lane, const HeadTable& htab,
+                                              const PlaneRegions& regions) {
     const int P = prm.P, n_fg = prm.C - 1;
     const int rows = seg_rows(P);
     const int r0 = min(P, seg * rows), r1 = min(P, r0 + rows);
@@ -684,6 +675,21 @@ __global__ void __launch_bounds__(ST, 4) score_kernel(const PredictParams prm) {
         }
     }
     if (lane == 0) prm.cand_count[b * SEGS + seg] = cnt;
+}
+
+template <int CT, int SRC>
+__global__ void __launch_bounds__(ST, 4) score_kernel(const PredictParams prm) {
+    pdl_trigger();                                 // nms_image_kernel's CTAs may be scheduled as SMs free up (they wait for this grid)
+    const int b = blockIdx.x / SCS, part = blockIdx.x % SCS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ HeadTable htab;                     // per-level bases of this image (head sources only)
+    __shared__ PlaneRegions regions;               // (NCHW heads)
+    if (SRC != SRC_PACKED) {
+        if (SRC == SRC_LEVEL_PLANES) plane_regions_fill(regions, prm.conf_h, b, threadIdx.x);
+        else head_table_fill<SRC, 6>(htab, prm.conf_h, b, threadIdx.x);
+        __syncthreads();
+    }
+    score_segment<CT, SRC>(prm, b, part * (ST / 32) + warp, lane, htab, regions);
 }
 
 // shared-memory carve-up of the stand-alone unit (nms_sets_kernel carves by hand)
