@@ -23,6 +23,8 @@
 // same lists, bit-identical results.
 // The stand-alone NMS entry point (mySSD.iou_nms, nms_sets_kernel / nms_unit) handles arbitrary set sizes
 // and unbounded survivor counts with tiles of 64 and a CTA-local radix select.
+#include <cstdlib>
+
 #include "boxmath.cuh"
 #include "heads.cuh"
 
@@ -77,6 +79,27 @@ __device__ __forceinline__ bool suppresses_exact(const BoxC& S, const BoxC& c, f
     }
     return !(m <= thr);
 }
+// the same with the metric as a (CTA-uniform) runtime value: the per-image kernels carry it in their parameters, which keeps
+// their instantiations to the head sources
+__device__ __forceinline__ bool suppresses_exact_rt(int metric, const BoxC& S, const BoxC& c, float inter, float uni, float thr) {
+    const float iou = fdiv(inter, uni);
+    float m = iou;
+    if (metric != SSDHOT_METRIC_IOU) {
+        m = pair_diou_from_iou(S, c, iou);
+        if (metric == SSDHOT_METRIC_CIOU) {
+            const float da = fsub(S.at, c.at);
+            const float v = fmul(kFourOverPiSq, fmul(da, da));
+            const float alpha = fdiv(v, fadd(fadd(fsub(1.0f, iou), v), kEps));
+            m = fsub(m, fmul(alpha, v));
+        }
+    }
+    return !(m <= thr);
+}
+__device__ __forceinline__ bool suppresses_rt(int metric, const BoxC& S, const BoxC& c, float thr, float thr_lo) {
+    float inter, uni;
+    if (!iou_gate(S, c, thr_lo, inter, uni)) return false;
+    return suppresses_exact_rt(metric, S, c, inter, uni, thr);
+}
 template <int METRIC>
 __device__ __forceinline__ bool suppresses(const BoxC& S, const BoxC& c, float thr, float thr_lo) {
     float inter, uni;
@@ -120,6 +143,28 @@ struct SegSource {             // 32 per-warp segments of (key << 32 | ~id) writ
     __device__ __forceinline__ void replace(int i, unsigned long long r) const { base[i] = r; }
     static __device__ __forceinline__ unsigned key(unsigned long long r) { return (unsigned)(r >> 32); }
     static __device__ __forceinline__ unsigned long long sortkey(unsigned long long r, int) { return r; }
+};
+
+// The fused predict kernel's candidate list: the same 16 per-warp segments, but in SHARED memory and as 32-bit entries
+//   (bits 30..15 of the approximate score) << 16 | candidate id          (candidate ids of SSD300 with C = 6 are < 43,660)
+// The 16 score bits are exactly the histogram bin of the score (score_bin), so `key` is the floor of the entry's bin.
+struct SmemSource {
+    unsigned* base; const int* counts; int seg_cap;
+    template <int NT, typename F>
+    __device__ __forceinline__ void for_each(F f) const {
+        static_assert((SEGS * 32) % NT == 0, "whole segments per warp");
+        const int lane = threadIdx.x & 31;
+        for (int seg = threadIdx.x >> 5; seg < SEGS; seg += NT / 32) {
+            const int c = counts[seg];
+            for (int j = lane; j < c; j += 32) f(seg * seg_cap + j, (unsigned long long)base[seg * seg_cap + j]);
+        }
+    }
+    __device__ __forceinline__ void consume(int) const {}
+    __device__ __forceinline__ void replace(int, unsigned long long) const {}
+    static __device__ __forceinline__ unsigned key(unsigned long long r) { return 0x80000000u | ((unsigned)(r >> 16) << 15); }
+    static __device__ __forceinline__ unsigned long long sortkey(unsigned long long r, int) {
+        return ((unsigned long long)key(r) << 32) | (unsigned long long)(0xffffffffu - (unsigned)(r & 0xffffull));
+    }
 };
 
 // ---- ranking helpers ---------------------------------------------------------------------------
@@ -498,6 +543,7 @@ __device__ int nms_unit(const Src src, const UnitBuffers buf, int n_cand, int n_
 struct PredictParams {
     const float* pri; int P; const float* loc_all; const float* conf_all; int B, C;
     float score_thresh, nms_thresh; int max_keep; float vc, vs, img_w, img_h;
+    int metric, agnostic;           // SSDHOT_METRIC_*, class-agnostic NMS (the per-image kernels read them at run time)
     unsigned long long* cand;       // [B][P*(C-1)] candidate keys
     int* cand_count;                // [B]
     int64_t* out_labels; float* out_scores; float* out_boxes; int32_t* out_cand; int32_t* out_count;
@@ -788,34 +834,24 @@ __device__ __noinline__ void nms_select_cut(const SegSource src, UnitShared& us,
     *tkey_out = tkey;
     *tie_floor_out = tie_floor;
 }
+#define SSDHOT_FAST_EXIT(code, info) do { if (prm.timeline && threadIdx.x == 0) prm.timeline[(long long)blockIdx.x * 16 + 15] = (unsigned long long)(code) | ((unsigned long long)(info) << 8); } while (0)
 #define SSDHOT_NSTAMP(k) do { if (prm.timeline && threadIdx.x == 0 && first) prm.timeline[(long long)blockIdx.x * 16 + (k)] = globaltimer_ns(); } while (0)
 
-template <int METRIC, bool AGN, bool APPROX, int SRC>
-__global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams prm) {
-    extern __shared__ __align__(16) unsigned char dyn[];
-    __shared__ UnitShared us;
-    __shared__ HeadTable loc_tab, conf_tab;        // per-level bases of this image (head sources only)
+// The rounds of one image (every thread of the CTA).  Preconditions: buf.hist16 and buf.ngroup are zero, the head tables are
+// filled, n_cand = candidates in `src`, and a barrier has published all of it.  FAST (the fused kernel's shared-memory
+// list, one round only): returns false -- CTA-uniformly -- as soon as the image needs anything beyond one histogram-cut
+// round (exact selection, exact keys for the whole list, a second round); the caller then runs the generic path.
+template <bool APPROX, int SRC, bool FAST, typename Src>
+__device__ __forceinline__ bool nms_image_body(const PredictParams& prm, const int b, const ImgBuffers& buf, UnitShared& us,
+                                               const HeadTable& loc_tab, const HeadTable& conf_tab, const Src& src, const int n_cand) {
     constexpr int KEY_MARGIN = 512;                // ulps: >= 3e-5 relative, 3x the worst error of an approximate score
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.x;
     const int n_fg = prm.C - 1, P = prm.P, max_keep = prm.max_keep;
+    const int METRIC = prm.metric;
+    const bool AGN = prm.agnostic != 0;
     const int n_groups = AGN ? 1 : n_fg;
-    const ImgBuffers buf = carve_img(dyn, max_keep, n_groups);
-    SegSource src;
-    src.seg_cap = seg_cap_rows(P) * n_fg;
-    src.base = prm.cand + (long long)b * SEGS * src.seg_cap;
-    src.counts = prm.cand_count + b * SEGS;
     bool first = true;
-    for (int i = tid; i < HBINS / 2; i += IT) buf.hist16[i] = 0u;
-    for (int g = tid; g < n_groups; g += IT) buf.ngroup[g] = 0;
-    pdl_wait();                                    // score_kernel's lists and counts are complete from here on
-    SSDHOT_NSTAMP(0);
-    const int n_cand = block_sum<int>(tid < SEGS ? src.counts[tid] : 0, us.iscratch);
     const float thr = prm.nms_thresh, thr_lo = fmul(thr, kFilterSlack);
-    if (SRC != SRC_PACKED) {                       // (published by the __syncthreads() below)
-        head_table_fill<SRC, 4>(loc_tab, prm.loc_h, b, tid);
-        head_table_fill<SRC, 6>(conf_tab, prm.conf_h, b, tid - 32);
-    }
     const HeadReader<SRC, 4> loc_rd = {SRC == SRC_PACKED ? prm.loc_all + 4ll * b * P : nullptr, &loc_tab};
     const HeadReader<SRC, 6> conf_rd = {SRC == SRC_PACKED ? prm.conf_all + (long long)b * P * prm.C : nullptr, &conf_tab};
     const bool want_atan = METRIC == SSDHOT_METRIC_CIOU;
@@ -825,40 +861,48 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
 
     bool use_hist = n_cand > CH && n_cand < 65536;          // 16-bit bin counters
     bool keys_exact = !APPROX;
+    if (use_hist) src.template for_each<IT>([&](int, unsigned long long r) { hist_add(buf.hist16, Src::key(r)); });
     __syncthreads();
-    if (use_hist) src.for_each<IT>([&](int, unsigned long long r) { hist_add(buf.hist16, SegSource::key(r)); });
-    __syncthreads();
-    auto make_exact = [&]() { nms_make_exact<SRC>(src, buf.hist16, conf_rd, use_hist); keys_exact = true; };
+    auto make_exact = [&]() {
+        if constexpr (!FAST) { nms_make_exact<SRC>(src, buf.hist16, conf_rd, use_hist); keys_exact = true; }
+    };
 
     SSDHOT_NSTAMP(1);
     int kept_n = 0, remaining = n_cand;
     while (remaining > 0 && kept_n < max_keep) {
         // ---- pull ----------------------------------------------------------------------------------
         int K = remaining < CH ? remaining : CH;
-        unsigned tkey = 1u, tie_floor = 0u;
+        unsigned tkey = 1u, tie_floor = 0u, fast_gkey = 1u;
         bool all = remaining <= CH;
         if (!all && use_hist) {
             int cap = keys_exact ? CH : CH - 16;            // (room for the few margin strays)
             if (first) cap = min(cap, max(64, max_keep + (max_keep >> 1) + 16));
             hist_cut<IT>(buf.hist16, cap, us);
-            if (us.cut_count > 0) { K = us.cut_count; tkey = bin_floor_key(us.cut_bin); all = true; }
+            int cut_bin = 0;
+            if (us.cut_count > 0) { K = us.cut_count; cut_bin = us.cut_bin; tkey = bin_floor_key(cut_bin); all = true; }
             else use_hist = false;                          // a single bin holds more than the cap: exact select from here on
             __syncthreads();
+            // FAST entries carry the floor of their (approximate) score's bin: an exact score at or above the cut can sit at most
+            // one bin lower, so the gather reaches one bin below the cut (bin_floor_key(<= 0) = 1 takes everything)
+            if (FAST && all) fast_gkey = bin_floor_key(cut_bin - 1);
         }
         if (!all) {
-            if (APPROX && !keys_exact) make_exact();
-            nms_select_cut(src, us, K, &tkey, &tie_floor);
+            if constexpr (FAST) { SSDHOT_FAST_EXIT(2, us.cut_bin); return false; }
+            else {
+                if (APPROX && !keys_exact) make_exact();
+                nms_select_cut(src, us, K, &tkey, &tie_floor);
+            }
         }
         SSDHOT_NSTAMP(2);
-        const unsigned gkey = (keys_exact || tkey <= (unsigned)KEY_MARGIN) ? tkey : tkey - (unsigned)KEY_MARGIN;
+        const unsigned gkey = FAST ? fast_gkey : ((keys_exact || tkey <= (unsigned)KEY_MARGIN) ? tkey : tkey - (unsigned)KEY_MARGIN);
         if (tid == 0) us.counter = 0;
         __syncthreads();
         src.for_each<IT>([&](int i, unsigned long long r) {
-            const unsigned k = SegSource::key(r);
+            const unsigned k = Src::key(r);
             if (k == 0u || k < gkey) return;
             if (keys_exact && k == tkey && (unsigned)(r & 0xffffffffull) < tie_floor) return;
             const int pos = atomicAdd(&us.counter, 1);
-            if (pos < CH) { buf.ckey[pos] = r; buf.cidx[pos] = i; }
+            if (pos < CH) { buf.ckey[pos] = Src::sortkey(r, i); buf.cidx[pos] = i; }
             if (keys_exact) src.consume(i);
         });
         __syncthreads();
@@ -866,6 +910,7 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
         if (APPROX && !keys_exact) {
             const int gathered = us.counter;
             if (gathered > CH) {                            // more margin strays than the slack: settle it with exact keys
+                if constexpr (FAST) { SSDHOT_FAST_EXIT(3, gathered); return false; }
                 __syncthreads();
                 make_exact();
                 continue;
@@ -885,7 +930,11 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
             __syncthreads();
         }
         SSDHOT_NSTAMP(4);
-        if (K == 0) { first = false; continue; }                               // (only margin strays: the next cut is lower)
+        if (K == 0) {                                                           // (only margin strays: the next cut is lower)
+            if constexpr (FAST) { SSDHOT_FAST_EXIT(4, 0); return false; }
+            first = false;
+            continue;
+        }
         if (K <= 128) bitonic_desc<128>(buf.ckey);           // (entries beyond K are zero and stay behind)
         else if (K <= 256) bitonic_desc<256>(buf.ckey);
         else bitonic_desc<CH>(buf.ckey);
@@ -967,7 +1016,7 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
             const unsigned short* kl = buf.kidx + (size_t)my_g * max_keep;
             const int ng = buf.ngroup[my_g];
             bool hit = false;
-            for (int i = 0; i < ng && !hit; ++i) hit = suppresses<METRIC>(buf.kept[kl[i]], my_box, thr, thr_lo);
+            for (int i = 0; i < ng && !hit; ++i) hit = suppresses_rt(METRIC, buf.kept[kl[i]], my_box, thr, thr_lo);
             if (hit) atomicAnd(reinterpret_cast<unsigned*>(buf.aliveW + my_g * MW) + (my_m >> 5), ~(1u << (my_m & 31)));
         }
         // (b) every entry against the earlier entries of its class (boxes and cell masks sit in class order).  The loop
@@ -980,7 +1029,7 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
             const BoxC S = buf.cbox[cbase + aq], c = buf.cbox[cbase + m];
             float inter, uni;
             iou_gate(S, c, thr_lo, inter, uni);
-            if (suppresses_exact<METRIC>(S, c, inter, uni, thr)) {
+            if (suppresses_exact_rt(METRIC, S, c, inter, uni, thr)) {
                 atomicOr(reinterpret_cast<unsigned*>(buf.mat + (size_t)(cbase + aq) * MW) + (m >> 5), 1u << (m & 31));
                 atomicOr(reinterpret_cast<unsigned*>(buf.nzW + g * MW) + (aq >> 5), 1u << (aq & 31));
             }
@@ -1108,8 +1157,207 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
         __syncthreads();
         SSDHOT_NSTAMP(9);
         first = false;
+        if (FAST && remaining > 0 && kept_n < max_keep) { SSDHOT_FAST_EXIT(5, kept_n | (K << 12)); return false; }   // a second round: the generic path redoes the image
     }
     if (tid == 0) { prm.out_count[b] = kept_n; if (prm.timeline) { prm.timeline[(long long)b * 16 + 10] = globaltimer_ns(); unsigned sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); prm.timeline[(long long)b * 16 + 11] = sm; prm.timeline[(long long)b * 16 + 12] = (unsigned long long)n_cand; } }
+    return true;
+}
+
+template <bool APPROX, int SRC>
+__global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams prm) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ UnitShared us;
+    __shared__ HeadTable loc_tab, conf_tab;        // per-level bases of this image (head sources only)
+    const int tid = threadIdx.x, b = blockIdx.x;
+    const int n_fg = prm.C - 1, n_groups = prm.agnostic ? 1 : n_fg;
+    const ImgBuffers buf = carve_img(dyn, prm.max_keep, n_groups);
+    SegSource src;
+    src.seg_cap = seg_cap_rows(prm.P) * n_fg;
+    src.base = prm.cand + (long long)b * SEGS * src.seg_cap;
+    src.counts = prm.cand_count + b * SEGS;
+    for (int i = tid; i < HBINS / 2; i += IT) buf.hist16[i] = 0u;
+    for (int g = tid; g < n_groups; g += IT) buf.ngroup[g] = 0;
+    pdl_wait();                                    // score_kernel's lists and counts are complete from here on
+    if (prm.timeline && tid == 0) prm.timeline[(long long)b * 16 + 0] = globaltimer_ns();
+    const int n_cand = block_sum<int>(tid < SEGS ? src.counts[tid] : 0, us.iscratch);
+    if (SRC != SRC_PACKED) {                       // (published by the __syncthreads() below)
+        head_table_fill<SRC, 4>(loc_tab, prm.loc_h, b, tid);
+        head_table_fill<SRC, 6>(conf_tab, prm.conf_h, b, tid - 32);
+    }
+    __syncthreads();
+    nms_image_body<APPROX, SRC, false>(prm, b, buf, us, loc_tab, conf_tab, src, n_cand);
+}
+
+
+// ---- predict in ONE kernel: stream -> shared-memory candidate list -> one NMS round -----------------------------------
+// predict_image_kernel (one CTA of 512 threads per image, two per SM) is score_kernel and nms_image_kernel back to back
+// inside one CTA for the case every typical image is: the 16 warps stream the image's logits exactly as score_kernel's
+// 16 warps do, but append the candidates to per-warp segments of a list in SHARED memory (32-bit entries, SmemSource), so
+// the 8-byte keys never travel to HBM and back, the score histogram is built from shared memory, and the gather reads
+// shared memory.  The list occupies the space the later stages use for the suppression matrix, the boxes and the
+// survivors; it is dead once the round's candidates have been gathered.  Whatever does not fit that mould -- a list
+// segment that overflows, a histogram that cannot give a cut, a second round -- makes the CTA redo its image on the generic
+// path: score_segment into the global lists, then nms_image_body on them (the two-kernel path, run by this CTA alone).
+// Results are those of the two-kernel path bit for bit: the candidate set is exact either way, pulled candidates get exact
+// scores, and every later stage is shared code.
+
+// One warp's share of the stream into its shared-memory segment.  -> number of entries, or -1 if the segment overflowed.
+template <int SRC>
+__device__ __forceinline__ int stream_segment_smem(const PredictParams& prm, int b, int seg, int lane, const HeadTable& htab,
+                                                   const PlaneRegions& regions, unsigned* __restrict__ list, int cap) {
+    const int P = prm.P;
+    const int rows = seg_rows(P);
+    const int r0 = min(P, seg * rows), r1 = min(P, r0 + rows);
+    const float* conf_b = SRC == SRC_PACKED ? prm.conf_all + (long long)b * P * 6 : nullptr;
+    const float thr = prm.score_thresh, thr_hi = thr * 1.0001f, thr_lo = thr * 0.9999f;
+    const HeadReader<SRC, 6> rd = {conf_b, &htab};
+    const int q0 = r0 >> 1, q1 = r1 >> 1;               // P is even on this path
+    const int n_it = SRC == SRC_LEVEL_PLANES ? (kPlaneChunks - seg + SEGS - 1) / SEGS : (q1 - q0 + 31) >> 5;
+    PlaneWalk walk(&regions);
+    auto load_it = [&](int it, float* xx, int& p0) -> bool {
+        if (it >= n_it) return false;
+        if (SRC == SRC_LEVEL_PLANES) {
+            return walk.load(seg + SEGS * it, lane, xx, p0);
+        } else {
+            const int q = q0 + 32 * it + lane;
+            p0 = 2 * q;
+            if (q < q1) rd.pair(q, xx);
+            return q < q1;
+        }
+    };
+    int cnt = 0;                                        // warp-uniform
+    bool overflow = false;
+    constexpr float kL2E = 1.4426950408889634f;
+    // one row pair of this lane: pass bits (bit h * 5 + k: row p0 + h, class k + 1), then the warp-wide append
+    auto process = [&](const float* x, int p0, bool live) {
+        unsigned pass = 0u;
+        float e[2][6], rs[2];
+        if (live) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float* xr = x + 6 * h;
+                const float mx = fmaxf(fmaxf(fmaxf(xr[0], xr[1]), fmaxf(xr[2], xr[3])), fmaxf(xr[4], xr[5]));
+                const float nm = -mx * kL2E;            // the common shift cancels in e_k / sum (a NaN / Inf row stays NaN)
+#pragma unroll
+                for (int i = 0; i < 6; ++i) e[h][i] = ex2_approx_ftz(fmaf(xr[i], kL2E, nm));
+                const float sum = ((e[h][0] + e[h][1]) + (e[h][2] + e[h][3])) + (e[h][4] + e[h][5]);
+                const float t_hi = sum * thr_hi, t_lo = sum * thr_lo;      // score > thr  <=>  e_k > thr * sum
+                rs[h] = rcp_approx_ftz(sum);
+                bool maybe = false;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const bool hi = e[h][k + 1] > t_hi;
+                    if (hi) pass |= 1u << (h * 5 + k);
+                    maybe |= (e[h][k + 1] >= t_lo) != hi;
+                }
+                if (maybe) {                            // within 1e-4 of the threshold: the exact arithmetic decides
+                    float ee[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) ee[i] = expf(fsub(xr[i], mx));
+                    const float se = fadd(fadd(fadd(ee[0], ee[4]), ee[2]), fadd(fadd(ee[1], ee[5]), ee[3]));
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const unsigned bit = 1u << (h * 5 + k);
+                        const bool near = (e[h][k + 1] >= t_lo) != ((pass & bit) != 0u);
+                        if (near && fdiv(ee[k + 1], se) > thr) pass |= bit;
+                    }
+                }
+            }
+        }
+        const int mine = __popc(pass);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        if (cnt + total > cap) { overflow = true; return; }          // warp-uniform
+        unsigned* at = list + cnt + incl - mine;
+        cnt += total;
+        if (pass) {
+            const unsigned id0 = (unsigned)p0 * 5u;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                if ((pass >> j) & 1u) {
+                    const float sc = e[j / 5][j % 5 + 1] * rs[j / 5];
+                    *at++ = ((__float_as_uint(sc) << 1) & 0xffff0000u) | (id0 + (unsigned)j);
+                }
+            }
+        }
+    };
+    float xa[12], xb[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) { xa[j] = 0.f; xb[j] = 0.f; }
+    int pa = 0, pb = 0;
+    bool la = load_it(0, xa, pa), lb = false;
+    for (int it = 0; it < n_it && !overflow; it += 2) {         // two iterations per trip: the next pair's loads are in flight
+        lb = load_it(it + 1, xb, pb);
+        process(xa, pa, la);
+        if (overflow) break;
+        la = load_it(it + 2, xa, pa);
+        if (it + 1 < n_it) process(xb, pb, lb);
+    }
+    return overflow ? -1 : cnt;
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(IT, 2) predict_image_kernel(const PredictParams prm) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ UnitShared us;
+    __shared__ HeadTable loc_tab, conf_tab;        // per-level bases of this image (head sources only)
+    __shared__ PlaneRegions regions;               // (NCHW heads)
+    __shared__ int seg_count[SEGS];
+    __shared__ int hard;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+    const int n_fg = prm.C - 1, n_groups = prm.agnostic ? 1 : n_fg;
+    const ImgBuffers buf = carve_img(dyn, prm.max_keep, n_groups);
+    // the list lives where the suppression rows, class-ordered boxes and survivors will be: [mat, hist16)
+    unsigned* list = reinterpret_cast<unsigned*>(buf.mat);
+    const int cap = (int)((reinterpret_cast<unsigned char*>(buf.hist16) - reinterpret_cast<unsigned char*>(buf.mat)) / (4 * SEGS));
+    for (int i = tid; i < HBINS / 2; i += IT) buf.hist16[i] = 0u;
+    for (int g = tid; g < n_groups; g += IT) buf.ngroup[g] = 0;
+    if (tid == 0) hard = 0;
+    if (SRC != SRC_PACKED) {
+        head_table_fill<SRC, 4>(loc_tab, prm.loc_h, b, tid);
+        head_table_fill<SRC, 6>(conf_tab, prm.conf_h, b, tid - 32);
+        if (SRC == SRC_LEVEL_PLANES) plane_regions_fill(regions, prm.conf_h, b, tid - 64);
+    }
+    if (prm.timeline && tid == 0) prm.timeline[(long long)b * 16 + 14] = globaltimer_ns();
+    __syncthreads();
+    {
+        const int c = stream_segment_smem<SRC>(prm, b, warp, lane, conf_tab, regions, list + warp * cap, cap);
+        if (lane == 0) {
+            seg_count[warp] = max(c, 0);
+            if (c < 0) hard = 1;
+        }
+    }
+    __syncthreads();
+    if (prm.timeline && tid == 0) prm.timeline[(long long)b * 16 + 0] = globaltimer_ns();
+    bool done = false;
+    if (!hard) {
+        SmemSource src;
+        src.base = list; src.counts = seg_count; src.seg_cap = cap;
+        int n_cand = 0;
+#pragma unroll
+        for (int w = 0; w < SEGS; ++w) n_cand += seg_count[w];
+        done = nms_image_body<true, SRC, true>(prm, b, buf, us, loc_tab, conf_tab, src, n_cand);
+    }
+    if (done) return;
+    if (prm.timeline && tid == 0 && hard) prm.timeline[(long long)b * 16 + 15] = 1ull;         // (debug: why this image left the fused mould)
+    // ---- the generic path, by this CTA alone: global lists, as many rounds as it takes -------------------------------
+    __syncthreads();
+    score_segment<6, SRC>(prm, b, warp, lane, conf_tab, regions);
+    for (int i = tid; i < HBINS / 2; i += IT) buf.hist16[i] = 0u;
+    for (int g = tid; g < n_groups; g += IT) buf.ngroup[g] = 0;
+    __syncthreads();                               // (the lists and counts this CTA wrote are visible to all its threads)
+    SegSource gsrc;
+    gsrc.seg_cap = seg_cap_rows(prm.P) * n_fg;
+    gsrc.base = prm.cand + (long long)b * SEGS * gsrc.seg_cap;
+    gsrc.counts = prm.cand_count + b * SEGS;
+    const int n_all = block_sum<int>(tid < SEGS ? gsrc.counts[tid] : 0, us.iscratch);
+    __syncthreads();
+    nms_image_body<true, SRC, false>(prm, b, buf, us, loc_tab, conf_tab, gsrc, n_all);
 }
 
 // ---- stand-alone NMS -------------------------------------------------------------------------------
@@ -1168,12 +1416,21 @@ static int set_smem(K kern, size_t bytes) {
     return SSDHOT_OK;
 }
 
-template <int METRIC, bool AGN, bool APPROX, int SRC = SRC_PACKED>
+template <int SRC>
+static int launch_predict_image(const PredictParams& prm, size_t dyn, cudaStream_t stream) {
+    int rc;
+    if ((rc = set_smem(predict_image_kernel<SRC>, dyn))) return rc;
+    predict_image_kernel<SRC><<<prm.B, IT, dyn, stream>>>(prm);
+    SSDHOT_CHECK_LAUNCH();
+    return SSDHOT_OK;
+}
+
+template <bool APPROX, int SRC>
 static int launch_nms_image(const PredictParams& prm, size_t dyn, cudaStream_t stream) {
     int rc;
-    if ((rc = set_smem(nms_image_kernel<METRIC, AGN, APPROX, SRC>, dyn))) return rc;
+    if ((rc = set_smem(nms_image_kernel<APPROX, SRC>, dyn))) return rc;
     // PDL: the CTAs may start (shared-memory carve-up, histogram clear) while score_kernel drains
-    cudaError_t e = launch_pdl(nms_image_kernel<METRIC, AGN, APPROX, SRC>, dim3(prm.B), dim3(IT), dyn, stream, prm);
+    cudaError_t e = launch_pdl(nms_image_kernel<APPROX, SRC>, dim3(prm.B), dim3(IT), dyn, stream, prm);
     ++g_launches;
     if (e != cudaSuccess) return (int)e;
     return SSDHOT_OK;
@@ -1269,6 +1526,16 @@ static int predict_launch(PredictParams& prm, int src, int class_agnostic, int m
     prm.cand = reinterpret_cast<unsigned long long*>(w + pw_cand_off(B));
     // C == 6 with 48-byte-aligned row pairs: approximate scores, refined by the NMS kernel; otherwise exact scores
     const bool approx = src != SRC_PACKED || (C == 6 && (P % 2) == 0 && al16(prm.conf_all));
+    // both stages of an approximable input (C == 6, candidate ids < 65536): ONE kernel, the candidate lists stay in shared
+    // memory (SSDHOT_PREDICT_TWO_KERNELS=1 keeps the two-kernel path, for A/B measurements)
+    static const bool two_kernels = getenv("SSDHOT_PREDICT_TWO_KERNELS") != nullptr;
+    prm.metric = metric;
+    prm.agnostic = class_agnostic ? 1 : 0;
+    if (stages == (SSDHOT_STAGE_SCORES | SSDHOT_STAGE_NMS) && approx && (long long)P * (C - 1) <= 65535 && !two_kernels) {
+        if (src == SRC_LEVEL_ROWS) return launch_predict_image<SRC_LEVEL_ROWS>(prm, dyn, s);
+        if (src == SRC_LEVEL_PLANES) return launch_predict_image<SRC_LEVEL_PLANES>(prm, dyn, s);
+        return launch_predict_image<SRC_PACKED>(prm, dyn, s);
+    }
     if (stages & SSDHOT_STAGE_SCORES) {
         if (src == SRC_LEVEL_ROWS) score_kernel<6, SRC_LEVEL_ROWS><<<B * SCS, ST, 0, s>>>(prm);
         else if (src == SRC_LEVEL_PLANES) score_kernel<6, SRC_LEVEL_PLANES><<<B * SCS, ST, 0, s>>>(prm);
@@ -1277,20 +1544,9 @@ static int predict_launch(PredictParams& prm, int src, int class_agnostic, int m
         SSDHOT_CHECK_LAUNCH();
     }
     if (!(stages & SSDHOT_STAGE_NMS)) return SSDHOT_OK;
-    int rc;
-#define SSDHOT_DISPATCH_SRC(M, S)                                                                                      \
-    rc = class_agnostic ? launch_nms_image<M, true, true, S>(prm, dyn, s) : launch_nms_image<M, false, true, S>(prm, dyn, s)
-#define SSDHOT_DISPATCH(M)                                                                                            \
-    if (src == SRC_LEVEL_ROWS) { SSDHOT_DISPATCH_SRC(M, SRC_LEVEL_ROWS); }                                            \
-    else if (src == SRC_LEVEL_PLANES) { SSDHOT_DISPATCH_SRC(M, SRC_LEVEL_PLANES); }                                   \
-    else rc = approx ? (class_agnostic ? launch_nms_image<M, true, true>(prm, dyn, s) : launch_nms_image<M, false, true>(prm, dyn, s))  \
-                     : (class_agnostic ? launch_nms_image<M, true, false>(prm, dyn, s) : launch_nms_image<M, false, false>(prm, dyn, s))
-    if (metric == SSDHOT_METRIC_DIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_DIOU); }
-    else if (metric == SSDHOT_METRIC_CIOU) { SSDHOT_DISPATCH(SSDHOT_METRIC_CIOU); }
-    else { SSDHOT_DISPATCH(SSDHOT_METRIC_IOU); }
-#undef SSDHOT_DISPATCH
-#undef SSDHOT_DISPATCH_SRC
-    return rc;
+    if (src == SRC_LEVEL_ROWS) return launch_nms_image<true, SRC_LEVEL_ROWS>(prm, dyn, s);
+    if (src == SRC_LEVEL_PLANES) return launch_nms_image<true, SRC_LEVEL_PLANES>(prm, dyn, s);
+    return approx ? launch_nms_image<true, SRC_PACKED>(prm, dyn, s) : launch_nms_image<false, SRC_PACKED>(prm, dyn, s);
 }
 
 extern "C" int ssdhot_predict_stages(const float* priors_cxcywh, int P, const float* loc_all, const float* conf_all,

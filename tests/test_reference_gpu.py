@@ -128,7 +128,7 @@ def test_reference_step_functions_run_through_patch(env):
             h.weight.mul_(40.0)
             h.bias.normal_()
     loader = _loader(synth, 2, 2, seed=3)
-    train_loader = _loader(synth, 2, 4, seed=4)
+    train_loader = _loader(synth, 1, 4, seed=4)      # ONE optimiser step: the loss is that of identical weights, the update is compared below
     thr = _calibrated_thresh(base, loader, dev)
     state = copy.deepcopy(base.state_dict())
     originals = {k: getattr(tr, k) for k in ("build_targets", "CELoss_w_neg_mining", "collate_detection", "SSD_train_step", "SSD_test_step")}
@@ -172,7 +172,7 @@ def test_reference_step_functions_run_through_patch(env):
         # --- unpatched reference ----------------------------------------------------------------------------------
         ref_eval, ref_preds = run_eval(new_model())
         ref_train, ref_params = run_train(new_model())
-        _, again = run_train(new_model())           # the reference against itself: the run-to-run noise of two SGD steps
+        _, again = run_train(new_model())           # the reference against itself: the run-to-run noise of one SGD step
         noise = param_distance(again, ref_params)   # through a VGG-16 with batch-norm in train mode (cuDNN's backward is not bit-reproducible)
         results = {}
         for mode, steps in (("dropins", False), ("fused", True)):

@@ -20,8 +20,18 @@ step.launch_predict(loc, ci, st)
 torch.cuda.synchronize()
 ssdhot.lib().ssdhot_debug_timeline(None)
 t = tl.cpu().double()
-t0 = t[:, 0].min()
-names = {0: "start", 1: "hist built", 2: "cut found", 3: "gathered", 4: "exact keys", 5: "sorted", 6: "decoded+ordered",
+fused = bool((t[:, 14] > 0).any())          # predict_image_kernel stamps its start (before the stream) in slot 14
+t0 = t[:, 14].min() if fused else t[:, 0].min()
+if fused:
+    print(f"fused predict_image_kernel: images that left the fused mould (generic path): {int((t[:, 15] > 0).sum())} of {batch}")
+    codes = tl.cpu()[:, 15]
+    for code in sorted(set((codes & 255).tolist()) - {0}):
+        sel = codes[(codes & 255) == code] >> 8
+        print(f"   reason {code} (1 list overflow, 2 no histogram cut, 3 gather overflow, 4 nothing valid, 5 second round): {sel.numel()} images, info "
+              f"{[(int(x) & 4095, int(x) >> 12) for x in sel[:6].tolist()]}")
+    v = (t[:, 14] - t0) / 1e3
+    print(f"{'CTA start':16s} med {v.median():6.1f} max {v.max():6.1f}")
+names = {0: "streamed" if fused else "start", 1: "hist built", 2: "cut found", 3: "gathered", 4: "exact keys", 5: "sorted", 6: "decoded+ordered",
          7: "pairs tested", 8: "resolved", 9: "emitted", 10: "end"}
 sm = t[:, 11].long()
 shared = torch.tensor([(sm == x).sum().item() > 1 for x in sm])
