@@ -145,28 +145,6 @@ struct SegSource {             // 32 per-warp segments of (key << 32 | ~id) writ
     static __device__ __forceinline__ unsigned long long sortkey(unsigned long long r, int) { return r; }
 };
 
-// The fused predict kernel's candidate list: the same 16 per-warp segments, but in SHARED memory and as 32-bit entries
-//   (bits 30..15 of the approximate score) << 16 | candidate id          (candidate ids of SSD300 with C = 6 are < 43,660)
-// The 16 score bits are exactly the histogram bin of the score (score_bin), so `key` is the floor of the entry's bin.
-struct SmemSource {
-    unsigned* base; const int* counts; int seg_cap;
-    template <int NT, typename F>
-    __device__ __forceinline__ void for_each(F f) const {
-        static_assert((SEGS * 32) % NT == 0, "whole segments per warp");
-        const int lane = threadIdx.x & 31;
-        for (int seg = threadIdx.x >> 5; seg < SEGS; seg += NT / 32) {
-            const int c = counts[seg];
-            for (int j = lane; j < c; j += 32) f(seg * seg_cap + j, (unsigned long long)base[seg * seg_cap + j]);
-        }
-    }
-    __device__ __forceinline__ void consume(int) const {}
-    __device__ __forceinline__ void replace(int, unsigned long long) const {}
-    static __device__ __forceinline__ unsigned key(unsigned long long r) { return 0x80000000u | ((unsigned)(r >> 16) << 15); }
-    static __device__ __forceinline__ unsigned long long sortkey(unsigned long long r, int) {
-        return ((unsigned long long)key(r) << 32) | (unsigned long long)(0xffffffffu - (unsigned)(r & 0xffffull));
-    }
-};
-
 // ---- ranking helpers ---------------------------------------------------------------------------
 
 // histogram bin of an ord_encode()d score in (0, 1]: exponent and the top 8 mantissa bits,
@@ -837,12 +815,247 @@ __device__ __noinline__ void nms_select_cut(const SegSource src, UnitShared& us,
 #define SSDHOT_FAST_EXIT(code, info) do { if (prm.timeline && threadIdx.x == 0) prm.timeline[(long long)blockIdx.x * 16 + 15] = (unsigned long long)(code) | ((unsigned long long)(info) << 8); } while (0)
 #define SSDHOT_NSTAMP(k) do { if (prm.timeline && threadIdx.x == 0 && first) prm.timeline[(long long)blockIdx.x * 16 + (k)] = globaltimer_ns(); } while (0)
 
-// The rounds of one image (every thread of the CTA).  Preconditions: buf.hist16 and buf.ngroup are zero, the head tables are
-// filled, n_cand = candidates in `src`, and a barrier has published all of it.  FAST (the fused kernel's shared-memory
-// list, one round only): returns false -- CTA-uniformly -- as soon as the image needs anything beyond one histogram-cut
-// round (exact selection, exact keys for the whole list, a second round); the caller then runs the generic path.
-template <bool APPROX, int SRC, bool FAST, typename Src>
-__device__ __forceinline__ bool nms_image_body(const PredictParams& prm, const int b, const ImgBuffers& buf, UnitShared& us,
+// ---- one round's back end (every thread of the CTA) ------------------------------------------------------------------
+// buf.ckey[0 .. K) holds the round's keys (exact score bits << 32 | ~candidate id), zero beyond K up to CH.  Sorts them,
+// decodes the boxes, orders the entries class by class, runs the pair tests against earlier survivors and inside the round,
+// resolves every class and emits the survivors in global score order behind the kept_n earlier ones.
+// -> the number of entries of this round that survive (the caller clamps kept_n + that to max_keep).
+template <int SRC>
+__device__ __forceinline__ int nms_round_backend(const PredictParams& prm, const int b, const ImgBuffers& buf, UnitShared& us,
+                                                 const HeadReader<SRC, 4>& loc_rd, const int K, const int kept_n, const bool first) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_fg = prm.C - 1, max_keep = prm.max_keep;
+    const int METRIC = prm.metric;
+    const bool AGN = prm.agnostic != 0;
+    const int n_groups = AGN ? 1 : n_fg;
+    const float thr = prm.nms_thresh, thr_lo = fmul(thr, kFilterSlack);
+    const bool want_atan = METRIC == SSDHOT_METRIC_CIOU;
+    const long long o = (long long)b * max_keep;
+    const unsigned lt = (1u << lane) - 1u;
+    if (K <= 128) bitonic_desc<128>(buf.ckey);           // (entries beyond K are zero and stay behind)
+    else if (K <= 256) bitonic_desc<256>(buf.ckey);
+    else bitonic_desc<CH>(buf.ckey);
+
+    SSDHOT_NSTAMP(5);
+    if (prm.timeline && tid == 0 && first) prm.timeline[(long long)blockIdx.x * 16 + 13] = (unsigned long long)K;
+    // ---- decode + class-local order --------------------------------------------------------------
+    int my_g = -1;
+    BoxC my_box = {};
+    unsigned my_cells = 0u;
+    if (tid < K) {
+        const unsigned id = 0xffffffffu - (unsigned)(buf.ckey[tid] & 0xffffffffull);
+        const unsigned p = id / (unsigned)n_fg;
+        float lv[4];
+        loc_rd.row((int)p, lv);
+        const float4 box = decode_box(make_float4(lv[0], lv[1], lv[2], lv[3]), ldg4(prm.pri + 4ll * p), prm.vc, prm.vs);
+        const float4 px = to_pixel_xyxy(box, prm.img_w, prm.img_h);
+        my_box = box_consts(px.x, px.y, px.z, px.w, want_atan);
+        {   // which quarter-columns / quarter-rows of the image the (clamped) box reaches: boxes that share no cell
+            // have an empty intersection, so the pair test can skip them on a 16-bit AND
+            const float qx = 4.0f / prm.img_w, qy = 4.0f / prm.img_h;
+            const int cx0 = min(3, max(0, (int)(px.x * qx))), cx1 = min(3, max(0, (int)(px.z * qx)));
+            const int cy0 = min(3, max(0, (int)(px.y * qy))), cy1 = min(3, max(0, (int)(px.w * qy)));
+            const unsigned xm = ((2u << cx1) - 1u) & ~((1u << cx0) - 1u);
+            unsigned m16 = 0u;
+            for (int r = cy0; r <= cy1; ++r) m16 |= xm << (4 * r);
+            // an empty (or NaN) box has union 0 with another empty box: IoU = NaN, which suppresses (SFS:690) -- always test it
+            if (!(fmul(fsub(px.z, px.x), fsub(px.w, px.y)) > 0.0f)) m16 = 0xffffu;
+            my_cells = m16;
+        }
+        my_g = AGN ? 0 : (int)(id % (unsigned)n_fg);
+        buf.cgroup[tid] = (unsigned char)my_g;
+    }
+    for (int i = tid; i < 16 * n_groups; i += IT) buf.wcnt[i] = 0;
+    for (int i = tid; i < n_groups * MW; i += IT) buf.nzW[i] = 0ull;
+    {
+        ulonglong2* m2 = reinterpret_cast<ulonglong2*>(buf.mat);
+        for (int i = tid; i < K * MW / 2; i += IT) m2[i] = make_ulonglong2(0ull, 0ull);
+    }
+    __syncthreads();
+    const unsigned peers = __match_any_sync(FULL, my_g);            // lanes of this warp with the same class
+    const int local_rank = __popc(peers & lt);
+    if (my_g >= 0 && local_rank == 0) buf.wcnt[warp * n_groups + my_g] = __popc(peers);
+    __syncthreads();
+    if (tid < n_groups) {                                           // class totals -> offsets (n_groups <= 255 < IT)
+        int tot = 0;
+        for (int w = 0; w < 16; ++w) tot += buf.wcnt[w * n_groups + tid];
+        us.hist[tid] = (unsigned)tot;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int g = 0; g < n_groups; ++g) { buf.coff[g] = run; run += (int)us.hist[g]; }
+        buf.coff[n_groups] = run;
+    }
+    int my_m = 0;
+    if (my_g >= 0) {
+        for (int w = 0; w < warp; ++w) my_m += buf.wcnt[w * n_groups + my_g];
+        my_m += local_rank;
+        buf.cpos[tid] = (unsigned short)my_m;
+    }
+    __syncthreads();
+    if (my_g >= 0) {                                                // boxes and cell masks in class order
+        const int at = buf.coff[my_g] + my_m;
+        buf.cbox[at] = my_box;
+        buf.cmask[at] = (unsigned short)my_cells;
+    }
+    for (int i = tid; i < n_groups * MW; i += IT) {                 // alive = every position the class has this round
+        const int g = i / MW, w = i % MW, n_c = buf.coff[g + 1] - buf.coff[g];
+        const int bits = min(max(n_c - 64 * w, 0), 64);
+        buf.aliveW[i] = bits == 64 ? ~0ull : ((1ull << bits) - 1ull);
+    }
+    __syncthreads();
+
+    SSDHOT_NSTAMP(6);
+    // ---- pair tests --------------------------------------------------------------------------------
+    // (a) later rounds only: entry j against the survivors of its class from earlier rounds
+    if (kept_n > 0 && tid < K) {
+        const unsigned short* kl = buf.kidx + (size_t)my_g * max_keep;
+        const int ng = buf.ngroup[my_g];
+        bool hit = false;
+        for (int i = 0; i < ng && !hit; ++i) hit = suppresses_rt(METRIC, buf.kept[kl[i]], my_box, thr, thr_lo);
+        if (hit) atomicAnd(reinterpret_cast<unsigned*>(buf.aliveW + my_g * MW) + (my_m >> 5), ~(1u << (my_m & 31)));
+    }
+    // (b) every entry against the earlier entries of its class (boxes and cell masks sit in class order).  The loop
+    //     only runs the cheap tests (common cell, IoU gate); the ~3 % of pairs that pass are listed and get the
+    //     exact metric in a second, dense pass -- in one divergent loop every warp would execute the exact path
+    //     in most iterations.
+    if (tid == 0) us.counter = 0;
+    __syncthreads();
+    auto settle = [&](int g, int cbase, int aq, int m) {          // bit m of row aq (rows in class order) = "aq suppresses m"
+        const BoxC S = buf.cbox[cbase + aq], c = buf.cbox[cbase + m];
+        float inter, uni;
+        iou_gate(S, c, thr_lo, inter, uni);
+        if (suppresses_exact_rt(METRIC, S, c, inter, uni, thr)) {
+            atomicOr(reinterpret_cast<unsigned*>(buf.mat + (size_t)(cbase + aq) * MW) + (m >> 5), 1u << (m & 31));
+            atomicOr(reinterpret_cast<unsigned*>(buf.nzW + g * MW) + (aq >> 5), 1u << (aq & 31));
+        }
+    };
+    {
+        // All (earlier, later) pairs of class positions, class after class, form one index space of
+        // T = sum n_c (n_c - 1) / 2 tests; every thread takes a contiguous run of ceil(T / IT) of them and walks it
+        // (later position m, earlier position aq: aq = 0 .. m-1, then m + 1, then the next class), so the work is
+        // balanced no matter how large individual boxes or classes are.
+        int T = 0;
+        for (int g = 0; g < n_groups; ++g) { const int n_c = buf.coff[g + 1] - buf.coff[g]; T += n_c * (n_c - 1) / 2; }
+        const int W = (T + IT - 1) / IT;
+        int t = tid * W;
+        const int t_end = min(T, t + W);
+        if (t < t_end) {
+            int g = 0, n_c = 0, r = t;
+            for (;; ++g) {                                          // the class that owns test t
+                n_c = buf.coff[g + 1] - buf.coff[g];
+                const int pairs = n_c * (n_c - 1) / 2;
+                if (r < pairs) break;
+                r -= pairs;
+            }
+            int m = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)r)) * 0.5f);      // r = m (m - 1) / 2 + aq, 0 <= aq < m
+            while (m * (m - 1) / 2 > r) --m;
+            while ((m + 1) * m / 2 <= r) ++m;
+            int aq = r - m * (m - 1) / 2;
+            int cbase = buf.coff[g];
+            BoxC c = buf.cbox[cbase + m];
+            unsigned cells = buf.cmask[cbase + m];
+            for (; t < t_end; ++t) {
+                if ((buf.cmask[cbase + aq] & cells) != 0u) {        // a common cell (else: empty intersection)
+                    float inter, uni;
+                    if (iou_gate(buf.cbox[cbase + aq], c, thr_lo, inter, uni)) {
+                        const int slot = atomicAdd(&us.counter, 1);
+                        if (slot < PAIRS_CAP) buf.plist[slot] = (unsigned)aq | ((unsigned)m << 9) | ((unsigned)g << 18);
+                        else settle(g, cbase, aq, m);
+                    }
+                }
+                if (++aq == m) {                                    // next later position / next class
+                    aq = 0;
+                    if (++m == n_c && t + 1 < t_end) {
+                        do { ++g; n_c = buf.coff[g + 1] - buf.coff[g]; } while (n_c < 2);
+                        cbase = buf.coff[g];
+                        m = 1;
+                    }
+                    if (t + 1 < t_end) { c = buf.cbox[cbase + m]; cells = buf.cmask[cbase + m]; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int n_list = min(us.counter, PAIRS_CAP);
+        for (int e = tid; e < n_list; e += IT) {
+            const unsigned pr = buf.plist[e];
+            const int g = (int)(pr >> 18);
+            settle(g, buf.coff[g], (int)(pr & 511u), (int)((pr >> 9) & 511u));
+        }
+    }
+    __syncthreads();
+
+    SSDHOT_NSTAMP(7);
+    // ---- resolve: one warp per class, rows in score order ----------------------------------------------
+    for (int g = warp; g < n_groups; g += IT / 32) {
+        const int cbase = buf.coff[g], n_c = buf.coff[g + 1] - cbase;
+        if (n_c == 0) continue;
+        const int words = (n_c + 63) >> 6;
+        if (words == 1) {                                   // the usual case: everything in the registers of one lane
+            if (lane == 0) {
+                unsigned long long a = buf.aliveW[g * MW];
+                const unsigned long long nz = buf.nzW[g * MW];
+                unsigned long long pend = a & nz;
+                while (pend) {
+                    const int bit = __ffsll((long long)pend) - 1;
+                    a &= ~buf.mat[(size_t)(cbase + bit) * MW];
+                    pend = a & nz & ~((2ull << bit) - 1ull);
+                }
+                buf.aliveW[g * MW] = a;
+            }
+            continue;
+        }
+        unsigned long long a = lane < MW ? buf.aliveW[g * MW + lane] : 0ull;
+        for (int w0 = 0; w0 < words; ++w0) {
+            const unsigned long long nz = buf.nzW[g * MW + w0];
+            unsigned long long pend = __shfl_sync(FULL, a, w0) & nz;
+            while (pend) {
+                const int bit = __ffsll((long long)pend) - 1;
+                if (lane < MW) a &= ~buf.mat[(size_t)(cbase + w0 * 64 + bit) * MW + lane];
+                pend = __shfl_sync(FULL, a, w0) & nz & ~((2ull << bit) - 1ull);
+            }
+        }
+        if (lane < MW) buf.aliveW[g * MW + lane] = a;
+    }
+    __syncthreads();
+
+    SSDHOT_NSTAMP(8);
+    // ---- emit survivors in global score order ------------------------------------------------------------
+    bool alive = false;
+    if (my_g >= 0) alive = (buf.aliveW[my_g * MW + (my_m >> 6)] >> (my_m & 63)) & 1ull;
+    const unsigned ab = __ballot_sync(FULL, alive);
+    if (lane == 0) us.iscratch[warp] = __popc(ab);
+    __syncthreads();
+    int before = __popc(ab & lt), total_alive = 0;
+    for (int w = 0; w < IT / 32; ++w) { const int c = us.iscratch[w]; if (w < warp) before += c; total_alive += c; }
+    const int pos = kept_n + before;
+    if (alive && pos < max_keep) {
+        const BoxC bx = my_box;
+        buf.kept[pos] = bx;
+        // survivors of the class ahead of this one in the round: alive positions below m
+        int crank = 0;
+        for (int w = 0; w < (my_m >> 6); ++w) crank += __popcll(buf.aliveW[my_g * MW + w]);
+        crank += __popcll(buf.aliveW[my_g * MW + (my_m >> 6)] & ((1ull << (my_m & 63)) - 1ull));
+        buf.kidx[(size_t)my_g * max_keep + buf.ngroup[my_g] + crank] = (unsigned short)pos;
+        const unsigned long long key = buf.ckey[tid];
+        const unsigned id = 0xffffffffu - (unsigned)(key & 0xffffffffull);
+        prm.out_labels[o + pos] = (int64_t)(id % (unsigned)n_fg);
+        prm.out_scores[o + pos] = __uint_as_float((unsigned)(key >> 32) & 0x7fffffffu);
+        reinterpret_cast<float4*>(prm.out_boxes)[o + pos] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
+        if (prm.out_cand) prm.out_cand[o + pos] = (int32_t)id;
+    }
+    __syncthreads();
+    if (alive && pos < max_keep) atomicAdd(&buf.ngroup[my_g], 1);
+    return total_alive;
+}
+
+// The rounds of one image on the GLOBAL candidate lists (every thread of the CTA).  Preconditions: buf.hist16 and buf.ngroup
+// are zero, the head tables are filled, n_cand = candidates in `src`, and a barrier has published all of it.
+template <bool APPROX, int SRC, typename Src>
+__device__ __forceinline__ void nms_image_body(const PredictParams& prm, const int b, const ImgBuffers& buf, UnitShared& us,
                                                const HeadTable& loc_tab, const HeadTable& conf_tab, const Src& src, const int n_cand) {
     constexpr int KEY_MARGIN = 512;                // ulps: >= 3e-5 relative, 3x the worst error of an approximate score
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -863,38 +1076,29 @@ __device__ __forceinline__ bool nms_image_body(const PredictParams& prm, const i
     bool keys_exact = !APPROX;
     if (use_hist) src.template for_each<IT>([&](int, unsigned long long r) { hist_add(buf.hist16, Src::key(r)); });
     __syncthreads();
-    auto make_exact = [&]() {
-        if constexpr (!FAST) { nms_make_exact<SRC>(src, buf.hist16, conf_rd, use_hist); keys_exact = true; }
-    };
+    auto make_exact = [&]() { nms_make_exact<SRC>(src, buf.hist16, conf_rd, use_hist); keys_exact = true; };
 
     SSDHOT_NSTAMP(1);
     int kept_n = 0, remaining = n_cand;
     while (remaining > 0 && kept_n < max_keep) {
         // ---- pull ----------------------------------------------------------------------------------
         int K = remaining < CH ? remaining : CH;
-        unsigned tkey = 1u, tie_floor = 0u, fast_gkey = 1u;
+        unsigned tkey = 1u, tie_floor = 0u;
         bool all = remaining <= CH;
         if (!all && use_hist) {
             int cap = keys_exact ? CH : CH - 16;            // (room for the few margin strays)
             if (first) cap = min(cap, max(64, max_keep + (max_keep >> 1) + 16));
             hist_cut<IT>(buf.hist16, cap, us);
-            int cut_bin = 0;
-            if (us.cut_count > 0) { K = us.cut_count; cut_bin = us.cut_bin; tkey = bin_floor_key(cut_bin); all = true; }
+            if (us.cut_count > 0) { K = us.cut_count; tkey = bin_floor_key(us.cut_bin); all = true; }
             else use_hist = false;                          // a single bin holds more than the cap: exact select from here on
             __syncthreads();
-            // FAST entries carry the floor of their (approximate) score's bin: an exact score at or above the cut can sit at most
-            // one bin lower, so the gather reaches one bin below the cut (bin_floor_key(<= 0) = 1 takes everything)
-            if (FAST && all) fast_gkey = bin_floor_key(cut_bin - 1);
         }
         if (!all) {
-            if constexpr (FAST) { SSDHOT_FAST_EXIT(2, us.cut_bin); return false; }
-            else {
-                if (APPROX && !keys_exact) make_exact();
-                nms_select_cut(src, us, K, &tkey, &tie_floor);
-            }
+            if (APPROX && !keys_exact) make_exact();
+            nms_select_cut(src, us, K, &tkey, &tie_floor);
         }
         SSDHOT_NSTAMP(2);
-        const unsigned gkey = FAST ? fast_gkey : ((keys_exact || tkey <= (unsigned)KEY_MARGIN) ? tkey : tkey - (unsigned)KEY_MARGIN);
+        const unsigned gkey = (keys_exact || tkey <= (unsigned)KEY_MARGIN) ? tkey : tkey - (unsigned)KEY_MARGIN;
         if (tid == 0) us.counter = 0;
         __syncthreads();
         src.for_each<IT>([&](int i, unsigned long long r) {
@@ -910,7 +1114,6 @@ __device__ __forceinline__ bool nms_image_body(const PredictParams& prm, const i
         if (APPROX && !keys_exact) {
             const int gathered = us.counter;
             if (gathered > CH) {                            // more margin strays than the slack: settle it with exact keys
-                if constexpr (FAST) { SSDHOT_FAST_EXIT(3, gathered); return false; }
                 __syncthreads();
                 make_exact();
                 continue;
@@ -931,236 +1134,17 @@ __device__ __forceinline__ bool nms_image_body(const PredictParams& prm, const i
         }
         SSDHOT_NSTAMP(4);
         if (K == 0) {                                                           // (only margin strays: the next cut is lower)
-            if constexpr (FAST) { SSDHOT_FAST_EXIT(4, 0); return false; }
             first = false;
             continue;
         }
-        if (K <= 128) bitonic_desc<128>(buf.ckey);           // (entries beyond K are zero and stay behind)
-        else if (K <= 256) bitonic_desc<256>(buf.ckey);
-        else bitonic_desc<CH>(buf.ckey);
-
-        SSDHOT_NSTAMP(5);
-        if (prm.timeline && tid == 0 && first) prm.timeline[(long long)blockIdx.x * 16 + 13] = (unsigned long long)K;
-        // ---- decode + class-local order --------------------------------------------------------------
-        int my_g = -1;
-        BoxC my_box = {};
-        unsigned my_cells = 0u;
-        if (tid < K) {
-            const unsigned id = 0xffffffffu - (unsigned)(buf.ckey[tid] & 0xffffffffull);
-            const unsigned p = id / (unsigned)n_fg;
-            float lv[4];
-            loc_rd.row((int)p, lv);
-            const float4 box = decode_box(make_float4(lv[0], lv[1], lv[2], lv[3]), ldg4(prm.pri + 4ll * p), prm.vc, prm.vs);
-            const float4 px = to_pixel_xyxy(box, prm.img_w, prm.img_h);
-            my_box = box_consts(px.x, px.y, px.z, px.w, want_atan);
-            {   // which quarter-columns / quarter-rows of the image the (clamped) box reaches: boxes that share no cell
-                // have an empty intersection, so the pair test can skip them on a 16-bit AND
-                const float qx = 4.0f / prm.img_w, qy = 4.0f / prm.img_h;
-                const int cx0 = min(3, max(0, (int)(px.x * qx))), cx1 = min(3, max(0, (int)(px.z * qx)));
-                const int cy0 = min(3, max(0, (int)(px.y * qy))), cy1 = min(3, max(0, (int)(px.w * qy)));
-                const unsigned xm = ((2u << cx1) - 1u) & ~((1u << cx0) - 1u);
-                unsigned m16 = 0u;
-                for (int r = cy0; r <= cy1; ++r) m16 |= xm << (4 * r);
-                // an empty (or NaN) box has union 0 with another empty box: IoU = NaN, which suppresses (SFS:690) -- always test it
-                if (!(fmul(fsub(px.z, px.x), fsub(px.w, px.y)) > 0.0f)) m16 = 0xffffu;
-                my_cells = m16;
-            }
-            my_g = AGN ? 0 : (int)(id % (unsigned)n_fg);
-            buf.cgroup[tid] = (unsigned char)my_g;
-        }
-        for (int i = tid; i < 16 * n_groups; i += IT) buf.wcnt[i] = 0;
-        for (int i = tid; i < n_groups * MW; i += IT) buf.nzW[i] = 0ull;
-        {
-            ulonglong2* m2 = reinterpret_cast<ulonglong2*>(buf.mat);
-            for (int i = tid; i < K * MW / 2; i += IT) m2[i] = make_ulonglong2(0ull, 0ull);
-        }
-        __syncthreads();
-        const unsigned peers = __match_any_sync(FULL, my_g);            // lanes of this warp with the same class
-        const int local_rank = __popc(peers & lt);
-        if (my_g >= 0 && local_rank == 0) buf.wcnt[warp * n_groups + my_g] = __popc(peers);
-        __syncthreads();
-        if (tid < n_groups) {                                           // class totals -> offsets (n_groups <= 255 < IT)
-            int tot = 0;
-            for (int w = 0; w < 16; ++w) tot += buf.wcnt[w * n_groups + tid];
-            us.hist[tid] = (unsigned)tot;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int run = 0;
-            for (int g = 0; g < n_groups; ++g) { buf.coff[g] = run; run += (int)us.hist[g]; }
-            buf.coff[n_groups] = run;
-        }
-        int my_m = 0;
-        if (my_g >= 0) {
-            for (int w = 0; w < warp; ++w) my_m += buf.wcnt[w * n_groups + my_g];
-            my_m += local_rank;
-            buf.cpos[tid] = (unsigned short)my_m;
-        }
-        __syncthreads();
-        if (my_g >= 0) {                                                // boxes and cell masks in class order
-            const int at = buf.coff[my_g] + my_m;
-            buf.cbox[at] = my_box;
-            buf.cmask[at] = (unsigned short)my_cells;
-        }
-        for (int i = tid; i < n_groups * MW; i += IT) {                 // alive = every position the class has this round
-            const int g = i / MW, w = i % MW, n_c = buf.coff[g + 1] - buf.coff[g];
-            const int bits = min(max(n_c - 64 * w, 0), 64);
-            buf.aliveW[i] = bits == 64 ? ~0ull : ((1ull << bits) - 1ull);
-        }
-        __syncthreads();
-
-        SSDHOT_NSTAMP(6);
-        // ---- pair tests --------------------------------------------------------------------------------
-        // (a) later rounds only: entry j against the survivors of its class from earlier rounds
-        if (kept_n > 0 && tid < K) {
-            const unsigned short* kl = buf.kidx + (size_t)my_g * max_keep;
-            const int ng = buf.ngroup[my_g];
-            bool hit = false;
-            for (int i = 0; i < ng && !hit; ++i) hit = suppresses_rt(METRIC, buf.kept[kl[i]], my_box, thr, thr_lo);
-            if (hit) atomicAnd(reinterpret_cast<unsigned*>(buf.aliveW + my_g * MW) + (my_m >> 5), ~(1u << (my_m & 31)));
-        }
-        // (b) every entry against the earlier entries of its class (boxes and cell masks sit in class order).  The loop
-        //     only runs the cheap tests (common cell, IoU gate); the ~3 % of pairs that pass are listed and get the
-        //     exact metric in a second, dense pass -- in one divergent loop every warp would execute the exact path
-        //     in most iterations.
-        if (tid == 0) us.counter = 0;
-        __syncthreads();
-        auto settle = [&](int g, int cbase, int aq, int m) {          // bit m of row aq (rows in class order) = "aq suppresses m"
-            const BoxC S = buf.cbox[cbase + aq], c = buf.cbox[cbase + m];
-            float inter, uni;
-            iou_gate(S, c, thr_lo, inter, uni);
-            if (suppresses_exact_rt(METRIC, S, c, inter, uni, thr)) {
-                atomicOr(reinterpret_cast<unsigned*>(buf.mat + (size_t)(cbase + aq) * MW) + (m >> 5), 1u << (m & 31));
-                atomicOr(reinterpret_cast<unsigned*>(buf.nzW + g * MW) + (aq >> 5), 1u << (aq & 31));
-            }
-        };
-        {
-            // All (earlier, later) pairs of class positions, class after class, form one index space of
-            // T = sum n_c (n_c - 1) / 2 tests; every thread takes a contiguous run of ceil(T / IT) of them and walks it
-            // (later position m, earlier position aq: aq = 0 .. m-1, then m + 1, then the next class), so the work is
-            // balanced no matter how large individual boxes or classes are.
-            int T = 0;
-            for (int g = 0; g < n_groups; ++g) { const int n_c = buf.coff[g + 1] - buf.coff[g]; T += n_c * (n_c - 1) / 2; }
-            const int W = (T + IT - 1) / IT;
-            int t = tid * W;
-            const int t_end = min(T, t + W);
-            if (t < t_end) {
-                int g = 0, n_c = 0, r = t;
-                for (;; ++g) {                                          // the class that owns test t
-                    n_c = buf.coff[g + 1] - buf.coff[g];
-                    const int pairs = n_c * (n_c - 1) / 2;
-                    if (r < pairs) break;
-                    r -= pairs;
-                }
-                int m = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)r)) * 0.5f);      // r = m (m - 1) / 2 + aq, 0 <= aq < m
-                while (m * (m - 1) / 2 > r) --m;
-                while ((m + 1) * m / 2 <= r) ++m;
-                int aq = r - m * (m - 1) / 2;
-                int cbase = buf.coff[g];
-                BoxC c = buf.cbox[cbase + m];
-                unsigned cells = buf.cmask[cbase + m];
-                for (; t < t_end; ++t) {
-                    if ((buf.cmask[cbase + aq] & cells) != 0u) {        // a common cell (else: empty intersection)
-                        float inter, uni;
-                        if (iou_gate(buf.cbox[cbase + aq], c, thr_lo, inter, uni)) {
-                            const int slot = atomicAdd(&us.counter, 1);
-                            if (slot < PAIRS_CAP) buf.plist[slot] = (unsigned)aq | ((unsigned)m << 9) | ((unsigned)g << 18);
-                            else settle(g, cbase, aq, m);
-                        }
-                    }
-                    if (++aq == m) {                                    // next later position / next class
-                        aq = 0;
-                        if (++m == n_c && t + 1 < t_end) {
-                            do { ++g; n_c = buf.coff[g + 1] - buf.coff[g]; } while (n_c < 2);
-                            cbase = buf.coff[g];
-                            m = 1;
-                        }
-                        if (t + 1 < t_end) { c = buf.cbox[cbase + m]; cells = buf.cmask[cbase + m]; }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        {
-            const int n_list = min(us.counter, PAIRS_CAP);
-            for (int e = tid; e < n_list; e += IT) {
-                const unsigned pr = buf.plist[e];
-                const int g = (int)(pr >> 18);
-                settle(g, buf.coff[g], (int)(pr & 511u), (int)((pr >> 9) & 511u));
-            }
-        }
-        __syncthreads();
-
-        SSDHOT_NSTAMP(7);
-        // ---- resolve: one warp per class, rows in score order ----------------------------------------------
-        for (int g = warp; g < n_groups; g += IT / 32) {
-            const int cbase = buf.coff[g], n_c = buf.coff[g + 1] - cbase;
-            if (n_c == 0) continue;
-            const int words = (n_c + 63) >> 6;
-            if (words == 1) {                                   // the usual case: everything in the registers of one lane
-                if (lane == 0) {
-                    unsigned long long a = buf.aliveW[g * MW];
-                    const unsigned long long nz = buf.nzW[g * MW];
-                    unsigned long long pend = a & nz;
-                    while (pend) {
-                        const int bit = __ffsll((long long)pend) - 1;
-                        a &= ~buf.mat[(size_t)(cbase + bit) * MW];
-                        pend = a & nz & ~((2ull << bit) - 1ull);
-                    }
-                    buf.aliveW[g * MW] = a;
-                }
-                continue;
-            }
-            unsigned long long a = lane < MW ? buf.aliveW[g * MW + lane] : 0ull;
-            for (int w0 = 0; w0 < words; ++w0) {
-                const unsigned long long nz = buf.nzW[g * MW + w0];
-                unsigned long long pend = __shfl_sync(FULL, a, w0) & nz;
-                while (pend) {
-                    const int bit = __ffsll((long long)pend) - 1;
-                    if (lane < MW) a &= ~buf.mat[(size_t)(cbase + w0 * 64 + bit) * MW + lane];
-                    pend = __shfl_sync(FULL, a, w0) & nz & ~((2ull << bit) - 1ull);
-                }
-            }
-            if (lane < MW) buf.aliveW[g * MW + lane] = a;
-        }
-        __syncthreads();
-
-        SSDHOT_NSTAMP(8);
-        // ---- emit survivors in global score order ------------------------------------------------------------
-        bool alive = false;
-        if (my_g >= 0) alive = (buf.aliveW[my_g * MW + (my_m >> 6)] >> (my_m & 63)) & 1ull;
-        const unsigned ab = __ballot_sync(FULL, alive);
-        if (lane == 0) us.iscratch[warp] = __popc(ab);
-        __syncthreads();
-        int before = __popc(ab & lt), total_alive = 0;
-        for (int w = 0; w < IT / 32; ++w) { const int c = us.iscratch[w]; if (w < warp) before += c; total_alive += c; }
-        const int pos = kept_n + before;
-        if (alive && pos < max_keep) {
-            const BoxC bx = my_box;
-            buf.kept[pos] = bx;
-            // survivors of the class ahead of this one in the round: alive positions below m
-            int crank = 0;
-            for (int w = 0; w < (my_m >> 6); ++w) crank += __popcll(buf.aliveW[my_g * MW + w]);
-            crank += __popcll(buf.aliveW[my_g * MW + (my_m >> 6)] & ((1ull << (my_m & 63)) - 1ull));
-            buf.kidx[(size_t)my_g * max_keep + buf.ngroup[my_g] + crank] = (unsigned short)pos;
-            const unsigned long long key = buf.ckey[tid];
-            const unsigned id = 0xffffffffu - (unsigned)(key & 0xffffffffull);
-            prm.out_labels[o + pos] = (int64_t)(id % (unsigned)n_fg);
-            prm.out_scores[o + pos] = __uint_as_float((unsigned)(key >> 32) & 0x7fffffffu);
-            reinterpret_cast<float4*>(prm.out_boxes)[o + pos] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
-            if (prm.out_cand) prm.out_cand[o + pos] = (int32_t)id;
-        }
-        __syncthreads();
-        if (alive && pos < max_keep) atomicAdd(&buf.ngroup[my_g], 1);
+        const int total_alive = nms_round_backend<SRC>(prm, b, buf, us, loc_rd, K, kept_n, first);
         kept_n = min(max_keep, kept_n + total_alive);
         remaining -= K;
         __syncthreads();
         SSDHOT_NSTAMP(9);
         first = false;
-        if (FAST && remaining > 0 && kept_n < max_keep) { SSDHOT_FAST_EXIT(5, kept_n | (K << 12)); return false; }   // a second round: the generic path redoes the image
     }
     if (tid == 0) { prm.out_count[b] = kept_n; if (prm.timeline) { prm.timeline[(long long)b * 16 + 10] = globaltimer_ns(); unsigned sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); prm.timeline[(long long)b * 16 + 11] = sm; prm.timeline[(long long)b * 16 + 12] = (unsigned long long)n_cand; } }
-    return true;
 }
 
 template <bool APPROX, int SRC>
@@ -1185,31 +1169,34 @@ __global__ void __launch_bounds__(IT, 2) nms_image_kernel(const PredictParams pr
         head_table_fill<SRC, 6>(conf_tab, prm.conf_h, b, tid - 32);
     }
     __syncthreads();
-    nms_image_body<APPROX, SRC, false>(prm, b, buf, us, loc_tab, conf_tab, src, n_cand);
+    nms_image_body<APPROX, SRC>(prm, b, buf, us, loc_tab, conf_tab, src, n_cand);
 }
 
 
-// ---- predict in ONE kernel: stream -> shared-memory candidate list -> one NMS round -----------------------------------
-// predict_image_kernel (one CTA of 512 threads per image, two per SM) is score_kernel and nms_image_kernel back to back
-// inside one CTA for the case every typical image is: the 16 warps stream the image's logits exactly as score_kernel's
-// 16 warps do, but append the candidates to per-warp segments of a list in SHARED memory (32-bit entries, SmemSource), so
-// the 8-byte keys never travel to HBM and back, the score histogram is built from shared memory, and the gather reads
-// shared memory.  The list occupies the space the later stages use for the suppression matrix, the boxes and the
-// survivors; it is dead once the round's candidates have been gathered.  Whatever does not fit that mould -- a list
-// segment that overflows, a histogram that cannot give a cut, a second round -- makes the CTA redo its image on the generic
-// path: score_segment into the global lists, then nms_image_body on them (the two-kernel path, run by this CTA alone).
-// Results are those of the two-kernel path bit for bit: the candidate set is exact either way, pulled candidates get exact
-// scores, and every later stage is shared code.
+// ---- predict in ONE kernel: stream -> row keys in shared memory -> hot rows -> one NMS round -----------------------------
+// predict_image_kernel (one CTA of 512 threads per image, two per SM) serves the case every typical image is: the
+// detections come out of ONE round over the few hundred best candidates.  Those candidates sit in few rows, so the stream
+// does not list candidates at all.  Per row it keeps ONE 16-bit key -- the histogram bin of the row's best approximate
+// foreground score (0: no class can pass the score threshold) -- in shared memory: no per-candidate work, no compaction, no
+// list in HBM.  Then: histogram of the row keys -> the cut that leaves <= ~1.5 max_per_img rows -> the "hot" rows (key at most
+// one bin below the cut: an approximate score is within 1.1e-5 of the exact one, a bin is 3.9e-3 wide) -> one thread per
+// hot row evaluates the row with the exact eager-CUDA arithmetic (SFS:388, :402) and appends every class whose exact score
+// passes the threshold and reaches the cut.  Every candidate at or above the cut lives in a hot row, so the pulled set is
+// exactly the set the two-kernel path pulls for the same cut, and the shared back end (nms_round_backend) does the rest.
+// Whatever does not fit that mould -- no usable cut, more than CH pulled candidates, a second round -- makes the CTA redo
+// its image on the generic path: score_segment into the global lists, then nms_image_body on them.
+constexpr int HOT_CAP = CH;        // hot rows of a round (one thread each)
 
-// One warp's share of the stream into its shared-memory segment.  -> number of entries, or -1 if the segment overflowed.
+// One warp's share of the stream: key16[p] for the rows of list segment `seg` (same row ranges as score_segment).
 template <int SRC>
-__device__ __forceinline__ int stream_segment_smem(const PredictParams& prm, int b, int seg, int lane, const HeadTable& htab,
-                                                   const PlaneRegions& regions, unsigned* __restrict__ list, int cap) {
+__device__ __forceinline__ void stream_row_keys(const PredictParams& prm, int b, int seg, int lane, const HeadTable& htab,
+                                                const PlaneRegions& regions, unsigned* __restrict__ rowkey32,
+                                                unsigned* __restrict__ hist16, int* __restrict__ n_rows_cand) {
     const int P = prm.P;
     const int rows = seg_rows(P);
     const int r0 = min(P, seg * rows), r1 = min(P, r0 + rows);
     const float* conf_b = SRC == SRC_PACKED ? prm.conf_all + (long long)b * P * 6 : nullptr;
-    const float thr = prm.score_thresh, thr_hi = thr * 1.0001f, thr_lo = thr * 0.9999f;
+    const float thr_lo = prm.score_thresh * 0.9999f;    // a row whose best approximate score is below this has no candidate
     const HeadReader<SRC, 6> rd = {conf_b, &htab};
     const int q0 = r0 >> 1, q1 = r1 >> 1;               // P is even on this path
     const int n_it = SRC == SRC_LEVEL_PLANES ? (kPlaneChunks - seg + SEGS - 1) / SEGS : (q1 - q0 + 31) >> 5;
@@ -1225,80 +1212,42 @@ __device__ __forceinline__ int stream_segment_smem(const PredictParams& prm, int
             return q < q1;
         }
     };
-    int cnt = 0;                                        // warp-uniform
-    bool overflow = false;
     constexpr float kL2E = 1.4426950408889634f;
-    // one row pair of this lane: pass bits (bit h * 5 + k: row p0 + h, class k + 1), then the warp-wide append
+    int n_cand_rows = 0;                                // this lane's rows that can hold a candidate
     auto process = [&](const float* x, int p0, bool live) {
-        unsigned pass = 0u;
-        float e[2][6], rs[2];
-        if (live) {
+        if (!live) return;
+        unsigned packed = 0u;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float* xr = x + 6 * h;
-                const float mx = fmaxf(fmaxf(fmaxf(xr[0], xr[1]), fmaxf(xr[2], xr[3])), fmaxf(xr[4], xr[5]));
-                const float nm = -mx * kL2E;            // the common shift cancels in e_k / sum (a NaN / Inf row stays NaN)
+        for (int h = 0; h < 2; ++h) {
+            const float* xr = x + 6 * h;
+            const float mx = fmaxf(fmaxf(fmaxf(xr[0], xr[1]), fmaxf(xr[2], xr[3])), fmaxf(xr[4], xr[5]));
+            const float nm = -mx * kL2E;                // the common shift cancels in e_k / sum (a NaN / Inf row stays NaN)
+            float e[6];
 #pragma unroll
-                for (int i = 0; i < 6; ++i) e[h][i] = ex2_approx_ftz(fmaf(xr[i], kL2E, nm));
-                const float sum = ((e[h][0] + e[h][1]) + (e[h][2] + e[h][3])) + (e[h][4] + e[h][5]);
-                const float t_hi = sum * thr_hi, t_lo = sum * thr_lo;      // score > thr  <=>  e_k > thr * sum
-                rs[h] = rcp_approx_ftz(sum);
-                bool maybe = false;
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const bool hi = e[h][k + 1] > t_hi;
-                    if (hi) pass |= 1u << (h * 5 + k);
-                    maybe |= (e[h][k + 1] >= t_lo) != hi;
-                }
-                if (maybe) {                            // within 1e-4 of the threshold: the exact arithmetic decides
-                    float ee[6];
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) ee[i] = expf(fsub(xr[i], mx));
-                    const float se = fadd(fadd(fadd(ee[0], ee[4]), ee[2]), fadd(fadd(ee[1], ee[5]), ee[3]));
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        const unsigned bit = 1u << (h * 5 + k);
-                        const bool near = (e[h][k + 1] >= t_lo) != ((pass & bit) != 0u);
-                        if (near && fdiv(ee[k + 1], se) > thr) pass |= bit;
-                    }
-                }
+            for (int i = 0; i < 6; ++i) e[i] = ex2_approx_ftz(fmaf(xr[i], kL2E, nm));
+            const float sum = ((e[0] + e[1]) + (e[2] + e[3])) + (e[4] + e[5]);
+            const float emax = fmaxf(fmaxf(fmaxf(e[1], e[2]), fmaxf(e[3], e[4])), e[5]);
+            const float sc = emax * rcp_approx_ftz(sum);                    // the row's best approximate foreground score
+            unsigned k16 = max(__float_as_uint(sc) >> 15, 1u);              // its histogram bin (+ HBASE); never 0 for a candidate row
+            if (emax >= thr_lo * sum) {                                     // (NaN rows: the comparison is false -> no candidate)
+                packed |= k16 << (16 * h);
+                hist_add(hist16, 0x80000000u | (k16 << 15));                // the histogram of the row keys rides along
+                ++n_cand_rows;
             }
         }
-        const int mine = __popc(pass);
-        int incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += y;
-        }
-        const int total = __shfl_sync(FULL, incl, 31);
-        if (cnt + total > cap) { overflow = true; return; }          // warp-uniform
-        unsigned* at = list + cnt + incl - mine;
-        cnt += total;
-        if (pass) {
-            const unsigned id0 = (unsigned)p0 * 5u;
-#pragma unroll
-            for (int j = 0; j < 10; ++j) {
-                if ((pass >> j) & 1u) {
-                    const float sc = e[j / 5][j % 5 + 1] * rs[j / 5];
-                    *at++ = ((__float_as_uint(sc) << 1) & 0xffff0000u) | (id0 + (unsigned)j);
-                }
-            }
-        }
+        rowkey32[p0 >> 1] = packed;
     };
     float xa[12], xb[12];
-#pragma unroll
-    for (int j = 0; j < 12; ++j) { xa[j] = 0.f; xb[j] = 0.f; }
     int pa = 0, pb = 0;
     bool la = load_it(0, xa, pa), lb = false;
-    for (int it = 0; it < n_it && !overflow; it += 2) {         // two iterations per trip: the next pair's loads are in flight
+    for (int it = 0; it < n_it; it += 2) {             // two iterations per trip: the next pair's loads are in flight
         lb = load_it(it + 1, xb, pb);
         process(xa, pa, la);
-        if (overflow) break;
         la = load_it(it + 2, xa, pa);
-        if (it + 1 < n_it) process(xb, pb, lb);
+        process(xb, pb, lb);
     }
-    return overflow ? -1 : cnt;
+    n_cand_rows = __reduce_add_sync(FULL, n_cand_rows);
+    if (lane == 0 && n_cand_rows) atomicAdd(n_rows_cand, n_cand_rows);
 }
 
 template <int SRC>
@@ -1307,17 +1256,16 @@ __global__ void __launch_bounds__(IT, 2) predict_image_kernel(const PredictParam
     __shared__ UnitShared us;
     __shared__ HeadTable loc_tab, conf_tab;        // per-level bases of this image (head sources only)
     __shared__ PlaneRegions regions;               // (NCHW heads)
-    __shared__ int seg_count[SEGS];
-    __shared__ int hard;
+    __shared__ int n_rows_cand, n_hot, more_low;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
-    const int n_fg = prm.C - 1, n_groups = prm.agnostic ? 1 : n_fg;
-    const ImgBuffers buf = carve_img(dyn, prm.max_keep, n_groups);
-    // the list lives where the suppression rows, class-ordered boxes and survivors will be: [mat, hist16)
-    unsigned* list = reinterpret_cast<unsigned*>(buf.mat);
-    const int cap = (int)((reinterpret_cast<unsigned char*>(buf.hist16) - reinterpret_cast<unsigned char*>(buf.mat)) / (4 * SEGS));
+    const int n_fg = prm.C - 1, n_groups = prm.agnostic ? 1 : n_fg, P = prm.P, max_keep = prm.max_keep;
+    const ImgBuffers buf = carve_img(dyn, max_keep, n_groups);
+    // the row keys and the hot-row list live where the suppression rows and class-ordered boxes will be (dead before those are written)
+    unsigned* rowkey32 = reinterpret_cast<unsigned*>(buf.mat);                 // [P / 2] two 16-bit keys per word
+    int* hot = reinterpret_cast<int*>(rowkey32 + ((P / 2 + 3) & ~3));            // [HOT_CAP]
     for (int i = tid; i < HBINS / 2; i += IT) buf.hist16[i] = 0u;
     for (int g = tid; g < n_groups; g += IT) buf.ngroup[g] = 0;
-    if (tid == 0) hard = 0;
+    if (tid == 0) { n_rows_cand = 0; n_hot = 0; more_low = 0; us.counter = 0; }
     if (SRC != SRC_PACKED) {
         head_table_fill<SRC, 4>(loc_tab, prm.loc_h, b, tid);
         head_table_fill<SRC, 6>(conf_tab, prm.conf_h, b, tid - 32);
@@ -1325,26 +1273,91 @@ __global__ void __launch_bounds__(IT, 2) predict_image_kernel(const PredictParam
     }
     if (prm.timeline && tid == 0) prm.timeline[(long long)b * 16 + 14] = globaltimer_ns();
     __syncthreads();
-    {
-        const int c = stream_segment_smem<SRC>(prm, b, warp, lane, conf_tab, regions, list + warp * cap, cap);
-        if (lane == 0) {
-            seg_count[warp] = max(c, 0);
-            if (c < 0) hard = 1;
+    stream_row_keys<SRC>(prm, b, warp, lane, conf_tab, regions, rowkey32, buf.hist16, &n_rows_cand);
+    __syncthreads();
+    bool first = true;
+    SSDHOT_NSTAMP(0);
+    const HeadReader<SRC, 4> loc_rd = {SRC == SRC_PACKED ? prm.loc_all + 4ll * b * P : nullptr, &loc_tab};
+    const HeadReader<SRC, 6> conf_rd = {SRC == SRC_PACKED ? prm.conf_all + (long long)b * P * prm.C : nullptr, &conf_tab};
+    const int rows_cand = n_rows_cand;
+    int fail = 0;                                   // (CTA-uniform) why the image leaves the fused mould, 0 = it does not
+    unsigned tkey = 1u, floor16 = 1u;               // pulled: exact key >= tkey; hot: row key >= floor16
+    const int cap_rows = min(HOT_CAP - 16, max(64, max_keep + (max_keep >> 2) + 16));      // rows of the round (~1.1 candidates each)
+    if (rows_cand > cap_rows) {
+        if (rows_cand >= 65536) fail = 2;           // (16-bit bin counters)
+        else {
+            hist_cut<IT>(buf.hist16, cap_rows, us);
+            if (us.cut_count > 0) {
+                tkey = bin_floor_key(us.cut_bin);
+                floor16 = us.cut_bin - 1 >= 1 ? (unsigned)(us.cut_bin - 1 + HBASE) : 1u;      // one bin below the cut
+            } else fail = 2;                        // a single bin holds more rows than a round takes
         }
     }
-    __syncthreads();
-    if (prm.timeline && tid == 0) prm.timeline[(long long)b * 16 + 0] = globaltimer_ns();
-    bool done = false;
-    if (!hard) {
-        SmemSource src;
-        src.base = list; src.counts = seg_count; src.seg_cap = cap;
-        int n_cand = 0;
+    SSDHOT_NSTAMP(2);
+    int kept_n = 0;
+    if (!fail && rows_cand > 0) {
+        // ---- hot rows ----------------------------------------------------------------------------------------------------
+        for (int q = tid; q < P / 2; q += IT) {
+            const unsigned w = rowkey32[q];
 #pragma unroll
-        for (int w = 0; w < SEGS; ++w) n_cand += seg_count[w];
-        done = nms_image_body<true, SRC, true>(prm, b, buf, us, loc_tab, conf_tab, src, n_cand);
+            for (int h = 0; h < 2; ++h) {
+                const unsigned k = h ? (w >> 16) : (w & 0xffffu);
+                if (k >= floor16 && k != 0u) {
+                    const int at = atomicAdd(&n_hot, 1);
+                    if (at < HOT_CAP) hot[at] = 2 * q + h;
+                }
+            }
+        }
+        __syncthreads();
+        SSDHOT_NSTAMP(3);
+        const int hot_n = n_hot;
+        if (hot_n > HOT_CAP) fail = 3;
+        else {
+            // ---- one thread per hot row: exact scores (SFS:388), exact threshold test (SFS:402), exact keys ------------------
+            if (tid < hot_n) {
+                const int p = hot[tid];
+                float x[6], e[6];
+                conf_rd.row(p, x);
+                const float sum = row_exps6(x, e);
+                bool low = false;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const float sc = fdiv(e[k + 1], sum);
+                    if (sc > prm.score_thresh) {
+                        const unsigned ek = __float_as_uint(sc) | 0x80000000u;
+                        if (ek >= tkey) {
+                            const int at = atomicAdd(&us.counter, 1);
+                            if (at < CH) buf.ckey[at] = ((unsigned long long)ek << 32) | (unsigned long long)(0xffffffffu - (unsigned)(p * 5 + k));
+                        } else low = true;          // a candidate below the cut: it would belong to a later round
+                    }
+                }
+                if (low) more_low = 1;              // (benign race: every writer stores 1)
+            }
+            __syncthreads();
+            const int K = us.counter;
+            if (K > CH) fail = 3;
+            else if (K == 0) fail = 4;              // (only strays below the cut)
+            else {
+                for (int i = K + tid; i < CH; i += IT) buf.ckey[i] = 0ull;
+                __syncthreads();
+                SSDHOT_NSTAMP(4);
+                const int total_alive = nms_round_backend<SRC>(prm, b, buf, us, loc_rd, K, 0, first);
+                kept_n = min(max_keep, total_alive);
+                __syncthreads();
+                SSDHOT_NSTAMP(9);
+                // candidates outside the round: rows that were not hot, or classes of hot rows below the cut
+                if (kept_n < max_keep && (rows_cand > hot_n || more_low)) fail = 5;
+            }
+        }
     }
-    if (done) return;
-    if (prm.timeline && tid == 0 && hard) prm.timeline[(long long)b * 16 + 15] = 1ull;         // (debug: why this image left the fused mould)
+    if (!fail) {
+        if (tid == 0) {
+            prm.out_count[b] = kept_n;
+            if (prm.timeline) { prm.timeline[(long long)b * 16 + 10] = globaltimer_ns(); unsigned sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); prm.timeline[(long long)b * 16 + 11] = sm; prm.timeline[(long long)b * 16 + 12] = (unsigned long long)rows_cand; }
+        }
+        return;
+    }
+    SSDHOT_FAST_EXIT(fail, kept_n);
     // ---- the generic path, by this CTA alone: global lists, as many rounds as it takes -------------------------------
     __syncthreads();
     score_segment<6, SRC>(prm, b, warp, lane, conf_tab, regions);
@@ -1352,12 +1365,12 @@ __global__ void __launch_bounds__(IT, 2) predict_image_kernel(const PredictParam
     for (int g = tid; g < n_groups; g += IT) buf.ngroup[g] = 0;
     __syncthreads();                               // (the lists and counts this CTA wrote are visible to all its threads)
     SegSource gsrc;
-    gsrc.seg_cap = seg_cap_rows(prm.P) * n_fg;
+    gsrc.seg_cap = seg_cap_rows(P) * n_fg;
     gsrc.base = prm.cand + (long long)b * SEGS * gsrc.seg_cap;
     gsrc.counts = prm.cand_count + b * SEGS;
     const int n_all = block_sum<int>(tid < SEGS ? gsrc.counts[tid] : 0, us.iscratch);
     __syncthreads();
-    nms_image_body<true, SRC, false>(prm, b, buf, us, loc_tab, conf_tab, gsrc, n_all);
+    nms_image_body<true, SRC>(prm, b, buf, us, loc_tab, conf_tab, gsrc, n_all);
 }
 
 // ---- stand-alone NMS -------------------------------------------------------------------------------

@@ -627,7 +627,10 @@ constexpr int FAST_MAX_GT = 64;
 constexpr int GT_ROUND = 32;                 // boxes enumerated per round
 constexpr int NSEG = GT_ROUND * 32;          // (box, level-shape) segments per round
 constexpr int PAIR_CAP = 1536;               // listed gate survivors of an image (rest: settled inline, box recomputed)
-constexpr int MT_LOSS = 512;                 // threads (warps 0..15) that match while the others stream the logits
+#ifndef SSDHOT_MT_LOSS
+#define SSDHOT_MT_LOSS 512
+#endif
+constexpr int MT_LOSS = SSDHOT_MT_LOSS;      // threads (warps 0..15) that match while the others stream the logits
 constexpr int POS_PER_WARP = 80;             // per-warp list of positive priors (rest: handled inline)
 constexpr int SEL_PER_WARP = 168;            // per-warp list of certainly-mined negatives
 constexpr int BAND_CAP = 1024;
@@ -645,9 +648,12 @@ struct FusedStatic {
     // the 30 (level, shape) combinations: grid side, shapes per cell, first prior (level offset + shape), (w, h)
     int cb_side[32], cb_shapes[32], cb_base[32];
     float cb_w[32], cb_h[32], cb_inv[32];      // (w, h) of the shape, 1 / side
+    float cb_hw[32], cb_hh[32];                // fl(0.5 w), fl(0.5 h): the half extents the clamped corners are built from
+    int cb_coff[32];                           // first entry of the level's centres in `centre`
+    float centre[80];                          // (i + 0.5) / side of every level, back to back (38 + 19 + 10 + 5 + 3 + 1 = 76)
     float4 gt_px[FAST_MAX_GT];                // the image's boxes as given (prefetched while the table is cleared)
     LossShared ls;
-    int first_nan, n_dense, n_pair, n_work, n_band, n_sure, pair_overflow, n_pos_img;
+    int first_nan, n_dense, n_pair, n_work, n_seg, n_chunk, n_band, n_sure, pair_overflow, n_pos_img;
     int wcount[FT / 32], wcount2[FT / 32];   // per-warp list lengths: positives, certainly-mined negatives
     unsigned r_bin, r_above;
 };
@@ -755,28 +761,35 @@ __device__ __forceinline__ float clamped_extent(int i, float inv_side, float w) 
 
 // Hull [lo, hi] of the cells whose (clamped) prior interval can satisfy  ov * A >= Bc * extent + Cc,  ov = its
 // overlap with [g1, g2]; empty if hi < lo.  Un-clamped cells have extent w and ov <= min(w, gw, (w + gw)/2 - |c - gc|),
-// which gives a closed-form centre range; the few cells the image border clamps are tested one by one
-// (their extents differ).  Every comparison is slackened, so the hull errs on the inclusive side.
+// which gives a closed-form centre range.  The nb cells the image border clamps on each side have a smaller extent -- at
+// least w/2, their centre lies inside the image -- and an overlap no larger than the un-clamped one, so the same closed
+// form with w/2 in the requirement bounds them; only border cells take that looser range.  Every comparison is
+// slackened, so the hull errs on the inclusive side (a superset costs a few more gate tests, never a match).
 __device__ __forceinline__ void axis_hull(float g1, float g2, int side, float inv_side, float w, float A, float Bc, float Cc, int& lo, int& hi) {
     const float fS = (float)side, gw = g2 - g1, gc = 0.5f * (g1 + g2);
     lo = side;
     hi = -1;
-    const float areq = __fdividef(Bc * w + Cc, A) * 0.9999f;
-    if (fminf(w, gw) >= areq) {
-        const float r = 0.5f * (w + gw) - areq;
+    const float rA = __fdividef(1.0f, A), wmin = fminf(w, gw), half = 0.5f * (w + gw);
+    const float areq = (Bc * w + Cc) * rA * 0.9999f;
+    if (wmin >= areq) {
+        const float r = half - areq;
         const int ia = max(0, (int)ceilf(fmaxf((gc - r) * fS - 0.51f, -1.0f)));
         const int ib = min(side - 1, (int)floorf(fminf((gc + r) * fS - 0.49f, fS)));
         if (ia <= ib) { lo = ia; hi = ib; }
     }
     const int nb = min(side, max(0, (int)ceilf(0.5f * w * fS - 0.49f)));      // cells clamped at each border
-    auto test = [&](int i) {
-        const float c = ((float)i + 0.5f) * inv_side;
-        const float p1 = fmaxf(0.0f, c - 0.5f * w), p2 = fminf(1.0f, c + 0.5f * w);
-        const float ov = fminf(p2, g2) - fmaxf(p1, g1);
-        if (ov > 0.0f && ov * A >= (Bc * (p2 - p1) + Cc) * 0.999f) { lo = min(lo, i); hi = max(hi, i); }
-    };
-    if (g1 < w) for (int i = 0; i < nb; ++i) test(i);
-    if (g2 > 1.0f - w) for (int i = side - nb; i < side; ++i) test(i);
+    const bool left = g1 < w, right = g2 > 1.0f - w;
+    if (nb > 0 && (left || right)) {
+        const float areq2 = (Bc * 0.5f * w + Cc) * rA * 0.999f;
+        if (wmin >= areq2) {
+            const float r = half - areq2;
+            const int ja = max(0, (int)ceilf(fmaxf((gc - r) * fS - 0.51f, -1.0f)));
+            const int jb = min(side - 1, (int)floorf(fminf((gc + r) * fS - 0.49f, fS)));
+            if (left && ja <= min(jb, nb - 1)) { lo = min(lo, ja); hi = max(hi, min(jb, nb - 1)); }
+            if (right && max(ja, side - nb) <= jb) { lo = min(lo, max(ja, side - nb)); hi = max(hi, jb); }
+        }
+    }
+    (void)inv_side;
 }
 
 #define SSDHOT_STAMP(k) do { if (prm.timeline && (threadIdx.x & 31) == 0) { if (threadIdx.x == 0 || (k) == 2) prm.timeline[(long long)blockIdx.x * 16 + (k)] = globaltimer_ns(); } } while (0)
@@ -789,6 +802,21 @@ __device__ __forceinline__ void role_sync() {
     else asm volatile("bar.sync 1, %0;" ::"n"(MT) : "memory");
 }
 
+// Prior (level-shape combination, cell i, j) exactly as the device tables hold it -- clamped corners and the per-prior CIoU
+// constants -- from arithmetic alone, so that matching never waits on the prior tables in L2 under the stream's load.
+// Bit-identical to prior_tables_kernel: the centres of SSD300 are fl32((i + 0.5) / side) computed in float64 (SFS:318-325),
+// which equals the correctly rounded fp32 quotient (2 i + 1) / (2 side) (the double's rounding error, 2^-53, is far below
+// the distance 1 / (2 side 2^25) of a non-dyadic small-integer ratio from any fp32 rounding boundary); the host layout check
+// admits only priors that satisfy this exactly.
+__device__ __forceinline__ BoxC grid_prior(const FusedStatic& fs, int combo, int i, int j, bool want_atan) {
+    const int c0 = fs.cb_coff[combo];
+    const float cx = fs.centre[c0 + i], cy = fs.centre[c0 + j];
+    const float hw = fs.cb_hw[combo], hh = fs.cb_hh[combo];
+    const float x1 = fminf(fmaxf(fsub(cx, hw), 0.f), 1.f), y1 = fminf(fmaxf(fsub(cy, hh), 0.f), 1.f);
+    const float x2 = fminf(fmaxf(fadd(cx, hw), 0.f), 1.f), y2 = fminf(fmaxf(fadd(cy, hh), 0.f), 1.f);
+    return box_consts(x1, y1, x2, y2, want_atan);
+}
+
 // Shared-memory views of the fused kernel.  The table has one 64-bit slot per prior: the HIGH word is the best
 // ord(CIoU) any box reached at that prior (matching, 32-bit atomicMax), the LOW word is written by the logit
 // stream (CE bits of the prior as a negative) and, once a prior is known to be positive, replaced by
@@ -796,11 +824,11 @@ __device__ __forceinline__ void role_sync() {
 struct FusedViews {
     unsigned* lo;              // lo[2p]
     unsigned* hi;              // hi[2p]  (= lo + 1)
-    int* seg_start;            // [NSEG + 1]
-    unsigned* seg_info;        // [NSEG] i0 | j0<<6 | ni<<12 | side<<18 | shapes<<24
-    unsigned* seg_base;        // [NSEG] first prior of the (level, shape) | box << 16
+    uint16_t* seg_n;           // [NSEG] cells of a listed (box, level-shape) rectangle
+    unsigned* seg_info;        // [NSEG] i0 | j0<<6 | ni<<12 | combination<<18 | box<<23
+    uint16_t* chunk_list;      // [2 NSEG] rectangle | (chunk of 32 cells)<<10: the work items of the gate, one warp each
     unsigned* pair_pg;         // [PAIR_CAP] prior | box << 16 : every pair that passed the IoU gate (all rounds)
-    unsigned* pair_ov;         // [PAIR_CAP] ord(CIoU) of that pair
+    unsigned* pair_ov;         // [PAIR_CAP] ord(CIoU) of that pair (until 1d: its grid position, combination | i<<5 | j<<11)
     uint16_t* work_list;       // [NSEG] (box in round) << 5 | level-shape
 };
 
@@ -811,17 +839,55 @@ __device__ __forceinline__ void match_phase(const TrainParams& prm, FusedStatic&
     const int P = prm.P;
     const float thresh = prm.thresh;
     // record a pair whose CIoU may matter: best value per prior (high word), best prior per box, list entry
-    auto settle_pair = [&](int p, int g, int slot) {
-        const float val = pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, p), gt_box(fs.gt_a[g], fs.gt_b[g]));
+    auto settle_box = [&](const BoxC& pr, int p, int g, int slot) {
+        const float val = pair_ciou(pr, gt_box(fs.gt_a[g], fs.gt_b[g]));
         const unsigned o = ord_encode(val);
         atomicMax(&v.hi[2 * p], o);
         const unsigned long long ck = ((unsigned long long)o << 32) | (unsigned long long)(0xffffffffu - (unsigned)p);
         if (ck > *reinterpret_cast<volatile unsigned long long*>(&fs.col[g])) atomicMax(&fs.col[g], ck);
         if (slot < PAIR_CAP) v.pair_ov[slot] = o;
     };
+    // cell t of listed rectangle sg: the IoU gate; a survivor joins the pair list with its grid position.  Called by a whole
+    // warp (lane = cell of a chunk; `solo` = false) or by a single thread working off an overfull chunk list (`solo`).
+    auto gate_cell = [&](int sg, int t, bool solo) {
+        const unsigned info = v.seg_info[sg];
+        const int n = (int)v.seg_n[sg];
+        const int i0 = (int)(info & 63u), j0 = (int)((info >> 6) & 63u), ni = (int)((info >> 12) & 63u);
+        const int combo = (int)((info >> 18) & 31u), g = (int)(info >> 23);
+        bool pass = false;
+        int p = 0, i = 0, j = 0;
+        if (t < n) {
+            const int lj = (int)(((float)t + 0.5f) * __fdividef(1.0f, (float)ni));      // t / ni  (t < 4096, ni < 64: exact)
+            i = i0 + t - lj * ni;
+            j = j0 + lj;
+            p = fs.cb_base[combo] + (j * fs.cb_side[combo] + i) * fs.cb_shapes[combo];
+            const BoxC pr = grid_prior(fs, combo, i, j, false);
+            const float4 ga = fs.gt_a[g];
+            const float w = fmaxf(fsub(fminf(pr.x2, ga.z), fmaxf(pr.x1, ga.x)), 0.0f);
+            const float h = fmaxf(fsub(fminf(pr.y2, ga.w), fmaxf(pr.y1, ga.y)), 0.0f);
+            const float inter = fmul(w, h);
+            const float uni = fsub(fadd(pr.area, fs.gt_b[g].x), inter);
+            pass = !(inter < fmul(fs.lim[g], uni));      // NaN-safe: anything odd takes the exact path
+        }
+        int dst = 0;
+        if (solo) {
+            if (!pass) return;
+            dst = atomicAdd(&fs.n_pair, 1);
+        } else {
+            const unsigned bal = __ballot_sync(FULL, pass);
+            if (!bal) return;
+            if (lane == 0) dst = atomicAdd(&fs.n_pair, __popc(bal));
+            dst = __shfl_sync(FULL, dst, 0) + __popc(bal & ((1u << lane) - 1u));
+            if (!pass) return;
+        }
+        if (dst < PAIR_CAP) {
+            v.pair_pg[dst] = (unsigned)p | ((unsigned)g << 16);
+            v.pair_ov[dst] = (unsigned)combo | ((unsigned)i << 5) | ((unsigned)j << 11);
+        } else { settle_box(grid_prior(fs, combo, i, j, true), p, g, dst); fs.pair_overflow = 1; }   // unlisted: its box is recovered by recomputation
+    };
     for (int g0 = 0; g0 < G; g0 += GT_ROUND) {
         const int gn = min(GT_ROUND, G - g0);
-        if (mtid == 0) fs.n_work = 0;
+        if (mtid == 0) { fs.n_work = 0; fs.n_seg = 0; fs.n_chunk = 0; }
         const int round_begin = min(fs.n_pair, PAIR_CAP);       // (stable: the previous round ended with a barrier)
         role_sync<MT>();
         // 1a. half a warp per box: constants, seed bound (two of the 30 seed priors per lane), and the
@@ -842,13 +908,12 @@ __device__ __forceinline__ void match_phase(const TrainParams& prm, FusedStatic&
             if (kind == 0) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int combo = (lane & 15) + 16 * h;  // 30, 31 repeat 0, 1 as seeds
-                    const int side = fs.cb_side[combo], shapes = fs.cb_shapes[combo];
+                    const int combo = (lane & 15) + 16 * h;  // 30, 31 repeat 0, 4 as seeds
+                    const int side = fs.cb_side[combo];
                     int ix = (int)floorf(c.xc * (float)side), iy = (int)floorf(c.yc * (float)side);
                     ix = min(max(ix, 0), side - 1);
                     iy = min(max(iy, 0), side - 1);
-                    const int ps = fs.cb_base[combo] + (iy * side + ix) * shapes;
-                    best = max(best, ord_encode(pair_ciou(load_prior(prm.pri_xyxy, prm.pri_aux, ps), c)));
+                    best = max(best, ord_encode(pair_ciou(grid_prior(fs, combo, ix, iy, true), c)));
                 }
             }
             // (the two halves of a warp hold different boxes: the shuffles below must run in every lane)
@@ -887,114 +952,52 @@ __device__ __forceinline__ void match_phase(const TrainParams& prm, FusedStatic&
         }
         role_sync<MT>();
         SSDHOT_STAMP(11);
-        // 1a'. one thread per surviving (box, level-shape): its rectangle of candidate cells
+        // 1a'. one thread per surviving (box, level-shape): its rectangle of candidate cells; the non-empty ones are listed
         {
             const int n_work = fs.n_work;
-            for (int e = mtid; e < NSEG; e += MT) {
-                int n = 0;
-                unsigned info = 0u, base = 0u;
-                if (e < n_work) {
-                    const int wk = (int)v.work_list[e], g = g0 + (wk >> 5), combo = wk & 31;
-                    const int side = fs.cb_side[combo], shapes = fs.cb_shapes[combo];
-                    const float w = fs.cb_w[combo], h = fs.cb_h[combo], l2 = 0.99f * fs.lim[g];
-                    const float inv_side = fs.cb_inv[combo];
-                    const float4 ga = fs.gt_a[g];
-                    const float gw = ga.z - ga.x, gh = ga.w - ga.y, ag = fs.gt_b[g].x;
-                    // rows whose 1-D IoU with the box can reach lim (2-D IoU <= each 1-D IoU) ...
-                    int j0, j1, i0, i1, a0, a1;
-                    axis_hull(ga.y, ga.w, side, inv_side, h, 1.0f + l2, l2, l2 * gh, j0, j1);
-                    if (j1 >= j0) {
-                        // ... then columns / rows that can satisfy inter (1 + lim) >= lim (a_p + a_g) given the best
-                        // overlap and the smallest clamped extent the other axis offers
-                        const float hcmin = fminf(clamped_extent(j0, inv_side, h), clamped_extent(j1, inv_side, h));
-                        axis_hull(ga.x, ga.z, side, inv_side, w, fminf(h, gh) * (1.0f + l2), l2 * hcmin, l2 * ag, i0, i1);
-                        if (i1 >= i0) {
-                            const float wcmin = fminf(clamped_extent(i0, inv_side, w), clamped_extent(i1, inv_side, w));
-                            axis_hull(ga.y, ga.w, side, inv_side, h, fminf(w, gw) * (1.0f + l2), l2 * wcmin, l2 * ag, a0, a1);
-                            j0 = max(j0, a0);
-                            j1 = min(j1, a1);
-                            if (j1 >= j0) {
-                                const int ni = i1 - i0 + 1;
-                                n = ni * (j1 - j0 + 1);
-                                info = (unsigned)i0 | ((unsigned)j0 << 6) | ((unsigned)ni << 12) | ((unsigned)side << 18) | ((unsigned)shapes << 24);
-                                base = (unsigned)fs.cb_base[combo] | ((unsigned)g << 16);
-                            }
-                        }
-                    }
+            for (int e = mtid; e < n_work; e += MT) {
+                const int wk = (int)v.work_list[e], g = g0 + (wk >> 5), combo = wk & 31;
+                const int side = fs.cb_side[combo];
+                const float w = fs.cb_w[combo], h = fs.cb_h[combo], l2 = 0.99f * fs.lim[g];
+                const float inv_side = fs.cb_inv[combo];
+                const float4 ga = fs.gt_a[g];
+                const float gw = ga.z - ga.x, gh = ga.w - ga.y, ag = fs.gt_b[g].x;
+                // rows whose 1-D IoU with the box can reach lim (2-D IoU <= each 1-D IoU) ...
+                int j0, j1, i0, i1, a0, a1;
+                axis_hull(ga.y, ga.w, side, inv_side, h, 1.0f + l2, l2, l2 * gh, j0, j1);
+                if (j1 < j0) continue;
+                // ... then columns / rows that can satisfy inter (1 + lim) >= lim (a_p + a_g) given the best
+                // overlap and the smallest clamped extent the other axis offers
+                const float hcmin = fminf(clamped_extent(j0, inv_side, h), clamped_extent(j1, inv_side, h));
+                axis_hull(ga.x, ga.z, side, inv_side, w, fminf(h, gh) * (1.0f + l2), l2 * hcmin, l2 * ag, i0, i1);
+                if (i1 < i0) continue;
+                const float wcmin = fminf(clamped_extent(i0, inv_side, w), clamped_extent(i1, inv_side, w));
+                axis_hull(ga.y, ga.w, side, inv_side, h, fminf(w, gw) * (1.0f + l2), l2 * wcmin, l2 * ag, a0, a1);
+                j0 = max(j0, a0);
+                j1 = min(j1, a1);
+                if (j1 < j0) continue;
+                const int ni = i1 - i0 + 1, n = ni * (j1 - j0 + 1);
+                const int at = atomicAdd(&fs.n_seg, 1);           // (n_work <= NSEG)
+                v.seg_n[at] = (uint16_t)n;
+                v.seg_info[at] = (unsigned)i0 | ((unsigned)j0 << 6) | ((unsigned)ni << 12) | ((unsigned)combo << 18) | ((unsigned)g << 23);
+                // the rectangle's cells in chunks of 32: the gate's work items (a full list leaves the rest to this thread)
+                const int nc = (n + 31) >> 5;
+                const int c0 = atomicAdd(&fs.n_chunk, nc);
+                for (int c = 0; c < nc; ++c) {
+                    if (c0 + c < 2 * NSEG) v.chunk_list[c0 + c] = (uint16_t)(at | (c << 10));
+                    else for (int t = 32 * c; t < min(n, 32 * c + 32); ++t) gate_cell(at, t, true);
                 }
-                v.seg_start[e] = n;
-                v.seg_info[e] = info;
-                v.seg_base[e] = base;
             }
         }
         role_sync<MT>();
-        // 1b. exclusive scan of the NSEG segment sizes (EPT consecutive entries per thread)
-        {
-            constexpr int EPT = (NSEG + MT - 1) / MT;
-            int cnt[EPT], sum = 0;
-#pragma unroll
-            for (int k = 0; k < EPT; ++k) {
-                const int e = mtid * EPT + k;
-                cnt[k] = e < NSEG ? v.seg_start[e] : 0;
-                sum += cnt[k];
-            }
-            int incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += y;
-            }
-            if (lane == 31) fs.ls.iscratch[mwarp] = incl;
-            role_sync<MT>();
-            int run = incl - sum;
-            for (int w = 0; w < mwarp; ++w) run += fs.ls.iscratch[w];
-#pragma unroll
-            for (int k = 0; k < EPT; ++k) {
-                const int e = mtid * EPT + k;
-                if (e < NSEG) v.seg_start[e] = run;
-                run += cnt[k];
-            }
-            if (mtid == MT - 1) v.seg_start[NSEG] = run;        // (the last thread's range ends at or beyond NSEG)
-            role_sync<MT>();
-        }
         SSDHOT_STAMP(12);
-        // 1c. every candidate cell: cheap IoU gate; survivors join the pair list
-        const int T = v.seg_start[NSEG];
-        for (int t0 = 0; t0 < T; t0 += MT) {
-            const int t = t0 + mtid;
-            bool pass = false;
-            int p = 0, g = 0;
-            if (t < T) {
-                int lo = 0, hi = NSEG;                       // seg_start[lo] <= t < seg_start[hi]
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (v.seg_start[mid] <= t) lo = mid; else hi = mid;
-                }
-                const unsigned info = v.seg_info[lo];
-                const int local = t - v.seg_start[lo];
-                const int ni = (int)((info >> 12) & 63u), side = (int)((info >> 18) & 63u), shapes = (int)(info >> 24);
-                const int lj = local / ni, li = local - lj * ni;
-                const unsigned sb = v.seg_base[lo];
-                p = (int)(sb & 0xffffu) + (((int)((info >> 6) & 63u) + lj) * side + (int)(info & 63u) + li) * shapes;
-                g = (int)(sb >> 16);
-                const float4 pb = ldg4(prm.pri_xyxy + 4ll * p);
-                const float pa = __ldg(prm.pri_aux + 4ll * p);
-                const float4 ga = fs.gt_a[g];
-                const float w = fmaxf(fsub(fminf(pb.z, ga.z), fmaxf(pb.x, ga.x)), 0.0f);
-                const float h = fmaxf(fsub(fminf(pb.w, ga.w), fmaxf(pb.y, ga.y)), 0.0f);
-                const float inter = fmul(w, h);
-                const float uni = fsub(fadd(pa, fs.gt_b[g].x), inter);
-                pass = !(inter < fmul(fs.lim[g], uni));      // NaN-safe: anything odd takes the exact path
-            }
-            const unsigned bal = __ballot_sync(FULL, pass);
-            if (bal) {
-                int dst = 0;
-                if (lane == 0) dst = atomicAdd(&fs.n_pair, __popc(bal));
-                dst = __shfl_sync(FULL, dst, 0) + __popc(bal & ((1u << lane) - 1u));
-                if (pass) {
-                    if (dst < PAIR_CAP) v.pair_pg[dst] = (unsigned)p | ((unsigned)g << 16);
-                    else { settle_pair(p, g, dst); fs.pair_overflow = 1; }   // unlisted: its box is recovered by recomputation
-                }
+        // 1c. one warp per chunk of 32 cells: the cheap IoU gate, the prior built from its grid position; survivors join
+        //     the pair list with that position
+        {
+            const int n_chunk = min(fs.n_chunk, 2 * NSEG);
+            for (int c = mwarp; c < n_chunk; c += MT / 32) {
+                const int e = (int)v.chunk_list[c];
+                gate_cell(e & 1023, 32 * (e >> 10) + lane, false);
             }
         }
         role_sync<MT>();
@@ -1003,8 +1006,8 @@ __device__ __forceinline__ void match_phase(const TrainParams& prm, FusedStatic&
         {
             const int round_end = min(fs.n_pair, PAIR_CAP);
             for (int e = round_begin + mtid; e < round_end; e += MT) {
-                const unsigned pr = v.pair_pg[e];
-                settle_pair((int)(pr & 0xffffu), (int)(pr >> 16), e);
+                const unsigned pr = v.pair_pg[e], at = v.pair_ov[e];
+                settle_box(grid_prior(fs, (int)(at & 31u), (int)((at >> 5) & 63u), (int)((at >> 11) & 63u), true), (int)(pr & 0xffffu), (int)(pr >> 16), e);
             }
         }
         role_sync<MT>();
@@ -1082,9 +1085,9 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     FusedViews v;
     v.lo = reinterpret_cast<unsigned*>(table);
     v.hi = v.lo + 1;
-    v.seg_start = reinterpret_cast<int*>(scratch);
+    v.seg_n = reinterpret_cast<uint16_t*>(scratch);
     v.seg_info = reinterpret_cast<unsigned*>(scratch + 4112);
-    v.seg_base = reinterpret_cast<unsigned*>(scratch + 4112 + 4096);
+    v.chunk_list = reinterpret_cast<uint16_t*>(scratch + 4112 + 4096);
     v.pair_pg = reinterpret_cast<unsigned*>(scratch + 4112 + 8192);
     v.pair_ov = v.pair_pg + PAIR_CAP;
     v.work_list = reinterpret_cast<uint16_t*>(v.pair_ov + PAIR_CAP);
@@ -1118,6 +1121,14 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
         const float4 sh = ldg4(prm.pri + 4ll * base);       // (w, h) of this level-shape: the same in every cell (checked on the host)
         fs.cb_side[tid] = kLevelSide[lv]; fs.cb_shapes[tid] = kLevelShapes[lv]; fs.cb_base[tid] = base;
         fs.cb_w[tid] = sh.z; fs.cb_h[tid] = sh.w; fs.cb_inv[tid] = 1.0f / (float)kLevelSide[lv];
+        fs.cb_hw[tid] = fmul(0.5f, sh.z); fs.cb_hh[tid] = fmul(0.5f, sh.w);
+        fs.cb_coff[tid] = lv == 0 ? 0 : lv == 1 ? 38 : lv == 2 ? 57 : lv == 3 ? 67 : lv == 4 ? 72 : 75;
+    }
+    if (tid >= 128 && tid < 128 + 76) {                     // the centres of the six grids: fl32((2 i + 1) / (2 side))
+        const int e = tid - 128;
+        const int lv = (e >= 38) + (e >= 57) + (e >= 67) + (e >= 72) + (e >= 75);
+        const int first = lv == 0 ? 0 : lv == 1 ? 38 : lv == 2 ? 57 : lv == 3 ? 67 : lv == 4 ? 72 : 75;
+        fs.centre[e] = fdiv((float)(2 * (e - first) + 1), (float)(2 * kLevelSide[lv]));
     }
     {
         ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
@@ -1717,7 +1728,7 @@ using namespace ssdhot;
 
 // Host-side check that `priors` (HOST memory) have the SSD300 structure train_image_kernel relies on:
 // levels of 38/19/10/5/3/1 cells with 4/6/6/6/4/4 shapes, cells row-major, shapes innermost
-// (SSD_from_scratch.py:289-323); centres (i + 0.5)/side within 1e-5; one (w, h) in (0, 1] per (level, shape).
+// (SSD_from_scratch.py:289-323); centres exactly fl32((i + 0.5)/side); one (w, h) in (0, 1] per (level, shape).
 extern "C" int ssdhot_ssd300_layout_host(const float* priors_cxcywh_host, int P) {
     if (!priors_cxcywh_host || P != 8732) return 0;
     static const int side[6] = {38, 19, 10, 5, 3, 1}, shapes[6] = {4, 6, 6, 6, 4, 4};
@@ -1728,8 +1739,9 @@ extern "C" int ssdhot_ssd300_layout_host(const float* priors_cxcywh_host, int P)
                 for (int k = 0; k < shapes[l]; ++k) {
                     const float* q = priors_cxcywh_host + 4ll * (off + (j * side[l] + i) * shapes[l] + k);
                     const float* q0 = priors_cxcywh_host + 4ll * (off + k);
-                    const float cx = (float)((i + 0.5) / side[l]), cy = (float)((j + 0.5) / side[l]);
-                    if (!(q[0] - cx <= 1e-5f && cx - q[0] <= 1e-5f && q[1] - cy <= 1e-5f && cy - q[1] <= 1e-5f)) return 0;
+                    // exactly the fp32 quotient the kernel rebuilds the priors from (grid_prior); SFS:318-325 satisfies it
+                    const float cx = (float)(2 * i + 1) / (float)(2 * side[l]), cy = (float)(2 * j + 1) / (float)(2 * side[l]);
+                    if (!(q[0] == cx && q[1] == cy)) return 0;
                     if (!(q[2] == q0[2] && q[3] == q0[3] && q[2] > 0.0f && q[2] <= 1.0f && q[3] > 0.0f && q[3] <= 1.0f)) return 0;
                 }
         off += side[l] * side[l] * shapes[l];

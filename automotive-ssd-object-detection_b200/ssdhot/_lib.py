@@ -8,7 +8,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libssdhot.so")
+LIB_PATH = os.environ.get("SSDHOT_LIB_PATH") or os.path.join(_HERE, "lib", "libssdhot.so")     # (the override serves A/B builds of the kernels)
 ABI_VERSION = 2
 
 _lock = threading.Lock()

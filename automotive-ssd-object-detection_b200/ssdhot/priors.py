@@ -63,6 +63,14 @@ class PriorSet:
                 self.priors_xyxy = priors_xyxy.detach().to(torch.float32).contiguous()
                 _lib.check(_lib.lib().ssdhot_prior_aux(self.priors_xyxy.data_ptr(), self.P, self.aux.data_ptr(), stream),
                            "ssdhot_prior_aux")
+                if self.layout:
+                    # the SSD300 fast path rebuilds the clamped corners from the grid position (train_path.cu: grid_prior);
+                    # corners that are not box_convert(priors).clamp(0, 1) (SFS:34) keep the table-driven kernels
+                    own = torch.empty_like(self.priors)
+                    _lib.check(_lib.lib().ssdhot_prior_tables(self.priors.data_ptr(), self.P, own.data_ptr(), None, stream),
+                               "ssdhot_prior_tables")
+                    if not torch.equal(own, self.priors_xyxy):
+                        self.layout = 0
 
     @property
     def device(self) -> torch.device:

@@ -21,6 +21,10 @@ if source != "packed":
 else:
     launch = lambda: step.launch_loss(loc, ct, gt, st)
 for _ in range(3): launch()
+COLD = os.environ.get("COLD")            # COLD=1: evict the inputs from L2 (as bench.py's rotating sets do) before the stamped launch
+if COLD:
+    junk = torch.empty((512 << 20,), dtype=torch.uint8, device=dev); junk.fill_(1); junk.fill_(2); torch.cuda.synchronize()
+    print("cold L2")
 tl = torch.zeros((batch, 16), dtype=torch.int64, device=dev)
 ssdhot.lib().ssdhot_debug_timeline(tl.data_ptr())
 launch()

@@ -14,6 +14,10 @@ loc, ci = cfg["loc_all"].to(dev), cfg["conf_infer"].to(dev)
 step = HotPathStep(ps, batch, 6, cfg["iou_thresh"], cfg["ratio"], cfg["score_thresh"], cfg["nms_thresh"], cfg["max_per_img"])
 st = torch.cuda.current_stream(dev).cuda_stream
 for _ in range(3): step.launch_predict(loc, ci, st)
+COLD = os.environ.get("COLD")            # COLD=1: evict the inputs from L2 (as bench.py's rotating sets do) before the stamped launch
+if COLD:
+    junk = torch.empty((512 << 20,), dtype=torch.uint8, device=dev); junk.fill_(1); junk.fill_(2); torch.cuda.synchronize()
+    print("cold L2")
 tl = torch.zeros((batch, 16), dtype=torch.int64, device=dev)
 ssdhot.lib().ssdhot_debug_timeline(tl.data_ptr())
 step.launch_predict(loc, ci, st)
