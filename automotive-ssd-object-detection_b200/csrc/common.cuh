@@ -43,6 +43,11 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(FULL, v); }
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
 
 // Block-wide sums in a fixed (deterministic) order.  `scratch` holds >= 32 elements; the result
 // is returned to every thread.  Contains two __syncthreads().

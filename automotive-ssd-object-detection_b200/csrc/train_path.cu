@@ -631,8 +631,8 @@ constexpr int PAIR_CAP = 1536;               // listed gate survivors of an imag
 #define SSDHOT_MT_LOSS 512
 #endif
 constexpr int MT_LOSS = SSDHOT_MT_LOSS;      // threads (warps 0..15) that match while the others stream the logits
-constexpr int POS_PER_WARP = 80;             // per-warp list of positive priors (rest: handled inline)
-constexpr int SEL_PER_WARP = 168;            // per-warp list of certainly-mined negatives
+constexpr int POS_CAP = 2048;                // listed positive priors of an image (more: the exact tail walks the slots)
+constexpr int SEL_CAP = 4096;                // listed certainly-mined negatives
 constexpr int BAND_CAP = 1024;
 constexpr unsigned kOrdTwo = 0xC0000000u;    // ord_encode(2.0f): the forced-match value (SFS:747)
 constexpr int FUSED_SCRATCH = 4112 + 8192 + 8 * PAIR_CAP + 2 * NSEG;     // 26640: matching view; the mining lists reuse it
@@ -654,7 +654,8 @@ struct FusedStatic {
     float4 gt_px[FAST_MAX_GT];                // the image's boxes as given (prefetched while the table is cleared)
     LossShared ls;
     int first_nan, n_dense, n_pair, n_work, n_seg, n_chunk, n_band, n_sure, pair_overflow, n_pos_img;
-    int wcount[FT / 32], wcount2[FT / 32];   // per-warp list lengths: positives, certainly-mined negatives
+    int n_pos_listed, n_sel;                 // listed positives (claim), listed certainly-mined negatives (scan)
+    double fin_odd[2][FT / 32];              // the final exchange's double parts
     unsigned r_bin, r_above;
 };
 
@@ -1092,11 +1093,13 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     v.pair_ov = v.pair_pg + PAIR_CAP;
     v.work_list = reinterpret_cast<uint16_t*>(v.pair_ov + PAIR_CAP);
     // after the matching the scratch holds the lists of the mining
-    uint16_t* pos_list = reinterpret_cast<uint16_t*>(scratch);                     // [FT/32][POS_PER_WARP]
-    uint16_t* sel_list = pos_list + (FT / 32) * POS_PER_WARP;                      // [FT/32][SEL_PER_WARP]
-    unsigned* band_v = reinterpret_cast<unsigned*>(sel_list + (FT / 32) * SEL_PER_WARP);   // [BAND_CAP] exact CE bits
+    // the positives are listed while the pair list is still being read: their list sits in the rectangle / chunk region
+    uint16_t* pos_list = reinterpret_cast<uint16_t*>(scratch);                     // [POS_CAP]   (4096 B of the first 12304)
+    uint16_t* sel_list = pos_list + POS_CAP;                                       // [SEL_CAP]   (filled after the pair list is dead)
+    unsigned* band_v = reinterpret_cast<unsigned*>(scratch + 4112 + 8192);         // [BAND_CAP] exact CE bits
     unsigned* band_sorted = band_v + BAND_CAP;                                     // [BAND_CAP] the band's winners by rank
     uint16_t* band_p = reinterpret_cast<uint16_t*>(band_sorted + BAND_CAP);        // [BAND_CAP]
+    static_assert(2 * (POS_CAP + SEL_CAP) <= 4112 + 8192 && 4112 + 8192 + 10 * BAND_CAP <= FUSED_SCRATCH, "mining lists fit the scratch");
 
     const int g_begin = prm.gt_offsets[b];
     int G = prm.gt_offsets[b + 1] - g_begin;
@@ -1111,7 +1114,7 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
         head_table_fill<SRC, 6>(conf_tab, prm.conf_h, b, tid - 96);
         if (SRC == SRC_LEVEL_PLANES) plane_regions_fill(regions, prm.conf_h, b, tid - 128);
     }
-    if (tid == 0) { fs.first_nan = INT_MAX; fs.n_dense = 0; fs.n_band = 0; fs.n_pair = 0; fs.pair_overflow = 0; fs.n_pos_img = 0; fs.n_sure = 0; }
+    if (tid == 0) { fs.first_nan = INT_MAX; fs.n_dense = 0; fs.n_band = 0; fs.n_pair = 0; fs.pair_overflow = 0; fs.n_pos_img = 0; fs.n_sure = 0; fs.n_pos_listed = 0; fs.n_sel = 0; }
     if (tid >= 32 && tid < 32 + G) {
         fs.gt_px[tid - 32] = ldg4(prm.gt_boxes + 4ll * (g_begin + tid - 32));
         fs.label[tid - 32] = (int)prm.gt_labels[g_begin + tid - 32];
@@ -1199,8 +1202,9 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     auto claim = [&](int p, int g) {
         const unsigned old = atomicMax(&v.lo[2 * p], 0x80000000u | (unsigned)(63 - g));
         if (!(old >> 31)) {
-            atomicAdd(&fs.n_pos_img, 1);
+            const int at = atomicAdd(&fs.n_pos_img, 1);
             if (LOSS) {
+                if (at < POS_CAP) pos_list[at] = (uint16_t)p;      // the positives are listed here, not found again by a scan
                 const int bin = ce_bin(old);
                 atomicSub(&hist16[bin >> 1], 1u << ((bin & 1) * 16));
             }
@@ -1278,15 +1282,22 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     }
 
     SSDHOT_STAMP(6);
-    // ---- 4. one scan of the slots (the scratch changes role): positives and certainly-mined negatives go to
-    //         per-warp lists in prior order, the few negatives inside the error band to one short list.
-    //         The lists are consumed in the canonical concatenation order, so every thread adds the same
-    //         terms in the same order on every run.
-    double acc_loc = 0.0, acc_ce = 0.0;
+    // ---- 4. one scan of the slots: the certainly-mined negatives and the few negatives inside the error band are listed (in
+    //         whatever order the threads arrive; the positives were listed by the claims).  The loss terms are summed as
+    //         64-bit fixed point, so the sums do not depend on that order: the same bits on every run and for every split of
+    //         the batch.  Terms the fixed point cannot hold (>= 2^14, Inf, NaN) go to a double beside it.
+    // Two fixed-point accumulators per sum: terms below 1 at 2^-48 (exact down to 2^-25; at most 8732 of them: < 2^62),
+    // terms in [1, 2^14) at 2^-34 (exact: their ulp is >= 2^-23).  What neither holds (>= 2^14, Inf, NaN) goes to a double.
+    struct Fx { long long small, big; double odd; };
+    Fx fx_loc = {0, 0, 0.0}, fx_ce = {0, 0, 0.0};
+    auto fx_add = [](Fx& a, float term) {
+        if (term < 1.0f) a.small += __float2ll_rn(term * 281474976710656.0f);          // 2^48 (a power of two: the product is exact)
+        else if (term < 16384.0f) a.big += __float2ll_rn(term * 17179869184.0f);       // 2^34
+        else a.odd += (double)term;                                                    // (NaN fails both comparisons)
+    };
     // a positive prior: exact CE of its class, smooth-L1 of its offsets (TR:108, :577-580)
-    auto positive_terms = [&](int p, int g) {
-        const long long row = (long long)b * P + p;
-        acc_ce += (double)exact_ce6(conf_rd, p, fs.label[g] + 1);
+    auto positive_terms = [&](int p, int g, bool with_ce) {
+        if (with_ce) fx_add(fx_ce, exact_ce6(conf_rd, p, fs.label[g] + 1));
         const float4 ga = fs.gt_a[g], gb = fs.gt_b[g];
         const float4 gbox = make_float4(gb.y, gb.z, fsub(ga.z, ga.x), fsub(ga.w, ga.y));
         const float4 t = encode_offsets(gbox, ldg4(prm.pri + 4ll * p), prm.inv_vc, prm.inv_vs);
@@ -1296,98 +1307,54 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float z = fabsf(d[j]);
-            acc_loc += (double)(z < 1.0f ? fmul(fmul(0.5f, z), z) : fsub(z, 0.5f));
+            fx_add(fx_loc, z < 1.0f ? fmul(fmul(0.5f, z), z) : fsub(z, 0.5f));
         }
     };
-    auto mined_term = [&](int p) {
-        acc_ce += (double)exact_ce6(conf_rd, p, 0);
-        if (prm.sel_cls) prm.sel_cls[(long long)b * P + p] = 0;
-    };
-    const unsigned lt = (1u << lane) - 1u;
+    const bool pos_listed = n_pos_img <= POS_CAP;
+    if (!pos_listed) { exact_all = true; fast = false; }               // (more positives than the list holds: the exact tail walks the slots)
     {
-        uint16_t* my_pos = pos_list + warp * POS_PER_WARP;
-        uint16_t* my_sel = sel_list + warp * SEL_PER_WARP;
         const ulonglong2* t2 = reinterpret_cast<const ulonglong2*>(table);
-        int wpos = 0, wsel = 0;                          // warp-uniform
-        for (int base = warp * 64; base < P; base += 2 * FT) {          // two adjacent slots per lane (P is even here)
-            const int p = base + 2 * lane;
-            unsigned lo[2] = {0u, 0u};
-            if (p < P) { const ulonglong2 sl = t2[p >> 1]; lo[0] = (unsigned)sl.x; lo[1] = (unsigned)sl.y; }
-            bool pos[2], sure[2], band[2];
+        for (int q = tid; q < P / 2; q += FT) {                      // two adjacent slots per thread and trip (P is even here)
+            const ulonglong2 sl = t2[q];
+            const unsigned lo[2] = {(unsigned)sl.x, (unsigned)sl.y};
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                pos[h] = (lo[h] >> 31) != 0u;
-                const bool cand = !pos[h] && lo[h] >= band_lo_key;   // (p >= P: lo = 0 is below any band key; fast path off:
-                sure[h] = cand && lo[h] > band_hi_key && fast;       //  the keys are 0xffffffff and nothing qualifies)
-                band[h] = cand && !sure[h] && fast;
-            }
-            if (prm.sel_cls && p < P) {
-                const long long row = (long long)b * P + p;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    prm.sel_cls[row + h] = pos[h] ? (int8_t)(fs.label[matched_box(lo[h])] + 1) : (int8_t)-1;
-                    if (prm.matched16) prm.matched16[row + h] = pos[h] ? (int16_t)matched_box(lo[h]) : (int16_t)-1;
+                const int p = 2 * q + h;
+                const bool pos = (lo[h] >> 31) != 0u;
+                if (prm.sel_cls) {
+                    const long long row = (long long)b * P + p;
+                    prm.sel_cls[row] = pos ? (int8_t)(fs.label[matched_box(lo[h])] + 1) : (int8_t)-1;
+                    if (prm.matched16) prm.matched16[row] = pos ? (int16_t)matched_box(lo[h]) : (int16_t)-1;
                 }
-            }
-            if (__any_sync(FULL, pos[0] || pos[1] || sure[0] || sure[1] || band[0] || band[1])) {
-                const unsigned bp0 = __ballot_sync(FULL, pos[0]), bp1 = __ballot_sync(FULL, pos[1]);
-                const unsigned bs0 = __ballot_sync(FULL, sure[0]), bs1 = __ballot_sync(FULL, sure[1]);
-                int at = wpos + __popc(bp0 & lt) + __popc(bp1 & lt);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (pos[h]) {
-                        if (at < POS_PER_WARP) my_pos[at] = (uint16_t)(p + h);
-                        else positive_terms(p + h, matched_box(lo[h]));
-                        ++at;
+                if (fast && !pos && lo[h] >= band_lo_key) {          // (fast path off: nothing qualifies)
+                    if (lo[h] > band_hi_key) {
+                        const int at = atomicAdd(&fs.n_sel, 1);
+                        if (at < SEL_CAP) sel_list[at] = (uint16_t)p;
+                    } else {
+                        const int at = atomicAdd(&fs.n_band, 1);
+                        if (at < BAND_CAP) band_p[at] = (uint16_t)p;
                     }
                 }
-                at = wsel + __popc(bs0 & lt) + __popc(bs1 & lt);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (sure[h]) {
-                        if (at < SEL_PER_WARP) my_sel[at] = (uint16_t)(p + h);
-                        else mined_term(p + h);
-                        ++at;
-                    }
-                    if (band[h]) {
-                        const int dst = atomicAdd(&fs.n_band, 1);
-                        if (dst < BAND_CAP) band_p[dst] = (uint16_t)(p + h);
-                    }
-                }
-                wpos += __popc(bp0) + __popc(bp1);
-                wsel += __popc(bs0) + __popc(bs1);
             }
-        }
-        if (lane == 0) {
-            fs.wcount[warp] = min(wpos, POS_PER_WARP);
-            fs.wcount2[warp] = min(wsel, SEL_PER_WARP);
-            atomicAdd(&fs.n_sure, wsel);
         }
     }
     __syncthreads();
     SSDHOT_STAMP(7);
     {
-        const int n_sure = fs.n_sure, n_band = fs.n_band;
-        if (fast && n_band > BAND_CAP) { exact_all = true; fast = false; }   // (massive ties): CTA-uniform
+        const int n_sure = fs.n_sel, n_band = fs.n_band;
+        if (fast && (n_band > BAND_CAP || n_sure > SEL_CAP)) { exact_all = true; fast = false; }   // (massive ties): CTA-uniform
         // one pass over the three lists: positives | certain negatives | band members
-        const int tot_pos = __reduce_add_sync(FULL, lane < FT / 32 ? fs.wcount[lane] : 0);
-        const int tot_sel = fast ? __reduce_add_sync(FULL, lane < FT / 32 ? fs.wcount2[lane] : 0) : 0;
+        const int tot_pos = pos_listed ? n_pos_img : 0;
+        const int tot_sel = fast ? n_sure : 0;
         const int tot_band = fast ? n_band : 0;
         for (int e = tid; e < tot_pos + tot_sel + tot_band; e += FT) {
-            if (e < tot_pos + tot_sel) {
-                const bool is_pos = e < tot_pos;
-                const int* wc = is_pos ? fs.wcount : fs.wcount2;
-                const uint16_t* lists = is_pos ? pos_list : sel_list;
-                const int per_warp = is_pos ? POS_PER_WARP : SEL_PER_WARP;
-                int run = 0, p = -1;
-                const int ee = is_pos ? e : e - tot_pos;
-                for (int w = 0; w < FT / 32; ++w) {
-                    const int c = wc[w];
-                    if (ee < run + c) { p = (int)lists[w * per_warp + (ee - run)]; break; }
-                    run += c;
-                }
-                if (is_pos) positive_terms(p, matched_box(v.lo[2 * p]));
-                else mined_term(p);
+            if (e < tot_pos) {
+                const int p = (int)pos_list[e];
+                positive_terms(p, matched_box(v.lo[2 * p]), true);
+            } else if (e < tot_pos + tot_sel) {
+                const int p = (int)sel_list[e - tot_pos];
+                fx_add(fx_ce, exact_ce6(conf_rd, p, 0));
+                if (prm.sel_cls) prm.sel_cls[(long long)b * P + p] = 0;
             } else {
                 const int eb = e - tot_pos - tot_sel;
                 band_v[eb] = __float_as_uint(exact_ce6(conf_rd, (int)band_p[eb], 0)) & 0x7fffffffu;
@@ -1410,13 +1377,15 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                 }
             }
             __syncthreads();
-            for (int e = tid; e < r; e += FT) acc_ce += (double)__uint_as_float(band_sorted[e]);
+            for (int e = tid; e < r; e += FT) fx_add(fx_ce, __uint_as_float(band_sorted[e]));
         }
     }
     SSDHOT_STAMP(8);
+    double acc_ce = 0.0;
     if (exact_all) {
-        // exact keys for every negative, then the exact radix selection (as loss_image_kernel)
-        acc_ce = 0.0;
+        // exact keys for every negative, then the exact radix selection (as loss_image_kernel); the cross-entropy side is
+        // redone in prior order (double accumulation), the smooth-L1 side only for positives the list could not hold
+        fx_ce = {0, 0, 0.0};
         __syncthreads();
         for (int i = tid; i < 256; i += FT) fs.ls.hist[i] = 0u;
         __syncthreads();
@@ -1428,6 +1397,7 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                 atomicAdd(&fs.ls.hist[key >> 24], 1u);
             } else {
                 acc_ce += (double)exact_ce6(conf_rd, p, fs.label[matched_box(lo)] + 1);
+                if (!pos_listed) positive_terms(p, matched_box(lo), false);
             }
         }
         __syncthreads();
@@ -1442,8 +1412,29 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                                        });
     }
 
-    const double s_loc = block_sum<double>(acc_loc, fs.ls.dscratch);
-    const double s_ce = block_sum<double>(acc_ce, fs.ls.dscratch);
+    // fixed point: integer addition is associative, so the order in which threads met the list entries does not matter.
+    // One exchange for the six partial sums (warp sums -> shared memory -> the first warp), instead of six block sums.
+    {
+        long long* isum = reinterpret_cast<long long*>(fs.ls.hist);       // [4][FT / 32]  (the radix histogram is dead by now)
+        const long long a0 = warp_sum(fx_loc.small), a1 = warp_sum(fx_loc.big), a2 = warp_sum(fx_ce.small), a3 = warp_sum(fx_ce.big);
+        const double d0 = warp_sum(fx_loc.odd), d1 = warp_sum(fx_ce.odd + acc_ce);
+        __syncthreads();
+        if (lane == 0) {
+            isum[warp] = a0; isum[FT / 32 + warp] = a1; isum[2 * (FT / 32) + warp] = a2; isum[3 * (FT / 32) + warp] = a3;
+            fs.fin_odd[0][warp] = d0; fs.fin_odd[1][warp] = d1;
+        }
+        __syncthreads();
+    }
+    double s_loc = 0.0, s_ce = 0.0;
+    if (warp == 0) {
+        const long long* isum = reinterpret_cast<const long long*>(fs.ls.hist);
+        const bool in = lane < FT / 32;
+        const long long t0 = warp_sum(in ? isum[lane] : 0ll), t1 = warp_sum(in ? isum[FT / 32 + lane] : 0ll);
+        const long long t2 = warp_sum(in ? isum[2 * (FT / 32) + lane] : 0ll), t3 = warp_sum(in ? isum[3 * (FT / 32) + lane] : 0ll);
+        const double o0 = warp_sum(in ? fs.fin_odd[0][lane] : 0.0), o1 = warp_sum(in ? fs.fin_odd[1][lane] : 0.0);
+        s_loc = (double)t0 * (1.0 / 281474976710656.0) + (double)t1 * (1.0 / 17179869184.0) + o0;
+        s_ce = (double)t2 * (1.0 / 281474976710656.0) + (double)t3 * (1.0 / 17179869184.0) + o1;
+    }
     if (tid == 0) {
         prm.img_part[2ll * b + 0] = s_loc;
         prm.img_part[2ll * b + 1] = s_ce;
