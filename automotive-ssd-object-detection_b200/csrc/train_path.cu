@@ -628,9 +628,9 @@ constexpr int GT_ROUND = 32;                 // boxes enumerated per round
 constexpr int NSEG = GT_ROUND * 32;          // (box, level-shape) segments per round
 constexpr int PAIR_CAP = 1536;               // listed gate survivors of an image (rest: settled inline, box recomputed)
 #ifndef SSDHOT_MT_LOSS
-#define SSDHOT_MT_LOSS 512
+#define SSDHOT_MT_LOSS 576
 #endif
-constexpr int MT_LOSS = SSDHOT_MT_LOSS;      // threads (warps 0..15) that match while the others stream the logits
+constexpr int MT_LOSS = SSDHOT_MT_LOSS;      // threads (warps 0..17) that match while the other six warps stream the logits (A/B on B200: 512 -> 43.5 us, 576 -> 41.6 us, 448 -> 45.6 us at B = 256)
 constexpr int POS_CAP = 2048;                // listed positive priors of an image (more: the exact tail walks the slots)
 constexpr int SEL_CAP = 4096;                // listed certainly-mined negatives
 constexpr int BAND_CAP = 1024;
@@ -1343,20 +1343,23 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     {
         const int n_sure = fs.n_sel, n_band = fs.n_band;
         if (fast && (n_band > BAND_CAP || n_sure > SEL_CAP)) { exact_all = true; fast = false; }   // (massive ties): CTA-uniform
-        // one pass over the three lists: positives | certain negatives | band members
+        // one pass over the lists: positives (cross-entropy) | positives (smooth-L1) | certain negatives | band members --
+        // the two sides of a positive are the longest chains of the pass, so they go to different threads
         const int tot_pos = pos_listed ? n_pos_img : 0;
         const int tot_sel = fast ? n_sure : 0;
         const int tot_band = fast ? n_band : 0;
-        for (int e = tid; e < tot_pos + tot_sel + tot_band; e += FT) {
-            if (e < tot_pos) {
-                const int p = (int)pos_list[e];
-                positive_terms(p, matched_box(v.lo[2 * p]), true);
-            } else if (e < tot_pos + tot_sel) {
-                const int p = (int)sel_list[e - tot_pos];
+        for (int e = tid; e < 2 * tot_pos + tot_sel + tot_band; e += FT) {
+            if (e < 2 * tot_pos) {
+                const int p = (int)pos_list[e < tot_pos ? e : e - tot_pos];
+                const int g = matched_box(v.lo[2 * p]);
+                if (e < tot_pos) fx_add(fx_ce, exact_ce6(conf_rd, p, fs.label[g] + 1));
+                else positive_terms(p, g, false);
+            } else if (e < 2 * tot_pos + tot_sel) {
+                const int p = (int)sel_list[e - 2 * tot_pos];
                 fx_add(fx_ce, exact_ce6(conf_rd, p, 0));
                 if (prm.sel_cls) prm.sel_cls[(long long)b * P + p] = 0;
             } else {
-                const int eb = e - tot_pos - tot_sel;
+                const int eb = e - 2 * tot_pos - tot_sel;
                 band_v[eb] = __float_as_uint(exact_ce6(conf_rd, (int)band_p[eb], 0)) & 0x7fffffffu;
             }
         }
