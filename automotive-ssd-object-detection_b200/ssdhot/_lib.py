@@ -22,6 +22,7 @@ PROTOTYPES = {
     "ssdhot_status_string": (C.c_char_p, [i32]),
     "ssdhot_launch_count": (u64, []),
     "ssdhot_debug_timeline": (i32, [vp]),
+    "ssdhot_debug_stream_probe": (i32, [vp, i32, i64, i32, vp, vp]),
     "ssdhot_prior_tables": (i32, [vp, i32, vp, vp, vp]),
     "ssdhot_prior_aux": (i32, [vp, i32, vp, vp]),
     "ssdhot_ssd300_layout_host": (i32, [vp, i32]),

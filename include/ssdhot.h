@@ -69,6 +69,12 @@ SSDHOT_API int ssdhot_abi_version(void);
 /* debug: device buffer [B][16] uint64 receiving %globaltimer stamps of ssdhot_multibox_loss_fwd's fused kernel
  * phases (NULL switches it off, the default); tools/timeline.py prints them */
 SSDHOT_API int ssdhot_debug_timeline(void* dev_buffer);
+
+/* Measurement aid (csrc/probe.cu): one CTA per image pulls `image_bytes` contiguous bytes (a multiple of 48, `conf` 16-byte
+ * aligned) and writes one checksum per image to out [B]; mode 0 = the 16-byte read-only loads the kernels use, mode 1 =
+ * 1-D bulk-async copies (cp.async.bulk + mbarrier) through a shared-memory ring.  tools/stream_probe.py times both. */
+SSDHOT_API int ssdhot_debug_stream_probe(const float* conf, int B, long long image_bytes, int mode, float* out,
+                                         ssdhot_stream_t stream);
 SSDHOT_API const char* ssdhot_status_string(int status);
 /* number of kernels this library has launched so far in this process (bench.py gpu_launches) */
 SSDHOT_API unsigned long long ssdhot_launch_count(void);
