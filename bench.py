@@ -39,12 +39,12 @@ N_SETS = 4             # rotating input sets: 4 x 89.5 MB > 126 MB L2, so no ste
 P, C = 8732, 6
 METRIC = "images/s for match+mined loss and decode+DIoU-NMS at bs=256 per GPU"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each half's kernels at this workload, from the
-# `ncu --set full` capture summarised in profiles/ (train_image_kernel; score_kernel + nms_image_kernel)
+# `ncu --set full` capture summarised in profiles/ (train_image_kernel + finalize_sums_kernel; predict_image_kernel)
 WORKLOAD = ("cfg3: B=256/GPU eval-step post-backbone path on one (loc_all, conf_all) pair per batch, as SSD_test_step runs it "
             "(match+mined loss, then predict thr 0.01 / nms 0.45 / max 200), P=8732, C=6, G~U{1..20}")
 TRAIN_KERNELS = "train_image_kernel + finalize_sums_kernel (match + encode + mined loss)"
-PREDICT_KERNELS = "score_kernel + nms_image_kernel (decode + threshold + rank + NMS)"
-TRAFFIC = {"match_loss": 57.24e6 + 0.78e6, "decode_nms": (53.73e6 + 0.60e6) + (31.74e6 + 0.01e6), "source": "profiles/r01_final2_ncu_full_summary.txt"}
+PREDICT_KERNELS = "predict_image_kernel (stream -> row keys -> hot rows -> decode + rank + NMS, one launch)"
+TRAFFIC = {"match_loss": 56.28e6 + 0.43e6 + 0.01e6, "decode_nms": 61.69e6 + 0.17e6, "source": "profiles/r02_final_ncu_full_summary.txt"}
 
 
 def peaks():
@@ -544,8 +544,30 @@ def main():
         return {"per_gpu_batch": batch, "ms": ms_k, "algorithmic_bytes": nbytes, "achieved": nbytes / (ms_k * 1e-3) / 1e9,
                 "frac": nbytes / (ms_k * 1e-3) / 1e9 / peak, "candidates_per_image": n_cand / batch}
 
-    kernels = {"score_kernel": {"b256": time_score_kernel(step, [(x["loc"], x["conf"]) for x in sets], BATCH)}}
+    kernels = {"score_kernel": {"b256": time_score_kernel(step, [(x["loc"], x["conf"]) for x in sets], BATCH),
+                                "note": "the generic two-kernel path's stream (logits in, 8-byte candidate keys out); the fast path is one kernel"}}
     roofline["kernels"] = kernels
+
+    # ---- what a kernel that ONLY reads the logits costs at this batch (csrc/probe.cu): the practical floor under both halves ---
+    def stream_floor(inputs, batch, iters=24):
+        from ssdhot import _lib
+        st_ = torch.cuda.current_stream(dev).cuda_stream
+        out = torch.empty((batch,), dtype=torch.float32, device=dev)
+        res = {}
+        for mode, name in ((0, "ldg128"), (1, "bulk_async")):
+            for i in range(3):
+                _lib.check(_lib.lib().ssdhot_debug_stream_probe(inputs[i % len(inputs)].data_ptr(), batch, P * C * 4, mode, out.data_ptr(), st_), "probe")
+            torch.cuda.synchronize(dev)
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+            for i, (a, b) in enumerate(evs):
+                a.record(); _lib.lib().ssdhot_debug_stream_probe(inputs[i % len(inputs)].data_ptr(), batch, P * C * 4, mode, out.data_ptr(), st_); b.record()
+            torch.cuda.synchronize(dev)
+            ms_k = statistics.median(a.elapsed_time(b) for a, b in evs)
+            res[name] = {"ms": ms_k, "gbs": batch * P * C * 4 / (ms_k * 1e-3) / 1e9}
+        return res
+    roofline["stream_floor"] = {"b256": stream_floor([x["conf"] for x in sets], BATCH),
+                                "note": "a kernel that only pulls conf_all (209,568 B per image, one CTA per image) and sums it, with the "
+                                        "kernels' 16-byte loads or with cp.async.bulk: what the HBM side alone costs at this batch, launch included"}
 
     # ---- the same halves at B = 2048 per GPU (wave quantisation and launch latency amortised) -------------
     large = None
@@ -571,6 +593,7 @@ def main():
 
         ml, mp = time_large(True), time_large(False)
         kernels["score_kernel"]["b2048"] = time_score_kernel(step_l, [(big["loc"], big["conf"])], LB, iters=10)
+        roofline["stream_floor"]["b2048"] = stream_floor([big["conf"]], LB, iters=10)
         g_l = statistics.mean(float(t["boxes"].shape[0]) for t in cfg_l["targets"])
         k_l = float(step_l.count.float().mean().item())
         bl, bp = LB * (349296 + 24 * g_l + 12), LB * (349296 + 28 * k_l + 4)
