@@ -606,6 +606,32 @@ def main():
         torch.cuda.empty_cache()
     roofline["large_batch"] = large
 
+    # ---- the layout-agnostic kernels (any priors / class count): cluster match + loss kernel, score + NMS kernels -------------
+    generic = None
+    if rank == 0:
+        psg = ssdhot.PriorSet.default(dev, generic=True)
+        step_g = HotPathStep(psg, BATCH, C, spec["iou_thresh"], spec["ratio"], spec["score_thresh"], spec["nms_thresh"], spec["max_per_img"])
+        st_ = torch.cuda.current_stream(dev).cuda_stream
+
+        def time_generic(fn, iters=24):
+            for i in range(3):
+                fn(i)
+            torch.cuda.synchronize(dev)
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+            for i, (a, b) in enumerate(evs):
+                a.record(); fn(i); b.record()
+            torch.cuda.synchronize(dev)
+            return statistics.median(a.elapsed_time(b) for a, b in evs)
+        g_loss = time_generic(lambda i: step_g.launch_loss(sets[i % N_SETS]["loc"], sets[i % N_SETS]["conf"], sets[i % N_SETS]["gt"], st_))
+        g_pred = time_generic(lambda i: (step_g.launch_predict(sets[i % N_SETS]["loc"], sets[i % N_SETS]["conf"], st_, stages=1),
+                                         step_g.launch_predict(sets[i % N_SETS]["loc"], sets[i % N_SETS]["conf"], st_, stages=2)))
+        generic = {"note": "the same halves on the layout-agnostic kernels (what other priors / class counts / > 64 boxes per image take): "
+                           "gt_prepare + match_kernel (cluster of 8 CTAs per image) + loss_image_kernel + finalize; score_kernel + nms_image_kernel",
+                   "match_loss_ms": g_loss, "decode_nms_ms": g_pred,
+                   "match_loss_frac": bytes_loss / (g_loss * 1e-3) / 1e9 / peak, "decode_nms_frac": bytes_pred / (g_pred * 1e-3) / 1e9 / peak}
+        del step_g
+    roofline["generic_path"] = generic
+
     barrier()       # (rank 0 alone measured the extra sections above; the sections below exchange sums again)
     # ---- strong scaling on BASELINE cfg 4: B = 4096 match + mined loss over the whole job, exchange inside the timed step ----
     strong = None

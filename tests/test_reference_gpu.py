@@ -230,3 +230,41 @@ def test_patched_model_methods_keep_reference_call_forms(env):
     assert torch.equal(a[0]["labels"], b[0]["labels"]) and torch.equal(a[0]["boxes"], b[0]["boxes"]) and torch.equal(a[0]["scores"], b[0]["scores"])
     assert torch.equal(m.decode_ssd(loc=loc[0, :8], priors=m.priors[:8], variances=(0.1, 0.2)),
                        sfs.mySSD.decode_ssd(loc=loc[0, :8], priors=m.priors[:8], variances=(0.1, 0.2)))
+
+
+def test_eval_step_and_packed_loader(env):
+    """ssdhot.eval_step (both halves on two streams, one conf tensor) equals the two calls it stands for; the fused step
+    functions accept the PackedTargets batches of ssdhot.collate_detection and give the List[Dict] loader's results."""
+    ssdhot, synth, dev, mdl = env["ssdhot"], env["synth"], env["dev"], env["mdl"]
+    cfg = synth.config(3, batch=6)
+    loc, conf = cfg["loc_all"].to(dev), cfg["conf_infer"].to(dev)
+    _, packed = ssdhot.collate_detection([(torch.zeros((1,)), t) for t in cfg["targets"]])
+    l_loc, l_conf, labels, scores, boxes, count = ssdhot.eval_step(mdl, loc, conf, packed, 0.5, 3.0, 0.01, 0.45, 200)
+    w_loc, w_conf = ssdhot.multibox_loss(mdl, loc, conf, cfg["targets"], 0.5, 3.0)
+    w_labels, w_scores, w_boxes, w_count = ssdhot.predict_padded(mdl, loc, conf, 0.01, 0.45, 200)
+    torch.cuda.synchronize()
+    assert l_loc.item() == w_loc.item() and l_conf.item() == w_conf.item()
+    assert torch.equal(count, w_count)
+    for b in range(6):
+        k = int(count[b])
+        assert torch.equal(labels[b, :k], w_labels[b, :k]) and torch.equal(scores[b, :k], w_scores[b, :k]) and torch.equal(boxes[b, :k], w_boxes[b, :k])
+    # the fused step functions on a TinySSD-sized stand-in: packed loader == list loader
+    import _util as U
+    torch.manual_seed(5)
+    gen = torch.Generator().manual_seed(9)
+    batches = [(torch.rand((3, 3, 300, 300), generator=gen), synth.make_targets(3, 1, 5, gen)) for _ in range(2)]
+    results = []
+    for use_packed in (False, True):
+        torch.manual_seed(21)
+        m = U.TinySSD().to(dev)
+        m.register_buffer("priors", ssdhot.default_boxes().to(dev), persistent=False)
+        loader = [(im.clone(), ssdhot.collate_detection([(torch.zeros((1,)), t) for t in tg])[1] if use_packed
+                   else [{k: v.clone() for k, v in t.items()} for t in tg]) for im, tg in batches]
+        opt = torch.optim.SGD(m.parameters(), lr=1e-3)
+        out = ssdhot.SSD_train_step(m, loader, opt, iou_thresh=0.5, neg_pos_ratio=3.0, device="cuda")
+        ev = ssdhot.trainer.make_test_step(R._StubMAP)(m, loader, score_thresh=0.05, nms_thresh=0.45, max_detections_per_img=20, device="cuda")
+        results.append((out, ev))
+    for key in ("training loss", "localization loss", "classification loss"):      # (cuDNN's weight gradients are not bit-reproducible)
+        assert close(results[0][0][key], results[1][0][key]), key
+    for key in ("testing loss", "localization loss", "classification loss"):
+        assert close(results[0][1][key], results[1][1][key]), key
