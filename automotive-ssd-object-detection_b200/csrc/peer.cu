@@ -30,13 +30,22 @@ struct PeerSlots {
     double* box[kPeerMax];      // box[r] = rank r's mailbox as mapped in THIS process (box[rank] = the local one)
 };
 
+// img_part != null: the kernel also does finalize_sums_kernel's job first -- it folds the per-image partial sums [B][2] and
+// the per-image positive counts of the loss kernel it was launched behind (PDL) into this rank's three sums, lane-strided
+// and then over a fixed shuffle tree (deterministic), so that the step's loss branch has one dependent launch less.
 __global__ void __launch_bounds__(32) peer_allreduce_kernel(double* __restrict__ sums, const PeerSlots ps, int rank, int world, int lag,
-                                                            unsigned long long* __restrict__ seq_counter, int32_t* __restrict__ flags) {
-    pdl_wait();                                     // (may be launched with PDL behind finalize_sums_kernel)
+                                                            unsigned long long* __restrict__ seq_counter, int32_t* __restrict__ flags,
+                                                            const double* __restrict__ img_part, const int32_t* __restrict__ n_pos, int B) {
+    pdl_wait();                                     // (launched with PDL behind finalize_sums_kernel or the loss kernel itself)
     const int lane = threadIdx.x;
     const unsigned long long seq = *seq_counter + 1ull;
     const int par = (int)(seq % kGenerations);
-    const double a = sums[0], c = sums[1], n = sums[2];
+    double a, c, n;
+    if (img_part) {
+        a = 0.0; c = 0.0; n = 0.0;
+        for (int i = lane; i < B; i += 32) { a += img_part[2ll * i]; c += img_part[2ll * i + 1]; n += (double)n_pos[i]; }
+        a = warp_sum(a); c = warp_sum(c); n = warp_sum(n);
+    } else { a = sums[0]; c = sums[1]; n = sums[2]; }
     __syncwarp();
     if (lane < world) {
         double* q = ps.box[0];
@@ -146,7 +155,32 @@ extern "C" int ssdhot_allreduce_sums_peer(double* sums, void* const* mailboxes_h
         ps.box[r] = reinterpret_cast<double*>(mailboxes_host[r]);
     }
     unsigned long long* seq = reinterpret_cast<unsigned long long*>(ps.box[rank] + kMailboxDoubles);
-    cudaError_t e = launch_pdl(peer_allreduce_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, sums, ps, rank, world, lag, seq, dev_flags);
+    cudaError_t e = launch_pdl(peer_allreduce_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, sums, ps, rank, world, lag, seq, dev_flags,
+                               (const double*)nullptr, (const int32_t*)nullptr, 0);
+    ++g_launches;
+    if (e != cudaSuccess) return (int)e;
+    return SSDHOT_OK;
+}
+
+// The same exchange fed by the per-image partial sums a loss forward left in its workspace (call the forward with
+// sums == NULL: it then skips its own final reduction): loss_work = that call's `work`, n_pos = that call's n_pos (NULL: the
+// workspace copy).  sums receives the all-reduced sums.  One dependent launch less per step than forward + ssdhot_allreduce_sums_peer.
+extern "C" int ssdhot_allreduce_partials_peer(const void* loss_work, int B, const int32_t* n_pos, double* sums, void* const* mailboxes_host,
+                                              int rank, int world, int lag, int32_t* dev_flags, ssdhot_stream_t stream) {
+    if (!loss_work || !sums || !mailboxes_host) return SSDHOT_ERR_NULL;
+    if (B <= 0 || world < 1 || world > kPeerMax || rank < 0 || rank >= world) return SSDHOT_ERR_SHAPE;
+    if (lag != 0 && lag != 1) return SSDHOT_ERR_VALUE;
+    PeerSlots ps = {};
+    for (int r = 0; r < world; ++r) {
+        if (!mailboxes_host[r]) return SSDHOT_ERR_NULL;
+        ps.box[r] = reinterpret_cast<double*>(mailboxes_host[r]);
+    }
+    // workspace layout of the loss forward (train_path.cu): img_part [B][2] double | n_pos [B] int32 | ...
+    const double* img_part = reinterpret_cast<const double*>(loss_work);
+    const int32_t* np = n_pos ? n_pos : reinterpret_cast<const int32_t*>(reinterpret_cast<const unsigned char*>(loss_work) + (size_t)B * 2 * sizeof(double));
+    unsigned long long* seq = reinterpret_cast<unsigned long long*>(ps.box[rank] + kMailboxDoubles);
+    cudaError_t e = launch_pdl(peer_allreduce_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, sums, ps, rank, world, lag, seq, dev_flags,
+                               img_part, np, B);
     ++g_launches;
     if (e != cudaSuccess) return (int)e;
     return SSDHOT_OK;

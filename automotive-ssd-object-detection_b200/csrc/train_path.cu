@@ -1827,6 +1827,7 @@ extern "C" unsigned long long ssdhot_loss_workspace_bytes(int B, int P, int max_
 }
 
 static int finalize(const TrainParams& prm, const int32_t* n_pos, double* sums, cudaStream_t stream) {
+    if (!sums) return SSDHOT_OK;        // the caller folds the per-image partials itself (ssdhot_allreduce_partials_peer)
     cudaError_t e = launch_pdl(finalize_sums_kernel, dim3(1), dim3(256), 0, stream, (const double*)prm.img_part, prm.B, n_pos, prm.B, sums);
     ++g_launches;
     if (e != cudaSuccess) return (int)e;
@@ -1843,7 +1844,7 @@ extern "C" int ssdhot_multibox_loss_fwd(const float* priors_cxcywh, const float*
     int rc = check_gt_args(priors_cxcywh, priors_xyxy, prior_aux, P, gt_boxes, gt_labels, gt_offsets, B, max_gt,
                            norm_w, norm_h, var_center, var_size);
     if (rc) return rc;
-    if (!loc_all || !conf_all || !sums || !work) return SSDHOT_ERR_NULL;
+    if (!loc_all || !conf_all || !work) return SSDHOT_ERR_NULL;
     if (C < 2 || C > SSDHOT_MAX_CLASSES) return SSDHOT_ERR_SHAPE;
     if (sel_cls && C > SSDHOT_MAX_CLASSES_BWD) return SSDHOT_ERR_SHAPE;       // sel_cls holds the target class in an int8
     if (!(neg_pos_ratio >= 0.0)) return SSDHOT_ERR_VALUE;
@@ -1891,7 +1892,7 @@ extern "C" int ssdhot_multibox_loss_heads_fwd(const float* priors_cxcywh, const 
     int rc = check_gt_args(priors_cxcywh, priors_xyxy, prior_aux, P, gt_boxes, gt_labels, gt_offsets, B, max_gt,
                            norm_w, norm_h, var_center, var_size);
     if (rc) return rc;
-    if (!loc_heads_host || !conf_heads_host || !sums || !work) return SSDHOT_ERR_NULL;
+    if (!loc_heads_host || !conf_heads_host || !work) return SSDHOT_ERR_NULL;
     if (head_layout != SSDHOT_HEADS_NHWC && head_layout != SSDHOT_HEADS_NCHW) return SSDHOT_ERR_VALUE;
     if (!(neg_pos_ratio >= 0.0)) return SSDHOT_ERR_VALUE;
     // other class counts, priors or box counts: ssdhot_pack_heads + ssdhot_multibox_loss_fwd

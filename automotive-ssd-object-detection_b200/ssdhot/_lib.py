@@ -56,6 +56,7 @@ PROTOTYPES = {
     "ssdhot_peer_open": (i32, [vp, vp]),
     "ssdhot_peer_close": (i32, [vp]),
     "ssdhot_allreduce_sums_peer": (i32, [vp, vp, i32, i32, i32, vp, vp]),
+    "ssdhot_allreduce_partials_peer": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, vp, vp]),
 }
 
 

@@ -172,6 +172,21 @@ class PeerSums:
         self._lib.check(rc, "ssdhot_allreduce_sums_peer")
         return sums
 
+    def allreduce_partials(self, loss_work: torch.Tensor, batch: int, n_pos: Optional[torch.Tensor], sums: torch.Tensor,
+                           stream: Optional[int] = None) -> torch.Tensor:
+        """allreduce() fed by the per-image partial sums a loss forward left in `loss_work` (forward called with sums=None):
+        the kernel folds them itself, so the loss branch of a step is loss kernel -> this kernel (no finalize launch)."""
+        if sums.dtype != torch.float64 or sums.numel() != 3 or not sums.is_cuda:
+            raise self._lib.SsdhotError("PeerSums.allreduce_partials needs a CUDA float64 tensor of 3 elements")
+        if stream is None:
+            stream = torch.cuda.current_stream(sums.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = self._lib.lib().ssdhot_allreduce_partials_peer(loss_work.data_ptr(), int(batch), None if n_pos is None else n_pos.data_ptr(),
+                                                                sums.data_ptr(), self._boxes_ptr, self.rank, self.world, self.lag,
+                                                                self.flags.data_ptr(), stream)
+        self._lib.check(rc, "ssdhot_allreduce_partials_peer")
+        return sums
+
     def timed_out(self) -> bool:
         """True if some allreduce gave up waiting for a peer (host synchronisation)."""
         return bool(int(self.flags.item()) & 2)

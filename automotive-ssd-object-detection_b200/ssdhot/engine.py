@@ -30,6 +30,8 @@ class HotPathStep:
         self.norm_wh = (float(norm_wh[0]), float(norm_wh[1]))
         self.train_half, self.infer_half = train_half, infer_half
         self.concurrent, self._fork = bool(concurrent), None
+        # with a PeerSums the exchange kernel folds the per-image partials itself: loss kernel -> exchange, no finalize launch
+        self._fold_in_peer = isinstance(group, _dist.PeerSums)
         self.group = group          # ranks that share the batch: a torch.distributed group (True = default) or a dist.PeerSums;
                                     # the three sums are all-reduced inside run()
         dev = priors.device
@@ -57,7 +59,7 @@ class HotPathStep:
             gt.boxes.data_ptr(), gt.labels.data_ptr(), gt.offsets.data_ptr(), self.B, gt.max_gt,
             self.norm_wh[0], self.norm_wh[1], loc.data_ptr(), conf.data_ptr(), self.C,
             self.iou_thresh, ps.variances[0], ps.variances[1], self.ratio,
-            self.sums.data_ptr(), self.loss_work.data_ptr(), None, None, self.n_pos.data_ptr(), None, stream)
+            None if self._fold_in_peer else self.sums.data_ptr(), self.loss_work.data_ptr(), None, None, self.n_pos.data_ptr(), None, stream)
         _lib.check(rc, "ssdhot_multibox_loss_fwd")
 
     def launch_loss_heads(self, heads: HeadSet, gt: PackedTargets, stream: int) -> None:
@@ -70,7 +72,7 @@ class HotPathStep:
             gt.boxes.data_ptr(), gt.labels.data_ptr(), gt.offsets.data_ptr(), self.B, gt.max_gt,
             self.norm_wh[0], self.norm_wh[1], heads.loc_ptr, heads.conf_ptr, heads.layout, self.C,
             self.iou_thresh, ps.variances[0], ps.variances[1], self.ratio,
-            self.sums.data_ptr(), self.loss_work.data_ptr(), None, None, self.n_pos.data_ptr(), None, stream)
+            None if self._fold_in_peer else self.sums.data_ptr(), self.loss_work.data_ptr(), None, None, self.n_pos.data_ptr(), None, stream)
         _lib.check(rc, "ssdhot_multibox_loss_heads_fwd")
 
     def launch_predict_heads(self, heads: HeadSet, stream: int, stages: int = 3) -> None:
@@ -171,7 +173,9 @@ class HotPathStep:
 
     def _reduce(self) -> None:
         """The sharded path's only exchange: all-reduce [sum smooth-L1, sum CE, sum positives] in place."""
-        if self.group is not None:                      # (a PeerSums is one kernel and becomes part of the step's CUDA graph)
+        if self._fold_in_peer:                          # one kernel, part of the step's CUDA graph: fold the partials + exchange
+            self.group.allreduce_partials(self.loss_work, self.B, self.n_pos, self.sums)
+        elif self.group is not None:
             _dist.reduce_sums(self.sums, self.group)
 
     def losses(self, group=None):

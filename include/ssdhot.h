@@ -131,6 +131,7 @@ SSDHOT_API int ssdhot_compact_rows(const float* loc_t, const uint8_t* pos_mask, 
  *   sums [3] double, OVERWRITTEN: { sum smooth-L1, sum CE (positives + mined), sum n_pos } --
  *   un-normalised, ready for one all-reduce; loss = sums[0..1] / max(sums[2], 1) (TR:105,600).
  *   work: scratch of ssdhot_loss_workspace_bytes(B, P, max_gt) bytes, 16-byte aligned.
+ *   sums may be NULL: the final reduction is then left to ssdhot_allreduce_partials_peer (the partials stay in `work`).
  *   Optional, for the backward pass: sel_cls [B,P] int8 (-1 = prior not in the loss, else its
  *   target class), matched_gt [B,P] int16 (positives only, -1 elsewhere), n_pos [B]. */
 SSDHOT_API unsigned long long ssdhot_loss_workspace_bytes(int B, int P, int max_gt);
@@ -282,6 +283,12 @@ SSDHOT_API int ssdhot_peer_open(const void* handle64_host, void** mailbox_out);
 SSDHOT_API int ssdhot_peer_close(void* mapped_mailbox);
 SSDHOT_API int ssdhot_allreduce_sums_peer(double* sums, void* const* mailboxes_host, int rank, int world, int lag, int32_t* dev_flags,
                                ssdhot_stream_t stream);
+/* The same exchange fed by the per-image partial sums of a loss forward that was called with sums == NULL (it then skips
+ * its own final reduction): loss_work = that call's `work`, B = its batch, n_pos = its n_pos (NULL: the workspace copy).
+ * The kernel folds the partials (fixed order) and exchanges them: one dependent launch less per step. */
+SSDHOT_API int ssdhot_allreduce_partials_peer(const void* loss_work, int B, const int32_t* n_pos, double* sums,
+                                              void* const* mailboxes_host, int rank, int world, int lag, int32_t* dev_flags,
+                                              ssdhot_stream_t stream);
 
 #ifdef __cplusplus
 }

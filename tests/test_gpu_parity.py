@@ -937,3 +937,36 @@ def test_full_size_stress_config(env):
     for k, b in enumerate(pick):
         assert bit_equal(cand[b, :200].long(), want[k]["cand"]), f"keep list, image {b}"
         assert bit_equal(labels[b], want[k]["labels"]) and bit_equal(scores[b], want[k]["scores"]) and bit_equal(boxes[b], want[k]["boxes"])
+
+
+def test_exchange_kernel_folds_the_partials(env):
+    """HotPathStep(group=PeerSums): the loss forward leaves its per-image partials (sums == NULL) and the exchange kernel
+    folds them itself (ssdhot_allreduce_partials_peer) -- same sums as loss kernel + finalize_sums_kernel, eager and replayed
+    from a CUDA graph, packed tensors and head layouts."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    from ssdhot import synth
+    from ssdhot.dist import PeerSums
+    from ssdhot.engine import HeadSet, HotPathStep
+    cfg = synth.config(3, batch=37)
+    loc, conf = cfg["loc_all"].to(dev), cfg["conf_infer"].to(dev)
+    gt = s.pack_targets(cfg["targets"], dev)
+    plain = HotPathStep(ps, 37, 6, 0.5, 3.0, 0.01, 0.45, 200)
+    plain.run(loc, conf, conf, gt)
+    torch.cuda.synchronize()
+    want = plain.sums.clone()
+    solo = PeerSums(dev)
+    try:
+        fused = HotPathStep(ps, 37, 6, 0.5, 3.0, 0.01, 0.45, 200, group=solo)
+        for use_graph in (False, True, True):
+            fused.sums.zero_()
+            fused.run(loc, conf, conf, gt, use_graph=use_graph)
+            torch.cuda.synchronize()
+            assert torch.allclose(fused.sums, want, rtol=1e-13, atol=0.0) and fused.sums[2].item() == want[2].item(), (fused.sums, want)
+        hs = HeadSet(U.unpack_heads(loc), U.unpack_heads(conf))
+        fused.sums.zero_()
+        fused.run_heads(hs, hs, gt)
+        torch.cuda.synchronize()
+        assert torch.allclose(fused.sums, want, rtol=1e-13, atol=0.0)
+        assert torch.equal(fused.count, plain.count) and not solo.timed_out()
+    finally:
+        solo.close()
