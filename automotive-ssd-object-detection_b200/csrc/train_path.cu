@@ -663,7 +663,6 @@ __host__ __device__ inline size_t fused_smem_bytes(int P) {
     return (size_t)P * 8 + FUSED_SCRATCH + 8192;         // table | scratch | CE histogram
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
@@ -1206,11 +1205,6 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
             const int at = atomicAdd(&fs.n_pos_img, 1);
             if (LOSS) {
                 if (at < POS_CAP) pos_list[at] = (uint16_t)p;      // the positives are listed here, not found again by a scan
-                if (SRC == SRC_PACKED) {                           // its rows are wanted ~3 us from now (exact pass): start them
-                    prefetch_l1(prm.loc_all + 4ll * ((long long)b * P + p));
-                    prefetch_l1(prm.conf_all + 6ll * ((long long)b * P + p));
-                    prefetch_l1(prm.pri + 4ll * p);
-                }
                 const int bin = ce_bin(old);
                 atomicSub(&hist16[bin >> 1], 1u << ((bin & 1) * 16));
             }
@@ -1333,7 +1327,6 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                     if (prm.matched16) prm.matched16[row] = pos ? (int16_t)matched_box(lo[h]) : (int16_t)-1;
                 }
                 if (fast && !pos && lo[h] >= band_lo_key) {          // (fast path off: nothing qualifies)
-                    if (SRC == SRC_PACKED) prefetch_l1(prm.conf_all + 6ll * ((long long)b * P + p));
                     if (lo[h] > band_hi_key) {
                         const int at = atomicAdd(&fs.n_sel, 1);
                         if (at < SEL_CAP) sel_list[at] = (uint16_t)p;
