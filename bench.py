@@ -420,6 +420,10 @@ def main():
                 "note": "peer collective with lag 1 (reduced sums arrive one step late: eval-step logging only, not a training step)"}
 
     # ---- per-half kernel time (CUDA events around each half, same rotation, direct launches) -------
+    # (a step object without a group: with a PeerSums the loss forward leaves its final reduction to the exchange kernel,
+    # and the halves are timed as a single GPU runs them -- loss kernel + finalize_sums_kernel -- at every N)
+    step_sharded, step = step, (make_step(None) if group is not None else step)
+
     def time_half(train: bool, iters: int):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
         st = torch.cuda.current_stream(dev).cuda_stream
@@ -632,6 +636,7 @@ def main():
         del step_g
     roofline["generic_path"] = generic
 
+    step = step_sharded
     barrier()       # (rank 0 alone measured the extra sections above; the sections below exchange sums again)
     # ---- strong scaling on BASELINE cfg 4: B = 4096 match + mined loss over the whole job, exchange inside the timed step ----
     strong = None
