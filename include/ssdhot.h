@@ -189,7 +189,10 @@ SSDHOT_API int ssdhot_nms(const float* boxes, const float* scores, const int32_t
  *   out_labels [B,max_per_img] int64 (0-based foreground id), out_scores [B,max_per_img],
  *   out_boxes [B,max_per_img,4] pixel xyxy, out_cand [B,max_per_img] int32 (optional: flat
  *   candidate id prior*(C-1)+class), out_count [B] int32 valid entries per image.
- * work: ssdhot_predict_workspace_bytes(B, P, C) bytes (16 candidate-list segments per image), 16-byte aligned. */
+ * work: ssdhot_predict_workspace_bytes(B, P, C) bytes (16 candidate-list segments per image), 16-byte aligned.
+ * SSD300 with C == 6 runs as ONE kernel (predict_image_kernel: the stream keeps one 16-bit key per row in shared memory, the
+ * candidates of the round come from the few "hot" rows; `work` is touched only by images that need more than one round);
+ * other shapes run the two-kernel path below.  Same results either way. */
 SSDHOT_API unsigned long long ssdhot_predict_workspace_bytes(int B, int P, int C);
 SSDHOT_API int ssdhot_predict(const float* priors_cxcywh, int P, const float* loc_all, const float* conf_all,
                    int B, int C, float score_thresh, float nms_thresh, int max_per_img,
@@ -208,7 +211,8 @@ SSDHOT_API int ssdhot_pack_heads(const float* const* heads_host, int B, int D, f
 /* The two stages of ssdhot_predict separately (same arguments): SSDHOT_STAGE_SCORES streams the logits and fills the
  * candidate lists in `work` (score_kernel, the HBM-bound stage); SSDHOT_STAGE_NMS ranks them and runs the greedy NMS
  * (nms_image_kernel) -- it consumes the lists, so it needs a fresh SCORES stage before every call.  ssdhot_predict is
- * stages = SCORES | NMS.  Used by bench.py to time the streaming kernel against the HBM roofline on its own. */
+ * stages = SCORES | NMS (for SSD300 / C == 6 that request takes the one-kernel path instead).  Used by bench.py to time the
+ * generic path's streaming kernel against the HBM roofline on its own. */
 #define SSDHOT_STAGE_SCORES 1
 #define SSDHOT_STAGE_NMS 2
 SSDHOT_API int ssdhot_predict_stages(const float* priors_cxcywh, int P, const float* loc_all, const float* conf_all,
