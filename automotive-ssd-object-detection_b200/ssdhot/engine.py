@@ -136,7 +136,9 @@ class HotPathStep:
         if hit is None:
             dev = self.ps.device
             g = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream(dev)
+            # the capture stream carries the loss branch, whose last node is the exchange: high priority lets its CTAs and the
+            # small exchange kernel ahead of the predict branch's (N = 2, lag 0: 81.9 -> 78.8 us per step; no effect at N = 1)
+            side = torch.cuda.Stream(dev, priority=-1)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 issue()                                              # warm (sets the shared-memory opt-ins)
