@@ -37,6 +37,16 @@ __device__ __forceinline__ float ord_decode(unsigned u) {
     return __uint_as_float(u);
 }
 
+// ---- key hand-off between the halves of an eval step (ssdhot_share_bytes): [B flags, 256-byte padded | B x stride words] ----
+__host__ __device__ inline int share_stride_words(int P) { return ((P / 2) + 3) & ~3; }
+__host__ __device__ inline size_t share_flags_bytes(int B) { return ((size_t)B * 4 + 255) & ~(size_t)255; }
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);

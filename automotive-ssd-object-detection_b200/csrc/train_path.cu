@@ -25,6 +25,8 @@
 //    column champion (its CIoU < cb0[g] <= max) nor make its prior positive (CIoU < iou_thresh).
 //    Positives, their matched boxes and the forced champions are therefore bit-identical to the
 //    exact sweep while ~98 % of the pairs cost 13 instructions instead of ~75.
+#include <type_traits>
+
 #include "boxmath.cuh"
 #include "heads.cuh"
 
@@ -60,6 +62,9 @@ struct TrainParams {
     int32_t* flags;
     unsigned long long* timeline;   // debug: [B][16] %globaltimer stamps of the fused kernel's phases (or null)
     HeadView loc_h, conf_h;         // head sources (SRC_LEVEL_ROWS / SRC_LEVEL_PLANES) instead of loc_all / conf_all
+    // key hand-off to predict_image_kernel of the same eval step (ssdhot_share_bytes; null = none): the stream also leaves the
+    // 16-bit row keys of the image's logits and raises the image's flag
+    int* share_flag; unsigned* share_keys;
 };
 
 // SSD300 pyramid (SSD_from_scratch.py:289-290): used only to pick seed priors, never for results
@@ -631,6 +636,12 @@ constexpr int PAIR_CAP = 1536;               // listed gate survivors of an imag
 #define SSDHOT_MT_LOSS 576
 #endif
 constexpr int MT_LOSS = SSDHOT_MT_LOSS;      // threads (warps 0..17) that match while the other six warps stream the logits (A/B on B200: 512 -> 43.5 us, 576 -> 41.6 us, 448 -> 45.6 us at B = 256)
+#ifndef SSDHOT_MT_SHARE
+#define SSDHOT_MT_SHARE 448
+#endif
+// ... and when predict waits for this stream's row keys (share buffer): ten stream warps deliver them ~5 us earlier; the kernel
+// alone is slower that way (44.1 vs 41.1 us), the forked step faster (B = 256: 69.1 -> 64.0 us)
+constexpr int MT_SHARE = SSDHOT_MT_SHARE;
 constexpr int POS_CAP = 2048;                // listed positive priors of an image (more: the exact tail walks the slots)
 constexpr int SEL_CAP = 4096;                // listed certainly-mined negatives
 constexpr int BAND_CAP = 1024;
@@ -669,16 +680,30 @@ __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.
 // Approximate -log_softmax(row)[0] of a 6-logit row.  d_i = x_i - max is the exact fp32 difference
 // the reference forms; each ex2.approx term is within 2.6e-7 absolute, the sum s in [1, 6] within
 // 4e-6 relative, ln(s) within 5e-6, so |result - exact CE| <= 6e-6 + 2e-7 CE  (bound used: 1e-5 + 1e-6 CE).
-__device__ __forceinline__ float approx_ce6(float x0, float x1, float x2, float x3, float x4, float x5) {
+template <bool RK>
+__device__ __forceinline__ float approx_ce6_rk(float x0, float x1, float x2, float x3, float x4, float x5, unsigned& rk) {
     const float mx = fmaxf(fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)), fmaxf(x4, x5));
     const float k = 1.4426950408889634f;
     const float d0 = x0 - mx;
-    const float s = ((ex2_approx(d0 * k) + ex2_approx((x1 - mx) * k)) + (ex2_approx((x2 - mx) * k) + ex2_approx((x3 - mx) * k))) +
-                    (ex2_approx((x4 - mx) * k) + ex2_approx((x5 - mx) * k));
+    const float e1 = ex2_approx((x1 - mx) * k), e2 = ex2_approx((x2 - mx) * k), e3 = ex2_approx((x3 - mx) * k);
+    const float e4 = ex2_approx((x4 - mx) * k), e5 = ex2_approx((x5 - mx) * k);
+    const float s = ((ex2_approx(d0 * k) + e1) + (e2 + e3)) + (e4 + e5);
     const float ce = lg2_approx(s) * 0.6931471805599453f - d0;
+    if (RK) {
+        // the row key of predict_image_kernel (infer_path.cu: stream_row_keys): the bin of the row's best approximate foreground
+        // score, from the exps already at hand; never 0 for a row of numbers, 0 for a row that holds a NaN / +Inf (no candidate)
+        float rs;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s));
+        const float sc = fmaxf(fmaxf(fmaxf(e1, e2), fmaxf(e3, e4)), e5) * rs;
+        rk = (s == s) ? max(__float_as_uint(sc) >> 15, 1u) : 0u;
+    }
     // a NaN / +-Inf logit makes the exact CE NaN or +Inf, which torch.topk ranks above every number (TR:597): keep it non-finite
     // here (fmaxf would turn NaN into 0) so that its key lands in the top, unresolved bin and the exact arithmetic decides
     return (ce != ce) ? __int_as_float(0x7fffffff) : fmaxf(ce, 0.0f);
+}
+__device__ __forceinline__ float approx_ce6(float x0, float x1, float x2, float x3, float x4, float x5) {
+    unsigned rk;
+    return approx_ce6_rk<false>(x0, x1, x2, x3, x4, x5, rk);
 }
 __device__ __forceinline__ float ce_error_bound(float ce) { return 1e-5f + 1e-6f * ce; }
 
@@ -1069,7 +1094,7 @@ __device__ __forceinline__ void match_phase(const TrainParams& prm, FusedStatic&
     role_sync<MT>();
 }
 
-template <bool LOSS, int SRC>
+template <bool LOSS, int SRC, bool SHARE>
 __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams prm) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ FusedStatic fs;
@@ -1077,7 +1102,7 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     __shared__ PlaneRegions regions;               // (NCHW heads: the stream's plane-wise order)
     pdl_trigger();                                 // finalize_sums_kernel may be scheduled early (it waits for this grid)
     SSDHOT_STAMP(0);
-    constexpr int MT = LOSS ? MT_LOSS : FT;                  // threads that run the matching
+    constexpr int MT = LOSS ? (SHARE ? MT_SHARE : MT_LOSS) : FT;       // threads that run the matching
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = prm.P;
     unsigned long long* table = reinterpret_cast<unsigned long long*>(dyn);
@@ -1151,41 +1176,51 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
         SSDHOT_STAMP(3);
     } else if (LOSS) {
         const int n_pairs = P / 2;
-        if (SRC == SRC_LEVEL_PLANES) {
-            // NCHW heads: plane-wise order (heads.cuh), a chunk of 32 cells per warp and iteration
-#pragma unroll 2
-            PlaneWalk walk(&regions);
-            for (int k = (tid - MT) >> 5; k < kPlaneChunks; k += (FT - MT) >> 5) {
-                float x[12];
-                int p0;
-                if (walk.load(k, lane, x, p0)) {
-                    const unsigned k0 = __float_as_uint(approx_ce6(x[0], x[1], x[2], x[3], x[4], x[5]));
-                    const unsigned k1 = __float_as_uint(approx_ce6(x[6], x[7], x[8], x[9], x[10], x[11]));
-                    v.lo[2 * p0] = k0;
-                    v.lo[2 * p0 + 2] = k1;
-                    ce_hist_add(hist16, k0);
-                    ce_hist_add(hist16, k1);
-                }
-            }
-        } else {
-#pragma unroll 2
-            for (int q = tid - MT; q < n_pairs; q += FT - MT) {
-                float x[12];
-                conf_rd.pair(q, x);
-                const unsigned k0 = __float_as_uint(approx_ce6(x[0], x[1], x[2], x[3], x[4], x[5]));
-                const unsigned k1 = __float_as_uint(approx_ce6(x[6], x[7], x[8], x[9], x[10], x[11]));
+        // key hand-off (eval step with one conf_all for both halves): flag 1 = this image's keys are on their way, 2 = delivered
+        unsigned* share_keys = SHARE ? prm.share_keys + (size_t)b * share_stride_words(P) : nullptr;
+        if (SHARE && tid == MT) st_release_gpu(prm.share_flag + b, 1);
+        // (two instances of the loop, so that neither carries the other's branch)
+        auto stream = [&](auto with_keys) {
+            constexpr bool RK = decltype(with_keys)::value;
+            auto row_pair = [&](const float* x, int q) {        // rows 2q, 2q + 1
+                unsigned r0 = 0u, r1 = 0u;
+                const unsigned k0 = __float_as_uint(approx_ce6_rk<RK>(x[0], x[1], x[2], x[3], x[4], x[5], r0));
+                const unsigned k1 = __float_as_uint(approx_ce6_rk<RK>(x[6], x[7], x[8], x[9], x[10], x[11], r1));
+                if (RK) share_keys[q] = r0 | (r1 << 16);
                 v.lo[4 * q] = k0;
                 v.lo[4 * q + 2] = k1;
                 ce_hist_add(hist16, k0);
                 ce_hist_add(hist16, k1);
+            };
+            if (SRC == SRC_LEVEL_PLANES) {
+                // NCHW heads: plane-wise order (heads.cuh), a chunk of 32 cells per warp and iteration
+                PlaneWalk walk(&regions);
+#pragma unroll 2
+                for (int k = (tid - MT) >> 5; k < kPlaneChunks; k += (FT - MT) >> 5) {
+                    float x[12];
+                    int p0;
+                    if (walk.load(k, lane, x, p0)) row_pair(x, p0 >> 1);
+                }
+            } else {
+#pragma unroll 2
+                for (int q = tid - MT; q < n_pairs; q += FT - MT) {
+                    float x[12];
+                    conf_rd.pair(q, x);
+                    row_pair(x, q);
+                }
             }
-        }
+        };
+        stream(std::integral_constant<bool, SHARE>{});
         if ((P & 1) && tid == MT) {                          // odd P: the last row (never SSD300)
             float r[6];
             conf_rd.row(P - 1, r);
             const unsigned k = __float_as_uint(approx_ce6(r[0], r[1], r[2], r[3], r[4], r[5]));
             v.lo[2 * (P - 1)] = k;
             ce_hist_add(hist16, k);
+        }
+        if (SHARE) {                                         // every stream warp's keys are out: publish
+            asm volatile("bar.sync 2, %0;" ::"n"(FT - MT) : "memory");
+            if (tid == MT) { __threadfence(); st_release_gpu(prm.share_flag + b, 2); }
         }
         if (tid == FT - 32) SSDHOT_STAMP(2);                 // (the last stream warp)
     }
@@ -1701,7 +1736,8 @@ static int launch_train_image(const TrainParams& prm_in, cudaStream_t stream) {
     TrainParams prm = prm_in;
     prm.timeline = g_timeline;
     const size_t dyn = fused_smem_bytes(prm.P);
-    auto kern = train_image_kernel<LOSS, SRC>;
+    auto kern = train_image_kernel<LOSS, SRC, false>;
+    if (LOSS && prm.share_keys) kern = train_image_kernel<LOSS, SRC, LOSS>;     // (<false, ., true> is never instantiated)
     {
         const int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), dyn);   // sticky per device; first raised by the warm-up call
         if (rc) return rc;
@@ -1826,6 +1862,27 @@ extern "C" unsigned long long ssdhot_loss_workspace_bytes(int B, int P, int max_
     return (unsigned long long)(ws_code_off(B, max_gt) + (size_t)B * P * sizeof(uint16_t) + 64);
 }
 
+// ---- key hand-off between the halves of an eval step -----------------------------------------------------------------------
+// SSD_test_step feeds ONE conf_all to the loss and to predict (SSD_trainer.py:208-256).  With a share buffer the loss kernel's
+// logit stream also leaves predict's 16-bit row keys (B x P/2 words) and raises one flag per image; predict_image_kernel of the
+// same step (on a second stream) picks them up instead of streaming conf_all again.  The flags are cleared by
+// ssdhot_share_reset, issued before the two launches fork; a predict CTA whose image's keys are not on their way streams itself.
+extern "C" unsigned long long ssdhot_share_bytes(int B, int P) {
+    if (B <= 0 || P <= 0) return 0;
+    return (unsigned long long)(share_flags_bytes(B) + (size_t)B * share_stride_words(P) * sizeof(unsigned));
+}
+extern "C" int ssdhot_share_reset(void* share, int B, ssdhot_stream_t stream) {
+    if (!share) return SSDHOT_ERR_NULL;
+    if (B <= 0) return SSDHOT_ERR_SHAPE;
+    const cudaError_t e = cudaMemsetAsync(share, 0, share_flags_bytes(B), (cudaStream_t)stream);
+    return e == cudaSuccess ? SSDHOT_OK : (int)e;
+}
+static void set_share(TrainParams& prm, void* share) {
+    if (!share || (prm.P & 1) || !aligned16(share)) return;
+    prm.share_flag = reinterpret_cast<int*>(share);
+    prm.share_keys = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(share) + share_flags_bytes(prm.B));
+}
+
 static int finalize(const TrainParams& prm, const int32_t* n_pos, double* sums, cudaStream_t stream) {
     if (!sums) return SSDHOT_OK;        // the caller folds the per-image partials itself (ssdhot_allreduce_partials_peer)
     cudaError_t e = launch_pdl(finalize_sums_kernel, dim3(1), dim3(256), 0, stream, (const double*)prm.img_part, prm.B, n_pos, prm.B, sums);
@@ -1840,7 +1897,7 @@ extern "C" int ssdhot_multibox_loss_fwd(const float* priors_cxcywh, const float*
                                         const float* loc_all, const float* conf_all, int C,
                                         float iou_thresh, float var_center, float var_size, double neg_pos_ratio,
                                         double* sums, void* work, int8_t* sel_cls, int16_t* matched_gt, int32_t* n_pos,
-                                        int32_t* dev_flags, ssdhot_stream_t stream) {
+                                        int32_t* dev_flags, void* share, ssdhot_stream_t stream) {
     int rc = check_gt_args(priors_cxcywh, priors_xyxy, prior_aux, P, gt_boxes, gt_labels, gt_offsets, B, max_gt,
                            norm_w, norm_h, var_center, var_size);
     if (rc) return rc;
@@ -1864,6 +1921,7 @@ extern "C" int ssdhot_multibox_loss_fwd(const float* priors_cxcywh, const float*
     if (C == 6 && aligned16(conf_all) && fast_path_ok(prior_layout, P, max_gt, iou_thresh)) {
         // SSD300 fast path: box-centric matching + mined loss, one kernel, one CTA per image
         prm.n_pos = np; prm.sel_cls = sel_cls; prm.matched16 = matched_gt; prm.code = nullptr;
+        set_share(prm, share);
         rc = launch_train_image<true>(prm, (cudaStream_t)stream);
         if (rc) return rc;
         return finalize(prm, np, sums, (cudaStream_t)stream);
@@ -1887,7 +1945,7 @@ extern "C" int ssdhot_multibox_loss_heads_fwd(const float* priors_cxcywh, const 
                                               int head_layout, int C,
                                               float iou_thresh, float var_center, float var_size, double neg_pos_ratio,
                                               double* sums, void* work, int8_t* sel_cls, int16_t* matched_gt, int32_t* n_pos,
-                                              int32_t* dev_flags, ssdhot_stream_t stream) {
+                                              int32_t* dev_flags, void* share, ssdhot_stream_t stream) {
     const int P = 8732;
     int rc = check_gt_args(priors_cxcywh, priors_xyxy, prior_aux, P, gt_boxes, gt_labels, gt_offsets, B, max_gt,
                            norm_w, norm_h, var_center, var_size);
@@ -1916,6 +1974,7 @@ extern "C" int ssdhot_multibox_loss_heads_fwd(const float* priors_cxcywh, const 
     prm.flags = dev_flags;
     int32_t* np = n_pos ? n_pos : reinterpret_cast<int32_t*>(w + ws_npos_off(B));
     prm.n_pos = np; prm.sel_cls = sel_cls; prm.matched16 = matched_gt; prm.code = nullptr;
+    set_share(prm, share);
     rc = head_layout == SSDHOT_HEADS_NHWC ? launch_train_image<true, SRC_LEVEL_ROWS>(prm, (cudaStream_t)stream)
                                           : launch_train_image<true, SRC_LEVEL_PLANES>(prm, (cudaStream_t)stream);
     if (rc) return rc;

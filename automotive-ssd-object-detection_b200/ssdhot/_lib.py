@@ -32,7 +32,9 @@ PROTOTYPES = {
     "ssdhot_compact_rows": (i32, [vp, vp, vp, i32, i32, vp, vp]),
     "ssdhot_loss_workspace_bytes": (u64, [i32, i32, i32]),
     "ssdhot_multibox_loss_fwd": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, i32, i32, f32, f32, vp, vp, i32,
-                                       f32, f32, f32, f64, vp, vp, vp, vp, vp, vp, vp]),
+                                       f32, f32, f32, f64, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "ssdhot_share_bytes": (u64, [i32, i32]),
+    "ssdhot_share_reset": (i32, [vp, i32, vp]),
     "ssdhot_mined_ce_fwd": (i32, [vp, vp, vp, i32, i32, i32, f64, vp, vp, vp, vp]),
     "ssdhot_multibox_loss_bwd": (i32, [vp, i32, vp, vp, i32, f32, f32, vp, vp, i32, f32, f32, vp, vp, vp, vp, vp, vp]),
     "ssdhot_decode": (i32, [vp, vp, i32, f32, f32, vp, vp]),
@@ -43,11 +45,11 @@ PROTOTYPES = {
     "ssdhot_predict": (i32, [vp, i32, vp, vp, i32, i32, f32, f32, i32, i32, i32, f32, f32, f32, f32,
                              vp, vp, vp, vp, vp, vp, vp]),
     "ssdhot_predict_stages": (i32, [vp, i32, vp, vp, i32, i32, f32, f32, i32, i32, i32, f32, f32, f32, f32,
-                                    vp, vp, vp, vp, vp, vp, i32, vp]),
+                                    vp, vp, vp, vp, vp, vp, i32, vp, vp]),
     "ssdhot_predict_heads": (i32, [vp, vp, vp, i32, i32, i32, f32, f32, i32, i32, i32, f32, f32, f32, f32,
-                                   vp, vp, vp, vp, vp, vp, i32, vp]),
+                                   vp, vp, vp, vp, vp, vp, i32, vp, vp]),
     "ssdhot_multibox_loss_heads_fwd": (i32, [vp, vp, vp, i32, vp, vp, vp, i32, i32, f32, f32, vp, vp, i32, i32,
-                                             f32, f32, f32, f64, vp, vp, vp, vp, vp, vp, vp]),
+                                             f32, f32, f32, f64, vp, vp, vp, vp, vp, vp, vp, vp]),
     "ssdhot_multibox_loss_heads_bwd": (i32, [vp, vp, vp, i32, f32, f32, vp, vp, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp]),
     "ssdhot_peer_mailbox_bytes": (u64, []),
     "ssdhot_peer_alloc": (i32, [vp]),

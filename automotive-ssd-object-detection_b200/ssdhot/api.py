@@ -295,7 +295,7 @@ def _check_group_for_grad(group, need_grad: bool) -> None:
 
 class _FusedLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, loc_all, conf_all, priors: PriorSet, packed: PackedTargets, iou_thresh, ratio, norm_wh, group):
+    def forward(ctx, loc_all, conf_all, priors: PriorSet, packed: PackedTargets, iou_thresh, ratio, norm_wh, group, share=None):
         dev = _need_cuda(loc_all, conf_all)
         B, P, C = conf_all.shape
         loc = loc_all.detach().to(torch.float32).contiguous()
@@ -311,7 +311,7 @@ class _FusedLoss(torch.autograd.Function):
                 packed.boxes.data_ptr(), packed.labels.data_ptr(), packed.offsets.data_ptr(), B, packed.max_gt,
                 float(norm_wh[0]), float(norm_wh[1]), loc.data_ptr(), conf.data_ptr(), C,
                 float(iou_thresh), priors.variances[0], priors.variances[1], float(ratio),
-                sums.data_ptr(), work.data_ptr(), _ptr(sel), _ptr(matched), None, None, _stream(dev))
+                sums.data_ptr(), work.data_ptr(), _ptr(sel), _ptr(matched), None, None, _ptr(share), _stream(dev))
         _lib.check(rc, "ssdhot_multibox_loss_fwd")
         if group is not None:
             # the only exchange of the sharded path: [sum smooth-L1, sum CE, sum positives]
@@ -341,11 +341,12 @@ class _FusedLoss(torch.autograd.Function):
                 priors.variances[0], priors.variances[1], sel.data_ptr(), matched.data_ptr(), scales.data_ptr(),
                 _ptr(d_loc), _ptr(d_conf), _stream(dev))
         _lib.check(rc, "ssdhot_multibox_loss_bwd")
-        return d_loc, d_conf, None, None, None, None, None, None
+        return d_loc, d_conf, None, None, None, None, None, None, None
 
 
 def multibox_loss(model, loc_all: torch.Tensor, conf_all: torch.Tensor, targets, iou_thresh: float = 0.5,
-                  neg_pos_ratio: float = 3.0, H: int = 300, W: int = 300, group=None, return_sums: bool = False):
+                  neg_pos_ratio: float = 3.0, H: int = 300, W: int = 300, group=None, return_sums: bool = False,
+                  _share: Optional[torch.Tensor] = None):
     """The whole post-backbone training step of SSD_train_step (SSD_trainer.py:92-117) in one
     launch: -> (batch_loc_loss, batch_conf_loss), 0-d fp32, differentiable w.r.t. loc_all/conf_all.
     With `group` (a torch.distributed process group, or True for the default group) the batch is
@@ -356,7 +357,7 @@ def multibox_loss(model, loc_all: torch.Tensor, conf_all: torch.Tensor, targets,
     priors = PriorSet.of(model)
     packed = pack_targets(targets, priors.device)
     l_loc, l_conf, sums = _FusedLoss.apply(loc_all, conf_all, priors, packed, float(iou_thresh), float(neg_pos_ratio),
-                                           (W, H), group)
+                                           (W, H), group, _share)
     if return_sums:
         return l_loc, l_conf, sums
     return l_loc, l_conf
@@ -418,7 +419,7 @@ def iou_nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float, met
 
 def predict_padded(model, loc_all: torch.Tensor, conf_all: torch.Tensor, score_thresh: float = 0.2,
                    nms_thresh: float = 0.5, max_per_img: int = 100, class_agnostic: bool = False,
-                   metric: str = "diou", want_cand: bool = False):
+                   metric: str = "diou", want_cand: bool = False, _share: Optional[torch.Tensor] = None):
     """Device-resident form of predict: padded outputs, no host synchronisation.
     -> (labels [B,max] i64, scores [B,max] f32, boxes [B,max,4] f32 px xyxy, count [B] i32[, cand])."""
     if not (0.0 <= score_thresh < 1.0):
@@ -439,13 +440,13 @@ def predict_padded(model, loc_all: torch.Tensor, conf_all: torch.Tensor, score_t
     count = torch.empty((B,), dtype=torch.int32, device=dev)
     work = _workspace("predict", dev, _lib.lib().ssdhot_predict_workspace_bytes(B, P, C))
     with torch.cuda.device(dev):
-        rc = _lib.lib().ssdhot_predict(priors.priors.data_ptr(), P, loc.data_ptr(), conf.data_ptr(), B, C,
-                                       float(score_thresh), float(nms_thresh), int(max_per_img), 1 if class_agnostic else 0,
-                                       METRICS[metric], priors.variances[0], priors.variances[1],
-                                       float(priors.img_w), float(priors.img_h),
-                                       labels.data_ptr(), scores.data_ptr(), boxes.data_ptr(), _ptr(cand),
-                                       count.data_ptr(), work.data_ptr(), _stream(dev))
-    _lib.check(rc, "ssdhot_predict")
+        rc = _lib.lib().ssdhot_predict_stages(priors.priors.data_ptr(), P, loc.data_ptr(), conf.data_ptr(), B, C,
+                                              float(score_thresh), float(nms_thresh), int(max_per_img), 1 if class_agnostic else 0,
+                                              METRICS[metric], priors.variances[0], priors.variances[1],
+                                              float(priors.img_w), float(priors.img_h),
+                                              labels.data_ptr(), scores.data_ptr(), boxes.data_ptr(), _ptr(cand),
+                                              count.data_ptr(), work.data_ptr(), 3, _ptr(_share), _stream(dev))
+    _lib.check(rc, "ssdhot_predict_stages")
     if want_cand:
         return labels, scores, boxes, count, cand
     return labels, scores, boxes, count
@@ -488,8 +489,8 @@ def eval_step(model, loc_all: torch.Tensor, conf_all: torch.Tensor, targets, iou
               score_thresh: float = 0.05, nms_thresh: float = 0.5, max_per_img: int = 100, class_agnostic: bool = False,
               H: int = 300, W: int = 300, group=None, metric: str = "diou"):
     """The post-backbone part of one SSD_test_step batch (SSD_trainer.py:214-256) on ONE pair of head outputs: targets + both
-    losses (one launch) and predict (two launches), which share nothing but the read-only inputs and therefore run on two
-    streams.  -> (loc_loss, conf_loss, labels [B,max] i64, scores [B,max], boxes [B,max,4], count [B] i32), all on the
+    losses and predict, one kernel each on two streams; the loss kernel's logit stream hands predict its row keys, so conf_all
+    is read from HBM once.  -> (loc_loss, conf_loss, labels [B,max] i64, scores [B,max], boxes [B,max,4], count [B] i32), all on the
     device, no host synchronisation."""
     dev = _need_cuda(loc_all, conf_all)
     cur = torch.cuda.current_stream(dev)
@@ -498,11 +499,16 @@ def eval_step(model, loc_all: torch.Tensor, conf_all: torch.Tensor, targets, iou
         side = _eval_fork[dev] = torch.cuda.Stream(dev)
     priors = PriorSet.of(model)
     packed = pack_targets(targets, dev)
+    # one conf_all feeds both halves: the loss kernel's logit stream leaves predict's row keys in `share` (ssdhot.h)
+    B, P, _ = conf_all.shape
+    share = _workspace("share", dev, _lib.lib().ssdhot_share_bytes(B, P))
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().ssdhot_share_reset(share.data_ptr(), B, _stream(dev)), "ssdhot_share_reset")
     side.wait_stream(cur)
+    l_loc, l_conf = multibox_loss(priors, loc_all, conf_all, packed, iou_thresh, neg_pos_ratio, H, W, group, _share=share)
     with torch.cuda.stream(side):
         labels, scores, boxes, count = predict_padded(priors, loc_all, conf_all, score_thresh, nms_thresh, max_per_img,
-                                                      class_agnostic, metric)
-    l_loc, l_conf = multibox_loss(priors, loc_all, conf_all, packed, iou_thresh, neg_pos_ratio, H, W, group)
+                                                      class_agnostic, metric, _share=share)
     cur.wait_stream(side)
     for t in (loc_all, conf_all):
         t.record_stream(side)
@@ -641,7 +647,7 @@ def predict_heads_padded(model, loc_heads: Sequence[torch.Tensor], conf_heads: S
                                              METRICS[metric], priors.variances[0], priors.variances[1],
                                              float(priors.img_w), float(priors.img_h),
                                              labels.data_ptr(), scores.data_ptr(), boxes.data_ptr(), _ptr(cand),
-                                             count.data_ptr(), work.data_ptr(), 3, _stream(dev))
+                                             count.data_ptr(), work.data_ptr(), 3, None, _stream(dev))
     _lib.check(rc, "ssdhot_predict_heads")
     hs.used_on(torch.cuda.current_stream(dev))
     if want_cand:
@@ -680,7 +686,7 @@ class _FusedLossHeads(torch.autograd.Function):
                 packed.boxes.data_ptr(), packed.labels.data_ptr(), packed.offsets.data_ptr(), B, packed.max_gt,
                 float(norm_wh[0]), float(norm_wh[1]), hs.loc_ptr, hs.conf_ptr, layout, C,
                 float(iou_thresh), priors.variances[0], priors.variances[1], float(ratio),
-                sums.data_ptr(), work.data_ptr(), _ptr(sel), _ptr(matched), None, None, _stream(dev))
+                sums.data_ptr(), work.data_ptr(), _ptr(sel), _ptr(matched), None, None, None, _stream(dev))
         _lib.check(rc, "ssdhot_multibox_loss_heads_fwd")
         hs.used_on(torch.cuda.current_stream(dev))
         if group is not None:

@@ -47,10 +47,13 @@ class HotPathStep:
         self.boxes = torch.zeros((self.B, m, 4), dtype=torch.float32, device=dev)
         self.count = torch.zeros((self.B,), dtype=torch.int32, device=dev)
         self.n_pos = torch.zeros((self.B,), dtype=torch.int32, device=dev)
+        # key hand-off between the halves when one conf_all feeds both (ssdhot.h: ssdhot_share_bytes)
+        self.share = torch.empty((int(L.ssdhot_share_bytes(self.B, priors.P)),), dtype=torch.uint8, device=dev)
+        self.share_keys = True
         self._graphs: Dict[tuple, tuple] = {}      # key -> (graph, tensors kept alive), in LRU order
 
     # -- raw launches -------------------------------------------------------------------------
-    def launch_loss(self, loc: torch.Tensor, conf: torch.Tensor, gt: PackedTargets, stream: int) -> None:
+    def launch_loss(self, loc: torch.Tensor, conf: torch.Tensor, gt: PackedTargets, stream: int, share: bool = False) -> None:
         ps = self.ps
         if gt.max_gt > self.max_gt:
             raise _lib.SsdhotError(f"HotPathStep was planned for at most {self.max_gt} boxes per image, got {gt.max_gt}")
@@ -59,10 +62,11 @@ class HotPathStep:
             gt.boxes.data_ptr(), gt.labels.data_ptr(), gt.offsets.data_ptr(), self.B, gt.max_gt,
             self.norm_wh[0], self.norm_wh[1], loc.data_ptr(), conf.data_ptr(), self.C,
             self.iou_thresh, ps.variances[0], ps.variances[1], self.ratio,
-            None if self._fold_in_peer else self.sums.data_ptr(), self.loss_work.data_ptr(), None, None, self.n_pos.data_ptr(), None, stream)
+            None if self._fold_in_peer else self.sums.data_ptr(), self.loss_work.data_ptr(), None, None, self.n_pos.data_ptr(), None,
+            self.share.data_ptr() if share else None, stream)
         _lib.check(rc, "ssdhot_multibox_loss_fwd")
 
-    def launch_loss_heads(self, heads: HeadSet, gt: PackedTargets, stream: int) -> None:
+    def launch_loss_heads(self, heads: HeadSet, gt: PackedTargets, stream: int, share: bool = False) -> None:
         """launch_loss reading the head outputs directly (train_image_kernel with a per-level source)."""
         ps = self.ps
         if gt.max_gt > self.max_gt:
@@ -72,10 +76,11 @@ class HotPathStep:
             gt.boxes.data_ptr(), gt.labels.data_ptr(), gt.offsets.data_ptr(), self.B, gt.max_gt,
             self.norm_wh[0], self.norm_wh[1], heads.loc_ptr, heads.conf_ptr, heads.layout, self.C,
             self.iou_thresh, ps.variances[0], ps.variances[1], self.ratio,
-            None if self._fold_in_peer else self.sums.data_ptr(), self.loss_work.data_ptr(), None, None, self.n_pos.data_ptr(), None, stream)
+            None if self._fold_in_peer else self.sums.data_ptr(), self.loss_work.data_ptr(), None, None, self.n_pos.data_ptr(), None,
+            self.share.data_ptr() if share else None, stream)
         _lib.check(rc, "ssdhot_multibox_loss_heads_fwd")
 
-    def launch_predict_heads(self, heads: HeadSet, stream: int, stages: int = 3) -> None:
+    def launch_predict_heads(self, heads: HeadSet, stream: int, stages: int = 3, share: bool = False) -> None:
         """launch_predict reading the head outputs directly (score_kernel / nms_image_kernel with a per-level source)."""
         ps = self.ps
         rc = _lib.lib().ssdhot_predict_heads(
@@ -83,10 +88,10 @@ class HotPathStep:
             self.score_thresh, self.nms_thresh, self.max_per_img, 1 if self.agnostic else 0, self.metric,
             ps.variances[0], ps.variances[1], float(ps.img_w), float(ps.img_h),
             self.labels.data_ptr(), self.scores.data_ptr(), self.boxes.data_ptr(), None,
-            self.count.data_ptr(), self.pred_work.data_ptr(), int(stages), stream)
+            self.count.data_ptr(), self.pred_work.data_ptr(), int(stages), self.share.data_ptr() if share else None, stream)
         _lib.check(rc, "ssdhot_predict_heads")
 
-    def launch_predict(self, loc: torch.Tensor, conf: torch.Tensor, stream: int, stages: int = 3) -> None:
+    def launch_predict(self, loc: torch.Tensor, conf: torch.Tensor, stream: int, stages: int = 3, share: bool = False) -> None:
         """stages: 1 = score_kernel only (fills the candidate lists), 2 = nms_image_kernel only, 3 = both."""
         ps = self.ps
         rc = _lib.lib().ssdhot_predict_stages(
@@ -94,7 +99,7 @@ class HotPathStep:
             self.score_thresh, self.nms_thresh, self.max_per_img, 1 if self.agnostic else 0, self.metric,
             ps.variances[0], ps.variances[1], float(ps.img_w), float(ps.img_h),
             self.labels.data_ptr(), self.scores.data_ptr(), self.boxes.data_ptr(), None,
-            self.count.data_ptr(), self.pred_work.data_ptr(), int(stages), stream)
+            self.count.data_ptr(), self.pred_work.data_ptr(), int(stages), self.share.data_ptr() if share else None, stream)
         _lib.check(rc, "ssdhot_predict_stages")
 
     def run(self, loc: torch.Tensor, conf_train: torch.Tensor, conf_infer: torch.Tensor, gt: PackedTargets,
@@ -109,9 +114,13 @@ class HotPathStep:
                 # the two halves are independent: fork the predict half onto a second stream and join
                 if self._fork is None:
                     self._fork = torch.cuda.Stream(dev)
+                # ONE conf_all for both halves (SSD_test_step): the loss kernel's stream hands predict its row keys
+                share = self.share_keys and conf_train.data_ptr() == conf_infer.data_ptr()
+                if share:
+                    _lib.check(_lib.lib().ssdhot_share_reset(self.share.data_ptr(), self.B, cur.cuda_stream), "ssdhot_share_reset")
                 self._fork.wait_stream(cur)
-                self.launch_loss(loc, conf_train, gt, cur.cuda_stream)
-                self.launch_predict(loc, conf_infer, self._fork.cuda_stream)
+                self.launch_loss(loc, conf_train, gt, cur.cuda_stream, share=share)
+                self.launch_predict(loc, conf_infer, self._fork.cuda_stream, share=share)
                 self._reduce()                                   # overlaps the predict half
                 cur.wait_stream(self._fork)
                 return
@@ -122,7 +131,7 @@ class HotPathStep:
                 self.launch_predict(loc, conf_infer, cur.cuda_stream)
             return
         tensors = (loc, conf_train, conf_infer, gt.boxes, gt.labels, gt.offsets)
-        g = self._graph_for(("packed",) + tuple(t.data_ptr() for t in tensors) + (gt.max_gt,), tensors,
+        g = self._graph_for(("packed",) + tuple(t.data_ptr() for t in tensors) + (gt.max_gt, self.share_keys), tensors,
                             lambda: self.run(loc, conf_train, conf_infer, gt))
         g.replay()
 
@@ -161,14 +170,17 @@ class HotPathStep:
             cur = torch.cuda.current_stream(dev)
             if self._fork is None:
                 self._fork = torch.cuda.Stream(dev)
+            share = self.share_keys and train_heads is infer_heads
+            if share:
+                _lib.check(_lib.lib().ssdhot_share_reset(self.share.data_ptr(), self.B, cur.cuda_stream), "ssdhot_share_reset")
             self._fork.wait_stream(cur)
-            self.launch_loss_heads(train_heads, gt, cur.cuda_stream)
-            self.launch_predict_heads(infer_heads, self._fork.cuda_stream)
+            self.launch_loss_heads(train_heads, gt, cur.cuda_stream, share=share)
+            self.launch_predict_heads(infer_heads, self._fork.cuda_stream, share=share)
             self._reduce()
             cur.wait_stream(self._fork)
             return
         tensors = tuple(train_heads.tensors) + tuple(infer_heads.tensors) + (gt.boxes, gt.labels, gt.offsets)
-        g = self._graph_for(("heads", train_heads.layout, infer_heads.layout) + tuple(t.data_ptr() for t in tensors) + (gt.max_gt,),
+        g = self._graph_for(("heads", train_heads.layout, infer_heads.layout) + tuple(t.data_ptr() for t in tensors) + (gt.max_gt, self.share_keys),
                             tensors + (train_heads, infer_heads),    # (the HeadSets own the host pointer arrays the launches read)
                             lambda: self.run_heads(train_heads, infer_heads, gt))
         g.replay()

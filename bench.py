@@ -275,6 +275,7 @@ def main():
     ap.add_argument("--collective-lag", type=int, default=0, choices=[0, 1],
                     help="peer collective: 0 = each step waits for its own reduced sums (what a training step needs; the headline), "
                          "1 = they arrive during the next step (eval-step logging only; also measured and printed as `lag1`)")
+    ap.add_argument("--no-share", action="store_true", help="the two halves each stream conf_all (no key hand-off from the loss kernel to predict)")
     ap.add_argument("--quick", action="store_true", help="diagnostics: only the main timed loop (no halves, roofline, heads, e2e)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-large-batch", action="store_true", help="skip the extra B=2048 roofline measurement")
@@ -341,6 +342,7 @@ def main():
         return HotPathStep(ps, BATCH, C, spec["iou_thresh"], spec["ratio"], spec["score_thresh"], spec["nms_thresh"],
                            spec["max_per_img"], concurrent=not args.serial, group=grp)
     step = make_step(peer)
+    step.share_keys = not args.no_share
     use_graph = not args.no_graph
 
     def barrier():
@@ -396,9 +398,12 @@ def main():
     clocks = sampler.result()
     sustained = {"steps": n_long, "ms_per_step": ms_long / n_long, "value": BATCH * world * n_long / (ms_long / 1e3),
                  "note": "the same loop run long enough (>= 0.25 s) for the clock sampler to cover it; `clocks` spans both regions"}
+    # key hand-off (ssdhot.h: ssdhot_share_bytes): images whose predict CTA took the row keys the loss kernel's stream left
+    picked = int((step.share[:4 * BATCH].view(torch.int32) == 3).sum().item()) if step.share_keys else 0
     if args.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "n_gpus": world, "value": value, "ms_per_step": ms_per_step, "sustained": sustained,
+                              "keys_handed_off": picked,
                               "per_rank_ms_per_step": [t / args.steps for t in per_rank_ms],
                               "collective": collective, "clocks": clocks}))
         if world > 1:
@@ -408,6 +413,15 @@ def main():
                     pr.close()
             dist.destroy_process_group()
         return
+    # the same step with each half streaming conf_all itself (the round-2 first-half form, for continuity)
+    step.share_keys = False
+    ms_ns, _ = timed_loop(step, args.steps)
+    step.share_keys = not args.no_share
+    handoff = {"on": step.share_keys, "images_handed_off_last_step": picked, "batch": BATCH,
+               "without": {"ms_per_step": ms_ns / args.steps, "value": BATCH * world * args.steps / (ms_ns / 1e3)},
+               "note": "one conf_all feeds both halves (SSD_test_step): the loss kernel's logit stream leaves predict's 16-bit row keys "
+                       "in HBM/L2 (17.5 KB per image) and predict_image_kernel picks them up instead of reading conf_all again; "
+                       "`without` = both halves stream the logits"}
     # the round-1 workload (the loss half reads its own, unbiased logits: two conf tensors per step) for continuity
     ms_sep, _ = timed_loop(step, args.steps, separate=True)
     separate = {"ms_per_step": ms_sep / args.steps, "value": BATCH * world * args.steps / (ms_sep / 1e3),
@@ -815,6 +829,7 @@ def main():
                       "decode_nms_images_per_s": BATCH * world / (ms_pred * 1e-3)},
             "sustained": sustained,
             "separate_conf": separate,
+            "key_handoff": handoff,
             "lag1": lag1,
             "strong_cfg4": strong,
             "roofline": roofline,

@@ -141,7 +141,18 @@ SSDHOT_API int ssdhot_multibox_loss_fwd(const float* priors_cxcywh, const float*
                              const float* loc_all, const float* conf_all, int C,
                              float iou_thresh, float var_center, float var_size, double neg_pos_ratio,
                              double* sums, void* work, int8_t* sel_cls, int16_t* matched_gt, int32_t* n_pos,
-                             int32_t* dev_flags, ssdhot_stream_t stream);
+                             int32_t* dev_flags, void* share, ssdhot_stream_t stream);
+
+/* ---- key hand-off inside an eval step (SSD_test_step, TR:208-256: ONE conf_all feeds the loss and predict) ------------
+ * `share` (device, ssdhot_share_bytes(B, P) bytes, 16-byte aligned; NULL = none) ties a ssdhot_multibox_loss_fwd /
+ * _heads_fwd launch to the ssdhot_predict_stages / _heads launch of the SAME logits issued on a second stream: the loss
+ * kernel's logit stream also leaves predict's 16-bit row keys there and raises one flag per image, and the predict kernel
+ * picks them up instead of reading conf_all a second time (SSD300 fast path and C == 6 on both sides; ignored otherwise --
+ * a predict CTA whose keys are not on their way streams the logits itself, so results never depend on it).  Results are
+ * identical with and without.  Per step: ssdhot_share_reset on the stream BEFORE the two launches fork (it clears the
+ * flags), then both launches with the same `share`; the next step's reset must be ordered after both. */
+SSDHOT_API unsigned long long ssdhot_share_bytes(int B, int P);
+SSDHOT_API int ssdhot_share_reset(void* share, int B, ssdhot_stream_t stream);
 
 /* CELoss_w_neg_mining (TR:551-600) with the targets given: sums[1] and sums[2] are written
  * (sums[0] = 0).  cls_t [B,P] int64, pos_mask [B,P] bytes. */
@@ -212,7 +223,7 @@ SSDHOT_API int ssdhot_pack_heads(const float* const* heads_host, int B, int D, f
  * candidate lists in `work` (score_kernel, the HBM-bound stage); SSDHOT_STAGE_NMS ranks them and runs the greedy NMS
  * (nms_image_kernel) -- it consumes the lists, so it needs a fresh SCORES stage before every call.  ssdhot_predict is
  * stages = SCORES | NMS (for SSD300 / C == 6 that request takes the one-kernel path instead).  Used by bench.py to time the
- * generic path's streaming kernel against the HBM roofline on its own. */
+ * generic path's streaming kernel against the HBM roofline on its own.  `share`: see ssdhot_share_bytes (NULL = none). */
 #define SSDHOT_STAGE_SCORES 1
 #define SSDHOT_STAGE_NMS 2
 SSDHOT_API int ssdhot_predict_stages(const float* priors_cxcywh, int P, const float* loc_all, const float* conf_all,
@@ -220,7 +231,7 @@ SSDHOT_API int ssdhot_predict_stages(const float* priors_cxcywh, int P, const fl
                           int class_agnostic, int metric, float var_center, float var_size,
                           float img_w, float img_h,
                           int64_t* out_labels, float* out_scores, float* out_boxes, int32_t* out_cand,
-                          int32_t* out_count, void* work, int stages, ssdhot_stream_t stream);
+                          int32_t* out_count, void* work, int stages, void* share, ssdhot_stream_t stream);
 
 /* The hot path straight from the head outputs (SSD_from_scratch.py:249-269): instead of the packed
  * loc_all / conf_all, the six per-level tensors of each branch (levels 38/19/10/5/3/1 with 4/6/6/6/4/4 shapes; HOST
@@ -239,7 +250,7 @@ SSDHOT_API int ssdhot_predict_heads(const float* priors_cxcywh, const float* con
                          int class_agnostic, int metric, float var_center, float var_size,
                          float img_w, float img_h,
                          int64_t* out_labels, float* out_scores, float* out_boxes, int32_t* out_cand,
-                         int32_t* out_count, void* work, int stages, ssdhot_stream_t stream);
+                         int32_t* out_count, void* work, int stages, void* share, ssdhot_stream_t stream);
 
 /* ssdhot_multibox_loss_fwd from the head outputs (see ssdhot_predict_heads for the two layouts).  SSD300 fast path only:
  * prior_layout == SSDHOT_LAYOUT_SSD300, C == 6, max_gt <= 64, iou_thresh > 0 -- SSDHOT_ERR_SHAPE otherwise (pack the heads
@@ -252,7 +263,7 @@ SSDHOT_API int ssdhot_multibox_loss_heads_fwd(const float* priors_cxcywh, const 
                          int head_layout, int C,
                          float iou_thresh, float var_center, float var_size, double neg_pos_ratio,
                          double* sums, void* work, int8_t* sel_cls, int16_t* matched_gt, int32_t* n_pos,
-                         int32_t* dev_flags, ssdhot_stream_t stream);
+                         int32_t* dev_flags, void* share, ssdhot_stream_t stream);
 
 /* ssdhot_multibox_loss_bwd on the head layouts: reads the head outputs, writes the gradients as six per-level tensors
  * of the same layout as the inputs (HOST arrays of DEVICE pointers; either gradient array may be NULL).  sel_cls /

@@ -462,7 +462,7 @@ def _raw_loss(s, ps, loc, conf, targets, thr, ratio):
         ps.priors.data_ptr(), ps.priors_xyxy.data_ptr(), ps.aux.data_ptr(), P, ps.layout,
         packed.boxes.data_ptr(), packed.labels.data_ptr(), packed.offsets.data_ptr(), B, packed.max_gt, 300.0, 300.0,
         loc.data_ptr(), conf.data_ptr(), C, float(thr), 0.1, 0.2, float(ratio),
-        sums.data_ptr(), work.data_ptr(), sel.data_ptr(), matched.data_ptr(), n_pos.data_ptr(), None,
+        sums.data_ptr(), work.data_ptr(), sel.data_ptr(), matched.data_ptr(), n_pos.data_ptr(), None, None,
         torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "ssdhot_multibox_loss_fwd")
     torch.cuda.synchronize(dev)
@@ -970,3 +970,71 @@ def test_exchange_kernel_folds_the_partials(env):
         assert torch.equal(fused.count, plain.count) and not solo.timed_out()
     finally:
         solo.close()
+
+
+def test_key_handoff_between_the_halves(env):
+    """One conf_all for both halves (SSD_test_step): the loss kernel's logit stream leaves predict's row keys in the share buffer
+    and predict_image_kernel picks them up instead of streaming the logits again.  Sums and detections are bit-identical to
+    the two independent launches: packed tensors and both head layouts, eager and replayed from a CUDA graph, a score
+    threshold of 0 (every row a candidate), non-finite logits, and a loss launch that does not deliver (generic path): the
+    predict CTAs then stream themselves."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    from ssdhot import synth
+    from ssdhot.engine import HeadSet, HotPathStep
+    B = 37
+    cfg = synth.config(3, batch=B)
+    loc, conf = cfg["loc_all"].to(dev), cfg["conf_infer"].to(dev).clone()
+    conf[3, 100:140, 2] = float("nan")
+    conf[5, 17, 0] = float("inf")
+    conf[7, 4000:4100] = float("-inf")
+    gt = s.pack_targets(cfg["targets"], dev)
+
+    def outputs(step):
+        torch.cuda.synchronize()
+        return [t.clone() for t in (step.sums, step.n_pos, step.count, step.labels, step.scores, step.boxes)]
+
+    def same(a, b):
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and bool(((x == y) | ((x != x) & (y != y))).all())
+
+    def picked_up(step):
+        return int((step.share[:4 * B].view(torch.int32) == 3).sum())
+
+    for thr in (0.01, 0.0):
+        apart = HotPathStep(ps, B, 6, 0.5, 3.0, thr, 0.45, 200)
+        apart.share_keys = False
+        apart.run(loc, conf, conf, gt)
+        want = outputs(apart)
+        together = HotPathStep(ps, B, 6, 0.5, 3.0, thr, 0.45, 200)
+        together.share.fill_(0xAB)                                  # (whatever the buffer held: the reset clears the flags)
+        for use_graph in (False, True, True):
+            for t in (together.count, together.labels, together.scores, together.boxes, together.sums):
+                t.zero_()
+            together.run(loc, conf, conf, gt, use_graph=use_graph)
+            same(outputs(together), want)
+            assert picked_up(together) >= B - 8, (thr, use_graph, picked_up(together))
+        for cl in (False, True):
+            hs = HeadSet(U.unpack_heads(loc, cl), U.unpack_heads(conf, cl))
+            together.count.zero_()
+            together.run_heads(hs, hs, gt)
+            same(outputs(together), want)
+            assert picked_up(together) >= B - 8, (thr, cl, picked_up(together))
+    # a loss launch that leaves no keys (generic priors -> match_kernel + loss_image_kernel): predict streams itself
+    generic = s.PriorSet.default(dev, generic=True)
+    apart = HotPathStep(generic, B, 6, 0.5, 3.0, 0.01, 0.45, 200)
+    apart.share_keys = False
+    apart.run(loc, conf, conf, gt)
+    want = outputs(apart)
+    together = HotPathStep(generic, B, 6, 0.5, 3.0, 0.01, 0.45, 200)
+    together.run(loc, conf, conf, gt)
+    same(outputs(together), want)
+    assert picked_up(together) == 0
+    # the public eval step goes the same way
+    l_loc, l_conf, labels, scores, boxes, count = s.eval_step(ps, loc, conf, cfg["targets"], 0.5, 3.0, 0.01, 0.45, 200)
+    a_loc, a_conf = s.multibox_loss(ps, loc, conf, cfg["targets"], 0.5, 3.0)
+    al, asc, ab, ac = s.predict_padded(ps, loc, conf, 0.01, 0.45, 200)
+    torch.cuda.synchronize()
+    same([l_loc, l_conf, count], [a_loc, a_conf, ac])
+    for b in range(B):
+        k = int(ac[b])
+        same([labels[b, :k], scores[b, :k], boxes[b, :k]], [al[b, :k], asc[b, :k], ab[b, :k]])

@@ -64,22 +64,25 @@ def test_validation_happens_before_launch_no_gpu_needed():
     odd = (ctypes.c_void_p * 6)(*([16] * 5 + [20]))
     ptr = lambda a: ctypes.cast(a, ctypes.c_void_p)
     heads = lambda loc, conf, layout, C: L.ssdhot_predict_heads(16, ptr(loc), ptr(conf), layout, 1, C, 0.1, 0.45, 200, 0, 0, 0.1, 0.2,
-                                                                  300.0, 300.0, 16, 16, 16, None, 16, 16, 3, None)
+                                                                  300.0, 300.0, 16, 16, 16, None, 16, 16, 3, None, None)
     assert heads(six, six, 7, 6) == -3                                      # unknown layout
     assert heads(six, six, 0, 21) == -2                                     # other class counts: pack first
     assert heads(six, five, 0, 6) == -1 and heads(six, odd, 1, 6) == -5     # missing / misaligned head
     assert L.ssdhot_predict_heads(16, None, ptr(six), 0, 1, 6, 0.1, 0.45, 200, 0, 0, 0.1, 0.2, 300.0, 300.0,
-                                  16, 16, 16, None, 16, 16, 3, None) == -1
+                                  16, 16, 16, None, 16, 16, 3, None, None) == -1
     assert L.ssdhot_multibox_loss_heads_fwd(16, 16, 16, 1, 16, 16, 16, 1, 4, 300.0, 300.0, ptr(six), ptr(six), 0, 21,
-                                            0.5, 0.1, 0.2, 3.0, 16, 16, None, None, None, None, None) == -2
+                                            0.5, 0.1, 0.2, 3.0, 16, 16, None, None, None, None, None, None) == -2
     assert L.ssdhot_multibox_loss_heads_fwd(16, 16, 16, 0, 16, 16, 16, 1, 4, 300.0, 300.0, ptr(six), ptr(six), 0, 6,
-                                            0.5, 0.1, 0.2, 3.0, 16, 16, None, None, None, None, None) == -2    # needs the SSD300 layout
+                                            0.5, 0.1, 0.2, 3.0, 16, 16, None, None, None, None, None, None) == -2    # needs the SSD300 layout
     assert L.ssdhot_multibox_loss_heads_bwd(16, 16, 16, 1, 300.0, 300.0, ptr(six), ptr(six), 5, 6, 0.1, 0.2, 16, 16, 16,
                                             ptr(six), ptr(six), None) == -3
     # the backward's class record sel_cls is an int8: more than 127 classes are refused when it is requested (forward-only is fine up to 256)
     fwd = lambda C, sel: L.ssdhot_multibox_loss_fwd(16, 16, 16, 8732, 0, 16, 16, 16, 1, 4, 300.0, 300.0, 16, 16, C,
-                                                     0.5, 0.1, 0.2, 3.0, 16, 20, sel, None, None, None, None)
+                                                     0.5, 0.1, 0.2, 3.0, 16, 20, sel, None, None, None, None, None)
     assert fwd(200, 16) == -2 and fwd(200, None) == -5 and fwd(127, 16) == -5      # (-5: past the shape checks, stopped by the misaligned workspace)
+    # key hand-off buffer: B flags (256-byte padded) + B x ceil4(P / 2) words
+    assert L.ssdhot_share_bytes(256, 8732) == 1024 + 256 * 4368 * 4 and L.ssdhot_share_bytes(0, 8732) == 0
+    assert L.ssdhot_share_reset(None, 4, None) == -1 and L.ssdhot_share_reset(16, 0, None) == -2
     assert L.ssdhot_mined_ce_fwd(16, 16, 16, 1, 8732, 128, 3.0, 16, 16, 16, None) == -2
     assert L.ssdhot_multibox_loss_bwd(16, 8732, 16, 16, 1, 300.0, 300.0, 16, 16, 128, 0.1, 0.2, 16, 16, 16, 16, 16, None) == -2
     # peer all-reduce: rank / world / lag are checked before anything is launched
