@@ -1193,7 +1193,8 @@ constexpr int HOT_CAP = CH;        // hot rows of a round (one thread each)
 template <int SRC>
 __device__ __forceinline__ void stream_row_keys(const PredictParams& prm, int b, int seg, int lane, const HeadTable& htab,
                                                 const PlaneRegions& regions, unsigned* __restrict__ rowkey32,
-                                                unsigned* __restrict__ hist16, int* __restrict__ n_rows_cand) {
+                                                unsigned* __restrict__ hist16, int* __restrict__ n_rows_cand,
+                                                const float* x_first = nullptr) {
     const int P = prm.P;
     const int rows = seg_rows(P);
     const int r0 = min(P, seg * rows), r1 = min(P, r0 + rows);
@@ -1241,7 +1242,13 @@ __device__ __forceinline__ void stream_row_keys(const PredictParams& prm, int b,
     };
     float xa[12], xb[12];
     int pa = 0, pb = 0;
-    bool la = load_it(0, xa, pa), lb = false;
+    bool la, lb = false;
+    if (SRC == SRC_PACKED && x_first) {                // (the first row pair was requested at the top of the kernel)
+#pragma unroll
+        for (int j = 0; j < 12; ++j) xa[j] = x_first[j];
+        pa = 2 * (q0 + lane);
+        la = n_it > 0 && q0 + lane < q1;
+    } else la = load_it(0, xa, pa);
     for (int it = 0; it < n_it; it += 2) {             // two iterations per trip: the next pair's loads are in flight
         lb = load_it(it + 1, xb, pb);
         process(xa, pa, la);
@@ -1310,6 +1317,16 @@ __global__ void __launch_bounds__(IT, 2) predict_image_kernel(const PredictParam
     // the row keys and the hot-row list live where the suppression rows and class-ordered boxes will be (dead before those are written)
     unsigned* rowkey32 = reinterpret_cast<unsigned*>(buf.mat);                 // [P / 2] two 16-bit keys per word
     int* hot = reinterpret_cast<int*>(rowkey32 + ((P / 2 + 3) & ~3));            // [HOT_CAP]
+    // a CTA that streams itself requests its first row pairs before anything else: their DRAM latency passes under the set-up
+    float x_first[12];
+    const bool pre = SRC == SRC_PACKED && !prm.share_keys;
+    if (pre) {
+        const int rows = seg_rows(P), r0 = min(P, warp * rows), r1 = min(P, r0 + rows), q = (r0 >> 1) + lane;
+        if (q < (r1 >> 1)) {
+            const HeadReader<SRC, 6> rd0 = {prm.conf_all + (long long)b * P * 6, nullptr};
+            rd0.pair(q, x_first);
+        }
+    }
     for (int i = tid; i < HBINS / 2; i += IT) buf.hist16[i] = 0u;
     for (int g = tid; g < n_groups; g += IT) buf.ngroup[g] = 0;
     if (tid == 0) { n_rows_cand = 0; n_hot = 0; more_low = 0; us.counter = 0; }
@@ -1326,7 +1343,7 @@ __global__ void __launch_bounds__(IT, 2) predict_image_kernel(const PredictParam
     }
     __syncthreads();
     if (keys_given) load_row_keys<IT>(prm.share_keys + (size_t)b * share_stride_words(P), P, prm.score_thresh, tid, rowkey32, buf.hist16, &n_rows_cand);
-    else stream_row_keys<SRC>(prm, b, warp, lane, conf_tab, regions, rowkey32, buf.hist16, &n_rows_cand);
+    else stream_row_keys<SRC>(prm, b, warp, lane, conf_tab, regions, rowkey32, buf.hist16, &n_rows_cand, pre ? x_first : nullptr);
     __syncthreads();
     bool first = true;
     SSDHOT_NSTAMP(0);

@@ -1133,6 +1133,13 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
         G = prm.max_gt;
     }
 
+    // the stream warps' first row pair is requested before anything else: its (cold) DRAM latency passes under the clear
+    float x_first[12];
+    if (LOSS && SRC == SRC_PACKED && tid >= MT && tid - MT < P / 2) {
+        const HeadReader<SRC, 6> rd0 = {prm.conf_all + (long long)b * P * 6, nullptr};
+        rd0.pair(tid - MT, x_first);
+    }
+
     // ---- 0. clear ------------------------------------------------------------------------------
     if (SRC != SRC_PACKED && LOSS) {
         head_table_fill<SRC, 4>(loc_tab, prm.loc_h, b, tid - 64);
@@ -1202,8 +1209,13 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
                     if (walk.load(k, lane, x, p0)) row_pair(x, p0 >> 1);
                 }
             } else {
+                int q = tid - MT;
+                if (SRC == SRC_PACKED) {                            // (requested at the top of the kernel)
+                    if (q < n_pairs) row_pair(x_first, q);
+                    q += FT - MT;
+                }
 #pragma unroll 2
-                for (int q = tid - MT; q < n_pairs; q += FT - MT) {
+                for (; q < n_pairs; q += FT - MT) {
                     float x[12];
                     conf_rd.pair(q, x);
                     row_pair(x, q);
