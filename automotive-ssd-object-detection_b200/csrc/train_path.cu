@@ -1103,6 +1103,7 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     pdl_trigger();                                 // finalize_sums_kernel may be scheduled early (it waits for this grid)
     SSDHOT_STAMP(0);
     constexpr int MT = LOSS ? (SHARE ? MT_SHARE : MT_LOSS) : FT;       // threads that run the matching
+    static_assert(MT % 32 == 0 && MT >= 256 && MT <= FT, "the matching prologue is spread over the first 204 threads");
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = prm.P;
     unsigned long long* table = reinterpret_cast<unsigned long long*>(dyn);
@@ -1126,19 +1127,15 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
     uint16_t* band_p = reinterpret_cast<uint16_t*>(band_sorted + BAND_CAP);        // [BAND_CAP]
     static_assert(2 * (POS_CAP + SEL_CAP) <= 4112 + 8192 && 4112 + 8192 + 10 * BAND_CAP <= FUSED_SCRATCH, "mining lists fit the scratch");
 
-    const int g_begin = prm.gt_offsets[b];
-    int G = prm.gt_offsets[b + 1] - g_begin;
-    if (G > prm.max_gt) {
-        if (tid == 0 && prm.flags) atomicOr(prm.flags, 1);
-        G = prm.max_gt;
-    }
-
     // the stream warps' first row pair is requested before anything else: its (cold) DRAM latency passes under the clear
     float x_first[12];
     if (LOSS && SRC == SRC_PACKED && tid >= MT && tid - MT < P / 2) {
         const HeadReader<SRC, 6> rd0 = {prm.conf_all + (long long)b * P * 6, nullptr};
         rd0.pair(tid - MT, x_first);
     }
+    // (requested here, first used behind the clear -- and by the matching warps only: the stream does not wait for the boxes)
+    const int g_begin = __ldg(prm.gt_offsets + b);
+    const int G_given = __ldg(prm.gt_offsets + b + 1) - g_begin;
 
     // ---- 0. clear ------------------------------------------------------------------------------
     if (SRC != SRC_PACKED && LOSS) {
@@ -1147,31 +1144,38 @@ __global__ void __launch_bounds__(FT, 2) train_image_kernel(const TrainParams pr
         if (SRC == SRC_LEVEL_PLANES) plane_regions_fill(regions, prm.conf_h, b, tid - 128);
     }
     if (tid == 0) { fs.first_nan = INT_MAX; fs.n_dense = 0; fs.n_band = 0; fs.n_pair = 0; fs.pair_overflow = 0; fs.n_pos_img = 0; fs.n_sure = 0; fs.n_pos_listed = 0; fs.n_sel = 0; }
-    if (tid >= 32 && tid < 32 + G) {
-        fs.gt_px[tid - 32] = ldg4(prm.gt_boxes + 4ll * (g_begin + tid - 32));
-        fs.label[tid - 32] = (int)prm.gt_labels[g_begin + tid - 32];
-    }
-    if (tid < 32) {
-        const int lv = kSeedLevel[tid], base = kLevelOffset[lv] + kSeedShape[tid];
-        const float4 sh = ldg4(prm.pri + 4ll * base);       // (w, h) of this level-shape: the same in every cell (checked on the host)
-        fs.cb_side[tid] = kLevelSide[lv]; fs.cb_shapes[tid] = kLevelShapes[lv]; fs.cb_base[tid] = base;
-        fs.cb_w[tid] = sh.z; fs.cb_h[tid] = sh.w; fs.cb_inv[tid] = 1.0f / (float)kLevelSide[lv];
-        fs.cb_hw[tid] = fmul(0.5f, sh.z); fs.cb_hh[tid] = fmul(0.5f, sh.w);
-        fs.cb_coff[tid] = lv == 0 ? 0 : lv == 1 ? 38 : lv == 2 ? 57 : lv == 3 ? 67 : lv == 4 ? 72 : 75;
-    }
-    if (tid >= 128 && tid < 128 + 76) {                     // the centres of the six grids: fl32((2 i + 1) / (2 side))
-        const int e = tid - 128;
-        const int lv = (e >= 38) + (e >= 57) + (e >= 67) + (e >= 72) + (e >= 75);
-        const int first = lv == 0 ? 0 : lv == 1 ? 38 : lv == 2 ? 57 : lv == 3 ? 67 : lv == 4 ? 72 : 75;
-        fs.centre[e] = fdiv((float)(2 * (e - first) + 1), (float)(2 * kLevelSide[lv]));
-    }
+    float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < 32) sh = ldg4(prm.pri + 4ll * (kLevelOffset[kSeedLevel[tid]] + kSeedShape[tid]));   // (w, h) of this level-shape: the same in every cell (checked on the host)
     {
         ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
         for (int i = tid; i < P / 2; i += FT) t2[i] = make_ulonglong2(0ull, 0ull);
         if ((P & 1) && tid == 0) table[P - 1] = 0ull;
         if (LOSS) for (int i = tid; i < 2048; i += FT) hist16[i] = 0u;
     }
-    __syncthreads();
+    __syncthreads();                                        // table, histogram and head tables are ready: the stream starts
+    const int G = min(G_given, prm.max_gt);
+    if (tid < MT) {
+        // what only the matching needs (the boxes arrive from HBM ~1 us after the offsets): behind its own barrier
+        if (tid == 0 && G_given > prm.max_gt && prm.flags) atomicOr(prm.flags, 1);
+        if (tid >= 32 && tid < 32 + G) {
+            fs.gt_px[tid - 32] = ldg4(prm.gt_boxes + 4ll * (g_begin + tid - 32));
+            fs.label[tid - 32] = (int)prm.gt_labels[g_begin + tid - 32];
+        }
+        if (tid < 32) {
+            const int lv = kSeedLevel[tid], base = kLevelOffset[lv] + kSeedShape[tid];
+            fs.cb_side[tid] = kLevelSide[lv]; fs.cb_shapes[tid] = kLevelShapes[lv]; fs.cb_base[tid] = base;
+            fs.cb_w[tid] = sh.z; fs.cb_h[tid] = sh.w; fs.cb_inv[tid] = 1.0f / (float)kLevelSide[lv];
+            fs.cb_hw[tid] = fmul(0.5f, sh.z); fs.cb_hh[tid] = fmul(0.5f, sh.w);
+            fs.cb_coff[tid] = lv == 0 ? 0 : lv == 1 ? 38 : lv == 2 ? 57 : lv == 3 ? 67 : lv == 4 ? 72 : 75;
+        }
+        if (tid >= 128 && tid < 128 + 76) {                 // the centres of the six grids: fl32((2 i + 1) / (2 side))
+            const int e = tid - 128;
+            const int lv = (e >= 38) + (e >= 57) + (e >= 67) + (e >= 72) + (e >= 75);
+            const int first = lv == 0 ? 0 : lv == 1 ? 38 : lv == 2 ? 57 : lv == 3 ? 67 : lv == 4 ? 72 : 75;
+            fs.centre[e] = fdiv((float)(2 * (e - first) + 1), (float)(2 * kLevelSide[lv]));
+        }
+        role_sync<MT>();
+    }
     const float thresh = prm.thresh;
     const HeadReader<SRC, 4> loc_rd = {SRC == SRC_PACKED && LOSS ? prm.loc_all + 4ll * b * P : nullptr, &loc_tab};
     const HeadReader<SRC, 6> conf_rd = {SRC == SRC_PACKED && LOSS ? prm.conf_all + (long long)b * P * 6 : nullptr, &conf_tab};
