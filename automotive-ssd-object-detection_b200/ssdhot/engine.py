@@ -124,11 +124,14 @@ class HotPathStep:
                 self._reduce()                                   # overlaps the predict half
                 cur.wait_stream(self._fork)
                 return
+            share = self.share_keys and self.train_half and self.infer_half and conf_train.data_ptr() == conf_infer.data_ptr()
+            if share:
+                _lib.check(_lib.lib().ssdhot_share_reset(self.share.data_ptr(), self.B, cur.cuda_stream), "ssdhot_share_reset")
             if self.train_half:
-                self.launch_loss(loc, conf_train, gt, cur.cuda_stream)
+                self.launch_loss(loc, conf_train, gt, cur.cuda_stream, share=share)
                 self._reduce()
             if self.infer_half:
-                self.launch_predict(loc, conf_infer, cur.cuda_stream)
+                self.launch_predict(loc, conf_infer, cur.cuda_stream, share=share)
             return
         tensors = (loc, conf_train, conf_infer, gt.boxes, gt.labels, gt.offsets)
         g = self._graph_for(("packed",) + tuple(t.data_ptr() for t in tensors) + (gt.max_gt, self.share_keys), tensors,

@@ -476,6 +476,13 @@ def main():
             "decode_nms": {"ms": ms_pred, "algorithmic_bytes": bytes_pred, "achieved": bytes_pred / (ms_pred * 1e-3) / 1e9,
                            "frac": bytes_pred / (ms_pred * 1e-3) / 1e9 / peak, "images_per_s": BATCH / (ms_pred * 1e-3)},
         },
+        # the whole forked step (what `value` times) against the same peak: as the two functions of the reference count their
+        # bytes (each reads conf_all + loc_all), and as the step moves them once the loss kernel hands predict its row keys
+        "step": {"ms": ms_per_step,
+                 "algorithmic_bytes_two_functions": bytes_loss + bytes_pred,
+                 "frac_two_functions": (bytes_loss + bytes_pred) / (ms_per_step * 1e-3) / 1e9 / peak,
+                 "algorithmic_bytes_shared_inputs": bytes_loss + BATCH * (28 * k_mean + 4),
+                 "frac_shared_inputs": (bytes_loss + BATCH * (28 * k_mean + 4)) / (ms_per_step * 1e-3) / 1e9 / peak},
     }
 
     # ---- the same halves fed by the head outputs: no permute / cat / pack pass ---------------
