@@ -275,6 +275,8 @@ def main():
     ap.add_argument("--collective-lag", type=int, default=0, choices=[0, 1],
                     help="peer collective: 0 = each step waits for its own reduced sums (what a training step needs; the headline), "
                          "1 = they arrive during the next step (eval-step logging only; also measured and printed as `lag1`)")
+    ap.add_argument("--in-flight", type=int, default=2, choices=[1, 2, 3],
+                    help="eval steps in flight (StepPipeline): consecutive eval batches are independent; 1 = strictly one after the other")
     ap.add_argument("--no-share", action="store_true", help="the two halves each stream conf_all (no key hand-off from the loss kernel to predict)")
     ap.add_argument("--quick", action="store_true", help="diagnostics: only the main timed loop (no halves, roofline, heads, e2e)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -317,10 +319,12 @@ def main():
     # --collective nccl (or a box without CUDA IPC between the ranks): torch.distributed all-reduce on a side stream, outside
     # the graph (a captured NCCL collective hung at process exit on this stack)
     peer, peer_lag1, reducer, collective = None, None, None, "none"
+    peers_more = []
     if group is not None:
         if args.collective == "peer":
             try:
                 peer = D.PeerSums(dev, lag=args.collective_lag)
+                peers_more = [D.PeerSums(dev, lag=args.collective_lag) for _ in range(args.in_flight - 1)]
                 peer_lag1 = D.PeerSums(dev, lag=1) if args.collective_lag == 0 else None
                 collective = ("peer-memory kernel over NVLink (ssdhot_allreduce_sums_peer), inside the step's CUDA graph, " +
                               ("lag 1: the reduced sums of step s are delivered during step s+1" if args.collective_lag else
@@ -330,10 +334,11 @@ def main():
         ok = torch.tensor([1 if (peer is not None or args.collective != "peer") else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if args.collective == "peer" and int(ok.item()) == 0:
-            for pr in (peer, peer_lag1):
+            for pr in [peer, peer_lag1] + peers_more:
                 if pr is not None:
                     pr.close()
             peer = peer_lag1 = None
+            peers_more = []
         if peer is None:
             reducer = D.SumsReducer(dev)
             collective = "NCCL all-reduce (torch.distributed) on a side stream, outside the CUDA graph"
@@ -344,6 +349,15 @@ def main():
     step = make_step(peer)
     step.share_keys = not args.no_share
     use_graph = not args.no_graph
+    # the headline keeps --in-flight eval steps in flight (engine.StepPipeline): consecutive eval batches do not depend on each
+    # other, so the loss kernel's logit stream of batch i+1 runs beside the NMS tail of batch i.  (The NCCL fallback reducer
+    # works on one step at a time: depth 1 there.)
+    from ssdhot.engine import StepPipeline
+    depth = args.in_flight if (reducer is None and use_graph and not args.serial) else 1
+    more_steps = [make_step(pr) for pr in (peers_more if group is not None else [None] * (depth - 1))][:depth - 1]
+    for st_ in more_steps:
+        st_.share_keys = step.share_keys
+    pipe = StepPipeline(lambda k: ([step] + more_steps)[k], depth=depth)
 
     def barrier():
         if world > 1:
@@ -351,9 +365,15 @@ def main():
         torch.cuda.synchronize(dev)
 
     def timed_loop(stp, n_steps, separate=False, use_reducer=True):
-        """n_steps steps, CUDA events on the launching stream -> (ms total, max over ranks; per-rank list)."""
+        """n_steps steps, CUDA events on the launching stream -> (ms total, max over ranks; per-rank list).  stp: a HotPathStep
+        (one step after the other) or a StepPipeline (its steps in flight; the closing event waits for all of them)."""
+        piped = isinstance(stp, StepPipeline)
+
         def one(i):
             s = sets[i % N_SETS]
+            if piped:
+                stp.submit(s["loc"], s["conf_t"] if separate else s["conf"], s["conf"], s["gt"], use_graph=use_graph)
+                return
             stp.run(s["loc"], s["conf_t"] if separate else s["conf"], s["conf"], s["gt"], use_graph=use_graph)
             if reducer is not None and use_reducer:
                 reducer.submit(stp.sums)
@@ -368,6 +388,8 @@ def main():
         e0.record()
         for i in range(n_steps):
             one(i)
+        if piped:
+            stp.wait()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -390,12 +412,17 @@ def main():
     sampler = ClockSampler(local)           # (opens NVML: slow and uneven across ranks, so before the barrier)
     if not os.environ.get("BENCH_NO_SAMPLER"):
         sampler.start()
-    ms_total, per_rank_ms = timed_loop(step, args.steps)
+    head = pipe if depth > 1 else step
+    ms_total, per_rank_ms = timed_loop(head, args.steps)
     ms_per_step = ms_total / args.steps
     value = BATCH * world * args.steps / (ms_total / 1e3)
     n_long = max(args.steps, int(250.0 / max(ms_per_step, 1e-3)) + 1)
-    ms_long, _ = timed_loop(step, n_long)
+    ms_long, _ = timed_loop(head, n_long)
     clocks = sampler.result()
+    ms_seq, _ = timed_loop(step, args.steps) if depth > 1 else (ms_total, None)
+    sequential = {"steps_in_flight": 1, "ms_per_step": ms_seq / args.steps, "value": BATCH * world * args.steps / (ms_seq / 1e3),
+                  "note": "the same steps strictly one after the other (one CUDA graph replay at a time on one stream): what rounds 1 and "
+                          "2a reported as `value`, and what a TRAINING loop, whose steps depend on each other, can use"}
     sustained = {"steps": n_long, "ms_per_step": ms_long / n_long, "value": BATCH * world * n_long / (ms_long / 1e3),
                  "note": "the same loop run long enough (>= 0.25 s) for the clock sampler to cover it; `clocks` spans both regions"}
     # key hand-off (ssdhot.h: ssdhot_share_bytes): images whose predict CTA took the row keys the loss kernel's stream left
@@ -403,12 +430,13 @@ def main():
     if args.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "n_gpus": world, "value": value, "ms_per_step": ms_per_step, "sustained": sustained,
+                              "steps_in_flight": depth, "sequential": sequential,
                               "keys_handed_off": picked,
                               "per_rank_ms_per_step": [t / args.steps for t in per_rank_ms],
                               "collective": collective, "clocks": clocks}))
         if world > 1:
             dist.barrier()
-            for pr in (peer, peer_lag1):
+            for pr in [peer, peer_lag1] + peers_more:
                 if pr is not None:
                     pr.close()
             dist.destroy_process_group()
@@ -831,10 +859,15 @@ def main():
                        "global_batch": BATCH * world, "per_gpu_batch": BATCH,
                        "l2": f"inputs rotate over {N_SETS} sets of 89.5 MB (> 126 MB L2) so no step re-reads a warm L2",
                        "cuda_graph": use_graph, "halves": "serial" if args.serial else "forked (independent halves on two streams)",
+                       "steps_in_flight": depth,
+                       "steps_in_flight_note": "consecutive eval batches are independent (SSD_test_step): the timed region keeps this many steps "
+                                               "in flight on as many streams (engine.StepPipeline), ms_per_step = elapsed / steps; `sequential` "
+                                               "is the same run with one step at a time",
                        "parallelism": f"image-sharded x{world}, all-reduce of 3 doubles per step" + (f": {collective}" if world > 1 else "")},
             "parts": {"match_loss_images_per_s": BATCH * world / (ms_loss * 1e-3),
                       "decode_nms_images_per_s": BATCH * world / (ms_pred * 1e-3)},
             "sustained": sustained,
+            "sequential": sequential,
             "separate_conf": separate,
             "key_handoff": handoff,
             "lag1": lag1,
@@ -857,11 +890,11 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
-        for pr in (peer, peer_lag1):
+        for pr in [peer, peer_lag1] + peers_more:
             if pr is not None and pr.timed_out():
                 print(f"[bench] rank {rank}: a peer all-reduce timed out", file=sys.stderr)
         dist.barrier()
-        for pr in (peer, peer_lag1):
+        for pr in [peer, peer_lag1] + peers_more:
             if pr is not None:
                 pr.close()
         dist.destroy_process_group()

@@ -1038,3 +1038,44 @@ def test_key_handoff_between_the_halves(env):
     for b in range(B):
         k = int(ac[b])
         same([labels[b, :k], scores[b, :k], boxes[b, :k]], [al[b, :k], asc[b, :k], ab[b, :k]])
+
+
+def test_two_steps_in_flight_equal_sequential(env):
+    """StepPipeline: two HotPathStep objects on two streams take the batches of an evaluation pass round-robin (the loss
+    kernel's stream of batch i+1 beside the NMS tail of batch i).  Every batch's sums and detections equal those of the
+    same batch run alone."""
+    s, dev, ps = env["ssdhot"], env["dev"], env["ps"]
+    from ssdhot import synth
+    from ssdhot.engine import HotPathStep, StepPipeline
+    B = 24
+    batches = []
+    for k in range(5):
+        cfg = synth.config(3, batch=B, seed_offset=k)
+        batches.append((cfg["loc_all"].to(dev), cfg["conf_infer"].to(dev), s.pack_targets(cfg["targets"], dev)))
+    mk = lambda k=0: HotPathStep(ps, B, 6, 0.5, 3.0, 0.01, 0.45, 200)
+    alone = mk()
+    want = []
+    for loc, conf, gt in batches:
+        alone.run(loc, conf, conf, gt)
+        torch.cuda.synchronize()
+        want.append([t.clone() for t in (alone.sums, alone.n_pos, alone.count, alone.labels, alone.scores, alone.boxes)])
+    pipe = StepPipeline(mk, depth=2)
+    for use_graph in (False, True, True):
+        got, pending = [], []
+        for i, (loc, conf, gt) in enumerate(batches):
+            if len(pending) == 2:                                   # the step object about to be reused: collect its batch first
+                st = pending.pop(0)
+                pipe.wait(st)
+                got.append([t.clone() for t in (st.sums, st.n_pos, st.count, st.labels, st.scores, st.boxes)])
+            pending.append(pipe.submit(loc, conf, conf, gt, use_graph=use_graph))
+        for st in pending:
+            pipe.wait(st)
+            got.append([t.clone() for t in (st.sums, st.n_pos, st.count, st.labels, st.scores, st.boxes)])
+        torch.cuda.synchronize()
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            k = w[2].long()
+            assert torch.equal(g[0], w[0]) and torch.equal(g[1], w[1]) and torch.equal(g[2], w[2])
+            for b in range(B):                                      # (rows beyond count hold what an earlier batch left there)
+                n = int(k[b])
+                assert torch.equal(g[3][b, :n], w[3][b, :n]) and torch.equal(g[4][b, :n], w[4][b, :n]) and torch.equal(g[5][b, :n], w[5][b, :n])
