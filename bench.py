@@ -484,6 +484,37 @@ def main():
     iters = max(8, min(args.steps, 64))
     ms_loss = time_half(True, iters)
     ms_pred = time_half(False, iters)
+
+    def time_half_two_in_flight(train: bool, n: int):
+        """The same half with two launches in flight (two step objects on two streams, alternating input sets): elapsed / launches.
+        Not a launch duration -- the rate at which the kernel retires batches when the 296 CTA slots stay filled (one launch of
+        256 CTAs fills 0.86 of a wave and all its CTAs run their phases in lockstep)."""
+        objs = [step, make_step(None)]
+        strs = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        cur = torch.cuda.current_stream(dev)
+
+        def go(i):
+            s_, o_, q_ = sets[i % N_SETS], objs[i % 2], strs[i % 2]
+            o_.launch_loss(s_["loc"], s_["conf"], s_["gt"], q_.cuda_stream) if train else o_.launch_predict(s_["loc"], s_["conf"], q_.cuda_stream)
+        for q_ in strs:
+            q_.wait_stream(cur)
+        for i in range(6):
+            go(i)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for q_ in strs:
+            q_.wait_stream(cur)
+        for i in range(n):
+            go(i)
+        for q_ in strs:
+            cur.wait_stream(q_)
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / n
+
+    ms_loss2 = time_half_two_in_flight(True, 4 * iters)
+    ms_pred2 = time_half_two_in_flight(False, 4 * iters)
     mean_g = statistics.mean(float(t["boxes"].shape[0]) for c in host_sets for t in c["targets"])
     k_mean = float(step.count.float().mean().item())
     bytes_loss = BATCH * (349296 + 24 * mean_g + 12)            # SURVEY.md 8d, path (i)
@@ -496,6 +527,8 @@ def main():
         "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
         "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": TRAFFIC["decode_nms" if dom_is_pred else "match_loss"],
         "traffic_source": TRAFFIC["source"], "peak_source": peak_src,
+        # the same kernel's rate with two launches in flight, as the timed region of `value` keeps them (see parts_two_in_flight)
+        "frac_two_in_flight": dom_bytes / ((ms_pred2 if dom_is_pred else ms_loss2) * 1e-3) / 1e9 / peak,
         "note": "algorithmic bytes = SURVEY.md 8(d) figure of the whole half (conf_all + loc_all + GT / outputs) over the CUDA-event "
                 "time of that half run alone; reported for the slower half (both under `parts`)",
         "parts": {
@@ -503,6 +536,12 @@ def main():
                            "frac": bytes_loss / (ms_loss * 1e-3) / 1e9 / peak, "images_per_s": BATCH / (ms_loss * 1e-3)},
             "decode_nms": {"ms": ms_pred, "algorithmic_bytes": bytes_pred, "achieved": bytes_pred / (ms_pred * 1e-3) / 1e9,
                            "frac": bytes_pred / (ms_pred * 1e-3) / 1e9 / peak, "images_per_s": BATCH / (ms_pred * 1e-3)},
+        },
+        "parts_two_in_flight": {
+            "note": "elapsed / launches with two launches of the half in flight on two streams (not a launch duration: the rate at which "
+                    "the kernel retires batches once the 296 CTA slots stay filled; one launch of 256 CTAs is 0.86 of a wave)",
+            "match_loss": {"ms_per_launch": ms_loss2, "achieved": bytes_loss / (ms_loss2 * 1e-3) / 1e9, "frac": bytes_loss / (ms_loss2 * 1e-3) / 1e9 / peak},
+            "decode_nms": {"ms_per_launch": ms_pred2, "achieved": bytes_pred / (ms_pred2 * 1e-3) / 1e9, "frac": bytes_pred / (ms_pred2 * 1e-3) / 1e9 / peak},
         },
         # the whole forked step (what `value` times) against the same peak: as the two functions of the reference count their
         # bytes (each reads conf_all + loc_all), and as the step moves them once the loss kernel hands predict its row keys
