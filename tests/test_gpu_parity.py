@@ -1019,6 +1019,21 @@ def test_key_handoff_between_the_halves(env):
             together.run_heads(hs, hs, gt)
             same(outputs(together), want)
             assert picked_up(together) >= B - 8, (thr, cl, picked_up(together))
+    # more images than the GPU holds CTAs at once (several waves of both kernels, the predict CTAs of late images start before
+    # their loss CTAs): every image is still served -- by the hand-off or by its own stream -- with the same results
+    Bw = 700
+    cw = synth.config(3, batch=Bw, seed_offset=3)
+    locw, confw, gtw = cw["loc_all"].to(dev), cw["conf_infer"].to(dev), s.pack_targets(cw["targets"], dev)
+    apart = HotPathStep(ps, Bw, 6, 0.5, 3.0, 0.01, 0.45, 200)
+    apart.share_keys = False
+    apart.run(locw, confw, confw, gtw)
+    want = outputs(apart)
+    together = HotPathStep(ps, Bw, 6, 0.5, 3.0, 0.01, 0.45, 200)
+    for use_graph in (False, True, True):
+        together.count.zero_()
+        together.run(locw, confw, confw, gtw, use_graph=use_graph)
+        same(outputs(together), want)
+        assert int((together.share[:4 * Bw].view(torch.int32) == 3).sum()) >= Bw // 2
     # a loss launch that leaves no keys (generic priors -> match_kernel + loss_image_kernel): predict streams itself
     generic = s.PriorSet.default(dev, generic=True)
     apart = HotPathStep(generic, B, 6, 0.5, 3.0, 0.01, 0.45, 200)
