@@ -419,6 +419,8 @@ def main():
     n_long = max(args.steps, int(250.0 / max(ms_per_step, 1e-3)) + 1)
     ms_long, _ = timed_loop(head, n_long)
     clocks = sampler.result()
+    count_picked = lambda: int((step.share[:4 * BATCH].view(torch.int32) == 3).sum().item()) if step.share_keys else 0
+    picked_in_flight = count_picked()       # (the last step this object ran inside the headline's loop)
     ms_seq, _ = timed_loop(step, args.steps) if depth > 1 else (ms_total, None)
     sequential = {"steps_in_flight": 1, "ms_per_step": ms_seq / args.steps, "value": BATCH * world * args.steps / (ms_seq / 1e3),
                   "note": "the same steps strictly one after the other (one CUDA graph replay at a time on one stream): what rounds 1 and "
@@ -426,12 +428,12 @@ def main():
     sustained = {"steps": n_long, "ms_per_step": ms_long / n_long, "value": BATCH * world * n_long / (ms_long / 1e3),
                  "note": "the same loop run long enough (>= 0.25 s) for the clock sampler to cover it; `clocks` spans both regions"}
     # key hand-off (ssdhot.h: ssdhot_share_bytes): images whose predict CTA took the row keys the loss kernel's stream left
-    picked = int((step.share[:4 * BATCH].view(torch.int32) == 3).sum().item()) if step.share_keys else 0
+    picked = count_picked()
     if args.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "n_gpus": world, "value": value, "ms_per_step": ms_per_step, "sustained": sustained,
                               "steps_in_flight": depth, "sequential": sequential,
-                              "keys_handed_off": picked,
+                              "keys_handed_off": picked, "keys_handed_off_in_flight": picked_in_flight,
                               "per_rank_ms_per_step": [t / args.steps for t in per_rank_ms],
                               "collective": collective, "clocks": clocks}))
         if world > 1:
@@ -445,7 +447,8 @@ def main():
     step.share_keys = False
     ms_ns, _ = timed_loop(step, args.steps)
     step.share_keys = not args.no_share
-    handoff = {"on": step.share_keys, "images_handed_off_last_step": picked, "batch": BATCH,
+    handoff = {"on": step.share_keys, "images_handed_off_last_step": picked, "images_handed_off_last_step_in_flight": picked_in_flight,
+               "batch": BATCH,
                "without": {"ms_per_step": ms_ns / args.steps, "value": BATCH * world * args.steps / (ms_ns / 1e3)},
                "note": "one conf_all feeds both halves (SSD_test_step): the loss kernel's logit stream leaves predict's 16-bit row keys "
                        "in HBM/L2 (17.5 KB per image) and predict_image_kernel picks them up instead of reading conf_all again; "
