@@ -1456,6 +1456,9 @@ __global__ void __launch_bounds__(IT, 2) predict_image_kernel(const PredictParam
                 const int p = hot[tid];
                 float x[6], e[6];
                 conf_rd.row(p, x);
+                // the decode of this row's candidates comes three barriers later and finds the box offsets cold in HBM: ask for them now
+                // (step 60.4 -> 59.2 us; the same for the hot rows' logits, one barrier ahead of the exact pass: no gain)
+                if (SRC != SRC_LEVEL_PLANES) asm volatile("prefetch.global.L2 [%0];" ::"l"(loc_rd.row_ptr(p)));
                 const float sum = row_exps6(x, e);
                 bool low = false;
 #pragma unroll
