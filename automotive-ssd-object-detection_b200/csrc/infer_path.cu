@@ -1,7 +1,14 @@
 // infer_path.cu -- decode, score threshold, ranking and greedy DIoU/CIoU NMS
 // (SURVEY.md section 8a rows a6-a8).
 //
-// predict = two kernels:
+// SSD300 with C == 6 (the reference's case) is ONE kernel, predict_image_kernel (second half of this file): the stream
+// keeps one 16-bit key per row in shared memory -- or takes the keys the loss kernel's stream of the same logits left in
+// the share buffer (ssdhot.h: ssdhot_share_bytes; train_path.cu) --, a histogram cut picks the few hundred "hot" rows, one
+// thread per hot row evaluates it exactly, the pulled keys are ranked by counting (rank_keys_by_counting) and the shared
+// back end (nms_round_backend) decodes, tests the pairs, resolves and emits.  Images that do not fit that mould are redone
+// by the same CTA on the generic path below.
+//
+// The generic predict (other class counts, candidate ids >= 65536, ssdhot_predict_stages) = two kernels:
 //  * score_kernel -- the HBM-bound stage.  The class logits are streamed once (two CTAs x 8 warps per image,
 //    16-byte loads, software-pipelined); every (prior, foreground class) pair is tested against the score
 //    threshold and the survivors are appended to the warp's own segment of the image's candidate list as

@@ -2,6 +2,9 @@
 //
 // The SSD300 fast path is ONE kernel, train_image_kernel (second half of this file): box-centric matching over
 // candidate rectangles beside the logit stream, approximate-then-exact hard-negative mining, one CTA per image.
+// Given a share buffer (ssdhot.h: ssdhot_share_bytes) its logit stream also leaves the 16-bit row keys that
+// predict_image_kernel of the same eval step needs, and raises one flag per image (template flag SHARE: 14 + 10 warps
+// instead of 18 + 6).
 // It is templated on the source of the head outputs (heads.cuh: packed tensors, channels_last rows or NCHW planes of the six
 // per-level tensors -- ssdhot_multibox_loss_heads_fwd; loss_bwd_heads_kernel writes the gradients in the same layouts).
 // The layout-agnostic path (any priors / class count / > 64 boxes per image, and encode_ssd's "every prior"
