@@ -919,10 +919,14 @@ __device__ __forceinline__ void match_phase(const TrainParams& prm, FusedStatic&
         if (mtid == 0) { fs.n_work = 0; fs.n_seg = 0; fs.n_chunk = 0; }
         const int round_begin = min(fs.n_pair, PAIR_CAP);       // (stable: the previous round ended with a barrier)
         role_sync<MT>();
-        // 1a. half a warp per box: constants, seed bound (two of the 30 seed priors per lane), and the
-        //     (level, shape) combinations whose sizes can reach IoU >= lim at all (1-D and area ratios; a
+        // 1a. a warp per box (one of the 30 seed priors per lane) while the round's boxes fit the matching warps, else half a
+        //     warp per box (two seed priors per lane: the longest dependent chain of the phase, twice): constants, seed
+        //     bound, and the (level, shape) combinations whose sizes can reach IoU >= lim at all (1-D and area ratios; a
         //     clamped extent is at least half the nominal one)
-        for (int gl = 2 * mwarp + (lane >> 4); gl < ((gn + 1) & ~1); gl += 2 * (MT / 32)) {     // warp-uniform trip count
+        const bool wide = gn <= MT / 32;
+        const int sub = wide ? lane : (lane & 15), nh = wide ? 1 : 2;
+        for (int gl = wide ? mwarp : 2 * mwarp + (lane >> 4); gl < (wide ? gn : ((gn + 1) & ~1));
+             gl += wide ? MT / 32 : 2 * (MT / 32)) {                                              // warp-uniform trip count
             const bool live = gl < gn;
             const int g = g0 + (live ? gl : gn - 1);
             const float4 px = fs.gt_px[g];
@@ -932,12 +936,13 @@ __device__ __forceinline__ void match_phase(const TrainParams& prm, FusedStatic&
             if (c.at != c.at) kind = 2;
             else if (!(gw > 0.0f && gh > 0.0f) || !(fabsf(c.x1) < 1e30f && fabsf(c.y1) < 1e30f && fabsf(c.x2) < 1e30f && fabsf(c.y2) < 1e30f)) kind = 1;
             float lim = 1e-30f;
-            unsigned keep = 0u;                              // bit h: combination (lane & 15) + 16 h stays
+            unsigned keep = 0u;                              // bit h: combination sub + 16 h stays
             unsigned best = 0u;
             if (kind == 0) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int combo = (lane & 15) + 16 * h;  // 30, 31 repeat 0, 4 as seeds
+                    if (h >= nh) break;
+                    const int combo = sub + 16 * h;          // 30, 31 repeat 0, 4 as seeds
                     const int side = fs.cb_side[combo];
                     int ix = (int)floorf(c.xc * (float)side), iy = (int)floorf(c.yc * (float)side);
                     ix = min(max(ix, 0), side - 1);
@@ -945,7 +950,8 @@ __device__ __forceinline__ void match_phase(const TrainParams& prm, FusedStatic&
                     best = max(best, ord_encode(pair_ciou(grid_prior(fs, combo, ix, iy, true), c)));
                 }
             }
-            // (the two halves of a warp hold different boxes: the shuffles below must run in every lane)
+            // (the two halves of a warp may hold different boxes: the shuffles below must run in every lane)
+            if (wide) best = max(best, __shfl_xor_sync(FULL, best, 16));
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
             if (kind == 0) {
@@ -954,7 +960,8 @@ __device__ __forceinline__ void match_phase(const TrainParams& prm, FusedStatic&
                 const float l2 = 0.99f * lim;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int combo = (lane & 15) + 16 * h;
+                    if (h >= nh) break;
+                    const int combo = sub + 16 * h;
                     const float w = fs.cb_w[combo], hh = fs.cb_h[combo];
                     if (combo < 30 && !(gw < l2 * 0.5f * w || w < l2 * gw || gh < l2 * 0.5f * hh || hh < l2 * gh ||
                                         c.area < l2 * 0.25f * w * hh || w * hh < l2 * c.area)) keep |= 1u << h;
@@ -966,9 +973,9 @@ __device__ __forceinline__ void match_phase(const TrainParams& prm, FusedStatic&
             if (lane == 0 && (b0 | b1)) dst = atomicAdd(&fs.n_work, __popc(b0) + __popc(b1));
             dst = __shfl_sync(FULL, dst, 0);
             const unsigned ltm = (1u << lane) - 1u;
-            if (keep & 1u) v.work_list[dst + __popc(b0 & ltm)] = (uint16_t)((gl << 5) | (lane & 15));
-            if (keep & 2u) v.work_list[dst + __popc(b0) + __popc(b1 & ltm)] = (uint16_t)((gl << 5) | ((lane & 15) + 16));
-            if (live && (lane & 15) == 0) {
+            if (keep & 1u) v.work_list[dst + __popc(b0 & ltm)] = (uint16_t)((gl << 5) | sub);
+            if (keep & 2u) v.work_list[dst + __popc(b0) + __popc(b1 & ltm)] = (uint16_t)((gl << 5) | (sub + 16));
+            if (live && sub == 0) {
                 fs.gt_a[g] = make_float4(c.x1, c.y1, c.x2, c.y2);
                 fs.gt_b[g] = make_float4(c.area, c.xc, c.yc, c.at);
                 fs.lim[g] = lim;
