@@ -853,12 +853,20 @@ __device__ __forceinline__ int nms_round_backend(const PredictParams& prm, const
     int my_g = -1;
     BoxC my_box = {};
     unsigned my_cells = 0u;
+    float lv[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 my_prior = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid < K) {
+        // the box offsets and the prior are requested here and used behind the class ordering (three barriers on): their
+        // latency passes under it
         const unsigned id = 0xffffffffu - (unsigned)(buf.ckey[tid] & 0xffffffffull);
         const unsigned p = id / (unsigned)n_fg;
-        float lv[4];
         loc_rd.row((int)p, lv);
-        const float4 box = decode_box(make_float4(lv[0], lv[1], lv[2], lv[3]), ldg4(prm.pri + 4ll * p), prm.vc, prm.vs);
+        my_prior = ldg4(prm.pri + 4ll * p);
+        my_g = AGN ? 0 : (int)(id % (unsigned)n_fg);
+        buf.cgroup[tid] = (unsigned char)my_g;
+    }
+    auto decode_mine = [&]() {
+        const float4 box = decode_box(make_float4(lv[0], lv[1], lv[2], lv[3]), my_prior, prm.vc, prm.vs);
         const float4 px = to_pixel_xyxy(box, prm.img_w, prm.img_h);
         my_box = box_consts(px.x, px.y, px.z, px.w, want_atan);
         {   // which quarter-columns / quarter-rows of the image the (clamped) box reaches: boxes that share no cell
@@ -873,9 +881,7 @@ __device__ __forceinline__ int nms_round_backend(const PredictParams& prm, const
             if (!(fmul(fsub(px.z, px.x), fsub(px.w, px.y)) > 0.0f)) m16 = 0xffffu;
             my_cells = m16;
         }
-        my_g = AGN ? 0 : (int)(id % (unsigned)n_fg);
-        buf.cgroup[tid] = (unsigned char)my_g;
-    }
+    };
     for (int i = tid; i < 16 * n_groups; i += IT) buf.wcnt[i] = 0;
     for (int i = tid; i < n_groups * MW; i += IT) buf.nzW[i] = 0ull;
     {
@@ -903,6 +909,7 @@ __device__ __forceinline__ int nms_round_backend(const PredictParams& prm, const
         for (int w = 0; w < warp; ++w) my_m += buf.wcnt[w * n_groups + my_g];
         my_m += local_rank;
         buf.cpos[tid] = (unsigned short)my_m;
+        decode_mine();
     }
     __syncthreads();
     if (my_g >= 0) {                                                // boxes and cell masks in class order
